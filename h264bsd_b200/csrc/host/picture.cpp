@@ -1,0 +1,676 @@
+// picture.cpp -- see picture.hpp
+#include "picture.hpp"
+#include "cavlc.hpp"
+#include <algorithm>
+#include <cstring>
+
+namespace b200 {
+
+namespace {
+// 4x4 luma block order inside a macroblock (clause 6.4.3; h264bsdBlockX/Y intra_prediction.c:86-89)
+const uint8_t kBlkX[16] = {0, 1, 0, 1, 2, 3, 2, 3, 0, 1, 0, 1, 2, 3, 2, 3};
+const uint8_t kBlkY[16] = {0, 0, 1, 1, 0, 0, 1, 1, 2, 2, 3, 3, 2, 2, 3, 3};
+const uint8_t kZ[4][4] = {{0, 1, 4, 5}, {2, 3, 6, 7}, {8, 9, 12, 13}, {10, 11, 14, 15}};  // [y][x]
+
+// Table 9-4, coded_block_pattern for chroma_format_idc 1/2: codeNum -> {Intra, Inter}
+const uint8_t kCbp[48][2] = {
+    {47, 0},  {31, 16}, {15, 1},  {0, 2},   {23, 4},  {27, 8},  {29, 32}, {30, 3},  {7, 5},   {11, 10},
+    {13, 12}, {14, 15}, {39, 47}, {43, 7},  {45, 11}, {46, 13}, {16, 14}, {3, 6},   {5, 9},   {10, 31},
+    {12, 35}, {19, 37}, {21, 42}, {26, 44}, {28, 33}, {35, 34}, {37, 36}, {42, 40}, {44, 39}, {1, 43},
+    {2, 45},  {4, 46},  {8, 17},  {17, 18}, {18, 20}, {20, 24}, {24, 19}, {6, 21},  {9, 26},  {22, 28},
+    {25, 23}, {32, 27}, {33, 29}, {34, 30}, {36, 22}, {40, 25}, {38, 38}, {41, 41}};
+
+// Table 8-15: QPc as a function of qPI (h264bsdQpC, h264bsd_util.c:53-55)
+const uint8_t kQpC[52] = {0,  1,  2,  3,  4,  5,  6,  7,  8,  9,  10, 11, 12, 13, 14, 15, 16, 17,
+                          18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 29, 30, 31, 32, 32, 33,
+                          34, 34, 35, 35, 36, 36, 37, 37, 37, 38, 38, 38, 39, 39, 39, 39};
+
+inline bool isInterType(uint32_t t) { return t <= B200_MB_P_8x8REF0; }
+inline int numMbPart(uint32_t t) { return (t == B200_MB_P_16x16 || t == B200_MB_P_SKIP) ? 1 : (t == B200_MB_P_16x8 || t == B200_MB_P_8x16) ? 2 : 4; }
+inline int numSubMbPart(uint32_t s) { return s == 0 ? 1 : s == 3 ? 4 : 2; }
+}  // namespace
+
+extern "C" uint32_t b200_cbp_probe(uint32_t codeNum, int intra) { return codeNum < 48 ? kCbp[codeNum][intra ? 0 : 1] : 0xFFFFFFFFu; }
+
+struct PictureState::MbSyntax {
+    uint32_t mbType;
+    uint32_t cbp;
+    int32_t qpDelta;
+    uint8_t prevFlag[16], remMode[16];
+    uint32_t chromaMode;
+    uint32_t refIdx[4];
+    int16_t mvd[4][2];
+    uint32_t subType[4];
+    int16_t subMvd[4][4][2];
+    uint8_t totalCoeff[27];
+    alignas(16) int16_t level[26][16];  // [0..23] blocks, [24] luma DC, [25] chroma DC (Cb 0..3, Cr 4..7)
+    uint8_t pcm[384];
+    void clear() {
+        // levels are cleared selectively after use; everything else here
+        cbp = 0; qpDelta = 0; chromaMode = 0;
+        std::memset(prevFlag, 0, sizeof prevFlag); std::memset(remMode, 0, sizeof remMode);
+        std::memset(refIdx, 0, sizeof refIdx); std::memset(mvd, 0, sizeof mvd);
+        std::memset(subType, 0, sizeof subType); std::memset(subMvd, 0, sizeof subMvd);
+        std::memset(totalCoeff, 0, sizeof totalCoeff);
+    }
+};
+
+void PictureState::resize(uint32_t w, uint32_t h) {
+    widthMbs = w; heightMbs = h; picSizeInMbs = w * h;
+    st.assign(picSizeInMbs, b200_mb_rec());
+    for (auto &r : st) std::memset(&r, 0, sizeof r);
+    aux.assign(picSizeInMbs, MbAux());
+    recs.assign(picSizeInMbs, b200_mb_rec());
+    for (auto &r : recs) std::memset(&r, 0, sizeof r);
+    sliceGroupMap.assign(picSizeInMbs, 0);
+    coefs.clear();
+    sliceIdCounter = numDecodedMbs = lastMbAddr = 0;
+}
+
+void PictureState::beginPicture() {
+    numDecodedMbs = 0;
+    sliceIdCounter = 0;
+    for (auto &a : aux) { a.sliceId = 0; a.decoded = 0; }
+    coefs.clear();
+}
+
+bool PictureState::allDecoded(bool redundant) const {
+    if (!redundant) return numDecodedMbs == picSizeInMbs;
+    uint32_t n = 0;
+    for (const auto &a : aux) n += a.decoded ? 1 : 0;
+    return n == picSizeInMbs;
+}
+
+uint32_t PictureState::nextMbAddress(uint32_t cur) const {
+    uint32_t g = sliceGroupMap[cur];
+    uint32_t i = cur + 1;
+    while (i < picSizeInMbs && sliceGroupMap[i] != g) i++;
+    return i == picSizeInMbs ? 0 : i;
+}
+
+// DetermineNc (h264bsd_macroblock_layer.c:810-870): average of left/above totalCoeff where available
+int PictureState::nC(uint32_t mbAddr, uint32_t blk, const uint8_t *cur) const {
+    int aMb, bMb;           // 0 current, 1 neighbour MB
+    uint32_t aIdx, bIdx;
+    if (blk < 16) {
+        int x = kBlkX[blk], y = kBlkY[blk];
+        if (x > 0) { aMb = 0; aIdx = kZ[y][x - 1]; } else { aMb = 1; aIdx = kZ[y][3]; }
+        if (y > 0) { bMb = 0; bIdx = kZ[y - 1][x]; } else { bMb = 1; bIdx = kZ[3][x]; }
+    } else {
+        uint32_t i = blk & 3;
+        if (i & 1) { aMb = 0; aIdx = blk - 1; } else { aMb = 1; aIdx = blk + 1; }
+        if (i & 2) { bMb = 0; bIdx = blk - 2; } else { bMb = 1; bIdx = blk + 2; }
+    }
+    int n;
+    if (!aMb && !bMb) {
+        n = (cur[aIdx] + cur[bIdx] + 1) >> 1;
+    } else if (!aMb) {
+        n = cur[aIdx];
+        int b = mbB(mbAddr);
+        if (avail(mbAddr, b)) n = (n + aux[b].totalCoeff[bIdx] + 1) >> 1;
+    } else if (!bMb) {
+        n = cur[bIdx];
+        int a = mbA(mbAddr);
+        if (avail(mbAddr, a)) n = (n + aux[a].totalCoeff[aIdx] + 1) >> 1;
+    } else {
+        n = 0;
+        bool haveA = false;
+        int a = mbA(mbAddr), b = mbB(mbAddr);
+        if (avail(mbAddr, a)) { n = aux[a].totalCoeff[aIdx]; haveA = true; }
+        if (avail(mbAddr, b)) n = haveA ? (n + aux[b].totalCoeff[bIdx] + 1) >> 1 : aux[b].totalCoeff[bIdx];
+    }
+    return n;
+}
+
+// h264bsdDecodeMacroblockLayer (h264bsd_macroblock_layer.c:134-243)
+bool PictureState::parseMacroblockLayer(BitReader &br, MbSyntax &mb, uint32_t mbAddr, bool iSlice, uint32_t numRefIdxActive) {
+    uint32_t v;
+    int32_t s;
+    mb.clear();
+    bool ok = br.ue(v);
+    uint32_t off = iSlice ? 6 : 1;
+    if (!ok || v + off > 31) return false;
+    mb.mbType = v + off;
+    if (mb.mbType == B200_MB_I_PCM) {
+        while (!br.byteAligned()) {
+            if (!br.get1(v) || v) return false;  // pcm_alignment_zero_bit
+        }
+        for (int i = 0; i < 384; i++) {
+            if (!br.get(8, v)) return false;
+            mb.pcm[i] = (uint8_t)v;
+        }
+        return true;
+    }
+    bool inter = isInterType(mb.mbType);
+    if (inter && numMbPart(mb.mbType) == 4) {
+        // sub_mb_pred()
+        for (int i = 0; i < 4; i++) {
+            if (!br.ue(v) || v > 3) return false;
+            mb.subType[i] = v;
+        }
+        if (numRefIdxActive > 1 && mb.mbType != B200_MB_P_8x8REF0) {
+            for (int i = 0; i < 4; i++) {
+                if (!br.te(v, numRefIdxActive > 2) || v >= numRefIdxActive) return false;
+                mb.refIdx[i] = v;
+            }
+        }
+        for (int i = 0; i < 4; i++)
+            for (int j = 0; j < numSubMbPart(mb.subType[i]); j++) {
+                if (!br.se(s)) return false;
+                mb.subMvd[i][j][0] = (int16_t)s;
+                if (!br.se(s)) return false;
+                mb.subMvd[i][j][1] = (int16_t)s;
+            }
+    } else if (inter) {
+        int np = numMbPart(mb.mbType);
+        if (numRefIdxActive > 1) {
+            for (int j = 0; j < np; j++) {
+                if (!br.te(v, numRefIdxActive > 2) || v >= numRefIdxActive) return false;
+                mb.refIdx[j] = v;
+            }
+        }
+        for (int j = 0; j < np; j++) {
+            if (!br.se(s)) return false;
+            mb.mvd[j][0] = (int16_t)s;
+            if (!br.se(s)) return false;
+            mb.mvd[j][1] = (int16_t)s;
+        }
+    } else {
+        if (mb.mbType == B200_MB_I_4x4) {
+            for (int i = 0; i < 16; i++) {
+                if (!br.get1(v)) return false;
+                mb.prevFlag[i] = (uint8_t)v;
+                if (!v) {
+                    if (!br.get(3, v)) return false;
+                    mb.remMode[i] = (uint8_t)v;
+                }
+            }
+        }
+        if (!br.ue(v) || v > 3) return false;
+        mb.chromaMode = v;
+    }
+    bool i16 = !inter && mb.mbType != B200_MB_I_4x4;
+    if (!i16) {
+        if (!br.ue(v) || v > 47) return false;
+        mb.cbp = kCbp[v][mb.mbType == B200_MB_I_4x4 ? 0 : 1];
+    } else {
+        uint32_t t = mb.mbType - B200_MB_I_16x16_FIRST;
+        uint32_t c = t >> 2;
+        if (c > 2) c -= 3;
+        mb.cbp = (t >= 12 ? 15u : 0u) + (c << 4);
+    }
+    if (mb.cbp || i16) {
+        if (!br.se(s) || s < -26 || s > 25) return false;
+        mb.qpDelta = s;
+        if (!parseResidual(br, mb, mbAddr)) return false;
+    }
+    return true;
+}
+
+// DecodeResidual (h264bsd_macroblock_layer.c:700-796)
+bool PictureState::parseResidual(BitReader &br, MbSyntax &mb, uint32_t mbAddr) {
+    bool i16 = !isInterType(mb.mbType) && mb.mbType != B200_MB_I_4x4;
+    uint32_t cbp = mb.cbp;
+    if (i16) {
+        CavlcResult r = cavlcResidualBlock(br, mb.level[24], nC(mbAddr, 0, mb.totalCoeff), 16);
+        if (r.totalCoeff < 0) return false;
+        mb.totalCoeff[24] = (uint8_t)r.totalCoeff;
+    }
+    uint32_t blk = 0;
+    for (int i8 = 0; i8 < 4; i8++) {
+        if (cbp & (1u << i8)) {
+            for (int j = 0; j < 4; j++, blk++) {
+                int n = nC(mbAddr, blk, mb.totalCoeff);
+                CavlcResult r = i16 ? cavlcResidualBlock(br, mb.level[blk] + 1, n, 15)
+                                    : cavlcResidualBlock(br, mb.level[blk], n, 16);
+                if (r.totalCoeff < 0) return false;
+                mb.totalCoeff[blk] = (uint8_t)r.totalCoeff;
+            }
+        } else {
+            blk += 4;
+        }
+    }
+    uint32_t chroma = cbp >> 4;
+    if (chroma & 3) {
+        CavlcResult r = cavlcResidualBlock(br, mb.level[25], -1, 4);
+        if (r.totalCoeff < 0) return false;
+        mb.totalCoeff[25] = (uint8_t)r.totalCoeff;
+        r = cavlcResidualBlock(br, mb.level[25] + 4, -1, 4);
+        if (r.totalCoeff < 0) return false;
+        mb.totalCoeff[26] = (uint8_t)r.totalCoeff;
+    }
+    if (chroma & 2) {
+        for (blk = 16; blk < 24; blk++) {
+            CavlcResult r = cavlcResidualBlock(br, mb.level[blk] + 1, nC(mbAddr, blk, mb.totalCoeff), 15);
+            if (r.totalCoeff < 0) return false;
+            mb.totalCoeff[blk] = (uint8_t)r.totalCoeff;
+        }
+    }
+    return true;
+}
+
+// GetInterNeighbour (h264bsd_inter_prediction.c:963-988) addressed by 4x4 coordinates relative to
+// the current macroblock; curZ = block index of the partition being predicted (blocks of the
+// current macroblock that come later in decoding order are "not available", clause 6.4.11.7)
+PictureState::NbMv PictureState::interNeighbour(uint32_t cur, int x, int y, int curZ) const {
+    NbMv n{false, 0xFFFFFFFFu, {0, 0}};
+    int nb;
+    if (y >= 0 && x > 3) return n;  // right neighbour: never available
+    if (x >= 0 && x <= 3 && y >= 0) {
+        int z = kZ[y][x];
+        if (z >= curZ) return n;
+        nb = (int)cur;
+    } else if (y < 0) {
+        nb = x < 0 ? mbD(cur) : x > 3 ? mbC(cur) : mbB(cur);
+    } else {
+        nb = mbA(cur);
+    }
+    if (nb != (int)cur && !avail(cur, nb)) return n;
+    n.avail = true;
+    const b200_mb_rec &r = st[nb];
+    if (isInterType(r.mbType)) {
+        int z = kZ[y & 3][x & 3];
+        n.refIdx = r.refIdx[z >> 2];
+        n.mv[0] = r.u.mv[z][0];
+        n.mv[1] = r.u.mv[z][1];
+    }
+    return n;
+}
+
+static int median3(int a, int b, int c) {
+    int mx = std::max(a, std::max(b, c)), mn = std::min(a, std::min(b, c));
+    return a + b + c - mx - mn;
+}
+
+// clause 8.4.1.3 (MvPrediction*, GetPredictionMv in h264bsd_inter_prediction.c:494-1026).
+// dirHint: 0 median, 1 prefer B (16x8 upper), 2 prefer A (16x8 lower, 8x16 left), 3 prefer C (8x16 right)
+bool PictureState::predictMv(uint32_t cur, int x, int y, int w, int h, uint32_t refIdx, int dirHint, int16_t out[2]) const {
+    (void)h;
+    int curZ = kZ[y][x];
+    NbMv a = interNeighbour(cur, x - 1, y, curZ);
+    NbMv b = interNeighbour(cur, x, y - 1, curZ);
+    NbMv c = interNeighbour(cur, x + w, y - 1, curZ);
+    if (!c.avail) c = interNeighbour(cur, x - 1, y - 1, curZ);
+    if (dirHint == 1 && b.refIdx == refIdx) { out[0] = b.mv[0]; out[1] = b.mv[1]; return true; }
+    if (dirHint == 2 && a.refIdx == refIdx) { out[0] = a.mv[0]; out[1] = a.mv[1]; return true; }
+    if (dirHint == 3 && c.refIdx == refIdx) { out[0] = c.mv[0]; out[1] = c.mv[1]; return true; }
+    if (b.avail || c.avail || !a.avail) {
+        int isA = a.refIdx == refIdx, isB = b.refIdx == refIdx, isC = c.refIdx == refIdx;
+        if (isA + isB + isC != 1) {
+            out[0] = (int16_t)median3(a.mv[0], b.mv[0], c.mv[0]);
+            out[1] = (int16_t)median3(a.mv[1], b.mv[1], c.mv[1]);
+        } else if (isA) { out[0] = a.mv[0]; out[1] = a.mv[1]; }
+        else if (isB) { out[0] = b.mv[0]; out[1] = b.mv[1]; }
+        else { out[0] = c.mv[0]; out[1] = c.mv[1]; }
+    } else {
+        out[0] = a.mv[0]; out[1] = a.mv[1];
+    }
+    return true;
+}
+
+static inline bool mvInRange(int16_t hor, int16_t ver) {
+    return (uint32_t)((int32_t)hor + 8192) < 16384u && (uint32_t)((int32_t)ver + 2048) < 4096u;
+}
+
+// motion vectors + reference slots of an inter macroblock (h264bsdInterPrediction's syntax half)
+bool PictureState::deriveInter(MbSyntax &mb, uint32_t mbAddr, const Dpb &dpb) {
+    b200_mb_rec &r = st[mbAddr];
+    auto setMv = [&](int x0, int y0, int w, int h, int16_t hor, int16_t ver) {
+        for (int yy = y0; yy < y0 + h; yy++)
+            for (int xx = x0; xx < x0 + w; xx++) { r.u.mv[kZ[yy][xx]][0] = hor; r.u.mv[kZ[yy][xx]][1] = ver; }
+    };
+    r.subMbTypes = 0;
+    switch (mb.mbType) {
+        case B200_MB_P_SKIP:
+        case B200_MB_P_16x16: {
+            uint32_t refIdx = mb.refIdx[0];
+            int16_t mv[2] = {0, 0};
+            bool zero = false;
+            if (mb.mbType == B200_MB_P_SKIP) {
+                NbMv a = interNeighbour(mbAddr, -1, 0, 0), b = interNeighbour(mbAddr, 0, -1, 0);
+                zero = !a.avail || !b.avail || (a.refIdx == 0 && a.mv[0] == 0 && a.mv[1] == 0) ||
+                       (b.refIdx == 0 && b.mv[0] == 0 && b.mv[1] == 0);
+            }
+            if (!zero) {
+                int16_t p[2];
+                predictMv(mbAddr, 0, 0, 4, 4, refIdx, 0, p);
+                mv[0] = (int16_t)(mb.mvd[0][0] + p[0]);
+                mv[1] = (int16_t)(mb.mvd[0][1] + p[1]);
+                if (!mvInRange(mv[0], mv[1])) return false;
+            }
+            int slot = dpb.refSlot(refIdx);
+            if (slot < 0) return false;
+            setMv(0, 0, 4, 4, mv[0], mv[1]);
+            for (int q = 0; q < 4; q++) { r.refIdx[q] = (uint8_t)refIdx; r.refSlot[q] = (uint8_t)slot; }
+            break;
+        }
+        case B200_MB_P_16x8: {
+            for (int p = 0; p < 2; p++) {
+                uint32_t refIdx = mb.refIdx[p];
+                int16_t pr[2];
+                predictMv(mbAddr, 0, 2 * p, 4, 2, refIdx, p == 0 ? 1 : 2, pr);
+                int16_t hor = (int16_t)(mb.mvd[p][0] + pr[0]), ver = (int16_t)(mb.mvd[p][1] + pr[1]);
+                if (!mvInRange(hor, ver)) return false;
+                int slot = dpb.refSlot(refIdx);
+                if (slot < 0) return false;
+                setMv(0, 2 * p, 4, 2, hor, ver);
+                r.refIdx[2 * p] = r.refIdx[2 * p + 1] = (uint8_t)refIdx;
+                r.refSlot[2 * p] = r.refSlot[2 * p + 1] = (uint8_t)slot;
+            }
+            break;
+        }
+        case B200_MB_P_8x16: {
+            for (int p = 0; p < 2; p++) {
+                uint32_t refIdx = mb.refIdx[p];
+                int16_t pr[2];
+                predictMv(mbAddr, 2 * p, 0, 2, 4, refIdx, p == 0 ? 2 : 3, pr);
+                int16_t hor = (int16_t)(mb.mvd[p][0] + pr[0]), ver = (int16_t)(mb.mvd[p][1] + pr[1]);
+                if (!mvInRange(hor, ver)) return false;
+                int slot = dpb.refSlot(refIdx);
+                if (slot < 0) return false;
+                setMv(2 * p, 0, 2, 4, hor, ver);
+                r.refIdx[p] = r.refIdx[p + 2] = (uint8_t)refIdx;
+                r.refSlot[p] = r.refSlot[p + 2] = (uint8_t)slot;
+            }
+            break;
+        }
+        default: {  // P_8x8 / P_8x8ref0
+            for (int q = 0; q < 4; q++) {
+                uint32_t refIdx = mb.refIdx[q];
+                int slot = dpb.refSlot(refIdx);
+                r.refIdx[q] = (uint8_t)refIdx;
+                if (slot < 0) return false;
+                r.refSlot[q] = (uint8_t)slot;
+                r.subMbTypes |= (uint8_t)(mb.subType[q] << (2 * q));
+                int qx = (q & 1) * 2, qy = (q >> 1) * 2;
+                int sw = (mb.subType[q] == 0 || mb.subType[q] == 1) ? 2 : 1;
+                int shh = (mb.subType[q] == 0 || mb.subType[q] == 2) ? 2 : 1;
+                int n = numSubMbPart(mb.subType[q]);
+                for (int j = 0; j < n; j++) {
+                    int sx = qx, sy = qy;
+                    if (mb.subType[q] == 1) sy += j;            // 8x4: stacked
+                    else if (mb.subType[q] == 2) sx += j;       // 4x8: side by side
+                    else if (mb.subType[q] == 3) { sx += j & 1; sy += j >> 1; }
+                    int16_t pr[2];
+                    predictMv(mbAddr, sx, sy, sw, shh, refIdx, 0, pr);
+                    int16_t hor = (int16_t)(mb.subMvd[q][j][0] + pr[0]), ver = (int16_t)(mb.subMvd[q][j][1] + pr[1]);
+                    if (!mvInRange(hor, ver)) return false;
+                    setMv(sx, sy, sw, shh, hor, ver);
+                }
+            }
+            break;
+        }
+    }
+    return true;
+}
+
+// Intra availability, Intra4x4 mode derivation and the "mode needs an unavailable neighbour"
+// checks of h264bsdIntra16x16Prediction / Intra4x4Prediction / IntraChromaPrediction
+bool PictureState::deriveIntra(MbSyntax &mb, uint32_t mbAddr, bool constrainedIntra) {
+    b200_mb_rec &r = st[mbAddr];
+    auto availIntra = [&](int nb) {
+        if (!avail(mbAddr, nb)) return false;
+        if (constrainedIntra && isInterType(st[nb].mbType)) return false;
+        return true;
+    };
+    int a = mbA(mbAddr), b = mbB(mbAddr), c = mbC(mbAddr), d = mbD(mbAddr);
+    bool avA = availIntra(a), avB = availIntra(b), avC = availIntra(c), avD = availIntra(d);
+    r.flags = (uint8_t)((avA ? B200_MBF_AVAIL_A : 0) | (avB ? B200_MBF_AVAIL_B : 0) |
+                        (avC ? B200_MBF_AVAIL_C : 0) | (avD ? B200_MBF_AVAIL_D : 0));
+    r.intraChromaMode = (uint8_t)mb.chromaMode;
+    std::memset(&r.u, 0, sizeof r.u);
+    if (mb.mbType == B200_MB_I_4x4) {
+        for (int blk = 0; blk < 16; blk++) {
+            int x = kBlkX[blk], y = kBlkY[blk];
+            // neighbouring 4x4 blocks A (left) and B (above): MB + block index
+            bool bA, bB, bD;
+            int modeA = 2, modeB = 2;
+            if (x > 0) { bA = true; modeA = r.u.intra.i4x4Mode[kZ[y][x - 1]]; }
+            else { bA = avA; if (bA && st[a].mbType == B200_MB_I_4x4) { modeA = st[a].u.intra.i4x4Mode[kZ[y][3]]; } }
+            if (y > 0) { bB = true; modeB = r.u.intra.i4x4Mode[kZ[y - 1][x]]; }
+            else { bB = avB; if (bB && st[b].mbType == B200_MB_I_4x4) { modeB = st[b].u.intra.i4x4Mode[kZ[3][x]]; } }
+            int mode;
+            if (!(bA && bB)) mode = 2;
+            else mode = std::min(modeA, modeB);
+            if (!mb.prevFlag[blk]) mode = mb.remMode[blk] < mode ? mb.remMode[blk] : mb.remMode[blk] + 1;
+            r.u.intra.i4x4Mode[blk] = (uint8_t)mode;
+            // D (above-left) availability, N_D_4x4B (neighbour.c:92-98); C only matters for pels
+            if (x == 0 && y == 0) bD = avD;
+            else if (x == 0) bD = avA;
+            else if (y == 0) bD = avB;
+            else bD = true;
+            switch (mode) {
+                case 0: case 3: case 7: if (!bB) return false; break;
+                case 1: case 8: if (!bA) return false; break;
+                case 2: break;
+                default: if (!bA || !bB || !bD) return false; break;  // 4,5,6
+            }
+        }
+    } else {
+        uint32_t predMode = (mb.mbType - B200_MB_I_16x16_FIRST) & 3;
+        switch (predMode) {
+            case 0: if (!avB) return false; break;
+            case 1: if (!avA) return false; break;
+            case 2: break;
+            default: if (!avA || !avB || !avD) return false; break;
+        }
+    }
+    switch (mb.chromaMode) {
+        case 0: break;
+        case 1: if (!avA) return false; break;
+        case 2: if (!avB) return false; break;
+        default: if (!avA || !avB || !avD) return false; break;
+    }
+    return true;
+}
+
+// the syntax-level half of h264bsdDecodeMacroblock (h264bsd_macroblock_layer.c:965-1131)
+bool PictureState::finishMacroblock(MbSyntax &mb, uint32_t mbAddr, int &qpY, const SliceHeader &sh, const Pps &pps, const Dpb &dpb) {
+    b200_mb_rec &r = st[mbAddr];
+    MbAux &ax = aux[mbAddr];
+    r.mbType = (uint8_t)mb.mbType;
+    ax.decoded++;
+    bool first = ax.decoded == 1;
+    // SetMbParams (h264bsd_slice_data.c:254-273) -- done by the caller for sliceId; the rest here
+    r.reserved0 = (uint8_t)sh.disableDeblockingFilterIdc;
+    r.filterOffsetA = (int8_t)sh.alphaOffset;
+    r.filterOffsetB = (int8_t)sh.betaOffset;
+    r.chromaQpIndexOffset = (int8_t)pps.chromaQpIndexOffset;
+    r.codedMask = 0;
+    r.coefIndex = 0;
+
+    if (mb.mbType == B200_MB_I_PCM) {
+        r.qpY = 0;
+        r.qpC = kQpC[std::min(51, std::max(0, 0 + pps.chromaQpIndexOffset))];
+        for (int i = 0; i < 24; i++) ax.totalCoeff[i] = 16;
+        r.flags = 0;
+        r.intraChromaMode = 0;
+        std::memset(&r.u, 0, sizeof r.u);
+        r.codedMask = 0xFFFFFFu;
+        if (!first) return true;
+        r.coefIndex = (uint32_t)(coefs.size() / 16);
+        size_t at = coefs.size();
+        coefs.resize(at + 12 * 16);
+        std::memcpy(&coefs[at], mb.pcm, 384);
+        recs[mbAddr] = r;
+        return true;
+    }
+
+    if (mb.mbType != B200_MB_P_SKIP) {
+        std::memcpy(ax.totalCoeff, mb.totalCoeff, 27);
+        if (mb.qpDelta) {
+            qpY += mb.qpDelta;
+            if (qpY < 0) qpY += 52;
+            else if (qpY >= 52) qpY -= 52;
+        }
+    } else {
+        std::memset(ax.totalCoeff, 0, 27);
+    }
+    r.qpY = (uint8_t)qpY;
+    r.qpC = kQpC[std::min(51, std::max(0, qpY + pps.chromaQpIndexOffset))];
+
+    uint32_t mask = 0;
+    for (int i = 0; i < 24; i++)
+        if (ax.totalCoeff[i]) mask |= 1u << i;
+    bool i16 = !isInterType(mb.mbType) && mb.mbType != B200_MB_I_4x4;
+    if (mb.mbType != B200_MB_P_SKIP) {
+        if (i16 && ax.totalCoeff[24]) mask |= B200_CM_LUMA_DC;
+        if (ax.totalCoeff[25] || ax.totalCoeff[26]) mask |= B200_CM_CHROMA_DC;
+    }
+    r.codedMask = mask;
+
+    if (isInterType(mb.mbType)) {
+        r.flags = 0;
+        r.intraChromaMode = 0;
+        if (!deriveInter(mb, mbAddr, dpb)) return false;
+    } else {
+        std::memset(r.refSlot, 0, 4);
+        std::memset(r.refIdx, 0, 4);
+        r.subMbTypes = 0;
+        if (!deriveIntra(mb, mbAddr, pps.constrainedIntraPred)) return false;
+    }
+    if (!first) return true;
+
+    // emit coefficients: [luma DC][chroma DC][coded blocks ascending]
+    r.coefIndex = (uint32_t)(coefs.size() / 16);
+    if (mask) {
+        uint32_t nblk = (uint32_t)__builtin_popcount(mask);
+        size_t at = coefs.size();
+        coefs.resize(at + (size_t)nblk * 16);
+        int16_t *dst = &coefs[at];
+        if (mask & B200_CM_LUMA_DC) { std::memcpy(dst, mb.level[24], 32); dst += 16; }
+        if (mask & B200_CM_CHROMA_DC) { std::memcpy(dst, mb.level[25], 16); std::memset(dst + 8, 0, 16); dst += 16; }
+        for (int i = 0; i < 24; i++)
+            if (mask & (1u << i)) { std::memcpy(dst, mb.level[i], 32); dst += 16; }
+    }
+    recs[mbAddr] = r;
+    return true;
+}
+
+// h264bsdDecodeSliceData (h264bsd_slice_data.c:86-232)
+SliceResult PictureState::decodeSlice(BitReader &br, const SliceHeader &sh, const Sps &sps, const Pps &pps, const Dpb &dpb) {
+    (void)sps;
+    static thread_local MbSyntax mb;
+    static thread_local bool mbInit = false;
+    if (!mbInit) { std::memset(&mb, 0, sizeof mb); mbInit = true; }
+
+    uint32_t cur = sh.firstMb;
+    uint32_t skipRun = 0;
+    bool prevSkipped = false;
+    sliceIdCounter++;
+    lastMbAddr = 0;
+    uint32_t mbCount = 0;
+    int qpY = (int)pps.picInitQp + sh.sliceQpDelta;
+    bool more;
+    do {
+        if (!sh.redundantPicCnt && aux[cur].decoded) return SliceResult::Error;
+        aux[cur].sliceId = (uint16_t)sliceIdCounter;
+        st[cur].sliceId = (uint16_t)sliceIdCounter;
+        bool parsed = false;
+        if (!sh.isI()) {
+            if (!prevSkipped) {
+                if (!br.ue(skipRun)) return SliceResult::Error;
+                if (skipRun > picSizeInMbs - cur) return SliceResult::Error;
+                if (skipRun) prevSkipped = true;
+            }
+        }
+        if (skipRun) {
+            skipRun--;
+            mb.clear();
+            mb.mbType = B200_MB_P_SKIP;
+        } else {
+            prevSkipped = false;
+            bool ok = parseMacroblockLayer(br, mb, cur, sh.isI(), sh.numRefIdxL0Active);
+            parsed = true;
+            if (!ok) {
+                std::memset(mb.level, 0, sizeof mb.level);
+                return SliceResult::Error;
+            }
+        }
+        bool ok = finishMacroblock(mb, cur, qpY, sh, pps, dpb);
+        if (parsed && mb.mbType != B200_MB_I_PCM && (mb.cbp || !isInterType(mb.mbType))) std::memset(mb.level, 0, sizeof mb.level);
+        if (!ok) return SliceResult::Error;
+        if (aux[cur].decoded == 1) mbCount++;
+        more = br.moreRbspData() || skipRun;
+        if (sh.isI()) lastMbAddr = cur;
+        cur = nextMbAddress(cur);
+        if (more && !cur) return SliceResult::Error;
+    } while (more);
+    if (numDecodedMbs + mbCount > picSizeInMbs) return SliceResult::Error;
+    numDecodedMbs += mbCount;
+    return SliceResult::Ok;
+}
+
+// h264bsdMarkSliceCorrupted (h264bsd_slice_data.c:298-354)
+void PictureState::markSliceCorrupted(uint32_t firstMbInSlice, const Sps &sps) {
+    uint32_t cur = firstMbInSlice;
+    uint32_t sliceId = sliceIdCounter;
+    if (lastMbAddr) {
+        uint32_t i = lastMbAddr - 1, tmp = 0;
+        while (i > cur) {
+            if (aux[i].sliceId == sliceId) {
+                tmp++;
+                if (tmp >= std::max<uint32_t>(sps.widthMbs, 10)) break;
+            }
+            i--;
+        }
+        cur = i;
+    }
+    do {
+        if (aux[cur].sliceId == sliceId && aux[cur].decoded) aux[cur].decoded--;
+        else break;
+        cur = nextMbAddress(cur);
+    } while (cur);
+}
+
+void PictureState::finalizeRecords() {
+    for (uint32_t a = 0; a < picSizeInMbs; a++) {
+        b200_mb_rec &r = recs[a];
+        uint32_t idc = r.reserved0;
+        uint8_t f = r.flags & (uint8_t)(B200_MBF_AVAIL_A | B200_MBF_AVAIL_B | B200_MBF_AVAIL_C | B200_MBF_AVAIL_D | B200_MBF_CONCEALED);
+        if (idc != 1) {
+            f |= B200_MBF_FILTER_INNER;
+            int l = mbA(a), t = mbB(a);
+            if (l >= 0 && (idc != 2 || aux[l].sliceId == aux[a].sliceId)) f |= B200_MBF_FILTER_LEFT;
+            if (t >= 0 && (idc != 2 || aux[t].sliceId == aux[a].sliceId)) f |= B200_MBF_FILTER_TOP;
+        }
+        r.flags = f;
+        r.sliceId = aux[a].sliceId;
+    }
+}
+
+// Error path only: macroblocks that never arrived get a record so the picture can still be
+// replayed.  P pictures: copy from reference index 0 (what conceal.c:266 ConcealMb does for P
+// slices when a reference exists); otherwise mid-grey I_PCM.  NOT the reference's spatial intra
+// concealment (conceal.c:266-639) -- see DESIGN.md.
+uint32_t PictureState::concealMissing(const Dpb &dpb, bool pSlice) {
+    uint32_t n = 0;
+    int slot = pSlice ? dpb.refSlot(0) : -1;
+    for (uint32_t a = 0; a < picSizeInMbs; a++) {
+        if (aux[a].decoded) continue;
+        n++;
+        b200_mb_rec r;
+        std::memset(&r, 0, sizeof r);
+        r.flags = B200_MBF_CONCEALED;
+        r.reserved0 = 1;  // no deblocking
+        r.qpY = 40;       // conceal.c: qp 40 for concealed macroblocks
+        r.qpC = kQpC[40];
+        if (slot >= 0) {
+            r.mbType = B200_MB_P_SKIP;
+            for (int q = 0; q < 4; q++) r.refSlot[q] = (uint8_t)slot;
+        } else {
+            r.mbType = B200_MB_I_PCM;
+            r.coefIndex = (uint32_t)(coefs.size() / 16);
+            size_t at = coefs.size();
+            coefs.resize(at + 12 * 16);
+            std::memset(&coefs[at], 128, 384);
+        }
+        st[a] = r;
+        recs[a] = r;
+        aux[a].decoded = 1;
+        std::memset(aux[a].totalCoeff, 0, 27);
+    }
+    return n;
+}
+
+}  // namespace b200

@@ -1,0 +1,70 @@
+// picture.hpp -- per-picture macroblock state + slice-data decoding of the host-side syntax
+// decoder.  Produces the tape records (include/h264bsd_b200_tape.h); touches no pel.
+//
+// Replaces the syntax half of h264bsd_slice_data.c:86-232 and h264bsd_macroblock_layer.c
+// (:134-243 parse, :965-1131 driver) plus the motion-vector / intra-mode derivations that the
+// reference performs inside its pixel functions (h264bsd_inter_prediction.c:494-1026,
+// h264bsd_intra_prediction.c:627-833,:1886-1937).
+#pragma once
+#include <cstdint>
+#include <vector>
+#include "bits.hpp"
+#include "params.hpp"
+#include "dpb.hpp"
+#include "h264bsd_b200_tape.h"
+
+namespace b200 {
+
+// side state that is not part of the tape record (h264bsd_macroblock_layer.h:162-185)
+struct MbAux {
+    uint16_t sliceId = 0;
+    uint8_t decoded = 0;
+    uint8_t totalCoeff[27] = {0};
+};
+
+enum class SliceResult { Ok, Error };
+
+class PictureState {
+public:
+    void resize(uint32_t widthMbs, uint32_t heightMbs);
+    void beginPicture();  // h264bsdResetStorage: sliceId/decoded cleared, the rest persists
+    uint32_t widthMbs = 0, heightMbs = 0, picSizeInMbs = 0;
+
+    std::vector<b200_mb_rec> st;    // persistent per-MB state (last decode of each MB, incl. redundant slices)
+    std::vector<MbAux> aux;
+    std::vector<b200_mb_rec> recs;  // records of the picture being built (first decode of each MB)
+    std::vector<int16_t> coefs;     // coefficient pool of the picture being built, 16 int16 per block
+    std::vector<uint32_t> sliceGroupMap;
+    uint32_t sliceIdCounter = 0, numDecodedMbs = 0, lastMbAddr = 0;
+
+    // decode one slice's macroblocks (h264bsdDecodeSliceData)
+    SliceResult decodeSlice(BitReader &br, const SliceHeader &sh, const Sps &sps, const Pps &pps, const Dpb &dpb);
+    void markSliceCorrupted(uint32_t firstMbInSlice, const Sps &sps);  // h264bsdMarkSliceCorrupted
+    bool allDecoded(bool redundant) const;                             // h264bsdIsEndOfPicture
+    // fill records of macroblocks that never arrived (error path; see DESIGN.md "concealment")
+    uint32_t concealMissing(const Dpb &dpb, bool pSlice);
+    // deblocking edge flags need the final slice ids of the whole picture (deblocking.c:289-320)
+    void finalizeRecords();
+
+private:
+    struct MbSyntax;
+    bool parseMacroblockLayer(BitReader &br, MbSyntax &mb, uint32_t mbAddr, bool iSlice, uint32_t numRefIdxActive);
+    bool parseResidual(BitReader &br, MbSyntax &mb, uint32_t mbAddr);
+    bool finishMacroblock(MbSyntax &mb, uint32_t mbAddr, int &qpY, const SliceHeader &sh, const Pps &pps, const Dpb &dpb);
+    bool deriveInter(MbSyntax &mb, uint32_t mbAddr, const Dpb &dpb);
+    bool deriveIntra(MbSyntax &mb, uint32_t mbAddr, bool constrainedIntra);
+    int nC(uint32_t mbAddr, uint32_t blk, const uint8_t *curTotalCoeff) const;
+    uint32_t nextMbAddress(uint32_t cur) const;
+
+    int mbA(uint32_t a) const { return (a % widthMbs) ? (int)a - 1 : -1; }
+    int mbB(uint32_t a) const { return a >= widthMbs ? (int)(a - widthMbs) : -1; }
+    int mbC(uint32_t a) const { return (a >= widthMbs && (a % widthMbs) < widthMbs - 1) ? (int)(a - widthMbs + 1) : -1; }
+    int mbD(uint32_t a) const { return (a >= widthMbs && (a % widthMbs)) ? (int)(a - widthMbs - 1) : -1; }
+    bool avail(uint32_t cur, int nb) const { return nb >= 0 && aux[nb].sliceId == aux[cur].sliceId; }
+
+    struct NbMv { bool avail; uint32_t refIdx; int16_t mv[2]; };
+    NbMv interNeighbour(uint32_t cur, int x, int y, int curZ) const;
+    bool predictMv(uint32_t cur, int x, int y, int w, int h, uint32_t refIdx, int dirHint, int16_t out[2]) const;
+};
+
+}  // namespace b200
