@@ -1,0 +1,137 @@
+"""Batched engine: many independent streams per GPU (include/h264bsd_b200.h)."""
+import ctypes as C
+import numpy as np
+from . import _lib
+
+
+class ParsedStream:
+    """A stream parsed on the host into a tape (h264bsdB200ParseStream)."""
+
+    def __init__(self, data, no_output_reordering=False):
+        self._L = _lib.load()
+        buf = (C.c_uint8 * len(data)).from_buffer_copy(bytes(data))
+        self.ptr = self._L.h264bsdB200ParseStream(buf, len(data), 1 if no_output_reordering else 0)
+        if not self.ptr:
+            raise MemoryError("h264bsdB200ParseStream failed")
+        t = self.ptr.contents
+        self.num_pics, self.width_mbs, self.height_mbs, self.num_slots = t.numPics, t.widthMbs, t.heightMbs, t.numSlots
+        self.status = t.status
+        self.rec_bytes, self.coef_bytes = t.mbRecBytes, t.coefBytes
+        self.outputs = [t.outputPicIndex[i] for i in range(t.numOutputs)]
+        self.pics = [t.pics[i] for i in range(t.numPics)]
+        self.video_range = t.videoRange
+
+    @property
+    def mbs_per_pic(self):
+        return self.width_mbs * self.height_mbs
+
+    @property
+    def frame_bytes(self):
+        return self.mbs_per_pic * 384
+
+    def coded_blocks(self):
+        return sum(p.numCoefBlocks for p in self.pics)
+
+    def close(self):
+        if self.ptr:
+            self._L.h264bsdB200FreeTape(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Batch:
+    def __init__(self, n_streams, width_mbs, height_mbs, num_slots, device=0):
+        self._L = _lib.load()
+        self.h = self._L.h264bsdB200BatchCreate(device, n_streams, width_mbs, height_mbs, num_slots)
+        if not self.h:
+            raise RuntimeError("h264bsdB200BatchCreate failed (no usable CUDA device? the engine has no CPU fallback)")
+        self.n_streams, self.width_mbs, self.height_mbs, self.num_slots = n_streams, width_mbs, height_mbs, num_slots
+        self.frame_bytes = width_mbs * height_mbs * 384
+
+    def _ck(self, r, what):
+        if r != 0:
+            raise RuntimeError(f"{what} failed")
+
+    def upload(self, stream, parsed):
+        self._ck(self._L.h264bsdB200BatchUploadTape(self.h, stream, parsed.ptr), "upload")
+
+    def replicate(self, src=0):
+        self._ck(self._L.h264bsdB200BatchReplicateTape(self.h, src), "replicate")
+
+    def decode_picture(self, k):
+        self._ck(self._L.h264bsdB200BatchDecodePicture(self.h, k), "decode_picture")
+
+    def run(self, first, count):
+        self._ck(self._L.h264bsdB200BatchRun(self.h, first, count), "run")
+
+    def debug_stage(self, k, recon, deblock):
+        self._ck(self._L.h264bsdB200BatchDebugStage(self.h, k, int(recon), int(deblock)), "debug_stage")
+
+    def sync(self):
+        self._ck(self._L.h264bsdB200BatchSync(self.h), "sync")
+
+    def timer_start(self):
+        self._ck(self._L.h264bsdB200BatchTimerStart(self.h), "timer_start")
+
+    def timer_stop(self):
+        ms = C.c_float(0)
+        self._ck(self._L.h264bsdB200BatchTimerStop(self.h, C.byref(ms)), "timer_stop")
+        return ms.value
+
+    def read_frame(self, stream, slot):
+        out = np.empty(self.frame_bytes, np.uint8)
+        self._ck(self._L.h264bsdB200BatchReadFrame(self.h, stream, slot, out.ctypes.data), "read_frame")
+        return out
+
+    def write_frame(self, stream, slot, frame):
+        f = np.ascontiguousarray(frame, dtype=np.uint8)
+        assert f.size == self.frame_bytes
+        self._ck(self._L.h264bsdB200BatchWriteFrame(self.h, stream, slot, f.ctypes.data), "write_frame")
+
+    def convert_frame(self, stream, slot, mode):
+        out = np.empty(self.width_mbs * self.height_mbs * 256, np.uint32)
+        self._ck(self._L.h264bsdB200BatchConvertFrame(self.h, stream, slot, mode, out.ctypes.data), "convert_frame")
+        return out
+
+    def convert_bench(self, stream, slot, mode, reps):
+        ms = C.c_float(0)
+        self._ck(self._L.h264bsdB200BatchConvertBench(self.h, stream, slot, mode, reps, C.byref(ms)), "convert_bench")
+        return ms.value
+
+    def compare_streams(self, slots):
+        arr = (C.c_uint32 * self.n_streams)(*slots)
+        r = self._L.h264bsdB200BatchCompareStreams(self.h, arr)
+        if r < 0:
+            raise RuntimeError("compare_streams failed")
+        return r
+
+    def idct_errors(self):
+        return self._L.h264bsdB200BatchIdctErrors(self.h)
+
+    def watchdog(self):
+        return (self._L.h264bsdB200BatchWatchdog(self.h, 0), self._L.h264bsdB200BatchWatchdog(self.h, 1))
+
+    def launches(self):
+        return self._L.h264bsdB200BatchLaunches(self.h)
+
+    def h2d_bytes(self):
+        return self._L.h264bsdB200BatchH2DBytes(self.h)
+
+    def d2h_bytes(self):
+        return self._L.h264bsdB200BatchD2HBytes(self.h)
+
+    def close(self):
+        if self.h:
+            self._L.h264bsdB200BatchDestroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

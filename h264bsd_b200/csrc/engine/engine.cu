@@ -1,0 +1,475 @@
+// engine.cu -- host side of the B200 reconstruction engine: HBM frame pool, tape upload, per-picture
+// launch sequence (reconstruct -> in-loop filter -> border replication), read-back.
+//
+// One Batch = N independent streams of identical geometry resident on one GPU.  Pictures with the same
+// decode index are processed together: one launch per stage covers all streams.  There is no CPU
+// fallback anywhere in this file: without a usable CUDA device every entry point fails loudly.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include "recon_kernel.cuh"
+#include "deblock_kernel.cuh"
+#include "engine.hpp"
+
+namespace b200 {
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) {                                                                     \
+            std::fprintf(stderr, "h264bsd_b200: CUDA error %s at %s:%d (%s)\n", cudaGetErrorName(e_), __FILE__, __LINE__, \
+                         cudaGetErrorString(e_));                                                    \
+            return false;                                                                            \
+        }                                                                                            \
+    } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn getEncodeTiled() {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return nullptr;
+    return (EncodeTiledFn)fn;
+}
+
+int deviceCount() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+Batch::~Batch() { destroy(); }
+
+void Batch::destroy() {
+    if (!created_) return;
+    cudaSetDevice(device_);
+    cudaStreamSynchronize(stream_);
+    for (auto &t : tapes_) {
+        if (t.owned) { cudaFree(t.recs); cudaFree(t.coefs); }
+    }
+    tapes_.clear();
+    cudaFree(pool_); cudaFree(dOrder_); cudaFree(dDoneRecon_); cudaFree(dDoneDeblock_); cudaFree(dCounters_);
+    cudaFree(dJobs_); cudaFree(dStage_[0]); cudaFree(dStage_[1]); cudaFree(dConvert_); cudaFree(dSlots_);
+    if (hStage_[0]) cudaFreeHost(hStage_[0]);
+    if (hStage_[1]) cudaFreeHost(hStage_[1]);
+    if (evA_) cudaEventDestroy(evA_);
+    if (evB_) cudaEventDestroy(evB_);
+    if (stream_) cudaStreamDestroy(stream_);
+    created_ = false;
+}
+
+bool Batch::create(int device, uint32_t nStreams, uint32_t widthMbs, uint32_t heightMbs, uint32_t numSlots) {
+    int n = deviceCount();
+    if (n <= 0) {
+        std::fprintf(stderr, "h264bsd_b200: no CUDA device visible -- this engine has no CPU fallback\n");
+        return false;
+    }
+    if (device < 0 || device >= n || !nStreams || !widthMbs || !heightMbs || !numSlots || numSlots > 32) return false;
+    device_ = device;
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 9) {
+        std::fprintf(stderr, "h264bsd_b200: device sm_%d%d lacks TMA; this engine targets sm_100a\n", prop.major, prop.minor);
+        return false;
+    }
+    numSms_ = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&evA_));
+    CK(cudaEventCreate(&evB_));
+    created_ = true;
+
+    PoolGeom &g = g_;
+    g.widthMbs = (int)widthMbs; g.heightMbs = (int)heightMbs; g.nMbs = (int)(widthMbs * heightMbs);
+    g.W = 16 * (int)widthMbs; g.H = 16 * (int)heightMbs;
+    g.pitchY = g.W + 2 * kPadY;
+    g.pitchC = (g.W / 2 + 2 * kPadC + 15) & ~15;
+    g.rowsY = g.H + 2 * kPadY;
+    g.rowsC = g.H / 2 + 2 * kPadC;
+    g.offCb = (unsigned long long)g.pitchY * g.rowsY;
+    g.offCr = g.offCb + (unsigned long long)g.pitchC * g.rowsC;
+    g.frameStride = (g.offCr + (unsigned long long)g.pitchC * g.rowsC + 255) & ~255ull;
+    g.numSlots = (int)numSlots; g.nStreams = (int)nStreams;
+    const unsigned long long nFrames = (unsigned long long)nStreams * numSlots;
+    CK(cudaMalloc(&pool_, nFrames * g.frameStride));
+    CK(cudaMemsetAsync(pool_, 128, nFrames * g.frameStride, stream_));
+
+    // wavefront order: x + 2y ascending (every dependency of a macroblock has a smaller key)
+    std::vector<uint16_t> order(g.nMbs);
+    {
+        std::vector<std::pair<uint32_t, uint32_t>> keyed(g.nMbs);
+        for (int mb = 0; mb < g.nMbs; mb++) keyed[mb] = {(uint32_t)(mb % g.widthMbs + 2 * (mb / g.widthMbs)), (uint32_t)mb};
+        std::sort(keyed.begin(), keyed.end());
+        for (int i = 0; i < g.nMbs; i++) order[i] = (uint16_t)keyed[i].second;
+    }
+    if (g.nMbs > 65535) return false;
+    CK(cudaMalloc(&dOrder_, sizeof(uint16_t) * g.nMbs));
+    CK(cudaMemcpyAsync(dOrder_, order.data(), sizeof(uint16_t) * g.nMbs, cudaMemcpyHostToDevice, stream_));
+    const size_t flagBytes = sizeof(uint32_t) * (size_t)nStreams * g.nMbs;
+    CK(cudaMalloc(&dDoneRecon_, flagBytes));
+    CK(cudaMalloc(&dDoneDeblock_, flagBytes));
+    CK(cudaMemsetAsync(dDoneRecon_, 0, flagBytes, stream_));
+    CK(cudaMemsetAsync(dDoneDeblock_, 0, flagBytes, stream_));
+    CK(cudaMalloc(&dCounters_, sizeof(uint32_t) * 8));
+    CK(cudaMemsetAsync(dCounters_, 0, sizeof(uint32_t) * 8, stream_));
+    CK(cudaMalloc(&dSlots_, sizeof(uint32_t) * nStreams));
+    serial_ = 0;
+    if (std::getenv("H264BSD_B200_HEARTBEAT")) {
+        CK(cudaHostAlloc(&hbHost_, sizeof(uint32_t) * 4 * 65536, cudaHostAllocMapped));
+        std::memset(hbHost_, 0, sizeof(uint32_t) * 4 * 65536);
+        CK(cudaHostGetDevicePointer(&hbDev_, hbHost_, 0));
+    }
+
+    // TMA descriptors over the whole pool: luma {x, y, frame}, chroma {x, y, plane, frame}
+    EncodeTiledFn enc = getEncodeTiled();
+    if (!enc) {
+        std::fprintf(stderr, "h264bsd_b200: cuTensorMapEncodeTiled unavailable\n");
+        return false;
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)g.pitchY, (cuuint64_t)g.rowsY, nFrames};
+        cuuint64_t strides[2] = {(cuuint64_t)g.pitchY, g.frameStride};
+        cuuint32_t box[3] = {kLumaBoxW, kLumaBoxH, 1}, es[3] = {1, 1, 1};
+        CUresult r = enc(&lumaMap_, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, pool_, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { std::fprintf(stderr, "h264bsd_b200: luma tensor map failed (%d)\n", (int)r); return false; }
+    }
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)g.pitchC, (cuuint64_t)g.rowsC, 2, nFrames};
+        cuuint64_t strides[3] = {(cuuint64_t)g.pitchC, (cuuint64_t)g.pitchC * g.rowsC, g.frameStride};
+        cuuint32_t box[4] = {kChromaBoxW, kChromaBoxH, 2, 1}, es[4] = {1, 1, 1, 1};
+        CUresult r = enc(&chromaMap_, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, pool_ + g.offCb, dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { std::fprintf(stderr, "h264bsd_b200: chroma tensor map failed (%d)\n", (int)r); return false; }
+    }
+    int occR = 0, occD = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occR, reconKernel, kReconWarps * 32, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occD, deblockKernel, kDeblockWarps * 32, 0));
+    reconBlocks_ = std::max(1, occR) * numSms_;
+    deblockBlocks_ = std::max(1, occD) * numSms_;
+    tapes_.assign(nStreams, DevTape());
+    CK(cudaStreamSynchronize(stream_));
+    return true;
+}
+
+bool Batch::uploadTape(uint32_t stream, const b200_tape *t) {
+    if (!created_ || stream >= (uint32_t)g_.nStreams || !t) return false;
+    if (t->widthMbs != (uint32_t)g_.widthMbs || t->heightMbs != (uint32_t)g_.heightMbs || t->numSlots > (uint32_t)g_.numSlots) return false;
+    CK(cudaSetDevice(device_));
+    DevTape &d = tapes_[stream];
+    if (d.owned) { cudaFree(d.recs); cudaFree(d.coefs); }
+    d = DevTape();
+    CK(cudaMalloc(&d.recs, t->mbRecBytes + 256));
+    CK(cudaMalloc(&d.coefs, t->coefBytes + 256));
+    d.owned = true;
+    d.recBytes = t->mbRecBytes; d.coefBytes = t->coefBytes;
+    CK(cudaMemcpyAsync(d.recs, t->mbRecs, t->mbRecBytes, cudaMemcpyHostToDevice, stream_));
+    CK(cudaMemcpyAsync(d.coefs, t->coefs, t->coefBytes, cudaMemcpyHostToDevice, stream_));
+    d.pics.assign(t->pics, t->pics + t->numPics);
+    jobsDirty_ = true;
+    h2dBytes_ += t->mbRecBytes + t->coefBytes;
+    return true;
+}
+
+// give every other stream its OWN copy in HBM of stream `src`'s tape (device-to-device)
+bool Batch::replicateTape(uint32_t src) {
+    if (!created_ || src >= (uint32_t)g_.nStreams || !tapes_[src].recs) return false;
+    CK(cudaSetDevice(device_));
+    const DevTape &s = tapes_[src];
+    for (uint32_t i = 0; i < (uint32_t)g_.nStreams; i++) {
+        if (i == src) continue;
+        DevTape &d = tapes_[i];
+        if (d.owned) { cudaFree(d.recs); cudaFree(d.coefs); }
+        d = DevTape();
+        CK(cudaMalloc(&d.recs, s.recBytes + 256));
+        CK(cudaMalloc(&d.coefs, s.coefBytes + 256));
+        d.owned = true;
+        d.recBytes = s.recBytes; d.coefBytes = s.coefBytes;
+        CK(cudaMemcpyAsync(d.recs, s.recs, s.recBytes, cudaMemcpyDeviceToDevice, stream_));
+        CK(cudaMemcpyAsync(d.coefs, s.coefs, s.coefBytes, cudaMemcpyDeviceToDevice, stream_));
+        d.pics = s.pics;
+    }
+    jobsDirty_ = true;
+    return true;
+}
+
+bool Batch::buildJobs() {
+    uint32_t np = 0xFFFFFFFFu;
+    for (const auto &t : tapes_) {
+        if (!t.recs) return false;
+        np = std::min<uint32_t>(np, (uint32_t)t.pics.size());
+    }
+    numPics_ = np;
+    std::vector<StreamJob> jobs((size_t)np * g_.nStreams);
+    for (uint32_t k = 0; k < np; k++)
+        for (int s = 0; s < g_.nStreams; s++) {
+            const DevTape &t = tapes_[s];
+            StreamJob &j = jobs[(size_t)k * g_.nStreams + s];
+            j.recs = reinterpret_cast<const b200_mb_rec *>(t.recs + t.pics[k].mbRecOffset);
+            j.coefs = reinterpret_cast<const int16_t *>(t.coefs + t.pics[k].coefOffset);
+            j.curSlot = t.pics[k].curSlot;
+            j.pad = 0;
+        }
+    cudaFree(dJobs_);
+    dJobs_ = nullptr;
+    CK(cudaMalloc(&dJobs_, sizeof(StreamJob) * jobs.size() + 64));
+    CK(cudaMemcpyAsync(dJobs_, jobs.data(), sizeof(StreamJob) * jobs.size(), cudaMemcpyHostToDevice, stream_));
+    CK(cudaStreamSynchronize(stream_));
+    jobsDirty_ = false;
+    return true;
+}
+
+bool Batch::launchPicture(const StreamJob *dJobs, bool recon, bool deblock) {
+    const uint32_t total = (uint32_t)g_.nStreams * (uint32_t)g_.nMbs;
+    serial_++;
+    if (recon) {
+        ReconParams rp;
+        rp.pool = pool_; rp.g = g_; rp.jobs = dJobs; rp.order = dOrder_; rp.done = dDoneRecon_;
+        rp.ticket = dCounters_ + 0; rp.errors = dCounters_ + 2; rp.serial = serial_; rp.totalTickets = total;
+        const int blocks = (int)std::min<uint32_t>((uint32_t)reconBlocks_, (total + kReconWarps - 1) / kReconWarps);
+        reconKernel<<<blocks, kReconWarps * 32, 0, stream_>>>(rp, lumaMap_, chromaMap_);
+        launches_++;
+    }
+    if (deblock) {
+        DeblockParams dp;
+        dp.pool = pool_; dp.g = g_; dp.jobs = dJobs; dp.order = dOrder_; dp.done = dDoneDeblock_;
+        dp.ticket = dCounters_ + 1; dp.serial = serial_; dp.totalTickets = total; dp.hb = hbDev_;
+        const int blocks = (int)std::min<uint32_t>((uint32_t)deblockBlocks_, (total + kDeblockWarps - 1) / kDeblockWarps);
+        deblockKernel<<<blocks, kDeblockWarps * 32, 0, stream_>>>(dp);
+        launches_++;
+    }
+    {
+        BorderParams bp;
+        bp.pool = pool_; bp.g = g_; bp.jobs = dJobs; bp.hb = hbDev_;
+        const long long rows = (long long)(g_.rowsY + 2 * g_.rowsC) * g_.nStreams;
+        const int blocks = (int)((rows + 7) / 8);
+        borderKernel<<<blocks, 256, 0, stream_>>>(bp);
+        launches_++;
+    }
+    CK(cudaMemsetAsync(dCounters_, 0, 2 * sizeof(uint32_t), stream_));
+    CK(cudaGetLastError());
+    return true;
+}
+
+bool Batch::decodePicture(uint32_t k) {
+    if (!created_) return false;
+    CK(cudaSetDevice(device_));
+    if (jobsDirty_ && !buildJobs()) return false;
+    if (k >= numPics_) return false;
+    return launchPicture(dJobs_ + (size_t)k * g_.nStreams, true, true);
+}
+
+bool Batch::debugStage(uint32_t k, bool recon, bool deblock) {
+    if (!created_) return false;
+    CK(cudaSetDevice(device_));
+    if (jobsDirty_ && !buildJobs()) return false;
+    if (k >= numPics_) return false;
+    return launchPicture(dJobs_ + (size_t)k * g_.nStreams, recon, deblock);
+}
+
+bool Batch::run(uint32_t first, uint32_t count) {
+    for (uint32_t k = first; k < first + count; k++)
+        if (!decodePicture(k)) return false;
+    return true;
+}
+
+bool Batch::sync() {
+    if (!created_) return false;
+    CK(cudaSetDevice(device_));
+    CK(cudaStreamSynchronize(stream_));
+    return true;
+}
+
+bool Batch::timerStart() { CK(cudaSetDevice(device_)); CK(cudaEventRecord(evA_, stream_)); return true; }
+bool Batch::timerStop(float *ms) {
+    CK(cudaSetDevice(device_));
+    CK(cudaEventRecord(evB_, stream_));
+    CK(cudaEventSynchronize(evB_));
+    CK(cudaEventElapsedTime(ms, evA_, evB_));
+    return true;
+}
+
+// streaming (single picture, host buffers): the legacy API path
+bool Batch::submitHostPicture(uint32_t stream, const b200_pic_hdr &hdr, const b200_mb_rec *recs, const int16_t *coefs) {
+    if (!created_ || g_.nStreams != 1 || stream != 0) return false;
+    CK(cudaSetDevice(device_));
+    const size_t recBytes = (size_t)g_.nMbs * sizeof(b200_mb_rec);
+    const size_t coefBytes = (size_t)hdr.numCoefBlocks * B200_COEF_BLOCK_BYTES;
+    const size_t need = recBytes + coefBytes + 512;
+    const int b = stageIdx_ ^= 1;
+    if (stageCap_[b] < need) {
+        // growing a staging buffer: make sure nothing in flight still reads it
+        CK(cudaStreamSynchronize(stream_));
+        if (hStage_[b]) cudaFreeHost(hStage_[b]);
+        cudaFree(dStage_[b]);
+        hStage_[b] = nullptr; dStage_[b] = nullptr;
+        const size_t cap = need + need / 2;
+        CK(cudaMallocHost(&hStage_[b], cap));
+        CK(cudaMalloc(&dStage_[b], cap));
+        stageCap_[b] = cap;
+        if (!stageEv_[b]) CK(cudaEventCreateWithFlags(&stageEv_[b], cudaEventDisableTiming));
+    } else if (stageEv_[b]) {
+        CK(cudaEventSynchronize(stageEv_[b]));  // the picture that last used this buffer has been consumed
+    }
+    uint8_t *h = hStage_[b];
+    StreamJob job;
+    const size_t recOff = 256, coefOff = (256 + recBytes + 255) & ~(size_t)255;
+    job.recs = reinterpret_cast<const b200_mb_rec *>(dStage_[b] + recOff);
+    job.coefs = reinterpret_cast<const int16_t *>(dStage_[b] + coefOff);
+    job.curSlot = hdr.curSlot;
+    job.pad = 0;
+    std::memcpy(h, &job, sizeof job);
+    std::memcpy(h + recOff, recs, recBytes);
+    std::memcpy(h + coefOff, coefs, coefBytes);
+    CK(cudaMemcpyAsync(dStage_[b], h, coefOff + coefBytes, cudaMemcpyHostToDevice, stream_));
+    h2dBytes_ += coefOff + coefBytes;
+    if (!launchPicture(reinterpret_cast<const StreamJob *>(dStage_[b]), true, true)) return false;
+    CK(cudaEventRecord(stageEv_[b], stream_));
+    return true;
+}
+
+bool Batch::readFrame(uint32_t stream, uint32_t slot, uint8_t *dst) {
+    if (!created_ || stream >= (uint32_t)g_.nStreams || slot >= (uint32_t)g_.numSlots) return false;
+    CK(cudaSetDevice(device_));
+    const uint8_t *f = pool_ + ((unsigned long long)stream * g_.numSlots + slot) * g_.frameStride;
+    const size_t ySize = (size_t)g_.W * g_.H, cSize = ySize / 4;
+    CK(cudaMemcpy2DAsync(dst, g_.W, f + (size_t)kPadY * g_.pitchY + kPadY, g_.pitchY, g_.W, g_.H, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaMemcpy2DAsync(dst + ySize, g_.W / 2, f + g_.offCb + (size_t)kPadC * g_.pitchC + kPadC, g_.pitchC, g_.W / 2, g_.H / 2,
+                         cudaMemcpyDeviceToHost, stream_));
+    CK(cudaMemcpy2DAsync(dst + ySize + cSize, g_.W / 2, f + g_.offCr + (size_t)kPadC * g_.pitchC + kPadC, g_.pitchC, g_.W / 2, g_.H / 2,
+                         cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+    d2hBytes_ += ySize + 2 * cSize;
+    return true;
+}
+
+// test hook: put an I420 picture into a slot (and replicate its border) so a stage can be checked in isolation
+bool Batch::writeFrame(uint32_t stream, uint32_t slot, const uint8_t *src) {
+    if (!created_ || stream >= (uint32_t)g_.nStreams || slot >= (uint32_t)g_.numSlots) return false;
+    CK(cudaSetDevice(device_));
+    uint8_t *f = pool_ + ((unsigned long long)stream * g_.numSlots + slot) * g_.frameStride;
+    const size_t ySize = (size_t)g_.W * g_.H, cSize = ySize / 4;
+    CK(cudaMemcpy2DAsync(f + (size_t)kPadY * g_.pitchY + kPadY, g_.pitchY, src, g_.W, g_.W, g_.H, cudaMemcpyHostToDevice, stream_));
+    CK(cudaMemcpy2DAsync(f + g_.offCb + (size_t)kPadC * g_.pitchC + kPadC, g_.pitchC, src + ySize, g_.W / 2, g_.W / 2, g_.H / 2,
+                         cudaMemcpyHostToDevice, stream_));
+    CK(cudaMemcpy2DAsync(f + g_.offCr + (size_t)kPadC * g_.pitchC + kPadC, g_.pitchC, src + ySize + cSize, g_.W / 2, g_.W / 2, g_.H / 2,
+                         cudaMemcpyHostToDevice, stream_));
+    // border: a one-stream BorderParams view whose "stream 0" is this frame
+    StreamJob job;
+    std::memset(&job, 0, sizeof job);
+    job.curSlot = 0;
+    StreamJob *dJob = nullptr;
+    CK(cudaMalloc(&dJob, sizeof job));
+    CK(cudaMemcpyAsync(dJob, &job, sizeof job, cudaMemcpyHostToDevice, stream_));
+    BorderParams bp;
+    bp.pool = f; bp.g = g_; bp.g.nStreams = 1; bp.jobs = dJob; bp.hb = nullptr;
+    const long long rows = (long long)(g_.rowsY + 2 * g_.rowsC);
+    borderKernel<<<(int)((rows + 7) / 8), 256, 0, stream_>>>(bp);
+    CK(cudaStreamSynchronize(stream_));
+    cudaFree(dJob);
+    return true;
+}
+
+bool Batch::convertFrame(uint32_t stream, uint32_t slot, int mode, uint32_t *dstHost) {
+    if (!created_ || stream >= (uint32_t)g_.nStreams || slot >= (uint32_t)g_.numSlots || mode < 0 || mode > 2) return false;
+    CK(cudaSetDevice(device_));
+    const size_t bytes = (size_t)g_.W * g_.H * 4;
+    if (!dConvert_) CK(cudaMalloc(&dConvert_, bytes));
+    const uint8_t *f = pool_ + ((unsigned long long)stream * g_.numSlots + slot) * g_.frameStride;
+    dim3 grid((g_.W / 4 + 255) / 256, g_.H);
+    convertKernel<<<grid, 256, 0, stream_>>>(f + (size_t)kPadY * g_.pitchY + kPadY, g_.pitchY, f + g_.offCb + (size_t)kPadC * g_.pitchC + kPadC,
+                                              f + g_.offCr + (size_t)kPadC * g_.pitchC + kPadC, g_.pitchC, g_.W, mode, dConvert_);
+    launches_++;
+    CK(cudaMemcpyAsync(dstHost, dConvert_, bytes, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+    d2hBytes_ += bytes;
+    return true;
+}
+
+// device-only conversion of one frame `reps` times (config 5 throughput); returns elapsed ms
+bool Batch::convertBench(uint32_t stream, uint32_t slot, int mode, int reps, float *ms) {
+    if (!created_ || stream >= (uint32_t)g_.nStreams || slot >= (uint32_t)g_.numSlots) return false;
+    CK(cudaSetDevice(device_));
+    const size_t bytes = (size_t)g_.W * g_.H * 4;
+    if (!dConvert_) CK(cudaMalloc(&dConvert_, bytes));
+    const uint8_t *f = pool_ + ((unsigned long long)stream * g_.numSlots + slot) * g_.frameStride;
+    dim3 grid((g_.W / 4 + 255) / 256, g_.H);
+    CK(cudaEventRecord(evA_, stream_));
+    for (int i = 0; i < reps; i++) convertKernel<<<grid, 256, 0, stream_>>>(f + (size_t)kPadY * g_.pitchY + kPadY, g_.pitchY, f + g_.offCb + (size_t)kPadC * g_.pitchC + kPadC,
+                                              f + g_.offCr + (size_t)kPadC * g_.pitchC + kPadC, g_.pitchC, g_.W, mode, dConvert_);
+    CK(cudaEventRecord(evB_, stream_));
+    CK(cudaEventSynchronize(evB_));
+    CK(cudaEventElapsedTime(ms, evA_, evB_));
+    launches_ += reps;
+    return true;
+}
+
+// h264bsdConvertTo{RGBA,BGRA,YCbCrA} for caller-owned host buffers (contiguous I420 in, u32 pixels out)
+bool convertHostI420(int mode, uint32_t width, uint32_t height, const uint8_t *yuv, uint32_t *out) {
+    if (deviceCount() <= 0) {
+        std::fprintf(stderr, "h264bsd_b200: no CUDA device visible -- this engine has no CPU fallback\n");
+        return false;
+    }
+    if (!width || !height || (width & 3)) return false;
+    const size_t inBytes = (size_t)width * height * 3 / 2, outBytes = (size_t)width * height * 4;
+    uint8_t *dIn = nullptr;
+    uint32_t *dOut = nullptr;
+    CK(cudaMalloc(&dIn, inBytes));
+    CK(cudaMalloc(&dOut, outBytes));
+    CK(cudaMemcpy(dIn, yuv, inBytes, cudaMemcpyHostToDevice));
+    dim3 grid((width / 4 + 255) / 256, height);
+    convertKernel<<<grid, 256>>>(dIn, (int)width, dIn + (size_t)width * height, dIn + (size_t)width * height * 5 / 4, (int)width / 2,
+                                 (int)width, mode, dOut);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out, dOut, outBytes, cudaMemcpyDeviceToHost));
+    cudaFree(dIn);
+    cudaFree(dOut);
+    return true;
+}
+
+// number of streams whose frame in slots[s] differs from stream 0's frame in slots[0]
+int Batch::compareStreams(const uint32_t *slots) {
+    if (!created_) return -1;
+    if (cudaSetDevice(device_) != cudaSuccess) return -1;
+    if (g_.nStreams == 1) return 0;
+    uint32_t *dMis = nullptr;
+    if (cudaMalloc(&dMis, sizeof(uint32_t) * g_.nStreams) != cudaSuccess) return -1;
+    cudaMemsetAsync(dMis, 0, sizeof(uint32_t) * g_.nStreams, stream_);
+    cudaMemcpyAsync(dSlots_, slots, sizeof(uint32_t) * g_.nStreams, cudaMemcpyHostToDevice, stream_);
+    dim3 grid(64, g_.nStreams - 1);
+    compareKernel<<<grid, 256, 0, stream_>>>(pool_, g_, dSlots_, dMis);
+    std::vector<uint32_t> mis(g_.nStreams);
+    cudaMemcpyAsync(mis.data(), dMis, sizeof(uint32_t) * g_.nStreams, cudaMemcpyDeviceToHost, stream_);
+    if (cudaStreamSynchronize(stream_) != cudaSuccess) { cudaFree(dMis); return -1; }
+    cudaFree(dMis);
+    int bad = 0;
+    for (int s = 1; s < g_.nStreams; s++) bad += mis[s] != 0;
+    return bad;
+}
+
+uint32_t Batch::watchdog(int which) {
+    uint32_t v[4] = {0, 0, 0, 0};
+    if (!created_) return 0;
+    cudaSetDevice(device_);
+    cudaStreamSynchronize(stream_);
+    cudaMemcpyFromSymbol(v, gWatchdog, sizeof v);
+    return v[which & 3];
+}
+
+uint32_t Batch::idctErrors() {
+    uint32_t v = 0;
+    if (!created_) return 0;
+    cudaSetDevice(device_);
+    cudaMemcpyAsync(&v, dCounters_ + 2, sizeof v, cudaMemcpyDeviceToHost, stream_);
+    cudaStreamSynchronize(stream_);
+    return v;
+}
+
+}  // namespace b200

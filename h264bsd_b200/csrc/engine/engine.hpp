@@ -1,0 +1,89 @@
+// engine.hpp -- host-visible interface of the B200 reconstruction engine (see engine.cu)
+#pragma once
+#include <cstdint>
+#include <vector>
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include "pool_geom.hpp"
+#include "h264bsd_b200_tape.h"
+
+namespace b200 {
+
+int deviceCount();
+bool convertHostI420(int mode, uint32_t width, uint32_t height, const uint8_t *yuv, uint32_t *out);
+
+class Batch {
+public:
+    Batch() = default;
+    ~Batch();
+    Batch(const Batch &) = delete;
+    Batch &operator=(const Batch &) = delete;
+
+    bool create(int device, uint32_t nStreams, uint32_t widthMbs, uint32_t heightMbs, uint32_t numSlots);
+    void destroy();
+
+    bool uploadTape(uint32_t stream, const b200_tape *t);
+    bool replicateTape(uint32_t srcStream);
+    bool decodePicture(uint32_t k);                // picture k of every stream
+    bool run(uint32_t first, uint32_t count);
+    bool debugStage(uint32_t k, bool recon, bool deblock);
+    bool sync();
+    bool timerStart();
+    bool timerStop(float *ms);
+
+    bool submitHostPicture(uint32_t stream, const b200_pic_hdr &hdr, const b200_mb_rec *recs, const int16_t *coefs);
+    bool readFrame(uint32_t stream, uint32_t slot, uint8_t *dst);
+    bool writeFrame(uint32_t stream, uint32_t slot, const uint8_t *src);
+    bool convertFrame(uint32_t stream, uint32_t slot, int mode, uint32_t *dstHost);
+    bool convertBench(uint32_t stream, uint32_t slot, int mode, int reps, float *ms);
+    int compareStreams(const uint32_t *slots);
+    uint32_t idctErrors();
+    uint32_t watchdog(int which);  // 0: flag waits that gave up, 1: TMA waits that gave up
+
+    const PoolGeom &geom() const { return g_; }
+    uint32_t numPics() const { return numPics_; }
+    uint64_t launches() const { return launches_; }
+    uint64_t h2dBytes() const { return h2dBytes_; }
+    uint64_t d2hBytes() const { return d2hBytes_; }
+    size_t frameBytes() const { return (size_t)g_.nMbs * 384; }
+    const std::vector<b200_pic_hdr> &pics(uint32_t stream) const { return tapes_[stream].pics; }
+    int device() const { return device_; }
+
+private:
+    struct DevTape {
+        uint8_t *recs = nullptr, *coefs = nullptr;
+        size_t recBytes = 0, coefBytes = 0;
+        bool owned = false;
+        std::vector<b200_pic_hdr> pics;
+    };
+    bool buildJobs();
+    bool launchPicture(const StreamJob *dJobs, bool recon, bool deblock);
+
+    bool created_ = false;
+    int device_ = 0, numSms_ = 0;
+    cudaStream_t stream_ = nullptr;
+    cudaEvent_t evA_ = nullptr, evB_ = nullptr;
+    PoolGeom g_{};
+    uint8_t *pool_ = nullptr;
+    CUtensorMap lumaMap_, chromaMap_;
+    uint16_t *dOrder_ = nullptr;
+    uint32_t *dDoneRecon_ = nullptr, *dDoneDeblock_ = nullptr, *dCounters_ = nullptr, *dSlots_ = nullptr;
+    uint32_t serial_ = 0;
+    int reconBlocks_ = 0, deblockBlocks_ = 0;
+    std::vector<DevTape> tapes_;
+    StreamJob *dJobs_ = nullptr;
+    uint32_t numPics_ = 0;
+    bool jobsDirty_ = true;
+    // streaming staging (legacy single-stream API)
+    uint8_t *hStage_[2] = {nullptr, nullptr}, *dStage_[2] = {nullptr, nullptr};
+    size_t stageCap_[2] = {0, 0};
+    cudaEvent_t stageEv_[2] = {nullptr, nullptr};
+    int stageIdx_ = 0;
+    uint32_t *dConvert_ = nullptr;
+    uint64_t launches_ = 0, h2dBytes_ = 0, d2hBytes_ = 0;
+    uint32_t *hbHost_ = nullptr, *hbDev_ = nullptr;  // debug heartbeat (env H264BSD_B200_HEARTBEAT)
+public:
+    const uint32_t *heartbeat() const { return hbHost_; }
+};
+
+}  // namespace b200

@@ -1,0 +1,536 @@
+// recon_kernel.cuh -- macroblock reconstruction: inverse zig-zag + dequant + IDCT, intra /
+// inter prediction, add residual, write.  One warp per macroblock, persistent CTAs, tickets
+// handed out in wavefront order so that a warp only ever waits on warps that already started.
+//
+// Restates, as sm_100a device code: h264bsd_transform.c:97-401 (residual),
+// h264bsd_intra_prediction.c:478-1830, h264bsd_inter_prediction.c:361-482 +
+// h264bsd_reconstruct.c:109-2367 (motion compensation), h264bsd_image.c:81-344 (write).
+#pragma once
+#include "device_common.cuh"
+
+namespace b200 {
+
+constexpr int kReconWarps = 8;
+
+struct ReconParams {
+    uint8_t *pool;
+    PoolGeom g;
+    const StreamJob *jobs;     // nStreams
+    const uint16_t *order;     // nMbs macroblock indices in wavefront order (x + 2y ascending)
+    uint32_t *done;            // nStreams * nMbs completion flags
+    uint32_t *ticket;          // global ticket counter (zeroed before launch)
+    uint32_t *errors;          // [0] IDCT range errors (h264bsd_transform.c:183-188)
+    uint32_t serial;           // value that marks "done in this launch"
+    uint32_t totalTickets;     // nStreams * nMbs
+};
+
+struct __align__(128) ReconWarpSmem {
+    uint8_t lumaWin[kLumaBoxW * kLumaBoxH + 16];          // 1024
+    uint8_t chromaWin[2 * kChromaBoxW * kChromaBoxH + 64]; // 640
+    int16_t res[24][16];                                   // 768
+    uint8_t pred[384];                                     // 384: Y 16x16, Cb 8x8, Cr 8x8
+    uint8_t itY[17][24];                                   // 408: rows -1..15, cols -1..19 (+pad)
+    uint8_t itC[2][9][12];                                 // 216: rows -1..7, cols -1..7 (+pad)
+    uint64_t mbar;
+    uint32_t pad[5];
+};
+
+// ---- residual -----------------------------------------------------------------------------------
+__device__ __forceinline__ int levelScale(int qpMod, int cls) {
+    // h264bsd_transform.c:58-59; cls 0 = both coordinates even, 2 = both odd, 1 = mixed
+    const int t[6][3] = {{10, 13, 16}, {11, 14, 18}, {13, 16, 20}, {14, 18, 23}, {16, 20, 25}, {18, 23, 29}};
+    return t[qpMod][cls];
+}
+
+// h264bsdProcessBlock (transform.c:97-234): lev in zig-zag order -> out[16] raster residual
+__device__ __forceinline__ bool idctBlock(const int16_t *lev, int qp, bool dcPreset, int dcValue, int *out) {
+    int qpDiv = qp / 6, qpMod = qp - 6 * qpDiv;
+    int s0 = levelScale(qpMod, 0) << qpDiv, s1 = levelScale(qpMod, 1) << qpDiv, s2 = levelScale(qpMod, 2) << qpDiv;
+    int d[16];
+    // zig-zag position -> raster: 0,1,4,8,5,2,3,6,9,12,13,10,7,11,14,15
+    d[0] = lev[0] * s0;   d[1] = lev[1] * s1;   d[4] = lev[2] * s1;   d[8] = lev[3] * s0;
+    d[5] = lev[4] * s2;   d[2] = lev[5] * s0;   d[3] = lev[6] * s1;   d[6] = lev[7] * s1;
+    d[9] = lev[8] * s1;   d[12] = lev[9] * s1;  d[13] = lev[10] * s2; d[10] = lev[11] * s0;
+    d[7] = lev[12] * s2;  d[11] = lev[13] * s1; d[14] = lev[14] * s1; d[15] = lev[15] * s2;
+    if (dcPreset) d[0] = dcValue;
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+        int t0 = d[i] + d[i + 2], t1 = d[i] - d[i + 2];
+        int t2 = (d[i + 1] >> 1) - d[i + 3], t3 = d[i + 1] + (d[i + 3] >> 1);
+        d[i] = t0 + t3; d[i + 1] = t1 + t2; d[i + 2] = t1 - t2; d[i + 3] = t0 - t3;
+    }
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int t0 = d[i] + d[i + 8], t1 = d[i] - d[i + 8];
+        int t2 = (d[i + 4] >> 1) - d[i + 12], t3 = d[i + 4] + (d[i + 12] >> 1);
+        out[i] = (t0 + t3 + 32) >> 6; out[i + 4] = (t1 + t2 + 32) >> 6;
+        out[i + 8] = (t1 - t2 + 32) >> 6; out[i + 12] = (t0 - t3 + 32) >> 6;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i++) bad |= (unsigned)(out[i] + 512) > 1023u;
+    return bad;
+}
+
+// h264bsdProcessLumaDc (transform.c:255-338); returns the element for DC-matrix raster index `pick`
+__device__ __forceinline__ int lumaDcPick(const int16_t *lev, int qp, int pick) {
+    int d[16];
+    d[0] = lev[0]; d[1] = lev[1]; d[4] = lev[2]; d[8] = lev[3]; d[5] = lev[4]; d[2] = lev[5]; d[3] = lev[6]; d[6] = lev[7];
+    d[9] = lev[8]; d[12] = lev[9]; d[13] = lev[10]; d[10] = lev[11]; d[7] = lev[12]; d[11] = lev[13]; d[14] = lev[14]; d[15] = lev[15];
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+        int t0 = d[i] + d[i + 2], t1 = d[i] - d[i + 2], t2 = d[i + 1] - d[i + 3], t3 = d[i + 1] + d[i + 3];
+        d[i] = t0 + t3; d[i + 1] = t1 + t2; d[i + 2] = t1 - t2; d[i + 3] = t0 - t3;
+    }
+    int v[16];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int t0 = d[i] + d[i + 8], t1 = d[i] - d[i + 8], t2 = d[i + 4] - d[i + 12], t3 = d[i + 4] + d[i + 12];
+        v[i] = t0 + t3; v[i + 4] = t1 + t2; v[i + 8] = t1 - t2; v[i + 12] = t0 - t3;
+    }
+    int sel = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) sel = (i == pick) ? v[i] : sel;
+    int qpDiv = qp / 6, ls = levelScale(qp - 6 * qpDiv, 0);
+    if (qp >= 12) return sel * (ls << (qpDiv - 2));
+    return (sel * ls + (qpDiv == 1 ? 1 : 2)) >> (2 - qpDiv);
+}
+
+// h264bsdProcessChromaDc (transform.c:359-401): lev[0..3] of one plane, element `pick`
+__device__ __forceinline__ int chromaDcPick(const int16_t *lev, int qp, int pick) {
+    int qpDiv = qp / 6, ls = levelScale(qp - 6 * qpDiv, 0), shift = 1;
+    if (qp >= 6) { ls <<= (qpDiv - 1); shift = 0; }
+    int t0 = lev[0] + lev[2], t1 = lev[0] - lev[2], t2 = lev[1] - lev[3], t3 = lev[1] + lev[3];
+    int v = pick == 0 ? t0 + t3 : pick == 1 ? t0 - t3 : pick == 2 ? t1 + t2 : t1 - t2;
+    return (v * ls) >> shift;
+}
+
+// ---- motion compensation from the staged window -----------------------------------------------------
+// window sample at picture position (xInt + dx, yInt + dy): `win` points at the sample (xInt-2, yInt-2) inside the box
+__device__ __forceinline__ int W_(const uint8_t *win, int dx, int dy) { return win[(dy + 2) * kLumaBoxW + dx + 2]; }
+__device__ __forceinline__ int tap6(int a, int b, int c, int d, int e, int f) { return a - 5 * b + 20 * c + 20 * d - 5 * e + f; }
+__device__ __forceinline__ int hsum(const uint8_t *win, int x, int y) {
+    return tap6(W_(win, x - 2, y), W_(win, x - 1, y), W_(win, x, y), W_(win, x + 1, y), W_(win, x + 2, y), W_(win, x + 3, y));
+}
+__device__ __forceinline__ int vsum(const uint8_t *win, int x, int y) {
+    return tap6(W_(win, x, y - 2), W_(win, x, y - 1), W_(win, x, y), W_(win, x, y + 1), W_(win, x, y + 2), W_(win, x, y + 3));
+}
+// clause 8.4.2.2.1; dispatch table of h264bsdPredictSamples (reconstruct.c:1848-1927)
+__device__ __forceinline__ int lumaQpel(const uint8_t *win, int x, int y, int xf, int yf) {
+    if ((xf | yf) == 0) return W_(win, x, y);
+    if (yf == 0) {
+        int b = clip255((hsum(win, x, y) + 16) >> 5);
+        if (xf == 2) return b;
+        return (b + W_(win, x + (xf >> 1), y) + 1) >> 1;
+    }
+    if (xf == 0) {
+        int h = clip255((vsum(win, x, y) + 16) >> 5);
+        if (yf == 2) return h;
+        return (h + W_(win, x, y + (yf >> 1)) + 1) >> 1;
+    }
+    if (xf != 2 && yf != 2) {
+        int b = clip255((hsum(win, x, y + (yf >> 1)) + 16) >> 5);
+        int h = clip255((vsum(win, x + (xf >> 1), y) + 16) >> 5);
+        return (b + h + 1) >> 1;
+    }
+    int j = clip255((tap6(hsum(win, x, y - 2), hsum(win, x, y - 1), hsum(win, x, y), hsum(win, x, y + 1),
+                          hsum(win, x, y + 2), hsum(win, x, y + 3)) + 512) >> 10);
+    if (xf == 2 && yf == 2) return j;
+    if (xf == 2) {
+        int b = clip255((hsum(win, x, y + (yf >> 1)) + 16) >> 5);
+        return (j + b + 1) >> 1;
+    }
+    int h = clip255((vsum(win, x + (xf >> 1), y) + 16) >> 5);
+    return (j + h + 1) >> 1;
+}
+
+// ---- Intra4x4 sample prediction (intra_prediction.c:1493-1830, clause 8.3.1.2) -----------------------
+// A(i): above row sample i in -1..7 (i >= 4 replicated from 3 when above-right is unavailable); L(i): left column
+template <typename FA, typename FL>
+__device__ __forceinline__ int intra4x4Pel(int mode, int x, int y, bool avA, bool avB, FA A, FL L) {
+    switch (mode) {
+        case 0: return A(x);
+        case 1: return L(y);
+        case 2: {
+            if (avA && avB) return (A(0) + A(1) + A(2) + A(3) + L(0) + L(1) + L(2) + L(3) + 4) >> 3;
+            if (avA) return (L(0) + L(1) + L(2) + L(3) + 2) >> 2;
+            if (avB) return (A(0) + A(1) + A(2) + A(3) + 2) >> 2;
+            return 128;
+        }
+        case 3:
+            if (x == 3 && y == 3) return (A(6) + 3 * A(7) + 2) >> 2;
+            return (A(x + y) + 2 * A(x + y + 1) + A(x + y + 2) + 2) >> 2;
+        case 4:
+            if (x > y) return (A(x - y - 2) + 2 * A(x - y - 1) + A(x - y) + 2) >> 2;
+            if (x < y) return ((y - x - 2 >= 0 ? L(y - x - 2) : A(-1)) + 2 * L(y - x - 1) + L(y - x) + 2) >> 2;
+            return (A(0) + 2 * A(-1) + L(0) + 2) >> 2;
+        case 5: {
+            int z = 2 * x - y, k = x - (y >> 1);
+            if (z >= 0 && !(z & 1)) return (A(k - 1) + A(k) + 1) >> 1;
+            if (z >= 0) return (A(k - 2) + 2 * A(k - 1) + A(k) + 2) >> 2;
+            if (z == -1) return (L(0) + 2 * A(-1) + A(0) + 2) >> 2;
+            return (L(y - 1) + 2 * L(y - 2) + (y - 3 >= 0 ? L(y - 3) : A(-1)) + 2) >> 2;
+        }
+        case 6: {
+            int z = 2 * y - x, k = y - (x >> 1);
+            if (z >= 0 && !(z & 1)) return ((k - 1 >= 0 ? L(k - 1) : A(-1)) + L(k) + 1) >> 1;
+            if (z >= 0) return ((k - 2 >= 0 ? L(k - 2) : A(-1)) + 2 * (k - 1 >= 0 ? L(k - 1) : A(-1)) + L(k) + 2) >> 2;
+            if (z == -1) return (L(0) + 2 * A(-1) + A(0) + 2) >> 2;
+            return (A(x - 1) + 2 * A(x - 2) + A(x - 3) + 2) >> 2;
+        }
+        case 7: {
+            int i = x + (y >> 1);
+            return (y & 1) ? (A(i) + 2 * A(i + 1) + A(i + 2) + 2) >> 2 : (A(i) + A(i + 1) + 1) >> 1;
+        }
+        default: {
+            int z = x + 2 * y, k = y + (x >> 1);
+            if (z > 5) return L(3);
+            if (z == 5) return (L(2) + 3 * L(3) + 2) >> 2;
+            if (z & 1) return (L(k) + 2 * L(k + 1) + L(k + 2) + 2) >> 2;
+            return (L(k) + L(k + 1) + 1) >> 1;
+        }
+    }
+}
+
+// =====================================================================================================
+__global__ void __launch_bounds__(kReconWarps * 32)
+reconKernel(const ReconParams p, const __grid_constant__ CUtensorMap lumaMap, const __grid_constant__ CUtensorMap chromaMap) {
+    __shared__ ReconWarpSmem smemAll[kReconWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    ReconWarpSmem &sm = smemAll[warp];
+    const PoolGeom &g = p.g;
+    if (lane == 0) {
+        mbarInit(&sm.mbar, 1);
+        fenceMbarInit();
+    }
+    __syncwarp();
+    uint32_t phase = 0;
+
+    for (;;) {
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(p.ticket, 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= p.totalTickets) break;
+        const uint32_t k = t / (uint32_t)g.nStreams, s = t - k * (uint32_t)g.nStreams;
+        const uint32_t mb = p.order[k];
+        const int mby = (int)(mb / (uint32_t)g.widthMbs), mbx = (int)(mb - (uint32_t)mby * g.widthMbs);
+        const StreamJob job = p.jobs[s];
+        const b200_mb_rec *rec = job.recs + mb;
+        uint32_t *doneS = p.done + (size_t)s * g.nMbs;
+        const uint32_t frameBase = s * (uint32_t)g.numSlots;
+        uint8_t *cur = framePtr(p.pool, g, frameBase + job.curSlot);
+
+        const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t *>(rec));  // mbType, qpY, qpC, flags
+        const int mbType = w0 & 0xFF, qpY = (w0 >> 8) & 0xFF, qpC = (w0 >> 16) & 0xFF, flags = w0 >> 24;
+        const uint32_t mask = __ldg(reinterpret_cast<const uint32_t *>(rec) + 1);
+        const uint32_t coefIndex = __ldg(reinterpret_cast<const uint32_t *>(rec) + 2);
+        const int16_t *coef = job.coefs + (size_t)coefIndex * 16;
+
+        // this lane's pels: luma row r8, columns c8..c8+7 ; chroma plane cp, row cr, columns cc..cc+3
+        const int r8 = lane >> 1, c8 = (lane & 1) * 8;
+        const int cp = lane >> 4, cr = (lane >> 1) & 7, cc = (lane & 1) * 4;
+        uint8_t *dstY = lumaAt(cur, g, mbx * 16 + c8, mby * 16 + r8);
+        uint8_t *dstC = chromaAt(cur, g, cp, mbx * 8 + cc, mby * 8 + cr);
+
+        if (mbType == B200_MB_I_PCM) {
+            // h264bsdWriteMacroblock (image.c:81-144): 384 raw bytes
+            const uint8_t *src = reinterpret_cast<const uint8_t *>(coef);
+            *reinterpret_cast<uint2 *>(dstY) = __ldg(reinterpret_cast<const uint2 *>(src + r8 * 16 + c8));
+            *reinterpret_cast<uint32_t *>(dstC) = __ldg(reinterpret_cast<const uint32_t *>(src + 256 + cp * 64 + cr * 8 + cc));
+        } else {
+            // ---------------- residual: one lane per 4x4 block -----------------------------------------
+            const bool i16 = mbType >= B200_MB_I_16x16_FIRST;
+            if (mask) {
+                if (lane < 24) {
+                    const int nDc = ((mask >> 24) & 1) + ((mask >> 25) & 1);
+                    const bool coded = (mask >> lane) & 1;
+                    int16_t lev[16];
+                    if (coded) {
+                        const uint4 *src = reinterpret_cast<const uint4 *>(coef + (size_t)(nDc + __popc(mask & ((1u << lane) - 1u))) * 16);
+                        uint4 a = __ldg(src), b = __ldg(src + 1);
+                        *reinterpret_cast<uint4 *>(lev) = a;
+                        *reinterpret_cast<uint4 *>(lev + 8) = b;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; i++) lev[i] = 0;
+                    }
+                    bool dcPreset = false;
+                    int dcVal = 0;
+                    if (lane < 16) {
+                        dcPreset = i16;
+                        if (i16 && (mask & B200_CM_LUMA_DC)) {
+                            int16_t dl[16];
+                            const uint4 *src = reinterpret_cast<const uint4 *>(coef);
+                            *reinterpret_cast<uint4 *>(dl) = __ldg(src);
+                            *reinterpret_cast<uint4 *>(dl + 8) = __ldg(src + 1);
+                            dcVal = lumaDcPick(dl, qpY, cBlkY[lane] * 4 + cBlkX[lane]);
+                        }
+                    } else {
+                        dcPreset = true;
+                        if (mask & B200_CM_CHROMA_DC) {
+                            int16_t dl[4];
+                            const uint2 *src = reinterpret_cast<const uint2 *>(coef + (size_t)((mask >> 24) & 1) * 16 + ((lane - 16) >> 2) * 4);
+                            *reinterpret_cast<uint2 *>(dl) = __ldg(src);
+                            dcVal = chromaDcPick(dl, qpC, lane & 3);
+                        }
+                    }
+                    int out[16];
+                    bool bad = false;
+                    if (coded || (dcPreset && dcVal != 0)) {
+                        bad = idctBlock(lev, lane < 16 ? qpY : qpC, dcPreset, dcVal, out);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; i++) out[i] = 0;
+                    }
+                    if (bad) atomicAdd(p.errors, 1u);
+                    int16_t *dst = sm.res[lane];
+#pragma unroll
+                    for (int i = 0; i < 16; i += 2)
+                        *reinterpret_cast<uint32_t *>(dst + i) = (uint32_t)(uint16_t)out[i] | ((uint32_t)(uint16_t)out[i + 1] << 16);
+                }
+                __syncwarp();
+            }
+
+            // this lane's residuals (zero when the macroblock has none)
+            int resY[8], resC[4];
+            if (mask) {
+                const int by = r8 >> 2, ry = r8 & 3, bx = (lane & 1) * 2;
+                const int16_t *ra = sm.res[cRasterToBlk[by * 4 + bx]] + ry * 4;
+                const int16_t *rb = sm.res[cRasterToBlk[by * 4 + bx + 1]] + ry * 4;
+#pragma unroll
+                for (int i = 0; i < 4; i++) { resY[i] = ra[i]; resY[4 + i] = rb[i]; }
+                const int16_t *rc = sm.res[16 + cp * 4 + (cr >> 2) * 2 + (lane & 1)] + (cr & 3) * 4;
+#pragma unroll
+                for (int i = 0; i < 4; i++) resC[i] = rc[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; i++) resY[i] = 0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) resC[i] = 0;
+            }
+
+            if (mbType <= B200_MB_P_8x8REF0) {
+                // ---------------- inter prediction (inter_prediction.c:361-482) ---------------------------
+                const uint32_t refSlots = __ldg(reinterpret_cast<const uint32_t *>(rec) + 4);
+                const uint32_t subTypes = (__ldg(reinterpret_cast<const uint32_t *>(rec) + 3) >> 24) & 0xFF;
+                const uint32_t *mvw = reinterpret_cast<const uint32_t *>(rec) + 8;
+                // enumerate partitions as (4x4 block index of its first block, width, height)
+                int nParts;
+                if (mbType <= B200_MB_P_16x16) nParts = 1;
+                else if (mbType <= B200_MB_P_8x16) nParts = 2;
+                else nParts = 16;  // walk all 4x4 blocks, skip those that are not a partition origin
+                for (int pi = 0; pi < nParts; pi++) {
+                    int blk, pw, ph;
+                    if (mbType <= B200_MB_P_16x16) { blk = 0; pw = 16; ph = 16; }
+                    else if (mbType == B200_MB_P_16x8) { blk = pi * 8; pw = 16; ph = 8; }
+                    else if (mbType == B200_MB_P_8x16) { blk = pi * 4; pw = 8; ph = 16; }
+                    else {
+                        blk = pi;
+                        const int sub = (subTypes >> (2 * (pi >> 2))) & 3, j = pi & 3;
+                        if (sub == 0) { if (j) continue; pw = 8; ph = 8; }
+                        else if (sub == 1) { if (j & 1) continue; pw = 8; ph = 4; }
+                        else if (sub == 2) { if (j & 2) continue; pw = 4; ph = 8; }
+                        else { pw = 4; ph = 4; }
+                    }
+                    const int px = cBlkX[blk] * 4, py = cBlkY[blk] * 4;
+                    const uint32_t mvv = __ldg(mvw + blk);
+                    const int mvx = (int)(int16_t)(mvv & 0xFFFF), mvy = (int)(int16_t)(mvv >> 16);
+                    const uint32_t refFrame = frameBase + ((refSlots >> (8 * (blk >> 2))) & 0xFF);
+                    const int xInt = mbx * 16 + px + (mvx >> 2), yInt = mby * 16 + py + (mvy >> 2);
+                    const int cxInt = ((mbx * 16 + px) >> 1) + (mvx >> 3), cyInt = ((mby * 16 + py) >> 1) + (mvy >> 3);
+                    // window origin in bordered-plane coordinates, clamped (see below); the box starts 16-byte aligned
+                    const int ox = clip3(-kPadY, g.W + kPadY - kLumaWin, xInt - 2) + kPadY;
+                    const int oy = clip3(-kPadY, g.H + kPadY - kLumaWin, yInt - 2) + kPadY;
+                    const int cox = clip3(-kPadC, g.W / 2 + kPadC - kChromaWin, cxInt) + kPadC;
+                    const int coy = clip3(-kPadC, g.H / 2 + kPadC - kChromaWin, cyInt) + kPadC;
+                    if (lane == 0) {
+                        fenceProxyAsync();
+                        mbarExpectTx(&sm.mbar, kLumaBoxW * kLumaBoxH + 2 * kChromaBoxW * kChromaBoxH);
+                        // clamp the box origin into the bordered plane: a box wholly outside the picture on an axis
+                        // equals the box at the clamped origin because the border is a replication
+                        tmaLoad3d(sm.lumaWin, &lumaMap, ox & ~15, oy, (int)refFrame, &sm.mbar);
+                        tmaLoad4d(sm.chromaWin, &chromaMap, cox & ~15, coy, 0, (int)refFrame, &sm.mbar);
+                    }
+                    mbarWait(&sm.mbar, phase);
+                    phase ^= 1;
+                    const int xf = mvx & 3, yf = mvy & 3;
+                    const int lw = 31 - __clz(pw);
+                    for (int i = lane; i < pw * ph; i += 32) {
+                        const int x = i & (pw - 1), y = i >> lw;
+                        sm.pred[(py + y) * 16 + px + x] = (uint8_t)lumaQpel(sm.lumaWin + (ox & 15), x, y, xf, yf);
+                    }
+                    const int cw = pw >> 1, chh = ph >> 1, ncp = cw * chh, lcw = lw - 1;
+                    const int cxf = mvx & 7, cyf = mvy & 7;
+                    for (int i = lane; i < 2 * ncp; i += 32) {
+                        const int pl = i >= ncp, ii = i - pl * ncp;
+                        const int x = ii & (cw - 1), y = ii >> lcw;
+                        const uint8_t *wp = sm.chromaWin + pl * (kChromaBoxW * kChromaBoxH) + y * kChromaBoxW + x + (cox & 15);
+                        const int A = wp[0], B = wp[1], C = wp[kChromaBoxW], D = wp[kChromaBoxW + 1];
+                        // PredictChroma (reconstruct.c:415-475)
+                        sm.pred[256 + pl * 64 + ((py >> 1) + y) * 8 + (px >> 1) + x] =
+                            (uint8_t)(((8 - cxf) * (8 - cyf) * A + cxf * (8 - cyf) * B + (8 - cxf) * cyf * C + cxf * cyf * D + 32) >> 6);
+                    }
+                    __syncwarp();
+                }
+                // add residual + clip + store (h264bsdWriteOutputBlocks, image.c:172-344)
+                const uint2 pv = *reinterpret_cast<const uint2 *>(sm.pred + r8 * 16 + c8);
+                uint32_t o0 = 0, o1 = 0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    o0 |= (uint32_t)clip255((int)((pv.x >> (8 * i)) & 0xFF) + resY[i]) << (8 * i);
+                    o1 |= (uint32_t)clip255((int)((pv.y >> (8 * i)) & 0xFF) + resY[4 + i]) << (8 * i);
+                }
+                *reinterpret_cast<uint2 *>(dstY) = make_uint2(o0, o1);
+                const uint32_t pc = *reinterpret_cast<const uint32_t *>(sm.pred + 256 + cp * 64 + cr * 8 + cc);
+                uint32_t oc = 0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) oc |= (uint32_t)clip255((int)((pc >> (8 * i)) & 0xFF) + resC[i]) << (8 * i);
+                *reinterpret_cast<uint32_t *>(dstC) = oc;
+                __syncwarp();
+            } else {
+                // ---------------- intra prediction (intra_prediction.c:478-533) ---------------------------
+                const bool avA = flags & B200_MBF_AVAIL_A, avB = flags & B200_MBF_AVAIL_B;
+                const bool avC = flags & B200_MBF_AVAIL_C, avD = flags & B200_MBF_AVAIL_D;
+                // wait until the neighbours this macroblock reads have been written (unfiltered picture)
+                if (lane < 4) {
+                    const bool need = lane == 0 ? avA : lane == 1 ? avB : lane == 2 ? avC : avD;
+                    if (need) {
+                        const int nmb = lane == 0 ? (int)mb - 1 : lane == 1 ? (int)mb - g.widthMbs : lane == 2 ? (int)mb - g.widthMbs + 1 : (int)mb - g.widthMbs - 1;
+                        waitFlag(doneS + nmb, p.serial);
+                    }
+                }
+                __syncwarp();
+                // neighbouring pels (h264bsdGetNeighbourPels :545-614), straight from L2
+                if (lane < 21) {
+                    const bool ok = lane == 0 ? avD : lane <= 16 ? avB : avC;
+                    sm.itY[0][lane] = ok ? __ldcg(lumaAt(cur, g, mbx * 16 - 1 + lane, mby * 16 - 1)) : 128;
+                }
+                if (lane < 16) sm.itY[1 + lane][0] = avA ? __ldcg(lumaAt(cur, g, mbx * 16 - 1, mby * 16 + lane)) : 128;
+                if (lane < 18) {
+                    const int pl = lane >= 9, i = lane - pl * 9;
+                    const bool ok = i == 0 ? avD : avB;
+                    sm.itC[pl][0][i] = ok ? __ldcg(chromaAt(cur, g, pl, mbx * 8 - 1 + i, mby * 8 - 1)) : 128;
+                }
+                if (lane < 16) {
+                    const int pl = lane >> 3, i = lane & 7;
+                    sm.itC[pl][1 + i][0] = avA ? __ldcg(chromaAt(cur, g, pl, mbx * 8 - 1, mby * 8 + i)) : 128;
+                }
+                __syncwarp();
+
+                if (mbType == B200_MB_I_4x4) {
+                    // h264bsdIntra4x4Prediction (:701-833): 16 sequential blocks; lanes 0..15 own one pel each
+                    const uint32_t *modew = reinterpret_cast<const uint32_t *>(rec) + 8;
+                    const int x = lane & 3, y = (lane >> 2) & 3;
+                    for (int b = 0; b < 16; b++) {
+                        const int bx = cBlkX[b], by = cBlkY[b];
+                        const int mode = (__ldg(modew + (b >> 2)) >> (8 * (b & 3))) & 0xFF;
+                        const bool bA = bx ? true : avA, bB = by ? true : avB;
+                        bool bC;
+                        if (by == 0) bC = (bx == 3) ? avC : avB;
+                        else if (bx == 3) bC = false;
+                        else bC = cRasterToBlk[(by - 1) * 4 + bx + 1] < b;
+                        if (lane < 16) {
+                            const uint8_t *above = &sm.itY[by * 4][bx * 4 + 1];   // above[i] = sample (i, -1)
+                            const uint8_t *left = &sm.itY[by * 4 + 1][bx * 4];    // left[i*24] = sample (-1, i)
+                            auto A = [&](int i) -> int { return above[(i > 3 && !bC) ? 3 : i]; };
+                            auto L = [&](int i) -> int { return left[i * 24]; };
+                            int v = intra4x4Pel(mode, x, y, bA, bB, A, L);
+                            if (mask) v = clip255(v + sm.res[b][y * 4 + x]);
+                            sm.pred[lane] = (uint8_t)v;
+                        }
+                        __syncwarp();
+                        if (lane < 16) sm.itY[by * 4 + 1 + y][bx * 4 + 1 + x] = sm.pred[lane];
+                        __syncwarp();
+                    }
+                    uint32_t o0 = 0, o1 = 0;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        o0 |= (uint32_t)sm.itY[1 + r8][1 + c8 + i] << (8 * i);
+                        o1 |= (uint32_t)sm.itY[1 + r8][1 + c8 + 4 + i] << (8 * i);
+                    }
+                    *reinterpret_cast<uint2 *>(dstY) = make_uint2(o0, o1);
+                } else {
+                    // h264bsdIntra16x16Prediction (:627-687)
+                    const int mode = (mbType - B200_MB_I_16x16_FIRST) & 3;
+                    int pv[8];
+                    if (mode == 0) {
+#pragma unroll
+                        for (int i = 0; i < 8; i++) pv[i] = sm.itY[0][1 + c8 + i];
+                    } else if (mode == 1) {
+#pragma unroll
+                        for (int i = 0; i < 8; i++) pv[i] = sm.itY[1 + r8][0];
+                    } else if (mode == 2) {
+                        int sa = 0, sl = 0;
+                        for (int i = 0; i < 16; i++) { sa += sm.itY[0][1 + i]; sl += sm.itY[1 + i][0]; }
+                        int v = (avA && avB) ? (sa + sl + 16) >> 5 : avA ? (sl + 8) >> 4 : avB ? (sa + 8) >> 4 : 128;
+#pragma unroll
+                        for (int i = 0; i < 8; i++) pv[i] = v;
+                    } else {
+                        int Hh = 0, V = 0;
+                        for (int i = 0; i < 8; i++) {
+                            Hh += (i + 1) * ((int)sm.itY[0][1 + 8 + i] - (int)sm.itY[0][1 + 6 - i]);
+                            V += (i + 1) * ((int)sm.itY[1 + 8 + i][0] - (int)sm.itY[1 + 6 - i][0]);
+                        }
+                        const int a = 16 * ((int)sm.itY[16][0] + (int)sm.itY[0][16]);
+                        const int bb = (5 * Hh + 32) >> 6, cc2 = (5 * V + 32) >> 6;
+#pragma unroll
+                        for (int i = 0; i < 8; i++) pv[i] = clip255((a + bb * (c8 + i - 7) + cc2 * (r8 - 7) + 16) >> 5);
+                    }
+                    uint32_t o0 = 0, o1 = 0;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        o0 |= (uint32_t)clip255(pv[i] + resY[i]) << (8 * i);
+                        o1 |= (uint32_t)clip255(pv[4 + i] + resY[4 + i]) << (8 * i);
+                    }
+                    *reinterpret_cast<uint2 *>(dstY) = make_uint2(o0, o1);
+                }
+                // h264bsdIntraChromaPrediction (:845-915)
+                {
+                    const int cmode = (__ldg(reinterpret_cast<const uint32_t *>(rec) + 5)) & 0xFF;
+                    const uint8_t(*tc)[12] = sm.itC[cp];
+                    int pv[4];
+                    if (cmode == 0) {
+                        const int bxq = lane & 1, byq = cr >> 2;
+                        int sa = 0, sl = 0;
+#pragma unroll
+                        for (int i = 0; i < 4; i++) { sa += tc[0][1 + bxq * 4 + i]; sl += tc[1 + byq * 4 + i][0]; }
+                        int v;
+                        if (bxq == byq) v = (avA && avB) ? (sa + sl + 4) >> 3 : avB ? (sa + 2) >> 2 : avA ? (sl + 2) >> 2 : 128;
+                        else if (bxq == 1) v = avB ? (sa + 2) >> 2 : avA ? (sl + 2) >> 2 : 128;
+                        else v = avA ? (sl + 2) >> 2 : avB ? (sa + 2) >> 2 : 128;
+#pragma unroll
+                        for (int i = 0; i < 4; i++) pv[i] = v;
+                    } else if (cmode == 1) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) pv[i] = tc[1 + cr][0];
+                    } else if (cmode == 2) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) pv[i] = tc[0][1 + cc + i];
+                    } else {
+                        int Hh = 0, V = 0;
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            Hh += (i + 1) * ((int)tc[0][1 + 4 + i] - (int)tc[0][1 + 2 - i]);
+                            V += (i + 1) * ((int)tc[1 + 4 + i][0] - (int)tc[1 + 2 - i][0]);
+                        }
+                        const int a = 16 * ((int)tc[8][0] + (int)tc[0][8]);
+                        const int bb = (17 * Hh + 16) >> 5, cc2 = (17 * V + 16) >> 5;
+#pragma unroll
+                        for (int i = 0; i < 4; i++) pv[i] = clip255((a + bb * (cc + i - 3) + cc2 * (cr - 3) + 16) >> 5);
+                    }
+                    uint32_t oc = 0;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) oc |= (uint32_t)clip255(pv[i] + resC[i]) << (8 * i);
+                    *reinterpret_cast<uint32_t *>(dstC) = oc;
+                }
+                __syncwarp();
+            }
+        }
+        // publish: every lane's stores, then the flag
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) stRelease(doneS + mb, p.serial);
+    }
+}
+
+}  // namespace b200

@@ -25,6 +25,53 @@ extern "C" {
 b200_tape *h264bsdB200ParseStream(const uint8_t *stream, size_t len, uint32_t noOutputReordering);
 void h264bsdB200FreeTape(b200_tape *tape);
 
+/* ---- GPU (fail loudly -- NULL / -1 and a message on stderr -- when no CUDA device is usable) ---- */
+
+typedef struct b200_batch b200_batch;
+
+int h264bsdB200DeviceCount(void);
+
+/* nStreams independent streams of one geometry on GPU `device`; numSlots frame slots per stream
+ * (tape->numSlots = dpbSize+1, what h264bsdInitDpb allocates: h264bsd_dpb.c:1014-1034). */
+b200_batch *h264bsdB200BatchCreate(int device, uint32_t nStreams, uint32_t widthMbs, uint32_t heightMbs, uint32_t numSlots);
+void h264bsdB200BatchDestroy(b200_batch *batch);
+
+/* copy a parsed tape into HBM as stream `stream`'s work-list (host -> device) */
+int h264bsdB200BatchUploadTape(b200_batch *batch, uint32_t stream, const b200_tape *tape);
+/* give every other stream its own HBM copy of stream `srcStream`'s work-list (device -> device) */
+int h264bsdB200BatchReplicateTape(b200_batch *batch, uint32_t srcStream);
+
+/* reconstruct + in-loop filter + border for picture `picIndex` of EVERY stream (asynchronous).
+ * Replaces, per macroblock, h264bsdDecodeMacroblock's pixel half (macroblock_layer.c:965-1131) and,
+ * per picture, h264bsdFilterPicture (deblocking.c:575-640). */
+int h264bsdB200BatchDecodePicture(b200_batch *batch, uint32_t picIndex);
+int h264bsdB200BatchRun(b200_batch *batch, uint32_t firstPic, uint32_t numPics);
+int h264bsdB200BatchSync(b200_batch *batch);
+uint32_t h264bsdB200BatchNumPics(b200_batch *batch);
+
+/* CUDA-event timing on the engine's own stream */
+int h264bsdB200BatchTimerStart(b200_batch *batch);
+int h264bsdB200BatchTimerStop(b200_batch *batch, float *ms);
+
+/* frame slot -> contiguous I420 of the coded size (widthMbs*heightMbs*384 bytes), as
+ * h264bsdNextOutputPicture hands out (decoder.c:599-623); and the reverse (test hook) */
+int h264bsdB200BatchReadFrame(b200_batch *batch, uint32_t stream, uint32_t slot, uint8_t *dst);
+int h264bsdB200BatchWriteFrame(b200_batch *batch, uint32_t stream, uint32_t slot, const uint8_t *src);
+/* h264bsdConvertTo{RGBA(0),BGRA(1),YCbCrA(2)} of a frame slot (decoder.c:1163-1370) into host memory */
+int h264bsdB200BatchConvertFrame(b200_batch *batch, uint32_t stream, uint32_t slot, int mode, uint32_t *dst);
+int h264bsdB200BatchConvertBench(b200_batch *batch, uint32_t stream, uint32_t slot, int mode, int reps, float *ms);
+/* number of streams whose frame in slots[s] differs from stream 0's frame in slots[0]; <0 on error */
+int h264bsdB200BatchCompareStreams(b200_batch *batch, const uint32_t *slots);
+/* run only some stages of a picture (test hook) */
+int h264bsdB200BatchDebugStage(b200_batch *batch, uint32_t picIndex, int recon, int deblock);
+/* blocks whose residual left [-512,511] since creation (h264bsd_transform.c:183-188 error return) */
+uint32_t h264bsdB200BatchIdctErrors(b200_batch *batch);
+/* waits inside the kernels that gave up (0: macroblock-flag waits, 1: TMA waits); non-zero = engine bug */
+uint32_t h264bsdB200BatchWatchdog(b200_batch *batch, int which);
+uint64_t h264bsdB200BatchLaunches(b200_batch *batch);
+uint64_t h264bsdB200BatchH2DBytes(b200_batch *batch);
+uint64_t h264bsdB200BatchD2HBytes(b200_batch *batch);
+
 #ifdef __cplusplus
 }
 #endif

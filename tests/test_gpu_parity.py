@@ -1,0 +1,181 @@
+"""GPU suite: the CUDA engine, called through the C-ABI, against the golden vectors of the reference and
+against the CPU oracle.  Bit-exact or fail."""
+import ctypes as C
+import hashlib
+import json
+import os
+import numpy as np
+import pytest
+import _oracle
+from h264bsd_b200 import _lib
+from h264bsd_b200.batch import Batch, ParsedStream
+from h264bsd_b200.decoder import H264bsdDecoder, decode_stream, PIC_RDY, HDRS_RDY
+
+pytestmark = pytest.mark.gpu
+
+GOLD = json.load(open(os.path.join(_oracle.GOLDEN, "md5.json")))
+STREAMS = list(GOLD.keys())
+
+
+def md5(a):
+    return hashlib.md5(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def parsed():
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            cache[name] = ParsedStream(_oracle.stream_bytes(name))
+        return cache[name]
+    return get
+
+
+def test_gpu_present_and_native_library_loaded():
+    L = _lib.load()
+    assert L.h264bsdB200DeviceCount() >= 1
+    assert os.path.basename(_lib.LIB_PATH) == "libh264bsd_b200.so"
+
+
+@pytest.mark.parametrize("name", STREAMS)
+def test_legacy_api_bit_exact(name):
+    """config 2 of BASELINE.json: the stream through h264bsdInit/Decode/NextOutputPicture/Shutdown, every frame
+    at full coded size compared with the reference decoder's (posix/test_h264bsd.c:146-177 loop)"""
+    g = GOLD[name]
+    frames = decode_stream(_oracle.stream_bytes(name))
+    assert len(frames) == g["pictures"]
+    for k, f in enumerate(frames):
+        assert md5(f) == g["post_frame_md5"][k], f"{name}: output picture {k} differs from the reference"
+    h = hashlib.md5()
+    for f in frames:
+        h.update(f.tobytes())
+    assert h.hexdigest() == g["post_md5"]
+
+
+def test_legacy_api_getters_and_headers_ready():
+    d = H264bsdDecoder()
+    d.queueInput(_oracle.stream_bytes("test_640x360.h264"))
+    seen_hdrs = 0
+    pics = 0
+    while d.inputBytesRemaining() > 0:
+        r = d.decode()
+        if r == HDRS_RDY:
+            seen_hdrs += 1
+            assert (d.outputPictureWidth(), d.outputPictureHeight()) == (640, 368)
+            assert d.croppingParams() == {"left": 0, "width": 640, "top": 0, "height": 360}
+        elif r == PIC_RDY:
+            assert d.nextOutputPicture() is not None
+            assert d.nextOutputPicture() is None  # exactly one picture per PIC_RDY when nothing is reordered
+            pics += 1
+        assert r in (0, 1, 2)
+    assert seen_hdrs == 1 and pics == 73
+    assert d.videoRange() == 0
+    d.release()
+    d2 = H264bsdDecoder()
+    d2.queueInput(_oracle.stream_bytes("test_1920x1080_fullRange.h264")[:200000])
+    while d2.inputBytesRemaining() > 0 and d2.decode() != PIC_RDY:
+        pass
+    assert d2.videoRange() == 1
+    d2.release()
+
+
+@pytest.mark.parametrize("name,pics", [("test_640x360.h264", list(range(0, 10)) + [39, 40, 41, 72]),
+                                       ("test_1920x1080.h264", [0, 1, 2, 40, 41])])
+def test_stages_in_isolation_vs_oracle(parsed, name, pics):
+    """reconstruction and in-loop filter each checked alone: the GPU gets the oracle's frames as input state"""
+    ps = parsed(name)
+    orc = _oracle.OracleDecoder(ps)
+    b = Batch(1, ps.width_mbs, ps.height_mbs, ps.num_slots)
+    b.upload(0, ps)
+    for k in range(max(pics) + 1):
+        h = ps.pics[k]
+        if k in pics:
+            for s in range(ps.num_slots):
+                b.write_frame(0, s, orc.frame(s))
+        orc.recon(k)
+        if k in pics:
+            pre = orc.frame(h.curSlot).copy()
+            b.debug_stage(k, True, False)
+            assert np.array_equal(b.read_frame(0, h.curSlot), pre), f"{name}: reconstruction of picture {k}"
+            assert md5(pre) == GOLD[name]["pre_frame_md5"][k]
+        orc.deblock(k)
+        if k in pics:
+            b.write_frame(0, h.curSlot, pre)
+            b.debug_stage(k, False, True)
+            assert np.array_equal(b.read_frame(0, h.curSlot), orc.frame(h.curSlot)), f"{name}: deblocking of picture {k}"
+    assert b.idct_errors() == 0 and b.watchdog() == (0, 0)
+    b.close()
+
+
+@pytest.mark.parametrize("name,n_streams", [("test_640x360.h264", 16), ("test_1920x1080.h264", 8)])
+def test_batch_of_replicated_streams(parsed, name, n_streams):
+    """many independent instances of one stream, each with its own HBM work-list and frame slots: every picture
+    of the first instance matches the reference, every other instance matches the first"""
+    ps = parsed(name)
+    g = GOLD[name]
+    b = Batch(n_streams, ps.width_mbs, ps.height_mbs, ps.num_slots)
+    b.upload(0, ps)
+    b.replicate(0)
+    for k in range(ps.num_pics):
+        b.decode_picture(k)
+        slot = ps.pics[k].curSlot
+        if k % 6 == 0 or k == ps.num_pics - 1:
+            assert md5(b.read_frame(0, slot)) == g["post_frame_md5"][k], f"picture {k}"
+            assert md5(b.read_frame(n_streams - 1, slot)) == g["post_frame_md5"][k], f"picture {k}, last instance"
+            assert b.compare_streams([slot] * n_streams) == 0
+    assert b.idct_errors() == 0 and b.watchdog() == (0, 0)
+    b.close()
+
+
+def test_looped_stream_is_idempotent(parsed):
+    """looping the tape (what the throughput bench does) leaves every slot as after the first pass"""
+    ps = parsed("test_640x360.h264")
+    b = Batch(4, ps.width_mbs, ps.height_mbs, ps.num_slots)
+    b.upload(0, ps)
+    b.replicate(0)
+    b.run(0, ps.num_pics)
+    first = [b.read_frame(1, s).copy() for s in range(ps.num_slots)]
+    for _ in range(2):
+        b.run(0, ps.num_pics)
+    for s in range(ps.num_slots):
+        assert np.array_equal(b.read_frame(2, s), first[s])
+    assert md5(first[ps.pics[-1].curSlot]) == GOLD["test_640x360.h264"]["post_frame_md5"][-1]
+    b.close()
+
+
+@pytest.mark.parametrize("name", [STREAMS[0], STREAMS[2]])
+def test_colour_conversion_kernel(parsed, name):
+    """config 5: YUV -> 32-bit pixels, against h264bsdConvertToRGBA/BGRA of the reference (golden md5) and the oracle"""
+    ps = parsed(name)
+    g = GOLD[name]
+    W, H = ps.width_mbs * 16, ps.height_mbs * 16
+    b = Batch(1, ps.width_mbs, ps.height_mbs, ps.num_slots)
+    b.upload(0, ps)
+    h = hashlib.md5()
+    for k in range(2):
+        b.decode_picture(k)
+        yuv = b.read_frame(0, ps.pics[k].curSlot)
+        for mode in (0, 1):
+            px = b.convert_frame(0, ps.pics[k].curSlot, mode)
+            assert np.array_equal(px, _oracle.oracle_convert(mode, W, H, yuv))
+            h.update(px.tobytes())
+        assert np.array_equal(b.convert_frame(0, ps.pics[k].curSlot, 2), _oracle.oracle_convert(2, W, H, yuv))
+    assert h.hexdigest() == g["rgba_bgra_first2_md5"]
+    b.close()
+    # the same through the preserved entry points
+    L = _lib.load()
+    out = np.empty(W * H, np.uint32)
+    yuv = np.ascontiguousarray(yuv)
+    for mode, fn in ((0, L.h264bsdConvertToRGBA), (1, L.h264bsdConvertToBGRA), (2, L.h264bsdConvertToYCbCrA)):
+        fn(W, H, yuv.ctypes.data, out.ctypes.data)
+        assert np.array_equal(out, _oracle.oracle_convert(mode, W, H, yuv))
+    d = H264bsdDecoder()
+    d.queueInput(_oracle.stream_bytes(name))
+    while d.decode() != PIC_RDY:
+        pass
+    rgba = d.nextOutputPictureRGBA()
+    d.release()
+    frames0 = decode_stream(_oracle.stream_bytes(name)[:400000])[0] if name == STREAMS[0] else None
+    if frames0 is not None:
+        assert np.array_equal(rgba, _oracle.oracle_convert(0, W, H, frames0))
