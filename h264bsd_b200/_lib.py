@@ -48,7 +48,7 @@ BATCH_SYMBOLS = [
     "h264bsdB200BatchDecodePicture", "h264bsdB200BatchRun", "h264bsdB200BatchSync", "h264bsdB200BatchNumPics",
     "h264bsdB200BatchTimerStart", "h264bsdB200BatchTimerStop", "h264bsdB200BatchReadFrame", "h264bsdB200BatchWriteFrame",
     "h264bsdB200BatchConvertFrame", "h264bsdB200BatchConvertBench", "h264bsdB200BatchCompareStreams",
-    "h264bsdB200BatchDebugStage", "h264bsdB200BatchIdctErrors", "h264bsdB200BatchWatchdog", "h264bsdB200BatchLaunches", "h264bsdB200BatchH2DBytes",
+    "h264bsdB200BatchDebugStage", "h264bsdB200BatchIdctErrors", "h264bsdB200BatchWatchdog", "h264bsdB200BatchKernelTiming", "h264bsdB200BatchKernelTimes", "h264bsdB200BatchLaunches", "h264bsdB200BatchH2DBytes",
     "h264bsdB200BatchD2HBytes",
 ]
 
@@ -105,6 +105,8 @@ def load():
     L.h264bsdB200BatchCompareStreams.restype = C.c_int; L.h264bsdB200BatchCompareStreams.argtypes = [vp, u32p]
     L.h264bsdB200BatchDebugStage.restype = C.c_int; L.h264bsdB200BatchDebugStage.argtypes = [vp, u32, C.c_int, C.c_int]
     L.h264bsdB200BatchIdctErrors.restype = u32; L.h264bsdB200BatchIdctErrors.argtypes = [vp]
+    L.h264bsdB200BatchKernelTiming.restype = None; L.h264bsdB200BatchKernelTiming.argtypes = [vp, C.c_int]
+    L.h264bsdB200BatchKernelTimes.restype = C.c_int; L.h264bsdB200BatchKernelTimes.argtypes = [vp, C.POINTER(C.c_float), u32p]
     L.h264bsdB200BatchWatchdog.restype = u32; L.h264bsdB200BatchWatchdog.argtypes = [vp, C.c_int]
     for n in ("h264bsdB200BatchLaunches", "h264bsdB200BatchH2DBytes", "h264bsdB200BatchD2HBytes"):
         getattr(L, n).restype = C.c_uint64; getattr(L, n).argtypes = [vp]

@@ -113,6 +113,16 @@ class Batch:
     def idct_errors(self):
         return self._L.h264bsdB200BatchIdctErrors(self.h)
 
+    def kernel_timing(self, enable):
+        self._L.h264bsdB200BatchKernelTiming(self.h, int(enable))
+
+    def kernel_times(self):
+        """({'recon': ms, 'deblock': ms, 'border': ms}, launches per stage) since the last call"""
+        ms = (C.c_float * 3)()
+        n = (C.c_uint32 * 3)()
+        self._ck(self._L.h264bsdB200BatchKernelTimes(self.h, ms, n), 'kernel_times')
+        return {'recon': ms[0], 'deblock': ms[1], 'border': ms[2]}, {'recon': n[0], 'deblock': n[1], 'border': n[2]}
+
     def watchdog(self):
         return (self._L.h264bsdB200BatchWatchdog(self.h, 0), self._L.h264bsdB200BatchWatchdog(self.h, 1))
 

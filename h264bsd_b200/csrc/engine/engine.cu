@@ -58,6 +58,10 @@ void Batch::destroy() {
     cudaFree(dJobs_); cudaFree(dStage_[0]); cudaFree(dStage_[1]); cudaFree(dConvert_); cudaFree(dSlots_);
     if (hStage_[0]) cudaFreeHost(hStage_[0]);
     if (hStage_[1]) cudaFreeHost(hStage_[1]);
+    for (cudaEvent_t e : evPool_) cudaEventDestroy(e);
+    evPool_.clear(); evStage_.clear();
+    if (hbHost_) cudaFreeHost(hbHost_);
+    hbHost_ = nullptr;
     if (evA_) cudaEventDestroy(evA_);
     if (evB_) cudaEventDestroy(evB_);
     if (stream_) cudaStreamDestroy(stream_);
@@ -226,9 +230,49 @@ bool Batch::buildJobs() {
     return true;
 }
 
+cudaEvent_t Batch::nextEvent() {
+    if (evUsed_ == evPool_.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        evPool_.push_back(e);
+        evStage_.push_back(-1);
+    }
+    return evPool_[evUsed_++];
+}
+
+void Batch::kernelTiming(bool enable) {
+    timing_ = enable;
+    evUsed_ = 0;
+}
+
+bool Batch::kernelTimes(float ms[3], uint32_t *launchesPerStage) {
+    CK(cudaSetDevice(device_));
+    CK(cudaStreamSynchronize(stream_));
+    ms[0] = ms[1] = ms[2] = 0.f;
+    uint32_t n[3] = {0, 0, 0};
+    for (size_t i = 1; i < evUsed_; i++) {
+        const int st = evStage_[i];
+        if (st < 0) continue;
+        float d = 0.f;
+        CK(cudaEventElapsedTime(&d, evPool_[i - 1], evPool_[i]));
+        ms[st] += d;
+        n[st]++;
+    }
+    if (launchesPerStage) { launchesPerStage[0] = n[0]; launchesPerStage[1] = n[1]; launchesPerStage[2] = n[2]; }
+    evUsed_ = 0;
+    return true;
+}
+
 bool Batch::launchPicture(const StreamJob *dJobs, bool recon, bool deblock) {
     const uint32_t total = (uint32_t)g_.nStreams * (uint32_t)g_.nMbs;
     serial_++;
+    auto mark = [&](int stageEnded) {
+        if (!timing_) return;
+        cudaEvent_t e = nextEvent();
+        evStage_[evUsed_ - 1] = stageEnded;
+        cudaEventRecord(e, stream_);
+    };
+    mark(-1);
     if (recon) {
         ReconParams rp;
         rp.pool = pool_; rp.g = g_; rp.jobs = dJobs; rp.order = dOrder_; rp.done = dDoneRecon_;
@@ -236,6 +280,7 @@ bool Batch::launchPicture(const StreamJob *dJobs, bool recon, bool deblock) {
         const int blocks = (int)std::min<uint32_t>((uint32_t)reconBlocks_, (total + kReconWarps - 1) / kReconWarps);
         reconKernel<<<blocks, kReconWarps * 32, 0, stream_>>>(rp, lumaMap_, chromaMap_);
         launches_++;
+        mark(0);
     }
     if (deblock) {
         DeblockParams dp;
@@ -244,6 +289,7 @@ bool Batch::launchPicture(const StreamJob *dJobs, bool recon, bool deblock) {
         const int blocks = (int)std::min<uint32_t>((uint32_t)deblockBlocks_, (total + kDeblockWarps - 1) / kDeblockWarps);
         deblockKernel<<<blocks, kDeblockWarps * 32, 0, stream_>>>(dp);
         launches_++;
+        mark(1);
     }
     {
         BorderParams bp;
@@ -252,6 +298,7 @@ bool Batch::launchPicture(const StreamJob *dJobs, bool recon, bool deblock) {
         const int blocks = (int)((rows + 7) / 8);
         borderKernel<<<blocks, 256, 0, stream_>>>(bp);
         launches_++;
+        mark(2);
     }
     CK(cudaMemsetAsync(dCounters_, 0, 2 * sizeof(uint32_t), stream_));
     CK(cudaGetLastError());

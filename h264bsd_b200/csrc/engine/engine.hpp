@@ -37,6 +37,9 @@ public:
     bool convertFrame(uint32_t stream, uint32_t slot, int mode, uint32_t *dstHost);
     bool convertBench(uint32_t stream, uint32_t slot, int mode, int reps, float *ms);
     int compareStreams(const uint32_t *slots);
+    // per-stage device time (CUDA events on the engine's stream around every launch)
+    void kernelTiming(bool enable);
+    bool kernelTimes(float ms[3], uint32_t *launchesPerStage);  // recon, deblock, border; resets the accumulators
     uint32_t idctErrors();
     uint32_t watchdog(int which);  // 0: flag waits that gave up, 1: TMA waits that gave up
 
@@ -81,6 +84,11 @@ private:
     int stageIdx_ = 0;
     uint32_t *dConvert_ = nullptr;
     uint64_t launches_ = 0, h2dBytes_ = 0, d2hBytes_ = 0;
+    bool timing_ = false;
+    std::vector<cudaEvent_t> evPool_;
+    size_t evUsed_ = 0;
+    std::vector<int> evStage_;  // stage id of the interval that ENDS at event i (or -1)
+    cudaEvent_t nextEvent();
     uint32_t *hbHost_ = nullptr, *hbDev_ = nullptr;  // debug heartbeat (env H264BSD_B200_HEARTBEAT)
 public:
     const uint32_t *heartbeat() const { return hbHost_; }
