@@ -18,7 +18,8 @@ class PicHdr(C.Structure):
         ("widthMbs", C.c_uint32), ("heightMbs", C.c_uint32), ("curSlot", C.c_uint32), ("numSlots", C.c_uint32),
         ("picIndex", C.c_uint32), ("isIdr", C.c_uint32), ("isRef", C.c_uint32), ("numCoefBlocks", C.c_uint32),
         ("mbRecOffset", C.c_uint64), ("coefOffset", C.c_uint64), ("numErrMbs", C.c_uint32), ("numOut", C.c_uint32),
-        ("outSlot", C.c_uint8 * 20), ("outPicIndex", C.c_uint32 * 20), ("picId", C.c_uint32), ("reserved", C.c_uint32 * 3),
+        ("outSlot", C.c_uint8 * 20), ("outPicIndex", C.c_uint32 * 20), ("picId", C.c_uint32), ("numPassA", C.c_uint32),
+        ("numPassB", C.c_uint32), ("reserved", C.c_uint32),
     ]
 
 
@@ -29,6 +30,7 @@ class Tape(C.Structure):
         ("cropHeight", C.c_uint32), ("videoRange", C.c_uint32), ("matrixCoefficients", C.c_uint32), ("reserved", C.c_uint32),
         ("mbRecBytes", C.c_uint64), ("coefBytes", C.c_uint64),
         ("pics", C.POINTER(PicHdr)), ("mbRecs", C.POINTER(C.c_uint8)), ("coefs", C.POINTER(C.c_uint8)),
+        ("mbOrder", C.POINTER(C.c_uint16)),
         ("numOutputs", C.c_uint32), ("reserved2", C.c_uint32), ("outputPicIndex", C.POINTER(C.c_uint32)),
         ("status", C.c_uint32), ("reserved3", C.c_uint32),
     ]

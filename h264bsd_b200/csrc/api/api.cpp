@@ -57,8 +57,8 @@ struct LegacyDecoder : public PictureSink {
             if (cudaMallocHost(&hostFrames[i], batch.frameBytes()) != cudaSuccess) { failed = true; return false; }
         return true;
     }
-    bool submitPicture(const b200_pic_hdr &hdr, const b200_mb_rec *recs, const int16_t *coefs) override {
-        if (!batch.submitHostPicture(0, hdr, recs, coefs)) { failed = true; return false; }
+    bool submitPicture(const b200_pic_hdr &hdr, const b200_mb_rec *recs, const int16_t *coefs, const uint16_t *order) override {
+        if (!batch.submitHostPicture(0, hdr, recs, coefs, order)) { failed = true; return false; }
         return true;
     }
 };
@@ -239,7 +239,7 @@ int h264bsdB200BatchCompareStreams(b200_batch *h, const uint32_t *slots) { retur
 int h264bsdB200BatchDebugStage(b200_batch *h, uint32_t picIndex, int recon, int deblock) { return h && B(h)->debugStage(picIndex, recon != 0, deblock != 0) ? 0 : -1; }
 uint32_t h264bsdB200BatchIdctErrors(b200_batch *h) { return h ? B(h)->idctErrors() : 0; }
 void h264bsdB200BatchKernelTiming(b200_batch *h, int enable) { if (h) B(h)->kernelTiming(enable != 0); }
-int h264bsdB200BatchKernelTimes(b200_batch *h, float *ms3, uint32_t *launches3) { return h && ms3 && B(h)->kernelTimes(ms3, launches3) ? 0 : -1; }
+int h264bsdB200BatchKernelTimes(b200_batch *h, float *ms4, uint32_t *launches4) { return h && ms4 && B(h)->kernelTimes(ms4, launches4) ? 0 : -1; }
 uint32_t h264bsdB200BatchWatchdog(b200_batch *h, int which) { return h ? B(h)->watchdog(which) : 0; }
 const uint32_t *h264bsdB200BatchHeartbeat(b200_batch *h) { return h ? B(h)->heartbeat() : nullptr; }
 uint64_t h264bsdB200BatchLaunches(b200_batch *h) { return h ? B(h)->launches() : 0; }

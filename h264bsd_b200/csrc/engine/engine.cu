@@ -51,7 +51,7 @@ void Batch::destroy() {
     cudaSetDevice(device_);
     cudaStreamSynchronize(stream_);
     for (auto &t : tapes_) {
-        if (t.owned) { cudaFree(t.recs); cudaFree(t.coefs); }
+        if (t.owned) { cudaFree(t.recs); cudaFree(t.coefs); cudaFree(t.order); }
     }
     tapes_.clear();
     cudaFree(pool_); cudaFree(dOrder_); cudaFree(dDoneRecon_); cudaFree(dDoneDeblock_); cudaFree(dCounters_);
@@ -153,8 +153,8 @@ bool Batch::create(int device, uint32_t nStreams, uint32_t widthMbs, uint32_t he
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { std::fprintf(stderr, "h264bsd_b200: chroma tensor map failed (%d)\n", (int)r); return false; }
     }
-    int occR = 0, occD = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occR, reconKernel, kReconWarps * 32, 0));
+    int occR = 1, occD = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occR, reconInterKernel, kReconWarps * 32, 0));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occD, deblockKernel, kDeblockWarps * 32, 0));
     reconBlocks_ = std::max(1, occR) * numSms_;
     deblockBlocks_ = std::max(1, occD) * numSms_;
@@ -168,17 +168,20 @@ bool Batch::uploadTape(uint32_t stream, const b200_tape *t) {
     if (t->widthMbs != (uint32_t)g_.widthMbs || t->heightMbs != (uint32_t)g_.heightMbs || t->numSlots > (uint32_t)g_.numSlots) return false;
     CK(cudaSetDevice(device_));
     DevTape &d = tapes_[stream];
-    if (d.owned) { cudaFree(d.recs); cudaFree(d.coefs); }
+    if (d.owned) { cudaFree(d.recs); cudaFree(d.coefs); cudaFree(d.order); }
     d = DevTape();
+    const size_t orderBytes = (size_t)t->numPics * g_.nMbs * sizeof(uint16_t);
     CK(cudaMalloc(&d.recs, t->mbRecBytes + 256));
     CK(cudaMalloc(&d.coefs, t->coefBytes + 256));
+    CK(cudaMalloc(&d.order, orderBytes + 256));
     d.owned = true;
-    d.recBytes = t->mbRecBytes; d.coefBytes = t->coefBytes;
+    d.recBytes = t->mbRecBytes; d.coefBytes = t->coefBytes; d.orderBytes = orderBytes;
     CK(cudaMemcpyAsync(d.recs, t->mbRecs, t->mbRecBytes, cudaMemcpyHostToDevice, stream_));
     CK(cudaMemcpyAsync(d.coefs, t->coefs, t->coefBytes, cudaMemcpyHostToDevice, stream_));
+    CK(cudaMemcpyAsync(d.order, t->mbOrder, orderBytes, cudaMemcpyHostToDevice, stream_));
     d.pics.assign(t->pics, t->pics + t->numPics);
     jobsDirty_ = true;
-    h2dBytes_ += t->mbRecBytes + t->coefBytes;
+    h2dBytes_ += t->mbRecBytes + t->coefBytes + orderBytes;
     return true;
 }
 
@@ -190,14 +193,16 @@ bool Batch::replicateTape(uint32_t src) {
     for (uint32_t i = 0; i < (uint32_t)g_.nStreams; i++) {
         if (i == src) continue;
         DevTape &d = tapes_[i];
-        if (d.owned) { cudaFree(d.recs); cudaFree(d.coefs); }
+        if (d.owned) { cudaFree(d.recs); cudaFree(d.coefs); cudaFree(d.order); }
         d = DevTape();
         CK(cudaMalloc(&d.recs, s.recBytes + 256));
         CK(cudaMalloc(&d.coefs, s.coefBytes + 256));
+        CK(cudaMalloc(&d.order, s.orderBytes + 256));
         d.owned = true;
-        d.recBytes = s.recBytes; d.coefBytes = s.coefBytes;
+        d.recBytes = s.recBytes; d.coefBytes = s.coefBytes; d.orderBytes = s.orderBytes;
         CK(cudaMemcpyAsync(d.recs, s.recs, s.recBytes, cudaMemcpyDeviceToDevice, stream_));
         CK(cudaMemcpyAsync(d.coefs, s.coefs, s.coefBytes, cudaMemcpyDeviceToDevice, stream_));
+        CK(cudaMemcpyAsync(d.order, s.order, s.orderBytes, cudaMemcpyDeviceToDevice, stream_));
         d.pics = s.pics;
     }
     jobsDirty_ = true;
@@ -211,6 +216,8 @@ bool Batch::buildJobs() {
         np = std::min<uint32_t>(np, (uint32_t)t.pics.size());
     }
     numPics_ = np;
+    picMaxA_.assign(np, 0);
+    picMaxB_.assign(np, 0);
     std::vector<StreamJob> jobs((size_t)np * g_.nStreams);
     for (uint32_t k = 0; k < np; k++)
         for (int s = 0; s < g_.nStreams; s++) {
@@ -218,8 +225,12 @@ bool Batch::buildJobs() {
             StreamJob &j = jobs[(size_t)k * g_.nStreams + s];
             j.recs = reinterpret_cast<const b200_mb_rec *>(t.recs + t.pics[k].mbRecOffset);
             j.coefs = reinterpret_cast<const int16_t *>(t.coefs + t.pics[k].coefOffset);
+            j.order = reinterpret_cast<const uint16_t *>(t.order) + (size_t)k * g_.nMbs;
             j.curSlot = t.pics[k].curSlot;
-            j.pad = 0;
+            j.nA = (uint16_t)t.pics[k].numPassA;
+            j.nB = (uint16_t)t.pics[k].numPassB;
+            picMaxA_[k] = std::max<uint32_t>(picMaxA_[k], j.nA);
+            picMaxB_[k] = std::max<uint32_t>(picMaxB_[k], j.nB);
         }
     cudaFree(dJobs_);
     dJobs_ = nullptr;
@@ -245,11 +256,11 @@ void Batch::kernelTiming(bool enable) {
     evUsed_ = 0;
 }
 
-bool Batch::kernelTimes(float ms[3], uint32_t *launchesPerStage) {
+bool Batch::kernelTimes(float ms[4], uint32_t *launchesPerStage) {
     CK(cudaSetDevice(device_));
     CK(cudaStreamSynchronize(stream_));
-    ms[0] = ms[1] = ms[2] = 0.f;
-    uint32_t n[3] = {0, 0, 0};
+    ms[0] = ms[1] = ms[2] = ms[3] = 0.f;
+    uint32_t n[4] = {0, 0, 0, 0};
     for (size_t i = 1; i < evUsed_; i++) {
         const int st = evStage_[i];
         if (st < 0) continue;
@@ -258,12 +269,12 @@ bool Batch::kernelTimes(float ms[3], uint32_t *launchesPerStage) {
         ms[st] += d;
         n[st]++;
     }
-    if (launchesPerStage) { launchesPerStage[0] = n[0]; launchesPerStage[1] = n[1]; launchesPerStage[2] = n[2]; }
+    if (launchesPerStage) { launchesPerStage[0] = n[0]; launchesPerStage[1] = n[1]; launchesPerStage[2] = n[2]; launchesPerStage[3] = n[3]; }
     evUsed_ = 0;
     return true;
 }
 
-bool Batch::launchPicture(const StreamJob *dJobs, bool recon, bool deblock) {
+bool Batch::launchPicture(const StreamJob *dJobs, uint32_t maxA, uint32_t maxB, bool recon, bool deblock) {
     const uint32_t total = (uint32_t)g_.nStreams * (uint32_t)g_.nMbs;
     serial_++;
     auto mark = [&](int stageEnded) {
@@ -275,12 +286,22 @@ bool Batch::launchPicture(const StreamJob *dJobs, bool recon, bool deblock) {
     mark(-1);
     if (recon) {
         ReconParams rp;
-        rp.pool = pool_; rp.g = g_; rp.jobs = dJobs; rp.order = dOrder_; rp.done = dDoneRecon_;
-        rp.ticket = dCounters_ + 0; rp.errors = dCounters_ + 2; rp.serial = serial_; rp.totalTickets = total;
-        const int blocks = (int)std::min<uint32_t>((uint32_t)reconBlocks_, (total + kReconWarps - 1) / kReconWarps);
-        reconKernel<<<blocks, kReconWarps * 32, 0, stream_>>>(rp, lumaMap_, chromaMap_);
-        launches_++;
-        mark(0);
+        rp.pool = pool_; rp.g = g_; rp.jobs = dJobs; rp.done = dDoneRecon_;
+        rp.ticket = dCounters_ + 0; rp.errors = dCounters_ + 2; rp.serial = serial_;
+        rp.chunksB = (maxB + kReconWarps * kChunkB - 1) / (kReconWarps * kChunkB);
+        rp.chunksA = (maxA + kReconWarps * kChunkA - 1) / (kReconWarps * kChunkA);
+        rp.virtualCtasA = rp.chunksA * (uint32_t)g_.nStreams;
+        if (maxA) {
+            const uint32_t grid = std::min<uint32_t>(rp.virtualCtasA, (uint32_t)reconBlocks_);
+            reconInterKernel<<<grid, kReconWarps * 32, 0, stream_>>>(rp, lumaMap_, chromaMap_);
+            launches_++;
+            mark(0);
+        }
+        if (maxB) {
+            reconIntraKernel<<<rp.chunksB * (uint32_t)g_.nStreams, kReconWarps * 32, 0, stream_>>>(rp);
+            launches_++;
+            mark(3);
+        }
     }
     if (deblock) {
         DeblockParams dp;
@@ -310,7 +331,7 @@ bool Batch::decodePicture(uint32_t k) {
     CK(cudaSetDevice(device_));
     if (jobsDirty_ && !buildJobs()) return false;
     if (k >= numPics_) return false;
-    return launchPicture(dJobs_ + (size_t)k * g_.nStreams, true, true);
+    return launchPicture(dJobs_ + (size_t)k * g_.nStreams, picMaxA_[k], picMaxB_[k], true, true);
 }
 
 bool Batch::debugStage(uint32_t k, bool recon, bool deblock) {
@@ -318,7 +339,7 @@ bool Batch::debugStage(uint32_t k, bool recon, bool deblock) {
     CK(cudaSetDevice(device_));
     if (jobsDirty_ && !buildJobs()) return false;
     if (k >= numPics_) return false;
-    return launchPicture(dJobs_ + (size_t)k * g_.nStreams, recon, deblock);
+    return launchPicture(dJobs_ + (size_t)k * g_.nStreams, picMaxA_[k], picMaxB_[k], recon, deblock);
 }
 
 bool Batch::run(uint32_t first, uint32_t count) {
@@ -344,12 +365,13 @@ bool Batch::timerStop(float *ms) {
 }
 
 // streaming (single picture, host buffers): the legacy API path
-bool Batch::submitHostPicture(uint32_t stream, const b200_pic_hdr &hdr, const b200_mb_rec *recs, const int16_t *coefs) {
+bool Batch::submitHostPicture(uint32_t stream, const b200_pic_hdr &hdr, const b200_mb_rec *recs, const int16_t *coefs, const uint16_t *order) {
     if (!created_ || g_.nStreams != 1 || stream != 0) return false;
     CK(cudaSetDevice(device_));
     const size_t recBytes = (size_t)g_.nMbs * sizeof(b200_mb_rec);
     const size_t coefBytes = (size_t)hdr.numCoefBlocks * B200_COEF_BLOCK_BYTES;
-    const size_t need = recBytes + coefBytes + 512;
+    const size_t orderBytes = (size_t)g_.nMbs * sizeof(uint16_t);
+    const size_t need = recBytes + coefBytes + orderBytes + 1024;
     const int b = stageIdx_ ^= 1;
     if (stageCap_[b] < need) {
         // growing a staging buffer: make sure nothing in flight still reads it
@@ -367,17 +389,20 @@ bool Batch::submitHostPicture(uint32_t stream, const b200_pic_hdr &hdr, const b2
     }
     uint8_t *h = hStage_[b];
     StreamJob job;
-    const size_t recOff = 256, coefOff = (256 + recBytes + 255) & ~(size_t)255;
+    const size_t recOff = 256, orderOff = (recOff + recBytes + 255) & ~(size_t)255, coefOff = (orderOff + orderBytes + 255) & ~(size_t)255;
     job.recs = reinterpret_cast<const b200_mb_rec *>(dStage_[b] + recOff);
     job.coefs = reinterpret_cast<const int16_t *>(dStage_[b] + coefOff);
+    job.order = reinterpret_cast<const uint16_t *>(dStage_[b] + orderOff);
     job.curSlot = hdr.curSlot;
-    job.pad = 0;
+    job.nA = (uint16_t)hdr.numPassA;
+    job.nB = (uint16_t)hdr.numPassB;
     std::memcpy(h, &job, sizeof job);
     std::memcpy(h + recOff, recs, recBytes);
+    std::memcpy(h + orderOff, order, orderBytes);
     std::memcpy(h + coefOff, coefs, coefBytes);
     CK(cudaMemcpyAsync(dStage_[b], h, coefOff + coefBytes, cudaMemcpyHostToDevice, stream_));
     h2dBytes_ += coefOff + coefBytes;
-    if (!launchPicture(reinterpret_cast<const StreamJob *>(dStage_[b]), true, true)) return false;
+    if (!launchPicture(reinterpret_cast<const StreamJob *>(dStage_[b]), hdr.numPassA, hdr.numPassB, true, true)) return false;
     CK(cudaEventRecord(stageEv_[b], stream_));
     return true;
 }

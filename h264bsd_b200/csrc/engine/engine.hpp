@@ -31,7 +31,7 @@ public:
     bool timerStart();
     bool timerStop(float *ms);
 
-    bool submitHostPicture(uint32_t stream, const b200_pic_hdr &hdr, const b200_mb_rec *recs, const int16_t *coefs);
+    bool submitHostPicture(uint32_t stream, const b200_pic_hdr &hdr, const b200_mb_rec *recs, const int16_t *coefs, const uint16_t *order);
     bool readFrame(uint32_t stream, uint32_t slot, uint8_t *dst);
     bool writeFrame(uint32_t stream, uint32_t slot, const uint8_t *src);
     bool convertFrame(uint32_t stream, uint32_t slot, int mode, uint32_t *dstHost);
@@ -39,7 +39,7 @@ public:
     int compareStreams(const uint32_t *slots);
     // per-stage device time (CUDA events on the engine's stream around every launch)
     void kernelTiming(bool enable);
-    bool kernelTimes(float ms[3], uint32_t *launchesPerStage);  // recon, deblock, border; resets the accumulators
+    bool kernelTimes(float ms[4], uint32_t *launchesPerStage);  // recon pass A, deblock, border, recon pass B; resets the accumulators
     uint32_t idctErrors();
     uint32_t watchdog(int which);  // 0: flag waits that gave up, 1: TMA waits that gave up
 
@@ -54,13 +54,14 @@ public:
 
 private:
     struct DevTape {
-        uint8_t *recs = nullptr, *coefs = nullptr;
-        size_t recBytes = 0, coefBytes = 0;
+        uint8_t *recs = nullptr, *coefs = nullptr, *order = nullptr;
+        size_t recBytes = 0, coefBytes = 0, orderBytes = 0;
         bool owned = false;
         std::vector<b200_pic_hdr> pics;
     };
     bool buildJobs();
-    bool launchPicture(const StreamJob *dJobs, bool recon, bool deblock);
+    bool launchPicture(const StreamJob *dJobs, uint32_t maxA, uint32_t maxB, bool recon, bool deblock);
+    std::vector<uint32_t> picMaxA_, picMaxB_;
 
     bool created_ = false;
     int device_ = 0, numSms_ = 0;

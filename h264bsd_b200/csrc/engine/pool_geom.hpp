@@ -29,8 +29,9 @@ struct PoolGeom {
 struct StreamJob {
     const b200_mb_rec *recs;  // nMbs records of this picture
     const int16_t *coefs;     // this picture's coefficient pool
+    const uint16_t *order;    // nMbs macroblock addresses: nA pass-A entries (raster), then nB pass-B entries (wavefront)
     uint32_t curSlot;
-    uint32_t pad;
+    uint16_t nA, nB;
 };
 
 }  // namespace b200

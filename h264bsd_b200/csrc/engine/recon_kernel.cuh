@@ -11,36 +11,41 @@
 namespace b200 {
 
 constexpr int kReconWarps = 8;
+constexpr int kChunkA = 4;   // consecutive pass-A list entries per warp (TMA of entry i+1 overlaps the math of entry i)
+constexpr int kChunkB = 2;   // consecutive pass-B (wavefront) entries per warp
 
 struct ReconParams {
     uint8_t *pool;
     PoolGeom g;
     const StreamJob *jobs;     // nStreams
-    const uint16_t *order;     // nMbs macroblock indices in wavefront order (x + 2y ascending)
-    uint32_t *done;            // nStreams * nMbs completion flags
-    uint32_t *ticket;          // global ticket counter (zeroed before launch)
+    uint32_t *done;            // nStreams * nMbs completion flags (pass B only)
+    uint32_t *ticket;          // CTA ticket counter of pass B (zeroed before launch)
     uint32_t *errors;          // [0] IDCT range errors (h264bsd_transform.c:183-188)
     uint32_t serial;           // value that marks "done in this launch"
-    uint32_t totalTickets;     // nStreams * nMbs
+    uint32_t chunksB;          // pass B: CTAs per stream
+    uint32_t chunksA;          // pass A: virtual CTAs per stream (kReconWarps * kChunkA entries each)
+    uint32_t virtualCtasA;     // chunksA * nStreams
 };
 
-struct __align__(128) ReconWarpSmem {
-    uint8_t lumaWin[kLumaBoxW * kLumaBoxH + 16];          // 1024
-    uint8_t chromaWin[2 * kChromaBoxW * kChromaBoxH + 64]; // 640
-    int16_t res[24][16];                                   // 768
-    uint8_t pred[384];                                     // 384: Y 16x16, Cb 8x8, Cr 8x8
-    uint8_t itY[17][24];                                   // 408: rows -1..15, cols -1..19 (+pad)
-    uint8_t itC[2][9][12];                                 // 216: rows -1..7, cols -1..7 (+pad)
-    uint64_t mbar;
-    uint32_t pad[5];
+struct __align__(128) InterWarpSmem {
+    uint8_t lumaWin[2][kLumaBoxW * kLumaBoxH + 16];           // 2 x 1024, double buffered
+    uint8_t chromaWin[2][2 * kChromaBoxW * kChromaBoxH + 64];  // 2 x 640
+    int16_t res[24][16];                                       // 768
+    uint8_t pred[384];                                         // 384: multi-partition macroblocks only
+    uint64_t mbar[2];
+    uint32_t pad[12];
+};
+struct __align__(16) IntraWarpSmem {
+    int16_t res[24][16];
+    uint8_t itY[17][24];   // rows -1..15, cols -1..19 (+pad)
+    uint8_t itC[2][9][12]; // rows -1..7, cols -1..7 (+pad)
+    uint8_t stage[16];
 };
 
 // ---- residual -----------------------------------------------------------------------------------
-__device__ __forceinline__ int levelScale(int qpMod, int cls) {
-    // h264bsd_transform.c:58-59; cls 0 = both coordinates even, 2 = both odd, 1 = mixed
-    const int t[6][3] = {{10, 13, 16}, {11, 14, 18}, {13, 16, 20}, {14, 18, 23}, {16, 20, 25}, {18, 23, 29}};
-    return t[qpMod][cls];
-}
+// h264bsd_transform.c:58-59; class 0 = both coordinates even, 2 = both odd, 1 = mixed
+__device__ __constant__ uint8_t cLevelScale[6][4] = {{10, 13, 16, 0}, {11, 14, 18, 0}, {13, 16, 20, 0}, {14, 18, 23, 0}, {16, 20, 25, 0}, {18, 23, 29, 0}};
+__device__ __forceinline__ int levelScale(int qpMod, int cls) { return cLevelScale[qpMod][cls]; }
 
 // h264bsdProcessBlock (transform.c:97-234): lev in zig-zag order -> out[16] raster residual
 __device__ __forceinline__ bool idctBlock(const int16_t *lev, int qp, bool dcPreset, int dcValue, int *out) {
@@ -192,344 +197,484 @@ __device__ __forceinline__ int intra4x4Pel(int mode, int x, int y, bool avA, boo
     }
 }
 
+// ---- shared by both passes --------------------------------------------------------------------------
+struct MbHead {
+    int mbType, qpY, qpC, flags;
+    uint32_t mask, coefIndex;
+};
+__device__ __forceinline__ MbHead loadHead(const b200_mb_rec *rec) {
+    const uint4 w = __ldg(reinterpret_cast<const uint4 *>(rec));  // bytes 0..15
+    MbHead h;
+    h.mbType = w.x & 0xFF; h.qpY = (w.x >> 8) & 0xFF; h.qpC = (w.x >> 16) & 0xFF; h.flags = w.x >> 24;
+    h.mask = w.y; h.coefIndex = w.z;
+    return h;
+}
+
+// residual of the whole macroblock into sm res[24][16] (lane b = block b); see mb_residual in oracle/px_oracle.c
+__device__ __forceinline__ void mbResidual(const MbHead &h, const int16_t *coef, int16_t (*res)[16], int lane, uint32_t *errors) {
+    const bool i16 = h.mbType >= B200_MB_I_16x16_FIRST;
+    const uint32_t mask = h.mask;
+    if (lane < 24) {
+        const int nDc = ((mask >> 24) & 1) + ((mask >> 25) & 1);
+        const bool coded = (mask >> lane) & 1;
+        int16_t lev[16];
+        if (coded) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(coef + (size_t)(nDc + __popc(mask & ((1u << lane) - 1u))) * 16);
+            *reinterpret_cast<uint4 *>(lev) = __ldg(src);
+            *reinterpret_cast<uint4 *>(lev + 8) = __ldg(src + 1);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; i++) lev[i] = 0;
+        }
+        bool dcPreset = false;
+        int dcVal = 0;
+        if (lane < 16) {
+            dcPreset = i16;
+            if (i16 && (mask & B200_CM_LUMA_DC)) {
+                int16_t dl[16];
+                const uint4 *src = reinterpret_cast<const uint4 *>(coef);
+                *reinterpret_cast<uint4 *>(dl) = __ldg(src);
+                *reinterpret_cast<uint4 *>(dl + 8) = __ldg(src + 1);
+                dcVal = lumaDcPick(dl, h.qpY, cBlkY[lane] * 4 + cBlkX[lane]);
+            }
+        } else {
+            dcPreset = true;
+            if (mask & B200_CM_CHROMA_DC) {
+                int16_t dl[4];
+                const uint2 *src = reinterpret_cast<const uint2 *>(coef + (size_t)((mask >> 24) & 1) * 16 + ((lane - 16) >> 2) * 4);
+                *reinterpret_cast<uint2 *>(dl) = __ldg(src);
+                dcVal = chromaDcPick(dl, h.qpC, lane & 3);
+            }
+        }
+        int out[16];
+        bool bad = false;
+        if (coded || (dcPreset && dcVal != 0)) {
+            bad = idctBlock(lev, lane < 16 ? h.qpY : h.qpC, dcPreset, dcVal, out);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; i++) out[i] = 0;
+        }
+        if (bad) atomicAdd(errors, 1u);
+        int16_t *dst = res[lane];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2)
+            *reinterpret_cast<uint32_t *>(dst + i) = (uint32_t)(uint16_t)out[i] | ((uint32_t)(uint16_t)out[i + 1] << 16);
+    }
+    __syncwarp();
+}
+
+// this lane's residuals: luma row r8 cols c8..c8+7, chroma plane cp row cr cols cc..cc+3
+__device__ __forceinline__ void laneResidual(const int16_t (*res)[16], int lane, int *resY, int *resC) {
+    const int r8 = lane >> 1, cp = lane >> 4, cr = (lane >> 1) & 7;
+    const int by = r8 >> 2, ry = r8 & 3, bx = (lane & 1) * 2;
+    const int16_t *ra = res[cRasterToBlk[by * 4 + bx]] + ry * 4;
+    const int16_t *rb = res[cRasterToBlk[by * 4 + bx + 1]] + ry * 4;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { resY[i] = ra[i]; resY[4 + i] = rb[i]; }
+    const int16_t *rc = res[16 + cp * 4 + (cr >> 2) * 2 + (lane & 1)] + (cr & 3) * 4;
+#pragma unroll
+    for (int i = 0; i < 4; i++) resC[i] = rc[i];
+}
+
+// 8 consecutive bytes from an arbitrarily aligned shared-memory address
+__device__ __forceinline__ uint2 lds8(const uint8_t *p) {
+    const uint32_t a = smemAddr(p), sh = (a & 3u) * 8u;
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(p - (a & 3u));
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+    return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
+}
+__device__ __forceinline__ uint32_t lds4(const uint8_t *p) {
+    const uint32_t a = smemAddr(p), sh = (a & 3u) * 8u;
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(p - (a & 3u));
+    return __funnelshift_r(w[0], w[1], sh);
+}
+
 // =====================================================================================================
-__global__ void __launch_bounds__(kReconWarps * 32)
-reconKernel(const ReconParams p, const __grid_constant__ CUtensorMap lumaMap, const __grid_constant__ CUtensorMap chromaMap) {
-    __shared__ ReconWarpSmem smemAll[kReconWarps];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    ReconWarpSmem &sm = smemAll[warp];
-    const PoolGeom &g = p.g;
+// pass A: inter-predicted (and I_PCM) macroblocks.  They read only finished reference frames, so there
+// is no ordering between them: plain grid, blockIdx.y = stream, a warp owns kChunkA consecutive entries
+// of the stream's raster-ordered list and prefetches the next entry's reference window by TMA while it
+// works on the current one.
+// =====================================================================================================
+struct InterInfo {
+    uint32_t mb;
+    MbHead h;
+    bool single;     // one 16x16 partition (P_Skip / P_L0_16x16): window prefetched
+    int mvx, mvy;
+    int ox, cox;     // clamped window origins (bordered-plane coordinates), luma / chroma
+};
+
+__device__ __forceinline__ void issueWindow(InterWarpSmem &sm, int buf, const PoolGeom &g, const CUtensorMap *lumaMap, const CUtensorMap *chromaMap,
+                                            int xInt, int yInt, int cxInt, int cyInt, uint32_t refFrame, int lane, int *oxOut, int *coxOut) {
+    // clamp the window origin into the bordered plane: a window wholly outside the picture on an axis equals the
+    // window at the clamped origin because the border is a replication; the box starts 16-byte aligned
+    const int ox = clip3(-kPadY, g.W + kPadY - kLumaWin, xInt - 2) + kPadY;
+    const int oy = clip3(-kPadY, g.H + kPadY - kLumaWin, yInt - 2) + kPadY;
+    const int cox = clip3(-kPadC, g.W / 2 + kPadC - kChromaWin, cxInt) + kPadC;
+    const int coy = clip3(-kPadC, g.H / 2 + kPadC - kChromaWin, cyInt) + kPadC;
     if (lane == 0) {
-        mbarInit(&sm.mbar, 1);
+        fenceProxyAsync();
+        mbarExpectTx(&sm.mbar[buf], kLumaBoxW * kLumaBoxH + 2 * kChromaBoxW * kChromaBoxH);
+        tmaLoad3d(sm.lumaWin[buf], lumaMap, ox & ~15, oy, (int)refFrame, &sm.mbar[buf]);
+        tmaLoad4d(sm.chromaWin[buf], chromaMap, cox & ~15, coy, 0, (int)refFrame, &sm.mbar[buf]);
+    }
+    *oxOut = ox;
+    *coxOut = cox;
+}
+
+__global__ void __launch_bounds__(kReconWarps * 32, 3)
+reconInterKernel(const ReconParams p, const __grid_constant__ CUtensorMap lumaMap, const __grid_constant__ CUtensorMap chromaMap) {
+    __shared__ InterWarpSmem smemAll[kReconWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const PoolGeom &g = p.g;
+    InterWarpSmem &sm = smemAll[warp];
+    if (lane == 0) {
+        mbarInit(&sm.mbar[0], 1);
+        mbarInit(&sm.mbar[1], 1);
         fenceMbarInit();
     }
     __syncwarp();
-    uint32_t phase = 0;
+    uint32_t phase[2] = {0, 0};
+    // persistent CTAs striding over virtual CTAs: v -> (stream, chunk of the stream's pass-A list); consecutive
+    // virtual CTAs belong to the same stream, so neighbouring macroblocks are in flight together (L2 locality)
+    for (uint32_t v = blockIdx.x; v < p.virtualCtasA; v += gridDim.x) {
+    const uint32_t s = v / p.chunksA, chunk = v - s * p.chunksA;
+    const StreamJob job = p.jobs[s];
+    const uint32_t e0 = (chunk * kReconWarps + warp) * kChunkA;
+    if (e0 >= job.nA) continue;
+    const int n = min((uint32_t)kChunkA, job.nA - e0);
+    const uint32_t frameBase = s * (uint32_t)g.numSlots;
+    uint8_t *cur = framePtr(p.pool, g, frameBase + job.curSlot);
+    const int r8 = lane >> 1, c8 = (lane & 1) * 8;
+    const int cp = lane >> 4, cr = (lane >> 1) & 7, cc = (lane & 1) * 4;
 
-    for (;;) {
-        uint32_t t = 0;
-        if (lane == 0) t = atomicAdd(p.ticket, 1u);
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= p.totalTickets) break;
-        const uint32_t k = t / (uint32_t)g.nStreams, s = t - k * (uint32_t)g.nStreams;
-        const uint32_t mb = p.order[k];
+    auto prepare = [&](int i, int buf) -> InterInfo {
+        InterInfo it;
+        it.mb = __ldg(job.order + e0 + i);
+        const b200_mb_rec *rec = job.recs + it.mb;
+        it.h = loadHead(rec);
+        it.single = it.h.mbType <= B200_MB_P_16x16;
+        it.mvx = it.mvy = 0; it.ox = it.cox = 0;
+        if (it.single) {
+            const uint32_t mvv = __ldg(reinterpret_cast<const uint32_t *>(rec) + 8);
+            const uint32_t refSlots = __ldg(reinterpret_cast<const uint32_t *>(rec) + 4);
+            it.mvx = (int)(int16_t)(mvv & 0xFFFF); it.mvy = (int)(int16_t)(mvv >> 16);
+            const int mby = (int)(it.mb / (uint32_t)g.widthMbs), mbx = (int)(it.mb - (uint32_t)mby * g.widthMbs);
+            issueWindow(sm, buf, g, &lumaMap, &chromaMap, mbx * 16 + (it.mvx >> 2), mby * 16 + (it.mvy >> 2),
+                        mbx * 8 + (it.mvx >> 3), mby * 8 + (it.mvy >> 3), frameBase + (refSlots & 0xFF), lane, &it.ox, &it.cox);
+        }
+        return it;
+    };
+
+    InterInfo nxt = prepare(0, 0);
+#pragma unroll 1
+    for (int i = 0; i < n; i++) {
+        const int buf = i & 1;
+        const InterInfo it = nxt;
+        if (i + 1 < n) nxt = prepare(i + 1, buf ^ 1);   // the other buffer's previous user finished before this point
+        const MbHead &h = it.h;
+        const uint32_t mb = it.mb;
         const int mby = (int)(mb / (uint32_t)g.widthMbs), mbx = (int)(mb - (uint32_t)mby * g.widthMbs);
-        const StreamJob job = p.jobs[s];
         const b200_mb_rec *rec = job.recs + mb;
-        uint32_t *doneS = p.done + (size_t)s * g.nMbs;
-        const uint32_t frameBase = s * (uint32_t)g.numSlots;
-        uint8_t *cur = framePtr(p.pool, g, frameBase + job.curSlot);
-
-        const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t *>(rec));  // mbType, qpY, qpC, flags
-        const int mbType = w0 & 0xFF, qpY = (w0 >> 8) & 0xFF, qpC = (w0 >> 16) & 0xFF, flags = w0 >> 24;
-        const uint32_t mask = __ldg(reinterpret_cast<const uint32_t *>(rec) + 1);
-        const uint32_t coefIndex = __ldg(reinterpret_cast<const uint32_t *>(rec) + 2);
-        const int16_t *coef = job.coefs + (size_t)coefIndex * 16;
-
-        // this lane's pels: luma row r8, columns c8..c8+7 ; chroma plane cp, row cr, columns cc..cc+3
-        const int r8 = lane >> 1, c8 = (lane & 1) * 8;
-        const int cp = lane >> 4, cr = (lane >> 1) & 7, cc = (lane & 1) * 4;
+        const int16_t *coef = job.coefs + (size_t)h.coefIndex * 16;
         uint8_t *dstY = lumaAt(cur, g, mbx * 16 + c8, mby * 16 + r8);
         uint8_t *dstC = chromaAt(cur, g, cp, mbx * 8 + cc, mby * 8 + cr);
 
-        if (mbType == B200_MB_I_PCM) {
+        if (h.mbType == B200_MB_I_PCM) {
             // h264bsdWriteMacroblock (image.c:81-144): 384 raw bytes
             const uint8_t *src = reinterpret_cast<const uint8_t *>(coef);
             *reinterpret_cast<uint2 *>(dstY) = __ldg(reinterpret_cast<const uint2 *>(src + r8 * 16 + c8));
             *reinterpret_cast<uint32_t *>(dstC) = __ldg(reinterpret_cast<const uint32_t *>(src + 256 + cp * 64 + cr * 8 + cc));
-        } else {
-            // ---------------- residual: one lane per 4x4 block -----------------------------------------
-            const bool i16 = mbType >= B200_MB_I_16x16_FIRST;
-            if (mask) {
-                if (lane < 24) {
-                    const int nDc = ((mask >> 24) & 1) + ((mask >> 25) & 1);
-                    const bool coded = (mask >> lane) & 1;
-                    int16_t lev[16];
-                    if (coded) {
-                        const uint4 *src = reinterpret_cast<const uint4 *>(coef + (size_t)(nDc + __popc(mask & ((1u << lane) - 1u))) * 16);
-                        uint4 a = __ldg(src), b = __ldg(src + 1);
-                        *reinterpret_cast<uint4 *>(lev) = a;
-                        *reinterpret_cast<uint4 *>(lev + 8) = b;
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 16; i++) lev[i] = 0;
-                    }
-                    bool dcPreset = false;
-                    int dcVal = 0;
-                    if (lane < 16) {
-                        dcPreset = i16;
-                        if (i16 && (mask & B200_CM_LUMA_DC)) {
-                            int16_t dl[16];
-                            const uint4 *src = reinterpret_cast<const uint4 *>(coef);
-                            *reinterpret_cast<uint4 *>(dl) = __ldg(src);
-                            *reinterpret_cast<uint4 *>(dl + 8) = __ldg(src + 1);
-                            dcVal = lumaDcPick(dl, qpY, cBlkY[lane] * 4 + cBlkX[lane]);
-                        }
-                    } else {
-                        dcPreset = true;
-                        if (mask & B200_CM_CHROMA_DC) {
-                            int16_t dl[4];
-                            const uint2 *src = reinterpret_cast<const uint2 *>(coef + (size_t)((mask >> 24) & 1) * 16 + ((lane - 16) >> 2) * 4);
-                            *reinterpret_cast<uint2 *>(dl) = __ldg(src);
-                            dcVal = chromaDcPick(dl, qpC, lane & 3);
-                        }
-                    }
-                    int out[16];
-                    bool bad = false;
-                    if (coded || (dcPreset && dcVal != 0)) {
-                        bad = idctBlock(lev, lane < 16 ? qpY : qpC, dcPreset, dcVal, out);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 16; i++) out[i] = 0;
-                    }
-                    if (bad) atomicAdd(p.errors, 1u);
-                    int16_t *dst = sm.res[lane];
-#pragma unroll
-                    for (int i = 0; i < 16; i += 2)
-                        *reinterpret_cast<uint32_t *>(dst + i) = (uint32_t)(uint16_t)out[i] | ((uint32_t)(uint16_t)out[i + 1] << 16);
-                }
-                __syncwarp();
-            }
-
-            // this lane's residuals (zero when the macroblock has none)
-            int resY[8], resC[4];
-            if (mask) {
-                const int by = r8 >> 2, ry = r8 & 3, bx = (lane & 1) * 2;
-                const int16_t *ra = sm.res[cRasterToBlk[by * 4 + bx]] + ry * 4;
-                const int16_t *rb = sm.res[cRasterToBlk[by * 4 + bx + 1]] + ry * 4;
-#pragma unroll
-                for (int i = 0; i < 4; i++) { resY[i] = ra[i]; resY[4 + i] = rb[i]; }
-                const int16_t *rc = sm.res[16 + cp * 4 + (cr >> 2) * 2 + (lane & 1)] + (cr & 3) * 4;
-#pragma unroll
-                for (int i = 0; i < 4; i++) resC[i] = rc[i];
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; i++) resY[i] = 0;
-#pragma unroll
-                for (int i = 0; i < 4; i++) resC[i] = 0;
-            }
-
-            if (mbType <= B200_MB_P_8x8REF0) {
-                // ---------------- inter prediction (inter_prediction.c:361-482) ---------------------------
-                const uint32_t refSlots = __ldg(reinterpret_cast<const uint32_t *>(rec) + 4);
-                const uint32_t subTypes = (__ldg(reinterpret_cast<const uint32_t *>(rec) + 3) >> 24) & 0xFF;
-                const uint32_t *mvw = reinterpret_cast<const uint32_t *>(rec) + 8;
-                // enumerate partitions as (4x4 block index of its first block, width, height)
-                int nParts;
-                if (mbType <= B200_MB_P_16x16) nParts = 1;
-                else if (mbType <= B200_MB_P_8x16) nParts = 2;
-                else nParts = 16;  // walk all 4x4 blocks, skip those that are not a partition origin
-                for (int pi = 0; pi < nParts; pi++) {
-                    int blk, pw, ph;
-                    if (mbType <= B200_MB_P_16x16) { blk = 0; pw = 16; ph = 16; }
-                    else if (mbType == B200_MB_P_16x8) { blk = pi * 8; pw = 16; ph = 8; }
-                    else if (mbType == B200_MB_P_8x16) { blk = pi * 4; pw = 8; ph = 16; }
-                    else {
-                        blk = pi;
-                        const int sub = (subTypes >> (2 * (pi >> 2))) & 3, j = pi & 3;
-                        if (sub == 0) { if (j) continue; pw = 8; ph = 8; }
-                        else if (sub == 1) { if (j & 1) continue; pw = 8; ph = 4; }
-                        else if (sub == 2) { if (j & 2) continue; pw = 4; ph = 8; }
-                        else { pw = 4; ph = 4; }
-                    }
-                    const int px = cBlkX[blk] * 4, py = cBlkY[blk] * 4;
-                    const uint32_t mvv = __ldg(mvw + blk);
-                    const int mvx = (int)(int16_t)(mvv & 0xFFFF), mvy = (int)(int16_t)(mvv >> 16);
-                    const uint32_t refFrame = frameBase + ((refSlots >> (8 * (blk >> 2))) & 0xFF);
-                    const int xInt = mbx * 16 + px + (mvx >> 2), yInt = mby * 16 + py + (mvy >> 2);
-                    const int cxInt = ((mbx * 16 + px) >> 1) + (mvx >> 3), cyInt = ((mby * 16 + py) >> 1) + (mvy >> 3);
-                    // window origin in bordered-plane coordinates, clamped (see below); the box starts 16-byte aligned
-                    const int ox = clip3(-kPadY, g.W + kPadY - kLumaWin, xInt - 2) + kPadY;
-                    const int oy = clip3(-kPadY, g.H + kPadY - kLumaWin, yInt - 2) + kPadY;
-                    const int cox = clip3(-kPadC, g.W / 2 + kPadC - kChromaWin, cxInt) + kPadC;
-                    const int coy = clip3(-kPadC, g.H / 2 + kPadC - kChromaWin, cyInt) + kPadC;
-                    if (lane == 0) {
-                        fenceProxyAsync();
-                        mbarExpectTx(&sm.mbar, kLumaBoxW * kLumaBoxH + 2 * kChromaBoxW * kChromaBoxH);
-                        // clamp the box origin into the bordered plane: a box wholly outside the picture on an axis
-                        // equals the box at the clamped origin because the border is a replication
-                        tmaLoad3d(sm.lumaWin, &lumaMap, ox & ~15, oy, (int)refFrame, &sm.mbar);
-                        tmaLoad4d(sm.chromaWin, &chromaMap, cox & ~15, coy, 0, (int)refFrame, &sm.mbar);
-                    }
-                    mbarWait(&sm.mbar, phase);
-                    phase ^= 1;
-                    const int xf = mvx & 3, yf = mvy & 3;
-                    const int lw = 31 - __clz(pw);
-                    for (int i = lane; i < pw * ph; i += 32) {
-                        const int x = i & (pw - 1), y = i >> lw;
-                        sm.pred[(py + y) * 16 + px + x] = (uint8_t)lumaQpel(sm.lumaWin + (ox & 15), x, y, xf, yf);
-                    }
-                    const int cw = pw >> 1, chh = ph >> 1, ncp = cw * chh, lcw = lw - 1;
-                    const int cxf = mvx & 7, cyf = mvy & 7;
-                    for (int i = lane; i < 2 * ncp; i += 32) {
-                        const int pl = i >= ncp, ii = i - pl * ncp;
-                        const int x = ii & (cw - 1), y = ii >> lcw;
-                        const uint8_t *wp = sm.chromaWin + pl * (kChromaBoxW * kChromaBoxH) + y * kChromaBoxW + x + (cox & 15);
-                        const int A = wp[0], B = wp[1], C = wp[kChromaBoxW], D = wp[kChromaBoxW + 1];
-                        // PredictChroma (reconstruct.c:415-475)
-                        sm.pred[256 + pl * 64 + ((py >> 1) + y) * 8 + (px >> 1) + x] =
-                            (uint8_t)(((8 - cxf) * (8 - cyf) * A + cxf * (8 - cyf) * B + (8 - cxf) * cyf * C + cxf * cyf * D + 32) >> 6);
-                    }
-                    __syncwarp();
-                }
-                // add residual + clip + store (h264bsdWriteOutputBlocks, image.c:172-344)
-                const uint2 pv = *reinterpret_cast<const uint2 *>(sm.pred + r8 * 16 + c8);
-                uint32_t o0 = 0, o1 = 0;
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    o0 |= (uint32_t)clip255((int)((pv.x >> (8 * i)) & 0xFF) + resY[i]) << (8 * i);
-                    o1 |= (uint32_t)clip255((int)((pv.y >> (8 * i)) & 0xFF) + resY[4 + i]) << (8 * i);
-                }
-                *reinterpret_cast<uint2 *>(dstY) = make_uint2(o0, o1);
-                const uint32_t pc = *reinterpret_cast<const uint32_t *>(sm.pred + 256 + cp * 64 + cr * 8 + cc);
-                uint32_t oc = 0;
-#pragma unroll
-                for (int i = 0; i < 4; i++) oc |= (uint32_t)clip255((int)((pc >> (8 * i)) & 0xFF) + resC[i]) << (8 * i);
-                *reinterpret_cast<uint32_t *>(dstC) = oc;
-                __syncwarp();
-            } else {
-                // ---------------- intra prediction (intra_prediction.c:478-533) ---------------------------
-                const bool avA = flags & B200_MBF_AVAIL_A, avB = flags & B200_MBF_AVAIL_B;
-                const bool avC = flags & B200_MBF_AVAIL_C, avD = flags & B200_MBF_AVAIL_D;
-                // wait until the neighbours this macroblock reads have been written (unfiltered picture)
-                if (lane < 4) {
-                    const bool need = lane == 0 ? avA : lane == 1 ? avB : lane == 2 ? avC : avD;
-                    if (need) {
-                        const int nmb = lane == 0 ? (int)mb - 1 : lane == 1 ? (int)mb - g.widthMbs : lane == 2 ? (int)mb - g.widthMbs + 1 : (int)mb - g.widthMbs - 1;
-                        waitFlag(doneS + nmb, p.serial);
-                    }
-                }
-                __syncwarp();
-                // neighbouring pels (h264bsdGetNeighbourPels :545-614), straight from L2
-                if (lane < 21) {
-                    const bool ok = lane == 0 ? avD : lane <= 16 ? avB : avC;
-                    sm.itY[0][lane] = ok ? __ldcg(lumaAt(cur, g, mbx * 16 - 1 + lane, mby * 16 - 1)) : 128;
-                }
-                if (lane < 16) sm.itY[1 + lane][0] = avA ? __ldcg(lumaAt(cur, g, mbx * 16 - 1, mby * 16 + lane)) : 128;
-                if (lane < 18) {
-                    const int pl = lane >= 9, i = lane - pl * 9;
-                    const bool ok = i == 0 ? avD : avB;
-                    sm.itC[pl][0][i] = ok ? __ldcg(chromaAt(cur, g, pl, mbx * 8 - 1 + i, mby * 8 - 1)) : 128;
-                }
-                if (lane < 16) {
-                    const int pl = lane >> 3, i = lane & 7;
-                    sm.itC[pl][1 + i][0] = avA ? __ldcg(chromaAt(cur, g, pl, mbx * 8 - 1, mby * 8 + i)) : 128;
-                }
-                __syncwarp();
-
-                if (mbType == B200_MB_I_4x4) {
-                    // h264bsdIntra4x4Prediction (:701-833): 16 sequential blocks; lanes 0..15 own one pel each
-                    const uint32_t *modew = reinterpret_cast<const uint32_t *>(rec) + 8;
-                    const int x = lane & 3, y = (lane >> 2) & 3;
-                    for (int b = 0; b < 16; b++) {
-                        const int bx = cBlkX[b], by = cBlkY[b];
-                        const int mode = (__ldg(modew + (b >> 2)) >> (8 * (b & 3))) & 0xFF;
-                        const bool bA = bx ? true : avA, bB = by ? true : avB;
-                        bool bC;
-                        if (by == 0) bC = (bx == 3) ? avC : avB;
-                        else if (bx == 3) bC = false;
-                        else bC = cRasterToBlk[(by - 1) * 4 + bx + 1] < b;
-                        if (lane < 16) {
-                            const uint8_t *above = &sm.itY[by * 4][bx * 4 + 1];   // above[i] = sample (i, -1)
-                            const uint8_t *left = &sm.itY[by * 4 + 1][bx * 4];    // left[i*24] = sample (-1, i)
-                            auto A = [&](int i) -> int { return above[(i > 3 && !bC) ? 3 : i]; };
-                            auto L = [&](int i) -> int { return left[i * 24]; };
-                            int v = intra4x4Pel(mode, x, y, bA, bB, A, L);
-                            if (mask) v = clip255(v + sm.res[b][y * 4 + x]);
-                            sm.pred[lane] = (uint8_t)v;
-                        }
-                        __syncwarp();
-                        if (lane < 16) sm.itY[by * 4 + 1 + y][bx * 4 + 1 + x] = sm.pred[lane];
-                        __syncwarp();
-                    }
-                    uint32_t o0 = 0, o1 = 0;
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        o0 |= (uint32_t)sm.itY[1 + r8][1 + c8 + i] << (8 * i);
-                        o1 |= (uint32_t)sm.itY[1 + r8][1 + c8 + 4 + i] << (8 * i);
-                    }
-                    *reinterpret_cast<uint2 *>(dstY) = make_uint2(o0, o1);
-                } else {
-                    // h264bsdIntra16x16Prediction (:627-687)
-                    const int mode = (mbType - B200_MB_I_16x16_FIRST) & 3;
-                    int pv[8];
-                    if (mode == 0) {
-#pragma unroll
-                        for (int i = 0; i < 8; i++) pv[i] = sm.itY[0][1 + c8 + i];
-                    } else if (mode == 1) {
-#pragma unroll
-                        for (int i = 0; i < 8; i++) pv[i] = sm.itY[1 + r8][0];
-                    } else if (mode == 2) {
-                        int sa = 0, sl = 0;
-                        for (int i = 0; i < 16; i++) { sa += sm.itY[0][1 + i]; sl += sm.itY[1 + i][0]; }
-                        int v = (avA && avB) ? (sa + sl + 16) >> 5 : avA ? (sl + 8) >> 4 : avB ? (sa + 8) >> 4 : 128;
-#pragma unroll
-                        for (int i = 0; i < 8; i++) pv[i] = v;
-                    } else {
-                        int Hh = 0, V = 0;
-                        for (int i = 0; i < 8; i++) {
-                            Hh += (i + 1) * ((int)sm.itY[0][1 + 8 + i] - (int)sm.itY[0][1 + 6 - i]);
-                            V += (i + 1) * ((int)sm.itY[1 + 8 + i][0] - (int)sm.itY[1 + 6 - i][0]);
-                        }
-                        const int a = 16 * ((int)sm.itY[16][0] + (int)sm.itY[0][16]);
-                        const int bb = (5 * Hh + 32) >> 6, cc2 = (5 * V + 32) >> 6;
-#pragma unroll
-                        for (int i = 0; i < 8; i++) pv[i] = clip255((a + bb * (c8 + i - 7) + cc2 * (r8 - 7) + 16) >> 5);
-                    }
-                    uint32_t o0 = 0, o1 = 0;
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        o0 |= (uint32_t)clip255(pv[i] + resY[i]) << (8 * i);
-                        o1 |= (uint32_t)clip255(pv[4 + i] + resY[4 + i]) << (8 * i);
-                    }
-                    *reinterpret_cast<uint2 *>(dstY) = make_uint2(o0, o1);
-                }
-                // h264bsdIntraChromaPrediction (:845-915)
-                {
-                    const int cmode = (__ldg(reinterpret_cast<const uint32_t *>(rec) + 5)) & 0xFF;
-                    const uint8_t(*tc)[12] = sm.itC[cp];
-                    int pv[4];
-                    if (cmode == 0) {
-                        const int bxq = lane & 1, byq = cr >> 2;
-                        int sa = 0, sl = 0;
-#pragma unroll
-                        for (int i = 0; i < 4; i++) { sa += tc[0][1 + bxq * 4 + i]; sl += tc[1 + byq * 4 + i][0]; }
-                        int v;
-                        if (bxq == byq) v = (avA && avB) ? (sa + sl + 4) >> 3 : avB ? (sa + 2) >> 2 : avA ? (sl + 2) >> 2 : 128;
-                        else if (bxq == 1) v = avB ? (sa + 2) >> 2 : avA ? (sl + 2) >> 2 : 128;
-                        else v = avA ? (sl + 2) >> 2 : avB ? (sa + 2) >> 2 : 128;
-#pragma unroll
-                        for (int i = 0; i < 4; i++) pv[i] = v;
-                    } else if (cmode == 1) {
-#pragma unroll
-                        for (int i = 0; i < 4; i++) pv[i] = tc[1 + cr][0];
-                    } else if (cmode == 2) {
-#pragma unroll
-                        for (int i = 0; i < 4; i++) pv[i] = tc[0][1 + cc + i];
-                    } else {
-                        int Hh = 0, V = 0;
-#pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            Hh += (i + 1) * ((int)tc[0][1 + 4 + i] - (int)tc[0][1 + 2 - i]);
-                            V += (i + 1) * ((int)tc[1 + 4 + i][0] - (int)tc[1 + 2 - i][0]);
-                        }
-                        const int a = 16 * ((int)tc[8][0] + (int)tc[0][8]);
-                        const int bb = (17 * Hh + 16) >> 5, cc2 = (17 * V + 16) >> 5;
-#pragma unroll
-                        for (int i = 0; i < 4; i++) pv[i] = clip255((a + bb * (cc + i - 3) + cc2 * (cr - 3) + 16) >> 5);
-                    }
-                    uint32_t oc = 0;
-#pragma unroll
-                    for (int i = 0; i < 4; i++) oc |= (uint32_t)clip255(pv[i] + resC[i]) << (8 * i);
-                    *reinterpret_cast<uint32_t *>(dstC) = oc;
-                }
-                __syncwarp();
-            }
+            continue;
         }
-        // publish: every lane's stores, then the flag
-        __threadfence();
+        int resY[8], resC[4];
+        if (h.mask) {
+            mbResidual(h, coef, sm.res, lane, p.errors);
+            laneResidual(sm.res, lane, resY, resC);
+        }
+        uint2 pv;      // this lane's 8 luma prediction samples
+        uint32_t pc;   // and 4 chroma prediction samples
+        if (it.single) {
+            mbarWait(&sm.mbar[buf], phase[buf]);
+            phase[buf] ^= 1;
+            const int xf = it.mvx & 3, yf = it.mvy & 3;
+            const uint8_t *win = sm.lumaWin[buf] + (it.ox & 15);
+            if ((xf | yf) == 0) {
+                pv = lds8(win + (r8 + 2) * kLumaBoxW + c8 + 2);   // h264bsdFillBlock copy (reconstruct.c:1852)
+            } else {
+                // one compact loop (NOT unrolled: this kernel must stay inside the instruction cache)
+                uint32_t o[2] = {0, 0};
+#pragma unroll 1
+                for (int k = 0; k < 8; k++) o[k >> 2] |= (uint32_t)lumaQpel(win, c8 + k, r8, xf, yf) << (8 * (k & 3));
+                pv = make_uint2(o[0], o[1]);
+            }
+            const int cxf = it.mvx & 7, cyf = it.mvy & 7;
+            const uint8_t *cw = sm.chromaWin[buf] + cp * (kChromaBoxW * kChromaBoxH) + cr * kChromaBoxW + cc + (it.cox & 15);
+            if ((cxf | cyf) == 0) {
+                pc = lds4(cw);
+            } else {
+                // PredictChroma (reconstruct.c:415-475)
+                const uint2 ra = lds8(cw), rb = lds8(cw + kChromaBoxW);
+                const int w00 = (8 - cxf) * (8 - cyf), w01 = cxf * (8 - cyf), w10 = (8 - cxf) * cyf, w11 = cxf * cyf;
+                pc = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int A = (ra.x >> (8 * k)) & 0xFF, B = k < 3 ? (ra.x >> (8 * k + 8)) & 0xFF : ra.y & 0xFF;
+                    const int Cc = (rb.x >> (8 * k)) & 0xFF, D = k < 3 ? (rb.x >> (8 * k + 8)) & 0xFF : rb.y & 0xFF;
+                    pc |= (uint32_t)((w00 * A + w01 * B + w10 * Cc + w11 * D + 32) >> 6) << (8 * k);
+                }
+            }
+        } else {
+            // multi-partition macroblocks (inter_prediction.c:361-482): one window per partition, generic path
+            const uint32_t refSlots = __ldg(reinterpret_cast<const uint32_t *>(rec) + 4);
+            const uint32_t subTypes = (__ldg(reinterpret_cast<const uint32_t *>(rec) + 3) >> 24) & 0xFF;
+            const uint32_t *mvw = reinterpret_cast<const uint32_t *>(rec) + 8;
+            const int nParts = h.mbType <= B200_MB_P_8x16 ? 2 : 16;
+#pragma unroll 1
+            for (int pi = 0; pi < nParts; pi++) {
+                int blk, pw, ph;
+                if (h.mbType == B200_MB_P_16x8) { blk = pi * 8; pw = 16; ph = 8; }
+                else if (h.mbType == B200_MB_P_8x16) { blk = pi * 4; pw = 8; ph = 16; }
+                else {
+                    blk = pi;
+                    const int sub = (subTypes >> (2 * (pi >> 2))) & 3, j = pi & 3;
+                    if (sub == 0) { if (j) continue; pw = 8; ph = 8; }
+                    else if (sub == 1) { if (j & 1) continue; pw = 8; ph = 4; }
+                    else if (sub == 2) { if (j & 2) continue; pw = 4; ph = 8; }
+                    else { pw = 4; ph = 4; }
+                }
+                const int px = cBlkX[blk] * 4, py = cBlkY[blk] * 4;
+                const uint32_t mvv = __ldg(mvw + blk);
+                const int mvx = (int)(int16_t)(mvv & 0xFFFF), mvy = (int)(int16_t)(mvv >> 16);
+                const uint32_t refFrame = frameBase + ((refSlots >> (8 * (blk >> 2))) & 0xFF);
+                int ox, cox;
+                issueWindow(sm, buf, g, &lumaMap, &chromaMap, mbx * 16 + px + (mvx >> 2), mby * 16 + py + (mvy >> 2),
+                            ((mbx * 16 + px) >> 1) + (mvx >> 3), ((mby * 16 + py) >> 1) + (mvy >> 3), refFrame, lane, &ox, &cox);
+                mbarWait(&sm.mbar[buf], phase[buf]);
+                phase[buf] ^= 1;
+                const int xf = mvx & 3, yf = mvy & 3;
+                const int lw = 31 - __clz(pw);
+#pragma unroll 1
+                for (int q = lane; q < pw * ph; q += 32) {
+                    const int x = q & (pw - 1), y = q >> lw;
+                    sm.pred[(py + y) * 16 + px + x] = (uint8_t)lumaQpel(sm.lumaWin[buf] + (ox & 15), x, y, xf, yf);
+                }
+                const int cw = pw >> 1, chh = ph >> 1, ncp = cw * chh, lcw = lw - 1;
+                const int cxf = mvx & 7, cyf = mvy & 7;
+#pragma unroll 1
+                for (int q = lane; q < 2 * ncp; q += 32) {
+                    const int pl = q >= ncp, qq = q - pl * ncp;
+                    const int x = qq & (cw - 1), y = qq >> lcw;
+                    const uint8_t *wp = sm.chromaWin[buf] + pl * (kChromaBoxW * kChromaBoxH) + y * kChromaBoxW + x + (cox & 15);
+                    const int A = wp[0], B = wp[1], Cc = wp[kChromaBoxW], D = wp[kChromaBoxW + 1];
+                    sm.pred[256 + pl * 64 + ((py >> 1) + y) * 8 + (px >> 1) + x] =
+                        (uint8_t)(((8 - cxf) * (8 - cyf) * A + cxf * (8 - cyf) * B + (8 - cxf) * cyf * Cc + cxf * cyf * D + 32) >> 6);
+                }
+                __syncwarp();
+            }
+            pv = *reinterpret_cast<const uint2 *>(sm.pred + r8 * 16 + c8);
+            pc = *reinterpret_cast<const uint32_t *>(sm.pred + 256 + cp * 64 + cr * 8 + cc);
+        }
+        // add residual + clip + store (h264bsdWriteOutputBlocks, image.c:172-344)
+        if (h.mask) {
+            uint32_t o0 = 0, o1 = 0, oc = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                o0 |= (uint32_t)clip255((int)((pv.x >> (8 * k)) & 0xFF) + resY[k]) << (8 * k);
+                o1 |= (uint32_t)clip255((int)((pv.y >> (8 * k)) & 0xFF) + resY[4 + k]) << (8 * k);
+                oc |= (uint32_t)clip255((int)((pc >> (8 * k)) & 0xFF) + resC[k]) << (8 * k);
+            }
+            pv = make_uint2(o0, o1);
+            pc = oc;
+        }
+        *reinterpret_cast<uint2 *>(dstY) = pv;
+        *reinterpret_cast<uint32_t *>(dstC) = pc;
         __syncwarp();
-        if (lane == 0) stRelease(doneS + mb, p.serial);
+    }
+    }  // virtual CTA loop
+}
+
+// =====================================================================================================
+// pass B: intra-predicted macroblocks.  They read the unfiltered current picture, so an intra macroblock
+// must come after its intra neighbours (the others were written by pass A).  CTAs take tickets; ticket t
+// is chunk t / nStreams of stream t % nStreams of the stream's wavefront-ordered list, so a warp only ever
+// waits for macroblocks whose CTA took an earlier ticket.
+// =====================================================================================================
+__global__ void __launch_bounds__(kReconWarps * 32) reconIntraKernel(const ReconParams p) {
+    __shared__ IntraWarpSmem smemAll[kReconWarps];
+    __shared__ uint32_t sTicket;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const PoolGeom &g = p.g;
+    if (threadIdx.x == 0) sTicket = atomicAdd(p.ticket, 1u);
+    __syncthreads();
+    const uint32_t t = sTicket;
+    const uint32_t chunk = t / (uint32_t)g.nStreams, s = t - chunk * (uint32_t)g.nStreams;
+    if (chunk >= p.chunksB) return;
+    const StreamJob job = p.jobs[s];
+    const uint32_t e0 = (chunk * kReconWarps + warp) * kChunkB;
+    if (e0 >= job.nB) return;
+    const int n = min((uint32_t)kChunkB, job.nB - e0);
+    IntraWarpSmem &sm = smemAll[warp];
+    uint32_t *doneS = p.done + (size_t)s * g.nMbs;
+    uint8_t *cur = framePtr(p.pool, g, s * (uint32_t)g.numSlots + job.curSlot);
+    const int r8 = lane >> 1, c8 = (lane & 1) * 8;
+    const int cp = lane >> 4, cr = (lane >> 1) & 7, cc = (lane & 1) * 4;
+
+#pragma unroll 1
+    for (int i = 0; i < n; i++) {
+        const uint32_t mb = __ldg(job.order + job.nA + e0 + i);
+        const int mby = (int)(mb / (uint32_t)g.widthMbs), mbx = (int)(mb - (uint32_t)mby * g.widthMbs);
+        const b200_mb_rec *rec = job.recs + mb;
+        const MbHead h = loadHead(rec);
+        const int16_t *coef = job.coefs + (size_t)h.coefIndex * 16;
+        uint8_t *dstY = lumaAt(cur, g, mbx * 16 + c8, mby * 16 + r8);
+        uint8_t *dstC = chromaAt(cur, g, cp, mbx * 8 + cc, mby * 8 + cr);
+        int resY[8], resC[4];
+        if (h.mask) {
+            mbResidual(h, coef, sm.res, lane, p.errors);
+            laneResidual(sm.res, lane, resY, resC);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) resY[k] = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) resC[k] = 0;
+        }
+        const int flags = h.flags;
+        const bool avA = flags & B200_MBF_AVAIL_A, avB = flags & B200_MBF_AVAIL_B;
+        const bool avC = flags & B200_MBF_AVAIL_C, avD = flags & B200_MBF_AVAIL_D;
+        // wait for the intra neighbours this macroblock reads (record byte 28: waitMask)
+        const int waitMask = __ldg(reinterpret_cast<const uint32_t *>(rec) + 7) & 0xFF;
+        if (lane < 4 && ((waitMask >> lane) & 1)) {
+            const int nmb = lane == 0 ? (int)mb - 1 : lane == 1 ? (int)mb - g.widthMbs : lane == 2 ? (int)mb - g.widthMbs + 1 : (int)mb - g.widthMbs - 1;
+            waitFlag(doneS + nmb, p.serial);
+        }
+        __syncwarp();
+        // neighbouring pels (h264bsdGetNeighbourPels :545-614), straight from L2
+        if (lane < 21) {
+            const bool ok = lane == 0 ? avD : lane <= 16 ? avB : avC;
+            sm.itY[0][lane] = ok ? __ldcg(lumaAt(cur, g, mbx * 16 - 1 + lane, mby * 16 - 1)) : 128;
+        }
+        if (lane < 16) sm.itY[1 + lane][0] = avA ? __ldcg(lumaAt(cur, g, mbx * 16 - 1, mby * 16 + lane)) : 128;
+        if (lane < 18) {
+            const int pl = lane >= 9, k = lane - pl * 9;
+            const bool ok = k == 0 ? avD : avB;
+            sm.itC[pl][0][k] = ok ? __ldcg(chromaAt(cur, g, pl, mbx * 8 - 1 + k, mby * 8 - 1)) : 128;
+        }
+        if (lane < 16) {
+            const int pl = lane >> 3, k = lane & 7;
+            sm.itC[pl][1 + k][0] = avA ? __ldcg(chromaAt(cur, g, pl, mbx * 8 - 1, mby * 8 + k)) : 128;
+        }
+        __syncwarp();
+
+        if (h.mbType == B200_MB_I_4x4) {
+            // h264bsdIntra4x4Prediction (:701-833): 16 sequential blocks; lanes 0..15 own one pel each
+            const uint32_t *modew = reinterpret_cast<const uint32_t *>(rec) + 8;
+            const int x = lane & 3, y = (lane >> 2) & 3;
+#pragma unroll 1
+            for (int b = 0; b < 16; b++) {
+                const int bx = cBlkX[b], by = cBlkY[b];
+                const int mode = (__ldg(modew + (b >> 2)) >> (8 * (b & 3))) & 0xFF;
+                const bool bA = bx ? true : avA, bB = by ? true : avB;
+                bool bC;
+                if (by == 0) bC = (bx == 3) ? avC : avB;
+                else if (bx == 3) bC = false;
+                else bC = cRasterToBlk[(by - 1) * 4 + bx + 1] < b;
+                if (lane < 16) {
+                    const uint8_t *above = &sm.itY[by * 4][bx * 4 + 1];   // above[k] = sample (k, -1)
+                    const uint8_t *left = &sm.itY[by * 4 + 1][bx * 4];    // left[k*24] = sample (-1, k)
+                    auto A = [&](int k) -> int { return above[(k > 3 && !bC) ? 3 : k]; };
+                    auto L = [&](int k) -> int { return left[k * 24]; };
+                    int v = intra4x4Pel(mode, x, y, bA, bB, A, L);
+                    if (h.mask) v = clip255(v + sm.res[b][y * 4 + x]);
+                    sm.stage[lane] = (uint8_t)v;
+                }
+                __syncwarp();
+                if (lane < 16) sm.itY[by * 4 + 1 + y][bx * 4 + 1 + x] = sm.stage[lane];
+                __syncwarp();
+            }
+            uint32_t o0 = 0, o1 = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                o0 |= (uint32_t)sm.itY[1 + r8][1 + c8 + k] << (8 * k);
+                o1 |= (uint32_t)sm.itY[1 + r8][1 + c8 + 4 + k] << (8 * k);
+            }
+            *reinterpret_cast<uint2 *>(dstY) = make_uint2(o0, o1);
+        } else {
+            // h264bsdIntra16x16Prediction (:627-687)
+            const int mode = (h.mbType - B200_MB_I_16x16_FIRST) & 3;
+            int pv[8];
+            if (mode == 0) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) pv[k] = sm.itY[0][1 + c8 + k];
+            } else if (mode == 1) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) pv[k] = sm.itY[1 + r8][0];
+            } else if (mode == 2) {
+                int sa = 0, sl = 0;
+                for (int k = 0; k < 16; k++) { sa += sm.itY[0][1 + k]; sl += sm.itY[1 + k][0]; }
+                const int v = (avA && avB) ? (sa + sl + 16) >> 5 : avA ? (sl + 8) >> 4 : avB ? (sa + 8) >> 4 : 128;
+#pragma unroll
+                for (int k = 0; k < 8; k++) pv[k] = v;
+            } else {
+                int Hh = 0, V = 0;
+                for (int k = 0; k < 8; k++) {
+                    Hh += (k + 1) * ((int)sm.itY[0][1 + 8 + k] - (int)sm.itY[0][1 + 6 - k]);
+                    V += (k + 1) * ((int)sm.itY[1 + 8 + k][0] - (int)sm.itY[1 + 6 - k][0]);
+                }
+                const int a = 16 * ((int)sm.itY[16][0] + (int)sm.itY[0][16]);
+                const int bb = (5 * Hh + 32) >> 6, cc2 = (5 * V + 32) >> 6;
+#pragma unroll
+                for (int k = 0; k < 8; k++) pv[k] = clip255((a + bb * (c8 + k - 7) + cc2 * (r8 - 7) + 16) >> 5);
+            }
+            uint32_t o0 = 0, o1 = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                o0 |= (uint32_t)clip255(pv[k] + resY[k]) << (8 * k);
+                o1 |= (uint32_t)clip255(pv[4 + k] + resY[4 + k]) << (8 * k);
+            }
+            *reinterpret_cast<uint2 *>(dstY) = make_uint2(o0, o1);
+        }
+        // h264bsdIntraChromaPrediction (:845-915)
+        {
+            const int cmode = (__ldg(reinterpret_cast<const uint32_t *>(rec) + 5)) & 0xFF;
+            const uint8_t(*tc)[12] = sm.itC[cp];
+            int pv[4];
+            if (cmode == 0) {
+                const int bxq = lane & 1, byq = cr >> 2;
+                int sa = 0, sl = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) { sa += tc[0][1 + bxq * 4 + k]; sl += tc[1 + byq * 4 + k][0]; }
+                int v;
+                if (bxq == byq) v = (avA && avB) ? (sa + sl + 4) >> 3 : avB ? (sa + 2) >> 2 : avA ? (sl + 2) >> 2 : 128;
+                else if (bxq == 1) v = avB ? (sa + 2) >> 2 : avA ? (sl + 2) >> 2 : 128;
+                else v = avA ? (sl + 2) >> 2 : avB ? (sa + 2) >> 2 : 128;
+#pragma unroll
+                for (int k = 0; k < 4; k++) pv[k] = v;
+            } else if (cmode == 1) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) pv[k] = tc[1 + cr][0];
+            } else if (cmode == 2) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) pv[k] = tc[0][1 + cc + k];
+            } else {
+                int Hh = 0, V = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    Hh += (k + 1) * ((int)tc[0][1 + 4 + k] - (int)tc[0][1 + 2 - k]);
+                    V += (k + 1) * ((int)tc[1 + 4 + k][0] - (int)tc[1 + 2 - k][0]);
+                }
+                const int a = 16 * ((int)tc[8][0] + (int)tc[0][8]);
+                const int bb = (17 * Hh + 16) >> 5, cc2 = (17 * V + 16) >> 5;
+#pragma unroll
+                for (int k = 0; k < 4; k++) pv[k] = clip255((a + bb * (cc + k - 3) + cc2 * (cr - 3) + 16) >> 5);
+            }
+            uint32_t oc = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) oc |= (uint32_t)clip255(pv[k] + resC[k]) << (8 * k);
+            *reinterpret_cast<uint32_t *>(dstC) = oc;
+        }
+        // publish: all lanes' stores happen-before the release by lane 0
+        __syncwarp();
+        if (lane == 0) { __threadfence(); stRelease(doneS + mb, p.serial); }
     }
 }
 

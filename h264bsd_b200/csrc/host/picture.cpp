@@ -637,6 +637,35 @@ void PictureState::finalizeRecords() {
         r.flags = f;
         r.sliceId = aux[a].sliceId;
     }
+    // processing order + which neighbours an intra macroblock has to wait for
+    auto passB = [&](int nb) { return nb >= 0 && recs[nb].mbType > B200_MB_P_8x8REF0 && recs[nb].mbType != B200_MB_I_PCM; };
+    order.resize(picSizeInMbs);
+    uint32_t nA = 0;
+    for (uint32_t a = 0; a < picSizeInMbs; a++)
+        if (!passB((int)a)) order[nA++] = (uint16_t)a;
+    numPassA = nA;
+    numPassB = picSizeInMbs - nA;
+    if (numPassB) {
+        // bucket by wavefront key x + 2y (stable in address order inside a key)
+        const uint32_t nKeys = widthMbs + 2 * heightMbs;
+        std::vector<uint32_t> cnt(nKeys + 1, 0);
+        for (uint32_t a = 0; a < picSizeInMbs; a++)
+            if (passB((int)a)) cnt[a % widthMbs + 2 * (a / widthMbs) + 1]++;
+        for (uint32_t k = 0; k < nKeys; k++) cnt[k + 1] += cnt[k];
+        for (uint32_t a = 0; a < picSizeInMbs; a++)
+            if (passB((int)a)) order[nA + cnt[a % widthMbs + 2 * (a / widthMbs)]++] = (uint16_t)a;
+    }
+    for (uint32_t a = 0; a < picSizeInMbs; a++) {
+        b200_mb_rec &r = recs[a];
+        uint8_t w = 0;
+        if (passB((int)a)) {
+            if ((r.flags & B200_MBF_AVAIL_A) && passB(mbA(a))) w |= B200_MBF_AVAIL_A;
+            if ((r.flags & B200_MBF_AVAIL_B) && passB(mbB(a))) w |= B200_MBF_AVAIL_B;
+            if ((r.flags & B200_MBF_AVAIL_C) && passB(mbC(a))) w |= B200_MBF_AVAIL_C;
+            if ((r.flags & B200_MBF_AVAIL_D) && passB(mbD(a))) w |= B200_MBF_AVAIL_D;
+        }
+        r.waitMask = w;
+    }
 }
 
 // Error path only: macroblocks that never arrived get a record so the picture can still be

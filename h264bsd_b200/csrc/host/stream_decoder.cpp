@@ -230,6 +230,8 @@ void StreamDecoder::finishPicture() {
     hdr.numCoefBlocks = (uint32_t)(pic_.coefs.size() / 16);
     hdr.numErrMbs = numConcealedMbs_;
     hdr.picId = currentPicId_;
+    hdr.numPassA = pic_.numPassA;
+    hdr.numPassB = pic_.numPassB;
 
     int32_t poc = decodePicOrderCnt(poc_, *activeSps_, sliceHeader_, prevNal_);
     if (validSliceInAccessUnit_) {
@@ -241,7 +243,7 @@ void StreamDecoder::finishPicture() {
         hdr.outSlot[i] = (uint8_t)dpb_.pendingOutput(i).slot;
         hdr.outPicIndex[i] = dpb_.pendingOutput(i).picIndex;
     }
-    if (sink_) sink_->submitPicture(hdr, pic_.recs.data(), pic_.coefs.data());
+    if (sink_) sink_->submitPicture(hdr, pic_.recs.data(), pic_.coefs.data(), pic_.order.data());
     picIndex_++;
     pic_.beginPicture();  // h264bsdResetStorage
     picStarted_ = false;

@@ -23,8 +23,8 @@ public:
     virtual ~PictureSink() {}
     // parameter sets activated: frame geometry and number of frame slots are now known
     virtual bool configure(uint32_t widthMbs, uint32_t heightMbs, uint32_t numSlots) = 0;
-    // a complete picture; `recs` (widthMbs*heightMbs records) and `coefs` are only valid during the call
-    virtual bool submitPicture(const b200_pic_hdr &hdr, const b200_mb_rec *recs, const int16_t *coefs) = 0;
+    // a complete picture; `recs` (widthMbs*heightMbs records), `coefs` and `order` are only valid during the call
+    virtual bool submitPicture(const b200_pic_hdr &hdr, const b200_mb_rec *recs, const int16_t *coefs, const uint16_t *order) = 0;
 };
 
 class StreamDecoder {

@@ -16,12 +16,13 @@ public:
     std::vector<b200_pic_hdr> pics;
     std::vector<uint8_t> recs;
     std::vector<uint8_t> coefs;
+    std::vector<uint16_t> order;
     uint32_t widthMbs = 0, heightMbs = 0, numSlots = 0;
     bool configure(uint32_t w, uint32_t h, uint32_t slots) override {
         widthMbs = w; heightMbs = h; numSlots = std::max(numSlots, slots);
         return true;
     }
-    bool submitPicture(const b200_pic_hdr &hdr, const b200_mb_rec *r, const int16_t *c) override {
+    bool submitPicture(const b200_pic_hdr &hdr, const b200_mb_rec *r, const int16_t *c, const uint16_t *o) override {
         b200_pic_hdr h = hdr;
         h.mbRecOffset = recs.size();
         h.coefOffset = coefs.size();
@@ -29,6 +30,7 @@ public:
         recs.insert(recs.end(), (const uint8_t *)r, (const uint8_t *)r + nrec);
         size_t ncoef = (size_t)hdr.numCoefBlocks * B200_COEF_BLOCK_BYTES;
         coefs.insert(coefs.end(), (const uint8_t *)c, (const uint8_t *)c + ncoef);
+        order.insert(order.end(), o, o + (size_t)hdr.widthMbs * hdr.heightMbs);
         pics.push_back(h);
         return true;
     }
@@ -86,13 +88,15 @@ extern "C" b200_tape *h264bsdB200ParseStream(const uint8_t *stream, size_t len, 
     t->mbRecs = (uint8_t *)std::malloc(sink.recs.size() + 64);
     t->coefs = (uint8_t *)std::malloc(sink.coefs.size() + 64);
     t->outputPicIndex = (uint32_t *)std::malloc(sizeof(uint32_t) * (outputs.size() + 1));
-    if (!t->pics || !t->mbRecs || !t->coefs || !t->outputPicIndex) {
+    t->mbOrder = (uint16_t *)std::malloc(sizeof(uint16_t) * (sink.order.size() + 1));
+    if (!t->pics || !t->mbRecs || !t->coefs || !t->outputPicIndex || !t->mbOrder) {
         h264bsdB200FreeTape(t);
         return nullptr;
     }
     std::memcpy(t->pics, sink.pics.data(), sizeof(b200_pic_hdr) * sink.pics.size());
     std::memcpy(t->mbRecs, sink.recs.data(), sink.recs.size());
     std::memcpy(t->coefs, sink.coefs.data(), sink.coefs.size());
+    std::memcpy(t->mbOrder, sink.order.data(), sizeof(uint16_t) * sink.order.size());
     std::memcpy(t->outputPicIndex, outputs.data(), sizeof(uint32_t) * outputs.size());
     t->numOutputs = (uint32_t)outputs.size();
     return t;
@@ -103,6 +107,7 @@ extern "C" void h264bsdB200FreeTape(b200_tape *t) {
     std::free(t->pics);
     std::free(t->mbRecs);
     std::free(t->coefs);
+    std::free(t->mbOrder);
     std::free(t->outputPicIndex);
     std::free(t);
 }

@@ -60,7 +60,8 @@ enum {
 #define B200_COEF_BLOCK_BYTES 32 /* 16 x int16, zig-zag order exactly as parsed */
 
 /*
- * One macroblock.  96 bytes (three 32-byte sectors).
+ * One macroblock.  96 bytes (three 32-byte sectors), plus 2 bytes in the per-picture order list: D = 98 bytes
+ * of work-list per macroblock enter the roofline accounting.
  *
  * coefficient pool layout for this MB, starting at 32-byte block index `coefIndex`
  * (relative to the picture's pool):
@@ -88,7 +89,9 @@ typedef struct b200_mb_rec {
     uint8_t reserved0;        /* 21 */
     uint16_t sliceId;         /* 22 (diagnostic; availability is already resolved in flags) */
     uint8_t refIdx[4];        /* 24 ref_idx_l0 per quadrant (diagnostic / MV-prediction state) */
-    uint8_t reserved1[4];     /* 28 */
+    uint8_t waitMask;         /* 28 intra MBs: B200_MBF_AVAIL_* bits of the neighbours that are themselves intra-predicted in
+                                    this picture (the only macroblocks an intra MB must wait for inside the intra pass) */
+    uint8_t reserved1[3];     /* 29 */
     union {                   /* 32 */
         int16_t mv[16][2];    /* inter: {hor,ver} quarter-pel per 4x4 block, standard block order */
         struct {
@@ -115,7 +118,9 @@ typedef struct b200_pic_hdr {
     uint8_t outSlot[20];   /* ... their frame slots, output order ... */
     uint32_t outPicIndex[20]; /* ... and the decode-order index of the picture held in that slot */
     uint32_t picId;        /* application picId (h264bsdDecode argument) */
-    uint32_t reserved[3];
+    uint32_t numPassA;     /* macroblocks reconstructed without looking at the current picture: inter + I_PCM */
+    uint32_t numPassB;     /* intra-predicted macroblocks (read unfiltered neighbours of the current picture) */
+    uint32_t reserved;
 } b200_pic_hdr;
 
 /* A fully parsed stream in host memory (built by h264bsdB200ParseStream). */
@@ -132,6 +137,10 @@ typedef struct b200_tape {
     b200_pic_hdr *pics;  /* numPics */
     uint8_t *mbRecs;     /* mbRecBytes */
     uint8_t *coefs;      /* coefBytes  */
+    /* processing order, widthMbs*heightMbs uint16 macroblock addresses per picture (picture p at p*nMbs):
+     * first numPassA entries in raster order, then numPassB entries in wavefront order (x + 2y ascending), so
+     * that every macroblock an intra MB depends on precedes it */
+    uint16_t *mbOrder;
     uint32_t numOutputs;        /* pictures in output order, incl. those drained by the final flush */
     uint32_t reserved2;
     uint32_t *outputPicIndex;   /* numOutputs decode-order indices */
