@@ -242,9 +242,11 @@ __global__ void __launch_bounds__(kDeblockWarps * 32) deblockKernel(const Debloc
             }
         }
         HB(7);
-        __threadfence();
         __syncwarp();
-        if (lane == 0) stRelease(doneS + mb, p.serial);
+        if (lane == 0) {
+            if (work) __threadfence();   // this macroblock's stores (all lanes, ordered by the warp barrier) before the flag
+            stRelease(doneS + mb, p.serial);
+        }
         HB(8);
     }
 #undef HB

@@ -23,6 +23,7 @@ struct PoolGeom {
     unsigned long long offCb, offCr;   // plane offsets inside a frame
     unsigned long long frameStride;
     int numSlots, nStreams;
+    unsigned invWidthMbs;     // ceil(2^32 / widthMbs): mb / widthMbs == __umulhi(mb, invWidthMbs) for mb < 65536
 };
 
 // what one stream contributes to one launch (one picture)

@@ -11,7 +11,7 @@
 namespace b200 {
 
 constexpr int kReconWarps = 8;
-constexpr int kChunkA = 4;   // consecutive pass-A list entries per warp (TMA of entry i+1 overlaps the math of entry i)
+constexpr int kChunkA = 8;   // consecutive pass-A list entries per warp (TMA of entry i+1 overlaps the math of entry i)
 constexpr int kChunkB = 2;   // consecutive pass-B (wavefront) entries per warp
 
 struct ReconParams {
@@ -32,6 +32,7 @@ struct __align__(128) InterWarpSmem {
     uint8_t chromaWin[2][2 * kChromaBoxW * kChromaBoxH + 64];  // 2 x 640
     int16_t res[24][16];                                       // 768
     uint8_t pred[384];                                         // 384: multi-partition macroblocks only
+    uint32_t meta[kChunkA][8];                                 // per entry: head words 0..3, refSlots, mv[0], mb address
     uint64_t mbar[2];
     uint32_t pad[12];
 };
@@ -289,6 +290,117 @@ __device__ __forceinline__ uint32_t lds4(const uint8_t *p) {
     return __funnelshift_r(w[0], w[1], sh);
 }
 
+
+// ---- 8-wide luma prediction for one lane (row y, columns x0..x0+7 of a 16x16 partition) --------------------
+// dp4a with unsigned pels and signed taps: the 6-tap filter (1,-5,20,20,-5,1) is two dot products
+__device__ __forceinline__ int dp4aUS(uint32_t pels, int taps, int acc) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(pels), "r"(taps), "r"(acc));
+    return d;
+}
+constexpr int kTapsLo = 0x1414FB01;  // bytes (1, -5, 20, 20)
+constexpr int kTapsHi = 0x000001FB;  // bytes (-5, 1, 0, 0)
+
+// unclipped horizontal 6-tap sums for 8 outputs; rowp points at sample x0-2 of the row (13 samples are read)
+__device__ __forceinline__ void hrow8(const uint8_t *rowp, int *hs) {
+    const uint32_t a = smemAddr(rowp), sh0 = (a & 3u) * 8u;
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(rowp - (a & 3u));
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+    // aligned view: byte k of the row = byte (k + (a&3)) of (w0,w1,w2,w3)
+    const uint32_t v0 = __funnelshift_r(w0, w1, sh0), v1 = __funnelshift_r(w1, w2, sh0), v2 = __funnelshift_r(w2, w3, sh0), v3 = w3 >> sh0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint32_t lo = (k & 3) == 0 ? (k == 0 ? v0 : v1) : __funnelshift_r(k < 4 ? v0 : v1, k < 4 ? v1 : v2, 8 * (k & 3));
+        const uint32_t hi = (k & 3) == 0 ? (k == 0 ? v1 : v2) : __funnelshift_r(k < 4 ? v1 : v2, k < 4 ? v2 : v3, 8 * (k & 3));
+        hs[k] = dp4aUS(hi, kTapsHi, dp4aUS(lo, kTapsLo, 0));
+    }
+}
+// unclipped vertical 6-tap sums for 8 outputs; colp points at sample (x0, y-2); rows are kLumaBoxW apart
+__device__ __forceinline__ void vcol8(const uint8_t *colp, int *vs) {
+    uint2 r[6];
+#pragma unroll
+    for (int t = 0; t < 6; t++) r[t] = lds8(colp + t * kLumaBoxW);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int sel = k & 3;
+        const uint32_t a0 = k < 4 ? r[0].x : r[0].y, a1 = k < 4 ? r[1].x : r[1].y, a2 = k < 4 ? r[2].x : r[2].y;
+        const uint32_t a3 = k < 4 ? r[3].x : r[3].y, a4 = k < 4 ? r[4].x : r[4].y, a5 = k < 4 ? r[5].x : r[5].y;
+        // gather byte `sel` of four rows into one word
+        const uint32_t t01 = __byte_perm(a0, a1, sel | ((4 + sel) << 4));
+        const uint32_t t23 = __byte_perm(a2, a3, sel | ((4 + sel) << 4));
+        const uint32_t lo = __byte_perm(t01, t23, 0x5410);
+        const uint32_t hi = __byte_perm(a4, a5, sel | ((4 + sel) << 4)) & 0xFFFFu;
+        vs[k] = dp4aUS(hi, kTapsHi, dp4aUS(lo, kTapsLo, 0));
+    }
+}
+// clause 8.4.2.2.1 for 8 horizontally adjacent samples: `win` points at window sample (xInt-2, yInt-2) (see W_);
+// (x0, y) = position of the first sample inside the partition; the same arithmetic as lumaQpel, 8 at a time
+__device__ __forceinline__ uint2 lumaQpel8(const uint8_t *win, int x0, int y, int xf, int yf) {
+    int out[8];
+    const bool jfam = (xf == 2 || yf == 2) && xf != 0 && yf != 0;
+    if (!jfam) {
+        int b[8], h[8];
+        const bool useH = xf != 0, useV = yf != 0;
+        if (useH) {
+            hrow8(win + (y + 2 + (yf == 3 ? 1 : 0)) * kLumaBoxW + x0, b);
+#pragma unroll
+            for (int k = 0; k < 8; k++) b[k] = clip255((b[k] + 16) >> 5);
+        }
+        if (useV) {
+            vcol8(win + y * kLumaBoxW + x0 + 2 + (xf == 3 ? 1 : 0), h);
+#pragma unroll
+            for (int k = 0; k < 8; k++) h[k] = clip255((h[k] + 16) >> 5);
+        }
+        if (useH && useV) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) out[k] = (b[k] + h[k] + 1) >> 1;
+        } else if (useH) {
+            const uint2 gpel = lds8(win + (y + 2) * kLumaBoxW + x0 + 2 + (xf >> 1));
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int gk = ((k < 4 ? gpel.x : gpel.y) >> (8 * (k & 3))) & 0xFF;
+                out[k] = xf == 2 ? b[k] : (b[k] + gk + 1) >> 1;
+            }
+        } else {
+            const uint2 gpel = lds8(win + (y + 2 + (yf >> 1)) * kLumaBoxW + x0 + 2);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int gk = ((k < 4 ? gpel.x : gpel.y) >> (8 * (k & 3))) & 0xFF;
+                out[k] = yf == 2 ? h[k] : (h[k] + gk + 1) >> 1;
+            }
+        }
+    } else {
+        int acc[8], bsel[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) { acc[k] = 0; bsel[k] = 0; }
+        const int brow = 2 + (yf == 3 ? 1 : 0);
+#pragma unroll 1
+        for (int t = 0; t < 6; t++) {
+            int hs[8];
+            hrow8(win + (y + t) * kLumaBoxW + x0, hs);
+            const int c = (t == 0 || t == 5) ? 1 : (t == 1 || t == 4) ? -5 : 20;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                acc[k] += c * hs[k];
+                if (t == brow) bsel[k] = hs[k];
+            }
+        }
+        int h[8];
+        if (yf == 2 && xf != 2) {
+            vcol8(win + y * kLumaBoxW + x0 + 2 + (xf == 3 ? 1 : 0), h);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int j = clip255((acc[k] + 512) >> 10);
+            if (xf == 2 && yf == 2) out[k] = j;
+            else if (xf == 2) out[k] = (j + clip255((bsel[k] + 16) >> 5) + 1) >> 1;
+            else out[k] = (j + clip255((h[k] + 16) >> 5) + 1) >> 1;
+        }
+    }
+    return make_uint2((uint32_t)out[0] | ((uint32_t)out[1] << 8) | ((uint32_t)out[2] << 16) | ((uint32_t)out[3] << 24),
+                      (uint32_t)out[4] | ((uint32_t)out[5] << 8) | ((uint32_t)out[6] << 16) | ((uint32_t)out[7] << 24));
+}
+
 // =====================================================================================================
 // pass A: inter-predicted (and I_PCM) macroblocks.  They read only finished reference frames, so there
 // is no ordering between them: plain grid, blockIdx.y = stream, a warp owns kChunkA consecutive entries
@@ -347,18 +459,28 @@ reconInterKernel(const ReconParams p, const __grid_constant__ CUtensorMap lumaMa
     const int r8 = lane >> 1, c8 = (lane & 1) * 8;
     const int cp = lane >> 4, cr = (lane >> 1) & 7, cc = (lane & 1) * 4;
 
+    // the chunk's records are fetched by the first n lanes in parallel (one dependent-load chain per chunk, not per MB)
+    if (lane < n) {
+        const uint32_t mb = __ldg(job.order + e0 + lane);
+        const uint32_t *rw = reinterpret_cast<const uint32_t *>(job.recs + mb);
+        const uint4 hw = __ldg(reinterpret_cast<const uint4 *>(rw));
+        const uint32_t refSlots = __ldg(rw + 4), mv0 = __ldg(rw + 8);
+        uint32_t *m = sm.meta[lane];
+        m[0] = hw.x; m[1] = hw.y; m[2] = hw.z; m[3] = hw.w; m[4] = refSlots; m[5] = mv0; m[6] = mb;
+    }
+    __syncwarp();
     auto prepare = [&](int i, int buf) -> InterInfo {
         InterInfo it;
-        it.mb = __ldg(job.order + e0 + i);
-        const b200_mb_rec *rec = job.recs + it.mb;
-        it.h = loadHead(rec);
+        const uint32_t *m = sm.meta[i];
+        it.mb = m[6];
+        it.h.mbType = m[0] & 0xFF; it.h.qpY = (m[0] >> 8) & 0xFF; it.h.qpC = (m[0] >> 16) & 0xFF; it.h.flags = m[0] >> 24;
+        it.h.mask = m[1]; it.h.coefIndex = m[2];
         it.single = it.h.mbType <= B200_MB_P_16x16;
         it.mvx = it.mvy = 0; it.ox = it.cox = 0;
         if (it.single) {
-            const uint32_t mvv = __ldg(reinterpret_cast<const uint32_t *>(rec) + 8);
-            const uint32_t refSlots = __ldg(reinterpret_cast<const uint32_t *>(rec) + 4);
+            const uint32_t mvv = m[5], refSlots = m[4];
             it.mvx = (int)(int16_t)(mvv & 0xFFFF); it.mvy = (int)(int16_t)(mvv >> 16);
-            const int mby = (int)(it.mb / (uint32_t)g.widthMbs), mbx = (int)(it.mb - (uint32_t)mby * g.widthMbs);
+            const int mby = (int)__umulhi(it.mb, g.invWidthMbs), mbx = (int)(it.mb - (uint32_t)mby * g.widthMbs);
             issueWindow(sm, buf, g, &lumaMap, &chromaMap, mbx * 16 + (it.mvx >> 2), mby * 16 + (it.mvy >> 2),
                         mbx * 8 + (it.mvx >> 3), mby * 8 + (it.mvy >> 3), frameBase + (refSlots & 0xFF), lane, &it.ox, &it.cox);
         }
@@ -373,7 +495,7 @@ reconInterKernel(const ReconParams p, const __grid_constant__ CUtensorMap lumaMa
         if (i + 1 < n) nxt = prepare(i + 1, buf ^ 1);   // the other buffer's previous user finished before this point
         const MbHead &h = it.h;
         const uint32_t mb = it.mb;
-        const int mby = (int)(mb / (uint32_t)g.widthMbs), mbx = (int)(mb - (uint32_t)mby * g.widthMbs);
+        const int mby = (int)__umulhi(mb, g.invWidthMbs), mbx = (int)(mb - (uint32_t)mby * g.widthMbs);
         const b200_mb_rec *rec = job.recs + mb;
         const int16_t *coef = job.coefs + (size_t)h.coefIndex * 16;
         uint8_t *dstY = lumaAt(cur, g, mbx * 16 + c8, mby * 16 + r8);
@@ -401,11 +523,7 @@ reconInterKernel(const ReconParams p, const __grid_constant__ CUtensorMap lumaMa
             if ((xf | yf) == 0) {
                 pv = lds8(win + (r8 + 2) * kLumaBoxW + c8 + 2);   // h264bsdFillBlock copy (reconstruct.c:1852)
             } else {
-                // one compact loop (NOT unrolled: this kernel must stay inside the instruction cache)
-                uint32_t o[2] = {0, 0};
-#pragma unroll 1
-                for (int k = 0; k < 8; k++) o[k >> 2] |= (uint32_t)lumaQpel(win, c8 + k, r8, xf, yf) << (8 * (k & 3));
-                pv = make_uint2(o[0], o[1]);
+                pv = lumaQpel8(win, c8, r8, xf, yf);
             }
             const int cxf = it.mvx & 7, cyf = it.mvy & 7;
             const uint8_t *cw = sm.chromaWin[buf] + cp * (kChromaBoxW * kChromaBoxH) + cr * kChromaBoxW + cc + (it.cox & 15);
