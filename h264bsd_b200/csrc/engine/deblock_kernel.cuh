@@ -11,6 +11,8 @@
 namespace b200 {
 
 constexpr int kDeblockWarps = 8;
+constexpr int kBsChunk = 8;      // stage 1: consecutive macroblocks per warp
+constexpr int kFilterChunk = 4;  // stage 2: consecutive tickets per warp (different streams)
 
 struct DeblockParams {
     uint8_t *pool;
@@ -21,7 +23,8 @@ struct DeblockParams {
     uint32_t *ticket;
     uint32_t serial;
     uint32_t totalTickets;
-    uint32_t *hb;              // optional heartbeat (mapped host memory): [warp*4] = ticket, [warp*4+1] = stage
+    uint32_t *bsWords;         // nStreams * nMbs * 4 words: packed boundary strengths (stage 1 -> stage 2)
+    uint8_t *work;             // nStreams * nMbs: 1 = the macroblock has a non-zero boundary strength
 };
 
 struct __align__(16) DeblockWarpSmem {
@@ -107,63 +110,100 @@ __device__ __forceinline__ int bsPair(const RecView &q, int qb, const RecView &p
     return 0;
 }
 
+// ---- stage 1: boundary strengths, embarrassingly parallel ----------------------------------------------------
+// GetBoundaryStrengths (deblocking.c:1187-1379) for every macroblock: 32 strengths packed as nibbles into 16 bytes
+// (word j = segments 8j..8j+7; segments 0..15 = vertical edge left of raster block, 16..31 = horizontal edge above it)
+// plus one "has work" byte.  Two thirds of the macroblocks of a typical P picture have nothing to filter.
+__global__ void __launch_bounds__(kDeblockWarps * 32) strengthKernel(const DeblockParams p) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const PoolGeom &g = p.g;
+    const uint32_t chunksPerStream = ((uint32_t)g.nMbs + kDeblockWarps * kBsChunk - 1) / (kDeblockWarps * kBsChunk);
+    const uint32_t total = chunksPerStream * (uint32_t)g.nStreams;
+    for (uint32_t v = blockIdx.x; v < total; v += gridDim.x) {
+        const uint32_t s = v / chunksPerStream, chunk = v - s * chunksPerStream;
+        const StreamJob job = p.jobs[s];
+        const uint32_t m0 = (chunk * kDeblockWarps + warp) * kBsChunk;
+#pragma unroll 1
+        for (uint32_t mb = m0; mb < min(m0 + kBsChunk, (uint32_t)g.nMbs); mb++) {
+            const RecView cur{reinterpret_cast<const uint32_t *>(job.recs + mb)};
+            const RecView lef{reinterpret_cast<const uint32_t *>(job.recs + mb - 1)};
+            const RecView top{reinterpret_cast<const uint32_t *>(job.recs + mb - g.widthMbs)};
+            const uint32_t w0 = __ldg(cur.w);
+            const int flags = w0 >> 24;
+            int bs = 0;
+            if (flags & B200_MBF_FILTER_INNER) {   // GetMbFilteringFlags :289-320 (resolved on the host)
+                const bool fLeft = flags & B200_MBF_FILTER_LEFT, fTop = flags & B200_MBF_FILTER_TOP;
+                const int e = lane & 15, bx = e & 3, by = e >> 2;
+                const int qb = cRasterToBlk[by * 4 + bx];
+                const bool curIntra = (w0 & 0xFF) > B200_MB_P_8x8REF0;
+                if (lane < 16) {
+                    if (bx == 0) bs = !fLeft ? 0 : (curIntra || lef.intra()) ? 4 : bsPair(cur, qb, lef, cRasterToBlk[by * 4 + 3]);
+                    else bs = curIntra ? 3 : bsPair(cur, qb, cur, cRasterToBlk[by * 4 + bx - 1]);
+                } else {
+                    if (by == 0) bs = !fTop ? 0 : (curIntra || top.intra()) ? 4 : bsPair(cur, qb, top, cRasterToBlk[12 + bx]);
+                    else bs = curIntra ? 3 : bsPair(cur, qb, cur, cRasterToBlk[(by - 1) * 4 + bx]);
+                }
+            }
+            uint32_t word = (uint32_t)bs << (4 * (lane & 7));
+            word |= __shfl_xor_sync(0xffffffffu, word, 1);
+            word |= __shfl_xor_sync(0xffffffffu, word, 2);
+            word |= __shfl_xor_sync(0xffffffffu, word, 4);
+            const bool any = __ballot_sync(0xffffffffu, word != 0) != 0;
+            const size_t idx = (size_t)s * g.nMbs + mb;
+            if ((lane & 7) == 0) p.bsWords[idx * 4 + (lane >> 3)] = word;
+            if (lane == 0) p.work[idx] = any ? 1 : 0;
+        }
+    }
+}
+
+// ---- stage 2: the filter proper, macroblocks with work only ---------------------------------------------------------
+// Tickets in wavefront order (x + 2y ascending, streams interleaved); a CTA takes kDeblockWarps * kFilterChunk
+// consecutive tickets, so a warp's consecutive tickets belong to different streams.  A macroblock waits for its left,
+// top and top-right neighbours -- the macroblocks whose filtering the reference's raster order puts before it and whose
+// pels it reads or rewrites -- but only for those that have work themselves (the others never touch a pel).
 __global__ void __launch_bounds__(kDeblockWarps * 32) deblockKernel(const DeblockParams p) {
     __shared__ DeblockWarpSmem smemAll[kDeblockWarps];
+    __shared__ uint32_t sBase;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     DeblockWarpSmem &sm = smemAll[warp];
     const PoolGeom &g = p.g;
-    if (p.hb && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&p.hb[65000 * 4], 1u);
 
     for (;;) {
-        uint32_t t = 0;
-        if (lane == 0) t = atomicAdd(p.ticket, 1u);
-        t = __shfl_sync(0xffffffffu, t, 0);
-        const uint32_t gw = blockIdx.x * kDeblockWarps + warp;
-#define HB(stage) do { if (p.hb && lane == 0) { p.hb[gw * 4] = t; p.hb[gw * 4 + 1] = (stage); } } while (0)
-        HB(1);
-        if (t >= p.totalTickets) { HB(99); break; }
-        const uint32_t k = t / (uint32_t)g.nStreams, s = t - k * (uint32_t)g.nStreams;
-        const uint32_t mb = p.order[k];
-        const int mby = (int)(mb / (uint32_t)g.widthMbs), mbx = (int)(mb - (uint32_t)mby * g.widthMbs);
-        const StreamJob job = p.jobs[s];
-        uint32_t *doneS = p.done + (size_t)s * g.nMbs;
-        const RecView cur{reinterpret_cast<const uint32_t *>(job.recs + mb)};
-        const RecView lef{reinterpret_cast<const uint32_t *>(job.recs + mb - 1)};
-        const RecView top{reinterpret_cast<const uint32_t *>(job.recs + mb - g.widthMbs)};
-        const uint32_t w0 = __ldg(cur.w);
-        const int flags = w0 >> 24;
-        bool work = (flags & B200_MBF_FILTER_INNER) != 0;   // GetMbFilteringFlags :289-320 (resolved on the host)
-        const bool fLeft = flags & B200_MBF_FILTER_LEFT, fTop = flags & B200_MBF_FILTER_TOP;
-
-        if (work) {
-            // GetBoundaryStrengths :1187-1379, one lane per 4-pel edge segment
-            const int e = lane & 15, bx = e & 3, by = e >> 2;
-            const int qb = cRasterToBlk[by * 4 + bx];
-            const bool curIntra = cur.intra();
-            int bs;
-            if (lane < 16) {
-                if (bx == 0) bs = !fLeft ? 0 : (curIntra || lef.intra()) ? 4 : bsPair(cur, qb, lef, cRasterToBlk[by * 4 + 3]);
-                else bs = curIntra ? 3 : bsPair(cur, qb, cur, cRasterToBlk[by * 4 + bx - 1]);
-            } else {
-                if (by == 0) bs = !fTop ? 0 : (curIntra || top.intra()) ? 4 : bsPair(cur, qb, top, cRasterToBlk[12 + bx]);
-                else bs = curIntra ? 3 : bsPair(cur, qb, cur, cRasterToBlk[(by - 1) * 4 + bx]);
+        __syncthreads();
+        if (threadIdx.x == 0) sBase = atomicAdd(p.ticket, (uint32_t)(kDeblockWarps * kFilterChunk));
+        __syncthreads();
+        const uint32_t base = sBase;
+        if (base >= p.totalTickets) break;
+#pragma unroll 1
+        for (uint32_t j = 0; j < kFilterChunk; j++) {
+            const uint32_t t = base + warp * kFilterChunk + j;
+            if (t >= p.totalTickets) break;
+            const uint32_t k = t / (uint32_t)g.nStreams, s = t - k * (uint32_t)g.nStreams;
+            const uint32_t mb = p.order[k];
+            const size_t sIdx = (size_t)s * g.nMbs;
+            if (!p.work[sIdx + mb]) continue;   // nothing to filter: this macroblock touches no pel
+            const int mby = (int)__umulhi(mb, g.invWidthMbs), mbx = (int)(mb - (uint32_t)mby * g.widthMbs);
+            const StreamJob job = p.jobs[s];
+            uint32_t *doneS = p.done + sIdx;
+            const RecView cur{reinterpret_cast<const uint32_t *>(job.recs + mb)};
+            const RecView lef{reinterpret_cast<const uint32_t *>(job.recs + mb - 1)};
+            const RecView top{reinterpret_cast<const uint32_t *>(job.recs + mb - g.widthMbs)};
+            const uint32_t w0 = __ldg(cur.w);
+            const int flags = w0 >> 24;
+            const bool fLeft = flags & B200_MBF_FILTER_LEFT, fTop = flags & B200_MBF_FILTER_TOP;
+            if (lane < 4) {
+                const uint32_t wv = p.bsWords[(sIdx + mb) * 4 + lane];
+#pragma unroll
+                for (int i = 0; i < 8; i++) sm.bs[lane * 8 + i] = (uint8_t)((wv >> (4 * i)) & 15u);
             }
-            HB(2);
-            sm.bs[lane] = (uint8_t)bs;
-            work = __ballot_sync(0xffffffffu, bs != 0) != 0;
-        }
-        if (work) {
-            HB(3);
-            // the three macroblocks whose filtering must be complete (reference order = raster order)
             if (lane < 3) {
                 int nmb = -1;
                 if (lane == 0 && mbx > 0) nmb = (int)mb - 1;
                 if (lane == 1 && mby > 0) nmb = (int)mb - g.widthMbs;
                 if (lane == 2 && mby > 0 && mbx < g.widthMbs - 1) nmb = (int)mb - g.widthMbs + 1;
-                if (nmb >= 0) waitFlag(doneS + nmb, p.serial);
+                if (nmb >= 0 && p.work[sIdx + nmb]) waitFlag(doneS + nmb, p.serial);
             }
             __syncwarp();
-            HB(4);
             uint8_t *frame = framePtr(p.pool, g, s * (uint32_t)g.numSlots + job.curSlot);
             // stage 20x20 luma + 2x 10x12 chroma (incl. 4 / 2 pels of the left and upper neighbours) from L2
             for (int i = lane; i < 100; i += 32) {
@@ -172,12 +212,11 @@ __global__ void __launch_bounds__(kDeblockWarps * 32) deblockKernel(const Debloc
                 *reinterpret_cast<uint32_t *>(&sm.y[r][wcol * 4]) = v;
             }
             for (int i = lane; i < 60; i += 32) {
-                const int pl = i / 30, j = i - pl * 30, r = j / 3, wcol = j - r * 3;
+                const int pl = i / 30, jj = i - pl * 30, r = jj / 3, wcol = jj - r * 3;
                 const uint32_t v = __ldcg(reinterpret_cast<const uint32_t *>(chromaAt(frame, g, pl, mbx * 8 - 4 + wcol * 4, mby * 8 - 2 + r)));
                 *reinterpret_cast<uint32_t *>(&sm.c[pl][r][wcol * 4]) = v;
             }
             __syncwarp();
-            HB(5);
             // thresholds: GetLumaEdgeThresholds :1390-1458, GetChromaEdgeThresholds :1469-1541
             const uint32_t w3 = __ldg(cur.w + 3);
             const int offA = (int)(int8_t)(w3 & 0xFF), offB = (int)(int8_t)((w3 >> 8) & 0xFF), cqo = (int)(int8_t)((w3 >> 16) & 0xFF);
@@ -185,8 +224,8 @@ __global__ void __launch_bounds__(kDeblockWarps * 32) deblockKernel(const Debloc
             const int qpL = fLeft ? lef.qpY() : qp, qpT = fTop ? top.qpY() : qp;
             if (lane < 16) {
                 const EdgeThr tIn = makeThr(qp, offA, offB), tL = makeThr((qp + qpL + 1) >> 1, offA, offB);
-                // all vertical edges of row `lane`, left to right
-                for (int bx = 0; bx < 4; bx++) {
+#pragma unroll 1
+                for (int bx = 0; bx < 4; bx++) {   // all vertical edges of row `lane`, left to right
                     const int bs = sm.bs[(lane >> 2) * 4 + bx];
                     if (bs) filterLumaLine(&sm.y[4 + lane][4 + bx * 4], 1, bs, bx ? tIn : tL);
                 }
@@ -194,6 +233,7 @@ __global__ void __launch_bounds__(kDeblockWarps * 32) deblockKernel(const Debloc
                 const int pl = (lane - 16) >> 3, r = lane & 7;
                 const int qc = cQpC[clip3(0, 51, qp + cqo)], qcL = cQpC[clip3(0, 51, qpL + cqo)];
                 const EdgeThr tIn = makeThr(qc, offA, offB), tL = makeThr((qc + qcL + 1) >> 1, offA, offB);
+#pragma unroll 1
                 for (int ed = 0; ed < 2; ed++) {
                     const int bs = sm.bs[(r >> 1) * 4 + ed * 2];
                     if (bs) filterChromaLine(&sm.c[pl][2 + r][4 + ed * 4], 1, bs, ed ? tIn : tL);
@@ -202,6 +242,7 @@ __global__ void __launch_bounds__(kDeblockWarps * 32) deblockKernel(const Debloc
             __syncwarp();
             if (lane < 16) {
                 const EdgeThr tIn = makeThr(qp, offA, offB), tT = makeThr((qp + qpT + 1) >> 1, offA, offB);
+#pragma unroll 1
                 for (int by = 0; by < 4; by++) {
                     const int bs = sm.bs[16 + by * 4 + (lane >> 2)];
                     if (bs) filterLumaLine(&sm.y[4 + by * 4][4 + lane], 24, bs, by ? tIn : tT);
@@ -210,13 +251,13 @@ __global__ void __launch_bounds__(kDeblockWarps * 32) deblockKernel(const Debloc
                 const int pl = (lane - 16) >> 3, cx = lane & 7;
                 const int qc = cQpC[clip3(0, 51, qp + cqo)], qcT = cQpC[clip3(0, 51, qpT + cqo)];
                 const EdgeThr tIn = makeThr(qc, offA, offB), tT = makeThr((qc + qcT + 1) >> 1, offA, offB);
+#pragma unroll 1
                 for (int half = 0; half < 2; half++) {
                     const int bs = sm.bs[16 + half * 8 + (cx >> 1)];
                     if (bs) filterChromaLine(&sm.c[pl][2 + half * 4][4 + cx], 12, bs, half ? tIn : tT);
                 }
             }
             __syncwarp();
-            HB(6);
             // write back: own rows incl. the 4 columns of the left neighbour, then the 4 rows of the upper neighbour
             for (int i = lane; i < 80; i += 32) {
                 const int r = i / 5, wcol = i - r * 5;
@@ -230,7 +271,7 @@ __global__ void __launch_bounds__(kDeblockWarps * 32) deblockKernel(const Debloc
                     *reinterpret_cast<const uint32_t *>(&sm.y[r][4 + wcol * 4]);
             }
             for (int i = lane; i < 48; i += 32) {
-                const int pl = i / 24, j = i - pl * 24, r = j / 3, wcol = j - r * 3;
+                const int pl = i / 24, jj = i - pl * 24, r = jj / 3, wcol = jj - r * 3;
                 if (wcol == 0 && mbx == 0) continue;
                 *reinterpret_cast<uint32_t *>(chromaAt(frame, g, pl, mbx * 8 - 4 + wcol * 4, mby * 8 + r)) =
                     *reinterpret_cast<const uint32_t *>(&sm.c[pl][2 + r][wcol * 4]);
@@ -240,16 +281,14 @@ __global__ void __launch_bounds__(kDeblockWarps * 32) deblockKernel(const Debloc
                 *reinterpret_cast<uint32_t *>(chromaAt(frame, g, pl, mbx * 8 + wcol * 4, mby * 8 - 2 + r)) =
                     *reinterpret_cast<const uint32_t *>(&sm.c[pl][r][4 + wcol * 4]);
             }
+            // publish: all lanes' stores happen-before the release by lane 0
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence();
+                stRelease(doneS + mb, p.serial);
+            }
         }
-        HB(7);
-        __syncwarp();
-        if (lane == 0) {
-            if (work) __threadfence();   // this macroblock's stores (all lanes, ordered by the warp barrier) before the flag
-            stRelease(doneS + mb, p.serial);
-        }
-        HB(8);
     }
-#undef HB
 }
 
 // ---- border replication -------------------------------------------------------------------------------
@@ -257,13 +296,11 @@ struct BorderParams {
     uint8_t *pool;
     PoolGeom g;
     const StreamJob *jobs;
-    uint32_t *hb;
 };
 // one warp per row of one plane (incl. border rows) of one stream's current frame
 __global__ void __launch_bounds__(256) borderKernel(const BorderParams p) {
     const PoolGeom &g = p.g;
     const int lane = threadIdx.x & 31;
-    if (p.hb && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&p.hb[65001 * 4], 1u);
     const int rowsTotal = g.rowsY + 2 * g.rowsC;
     const long long task = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (task >= (long long)rowsTotal * g.nStreams) return;

@@ -54,6 +54,7 @@ void Batch::destroy() {
         if (t.owned) { cudaFree(t.recs); cudaFree(t.coefs); cudaFree(t.order); }
     }
     tapes_.clear();
+    cudaFree(dBsWords_); cudaFree(dWork_);
     cudaFree(pool_); cudaFree(dOrder_); cudaFree(dDoneRecon_); cudaFree(dDoneDeblock_); cudaFree(dCounters_);
     cudaFree(dJobs_); cudaFree(dStage_[0]); cudaFree(dStage_[1]); cudaFree(dConvert_); cudaFree(dSlots_);
     if (hStage_[0]) cudaFreeHost(hStage_[0]);
@@ -121,6 +122,8 @@ bool Batch::create(int device, uint32_t nStreams, uint32_t widthMbs, uint32_t he
     CK(cudaMalloc(&dDoneDeblock_, flagBytes));
     CK(cudaMemsetAsync(dDoneRecon_, 0, flagBytes, stream_));
     CK(cudaMemsetAsync(dDoneDeblock_, 0, flagBytes, stream_));
+    CK(cudaMalloc(&dBsWords_, flagBytes * 4));
+    CK(cudaMalloc(&dWork_, (size_t)nStreams * g.nMbs));
     CK(cudaMalloc(&dCounters_, sizeof(uint32_t) * 8));
     CK(cudaMemsetAsync(dCounters_, 0, sizeof(uint32_t) * 8, stream_));
     CK(cudaMalloc(&dSlots_, sizeof(uint32_t) * nStreams));
@@ -157,6 +160,9 @@ bool Batch::create(int device, uint32_t nStreams, uint32_t widthMbs, uint32_t he
     int occR = 1, occD = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occR, reconInterKernel, kReconWarps * 32, 0));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occD, deblockKernel, kDeblockWarps * 32, 0));
+    int occS = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, strengthKernel, kDeblockWarps * 32, 0));
+    strengthBlocks_ = std::max(1, occS) * numSms_;
     reconBlocks_ = std::max(1, occR) * numSms_;
     deblockBlocks_ = std::max(1, occD) * numSms_;
     tapes_.assign(nStreams, DevTape());
@@ -257,11 +263,11 @@ void Batch::kernelTiming(bool enable) {
     evUsed_ = 0;
 }
 
-bool Batch::kernelTimes(float ms[4], uint32_t *launchesPerStage) {
+bool Batch::kernelTimes(float ms[5], uint32_t *launchesPerStage) {
     CK(cudaSetDevice(device_));
     CK(cudaStreamSynchronize(stream_));
-    ms[0] = ms[1] = ms[2] = ms[3] = 0.f;
-    uint32_t n[4] = {0, 0, 0, 0};
+    ms[0] = ms[1] = ms[2] = ms[3] = ms[4] = 0.f;
+    uint32_t n[5] = {0, 0, 0, 0, 0};
     for (size_t i = 1; i < evUsed_; i++) {
         const int st = evStage_[i];
         if (st < 0) continue;
@@ -270,7 +276,7 @@ bool Batch::kernelTimes(float ms[4], uint32_t *launchesPerStage) {
         ms[st] += d;
         n[st]++;
     }
-    if (launchesPerStage) { launchesPerStage[0] = n[0]; launchesPerStage[1] = n[1]; launchesPerStage[2] = n[2]; launchesPerStage[3] = n[3]; }
+    if (launchesPerStage) { launchesPerStage[0] = n[0]; launchesPerStage[1] = n[1]; launchesPerStage[2] = n[2]; launchesPerStage[3] = n[3]; launchesPerStage[4] = n[4]; }
     evUsed_ = 0;
     return true;
 }
@@ -307,15 +313,20 @@ bool Batch::launchPicture(const StreamJob *dJobs, uint32_t maxA, uint32_t maxB, 
     if (deblock) {
         DeblockParams dp;
         dp.pool = pool_; dp.g = g_; dp.jobs = dJobs; dp.order = dOrder_; dp.done = dDoneDeblock_;
-        dp.ticket = dCounters_ + 1; dp.serial = serial_; dp.totalTickets = total; dp.hb = hbDev_;
-        const int blocks = (int)std::min<uint32_t>((uint32_t)deblockBlocks_, (total + kDeblockWarps - 1) / kDeblockWarps);
-        deblockKernel<<<blocks, kDeblockWarps * 32, 0, stream_>>>(dp);
+        dp.ticket = dCounters_ + 1; dp.serial = serial_; dp.totalTickets = total;
+        dp.bsWords = dBsWords_; dp.work = dWork_;
+        const uint32_t chunks = ((uint32_t)g_.nMbs + kDeblockWarps * kBsChunk - 1) / (kDeblockWarps * kBsChunk) * (uint32_t)g_.nStreams;
+        strengthKernel<<<std::min<uint32_t>(chunks, (uint32_t)strengthBlocks_), kDeblockWarps * 32, 0, stream_>>>(dp);
+        launches_++;
+        mark(4);
+        const uint32_t ctas = (total + kDeblockWarps * kFilterChunk - 1) / (kDeblockWarps * kFilterChunk);
+        deblockKernel<<<std::min<uint32_t>(ctas, (uint32_t)deblockBlocks_), kDeblockWarps * 32, 0, stream_>>>(dp);
         launches_++;
         mark(1);
     }
     {
         BorderParams bp;
-        bp.pool = pool_; bp.g = g_; bp.jobs = dJobs; bp.hb = hbDev_;
+        bp.pool = pool_; bp.g = g_; bp.jobs = dJobs;
         const long long rows = (long long)(g_.rowsY + 2 * g_.rowsC) * g_.nStreams;
         const int blocks = (int)((rows + 7) / 8);
         borderKernel<<<blocks, 256, 0, stream_>>>(bp);
@@ -442,7 +453,7 @@ bool Batch::writeFrame(uint32_t stream, uint32_t slot, const uint8_t *src) {
     CK(cudaMalloc(&dJob, sizeof job));
     CK(cudaMemcpyAsync(dJob, &job, sizeof job, cudaMemcpyHostToDevice, stream_));
     BorderParams bp;
-    bp.pool = f; bp.g = g_; bp.g.nStreams = 1; bp.jobs = dJob; bp.hb = nullptr;
+    bp.pool = f; bp.g = g_; bp.g.nStreams = 1; bp.jobs = dJob;
     const long long rows = (long long)(g_.rowsY + 2 * g_.rowsC);
     borderKernel<<<(int)((rows + 7) / 8), 256, 0, stream_>>>(bp);
     CK(cudaStreamSynchronize(stream_));

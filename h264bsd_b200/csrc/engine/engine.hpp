@@ -39,7 +39,7 @@ public:
     int compareStreams(const uint32_t *slots);
     // per-stage device time (CUDA events on the engine's stream around every launch)
     void kernelTiming(bool enable);
-    bool kernelTimes(float ms[4], uint32_t *launchesPerStage);  // recon pass A, deblock, border, recon pass B; resets the accumulators
+    bool kernelTimes(float ms[5], uint32_t *launchesPerStage);  // recon pass A, deblock filter, border, recon pass B, boundary strengths
     uint32_t idctErrors();
     uint32_t watchdog(int which);  // 0: flag waits that gave up, 1: TMA waits that gave up
 
@@ -71,7 +71,9 @@ private:
     uint8_t *pool_ = nullptr;
     CUtensorMap lumaMap_, chromaMap_;
     uint16_t *dOrder_ = nullptr;
-    uint32_t *dDoneRecon_ = nullptr, *dDoneDeblock_ = nullptr, *dCounters_ = nullptr, *dSlots_ = nullptr;
+    uint32_t *dDoneRecon_ = nullptr, *dDoneDeblock_ = nullptr, *dCounters_ = nullptr, *dSlots_ = nullptr, *dBsWords_ = nullptr;
+    uint8_t *dWork_ = nullptr;
+    int strengthBlocks_ = 0;
     uint32_t serial_ = 0;
     int reconBlocks_ = 0, deblockBlocks_ = 0;
     std::vector<DevTape> tapes_;
