@@ -169,7 +169,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--streams", type=int, default=int(os.environ.get("B200_BENCH_STREAMS", "512")), help="streams per GPU")
-    ap.add_argument("--e2e-streams", type=int, default=int(os.environ.get("B200_BENCH_E2E_STREAMS", "32")))
+    ap.add_argument("--e2e-streams", type=int, default=int(os.environ.get("B200_BENCH_E2E_STREAMS", "0")), help="0 = one per host core")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -283,32 +283,61 @@ def main():
     e2e = None
     if not args.no_e2e:
         from concurrent.futures import ThreadPoolExecutor
-        ne = max(1, min(args.e2e_streams, count))
-        threads = max(1, min(ne, host_cores() // world))
+        from h264bsd_b200 import _lib
+        L = _lib.load()
+        cores_here = max(1, host_cores() // world)
+        ne = max(1, min(args.e2e_streams if args.e2e_streams > 0 else cores_here, count))
+        threads = max(1, min(ne, cores_here))
         b.close()
         eb = Batch(ne, ps.width_mbs, ps.height_mbs, ps.num_slots, device=local)
-        out = np.empty(ps.frame_bytes, np.uint8)
+        fb = ps.frame_bytes
+        host_out = [L.h264bsdB200HostAlloc(fb * ne) for _ in range(2)]   # page-locked landing zones, double buffered by picture
+        assert all(host_out)
+        bits = (C.c_uint8 * len(data)).from_buffer_copy(data)             # the bitstream bytes every stream decodes
+        tapes = [[None] * ne, [None] * ne]     # two sets: the host parses pass i+1 while the GPU side works on pass i
         pool = ThreadPoolExecutor(max_workers=threads)
 
-        def one_pass():
-            h2d0, d2h0 = eb.h2d_bytes(), eb.d2h_bytes()
-            tapes = list(pool.map(lambda _: ParsedStream(data), range(ne)))   # host: NAL/CAVLC/MV prediction/DPB
-            for s, tp in enumerate(tapes):
-                eb.upload(s, tp)                                              # H2D: records + coefficients
+        def parse_one(args_):
+            st_, i = args_
+            if tapes[st_][i] is None:
+                tapes[st_][i] = ParsedStream(bits)
+            else:
+                tapes[st_][i].reparse(bits)     # same arrays: no fresh pages, page-lock kept
+            if not tapes[st_][i].pinned:
+                tapes[st_][i].pin()
+            return tapes[st_][i].status
+
+        def start_parse(st_):                  # host: NAL / CAVLC / MV prediction / DPB, one thread per stream
+            return [pool.submit(parse_one, (st_, i)) for i in range(ne)]
+
+        def gpu_side(st_):
+            for s_ in range(ne):
+                eb.upload(s_, tapes[st_][s_])                            # H2D (page-locked): records + coefficients + order lists
             for k in range(ps.num_pics):
-                eb.decode_picture(k)
-                for s in range(ne):                                           # D2H: every output picture of every stream
-                    eb._L.h264bsdB200BatchReadFrame(eb.h, s, ps.pics[k].curSlot, out.ctypes.data)
+                eb.decode_picture(k)                                     # GPU: reconstruct + in-loop filter + border
+                eb.read_picture_all(k, host_out[k & 1], fb)              # D2H: picture k of every stream, packed, page-locked
             eb.sync()
-            return eb.h2d_bytes() - h2d0, eb.d2h_bytes() - d2h0
-        one_pass()
-        reps = max(1, min(args.steps, 2))
+
+        reps = max(2, min(args.steps, 3))
+        fut = start_parse(0)
+        assert not any(f.result() for f in fut)
+        gpu_side(0)                                                       # warm-up pass (allocations, page-locking)
+        fut = start_parse(1)
+        assert not any(f.result() for f in fut)
+        gpu_side(1)
         barrier()
+        h2d0, d2h0 = eb.h2d_bytes(), eb.d2h_bytes()
         t0 = time.time()
-        for _ in range(reps):
-            h2d, d2h = one_pass()
+        fut = start_parse(0)                                              # pass 0 is parsed inside the timed region too
+        for i in range(reps):
+            assert not any(f.result() for f in fut)
+            if i + 1 < reps:
+                fut = start_parse((i + 1) & 1)
+            gpu_side(i & 1)
         dt = (time.time() - t0) / reps
-        ok2 = hashlib.md5(out.tobytes()).hexdigest() == gold["post_frame_md5"][-1]
+        h2d, d2h = (eb.h2d_bytes() - h2d0) // reps, (eb.d2h_bytes() - d2h0) // reps
+        last = np.ctypeslib.as_array(C.cast(host_out[(ps.num_pics - 1) & 1], C.POINTER(C.c_uint8)), shape=(fb * ne,))
+        ok2 = all(hashlib.md5(last[i * fb:(i + 1) * fb].tobytes()).hexdigest() == gold["post_frame_md5"][-1] for i in (0, ne - 1))
         if dist is not None:
             import torch
             tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
@@ -316,8 +345,16 @@ def main():
             dt = float(tt.item())
         e2e = {"value": world * ne * ps.num_pics * nmb / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world,
                "d2h_bytes_per_step": int(d2h) * world, "streams_per_gpu": ne, "host_threads_per_gpu": threads, "bit_exact": bool(ok2),
-               "note": "host bitstream bytes -> host I420 frames through the C-ABI: parse on host threads, tape H2D, GPU replay, "
-                       "every output frame D2H; all inside the timed region"}
+               "seconds_per_pass": dt,
+               "note": "host bitstream bytes -> host I420 frames through the C-ABI: parse on host threads (one per stream, the parse of "
+                       "pass i+1 overlapping the GPU side of pass i), work-list H2D from page-locked memory, GPU replay, every output "
+                       "frame D2H into page-locked memory; all inside the timed region"}
+        for set_ in tapes:
+            for t_ in set_:
+                if t_ is not None:
+                    t_.close()
+        for hp in host_out:
+            L.h264bsdB200HostFree(hp)
         eb.close()
 
     if rank != 0:

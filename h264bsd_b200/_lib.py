@@ -32,7 +32,9 @@ class Tape(C.Structure):
         ("pics", C.POINTER(PicHdr)), ("mbRecs", C.POINTER(C.c_uint8)), ("coefs", C.POINTER(C.c_uint8)),
         ("mbOrder", C.POINTER(C.c_uint16)),
         ("numOutputs", C.c_uint32), ("reserved2", C.c_uint32), ("outputPicIndex", C.POINTER(C.c_uint32)),
-        ("status", C.c_uint32), ("reserved3", C.c_uint32),
+        ("status", C.c_uint32), ("pinned", C.c_uint32),
+        ("capRecs", C.c_uint64), ("capCoefs", C.c_uint64), ("capOrder", C.c_uint64), ("capPics", C.c_uint64),
+        ("capOutputs", C.c_uint32), ("reserved4", C.c_uint32),
     ]
 
 
@@ -45,12 +47,13 @@ LEGACY_SYMBOLS = [
     "h264bsdConvertToRGBA", "h264bsdConvertToBGRA", "h264bsdConvertToYCbCrA",
 ]
 BATCH_SYMBOLS = [
-    "h264bsdB200ParseStream", "h264bsdB200FreeTape", "h264bsdB200DeviceCount", "h264bsdB200BatchCreate",
+    "h264bsdB200ParseStream", "h264bsdB200ReparseStream", "h264bsdB200FreeTape", "h264bsdB200DeviceCount", "h264bsdB200BatchCreate",
     "h264bsdB200BatchDestroy", "h264bsdB200BatchUploadTape", "h264bsdB200BatchReplicateTape",
     "h264bsdB200BatchDecodePicture", "h264bsdB200BatchRun", "h264bsdB200BatchSync", "h264bsdB200BatchNumPics",
     "h264bsdB200BatchTimerStart", "h264bsdB200BatchTimerStop", "h264bsdB200BatchReadFrame", "h264bsdB200BatchWriteFrame",
     "h264bsdB200BatchConvertFrame", "h264bsdB200BatchConvertBench", "h264bsdB200BatchCompareStreams",
-    "h264bsdB200BatchDebugStage", "h264bsdB200BatchIdctErrors", "h264bsdB200BatchWatchdog", "h264bsdB200BatchKernelTiming", "h264bsdB200BatchKernelTimes", "h264bsdB200BatchLaunches", "h264bsdB200BatchH2DBytes",
+    "h264bsdB200BatchDebugStage", "h264bsdB200BatchIdctErrors", "h264bsdB200BatchWatchdog", "h264bsdB200BatchReadPictureAll", "h264bsdB200HostAlloc", "h264bsdB200HostFree",
+    "h264bsdB200PinTape", "h264bsdB200UnpinTape", "h264bsdB200BatchKernelTiming", "h264bsdB200BatchKernelTimes", "h264bsdB200BatchLaunches", "h264bsdB200BatchH2DBytes",
     "h264bsdB200BatchD2HBytes",
 ]
 
@@ -87,6 +90,7 @@ def load():
         getattr(L, n).restype = None; getattr(L, n).argtypes = [u32, u32, vp, vp]
     # batch API
     L.h264bsdB200ParseStream.restype = C.POINTER(Tape); L.h264bsdB200ParseStream.argtypes = [vp, C.c_size_t, u32]
+    L.h264bsdB200ReparseStream.restype = C.POINTER(Tape); L.h264bsdB200ReparseStream.argtypes = [C.POINTER(Tape), vp, C.c_size_t, u32]
     L.h264bsdB200FreeTape.restype = None; L.h264bsdB200FreeTape.argtypes = [C.POINTER(Tape)]
     L.h264bsdB200DeviceCount.restype = C.c_int; L.h264bsdB200DeviceCount.argtypes = []
     L.h264bsdB200BatchCreate.restype = vp; L.h264bsdB200BatchCreate.argtypes = [C.c_int, u32, u32, u32, u32]
@@ -109,6 +113,11 @@ def load():
     L.h264bsdB200BatchIdctErrors.restype = u32; L.h264bsdB200BatchIdctErrors.argtypes = [vp]
     L.h264bsdB200BatchKernelTiming.restype = None; L.h264bsdB200BatchKernelTiming.argtypes = [vp, C.c_int]
     L.h264bsdB200BatchKernelTimes.restype = C.c_int; L.h264bsdB200BatchKernelTimes.argtypes = [vp, C.POINTER(C.c_float), u32p]
+    L.h264bsdB200BatchReadPictureAll.restype = C.c_int; L.h264bsdB200BatchReadPictureAll.argtypes = [vp, u32, vp, C.c_size_t]
+    L.h264bsdB200HostAlloc.restype = vp; L.h264bsdB200HostAlloc.argtypes = [C.c_size_t]
+    L.h264bsdB200HostFree.restype = None; L.h264bsdB200HostFree.argtypes = [vp]
+    L.h264bsdB200PinTape.restype = C.c_int; L.h264bsdB200PinTape.argtypes = [C.POINTER(Tape)]
+    L.h264bsdB200UnpinTape.restype = None; L.h264bsdB200UnpinTape.argtypes = [C.POINTER(Tape)]
     L.h264bsdB200BatchWatchdog.restype = u32; L.h264bsdB200BatchWatchdog.argtypes = [vp, C.c_int]
     for n in ("h264bsdB200BatchLaunches", "h264bsdB200BatchH2DBytes", "h264bsdB200BatchD2HBytes"):
         getattr(L, n).restype = C.c_uint64; getattr(L, n).argtypes = [vp]

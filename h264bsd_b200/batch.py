@@ -9,11 +9,18 @@ class ParsedStream:
 
     def __init__(self, data, no_output_reordering=False):
         self._L = _lib.load()
-        buf = (C.c_uint8 * len(data)).from_buffer_copy(bytes(data))
-        self.ptr = self._L.h264bsdB200ParseStream(buf, len(data), 1 if no_output_reordering else 0)
+        self.ptr = None
+        self.pinned = False
+        self.reparse(data, no_output_reordering)
+
+    def reparse(self, data, no_output_reordering=False):
+        """parse another stream into the same tape (arrays and page-lock are kept)"""
+        buf = data if isinstance(data, C.Array) else (C.c_uint8 * len(data)).from_buffer_copy(bytes(data))
+        self.ptr = self._L.h264bsdB200ReparseStream(self.ptr, buf, len(buf), 1 if no_output_reordering else 0)
         if not self.ptr:
             raise MemoryError("h264bsdB200ParseStream failed")
         t = self.ptr.contents
+        self.pinned = t.pinned == 1
         self.num_pics, self.width_mbs, self.height_mbs, self.num_slots = t.numPics, t.widthMbs, t.heightMbs, t.numSlots
         self.status = t.status
         self.rec_bytes, self.coef_bytes = t.mbRecBytes, t.coefBytes
@@ -32,8 +39,16 @@ class ParsedStream:
     def coded_blocks(self):
         return sum(p.numCoefBlocks for p in self.pics)
 
+    def pin(self):
+        """page-lock the tape for full-speed uploads"""
+        if not self.pinned and self._L.h264bsdB200PinTape(self.ptr) == 0:
+            self.pinned = True
+        return self.pinned
+
     def close(self):
         if self.ptr:
+            if self.pinned:
+                self._L.h264bsdB200UnpinTape(self.ptr)
             self._L.h264bsdB200FreeTape(self.ptr)
             self.ptr = None
 
@@ -87,6 +102,9 @@ class Batch:
         out = np.empty(self.frame_bytes, np.uint8)
         self._ck(self._L.h264bsdB200BatchReadFrame(self.h, stream, slot, out.ctypes.data), "read_frame")
         return out
+
+    def read_picture_all(self, k, dst_ptr, stride):
+        self._ck(self._L.h264bsdB200BatchReadPictureAll(self.h, k, dst_ptr, stride), 'read_picture_all')
 
     def write_frame(self, stream, slot, frame):
         f = np.ascontiguousarray(frame, dtype=np.uint8)

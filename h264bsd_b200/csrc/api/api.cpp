@@ -212,6 +212,32 @@ void h264bsdConvertToYCbCrA(u32 width, u32 height, u8 *data, u32 *pOutput) { con
 // ---------------------------------------------------------------------------------------------
 int h264bsdB200DeviceCount(void) { return deviceCount(); }
 
+void *h264bsdB200HostAlloc(size_t bytes) {
+    void *p = nullptr;
+    if (deviceCount() <= 0 || cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) return nullptr;
+    return p;
+}
+void h264bsdB200HostFree(void *p) { if (p) cudaFreeHost(p); }
+// page-lock a parsed tape's arrays so that uploads run at full PCIe speed (no-op without a device)
+int h264bsdB200PinTape(b200_tape *t) {
+    if (!t || deviceCount() <= 0) return -1;
+    if (t->pinned == 1) return 0;
+    int rc = 0;
+    if (t->mbRecBytes) rc |= cudaHostRegister(t->mbRecs, t->mbRecBytes, cudaHostRegisterPortable) != cudaSuccess;
+    if (t->coefBytes) rc |= cudaHostRegister(t->coefs, t->coefBytes, cudaHostRegisterPortable) != cudaSuccess;
+    rc |= cudaHostRegister(t->mbOrder, (size_t)t->numPics * t->widthMbs * t->heightMbs * 2, cudaHostRegisterPortable) != cudaSuccess;
+    if (rc) cudaGetLastError();
+    t->pinned = rc ? 0 : 1;
+    return rc ? -1 : 0;
+}
+void h264bsdB200UnpinTape(b200_tape *t) {
+    if (!t || t->pinned != 1) return;
+    cudaHostUnregister(t->mbRecs);
+    cudaHostUnregister(t->coefs);
+    cudaHostUnregister(t->mbOrder);
+    t->pinned = 0;
+}
+
 b200_batch *h264bsdB200BatchCreate(int device, uint32_t nStreams, uint32_t widthMbs, uint32_t heightMbs, uint32_t numSlots) {
     Batch *b = new (std::nothrow) Batch();
     if (!b) return nullptr;
@@ -232,6 +258,7 @@ int h264bsdB200BatchSync(b200_batch *h) { return h && B(h)->sync() ? 0 : -1; }
 int h264bsdB200BatchTimerStart(b200_batch *h) { return h && B(h)->timerStart() ? 0 : -1; }
 int h264bsdB200BatchTimerStop(b200_batch *h, float *ms) { return h && ms && B(h)->timerStop(ms) ? 0 : -1; }
 int h264bsdB200BatchReadFrame(b200_batch *h, uint32_t stream, uint32_t slot, uint8_t *dst) { return h && B(h)->readFrame(stream, slot, dst) ? 0 : -1; }
+int h264bsdB200BatchReadPictureAll(b200_batch *h, uint32_t picIndex, uint8_t *dst, size_t strideBytes) { return h && B(h)->readPictureAll(picIndex, dst, strideBytes) ? 0 : -1; }
 int h264bsdB200BatchWriteFrame(b200_batch *h, uint32_t stream, uint32_t slot, const uint8_t *src) { return h && B(h)->writeFrame(stream, slot, src) ? 0 : -1; }
 int h264bsdB200BatchConvertFrame(b200_batch *h, uint32_t stream, uint32_t slot, int mode, uint32_t *dst) { return h && B(h)->convertFrame(stream, slot, mode, dst) ? 0 : -1; }
 int h264bsdB200BatchConvertBench(b200_batch *h, uint32_t stream, uint32_t slot, int mode, int reps, float *ms) { return h && B(h)->convertBench(stream, slot, mode, reps, ms) ? 0 : -1; }

@@ -54,15 +54,13 @@ void Batch::destroy() {
         if (t.owned) { cudaFree(t.recs); cudaFree(t.coefs); cudaFree(t.order); }
     }
     tapes_.clear();
-    cudaFree(dBsWords_); cudaFree(dWork_);
+    cudaFree(dBsWords_); cudaFree(dWork_); cudaFree(dPack_[0]); cudaFree(dPack_[1]);
     cudaFree(pool_); cudaFree(dOrder_); cudaFree(dDoneRecon_); cudaFree(dDoneDeblock_); cudaFree(dCounters_);
     cudaFree(dJobs_); cudaFree(dStage_[0]); cudaFree(dStage_[1]); cudaFree(dConvert_); cudaFree(dSlots_);
     if (hStage_[0]) cudaFreeHost(hStage_[0]);
     if (hStage_[1]) cudaFreeHost(hStage_[1]);
     for (cudaEvent_t e : evPool_) cudaEventDestroy(e);
     evPool_.clear(); evStage_.clear();
-    if (hbHost_) cudaFreeHost(hbHost_);
-    hbHost_ = nullptr;
     if (evA_) cudaEventDestroy(evA_);
     if (evB_) cudaEventDestroy(evB_);
     if (stream_) cudaStreamDestroy(stream_);
@@ -128,11 +126,6 @@ bool Batch::create(int device, uint32_t nStreams, uint32_t widthMbs, uint32_t he
     CK(cudaMemsetAsync(dCounters_, 0, sizeof(uint32_t) * 8, stream_));
     CK(cudaMalloc(&dSlots_, sizeof(uint32_t) * nStreams));
     serial_ = 0;
-    if (std::getenv("H264BSD_B200_HEARTBEAT")) {
-        CK(cudaHostAlloc(&hbHost_, sizeof(uint32_t) * 4 * 65536, cudaHostAllocMapped));
-        std::memset(hbHost_, 0, sizeof(uint32_t) * 4 * 65536);
-        CK(cudaHostGetDevicePointer(&hbDev_, hbHost_, 0));
-    }
 
     // TMA descriptors over the whole pool: luma {x, y, frame}, chroma {x, y, plane, frame}
     EncodeTiledFn enc = getEncodeTiled();
@@ -175,13 +168,20 @@ bool Batch::uploadTape(uint32_t stream, const b200_tape *t) {
     if (t->widthMbs != (uint32_t)g_.widthMbs || t->heightMbs != (uint32_t)g_.heightMbs || t->numSlots > (uint32_t)g_.numSlots) return false;
     CK(cudaSetDevice(device_));
     DevTape &d = tapes_[stream];
-    if (d.owned) { cudaFree(d.recs); cudaFree(d.coefs); cudaFree(d.order); }
-    d = DevTape();
     const size_t orderBytes = (size_t)t->numPics * g_.nMbs * sizeof(uint16_t);
-    CK(cudaMalloc(&d.recs, t->mbRecBytes + 256));
-    CK(cudaMalloc(&d.coefs, t->coefBytes + 256));
-    CK(cudaMalloc(&d.order, orderBytes + 256));
-    d.owned = true;
+    // re-use the device arrays of a previous upload when they are large enough (no cudaMalloc in steady state)
+    if (!d.owned || d.capRecs < t->mbRecBytes || d.capCoefs < t->coefBytes || d.capOrder < orderBytes) {
+        CK(cudaStreamSynchronize(stream_));
+        if (d.owned) { cudaFree(d.recs); cudaFree(d.coefs); cudaFree(d.order); }
+        d = DevTape();
+        d.capRecs = t->mbRecBytes + t->mbRecBytes / 8 + 256;
+        d.capCoefs = t->coefBytes + t->coefBytes / 4 + 256;
+        d.capOrder = orderBytes + 256;
+        CK(cudaMalloc(&d.recs, d.capRecs));
+        CK(cudaMalloc(&d.coefs, d.capCoefs));
+        CK(cudaMalloc(&d.order, d.capOrder));
+        d.owned = true;
+    }
     d.recBytes = t->mbRecBytes; d.coefBytes = t->coefBytes; d.orderBytes = orderBytes;
     CK(cudaMemcpyAsync(d.recs, t->mbRecs, t->mbRecBytes, cudaMemcpyHostToDevice, stream_));
     CK(cudaMemcpyAsync(d.coefs, t->coefs, t->coefBytes, cudaMemcpyHostToDevice, stream_));
@@ -515,6 +515,56 @@ bool convertHostI420(int mode, uint32_t width, uint32_t height, const uint8_t *y
     CK(cudaMemcpy(out, dOut, outBytes, cudaMemcpyDeviceToHost));
     cudaFree(dIn);
     cudaFree(dOut);
+    return true;
+}
+
+// copy picture k of every stream (frame slot of that picture, border stripped) into one contiguous device staging
+// buffer and send it to the host in a single transfer: dst + s * strideBytes receives stream s's coded-size I420 frame
+__global__ void __launch_bounds__(256) packKernel(const uint8_t *pool, PoolGeom g, const StreamJob *jobs, uint8_t *staging) {
+    const uint32_t s = blockIdx.y;
+    const uint8_t *f = pool + (unsigned long long)(s * (uint32_t)g.numSlots + jobs[s].curSlot) * g.frameStride;
+    uint8_t *out = staging + (size_t)s * g.nMbs * 384;
+    const int wordsY = g.W / 4, wordsC = g.W / 8;
+    const long long total = (long long)wordsY * g.H + 2ll * wordsC * (g.H / 2);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        size_t off;
+        if (i < (long long)wordsY * g.H) {
+            const int y = (int)(i / wordsY), x = (int)(i - (long long)y * wordsY);
+            off = (size_t)(y + kPadY) * g.pitchY + kPadY + x * 4;
+        } else {
+            long long j = i - (long long)wordsY * g.H;
+            const int pl = j >= (long long)wordsC * (g.H / 2);
+            if (pl) j -= (long long)wordsC * (g.H / 2);
+            const int y = (int)(j / wordsC), x = (int)(j - (long long)y * wordsC);
+            off = (pl ? g.offCr : g.offCb) + (size_t)(y + kPadC) * g.pitchC + kPadC + x * 4;
+        }
+        reinterpret_cast<uint32_t *>(out)[i] = *reinterpret_cast<const uint32_t *>(f + off);
+    }
+}
+
+bool Batch::readPictureAll(uint32_t k, uint8_t *dst, size_t strideBytes) {
+    if (!created_ || k >= numPics_) return false;
+    CK(cudaSetDevice(device_));
+    const size_t fb = frameBytes();
+    if (!dPack_[0]) {
+        CK(cudaMalloc(&dPack_[0], fb * g_.nStreams));
+        CK(cudaMalloc(&dPack_[1], fb * g_.nStreams));
+        CK(cudaEventCreateWithFlags(&packEv_[0], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&packEv_[1], cudaEventDisableTiming));
+    }
+    const int b = packIdx_ ^= 1;
+    if (packUsed_[b]) CK(cudaEventSynchronize(packEv_[b]));   // the transfer that last used this staging buffer is done
+    dim3 grid(32, g_.nStreams);
+    packKernel<<<grid, 256, 0, stream_>>>(pool_, g_, dJobs_ + (size_t)k * g_.nStreams, dPack_[b]);
+    launches_++;
+    if (strideBytes == fb) {
+        CK(cudaMemcpyAsync(dst, dPack_[b], fb * g_.nStreams, cudaMemcpyDeviceToHost, stream_));
+    } else {
+        CK(cudaMemcpy2DAsync(dst, strideBytes, dPack_[b], fb, fb, g_.nStreams, cudaMemcpyDeviceToHost, stream_));
+    }
+    CK(cudaEventRecord(packEv_[b], stream_));
+    packUsed_[b] = true;
+    d2hBytes_ += fb * g_.nStreams;
     return true;
 }
 

@@ -33,6 +33,8 @@ public:
 
     bool submitHostPicture(uint32_t stream, const b200_pic_hdr &hdr, const b200_mb_rec *recs, const int16_t *coefs, const uint16_t *order);
     bool readFrame(uint32_t stream, uint32_t slot, uint8_t *dst);
+    // picture k's frame of EVERY stream -> dst + s * strideBytes (asynchronous; dst should be pinned; sync() to wait)
+    bool readPictureAll(uint32_t k, uint8_t *dst, size_t strideBytes);
     bool writeFrame(uint32_t stream, uint32_t slot, const uint8_t *src);
     bool convertFrame(uint32_t stream, uint32_t slot, int mode, uint32_t *dstHost);
     bool convertBench(uint32_t stream, uint32_t slot, int mode, int reps, float *ms);
@@ -55,7 +57,7 @@ public:
 private:
     struct DevTape {
         uint8_t *recs = nullptr, *coefs = nullptr, *order = nullptr;
-        size_t recBytes = 0, coefBytes = 0, orderBytes = 0;
+        size_t recBytes = 0, coefBytes = 0, orderBytes = 0, capRecs = 0, capCoefs = 0, capOrder = 0;
         bool owned = false;
         std::vector<b200_pic_hdr> pics;
     };
@@ -92,9 +94,10 @@ private:
     size_t evUsed_ = 0;
     std::vector<int> evStage_;  // stage id of the interval that ENDS at event i (or -1)
     cudaEvent_t nextEvent();
-    uint32_t *hbHost_ = nullptr, *hbDev_ = nullptr;  // debug heartbeat (env H264BSD_B200_HEARTBEAT)
-public:
-    const uint32_t *heartbeat() const { return hbHost_; }
+    uint8_t *dPack_[2] = {nullptr, nullptr};
+    cudaEvent_t packEv_[2] = {nullptr, nullptr};
+    bool packUsed_[2] = {false, false};
+    int packIdx_ = 0;
 };
 
 }  // namespace b200

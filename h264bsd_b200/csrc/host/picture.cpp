@@ -284,11 +284,12 @@ static int median3(int a, int b, int c) {
 
 // clause 8.4.1.3 (MvPrediction*, GetPredictionMv in h264bsd_inter_prediction.c:494-1026).
 // dirHint: 0 median, 1 prefer B (16x8 upper), 2 prefer A (16x8 lower, 8x16 left), 3 prefer C (8x16 right)
-bool PictureState::predictMv(uint32_t cur, int x, int y, int w, int h, uint32_t refIdx, int dirHint, int16_t out[2]) const {
+bool PictureState::predictMv(uint32_t cur, int x, int y, int w, int h, uint32_t refIdx, int dirHint, int16_t out[2],
+                             const NbMv *preA, const NbMv *preB) const {
     (void)h;
     int curZ = kZ[y][x];
-    NbMv a = interNeighbour(cur, x - 1, y, curZ);
-    NbMv b = interNeighbour(cur, x, y - 1, curZ);
+    NbMv a = preA ? *preA : interNeighbour(cur, x - 1, y, curZ);
+    NbMv b = preB ? *preB : interNeighbour(cur, x, y - 1, curZ);
     NbMv c = interNeighbour(cur, x + w, y - 1, curZ);
     if (!c.avail) c = interNeighbour(cur, x - 1, y - 1, curZ);
     if (dirHint == 1 && b.refIdx == refIdx) { out[0] = b.mv[0]; out[1] = b.mv[1]; return true; }
@@ -326,21 +327,21 @@ bool PictureState::deriveInter(MbSyntax &mb, uint32_t mbAddr, const Dpb &dpb) {
             uint32_t refIdx = mb.refIdx[0];
             int16_t mv[2] = {0, 0};
             bool zero = false;
+            const NbMv a = interNeighbour(mbAddr, -1, 0, 0), b = interNeighbour(mbAddr, 0, -1, 0);
             if (mb.mbType == B200_MB_P_SKIP) {
-                NbMv a = interNeighbour(mbAddr, -1, 0, 0), b = interNeighbour(mbAddr, 0, -1, 0);
                 zero = !a.avail || !b.avail || (a.refIdx == 0 && a.mv[0] == 0 && a.mv[1] == 0) ||
                        (b.refIdx == 0 && b.mv[0] == 0 && b.mv[1] == 0);
             }
             if (!zero) {
                 int16_t p[2];
-                predictMv(mbAddr, 0, 0, 4, 4, refIdx, 0, p);
+                predictMv(mbAddr, 0, 0, 4, 4, refIdx, 0, p, &a, &b);
                 mv[0] = (int16_t)(mb.mvd[0][0] + p[0]);
                 mv[1] = (int16_t)(mb.mvd[0][1] + p[1]);
                 if (!mvInRange(mv[0], mv[1])) return false;
             }
             int slot = dpb.refSlot(refIdx);
             if (slot < 0) return false;
-            setMv(0, 0, 4, 4, mv[0], mv[1]);
+            for (int z = 0; z < 16; z++) { r.u.mv[z][0] = mv[0]; r.u.mv[z][1] = mv[1]; }
             for (int q = 0; q < 4; q++) { r.refIdx[q] = (uint8_t)refIdx; r.refSlot[q] = (uint8_t)slot; }
             break;
         }
@@ -510,10 +511,10 @@ bool PictureState::finishMacroblock(MbSyntax &mb, uint32_t mbAddr, int &qpY, con
     r.qpC = kQpC[std::min(51, std::max(0, qpY + pps.chromaQpIndexOffset))];
 
     uint32_t mask = 0;
-    for (int i = 0; i < 24; i++)
-        if (ax.totalCoeff[i]) mask |= 1u << i;
     bool i16 = !isInterType(mb.mbType) && mb.mbType != B200_MB_I_4x4;
     if (mb.mbType != B200_MB_P_SKIP) {
+        for (int i = 0; i < 24; i++)
+            if (ax.totalCoeff[i]) mask |= 1u << i;
         if (i16 && ax.totalCoeff[24]) mask |= B200_CM_LUMA_DC;
         if (ax.totalCoeff[25] || ax.totalCoeff[26]) mask |= B200_CM_CHROMA_DC;
     }
@@ -576,8 +577,10 @@ SliceResult PictureState::decodeSlice(BitReader &br, const SliceHeader &sh, cons
         }
         if (skipRun) {
             skipRun--;
-            mb.clear();
+            // P_Skip: only what finishMacroblock / deriveInter read (slice_data.c:160-166 clears mbPred there)
             mb.mbType = B200_MB_P_SKIP;
+            mb.cbp = 0; mb.qpDelta = 0;
+            mb.refIdx[0] = 0; mb.mvd[0][0] = mb.mvd[0][1] = 0;
         } else {
             prevSkipped = false;
             bool ok = parseMacroblockLayer(br, mb, cur, sh.isI(), sh.numRefIdxL0Active);

@@ -66,7 +66,8 @@ private:
 
     struct NbMv { bool avail; uint32_t refIdx; int16_t mv[2]; };
     NbMv interNeighbour(uint32_t cur, int x, int y, int curZ) const;
-    bool predictMv(uint32_t cur, int x, int y, int w, int h, uint32_t refIdx, int dirHint, int16_t out[2]) const;
+    bool predictMv(uint32_t cur, int x, int y, int w, int h, uint32_t refIdx, int dirHint, int16_t out[2],
+                   const NbMv *preA = nullptr, const NbMv *preB = nullptr) const;
 };
 
 }  // namespace b200

@@ -3,6 +3,9 @@
 // batched engine (pre-parsed work-lists) and by the CPU tests; it drives the
 // same StreamDecoder as the legacy h264bsdDecode() entry point, with the decode loop of
 // posix/test_h264bsd.c:146-177.
+//
+// A tape can be re-used for the next stream (h264bsdB200ReparseStream): its arrays keep their capacity,
+// so steady-state parsing touches no fresh pages and a page-locked tape stays page-locked.
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -11,40 +14,77 @@
 
 namespace b200 {
 
+// growth of one tape array (malloc'd: the tape owns it)
+template <typename T>
+static bool ensure(T *&p, uint64_t &capBytes, uint64_t needBytes) {
+    if (needBytes <= capBytes) return true;
+    uint64_t cap = capBytes ? capBytes : (1u << 20);
+    while (cap < needBytes) cap += cap / 2 + (1u << 20);
+    void *q = std::realloc(p, cap + 64);
+    if (!q) return false;
+    p = (T *)q;
+    capBytes = cap;
+    return true;
+}
+
 class TapeSink : public PictureSink {
 public:
-    std::vector<b200_pic_hdr> pics;
-    std::vector<uint8_t> recs;
-    std::vector<uint8_t> coefs;
-    std::vector<uint16_t> order;
-    uint32_t widthMbs = 0, heightMbs = 0, numSlots = 0;
+    explicit TapeSink(b200_tape *t) : t_(t) {}
+    bool ok = true, repin = false;
     bool configure(uint32_t w, uint32_t h, uint32_t slots) override {
-        widthMbs = w; heightMbs = h; numSlots = std::max(numSlots, slots);
+        t_->widthMbs = w; t_->heightMbs = h;
+        if (slots > t_->numSlots) t_->numSlots = slots;
         return true;
     }
     bool submitPicture(const b200_pic_hdr &hdr, const b200_mb_rec *r, const int16_t *c, const uint16_t *o) override {
+        const size_t nMbs = (size_t)hdr.widthMbs * hdr.heightMbs;
+        const size_t nrec = nMbs * sizeof(b200_mb_rec), ncoef = (size_t)hdr.numCoefBlocks * B200_COEF_BLOCK_BYTES, nord = nMbs * 2;
+        uint64_t orderBytes = (uint64_t)t_->numPics * nMbs * 2;
+        uint64_t picBytes = (uint64_t)t_->numPics * sizeof(b200_pic_hdr);
+        if (t_->pinned == 1 && (t_->mbRecBytes + nrec > t_->capRecs || t_->coefBytes + ncoef > t_->capCoefs || orderBytes + nord > t_->capOrder)) {
+            h264bsdB200UnpinTape(t_);   // never realloc a page-locked block
+            repin = true;
+        }
+        if (!ensure(t_->mbRecs, t_->capRecs, t_->mbRecBytes + nrec) || !ensure(t_->coefs, t_->capCoefs, t_->coefBytes + ncoef) ||
+            !ensure(t_->mbOrder, t_->capOrder, orderBytes + nord) || !ensure(t_->pics, t_->capPics, picBytes + sizeof(b200_pic_hdr))) {
+            ok = false;
+            return false;
+        }
         b200_pic_hdr h = hdr;
-        h.mbRecOffset = recs.size();
-        h.coefOffset = coefs.size();
-        size_t nrec = (size_t)hdr.widthMbs * hdr.heightMbs * sizeof(b200_mb_rec);
-        recs.insert(recs.end(), (const uint8_t *)r, (const uint8_t *)r + nrec);
-        size_t ncoef = (size_t)hdr.numCoefBlocks * B200_COEF_BLOCK_BYTES;
-        coefs.insert(coefs.end(), (const uint8_t *)c, (const uint8_t *)c + ncoef);
-        order.insert(order.end(), o, o + (size_t)hdr.widthMbs * hdr.heightMbs);
-        pics.push_back(h);
+        h.mbRecOffset = t_->mbRecBytes;
+        h.coefOffset = t_->coefBytes;
+        std::memcpy(t_->mbRecs + t_->mbRecBytes, r, nrec);
+        std::memcpy(t_->coefs + t_->coefBytes, c, ncoef);
+        std::memcpy((uint8_t *)t_->mbOrder + orderBytes, o, nord);
+        t_->pics[t_->numPics] = h;
+        t_->mbRecBytes += nrec;
+        t_->coefBytes += ncoef;
+        t_->numPics++;
         return true;
     }
+private:
+    b200_tape *t_;
 };
 
 }  // namespace b200
 
-extern "C" b200_tape *h264bsdB200ParseStream(const uint8_t *stream, size_t len, uint32_t noOutputReordering) {
+extern "C" b200_tape *h264bsdB200ReparseStream(b200_tape *t, const uint8_t *stream, size_t len, uint32_t noOutputReordering) {
     using namespace b200;
-    TapeSink sink;
+    if (!t) {
+        t = (b200_tape *)std::calloc(1, sizeof(b200_tape));
+        if (!t) return nullptr;
+    }
+    // keep arrays + capacities (+ page-lock state), reset the content
+    t->numPics = 0; t->widthMbs = t->heightMbs = t->numSlots = 0;
+    t->cropFlag = t->cropLeft = t->cropWidth = t->cropTop = t->cropHeight = 0;
+    t->videoRange = 0; t->matrixCoefficients = 2;
+    t->mbRecBytes = t->coefBytes = 0;
+    t->numOutputs = 0; t->status = 0;
+    const uint64_t cap0[3] = {t->capRecs, t->capCoefs, t->capOrder};
+
+    TapeSink sink(t);
     StreamDecoder dec(&sink, noOutputReordering != 0);
     std::vector<uint32_t> outputs;
-    b200_tape *t = (b200_tape *)std::calloc(1, sizeof(b200_tape));
-    if (!t) return nullptr;
     const uint8_t *p = stream;
     size_t left = len;
     while (left > 0) {
@@ -74,32 +114,26 @@ extern "C" b200_tape *h264bsdB200ParseStream(const uint8_t *stream, size_t len, 
             break;
         }
     }
+    if (!sink.ok) t->status = MEMALLOC_ERROR;
     if (!t->status) {
         dec.flushBuffer();
         while (const OutPic *o = dec.nextOutput()) outputs.push_back(o->picIndex);
     }
-    t->numPics = (uint32_t)sink.pics.size();
-    t->widthMbs = sink.widthMbs;
-    t->heightMbs = sink.heightMbs;
-    t->numSlots = sink.numSlots;
-    t->mbRecBytes = sink.recs.size();
-    t->coefBytes = sink.coefs.size();
-    t->pics = (b200_pic_hdr *)std::malloc(sizeof(b200_pic_hdr) * (sink.pics.size() + 1));
-    t->mbRecs = (uint8_t *)std::malloc(sink.recs.size() + 64);
-    t->coefs = (uint8_t *)std::malloc(sink.coefs.size() + 64);
-    t->outputPicIndex = (uint32_t *)std::malloc(sizeof(uint32_t) * (outputs.size() + 1));
-    t->mbOrder = (uint16_t *)std::malloc(sizeof(uint16_t) * (sink.order.size() + 1));
-    if (!t->pics || !t->mbRecs || !t->coefs || !t->outputPicIndex || !t->mbOrder) {
+    uint64_t capOut = (uint64_t)t->capOutputs * sizeof(uint32_t);
+    if (!ensure(t->outputPicIndex, capOut, (outputs.size() + 1) * sizeof(uint32_t))) {
         h264bsdB200FreeTape(t);
         return nullptr;
     }
-    std::memcpy(t->pics, sink.pics.data(), sizeof(b200_pic_hdr) * sink.pics.size());
-    std::memcpy(t->mbRecs, sink.recs.data(), sink.recs.size());
-    std::memcpy(t->coefs, sink.coefs.data(), sink.coefs.size());
-    std::memcpy(t->mbOrder, sink.order.data(), sizeof(uint16_t) * sink.order.size());
+    t->capOutputs = (uint32_t)(capOut / sizeof(uint32_t));
     std::memcpy(t->outputPicIndex, outputs.data(), sizeof(uint32_t) * outputs.size());
     t->numOutputs = (uint32_t)outputs.size();
+    (void)cap0;
+    if (sink.repin) t->pinned = 2;   // the arrays moved: the caller may page-lock again
     return t;
+}
+
+extern "C" b200_tape *h264bsdB200ParseStream(const uint8_t *stream, size_t len, uint32_t noOutputReordering) {
+    return h264bsdB200ReparseStream(nullptr, stream, len, noOutputReordering);
 }
 
 extern "C" void h264bsdB200FreeTape(b200_tape *t) {

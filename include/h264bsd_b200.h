@@ -23,6 +23,9 @@ extern "C" {
  * h264bsdDecode, h264bsd_decoder.c:152-515) into a tape.  The input is not modified.
  * tape->status != 0 if the parse stopped on a decoder error.  NULL only on allocation failure. */
 b200_tape *h264bsdB200ParseStream(const uint8_t *stream, size_t len, uint32_t noOutputReordering);
+/* same, re-using `tape`'s arrays (NULL: allocate a new tape).  Steady-state parsing then touches no fresh pages and a
+ * page-locked tape stays page-locked unless an array had to grow (tape->pinned == 2: pin again). */
+b200_tape *h264bsdB200ReparseStream(b200_tape *tape, const uint8_t *stream, size_t len, uint32_t noOutputReordering);
 void h264bsdB200FreeTape(b200_tape *tape);
 
 /* ---- GPU (fail loudly -- NULL / -1 and a message on stderr -- when no CUDA device is usable) ---- */
@@ -30,6 +33,12 @@ void h264bsdB200FreeTape(b200_tape *tape);
 typedef struct b200_batch b200_batch;
 
 int h264bsdB200DeviceCount(void);
+
+/* page-locked host memory for read-backs, and page-locking of a parsed tape for uploads */
+void *h264bsdB200HostAlloc(size_t bytes);
+void h264bsdB200HostFree(void *p);
+int h264bsdB200PinTape(b200_tape *tape);
+void h264bsdB200UnpinTape(b200_tape *tape);
 
 /* nStreams independent streams of one geometry on GPU `device`; numSlots frame slots per stream
  * (tape->numSlots = dpbSize+1, what h264bsdInitDpb allocates: h264bsd_dpb.c:1014-1034). */
@@ -56,6 +65,9 @@ int h264bsdB200BatchTimerStop(b200_batch *batch, float *ms);
 /* frame slot -> contiguous I420 of the coded size (widthMbs*heightMbs*384 bytes), as
  * h264bsdNextOutputPicture hands out (decoder.c:599-623); and the reverse (test hook) */
 int h264bsdB200BatchReadFrame(b200_batch *batch, uint32_t stream, uint32_t slot, uint8_t *dst);
+/* picture `picIndex` of EVERY stream -> dst + s * strideBytes, one packed transfer (asynchronous: call
+ * h264bsdB200BatchSync before reading dst; dst should come from h264bsdB200HostAlloc) */
+int h264bsdB200BatchReadPictureAll(b200_batch *batch, uint32_t picIndex, uint8_t *dst, size_t strideBytes);
 int h264bsdB200BatchWriteFrame(b200_batch *batch, uint32_t stream, uint32_t slot, const uint8_t *src);
 /* h264bsdConvertTo{RGBA(0),BGRA(1),YCbCrA(2)} of a frame slot (decoder.c:1163-1370) into host memory */
 int h264bsdB200BatchConvertFrame(b200_batch *batch, uint32_t stream, uint32_t slot, int mode, uint32_t *dst);

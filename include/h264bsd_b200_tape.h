@@ -145,7 +145,10 @@ typedef struct b200_tape {
     uint32_t reserved2;
     uint32_t *outputPicIndex;   /* numOutputs decode-order indices */
     uint32_t status;            /* 0 ok, else the H264BSD_* code the parse stopped on */
-    uint32_t reserved3;
+    uint32_t pinned;            /* 0 pageable, 1 arrays page-locked (h264bsdB200PinTape), 2 page-lock stale after growth */
+    /* allocation sizes of the arrays (they are kept when a tape is re-used, h264bsdB200ReparseStream) */
+    uint64_t capRecs, capCoefs, capOrder, capPics;
+    uint32_t capOutputs, reserved4;
 } b200_tape;
 
 #ifdef __cplusplus
