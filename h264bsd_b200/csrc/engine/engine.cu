@@ -55,6 +55,7 @@ void Batch::destroy() {
     }
     tapes_.clear();
     cudaFree(dBsWords_); cudaFree(dWork_); cudaFree(dPack_[0]); cudaFree(dPack_[1]);
+    if (copyStream_) { cudaStreamSynchronize(copyStream_); cudaStreamDestroy(copyStream_); copyStream_ = nullptr; }
     cudaFree(pool_); cudaFree(dOrder_); cudaFree(dDoneRecon_); cudaFree(dDoneDeblock_); cudaFree(dCounters_);
     cudaFree(dJobs_); cudaFree(dStage_[0]); cudaFree(dStage_[1]); cudaFree(dConvert_); cudaFree(dSlots_);
     if (hStage_[0]) cudaFreeHost(hStage_[0]);
@@ -364,6 +365,7 @@ bool Batch::sync() {
     if (!created_) return false;
     CK(cudaSetDevice(device_));
     CK(cudaStreamSynchronize(stream_));
+    if (copyStream_) CK(cudaStreamSynchronize(copyStream_));
     return true;
 }
 
@@ -551,18 +553,25 @@ bool Batch::readPictureAll(uint32_t k, uint8_t *dst, size_t strideBytes) {
         CK(cudaMalloc(&dPack_[1], fb * g_.nStreams));
         CK(cudaEventCreateWithFlags(&packEv_[0], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&packEv_[1], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&packedEv_[0], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&packedEv_[1], cudaEventDisableTiming));
+        CK(cudaStreamCreateWithFlags(&copyStream_, cudaStreamNonBlocking));
     }
     const int b = packIdx_ ^= 1;
-    if (packUsed_[b]) CK(cudaEventSynchronize(packEv_[b]));   // the transfer that last used this staging buffer is done
+    // the transfer that last used this staging buffer must be done before it is overwritten (device-side wait)
+    if (packUsed_[b]) CK(cudaStreamWaitEvent(stream_, packEv_[b], 0));
     dim3 grid(32, g_.nStreams);
     packKernel<<<grid, 256, 0, stream_>>>(pool_, g_, dJobs_ + (size_t)k * g_.nStreams, dPack_[b]);
     launches_++;
+    // the transfer runs on its own stream so that the next picture's kernels overlap it
+    CK(cudaEventRecord(packedEv_[b], stream_));
+    CK(cudaStreamWaitEvent(copyStream_, packedEv_[b], 0));
     if (strideBytes == fb) {
-        CK(cudaMemcpyAsync(dst, dPack_[b], fb * g_.nStreams, cudaMemcpyDeviceToHost, stream_));
+        CK(cudaMemcpyAsync(dst, dPack_[b], fb * g_.nStreams, cudaMemcpyDeviceToHost, copyStream_));
     } else {
-        CK(cudaMemcpy2DAsync(dst, strideBytes, dPack_[b], fb, fb, g_.nStreams, cudaMemcpyDeviceToHost, stream_));
+        CK(cudaMemcpy2DAsync(dst, strideBytes, dPack_[b], fb, fb, g_.nStreams, cudaMemcpyDeviceToHost, copyStream_));
     }
-    CK(cudaEventRecord(packEv_[b], stream_));
+    CK(cudaEventRecord(packEv_[b], copyStream_));
     packUsed_[b] = true;
     d2hBytes_ += fb * g_.nStreams;
     return true;

@@ -95,7 +95,8 @@ private:
     std::vector<int> evStage_;  // stage id of the interval that ENDS at event i (or -1)
     cudaEvent_t nextEvent();
     uint8_t *dPack_[2] = {nullptr, nullptr};
-    cudaEvent_t packEv_[2] = {nullptr, nullptr};
+    cudaEvent_t packEv_[2] = {nullptr, nullptr}, packedEv_[2] = {nullptr, nullptr};
+    cudaStream_t copyStream_ = nullptr;
     bool packUsed_[2] = {false, false};
     int packIdx_ = 0;
 };
