@@ -87,3 +87,187 @@ def test_parse_garbage_does_not_crash():
         data[i] ^= 0x5A
     ps = ParsedStream(bytes(data))
     assert ps.num_pics <= 80
+
+
+# ---- CAVLC tables against the reference's own look-up arrays (needs the reference sources: build container only) ----
+REF_CAVLC = "/root/reference/src/h264bsd_cavlc.c"
+REF_VLC = "/root/reference/src/h264bsd_vlc.c"
+
+
+def _ref_arrays(path):
+    txt = open(path, encoding="latin1").read()
+    out = {}
+    for m in re.finditer(r"static const u(?:8|16|32) (\w+)\[\d*\]\s*=\s*\{([^}]*)\}", txt):
+        out[m.group(1)] = [int(x, 0) for x in re.findall(r"0x[0-9a-fA-F]+|\d+", m.group(2))]
+    return out
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CAVLC), reason="reference sources not mounted")
+def test_cavlc_tables_match_reference():
+    """every 16-bit prefix decodes to the same (length, TrailingOnes, TotalCoeff) / total_zeros / run_before as the
+    reference's DecodeCoeffToken / DecodeTotalZeros / DecodeRunBefore (h264bsd_cavlc.c:400-700)"""
+    A = _ref_arrays(REF_CAVLC)
+    L = _lib.load()
+    L.b200_cavlc_probe.restype = C.c_uint32
+    L.b200_cavlc_probe.argtypes = [C.c_int, C.c_int, C.c_uint32]
+
+    def ref_token(bits, nc):
+        if nc < 0:
+            v = A["coeffTokenMinus1_0"][bits >> 13] or A["coeffTokenMinus1_1"][bits >> 8]
+        elif nc < 2:
+            if bits >= 0x8000: v = 0x0001
+            elif bits >= 0x0C00: v = A["coeffToken0_0"][bits >> 10]
+            elif bits >= 0x0100: v = A["coeffToken0_1"][bits >> 6]
+            elif bits >= 0x0020: v = A["coeffToken0_2"][(bits >> 2) - 8]
+            else: v = A["coeffToken0_3"][bits]
+        elif nc < 4:
+            if bits >= 0x8000: v = 0x0002 if bits & 0x4000 else 0x0822
+            elif bits >= 0x1000: v = A["coeffToken2_0"][bits >> 10]
+            elif bits >= 0x0200: v = A["coeffToken2_1"][bits >> 7]
+            else: v = A["coeffToken2_2"][bits >> 2]
+        elif nc < 8:
+            v = A["coeffToken4_0"][bits >> 10] or A["coeffToken4_1"][bits >> 6]
+        else:
+            v = A["coeffToken8"][bits >> 10]
+        return (v & 0x1F, (v >> 5) & 0x3F, (v >> 11) & 0x1F) if v else None
+
+    for nc in (-1, 0, 2, 4, 8):
+        for bits in range(0, 1 << 16, 1 if nc in (0, 2) else 4):
+            mine = L.b200_cavlc_probe(0, nc, bits)
+            got = (mine & 31, (mine >> 5) & 3, mine >> 7) if mine & 31 else None
+            assert got == ref_token(bits, nc), (nc, hex(bits))
+
+    def ref_tz(bits9, tc):
+        t = {1: None, 2: ("totalZeros_2", 3), 3: ("totalZeros_3", 3), 4: ("totalZeros_4", 4), 5: ("totalZeros_5", 4),
+             6: ("totalZeros_6", 3), 7: ("totalZeros_7", 3), 8: ("totalZeros_8", 3), 9: ("totalZeros_9", 3),
+             10: ("totalZeros_10", 4), 11: ("totalZeros_11", 5), 12: ("totalZeros_12", 5), 13: ("totalZeros_13", 6),
+             14: ("totalZeros_14", 7)}
+        if tc == 1:
+            v = A["totalZeros_1_0"][bits9 >> 4] or A["totalZeros_1_1"][bits9]
+        elif tc == 15:
+            v = 0x11 if bits9 >> 8 else 0x01
+        else:
+            v = A[t[tc][0]][bits9 >> t[tc][1]]
+        return (v & 0xF, v >> 4) if v else None
+
+    for tc in range(1, 16):
+        for b9 in range(512):
+            mine = L.b200_cavlc_probe(1, tc, b9 << 7)
+            got = (mine & 15, mine >> 4) if mine & 15 else None
+            assert got == ref_tz(b9, tc), (tc, b9)
+
+    def ref_tz_dc(bits9, tc):
+        b = bits9 >> 6
+        if b > 3: v = 0x01
+        elif tc == 3: v = 0x11
+        elif b > 1: v = 0x12
+        elif tc == 2: v = 0x22
+        elif b: v = 0x23
+        else: v = 0x33
+        return (v & 0xF, v >> 4)
+
+    for tc in range(1, 4):
+        for b9 in range(512):
+            mine = L.b200_cavlc_probe(2, tc, b9 << 7)
+            assert (mine & 15, mine >> 4) == ref_tz_dc(b9, tc), (tc, b9)
+
+    def ref_run(bits11, zl):
+        if zl <= 6:
+            name, sh = {1: ("runBefore_1", 10), 2: ("runBefore_2", 9), 3: ("runBefore_3", 9), 4: ("runBefore_4", 8),
+                        5: ("runBefore_5", 8), 6: ("runBefore_6", 8)}[zl]
+            v = A[name][bits11 >> sh]
+        else:
+            if bits11 >= 0x100: v = ((7 - (bits11 >> 8)) << 4) + 3
+            else:
+                v = 0
+                for k, thr in enumerate((0x80, 0x40, 0x20, 0x10, 0x8, 0x4, 0x2, 0x1)):
+                    if bits11 >= thr:
+                        v = ((7 + k) << 4) | (4 + k)
+                        break
+            if (v >> 4) > zl: v = 0
+        return (v & 0xF, v >> 4) if v else None
+
+    for zl in range(1, 15):
+        for b11 in range(2048):
+            mine = L.b200_cavlc_probe(3, zl, b11 << 5)
+            got = (mine & 15, mine >> 4) if mine & 15 else None
+            if got is not None and got[1] > zl:
+                got = None   # the decoder rejects run_before > zerosLeft, as the reference's INFO(value) > zerosLeft test does
+            assert got == ref_run(b11, zl), (zl, b11)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_VLC), reason="reference sources not mounted")
+def test_coded_block_pattern_mapping_matches_reference():
+    A = _ref_arrays(REF_VLC)
+    L = _lib.load()
+    L.b200_cbp_probe.restype = C.c_uint32
+    L.b200_cbp_probe.argtypes = [C.c_uint32, C.c_int]
+    intra = [v for k, v in A.items() if "ntra" in k and len(v) == 48]
+    inter = [v for k, v in A.items() if "nter" in k and len(v) == 48]
+    assert intra and inter
+    for code in range(48):
+        assert L.b200_cbp_probe(code, 1) == intra[0][code]
+        assert L.b200_cbp_probe(code, 0) == inter[0][code]
+
+
+# ---- multi-GPU host logic on CPU (gloo, world size 2) ----------------------------------------------------------------
+def _gloo_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    sys_path = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import sys
+    sys.path.insert(0, sys_path)
+    import bench
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    first, count = bench.shard_streams(1000, world, rank)
+    # what bench.py reduces across ranks: slowest rank's time, summed work
+    t = torch.tensor([10.0 + rank]); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    n = torch.tensor([float(count)], dtype=torch.float64); dist.all_reduce(n, op=dist.ReduceOp.SUM)
+    dist.barrier()
+    q.put((rank, first, count, float(t.item()), float(n.item())))
+    dist.destroy_process_group()
+
+
+def test_shard_streams_gloo():
+    import bench
+    # static contiguous shards cover every stream exactly once
+    for total, world in ((4096, 8), (1000, 3), (5, 8)):
+        seen = []
+        for r in range(world):
+            first, count = bench.shard_streams(total, world, r)
+            seen += list(range(first, first + count))
+        assert seen == list(range(total))
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs: p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs: p.join(60)
+    assert [r[1:3] for r in res] == [(0, 500), (500, 500)]
+    assert all(r[3] == 11.0 and r[4] == 1000.0 for r in res)
+
+
+def _build_example(tmp_path):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "decode_file")
+    libdir = os.path.join(root, "h264bsd_b200")
+    subprocess.check_call(["gcc", "-Wall", "-Werror", "-I" + os.path.join(root, "include"),
+                           os.path.join(root, "examples", "decode_file.c"), "-L" + libdir, "-lh264bsd_b200",
+                           "-Wl,-rpath," + libdir, "-o", exe])
+    return exe
+
+
+def test_example_links_against_public_headers(tmp_path):
+    """a C program written like posix/test_h264bsd.c:130-179 compiles against include/ alone and links against the
+    shared library (the drop-in boundary); without a GPU it must fail loudly, not decode on the CPU"""
+    import subprocess
+    exe = _build_example(tmp_path)
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe, os.path.join(_oracle.GOLDEN, "test_640x360.h264")], capture_output=True, text=True)
+        assert r.returncode != 0 and "no CUDA device" in r.stderr

@@ -179,3 +179,17 @@ def test_colour_conversion_kernel(parsed, name):
     frames0 = decode_stream(_oracle.stream_bytes(name)[:400000])[0] if name == STREAMS[0] else None
     if frames0 is not None:
         assert np.array_equal(rgba, _oracle.oracle_convert(0, W, H, frames0))
+
+
+def test_example_decoder_matches_oracle(tmp_path):
+    """the C driver of examples/ (the posix/test_h264bsd.c loop) linked against the shared library writes the same
+    I420 file as the reference decoder"""
+    import subprocess
+    from test_cpu_host import _build_example
+    exe = _build_example(tmp_path)
+    name = "test_640x360.h264"
+    out = str(tmp_path / "out.yuv")
+    r = subprocess.run([exe, "-o", out, os.path.join(_oracle.GOLDEN, name)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert f"{GOLD[name]['pictures']} pictures decoded" in r.stdout
+    assert hashlib.md5(open(out, "rb").read()).hexdigest() == GOLD[name]["post_md5"]
