@@ -154,12 +154,15 @@ def algorithmic_bytes(ps):
     pop[types == 31] = 12
     inter = types <= 5
     pass_a = inter | (types == 31)
+    mv0 = recs[:, 32:36].copy().view("<i2")
+    copy = (types <= 1) & (masks == 0) & (((mv0[:, 0] | mv0[:, 1]) & 7) == 0)   # picture.cpp finalizeRecords: plainCopy
     recon = np.where(inter, 768, 384) + 32 * pop + MB_REC_BYTES + 2   # + 2: the macroblock's entry in the order list
     nmb = ps.mbs_per_pic
-    per_pic_recon_a = np.where(pass_a, recon, 0).reshape(-1, nmb).sum(axis=1)
+    per_pic_recon_a = np.where(pass_a & ~copy, recon, 0).reshape(-1, nmb).sum(axis=1)
     per_pic_recon_b = np.where(pass_a, 0, recon).reshape(-1, nmb).sum(axis=1)
+    per_pic_copy = np.where(copy, 768 + 8 + 2, 0).reshape(-1, nmb).sum(axis=1)   # the copy kernel reads 8 bytes of the record
     per_pic_deblock = np.full(ps.num_pics, (768 + MB_REC_BYTES) * nmb, np.int64)
-    return per_pic_recon_a, per_pic_recon_b, per_pic_deblock, float(inter.mean()), float(pop.mean())
+    return per_pic_recon_a, per_pic_recon_b, per_pic_deblock, float(inter.mean()), float(pop.mean()), per_pic_copy, float(copy.mean())
 
 
 def main():
@@ -199,7 +202,7 @@ def main():
     first, count = shard_streams(total_streams, world, rank)
     nmb = ps.mbs_per_pic
     mbs_per_step_rank = count * ps.num_pics * nmb
-    per_pic_recon_bytes, per_pic_intra_bytes, per_pic_deblock_bytes, inter_frac, coded_per_mb = algorithmic_bytes(ps)
+    per_pic_recon_bytes, per_pic_intra_bytes, per_pic_deblock_bytes, inter_frac, coded_per_mb, per_pic_copy_bytes, copy_frac = algorithmic_bytes(ps)
 
     b = Batch(count, ps.width_mbs, ps.height_mbs, ps.num_slots, device=local)
     b.upload(0, ps)
@@ -262,14 +265,20 @@ def main():
     achieved = recon_bytes_per_launch / (recon_ms_per_launch / 1000.0) / 1e9
     deb_bytes_per_launch = float(per_pic_deblock_bytes.mean()) * count
     deb_ms_per_launch = stage_ms["deblock"] / max(1, stage_n["deblock"])
-    roof = {"bound": "hbm", "kernel": "reconInterKernel (fused MC + dequant/IDCT + add + write, TMA-staged reference windows)", "achieved": achieved, "peak": peak,
+    copy_bytes_per_launch = float(per_pic_copy_bytes[per_pic_copy_bytes > 0].mean()) * count
+    copy_ms_per_launch = stage_ms["recon_copy"] / max(1, stage_n["recon_copy"])
+    roof = {"bound": "hbm", "kernel": "reconInterKernel (fused MC + dequant/IDCT + add + write, TMA-staged reference windows; the macroblocks that are "
+                                      "not plain copies)", "achieved": achieved, "peak": peak,
             "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": recon_bytes_per_launch, "ms_per_launch": recon_ms_per_launch,
             "share_of_step": stage_ms["recon"] / max(1e-9, sum(stage_ms.values())),
-            "other_kernels": {"deblockKernel": {"achieved_gbs": deb_bytes_per_launch / (deb_ms_per_launch / 1000.0) / 1e9,
+            "other_kernels": {"reconCopyKernel": {"achieved_gbs": copy_bytes_per_launch / (copy_ms_per_launch / 1000.0) / 1e9, "ms_per_launch": copy_ms_per_launch,
+                                                  "frac": copy_bytes_per_launch / (copy_ms_per_launch / 1000.0) / 1e9 / peak, "share_of_macroblocks": copy_frac},
+                              "deblockKernel": {"achieved_gbs": deb_bytes_per_launch / (deb_ms_per_launch / 1000.0) / 1e9,
                                                 "ms_per_launch": deb_ms_per_launch, "frac": deb_bytes_per_launch / (deb_ms_per_launch / 1000.0) / 1e9 / peak},
                               "reconIntraKernel": {"ms_per_launch": stage_ms["recon_intra"] / max(1, stage_n["recon_intra"]),
                                                    "achieved_gbs": float(per_pic_intra_bytes.mean()) * count / max(1e-9, stage_ms["recon_intra"] / max(1, stage_n["recon_intra"]) / 1000.0) / 1e9},
+                              "strengthKernel": {"ms_per_launch": stage_ms["strength"] / max(1, stage_n["strength"])},
                               "borderKernel": {"ms_per_launch": stage_ms["border"] / max(1, stage_n["border"])}}}
     prof = os.path.join(ROOT, "profiles", "r01_recon_traffic.json")
     if os.path.exists(prof):
@@ -297,26 +306,36 @@ def main():
         tapes = [[None] * ne, [None] * ne]     # two sets: the host parses pass i+1 while the GPU side works on pass i
         pool = ThreadPoolExecutor(max_workers=threads)
 
+        phase = {"parse_wait": 0.0, "upload": 0.0, "pictures": 0.0, "parse_thread_max": 0.0, "parse_thread_mean": 0.0}
+
         def parse_one(args_):
             st_, i = args_
+            tp = time.time()
             if tapes[st_][i] is None:
                 tapes[st_][i] = ParsedStream(bits)
             else:
                 tapes[st_][i].reparse(bits)     # same arrays: no fresh pages, page-lock kept
             if not tapes[st_][i].pinned:
                 tapes[st_][i].pin()
+            tp = time.time() - tp
+            phase["parse_thread_max"] = max(phase["parse_thread_max"], tp)
+            phase["parse_thread_mean"] += tp / ne
             return tapes[st_][i].status
 
         def start_parse(st_):                  # host: NAL / CAVLC / MV prediction / DPB, one thread per stream
             return [pool.submit(parse_one, (st_, i)) for i in range(ne)]
 
         def gpu_side(st_):
+            ta = time.time()
             for s_ in range(ne):
                 eb.upload(s_, tapes[st_][s_])                            # H2D (page-locked): records + coefficients + order lists
+            tb = time.time()
             for k in range(ps.num_pics):
                 eb.decode_picture(k)                                     # GPU: reconstruct + in-loop filter + border
                 eb.read_picture_all(k, host_out[k & 1], fb)              # D2H: picture k of every stream, packed, page-locked
             eb.sync()
+            phase["upload"] += tb - ta
+            phase["pictures"] += time.time() - tb
 
         reps = max(2, min(args.steps, 3))
         fut = start_parse(0)
@@ -327,10 +346,14 @@ def main():
         gpu_side(1)
         barrier()
         h2d0, d2h0 = eb.h2d_bytes(), eb.d2h_bytes()
+        for k_ in phase:
+            phase[k_] = 0.0
         t0 = time.time()
         fut = start_parse(0)                                              # pass 0 is parsed inside the timed region too
         for i in range(reps):
+            tw = time.time()
             assert not any(f.result() for f in fut)
+            phase["parse_wait"] += time.time() - tw
             if i + 1 < reps:
                 fut = start_parse((i + 1) & 1)
             gpu_side(i & 1)
@@ -346,6 +369,7 @@ def main():
         e2e = {"value": world * ne * ps.num_pics * nmb / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world,
                "d2h_bytes_per_step": int(d2h) * world, "streams_per_gpu": ne, "host_threads_per_gpu": threads, "bit_exact": bool(ok2),
                "seconds_per_pass": dt,
+               "phase_seconds_per_pass": {k_: round((v_ if k_ == "parse_thread_max" else v_ / reps), 4) for k_, v_ in phase.items()},
                "note": "host bitstream bytes -> host I420 frames through the C-ABI: parse on host threads (one per stream, the parse of "
                        "pass i+1 overlapping the GPU side of pass i), work-list H2D from page-locked memory, GPU replay, every output "
                        "frame D2H into page-locked memory; all inside the timed region"}

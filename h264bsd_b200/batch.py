@@ -136,11 +136,11 @@ class Batch:
 
     def kernel_times(self):
         """({'recon': ms, 'deblock': ms, 'border': ms}, launches per stage) since the last call"""
-        ms = (C.c_float * 5)()
-        n = (C.c_uint32 * 5)()
+        ms = (C.c_float * 6)()
+        n = (C.c_uint32 * 6)()
         self._ck(self._L.h264bsdB200BatchKernelTimes(self.h, ms, n), 'kernel_times')
-        return ({'recon': ms[0], 'deblock': ms[1], 'border': ms[2], 'recon_intra': ms[3], 'strength': ms[4]},
-                {'recon': n[0], 'deblock': n[1], 'border': n[2], 'recon_intra': n[3], 'strength': n[4]})
+        keys = ('recon', 'deblock', 'border', 'recon_intra', 'strength', 'recon_copy')
+        return ({k: ms[i] for i, k in enumerate(keys)}, {k: n[i] for i, k in enumerate(keys)})
 
     def watchdog(self):
         return (self._L.h264bsdB200BatchWatchdog(self.h, 0), self._L.h264bsdB200BatchWatchdog(self.h, 1))

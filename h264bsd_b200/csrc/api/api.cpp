@@ -266,7 +266,7 @@ int h264bsdB200BatchCompareStreams(b200_batch *h, const uint32_t *slots) { retur
 int h264bsdB200BatchDebugStage(b200_batch *h, uint32_t picIndex, int recon, int deblock) { return h && B(h)->debugStage(picIndex, recon != 0, deblock != 0) ? 0 : -1; }
 uint32_t h264bsdB200BatchIdctErrors(b200_batch *h) { return h ? B(h)->idctErrors() : 0; }
 void h264bsdB200BatchKernelTiming(b200_batch *h, int enable) { if (h) B(h)->kernelTiming(enable != 0); }
-int h264bsdB200BatchKernelTimes(b200_batch *h, float *ms5, uint32_t *launches5) { return h && ms5 && B(h)->kernelTimes(ms5, launches5) ? 0 : -1; }
+int h264bsdB200BatchKernelTimes(b200_batch *h, float *ms6, uint32_t *launches6) { return h && ms6 && B(h)->kernelTimes(ms6, launches6) ? 0 : -1; }
 uint32_t h264bsdB200BatchWatchdog(b200_batch *h, int which) { return h ? B(h)->watchdog(which) : 0; }
 uint64_t h264bsdB200BatchLaunches(b200_batch *h) { return h ? B(h)->launches() : 0; }
 uint64_t h264bsdB200BatchH2DBytes(b200_batch *h) { return h ? B(h)->h2dBytes() : 0; }

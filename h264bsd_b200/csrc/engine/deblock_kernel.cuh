@@ -28,66 +28,62 @@ struct DeblockParams {
 };
 
 struct __align__(16) DeblockWarpSmem {
-    uint8_t y[20][24];      // rows -4..15, cols -4..15 (+4 pad)
-    uint8_t c[2][10][12];   // rows -2..7,  cols -4..7
-    uint8_t bs[32];         // [0..15] vertical edge left of block (bx,by) at by*4+bx ; [16..31] horizontal edge above it
+    uint8_t y[20][32];      // rows -4..15; bytes 12..15 = cols -4..-1 (left neighbour), bytes 16..31 = cols 0..15
+    uint8_t c[2][10][16];   // rows -2..7;  bytes  4..7  = cols -4..-1,                  bytes  8..15 = cols 0..7
+};
+// alpha / beta / tc0 / chroma-qp tables in shared memory: the lanes of a warp look them up at different indices
+// (luma and chroma lanes, inner and macroblock edges), which serialises on the constant cache
+struct DeblockTables {
+    uint8_t alpha[52], beta[52], qpc[52], tc0[52][4];
 };
 
 struct EdgeThr { int alpha, beta, idxA; };
-__device__ __forceinline__ EdgeThr makeThr(int qp, int offA, int offB) {
+__device__ __forceinline__ EdgeThr makeThr(const DeblockTables &tb, int qp, int offA, int offB) {
     EdgeThr t;
     t.idxA = clip3(0, 51, qp + offA);
-    t.alpha = cAlpha[t.idxA];
-    t.beta = cBeta[clip3(0, 51, qp + offB)];
+    t.alpha = tb.alpha[t.idxA];
+    t.beta = tb.beta[clip3(0, 51, qp + offB)];
     return t;
 }
 
-// FilterVerLumaEdge / FilterHorLuma(Edge), deblocking.c:656-965: one line of samples, q0 at *q, p side at -step
-__device__ __forceinline__ void filterLumaLine(uint8_t *q, int step, int bS, const EdgeThr &t) {
-    const int p0 = q[-step], p1 = q[-2 * step], q0 = q[0], q1 = q[step];
-    if (!(abs(p0 - q0) < t.alpha && abs(p1 - p0) < t.beta && abs(q1 - q0) < t.beta)) return;
-    const int p2 = q[-3 * step], q2 = q[2 * step];
+// One line of samples across one edge, luma or chroma, in registers.
+// FilterVerLumaEdge / FilterHorLuma(Edge) deblocking.c:656-965 and FilterVerChromaEdge / FilterHorChroma(Edge) :967-1146:
+// the chroma filter is the luma filter without the p1/q1 updates (bS < 4, tc = tc0 + 1) resp. the luma filter's weak
+// branch (bS == 4), so luma and chroma lanes run the same instructions.  Returns false when the line stays as it is.
+struct EdgeLine { int p3, p2, p1, p0, q0, q1, q2, q3; };
+__device__ __forceinline__ bool filterLine(EdgeLine &v, int bS, const EdgeThr &t, int tc0, bool chroma) {
+    const int p0 = v.p0, p1 = v.p1, q0 = v.q0, q1 = v.q1;
+    if (!(abs(p0 - q0) < t.alpha && abs(p1 - p0) < t.beta && abs(q1 - q0) < t.beta)) return false;
+    const int p2 = v.p2, q2 = v.q2;
+    const bool ap = !chroma && abs(p2 - p0) < t.beta, aq = !chroma && abs(q2 - q0) < t.beta;
     if (bS < 4) {
-        const int tc = cTc0[t.idxA][bS - 1];
-        int tcx = tc;
-        if (abs(p2 - p0) < t.beta) { q[-2 * step] = (uint8_t)(p1 + clip3(-tc, tc, (p2 + ((p0 + q0 + 1) >> 1) - (p1 << 1)) >> 1)); tcx++; }
-        if (abs(q2 - q0) < t.beta) { q[step] = (uint8_t)(q1 + clip3(-tc, tc, (q2 + ((p0 + q0 + 1) >> 1) - (q1 << 1)) >> 1)); tcx++; }
-        const int d = clip3(-tcx, tcx, (((q0 - p0) << 2) + (p1 - q1) + 4) >> 3);
-        q[-step] = (uint8_t)clip255(p0 + d);
-        q[0] = (uint8_t)clip255(q0 - d);
+        const int tc = tc0 + (chroma ? 1 : (int)ap + (int)aq);
+        const int avg = (p0 + q0 + 1) >> 1;
+        if (ap) v.p1 = p1 + clip3(-tc0, tc0, (p2 + avg - (p1 << 1)) >> 1);
+        if (aq) v.q1 = q1 + clip3(-tc0, tc0, (q2 + avg - (q1 << 1)) >> 1);
+        const int d = clip3(-tc, tc, (((q0 - p0) << 2) + (p1 - q1) + 4) >> 3);
+        v.p0 = clip255(p0 + d);
+        v.q0 = clip255(q0 - d);
     } else {
         const bool strong = abs(p0 - q0) < ((t.alpha >> 2) + 2);
-        if (strong && abs(p2 - p0) < t.beta) {
-            const int s = p1 + p0 + q0, p3 = q[-4 * step];
-            q[-step] = (uint8_t)((p2 + 2 * s + q1 + 4) >> 3);
-            q[-2 * step] = (uint8_t)((p2 + s + 2) >> 2);
-            q[-3 * step] = (uint8_t)((2 * p3 + 3 * p2 + s + 4) >> 3);
+        if (strong && ap) {
+            const int sum = p1 + p0 + q0;
+            v.p0 = (p2 + 2 * sum + q1 + 4) >> 3;
+            v.p1 = (p2 + sum + 2) >> 2;
+            v.p2 = (2 * v.p3 + 3 * p2 + sum + 4) >> 3;
         } else {
-            q[-step] = (uint8_t)((2 * p1 + p0 + q1 + 2) >> 2);
+            v.p0 = (2 * p1 + p0 + q1 + 2) >> 2;
         }
-        if (strong && abs(q2 - q0) < t.beta) {
-            const int s = p0 + q0 + q1, q3 = q[3 * step];
-            q[0] = (uint8_t)((p1 + 2 * s + q2 + 4) >> 3);
-            q[step] = (uint8_t)((s + q2 + 2) >> 2);
-            q[2 * step] = (uint8_t)((2 * q3 + 3 * q2 + s + 4) >> 3);
+        if (strong && aq) {
+            const int sum = p0 + q0 + q1;
+            v.q0 = (p1 + 2 * sum + q2 + 4) >> 3;
+            v.q1 = (sum + q2 + 2) >> 2;
+            v.q2 = (2 * v.q3 + 3 * q2 + sum + 4) >> 3;
         } else {
-            q[0] = (uint8_t)((2 * q1 + q0 + p1 + 2) >> 2);
+            v.q0 = (2 * q1 + q0 + p1 + 2) >> 2;
         }
     }
-}
-// FilterVerChromaEdge / FilterHorChroma(Edge), deblocking.c:967-1146
-__device__ __forceinline__ void filterChromaLine(uint8_t *q, int step, int bS, const EdgeThr &t) {
-    const int p0 = q[-step], p1 = q[-2 * step], q0 = q[0], q1 = q[step];
-    if (!(abs(p0 - q0) < t.alpha && abs(p1 - p0) < t.beta && abs(q1 - q0) < t.beta)) return;
-    if (bS < 4) {
-        const int tc = cTc0[t.idxA][bS - 1] + 1;
-        const int d = clip3(-tc, tc, (((q0 - p0) << 2) + (p1 - q1) + 4) >> 3);
-        q[-step] = (uint8_t)clip255(p0 + d);
-        q[0] = (uint8_t)clip255(q0 - d);
-    } else {
-        q[-step] = (uint8_t)((2 * p1 + p0 + q1 + 2) >> 2);
-        q[0] = (uint8_t)((2 * q1 + q0 + p1 + 2) >> 2);
-    }
+    return true;
 }
 
 struct RecView {
@@ -100,58 +96,73 @@ struct RecView {
     __device__ __forceinline__ uint32_t mv(int b) const { return __ldg(w + 8 + b); }
 };
 
-// EdgeBoundaryStrength (:395-411) / InnerBoundaryStrength (:332-355) for two non-intra 4x4 blocks
-__device__ __forceinline__ int bsPair(const RecView &q, int qb, const RecView &p, int pb) {
-    if (((q.coded() >> qb) & 1) || ((p.coded() >> pb) & 1)) return 2;
-    const uint32_t mq = q.mv(qb), mp = p.mv(pb);
-    const int dx = (int)(int16_t)(mq & 0xFFFF) - (int)(int16_t)(mp & 0xFFFF);
-    const int dy = (int)(int16_t)(mq >> 16) - (int)(int16_t)(mp >> 16);
-    if (q.refSlot(qb >> 2) != p.refSlot(pb >> 2) || abs(dx) >= 4 || abs(dy) >= 4) return 1;
-    return 0;
-}
-
 // ---- stage 1: boundary strengths, embarrassingly parallel ----------------------------------------------------
 // GetBoundaryStrengths (deblocking.c:1187-1379) for every macroblock: 32 strengths packed as nibbles into 16 bytes
 // (word j = segments 8j..8j+7; segments 0..15 = vertical edge left of raster block, 16..31 = horizontal edge above it)
 // plus one "has work" byte.  Two thirds of the macroblocks of a typical P picture have nothing to filter.
+//
+// Half a warp per macroblock: lane e owns raster block e and computes the strength of the edge on its left and of the
+// edge above it.  Every load of an iteration is independent of every other (one memory latency per pair of
+// macroblocks), and the loop is unrolled so that two pairs are in flight per warp.
+struct BsSide {
+    uint32_t w0, coded, refs, mv;
+};
+__device__ __forceinline__ BsSide loadSide(const b200_mb_rec *rec, int blk) {
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(rec);
+    BsSide r;
+    r.w0 = __ldg(w); r.coded = __ldg(w + 1); r.refs = __ldg(w + 4); r.mv = __ldg(w + 8 + blk);
+    return r;
+}
+// EdgeBoundaryStrength (:395-411) / InnerBoundaryStrength (:332-355) for two non-intra 4x4 blocks
+__device__ __forceinline__ int bsInter(const BsSide &q, int qb, const BsSide &p, int pb) {
+    if (((q.coded >> qb) | (p.coded >> pb)) & 1u) return 2;
+    const int dx = (int)(int16_t)(q.mv & 0xFFFF) - (int)(int16_t)(p.mv & 0xFFFF);
+    const int dy = (int)(int16_t)(q.mv >> 16) - (int)(int16_t)(p.mv >> 16);
+    const uint32_t rq = (q.refs >> (8 * (qb >> 2))) & 0xFF, rp = (p.refs >> (8 * (pb >> 2))) & 0xFF;
+    return (rq != rp || abs(dx) >= 4 || abs(dy) >= 4) ? 1 : 0;
+}
 __global__ void __launch_bounds__(kDeblockWarps * 32) strengthKernel(const DeblockParams p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const PoolGeom &g = p.g;
     const uint32_t chunksPerStream = ((uint32_t)g.nMbs + kDeblockWarps * kBsChunk - 1) / (kDeblockWarps * kBsChunk);
     const uint32_t total = chunksPerStream * (uint32_t)g.nStreams;
+    const int e = lane & 15, bx = e & 3, by = e >> 2;
+    const int qb = cRasterToBlk[e];
+    const int lb = cRasterToBlk[by * 4 + ((bx + 3) & 3)];   // block on the left (of the left neighbour when bx == 0)
+    const int tb = cRasterToBlk[((by + 3) & 3) * 4 + bx];   // block above (of the upper neighbour when by == 0)
     for (uint32_t v = blockIdx.x; v < total; v += gridDim.x) {
         const uint32_t s = v / chunksPerStream, chunk = v - s * chunksPerStream;
         const StreamJob job = p.jobs[s];
-        const uint32_t m0 = (chunk * kDeblockWarps + warp) * kBsChunk;
-#pragma unroll 1
-        for (uint32_t mb = m0; mb < min(m0 + kBsChunk, (uint32_t)g.nMbs); mb++) {
-            const RecView cur{reinterpret_cast<const uint32_t *>(job.recs + mb)};
-            const RecView lef{reinterpret_cast<const uint32_t *>(job.recs + mb - 1)};
-            const RecView top{reinterpret_cast<const uint32_t *>(job.recs + mb - g.widthMbs)};
-            const uint32_t w0 = __ldg(cur.w);
-            const int flags = w0 >> 24;
-            int bs = 0;
-            if (flags & B200_MBF_FILTER_INNER) {   // GetMbFilteringFlags :289-320 (resolved on the host)
-                const bool fLeft = flags & B200_MBF_FILTER_LEFT, fTop = flags & B200_MBF_FILTER_TOP;
-                const int e = lane & 15, bx = e & 3, by = e >> 2;
-                const int qb = cRasterToBlk[by * 4 + bx];
-                const bool curIntra = (w0 & 0xFF) > B200_MB_P_8x8REF0;
-                if (lane < 16) {
-                    if (bx == 0) bs = !fLeft ? 0 : (curIntra || lef.intra()) ? 4 : bsPair(cur, qb, lef, cRasterToBlk[by * 4 + 3]);
-                    else bs = curIntra ? 3 : bsPair(cur, qb, cur, cRasterToBlk[by * 4 + bx - 1]);
-                } else {
-                    if (by == 0) bs = !fTop ? 0 : (curIntra || top.intra()) ? 4 : bsPair(cur, qb, top, cRasterToBlk[12 + bx]);
-                    else bs = curIntra ? 3 : bsPair(cur, qb, cur, cRasterToBlk[(by - 1) * 4 + bx]);
-                }
+        const uint32_t m0 = (chunk * kDeblockWarps + warp) * kBsChunk + (lane >> 4);
+#pragma unroll 2
+        for (uint32_t it = 0; it < kBsChunk / 2; it++) {
+            const uint32_t mb = min(m0 + 2 * it, (uint32_t)g.nMbs - 1);   // clamped duplicates rewrite the same values
+            const b200_mb_rec *rc = job.recs + mb;
+            const BsSide cur = loadSide(rc, qb);
+            const int flags = cur.w0 >> 24;
+            const bool fLeft = flags & B200_MBF_FILTER_LEFT, fTop = flags & B200_MBF_FILTER_TOP;
+            // GetMbFilteringFlags :289-320 was resolved on the host; a neighbour that is not filtered against is never read
+            const BsSide lef = loadSide((bx == 0 && fLeft) ? rc - 1 : rc, lb);
+            const BsSide top = loadSide((by == 0 && fTop) ? rc - g.widthMbs : rc, tb);
+            const bool curIntra = (cur.w0 & 0xFF) > B200_MB_P_8x8REF0;
+            int bv, bh;
+            if (bx == 0) bv = !fLeft ? 0 : (curIntra || (lef.w0 & 0xFF) > B200_MB_P_8x8REF0) ? 4 : bsInter(cur, qb, lef, lb);
+            else bv = curIntra ? 3 : bsInter(cur, qb, lef, lb);
+            if (by == 0) bh = !fTop ? 0 : (curIntra || (top.w0 & 0xFF) > B200_MB_P_8x8REF0) ? 4 : bsInter(cur, qb, top, tb);
+            else bh = curIntra ? 3 : bsInter(cur, qb, top, tb);
+            if (!(flags & B200_MBF_FILTER_INNER)) bv = bh = 0;
+            uint32_t wv = (uint32_t)bv << (4 * (lane & 7)), wh = (uint32_t)bh << (4 * (lane & 7));
+#pragma unroll
+            for (int d = 1; d < 8; d <<= 1) {
+                wv |= __shfl_xor_sync(0xffffffffu, wv, d);
+                wh |= __shfl_xor_sync(0xffffffffu, wh, d);
             }
-            uint32_t word = (uint32_t)bs << (4 * (lane & 7));
-            word |= __shfl_xor_sync(0xffffffffu, word, 1);
-            word |= __shfl_xor_sync(0xffffffffu, word, 2);
-            word |= __shfl_xor_sync(0xffffffffu, word, 4);
-            const bool any = __ballot_sync(0xffffffffu, word != 0) != 0;
-            const size_t idx = (size_t)s * g.nMbs + mb;
-            if ((lane & 7) == 0) p.bsWords[idx * 4 + (lane >> 3)] = word;
-            if (lane == 0) p.work[idx] = any ? 1 : 0;
+            const uint32_t wv1 = __shfl_down_sync(0xffffffffu, wv, 8), wh1 = __shfl_down_sync(0xffffffffu, wh, 8);
+            if (e == 0) {
+                const size_t idx = (size_t)s * g.nMbs + mb;
+                *reinterpret_cast<uint4 *>(p.bsWords + idx * 4) = make_uint4(wv, wv1, wh, wh1);
+                p.work[idx] = (wv | wv1 | wh | wh1) ? 1 : 0;
+            }
         }
     }
 }
@@ -161,12 +172,35 @@ __global__ void __launch_bounds__(kDeblockWarps * 32) strengthKernel(const Deblo
 // consecutive tickets, so a warp's consecutive tickets belong to different streams.  A macroblock waits for its left,
 // top and top-right neighbours -- the macroblocks whose filtering the reference's raster order puts before it and whose
 // pels it reads or rewrites -- but only for those that have work themselves (the others never touch a pel).
+//
+// The macroblock and the 4 (2) pels of its left / upper neighbours are staged in shared memory by vector loads.  Lanes
+// 0..15 own a luma line, lanes 16..31 a chroma line (8 per plane); all vertical edges left to right (the lines are rows),
+// then all horizontal edges top to bottom (the lines are columns), which is the order of FilterLuma / FilterChroma
+// (deblocking.c:1569-1836) because edges of one direction only interact along a line.  Chroma edges are luma edges 0
+// and 2.  A step is skipped when no lane of the warp has a strength for it.
+__device__ __forceinline__ int bsNibble(uint32_t word, int idx) { return (int)((word >> (4 * idx)) & 15u); }
+
 __global__ void __launch_bounds__(kDeblockWarps * 32) deblockKernel(const DeblockParams p) {
     __shared__ DeblockWarpSmem smemAll[kDeblockWarps];
+    __shared__ DeblockTables tb;
     __shared__ uint32_t sBase;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     DeblockWarpSmem &sm = smemAll[warp];
     const PoolGeom &g = p.g;
+    if (threadIdx.x < 52) {
+        tb.alpha[threadIdx.x] = cAlpha[threadIdx.x];
+        tb.beta[threadIdx.x] = cBeta[threadIdx.x];
+        tb.qpc[threadIdx.x] = cQpC[threadIdx.x];
+        *reinterpret_cast<uint32_t *>(tb.tc0[threadIdx.x]) = *reinterpret_cast<const uint32_t *>(cTc0[threadIdx.x]);
+    }
+    // this lane's line: luma row / column `li` (lanes 0..15) or chroma plane `pl` row / column `li` (lanes 16..31)
+    const bool chroma = lane >= 16;
+    const int pl = (lane >> 3) & 1, li = chroma ? (lane & 7) : lane;
+    const int grp = chroma ? li >> 1 : li >> 2;                  // which 4-line strength segment the line belongs to
+    uint8_t *rowp = chroma ? &sm.c[pl][2 + li][8] : &sm.y[4 + li][16];    // sample (0, li)
+    uint8_t *colp = chroma ? &sm.c[pl][2][8 + li] : &sm.y[4][16 + li];    // sample (li, 0)
+    const int pitch = chroma ? 16 : 32;
+    const int estep = chroma ? 2 : 4;                            // pels between edge e and e + 1 (luma numbering)
 
     for (;;) {
         __syncthreads();
@@ -185,17 +219,15 @@ __global__ void __launch_bounds__(kDeblockWarps * 32) deblockKernel(const Debloc
             const int mby = (int)__umulhi(mb, g.invWidthMbs), mbx = (int)(mb - (uint32_t)mby * g.widthMbs);
             const StreamJob job = p.jobs[s];
             uint32_t *doneS = p.done + sIdx;
-            const RecView cur{reinterpret_cast<const uint32_t *>(job.recs + mb)};
-            const RecView lef{reinterpret_cast<const uint32_t *>(job.recs + mb - 1)};
-            const RecView top{reinterpret_cast<const uint32_t *>(job.recs + mb - g.widthMbs)};
-            const uint32_t w0 = __ldg(cur.w);
+            const uint32_t *cw = reinterpret_cast<const uint32_t *>(job.recs + mb);
+            const uint32_t w0 = __ldg(cw), w3 = __ldg(cw + 3);
+            const uint4 bw = __ldg(reinterpret_cast<const uint4 *>(p.bsWords + (sIdx + mb) * 4));
             const int flags = w0 >> 24;
             const bool fLeft = flags & B200_MBF_FILTER_LEFT, fTop = flags & B200_MBF_FILTER_TOP;
-            if (lane < 4) {
-                const uint32_t wv = p.bsWords[(sIdx + mb) * 4 + lane];
-#pragma unroll
-                for (int i = 0; i < 8; i++) sm.bs[lane * 8 + i] = (uint8_t)((wv >> (4 * i)) & 15u);
-            }
+            // qp of the neighbours filtered against (never read otherwise: they may not exist)
+            const int qp = (w0 >> 8) & 0xFF;
+            const int qpL = fLeft ? (int)((__ldg(cw - 24) >> 8) & 0xFF) : qp;
+            const int qpT = fTop ? (int)((__ldg(cw - 24 * g.widthMbs) >> 8) & 0xFF) : qp;
             if (lane < 3) {
                 int nmb = -1;
                 if (lane == 0 && mbx > 0) nmb = (int)mb - 1;
@@ -205,81 +237,80 @@ __global__ void __launch_bounds__(kDeblockWarps * 32) deblockKernel(const Debloc
             }
             __syncwarp();
             uint8_t *frame = framePtr(p.pool, g, s * (uint32_t)g.numSlots + job.curSlot);
-            // stage 20x20 luma + 2x 10x12 chroma (incl. 4 / 2 pels of the left and upper neighbours) from L2
-            for (int i = lane; i < 100; i += 32) {
-                const int r = i / 5, wcol = i - r * 5;
-                const uint32_t v = __ldcg(reinterpret_cast<const uint32_t *>(lumaAt(frame, g, mbx * 16 - 4 + wcol * 4, mby * 16 - 4 + r)));
-                *reinterpret_cast<uint32_t *>(&sm.y[r][wcol * 4]) = v;
+            // stage 20 luma rows and 2 x 10 chroma rows (incl. 4 / 2 rows of the upper and 4 columns of the left neighbour)
+            uint8_t *gy = nullptr, *gc = nullptr;
+            if (lane < 20) {
+                const int cpl = lane >= 10, cr = lane - cpl * 10;
+                gy = lumaAt(frame, g, mbx * 16, mby * 16 - 4 + lane);
+                gc = chromaAt(frame, g, cpl, mbx * 8, mby * 8 - 2 + cr);
+                const uint4 own = __ldcg(reinterpret_cast<const uint4 *>(gy));
+                const uint32_t lef = __ldcg(reinterpret_cast<const uint32_t *>(gy - 4));
+                const uint2 cown = __ldcg(reinterpret_cast<const uint2 *>(gc));
+                const uint32_t clef = __ldcg(reinterpret_cast<const uint32_t *>(gc - 4));
+                *reinterpret_cast<uint4 *>(&sm.y[lane][16]) = own;
+                *reinterpret_cast<uint32_t *>(&sm.y[lane][12]) = lef;
+                *reinterpret_cast<uint2 *>(&sm.c[cpl][cr][8]) = cown;
+                *reinterpret_cast<uint32_t *>(&sm.c[cpl][cr][4]) = clef;
             }
-            for (int i = lane; i < 60; i += 32) {
-                const int pl = i / 30, jj = i - pl * 30, r = jj / 3, wcol = jj - r * 3;
-                const uint32_t v = __ldcg(reinterpret_cast<const uint32_t *>(chromaAt(frame, g, pl, mbx * 8 - 4 + wcol * 4, mby * 8 - 2 + r)));
-                *reinterpret_cast<uint32_t *>(&sm.c[pl][r][wcol * 4]) = v;
-            }
-            __syncwarp();
             // thresholds: GetLumaEdgeThresholds :1390-1458, GetChromaEdgeThresholds :1469-1541
-            const uint32_t w3 = __ldg(cur.w + 3);
             const int offA = (int)(int8_t)(w3 & 0xFF), offB = (int)(int8_t)((w3 >> 8) & 0xFF), cqo = (int)(int8_t)((w3 >> 16) & 0xFF);
-            const int qp = (w0 >> 8) & 0xFF;
-            const int qpL = fLeft ? lef.qpY() : qp, qpT = fTop ? top.qpY() : qp;
-            if (lane < 16) {
-                const EdgeThr tIn = makeThr(qp, offA, offB), tL = makeThr((qp + qpL + 1) >> 1, offA, offB);
+            const int qs = chroma ? tb.qpc[clip3(0, 51, qp + cqo)] : qp;
+            const int qsL = chroma ? tb.qpc[clip3(0, 51, qpL + cqo)] : qpL;
+            const int qsT = chroma ? tb.qpc[clip3(0, 51, qpT + cqo)] : qpT;
+            const EdgeThr tIn = makeThr(tb, qs, offA, offB);
+            const EdgeThr tL = makeThr(tb, (qs + qsL + 1) >> 1, offA, offB), tT = makeThr(tb, (qs + qsT + 1) >> 1, offA, offB);
+            __syncwarp();
+
+            // vertical edges: segment (grp, e) is nibble (grp & 1) * 4 + e of word grp >> 1
+            const uint32_t vWord = (grp >> 1) ? bw.y : bw.x;
 #pragma unroll 1
-                for (int bx = 0; bx < 4; bx++) {   // all vertical edges of row `lane`, left to right
-                    const int bs = sm.bs[(lane >> 2) * 4 + bx];
-                    if (bs) filterLumaLine(&sm.y[4 + lane][4 + bx * 4], 1, bs, bx ? tIn : tL);
-                }
-            } else {
-                const int pl = (lane - 16) >> 3, r = lane & 7;
-                const int qc = cQpC[clip3(0, 51, qp + cqo)], qcL = cQpC[clip3(0, 51, qpL + cqo)];
-                const EdgeThr tIn = makeThr(qc, offA, offB), tL = makeThr((qc + qcL + 1) >> 1, offA, offB);
-#pragma unroll 1
-                for (int ed = 0; ed < 2; ed++) {
-                    const int bs = sm.bs[(r >> 1) * 4 + ed * 2];
-                    if (bs) filterChromaLine(&sm.c[pl][2 + r][4 + ed * 4], 1, bs, ed ? tIn : tL);
+            for (int e = 0; e < 4; e++) {
+                const int bs = (chroma && (e & 1)) ? 0 : bsNibble(vWord, (grp & 1) * 4 + e);
+                if (!__any_sync(0xffffffffu, bs != 0)) continue;
+                if (bs) {
+                    uint32_t *wp = reinterpret_cast<uint32_t *>(rowp + e * estep);
+                    const uint32_t P = wp[-1], Q = wp[0];
+                    EdgeLine v;
+                    v.p3 = P & 0xFF; v.p2 = (P >> 8) & 0xFF; v.p1 = (P >> 16) & 0xFF; v.p0 = P >> 24;
+                    v.q0 = Q & 0xFF; v.q1 = (Q >> 8) & 0xFF; v.q2 = (Q >> 16) & 0xFF; v.q3 = Q >> 24;
+                    const EdgeThr &th = e ? tIn : tL;
+                    if (filterLine(v, bs, th, tb.tc0[th.idxA][bs - 1], chroma)) {
+                        wp[-1] = (uint32_t)v.p3 | ((uint32_t)(v.p2 & 0xFF) << 8) | ((uint32_t)(v.p1 & 0xFF) << 16) | ((uint32_t)v.p0 << 24);
+                        wp[0] = (uint32_t)(v.q0 & 0xFF) | ((uint32_t)(v.q1 & 0xFF) << 8) | ((uint32_t)(v.q2 & 0xFF) << 16) | ((uint32_t)v.q3 << 24);
+                    }
                 }
             }
             __syncwarp();
-            if (lane < 16) {
-                const EdgeThr tIn = makeThr(qp, offA, offB), tT = makeThr((qp + qpT + 1) >> 1, offA, offB);
+            // horizontal edges: segment 16 + e * 4 + grp is nibble (e & 1) * 4 + grp of word 2 + (e >> 1)
 #pragma unroll 1
-                for (int by = 0; by < 4; by++) {
-                    const int bs = sm.bs[16 + by * 4 + (lane >> 2)];
-                    if (bs) filterLumaLine(&sm.y[4 + by * 4][4 + lane], 24, bs, by ? tIn : tT);
-                }
-            } else {
-                const int pl = (lane - 16) >> 3, cx = lane & 7;
-                const int qc = cQpC[clip3(0, 51, qp + cqo)], qcT = cQpC[clip3(0, 51, qpT + cqo)];
-                const EdgeThr tIn = makeThr(qc, offA, offB), tT = makeThr((qc + qcT + 1) >> 1, offA, offB);
-#pragma unroll 1
-                for (int half = 0; half < 2; half++) {
-                    const int bs = sm.bs[16 + half * 8 + (cx >> 1)];
-                    if (bs) filterChromaLine(&sm.c[pl][2 + half * 4][4 + cx], 12, bs, half ? tIn : tT);
+            for (int e = 0; e < 4; e++) {
+                const int bs = (chroma && (e & 1)) ? 0 : bsNibble((e >> 1) ? bw.w : bw.z, (e & 1) * 4 + grp);
+                if (!__any_sync(0xffffffffu, bs != 0)) continue;
+                if (bs) {
+                    uint8_t *q = colp + e * estep * pitch;
+                    EdgeLine v;
+                    v.p0 = q[-pitch]; v.p1 = q[-2 * pitch]; v.q0 = q[0]; v.q1 = q[pitch];
+                    if (chroma) { v.p2 = v.p3 = v.q2 = v.q3 = 0; }   // outside the chroma tile for the top edge; never used
+                    else { v.p2 = q[-3 * pitch]; v.p3 = q[-4 * pitch]; v.q2 = q[2 * pitch]; v.q3 = q[3 * pitch]; }
+                    const EdgeLine o = v;
+                    const EdgeThr &th = e ? tIn : tT;
+                    if (filterLine(v, bs, th, tb.tc0[th.idxA][bs - 1], chroma)) {
+                        q[-pitch] = (uint8_t)v.p0; q[0] = (uint8_t)v.q0;
+                        if (v.p1 != o.p1) q[-2 * pitch] = (uint8_t)v.p1;
+                        if (v.q1 != o.q1) q[pitch] = (uint8_t)v.q1;
+                        if (v.p2 != o.p2) q[-3 * pitch] = (uint8_t)v.p2;
+                        if (v.q2 != o.q2) q[2 * pitch] = (uint8_t)v.q2;
+                    }
                 }
             }
             __syncwarp();
-            // write back: own rows incl. the 4 columns of the left neighbour, then the 4 rows of the upper neighbour
-            for (int i = lane; i < 80; i += 32) {
-                const int r = i / 5, wcol = i - r * 5;
-                if (wcol == 0 && mbx == 0) continue;
-                *reinterpret_cast<uint32_t *>(lumaAt(frame, g, mbx * 16 - 4 + wcol * 4, mby * 16 + r)) =
-                    *reinterpret_cast<const uint32_t *>(&sm.y[4 + r][wcol * 4]);
-            }
-            if (mby > 0 && lane < 16) {
-                const int r = lane >> 2, wcol = lane & 3;
-                *reinterpret_cast<uint32_t *>(lumaAt(frame, g, mbx * 16 + wcol * 4, mby * 16 - 4 + r)) =
-                    *reinterpret_cast<const uint32_t *>(&sm.y[r][4 + wcol * 4]);
-            }
-            for (int i = lane; i < 48; i += 32) {
-                const int pl = i / 24, jj = i - pl * 24, r = jj / 3, wcol = jj - r * 3;
-                if (wcol == 0 && mbx == 0) continue;
-                *reinterpret_cast<uint32_t *>(chromaAt(frame, g, pl, mbx * 8 - 4 + wcol * 4, mby * 8 + r)) =
-                    *reinterpret_cast<const uint32_t *>(&sm.c[pl][2 + r][wcol * 4]);
-            }
-            if (mby > 0 && lane < 8) {
-                const int pl = lane >> 2, r = (lane >> 1) & 1, wcol = lane & 1;
-                *reinterpret_cast<uint32_t *>(chromaAt(frame, g, pl, mbx * 8 + wcol * 4, mby * 8 - 2 + r)) =
-                    *reinterpret_cast<const uint32_t *>(&sm.c[pl][r][4 + wcol * 4]);
+            // write back: own rows incl. the 4 columns of the left neighbour, and the 4 (2) rows of the upper neighbour
+            if (lane < 20) {
+                const int cpl = lane >= 10, cr = lane - cpl * 10;
+                if (lane >= 4 || mby > 0) *reinterpret_cast<uint4 *>(gy) = *reinterpret_cast<const uint4 *>(&sm.y[lane][16]);
+                if (lane >= 4 && mbx > 0) *reinterpret_cast<uint32_t *>(gy - 4) = *reinterpret_cast<const uint32_t *>(&sm.y[lane][12]);
+                if (cr >= 2 || mby > 0) *reinterpret_cast<uint2 *>(gc) = *reinterpret_cast<const uint2 *>(&sm.c[cpl][cr][8]);
+                if (cr >= 2 && mbx > 0) *reinterpret_cast<uint32_t *>(gc - 4) = *reinterpret_cast<const uint32_t *>(&sm.c[cpl][cr][4]);
             }
             // publish: all lanes' stores happen-before the release by lane 0
             __syncwarp();

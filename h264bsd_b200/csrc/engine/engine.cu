@@ -158,6 +158,9 @@ bool Batch::create(int device, uint32_t nStreams, uint32_t widthMbs, uint32_t he
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, strengthKernel, kDeblockWarps * 32, 0));
     strengthBlocks_ = std::max(1, occS) * numSms_;
     reconBlocks_ = std::max(1, occR) * numSms_;
+    int occC = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occC, reconCopyKernel, kCopyWarps * 32, 0));
+    copyBlocks_ = std::max(1, occC) * numSms_;
     deblockBlocks_ = std::max(1, occD) * numSms_;
     tapes_.assign(nStreams, DevTape());
     CK(cudaStreamSynchronize(stream_));
@@ -224,6 +227,7 @@ bool Batch::buildJobs() {
         np = std::min<uint32_t>(np, (uint32_t)t.pics.size());
     }
     numPics_ = np;
+    picMaxC_.assign(np, 0);
     picMaxA_.assign(np, 0);
     picMaxB_.assign(np, 0);
     std::vector<StreamJob> jobs((size_t)np * g_.nStreams);
@@ -234,10 +238,12 @@ bool Batch::buildJobs() {
             j.recs = reinterpret_cast<const b200_mb_rec *>(t.recs + t.pics[k].mbRecOffset);
             j.coefs = reinterpret_cast<const int16_t *>(t.coefs + t.pics[k].coefOffset);
             j.order = reinterpret_cast<const uint16_t *>(t.order) + (size_t)k * g_.nMbs;
-            j.curSlot = t.pics[k].curSlot;
+            j.curSlot = (uint16_t)t.pics[k].curSlot;
+            j.nC = (uint16_t)t.pics[k].numCopy;
             j.nA = (uint16_t)t.pics[k].numPassA;
             j.nB = (uint16_t)t.pics[k].numPassB;
-            picMaxA_[k] = std::max<uint32_t>(picMaxA_[k], j.nA);
+            picMaxC_[k] = std::max<uint32_t>(picMaxC_[k], j.nC);
+            picMaxA_[k] = std::max<uint32_t>(picMaxA_[k], (uint32_t)(j.nA - j.nC));
             picMaxB_[k] = std::max<uint32_t>(picMaxB_[k], j.nB);
         }
     cudaFree(dJobs_);
@@ -264,11 +270,11 @@ void Batch::kernelTiming(bool enable) {
     evUsed_ = 0;
 }
 
-bool Batch::kernelTimes(float ms[5], uint32_t *launchesPerStage) {
+bool Batch::kernelTimes(float ms[6], uint32_t *launchesPerStage) {
     CK(cudaSetDevice(device_));
     CK(cudaStreamSynchronize(stream_));
-    ms[0] = ms[1] = ms[2] = ms[3] = ms[4] = 0.f;
-    uint32_t n[5] = {0, 0, 0, 0, 0};
+    for (int i = 0; i < 6; i++) ms[i] = 0.f;
+    uint32_t n[6] = {0, 0, 0, 0, 0, 0};
     for (size_t i = 1; i < evUsed_; i++) {
         const int st = evStage_[i];
         if (st < 0) continue;
@@ -277,12 +283,12 @@ bool Batch::kernelTimes(float ms[5], uint32_t *launchesPerStage) {
         ms[st] += d;
         n[st]++;
     }
-    if (launchesPerStage) { launchesPerStage[0] = n[0]; launchesPerStage[1] = n[1]; launchesPerStage[2] = n[2]; launchesPerStage[3] = n[3]; launchesPerStage[4] = n[4]; }
+    if (launchesPerStage) for (int i = 0; i < 6; i++) launchesPerStage[i] = n[i];
     evUsed_ = 0;
     return true;
 }
 
-bool Batch::launchPicture(const StreamJob *dJobs, uint32_t maxA, uint32_t maxB, bool recon, bool deblock) {
+bool Batch::launchPicture(const StreamJob *dJobs, uint32_t maxC, uint32_t maxA, uint32_t maxB, bool recon, bool deblock) {
     const uint32_t total = (uint32_t)g_.nStreams * (uint32_t)g_.nMbs;
     serial_++;
     auto mark = [&](int stageEnded) {
@@ -296,9 +302,16 @@ bool Batch::launchPicture(const StreamJob *dJobs, uint32_t maxA, uint32_t maxB, 
         ReconParams rp;
         rp.pool = pool_; rp.g = g_; rp.jobs = dJobs; rp.done = dDoneRecon_;
         rp.ticket = dCounters_ + 0; rp.errors = dCounters_ + 2; rp.serial = serial_;
-        rp.chunksB = (maxB + kReconWarps * kChunkB - 1) / (kReconWarps * kChunkB);
+        rp.chunksB = (maxB + kChunkB - 1) / kChunkB;
         rp.chunksA = (maxA + kReconWarps * kChunkA - 1) / (kReconWarps * kChunkA);
         rp.virtualCtasA = rp.chunksA * (uint32_t)g_.nStreams;
+        rp.chunksC = (maxC + 31) / 32;
+        if (maxC) {
+            const uint32_t ctas = (rp.chunksC * (uint32_t)g_.nStreams + kCopyWarps - 1) / kCopyWarps;
+            reconCopyKernel<<<std::min<uint32_t>(ctas, (uint32_t)copyBlocks_), kCopyWarps * 32, 0, stream_>>>(rp);
+            launches_++;
+            mark(5);
+        }
         if (maxA) {
             const uint32_t grid = std::min<uint32_t>(rp.virtualCtasA, (uint32_t)reconBlocks_);
             reconInterKernel<<<grid, kReconWarps * 32, 0, stream_>>>(rp, lumaMap_, chromaMap_);
@@ -306,7 +319,7 @@ bool Batch::launchPicture(const StreamJob *dJobs, uint32_t maxA, uint32_t maxB, 
             mark(0);
         }
         if (maxB) {
-            reconIntraKernel<<<rp.chunksB * (uint32_t)g_.nStreams, kReconWarps * 32, 0, stream_>>>(rp);
+            reconIntraKernel<<<(rp.chunksB * (uint32_t)g_.nStreams + kReconWarps - 1) / kReconWarps, kReconWarps * 32, 0, stream_>>>(rp);
             launches_++;
             mark(3);
         }
@@ -344,7 +357,7 @@ bool Batch::decodePicture(uint32_t k) {
     CK(cudaSetDevice(device_));
     if (jobsDirty_ && !buildJobs()) return false;
     if (k >= numPics_) return false;
-    return launchPicture(dJobs_ + (size_t)k * g_.nStreams, picMaxA_[k], picMaxB_[k], true, true);
+    return launchPicture(dJobs_ + (size_t)k * g_.nStreams, picMaxC_[k], picMaxA_[k], picMaxB_[k], true, true);
 }
 
 bool Batch::debugStage(uint32_t k, bool recon, bool deblock) {
@@ -352,7 +365,7 @@ bool Batch::debugStage(uint32_t k, bool recon, bool deblock) {
     CK(cudaSetDevice(device_));
     if (jobsDirty_ && !buildJobs()) return false;
     if (k >= numPics_) return false;
-    return launchPicture(dJobs_ + (size_t)k * g_.nStreams, picMaxA_[k], picMaxB_[k], recon, deblock);
+    return launchPicture(dJobs_ + (size_t)k * g_.nStreams, picMaxC_[k], picMaxA_[k], picMaxB_[k], recon, deblock);
 }
 
 bool Batch::run(uint32_t first, uint32_t count) {
@@ -407,7 +420,8 @@ bool Batch::submitHostPicture(uint32_t stream, const b200_pic_hdr &hdr, const b2
     job.recs = reinterpret_cast<const b200_mb_rec *>(dStage_[b] + recOff);
     job.coefs = reinterpret_cast<const int16_t *>(dStage_[b] + coefOff);
     job.order = reinterpret_cast<const uint16_t *>(dStage_[b] + orderOff);
-    job.curSlot = hdr.curSlot;
+    job.curSlot = (uint16_t)hdr.curSlot;
+    job.nC = (uint16_t)hdr.numCopy;
     job.nA = (uint16_t)hdr.numPassA;
     job.nB = (uint16_t)hdr.numPassB;
     std::memcpy(h, &job, sizeof job);
@@ -416,7 +430,7 @@ bool Batch::submitHostPicture(uint32_t stream, const b200_pic_hdr &hdr, const b2
     std::memcpy(h + coefOff, coefs, coefBytes);
     CK(cudaMemcpyAsync(dStage_[b], h, coefOff + coefBytes, cudaMemcpyHostToDevice, stream_));
     h2dBytes_ += coefOff + coefBytes;
-    if (!launchPicture(reinterpret_cast<const StreamJob *>(dStage_[b]), hdr.numPassA, hdr.numPassB, true, true)) return false;
+    if (!launchPicture(reinterpret_cast<const StreamJob *>(dStage_[b]), hdr.numCopy, hdr.numPassA - hdr.numCopy, hdr.numPassB, true, true)) return false;
     CK(cudaEventRecord(stageEv_[b], stream_));
     return true;
 }

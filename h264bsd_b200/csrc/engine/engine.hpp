@@ -41,7 +41,7 @@ public:
     int compareStreams(const uint32_t *slots);
     // per-stage device time (CUDA events on the engine's stream around every launch)
     void kernelTiming(bool enable);
-    bool kernelTimes(float ms[5], uint32_t *launchesPerStage);  // recon pass A, deblock filter, border, recon pass B, boundary strengths
+    bool kernelTimes(float ms[6], uint32_t *launchesPerStage);  // recon pass A, deblock filter, border, recon pass B, boundary strengths, copy pass
     uint32_t idctErrors();
     uint32_t watchdog(int which);  // 0: flag waits that gave up, 1: TMA waits that gave up
 
@@ -62,8 +62,8 @@ private:
         std::vector<b200_pic_hdr> pics;
     };
     bool buildJobs();
-    bool launchPicture(const StreamJob *dJobs, uint32_t maxA, uint32_t maxB, bool recon, bool deblock);
-    std::vector<uint32_t> picMaxA_, picMaxB_;
+    bool launchPicture(const StreamJob *dJobs, uint32_t maxC, uint32_t maxA, uint32_t maxB, bool recon, bool deblock);
+    std::vector<uint32_t> picMaxC_, picMaxA_, picMaxB_;
 
     bool created_ = false;
     int device_ = 0, numSms_ = 0;
@@ -77,7 +77,7 @@ private:
     uint8_t *dWork_ = nullptr;
     int strengthBlocks_ = 0;
     uint32_t serial_ = 0;
-    int reconBlocks_ = 0, deblockBlocks_ = 0;
+    int reconBlocks_ = 0, deblockBlocks_ = 0, copyBlocks_ = 0;
     std::vector<DevTape> tapes_;
     StreamJob *dJobs_ = nullptr;
     uint32_t numPics_ = 0;

@@ -30,8 +30,9 @@ struct PoolGeom {
 struct StreamJob {
     const b200_mb_rec *recs;  // nMbs records of this picture
     const int16_t *coefs;     // this picture's coefficient pool
-    const uint16_t *order;    // nMbs macroblock addresses: nA pass-A entries (raster), then nB pass-B entries (wavefront)
-    uint32_t curSlot;
+    const uint16_t *order;    // nMbs macroblock addresses: nA pass-A entries (the first nC of them plain copies), then nB pass-B entries (wavefront)
+    uint16_t curSlot;
+    uint16_t nC;              // plain copies at the head of the pass-A list (b200_pic_hdr.numCopy)
     uint16_t nA, nB;
 };
 

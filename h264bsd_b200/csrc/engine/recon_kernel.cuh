@@ -12,7 +12,7 @@ namespace b200 {
 
 constexpr int kReconWarps = 8;
 constexpr int kChunkA = 8;   // consecutive pass-A list entries per warp (TMA of entry i+1 overlaps the math of entry i)
-constexpr int kChunkB = 2;   // consecutive pass-B (wavefront) entries per warp
+constexpr int kChunkB = 4;   // consecutive pass-B (wavefront) entries per warp task
 
 struct ReconParams {
     uint8_t *pool;
@@ -22,9 +22,10 @@ struct ReconParams {
     uint32_t *ticket;          // CTA ticket counter of pass B (zeroed before launch)
     uint32_t *errors;          // [0] IDCT range errors (h264bsd_transform.c:183-188)
     uint32_t serial;           // value that marks "done in this launch"
-    uint32_t chunksB;          // pass B: CTAs per stream
+    uint32_t chunksB;          // pass B: warp tasks (kChunkB entries) per stream
     uint32_t chunksA;          // pass A: virtual CTAs per stream (kReconWarps * kChunkA entries each)
     uint32_t virtualCtasA;     // chunksA * nStreams
+    uint32_t chunksC;          // copy pass: warp tasks per stream (32 entries each)
 };
 
 struct __align__(128) InterWarpSmem {
@@ -198,6 +199,27 @@ __device__ __forceinline__ int intra4x4Pel(int mode, int x, int y, bool avA, boo
     }
 }
 
+// Intra4x4 as a table: every predicted sample of every directional mode is one of three forms over the 13 edge samples
+// E[0..3] = left column bottom-to-top, E[4] = corner, E[5..12] = above row incl. above-right (clause 8.3.1.2.1-8.3.1.2.9;
+// generated and checked against the clause formulas by tools/gen_i4x4_table.py).  Entry [mode][y * 4 + x] =
+// i0 | i1 << 8 | i2 << 16 | kind << 24; kind 0: E[i0], 1: (E[i0] + E[i1] + 1) >> 1, 2: (E[i0] + 2 E[i1] + E[i2] + 2) >> 2,
+// 3: DC (mode 2, computed from sums).
+__device__ const uint32_t gIntra4x4Table[9 * 16] = {
+    0x00000005, 0x00000006, 0x00000007, 0x00000008, 0x00000005, 0x00000006, 0x00000007, 0x00000008, 0x00000005, 0x00000006, 0x00000007, 0x00000008, 0x00000005, 0x00000006, 0x00000007, 0x00000008,
+    0x00000003, 0x00000003, 0x00000003, 0x00000003, 0x00000002, 0x00000002, 0x00000002, 0x00000002, 0x00000001, 0x00000001, 0x00000001, 0x00000001, 0x00000000, 0x00000000, 0x00000000, 0x00000000,
+    0x03000000, 0x03000000, 0x03000000, 0x03000000, 0x03000000, 0x03000000, 0x03000000, 0x03000000, 0x03000000, 0x03000000, 0x03000000, 0x03000000, 0x03000000, 0x03000000, 0x03000000, 0x03000000,
+    0x02070605, 0x02080706, 0x02090807, 0x020a0908, 0x02080706, 0x02090807, 0x020a0908, 0x020b0a09, 0x02090807, 0x020a0908, 0x020b0a09, 0x020c0b0a, 0x020a0908, 0x020b0a09, 0x020c0b0a, 0x020c0c0b,
+    0x02050403, 0x02060504, 0x02070605, 0x02080706, 0x02040302, 0x02050403, 0x02060504, 0x02070605, 0x02030201, 0x02040302, 0x02050403, 0x02060504, 0x02020100, 0x02030201, 0x02040302, 0x02050403,
+    0x01000504, 0x01000605, 0x01000706, 0x01000807, 0x02050403, 0x02060504, 0x02070605, 0x02080706, 0x02040302, 0x01000504, 0x01000605, 0x01000706, 0x02030201, 0x02050403, 0x02060504, 0x02070605,
+    0x01000304, 0x02050403, 0x02040506, 0x02050607, 0x01000203, 0x02020304, 0x01000304, 0x02050403, 0x01000102, 0x02010203, 0x01000203, 0x02020304, 0x01000001, 0x02000102, 0x01000102, 0x02010203,
+    0x01000605, 0x01000706, 0x01000807, 0x01000908, 0x02070605, 0x02080706, 0x02090807, 0x020a0908, 0x01000706, 0x01000807, 0x01000908, 0x01000a09, 0x02080706, 0x02090807, 0x020a0908, 0x020b0a09,
+    0x01000203, 0x02010203, 0x01000102, 0x02000102, 0x01000102, 0x02000102, 0x01000001, 0x02000001, 0x01000001, 0x02000001, 0x00000000, 0x00000000, 0x00000000, 0x00000000, 0x00000000, 0x00000000,
+};
+// the reference decodes the sixteen 4x4 blocks one after the other (intra_prediction.c:701-833); blocks that do not
+// depend on each other can share a step: two half-warps, ten steps
+__device__ __constant__ int8_t cI4StepA[10] = {0, 1, 2, 3, 6, 7, 10, 11, 14, 15};
+__device__ __constant__ int8_t cI4StepB[10] = {-1, -1, 4, 5, 8, 9, 12, 13, -1, -1};
+
 // ---- shared by both passes --------------------------------------------------------------------------
 struct MbHead {
     int mbType, qpY, qpC, flags;
@@ -333,72 +355,139 @@ __device__ __forceinline__ void vcol8(const uint8_t *colp, int *vs) {
         vs[k] = dp4aUS(hi, kTapsHi, dp4aUS(lo, kTapsLo, 0));
     }
 }
+// four values -> four bytes with unsigned saturation, element 0 in the low byte (I2IP.U8.S32.SAT, two instructions)
+__device__ __forceinline__ uint32_t pack4sat(int p0, int p1, int p2, int p3) {
+    uint32_t hi, r;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, 0;" : "=r"(hi) : "r"(p3), "r"(p2));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(p1), "r"(p0), "r"(hi));
+    return r;
+}
+// clip255((v + 16) >> 5) / clip255((v + 512) >> 10) of eight sums, packed
+__device__ __forceinline__ uint2 pack8shift(const int *v, int rnd, int sh) {
+    return make_uint2(pack4sat((v[0] + rnd) >> sh, (v[1] + rnd) >> sh, (v[2] + rnd) >> sh, (v[3] + rnd) >> sh),
+                      pack4sat((v[4] + rnd) >> sh, (v[5] + rnd) >> sh, (v[6] + rnd) >> sh, (v[7] + rnd) >> sh));
+}
+__device__ __forceinline__ uint2 avg8(uint2 a, uint2 b) { return make_uint2(__vavgu4(a.x, b.x), __vavgu4(a.y, b.y)); }
+
 // clause 8.4.2.2.1 for 8 horizontally adjacent samples: `win` points at window sample (xInt-2, yInt-2) (see W_);
-// (x0, y) = position of the first sample inside the partition; the same arithmetic as lumaQpel, 8 at a time
+// (x0, y) = position of the first sample inside the partition; the same arithmetic as lumaQpel, 8 at a time, on packed
+// bytes: the rounded averages (a + b + 1) >> 1 are per-byte averages of clipped values
 __device__ __forceinline__ uint2 lumaQpel8(const uint8_t *win, int x0, int y, int xf, int yf) {
-    int out[8];
     const bool jfam = (xf == 2 || yf == 2) && xf != 0 && yf != 0;
     if (!jfam) {
-        int b[8], h[8];
         const bool useH = xf != 0, useV = yf != 0;
+        uint2 b = make_uint2(0, 0), h = make_uint2(0, 0);
         if (useH) {
-            hrow8(win + (y + 2 + (yf == 3 ? 1 : 0)) * kLumaBoxW + x0, b);
-#pragma unroll
-            for (int k = 0; k < 8; k++) b[k] = clip255((b[k] + 16) >> 5);
+            int t[8];
+            hrow8(win + (y + 2 + (yf == 3 ? 1 : 0)) * kLumaBoxW + x0, t);
+            b = pack8shift(t, 16, 5);
         }
         if (useV) {
-            vcol8(win + y * kLumaBoxW + x0 + 2 + (xf == 3 ? 1 : 0), h);
-#pragma unroll
-            for (int k = 0; k < 8; k++) h[k] = clip255((h[k] + 16) >> 5);
+            int t[8];
+            vcol8(win + y * kLumaBoxW + x0 + 2 + (xf == 3 ? 1 : 0), t);
+            h = pack8shift(t, 16, 5);
         }
-        if (useH && useV) {
+        if (useH && useV) return avg8(b, h);
+        if (useH) return xf == 2 ? b : avg8(b, lds8(win + (y + 2) * kLumaBoxW + x0 + 2 + (xf >> 1)));
+        return yf == 2 ? h : avg8(h, lds8(win + (y + 2 + (yf >> 1)) * kLumaBoxW + x0 + 2));
+    }
+    int acc[8], bsel[8];
 #pragma unroll
-            for (int k = 0; k < 8; k++) out[k] = (b[k] + h[k] + 1) >> 1;
-        } else if (useH) {
-            const uint2 gpel = lds8(win + (y + 2) * kLumaBoxW + x0 + 2 + (xf >> 1));
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const int gk = ((k < 4 ? gpel.x : gpel.y) >> (8 * (k & 3))) & 0xFF;
-                out[k] = xf == 2 ? b[k] : (b[k] + gk + 1) >> 1;
-            }
-        } else {
-            const uint2 gpel = lds8(win + (y + 2 + (yf >> 1)) * kLumaBoxW + x0 + 2);
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const int gk = ((k < 4 ? gpel.x : gpel.y) >> (8 * (k & 3))) & 0xFF;
-                out[k] = yf == 2 ? h[k] : (h[k] + gk + 1) >> 1;
-            }
-        }
-    } else {
-        int acc[8], bsel[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) { acc[k] = 0; bsel[k] = 0; }
-        const int brow = 2 + (yf == 3 ? 1 : 0);
+    for (int k = 0; k < 8; k++) { acc[k] = 0; bsel[k] = 0; }
+    const int brow = 2 + (yf == 3 ? 1 : 0);
 #pragma unroll 1
-        for (int t = 0; t < 6; t++) {
-            int hs[8];
-            hrow8(win + (y + t) * kLumaBoxW + x0, hs);
-            const int c = (t == 0 || t == 5) ? 1 : (t == 1 || t == 4) ? -5 : 20;
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                acc[k] += c * hs[k];
-                if (t == brow) bsel[k] = hs[k];
-            }
-        }
-        int h[8];
-        if (yf == 2 && xf != 2) {
-            vcol8(win + y * kLumaBoxW + x0 + 2 + (xf == 3 ? 1 : 0), h);
-        }
+    for (int t = 0; t < 6; t++) {
+        int hs[8];
+        hrow8(win + (y + t) * kLumaBoxW + x0, hs);
+        const int c = (t == 0 || t == 5) ? 1 : (t == 1 || t == 4) ? -5 : 20;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-            const int j = clip255((acc[k] + 512) >> 10);
-            if (xf == 2 && yf == 2) out[k] = j;
-            else if (xf == 2) out[k] = (j + clip255((bsel[k] + 16) >> 5) + 1) >> 1;
-            else out[k] = (j + clip255((h[k] + 16) >> 5) + 1) >> 1;
+            acc[k] += c * hs[k];
+            if (t == brow) bsel[k] = hs[k];
         }
     }
-    return make_uint2((uint32_t)out[0] | ((uint32_t)out[1] << 8) | ((uint32_t)out[2] << 16) | ((uint32_t)out[3] << 24),
-                      (uint32_t)out[4] | ((uint32_t)out[5] << 8) | ((uint32_t)out[6] << 16) | ((uint32_t)out[7] << 24));
+    const uint2 j = pack8shift(acc, 512, 10);
+    if (xf == 2 && yf == 2) return j;
+    if (xf == 2) return avg8(j, pack8shift(bsel, 16, 5));
+    int hv[8];
+    vcol8(win + y * kLumaBoxW + x0 + 2 + (xf == 3 ? 1 : 0), hv);
+    return avg8(j, pack8shift(hv, 16, 5));
+}
+
+// =====================================================================================================
+// copy pass: the macroblocks the host classified as plain copies (P_Skip / P_L0_16x16, no residual, vector integer
+// for luma and chroma -- two thirds of a typical P picture).  h264bsdPredictSamples degenerates to h264bsdFillBlock
+// (reconstruct.c:1852, :2244) and h264bsdWriteOutputBlocks to a store: 384 bytes in, 384 bytes out, no shared memory.
+// A warp owns 32 consecutive list entries: lane j fetches entry j's address, reference slot and vector (one
+// dependent-load chain per 32 macroblocks), then the warp copies four macroblocks per step, loads before stores.
+// =====================================================================================================
+constexpr int kCopyWarps = 8;
+constexpr int kCopyUnroll = 4;
+
+__global__ void __launch_bounds__(kCopyWarps * 32) reconCopyKernel(const ReconParams p) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const PoolGeom &g = p.g;
+    const int r8 = lane >> 1, c8 = (lane & 1) * 8;
+    const int cp = lane >> 4, cr = (lane >> 1) & 7, cc = (lane & 1) * 4;
+    const uint32_t totalTasks = p.chunksC * (uint32_t)g.nStreams;
+    for (uint32_t t = blockIdx.x * kCopyWarps + warp; t < totalTasks; t += gridDim.x * kCopyWarps) {
+        const uint32_t s = t / p.chunksC, chunk = t - s * p.chunksC;
+        const StreamJob job = p.jobs[s];
+        const uint32_t e0 = chunk * 32u;
+        if (e0 >= job.nC) continue;
+        const int n = (int)min(32u, (uint32_t)job.nC - e0);
+        const uint32_t frameBase = s * (uint32_t)g.numSlots;
+        uint8_t *cur = framePtr(p.pool, g, frameBase + job.curSlot);
+        // lane j: where entry j's source lies (clamped like issueWindow: a block wholly outside the picture on an axis equals
+        // the block at the clamped origin because the border is a replication)
+        uint32_t mMb = 0;
+        unsigned long long mSrcY = 0, mSrcC = 0;
+        if (lane < n) {
+            mMb = __ldg(job.order + e0 + lane);
+            const uint32_t *rw = reinterpret_cast<const uint32_t *>(job.recs + mMb);
+            const uint32_t refSlots = __ldg(rw + 4), mvv = __ldg(rw + 8);
+            const int mvx = (int)(int16_t)(mvv & 0xFFFF), mvy = (int)(int16_t)(mvv >> 16);
+            const int mby = (int)__umulhi(mMb, g.invWidthMbs), mbx = (int)(mMb - (uint32_t)mby * g.widthMbs);
+            const int x = clip3(-kPadY, g.W + kPadY - 16, mbx * 16 + (mvx >> 2)), y = clip3(-kPadY, g.H + kPadY - 16, mby * 16 + (mvy >> 2));
+            const int cx = clip3(-kPadC, g.W / 2 + kPadC - 8, mbx * 8 + (mvx >> 3)), cy = clip3(-kPadC, g.H / 2 + kPadC - 8, mby * 8 + (mvy >> 3));
+            const unsigned long long ref = (unsigned long long)(frameBase + (refSlots & 0xFF)) * g.frameStride;
+            mSrcY = ref + (unsigned long long)(y + kPadY) * g.pitchY + (x + kPadY);
+            mSrcC = ref + g.offCb + (unsigned long long)(cy + kPadC) * g.pitchC + (cx + kPadC);
+        }
+#pragma unroll 1
+        for (int i0 = 0; i0 < n; i0 += kCopyUnroll) {
+            uint2 pv[kCopyUnroll];
+            uint32_t pc[kCopyUnroll];
+            uint32_t mbs[kCopyUnroll];
+#pragma unroll
+            for (int u = 0; u < kCopyUnroll; u++) {
+                const int i = min(i0 + u, n - 1);   // a short tail repeats the last entry (same bytes, same place)
+                mbs[u] = __shfl_sync(0xffffffffu, mMb, i);
+                const unsigned long long sy = __shfl_sync(0xffffffffu, mSrcY, i), sc = __shfl_sync(0xffffffffu, mSrcC, i);
+                const uint8_t *srcY = p.pool + sy + (size_t)r8 * g.pitchY + c8;
+                const uint8_t *srcC = p.pool + sc + (cp ? g.offCr - g.offCb : 0ull) + (size_t)cr * g.pitchC + cc;
+                // the vector is a multiple of two luma pels / one chroma pel: 2-byte aligned luma, 1-byte aligned chroma
+                const uint32_t ay = (uint32_t)(sy + c8) & 3u, ac = (uint32_t)(sc + cc) & 3u;
+                const uint32_t *wy = reinterpret_cast<const uint32_t *>(srcY - ay);
+                const uint32_t *wc = reinterpret_cast<const uint32_t *>(srcC - ac);
+                if (ay == 0) {                       // warp-uniform: every lane has the same vector
+                    pv[u] = make_uint2(__ldg(wy), __ldg(wy + 1));
+                } else {
+                    const uint32_t w0 = __ldg(wy), w1 = __ldg(wy + 1), w2 = __ldg(wy + 2);
+                    pv[u] = make_uint2(__funnelshift_r(w0, w1, ay * 8), __funnelshift_r(w1, w2, ay * 8));
+                }
+                if (ac == 0) pc[u] = __ldg(wc);
+                else pc[u] = __funnelshift_r(__ldg(wc), __ldg(wc + 1), ac * 8);
+            }
+#pragma unroll
+            for (int u = 0; u < kCopyUnroll; u++) {
+                const uint32_t mb = mbs[u];
+                const int mby = (int)__umulhi(mb, g.invWidthMbs), mbx = (int)(mb - (uint32_t)mby * g.widthMbs);
+                *reinterpret_cast<uint2 *>(lumaAt(cur, g, mbx * 16 + c8, mby * 16 + r8)) = pv[u];
+                *reinterpret_cast<uint32_t *>(chromaAt(cur, g, cp, mbx * 8 + cc, mby * 8 + cr)) = pc[u];
+            }
+        }
+    }
 }
 
 // =====================================================================================================
@@ -451,7 +540,7 @@ reconInterKernel(const ReconParams p, const __grid_constant__ CUtensorMap lumaMa
     for (uint32_t v = blockIdx.x; v < p.virtualCtasA; v += gridDim.x) {
     const uint32_t s = v / p.chunksA, chunk = v - s * p.chunksA;
     const StreamJob job = p.jobs[s];
-    const uint32_t e0 = (chunk * kReconWarps + warp) * kChunkA;
+    const uint32_t e0 = (uint32_t)job.nC + (chunk * kReconWarps + warp) * kChunkA;   // the plain copies went to reconCopyKernel
     if (e0 >= job.nA) continue;
     const int n = min((uint32_t)kChunkA, job.nA - e0);
     const uint32_t frameBase = s * (uint32_t)g.numSlots;
@@ -594,15 +683,10 @@ reconInterKernel(const ReconParams p, const __grid_constant__ CUtensorMap lumaMa
         }
         // add residual + clip + store (h264bsdWriteOutputBlocks, image.c:172-344)
         if (h.mask) {
-            uint32_t o0 = 0, o1 = 0, oc = 0;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                o0 |= (uint32_t)clip255((int)((pv.x >> (8 * k)) & 0xFF) + resY[k]) << (8 * k);
-                o1 |= (uint32_t)clip255((int)((pv.y >> (8 * k)) & 0xFF) + resY[4 + k]) << (8 * k);
-                oc |= (uint32_t)clip255((int)((pc >> (8 * k)) & 0xFF) + resC[k]) << (8 * k);
-            }
-            pv = make_uint2(o0, o1);
-            pc = oc;
+            auto px = [](uint32_t w, int k) { return (int)((w >> (8 * k)) & 0xFF); };
+            pv = make_uint2(pack4sat(px(pv.x, 0) + resY[0], px(pv.x, 1) + resY[1], px(pv.x, 2) + resY[2], px(pv.x, 3) + resY[3]),
+                            pack4sat(px(pv.y, 0) + resY[4], px(pv.y, 1) + resY[5], px(pv.y, 2) + resY[6], px(pv.y, 3) + resY[7]));
+            pc = pack4sat(px(pc, 0) + resC[0], px(pc, 1) + resC[1], px(pc, 2) + resC[2], px(pc, 3) + resC[3]);
         }
         *reinterpret_cast<uint2 *>(dstY) = pv;
         *reinterpret_cast<uint32_t *>(dstC) = pc;
@@ -613,22 +697,26 @@ reconInterKernel(const ReconParams p, const __grid_constant__ CUtensorMap lumaMa
 
 // =====================================================================================================
 // pass B: intra-predicted macroblocks.  They read the unfiltered current picture, so an intra macroblock
-// must come after its intra neighbours (the others were written by pass A).  CTAs take tickets; ticket t
-// is chunk t / nStreams of stream t % nStreams of the stream's wavefront-ordered list, so a warp only ever
-// waits for macroblocks whose CTA took an earlier ticket.
+// must come after its intra neighbours (the others were written by the copy pass and pass A).  CTAs take tickets; a
+// ticket is kReconWarps warp tasks; warp task w is chunk w / nStreams of stream w % nStreams of the stream's
+// wavefront-ordered list.  A warp works through its chunk in list order, so dependencies inside a chunk cost nothing,
+// the warps of a CTA belong to different streams (they never wait for each other), and a warp only ever waits for
+// chunks whose CTA took an earlier ticket.
 // =====================================================================================================
-__global__ void __launch_bounds__(kReconWarps * 32) reconIntraKernel(const ReconParams p) {
+__global__ void __launch_bounds__(kReconWarps * 32, 3) reconIntraKernel(const ReconParams p) {
     __shared__ IntraWarpSmem smemAll[kReconWarps];
+    __shared__ uint32_t sI4Table[9 * 16];
     __shared__ uint32_t sTicket;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const PoolGeom &g = p.g;
     if (threadIdx.x == 0) sTicket = atomicAdd(p.ticket, 1u);
+    if (threadIdx.x < 9 * 16) sI4Table[threadIdx.x] = gIntra4x4Table[threadIdx.x];
     __syncthreads();
-    const uint32_t t = sTicket;
+    const uint32_t t = sTicket * kReconWarps + warp;
     const uint32_t chunk = t / (uint32_t)g.nStreams, s = t - chunk * (uint32_t)g.nStreams;
     if (chunk >= p.chunksB) return;
     const StreamJob job = p.jobs[s];
-    const uint32_t e0 = (chunk * kReconWarps + warp) * kChunkB;
+    const uint32_t e0 = chunk * kChunkB;
     if (e0 >= job.nB) return;
     const int n = min((uint32_t)kChunkB, job.nB - e0);
     IntraWarpSmem &sm = smemAll[warp];
@@ -684,38 +772,47 @@ __global__ void __launch_bounds__(kReconWarps * 32) reconIntraKernel(const Recon
         __syncwarp();
 
         if (h.mbType == B200_MB_I_4x4) {
-            // h264bsdIntra4x4Prediction (:701-833): 16 sequential blocks; lanes 0..15 own one pel each
+            // h264bsdIntra4x4Prediction (:701-833): half-warp = block, lane = sample; edge samples straight from the tile
             const uint32_t *modew = reinterpret_cast<const uint32_t *>(rec) + 8;
             const int x = lane & 3, y = (lane >> 2) & 3;
 #pragma unroll 1
-            for (int b = 0; b < 16; b++) {
-                const int bx = cBlkX[b], by = cBlkY[b];
-                const int mode = (__ldg(modew + (b >> 2)) >> (8 * (b & 3))) & 0xFF;
-                const bool bA = bx ? true : avA, bB = by ? true : avB;
-                bool bC;
-                if (by == 0) bC = (bx == 3) ? avC : avB;
-                else if (bx == 3) bC = false;
-                else bC = cRasterToBlk[(by - 1) * 4 + bx + 1] < b;
-                if (lane < 16) {
-                    const uint8_t *above = &sm.itY[by * 4][bx * 4 + 1];   // above[k] = sample (k, -1)
-                    const uint8_t *left = &sm.itY[by * 4 + 1][bx * 4];    // left[k*24] = sample (-1, k)
-                    auto A = [&](int k) -> int { return above[(k > 3 && !bC) ? 3 : k]; };
-                    auto L = [&](int k) -> int { return left[k * 24]; };
-                    int v = intra4x4Pel(mode, x, y, bA, bB, A, L);
+            for (int st = 0; st < 10; st++) {
+                const int b = lane < 16 ? cI4StepA[st] : cI4StepB[st];
+                if (b >= 0) {
+                    const int bx = cBlkX[b], by = cBlkY[b];
+                    const int mode = (__ldg(modew + (b >> 2)) >> (8 * (b & 3))) & 0xFF;
+                    const bool bA = bx ? true : avA, bB = by ? true : avB;
+                    bool bC;   // above-right block available: decoded earlier (or the neighbouring macroblock's)
+                    if (by == 0) bC = (bx == 3) ? avC : avB;
+                    else if (bx == 3) bC = false;
+                    else bC = cRasterToBlk[(by - 1) * 4 + bx + 1] < b;
+                    const uint8_t *corner = &sm.itY[by * 4][bx * 4];   // E[4]; above row to its right, left column below it
+                    auto E = [&](int i) -> int {
+                        if (i <= 3) return corner[(4 - i) * 24];
+                        int k = i - 4;                         // 0 = corner, 1..8 = above row
+                        if (k > 4 && !bC) k = 4;
+                        return corner[k];
+                    };
+                    int v;
+                    if (mode == 2) {
+                        const int sa = corner[1] + corner[2] + corner[3] + corner[4];
+                        const int sl = corner[24] + corner[48] + corner[72] + corner[96];
+                        v = (bA && bB) ? (sa + sl + 4) >> 3 : bA ? (sl + 2) >> 2 : bB ? (sa + 2) >> 2 : 128;
+                    } else {
+                        const uint32_t d = sI4Table[mode * 16 + y * 4 + x];
+                        const int kind = d >> 24, e0 = E(d & 0xFF);
+                        if (kind == 0) v = e0;
+                        else if (kind == 1) v = (e0 + E((d >> 8) & 0xFF) + 1) >> 1;
+                        else v = (e0 + 2 * E((d >> 8) & 0xFF) + E((d >> 16) & 0xFF) + 2) >> 2;
+                    }
                     if (h.mask) v = clip255(v + sm.res[b][y * 4 + x]);
-                    sm.stage[lane] = (uint8_t)v;
+                    // the sample lies inside the block, every edge sample outside it, and the two blocks of a step do not
+                    // touch each other's edges: no barrier between the reads above and this write
+                    sm.itY[by * 4 + 1 + y][bx * 4 + 1 + x] = (uint8_t)v;
                 }
                 __syncwarp();
-                if (lane < 16) sm.itY[by * 4 + 1 + y][bx * 4 + 1 + x] = sm.stage[lane];
-                __syncwarp();
             }
-            uint32_t o0 = 0, o1 = 0;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                o0 |= (uint32_t)sm.itY[1 + r8][1 + c8 + k] << (8 * k);
-                o1 |= (uint32_t)sm.itY[1 + r8][1 + c8 + 4 + k] << (8 * k);
-            }
-            *reinterpret_cast<uint2 *>(dstY) = make_uint2(o0, o1);
+            *reinterpret_cast<uint2 *>(dstY) = lds8(&sm.itY[1 + r8][1 + c8]);
         } else {
             // h264bsdIntra16x16Prediction (:627-687)
             const int mode = (h.mbType - B200_MB_I_16x16_FIRST) & 3;

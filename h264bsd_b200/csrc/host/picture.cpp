@@ -643,9 +643,17 @@ void PictureState::finalizeRecords() {
     // processing order + which neighbours an intra macroblock has to wait for
     auto passB = [&](int nb) { return nb >= 0 && recs[nb].mbType > B200_MB_P_8x8REF0 && recs[nb].mbType != B200_MB_I_PCM; };
     order.resize(picSizeInMbs);
+    // plain copies first: P_Skip / P_L0_16x16 without residual whose vector is integer for luma and chroma
+    auto plainCopy = [&](uint32_t a) {
+        const b200_mb_rec &r = recs[a];
+        return r.mbType <= B200_MB_P_16x16 && r.codedMask == 0 && ((r.u.mv[0][0] | r.u.mv[0][1]) & 7) == 0;
+    };
     uint32_t nA = 0;
     for (uint32_t a = 0; a < picSizeInMbs; a++)
-        if (!passB((int)a)) order[nA++] = (uint16_t)a;
+        if (!passB((int)a) && plainCopy(a)) order[nA++] = (uint16_t)a;
+    numCopy = nA;
+    for (uint32_t a = 0; a < picSizeInMbs; a++)
+        if (!passB((int)a) && !plainCopy(a)) order[nA++] = (uint16_t)a;
     numPassA = nA;
     numPassB = picSizeInMbs - nA;
     if (numPassB) {

@@ -232,6 +232,7 @@ void StreamDecoder::finishPicture() {
     hdr.picId = currentPicId_;
     hdr.numPassA = pic_.numPassA;
     hdr.numPassB = pic_.numPassB;
+    hdr.numCopy = pic_.numCopy;
 
     int32_t poc = decodePicOrderCnt(poc_, *activeSps_, sliceHeader_, prevNal_);
     if (validSliceInAccessUnit_) {

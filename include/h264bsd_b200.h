@@ -78,10 +78,10 @@ int h264bsdB200BatchCompareStreams(b200_batch *batch, const uint32_t *slots);
 int h264bsdB200BatchDebugStage(b200_batch *batch, uint32_t picIndex, int recon, int deblock);
 /* blocks whose residual left [-512,511] since creation (h264bsd_transform.c:183-188 error return) */
 uint32_t h264bsdB200BatchIdctErrors(b200_batch *batch);
-/* per-stage device time: CUDA events around every launch on the engine's stream.  ms5/launches5 = {reconstruct pass A
- * (inter), in-loop filter, border, reconstruct pass B (intra), boundary strengths}; reading resets the accumulators */
+/* per-stage device time: CUDA events around every launch on the engine's stream.  ms6/launches6 = {reconstruct pass A
+ * (inter), in-loop filter, border, reconstruct pass B (intra), boundary strengths, copy pass}; reading resets the accumulators */
 void h264bsdB200BatchKernelTiming(b200_batch *batch, int enable);
-int h264bsdB200BatchKernelTimes(b200_batch *batch, float *ms5, uint32_t *launches5);
+int h264bsdB200BatchKernelTimes(b200_batch *batch, float *ms6, uint32_t *launches6);
 /* waits inside the kernels that gave up (0: macroblock-flag waits, 1: TMA waits); non-zero = engine bug */
 uint32_t h264bsdB200BatchWatchdog(b200_batch *batch, int which);
 uint64_t h264bsdB200BatchLaunches(b200_batch *batch);
