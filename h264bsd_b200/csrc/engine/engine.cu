@@ -62,6 +62,7 @@ void Batch::destroy() {
     if (hStage_[1]) cudaFreeHost(hStage_[1]);
     for (cudaEvent_t e : evPool_) cudaEventDestroy(e);
     evPool_.clear(); evStage_.clear();
+    if (syncEv_) cudaEventDestroy(syncEv_);
     if (evA_) cudaEventDestroy(evA_);
     if (evB_) cudaEventDestroy(evB_);
     if (stream_) cudaStreamDestroy(stream_);
@@ -227,6 +228,7 @@ bool Batch::buildJobs() {
         np = std::min<uint32_t>(np, (uint32_t)t.pics.size());
     }
     numPics_ = np;
+    picMaxQ_.assign(np, 0);
     picMaxC_.assign(np, 0);
     picMaxA_.assign(np, 0);
     picMaxB_.assign(np, 0);
@@ -239,11 +241,13 @@ bool Batch::buildJobs() {
             j.coefs = reinterpret_cast<const int16_t *>(t.coefs + t.pics[k].coefOffset);
             j.order = reinterpret_cast<const uint16_t *>(t.order) + (size_t)k * g_.nMbs;
             j.curSlot = (uint16_t)t.pics[k].curSlot;
+            j.nQ = (uint16_t)t.pics[k].numQuad;
             j.nC = (uint16_t)t.pics[k].numCopy;
-            j.nA = (uint16_t)t.pics[k].numPassA;
+            j.nA = (uint16_t)(t.pics[k].numPassA - 4 * t.pics[k].numQuad - t.pics[k].numCopy);
             j.nB = (uint16_t)t.pics[k].numPassB;
+            picMaxQ_[k] = std::max<uint32_t>(picMaxQ_[k], j.nQ);
             picMaxC_[k] = std::max<uint32_t>(picMaxC_[k], j.nC);
-            picMaxA_[k] = std::max<uint32_t>(picMaxA_[k], (uint32_t)(j.nA - j.nC));
+            picMaxA_[k] = std::max<uint32_t>(picMaxA_[k], j.nA);
             picMaxB_[k] = std::max<uint32_t>(picMaxB_[k], j.nB);
         }
     cudaFree(dJobs_);
@@ -288,7 +292,7 @@ bool Batch::kernelTimes(float ms[6], uint32_t *launchesPerStage) {
     return true;
 }
 
-bool Batch::launchPicture(const StreamJob *dJobs, uint32_t maxC, uint32_t maxA, uint32_t maxB, bool recon, bool deblock) {
+bool Batch::launchPicture(const StreamJob *dJobs, uint32_t maxQ, uint32_t maxC, uint32_t maxA, uint32_t maxB, bool recon, bool deblock) {
     const uint32_t total = (uint32_t)g_.nStreams * (uint32_t)g_.nMbs;
     serial_++;
     auto mark = [&](int stageEnded) {
@@ -306,8 +310,9 @@ bool Batch::launchPicture(const StreamJob *dJobs, uint32_t maxC, uint32_t maxA, 
         rp.chunksA = (maxA + kReconWarps * kChunkA - 1) / (kReconWarps * kChunkA);
         rp.virtualCtasA = rp.chunksA * (uint32_t)g_.nStreams;
         rp.chunksC = (maxC + 31) / 32;
-        if (maxC) {
-            const uint32_t ctas = (rp.chunksC * (uint32_t)g_.nStreams + kCopyWarps - 1) / kCopyWarps;
+        rp.chunksQ = (maxQ + 31) / 32;
+        if (maxC || maxQ) {
+            const uint32_t ctas = ((rp.chunksC + rp.chunksQ) * (uint32_t)g_.nStreams + kCopyWarps - 1) / kCopyWarps;
             reconCopyKernel<<<std::min<uint32_t>(ctas, (uint32_t)copyBlocks_), kCopyWarps * 32, 0, stream_>>>(rp);
             launches_++;
             mark(5);
@@ -357,7 +362,7 @@ bool Batch::decodePicture(uint32_t k) {
     CK(cudaSetDevice(device_));
     if (jobsDirty_ && !buildJobs()) return false;
     if (k >= numPics_) return false;
-    return launchPicture(dJobs_ + (size_t)k * g_.nStreams, picMaxC_[k], picMaxA_[k], picMaxB_[k], true, true);
+    return launchPicture(dJobs_ + (size_t)k * g_.nStreams, picMaxQ_[k], picMaxC_[k], picMaxA_[k], picMaxB_[k], true, true);
 }
 
 bool Batch::debugStage(uint32_t k, bool recon, bool deblock) {
@@ -365,7 +370,7 @@ bool Batch::debugStage(uint32_t k, bool recon, bool deblock) {
     CK(cudaSetDevice(device_));
     if (jobsDirty_ && !buildJobs()) return false;
     if (k >= numPics_) return false;
-    return launchPicture(dJobs_ + (size_t)k * g_.nStreams, picMaxC_[k], picMaxA_[k], picMaxB_[k], recon, deblock);
+    return launchPicture(dJobs_ + (size_t)k * g_.nStreams, picMaxQ_[k], picMaxC_[k], picMaxA_[k], picMaxB_[k], recon, deblock);
 }
 
 bool Batch::run(uint32_t first, uint32_t count) {
@@ -377,8 +382,14 @@ bool Batch::run(uint32_t first, uint32_t count) {
 bool Batch::sync() {
     if (!created_) return false;
     CK(cudaSetDevice(device_));
-    CK(cudaStreamSynchronize(stream_));
-    if (copyStream_) CK(cudaStreamSynchronize(copyStream_));
+    // blocking-sync events: the waiting host thread sleeps instead of spinning (the host cores are busy parsing)
+    if (!syncEv_) CK(cudaEventCreateWithFlags(&syncEv_, cudaEventBlockingSync | cudaEventDisableTiming));
+    CK(cudaEventRecord(syncEv_, stream_));
+    CK(cudaEventSynchronize(syncEv_));
+    if (copyStream_) {
+        CK(cudaEventRecord(syncEv_, copyStream_));
+        CK(cudaEventSynchronize(syncEv_));
+    }
     return true;
 }
 
@@ -421,8 +432,9 @@ bool Batch::submitHostPicture(uint32_t stream, const b200_pic_hdr &hdr, const b2
     job.coefs = reinterpret_cast<const int16_t *>(dStage_[b] + coefOff);
     job.order = reinterpret_cast<const uint16_t *>(dStage_[b] + orderOff);
     job.curSlot = (uint16_t)hdr.curSlot;
+    job.nQ = (uint16_t)hdr.numQuad;
     job.nC = (uint16_t)hdr.numCopy;
-    job.nA = (uint16_t)hdr.numPassA;
+    job.nA = (uint16_t)(hdr.numPassA - 4 * hdr.numQuad - hdr.numCopy);
     job.nB = (uint16_t)hdr.numPassB;
     std::memcpy(h, &job, sizeof job);
     std::memcpy(h + recOff, recs, recBytes);
@@ -430,7 +442,7 @@ bool Batch::submitHostPicture(uint32_t stream, const b200_pic_hdr &hdr, const b2
     std::memcpy(h + coefOff, coefs, coefBytes);
     CK(cudaMemcpyAsync(dStage_[b], h, coefOff + coefBytes, cudaMemcpyHostToDevice, stream_));
     h2dBytes_ += coefOff + coefBytes;
-    if (!launchPicture(reinterpret_cast<const StreamJob *>(dStage_[b]), hdr.numCopy, hdr.numPassA - hdr.numCopy, hdr.numPassB, true, true)) return false;
+    if (!launchPicture(reinterpret_cast<const StreamJob *>(dStage_[b]), hdr.numQuad, hdr.numCopy, hdr.numPassA - 4 * hdr.numQuad - hdr.numCopy, hdr.numPassB, true, true)) return false;
     CK(cudaEventRecord(stageEv_[b], stream_));
     return true;
 }

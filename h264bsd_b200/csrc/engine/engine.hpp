@@ -62,8 +62,8 @@ private:
         std::vector<b200_pic_hdr> pics;
     };
     bool buildJobs();
-    bool launchPicture(const StreamJob *dJobs, uint32_t maxC, uint32_t maxA, uint32_t maxB, bool recon, bool deblock);
-    std::vector<uint32_t> picMaxC_, picMaxA_, picMaxB_;
+    bool launchPicture(const StreamJob *dJobs, uint32_t maxQ, uint32_t maxC, uint32_t maxA, uint32_t maxB, bool recon, bool deblock);
+    std::vector<uint32_t> picMaxQ_, picMaxC_, picMaxA_, picMaxB_;
 
     bool created_ = false;
     int device_ = 0, numSms_ = 0;
@@ -78,6 +78,7 @@ private:
     int strengthBlocks_ = 0;
     uint32_t serial_ = 0;
     int reconBlocks_ = 0, deblockBlocks_ = 0, copyBlocks_ = 0;
+    cudaEvent_t syncEv_ = nullptr;
     std::vector<DevTape> tapes_;
     StreamJob *dJobs_ = nullptr;
     uint32_t numPics_ = 0;

@@ -30,10 +30,11 @@ struct PoolGeom {
 struct StreamJob {
     const b200_mb_rec *recs;  // nMbs records of this picture
     const int16_t *coefs;     // this picture's coefficient pool
-    const uint16_t *order;    // nMbs macroblock addresses: nA pass-A entries (the first nC of them plain copies), then nB pass-B entries (wavefront)
+    const uint16_t *order;    // macroblock addresses: nQ zero-motion quads (first address), nC single plain copies, nA other
+                              // pass-A macroblocks, nB pass-B macroblocks in wavefront order (b200_tape.mbOrder)
     uint16_t curSlot;
-    uint16_t nC;              // plain copies at the head of the pass-A list (b200_pic_hdr.numCopy)
-    uint16_t nA, nB;
+    uint16_t nQ, nC, nA, nB;
+    uint16_t pad[3];
 };
 
 }  // namespace b200

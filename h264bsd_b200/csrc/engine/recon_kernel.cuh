@@ -25,7 +25,8 @@ struct ReconParams {
     uint32_t chunksB;          // pass B: warp tasks (kChunkB entries) per stream
     uint32_t chunksA;          // pass A: virtual CTAs per stream (kReconWarps * kChunkA entries each)
     uint32_t virtualCtasA;     // chunksA * nStreams
-    uint32_t chunksC;          // copy pass: warp tasks per stream (32 entries each)
+    uint32_t chunksC;          // copy pass: warp tasks of 32 single copies per stream
+    uint32_t chunksQ;          // copy pass: warp tasks of 32 quads per stream (they come first)
 };
 
 struct __align__(128) InterWarpSmem {
@@ -429,21 +430,65 @@ __global__ void __launch_bounds__(kCopyWarps * 32) reconCopyKernel(const ReconPa
     const PoolGeom &g = p.g;
     const int r8 = lane >> 1, c8 = (lane & 1) * 8;
     const int cp = lane >> 4, cr = (lane >> 1) & 7, cc = (lane & 1) * 4;
-    const uint32_t totalTasks = p.chunksC * (uint32_t)g.nStreams;
+    const uint32_t tasksPerStream = p.chunksQ + p.chunksC;
+    const uint32_t totalTasks = tasksPerStream * (uint32_t)g.nStreams;
     for (uint32_t t = blockIdx.x * kCopyWarps + warp; t < totalTasks; t += gridDim.x * kCopyWarps) {
-        const uint32_t s = t / p.chunksC, chunk = t - s * p.chunksC;
+        const uint32_t s = t / tasksPerStream, task = t - s * tasksPerStream;
         const StreamJob job = p.jobs[s];
-        const uint32_t e0 = chunk * 32u;
-        if (e0 >= job.nC) continue;
-        const int n = (int)min(32u, (uint32_t)job.nC - e0);
         const uint32_t frameBase = s * (uint32_t)g.numSlots;
         uint8_t *cur = framePtr(p.pool, g, frameBase + job.curSlot);
+        if (task < p.chunksQ) {
+            // ---- quads: four macroblocks side by side, zero vector, one reference frame: 16 rows of 64 bytes + 2 x 8 rows
+            // of 32 bytes, moved as 16-byte vectors (whole sectors), same offset in the reference and the current frame
+            const uint32_t e0 = task * 32u;
+            if (e0 >= job.nQ) continue;
+            const int n = (int)min(32u, (uint32_t)job.nQ - e0);
+            uint32_t mOff = 0, mOffC = 0;
+            long long mDelta = 0;   // reference frame - current frame
+            if (lane < n) {
+                const uint32_t mb = __ldg(job.order + e0 + lane);
+                const uint32_t refSlots = __ldg(reinterpret_cast<const uint32_t *>(job.recs + mb) + 4);
+                const int mby = (int)__umulhi(mb, g.invWidthMbs), mbx = (int)(mb - (uint32_t)mby * g.widthMbs);
+                mOff = (uint32_t)((mby * 16 + kPadY) * g.pitchY + mbx * 16 + kPadY);
+                mOffC = (uint32_t)((mby * 8 + kPadC) * g.pitchC + mbx * 8 + kPadC);
+                mDelta = ((long long)(refSlots & 0xFF) - (long long)job.curSlot) * (long long)g.frameStride;
+            }
+            // lane -> luma chunk (row lane >> 2 (+8), 16-byte column lane & 3), chroma chunk (plane, row, half)
+            const uint32_t lY = (uint32_t)(lane >> 2) * g.pitchY + (lane & 3) * 16, lY2 = lY + 8u * g.pitchY;
+            const size_t lC = (cp ? g.offCr : g.offCb) + (size_t)cr * g.pitchC + (lane & 1) * 16;
+#pragma unroll 1
+            for (int i0 = 0; i0 < n; i0 += 2) {
+                uint4 a[2], b[2], c[2];
+                uint8_t *dst[2], *dstC[2];
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const int i = min(i0 + u, n - 1);
+                    const uint32_t off = __shfl_sync(0xffffffffu, mOff, i), offC = __shfl_sync(0xffffffffu, mOffC, i);
+                    const long long delta = __shfl_sync(0xffffffffu, mDelta, i);
+                    dst[u] = cur + off;
+                    dstC[u] = cur + offC + lC;
+                    a[u] = __ldg(reinterpret_cast<const uint4 *>(dst[u] + delta + lY));
+                    b[u] = __ldg(reinterpret_cast<const uint4 *>(dst[u] + delta + lY2));
+                    c[u] = __ldg(reinterpret_cast<const uint4 *>(dstC[u] + delta));
+                }
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    *reinterpret_cast<uint4 *>(dst[u] + lY) = a[u];
+                    *reinterpret_cast<uint4 *>(dst[u] + lY2) = b[u];
+                    *reinterpret_cast<uint4 *>(dstC[u]) = c[u];
+                }
+            }
+            continue;
+        }
+        const uint32_t e0 = (task - p.chunksQ) * 32u;
+        if (e0 >= job.nC) continue;
+        const int n = (int)min(32u, (uint32_t)job.nC - e0);
         // lane j: where entry j's source lies (clamped like issueWindow: a block wholly outside the picture on an axis equals
         // the block at the clamped origin because the border is a replication)
         uint32_t mMb = 0;
         unsigned long long mSrcY = 0, mSrcC = 0;
         if (lane < n) {
-            mMb = __ldg(job.order + e0 + lane);
+            mMb = __ldg(job.order + job.nQ + e0 + lane);
             const uint32_t *rw = reinterpret_cast<const uint32_t *>(job.recs + mMb);
             const uint32_t refSlots = __ldg(rw + 4), mvv = __ldg(rw + 8);
             const int mvx = (int)(int16_t)(mvv & 0xFFFF), mvy = (int)(int16_t)(mvv >> 16);
@@ -540,9 +585,10 @@ reconInterKernel(const ReconParams p, const __grid_constant__ CUtensorMap lumaMa
     for (uint32_t v = blockIdx.x; v < p.virtualCtasA; v += gridDim.x) {
     const uint32_t s = v / p.chunksA, chunk = v - s * p.chunksA;
     const StreamJob job = p.jobs[s];
-    const uint32_t e0 = (uint32_t)job.nC + (chunk * kReconWarps + warp) * kChunkA;   // the plain copies went to reconCopyKernel
-    if (e0 >= job.nA) continue;
-    const int n = min((uint32_t)kChunkA, job.nA - e0);
+    const uint32_t l0 = (chunk * kReconWarps + warp) * kChunkA;   // index into the stream's pass-A entries that are not plain copies
+    if (l0 >= job.nA) continue;
+    const int n = min((uint32_t)kChunkA, job.nA - l0);
+    const uint32_t e0 = (uint32_t)job.nQ + job.nC + l0;           // the plain copies went to reconCopyKernel
     const uint32_t frameBase = s * (uint32_t)g.numSlots;
     uint8_t *cur = framePtr(p.pool, g, frameBase + job.curSlot);
     const int r8 = lane >> 1, c8 = (lane & 1) * 8;
@@ -727,7 +773,7 @@ __global__ void __launch_bounds__(kReconWarps * 32, 3) reconIntraKernel(const Re
 
 #pragma unroll 1
     for (int i = 0; i < n; i++) {
-        const uint32_t mb = __ldg(job.order + job.nA + e0 + i);
+        const uint32_t mb = __ldg(job.order + ((uint32_t)job.nQ + job.nC + job.nA) + e0 + i);
         const int mby = (int)(mb / (uint32_t)g.widthMbs), mbx = (int)(mb - (uint32_t)mby * g.widthMbs);
         const b200_mb_rec *rec = job.recs + mb;
         const MbHead h = loadHead(rec);

@@ -643,18 +643,38 @@ void PictureState::finalizeRecords() {
     // processing order + which neighbours an intra macroblock has to wait for
     auto passB = [&](int nb) { return nb >= 0 && recs[nb].mbType > B200_MB_P_8x8REF0 && recs[nb].mbType != B200_MB_I_PCM; };
     order.resize(picSizeInMbs);
-    // plain copies first: P_Skip / P_L0_16x16 without residual whose vector is integer for luma and chroma
+    // plain copies first: P_Skip / P_L0_16x16 without residual whose vector is integer for luma and chroma; four of them
+    // side by side (x = 4q..4q+3) with a zero vector and one reference slot become one "quad" entry (full 64-byte rows)
     auto plainCopy = [&](uint32_t a) {
         const b200_mb_rec &r = recs[a];
         return r.mbType <= B200_MB_P_16x16 && r.codedMask == 0 && ((r.u.mv[0][0] | r.u.mv[0][1]) & 7) == 0;
     };
-    uint32_t nA = 0;
+    std::vector<uint8_t> &cls = orderClass;   // 0 other, 1 single copy, 2 first of a quad, 3 rest of a quad
+    cls.assign(picSizeInMbs, 0);
     for (uint32_t a = 0; a < picSizeInMbs; a++)
-        if (!passB((int)a) && plainCopy(a)) order[nA++] = (uint16_t)a;
-    numCopy = nA;
+        if (!passB((int)a) && plainCopy(a)) cls[a] = 1;
+    for (uint32_t row = 0; row < heightMbs; row++)
+        for (uint32_t x = 0; x + 3 < widthMbs; x += 4) {
+            const uint32_t a = row * widthMbs + x;
+            bool ok = true;
+            for (uint32_t i = 0; i < 4 && ok; i++) {
+                const b200_mb_rec &r = recs[a + i];
+                ok = cls[a + i] == 1 && r.u.mv[0][0] == 0 && r.u.mv[0][1] == 0 && r.refSlot[0] == recs[a].refSlot[0];
+            }
+            if (ok) { cls[a] = 2; cls[a + 1] = cls[a + 2] = cls[a + 3] = 3; }
+        }
+    uint32_t n = 0;
     for (uint32_t a = 0; a < picSizeInMbs; a++)
-        if (!passB((int)a) && !plainCopy(a)) order[nA++] = (uint16_t)a;
+        if (cls[a] == 2) order[n++] = (uint16_t)a;
+    numQuad = n;
+    for (uint32_t a = 0; a < picSizeInMbs; a++)
+        if (cls[a] == 1) order[n++] = (uint16_t)a;
+    numCopy = n - numQuad;
+    uint32_t nA = 4 * numQuad + numCopy;
+    for (uint32_t a = 0; a < picSizeInMbs; a++)
+        if (!passB((int)a) && cls[a] == 0) { order[n++] = (uint16_t)a; nA++; }
     numPassA = nA;
+    const uint32_t listB = n;   // where the pass-B entries start in the list
     numPassB = picSizeInMbs - nA;
     if (numPassB) {
         // bucket by wavefront key x + 2y (stable in address order inside a key)
@@ -664,7 +684,7 @@ void PictureState::finalizeRecords() {
             if (passB((int)a)) cnt[a % widthMbs + 2 * (a / widthMbs) + 1]++;
         for (uint32_t k = 0; k < nKeys; k++) cnt[k + 1] += cnt[k];
         for (uint32_t a = 0; a < picSizeInMbs; a++)
-            if (passB((int)a)) order[nA + cnt[a % widthMbs + 2 * (a / widthMbs)]++] = (uint16_t)a;
+            if (passB((int)a)) order[listB + cnt[a % widthMbs + 2 * (a / widthMbs)]++] = (uint16_t)a;
     }
     for (uint32_t a = 0; a < picSizeInMbs; a++) {
         b200_mb_rec &r = recs[a];

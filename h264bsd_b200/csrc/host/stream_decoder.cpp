@@ -233,6 +233,7 @@ void StreamDecoder::finishPicture() {
     hdr.numPassA = pic_.numPassA;
     hdr.numPassB = pic_.numPassB;
     hdr.numCopy = pic_.numCopy;
+    hdr.numQuad = pic_.numQuad;
 
     int32_t poc = decodePicOrderCnt(poc_, *activeSps_, sliceHeader_, prevNal_);
     if (validSliceInAccessUnit_) {

@@ -120,8 +120,11 @@ typedef struct b200_pic_hdr {
     uint32_t picId;        /* application picId (h264bsdDecode argument) */
     uint32_t numPassA;     /* macroblocks reconstructed without looking at the current picture: inter + I_PCM */
     uint32_t numPassB;     /* intra-predicted macroblocks (read unfiltered neighbours of the current picture) */
-    uint32_t numCopy;      /* the first numCopy pass-A entries are plain copies: one 16x16 partition, no residual, motion
-                              vector a multiple of 8 quarter-pels in both components (integer for luma AND chroma) */
+    uint32_t numCopy;      /* plain copies listed one by one: one 16x16 partition, no residual, motion vector a multiple of
+                              8 quarter-pels in both components (integer for luma AND chroma) */
+    uint32_t numQuad;      /* groups of four horizontally adjacent plain copies (x = 4q .. 4q+3) with a zero vector and the
+                              same reference slot: one list entry (the address of the first) per group */
+    uint32_t reserved;
 } b200_pic_hdr;
 
 /* A fully parsed stream in host memory (built by h264bsdB200ParseStream). */
@@ -139,9 +142,10 @@ typedef struct b200_tape {
     uint8_t *mbRecs;     /* mbRecBytes */
     uint8_t *coefs;      /* coefBytes  */
     /* processing order, widthMbs*heightMbs uint16 macroblock addresses per picture (picture p at p*nMbs):
-     * first numPassA entries (numCopy plain copies in raster order, then the other inter / I_PCM macroblocks in raster
-     * order), then numPassB entries in wavefront order (x + 2y ascending), so that every macroblock an intra MB depends
-     * on precedes it */
+     * numQuad zero-motion groups (first address of each), numCopy single plain copies, the other
+     * numPassA - 4*numQuad - numCopy inter / I_PCM macroblocks (all three in raster order), then numPassB entries in
+     * wavefront order (x + 2y ascending), so that every macroblock an intra MB depends on precedes it.  The list of a
+     * picture has numQuad + numCopy + (numPassA - 4*numQuad - numCopy) + numPassB <= widthMbs*heightMbs entries. */
     uint16_t *mbOrder;
     uint32_t numOutputs;        /* pictures in output order, incl. those drained by the final flush */
     uint32_t reserved2;
