@@ -141,9 +141,11 @@ __global__ void __launch_bounds__(kDeblockWarps * 32) strengthKernel(const Deblo
             const BsSide cur = loadSide(rc, qb);
             const int flags = cur.w0 >> 24;
             const bool fLeft = flags & B200_MBF_FILTER_LEFT, fTop = flags & B200_MBF_FILTER_TOP;
-            // GetMbFilteringFlags :289-320 was resolved on the host; a neighbour that is not filtered against is never read
-            const BsSide lef = loadSide((bx == 0 && fLeft) ? rc - 1 : rc, lb);
-            const BsSide top = loadSide((by == 0 && fTop) ? rc - g.widthMbs : rc, tb);
+            // GetMbFilteringFlags :289-320 was resolved on the host.  The neighbour records are fetched whether or not the edge
+            // is filtered (their addresses must not depend on the flags just loaded: one memory round trip per iteration, not
+            // two); a record that does not exist (first macroblock / first row) is replaced by the current one and ignored
+            const BsSide lef = loadSide((bx == 0 && mb > 0) ? rc - 1 : rc, lb);
+            const BsSide top = loadSide((by == 0 && mb >= (uint32_t)g.widthMbs) ? rc - g.widthMbs : rc, tb);
             const bool curIntra = (cur.w0 & 0xFF) > B200_MB_P_8x8REF0;
             int bv, bh;
             if (bx == 0) bv = !fLeft ? 0 : (curIntra || (lef.w0 & 0xFF) > B200_MB_P_8x8REF0) ? 4 : bsInter(cur, qb, lef, lb);
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(kDeblockWarps * 32) strengthKernel(const Deblo
 // and 2.  A step is skipped when no lane of the warp has a strength for it.
 __device__ __forceinline__ int bsNibble(uint32_t word, int idx) { return (int)((word >> (4 * idx)) & 15u); }
 
-__global__ void __launch_bounds__(kDeblockWarps * 32) deblockKernel(const DeblockParams p) {
+__global__ void __launch_bounds__(kDeblockWarps * 32, 4) deblockKernel(const DeblockParams p) {
     __shared__ DeblockWarpSmem smemAll[kDeblockWarps];
     __shared__ DeblockTables tb;
     __shared__ uint32_t sBase;
@@ -208,35 +210,59 @@ __global__ void __launch_bounds__(kDeblockWarps * 32) deblockKernel(const Debloc
         __syncthreads();
         const uint32_t base = sBase;
         if (base >= p.totalTickets) break;
+        // lane j < kFilterChunk walks the dependent loads of the warp's ticket j (order -> work flag -> record, strengths,
+        // neighbours), all tickets at once: one chain of memory latencies per chunk instead of one per macroblock
+        uint32_t mMb = 0, mS = 0, mW0 = 0, mW3 = 0, mQp = 0, mWork = 0;
+        uint4 mBw = make_uint4(0, 0, 0, 0);
+        unsigned long long mFrame = 0;
+        if (lane < kFilterChunk) {
+            const uint32_t t = base + warp * kFilterChunk + lane;
+            if (t < p.totalTickets) {
+                const uint32_t k = t / (uint32_t)g.nStreams, s = t - k * (uint32_t)g.nStreams;
+                const uint32_t mb = p.order[k];
+                const size_t sIdx = (size_t)s * g.nMbs;
+                if (p.work[sIdx + mb]) {   // else nothing to filter: this macroblock touches no pel
+                    const int mby = (int)__umulhi(mb, g.invWidthMbs), mbx = (int)(mb - (uint32_t)mby * g.widthMbs);
+                    const StreamJob job = p.jobs[s];
+                    const uint32_t *cw = reinterpret_cast<const uint32_t *>(job.recs + mb);
+                    mW0 = __ldg(cw); mW3 = __ldg(cw + 3);
+                    mBw = __ldg(reinterpret_cast<const uint4 *>(p.bsWords + (sIdx + mb) * 4));
+                    const int flags = mW0 >> 24;
+                    // qp of the neighbours filtered against (never read otherwise: they may not exist)
+                    const uint32_t qp = (mW0 >> 8) & 0xFF;
+                    const uint32_t qpL = (flags & B200_MBF_FILTER_LEFT) ? (__ldg(cw - 24) >> 8) & 0xFF : qp;
+                    const uint32_t qpT = (flags & B200_MBF_FILTER_TOP) ? (__ldg(cw - 24 * g.widthMbs) >> 8) & 0xFF : qp;
+                    mQp = qpL | (qpT << 8);
+                    // bits 1..3: wait for the left / top / top-right neighbour (it exists and has work)
+                    mWork = 1;
+                    if (mbx > 0 && p.work[sIdx + mb - 1]) mWork |= 2;
+                    if (mby > 0 && p.work[sIdx + mb - g.widthMbs]) mWork |= 4;
+                    if (mby > 0 && mbx < g.widthMbs - 1 && p.work[sIdx + mb - g.widthMbs + 1]) mWork |= 8;
+                    mMb = mb; mS = s;
+                    mFrame = (unsigned long long)(s * (uint32_t)g.numSlots + job.curSlot) * g.frameStride;
+                }
+            }
+        }
 #pragma unroll 1
-        for (uint32_t j = 0; j < kFilterChunk; j++) {
-            const uint32_t t = base + warp * kFilterChunk + j;
-            if (t >= p.totalTickets) break;
-            const uint32_t k = t / (uint32_t)g.nStreams, s = t - k * (uint32_t)g.nStreams;
-            const uint32_t mb = p.order[k];
+        for (int j = 0; j < kFilterChunk; j++) {
+            const uint32_t workBits = __shfl_sync(0xffffffffu, mWork, j);
+            if (!workBits) continue;
+            const uint32_t mb = __shfl_sync(0xffffffffu, mMb, j), s = __shfl_sync(0xffffffffu, mS, j);
+            const uint32_t w0 = __shfl_sync(0xffffffffu, mW0, j), w3 = __shfl_sync(0xffffffffu, mW3, j);
+            const uint32_t qpn = __shfl_sync(0xffffffffu, mQp, j);
+            uint4 bw;
+            bw.x = __shfl_sync(0xffffffffu, mBw.x, j); bw.y = __shfl_sync(0xffffffffu, mBw.y, j);
+            bw.z = __shfl_sync(0xffffffffu, mBw.z, j); bw.w = __shfl_sync(0xffffffffu, mBw.w, j);
+            uint8_t *frame = p.pool + __shfl_sync(0xffffffffu, mFrame, j);
             const size_t sIdx = (size_t)s * g.nMbs;
-            if (!p.work[sIdx + mb]) continue;   // nothing to filter: this macroblock touches no pel
             const int mby = (int)__umulhi(mb, g.invWidthMbs), mbx = (int)(mb - (uint32_t)mby * g.widthMbs);
-            const StreamJob job = p.jobs[s];
             uint32_t *doneS = p.done + sIdx;
-            const uint32_t *cw = reinterpret_cast<const uint32_t *>(job.recs + mb);
-            const uint32_t w0 = __ldg(cw), w3 = __ldg(cw + 3);
-            const uint4 bw = __ldg(reinterpret_cast<const uint4 *>(p.bsWords + (sIdx + mb) * 4));
-            const int flags = w0 >> 24;
-            const bool fLeft = flags & B200_MBF_FILTER_LEFT, fTop = flags & B200_MBF_FILTER_TOP;
-            // qp of the neighbours filtered against (never read otherwise: they may not exist)
-            const int qp = (w0 >> 8) & 0xFF;
-            const int qpL = fLeft ? (int)((__ldg(cw - 24) >> 8) & 0xFF) : qp;
-            const int qpT = fTop ? (int)((__ldg(cw - 24 * g.widthMbs) >> 8) & 0xFF) : qp;
-            if (lane < 3) {
-                int nmb = -1;
-                if (lane == 0 && mbx > 0) nmb = (int)mb - 1;
-                if (lane == 1 && mby > 0) nmb = (int)mb - g.widthMbs;
-                if (lane == 2 && mby > 0 && mbx < g.widthMbs - 1) nmb = (int)mb - g.widthMbs + 1;
-                if (nmb >= 0 && p.work[sIdx + nmb]) waitFlag(doneS + nmb, p.serial);
+            const int qp = (w0 >> 8) & 0xFF, qpL = qpn & 0xFF, qpT = (qpn >> 8) & 0xFF;
+            if (lane < 3 && ((workBits >> (lane + 1)) & 1)) {
+                const int nmb = lane == 0 ? (int)mb - 1 : lane == 1 ? (int)mb - g.widthMbs : (int)mb - g.widthMbs + 1;
+                waitFlag(doneS + nmb, p.serial);
             }
             __syncwarp();
-            uint8_t *frame = framePtr(p.pool, g, s * (uint32_t)g.numSlots + job.curSlot);
             // stage 20 luma rows and 2 x 10 chroma rows (incl. 4 / 2 rows of the upper and 4 columns of the left neighbour)
             uint8_t *gy = nullptr, *gc = nullptr;
             if (lane < 20) {

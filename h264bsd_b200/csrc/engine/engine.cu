@@ -63,6 +63,11 @@ void Batch::destroy() {
     for (cudaEvent_t e : evPool_) cudaEventDestroy(e);
     evPool_.clear(); evStage_.clear();
     if (syncEv_) cudaEventDestroy(syncEv_);
+    if (forkEv_) cudaEventDestroy(forkEv_);
+    for (int i = 0; i < 2; i++) {
+        if (joinEv_[i]) cudaEventDestroy(joinEv_[i]);
+        if (auxStream_[i]) cudaStreamDestroy(auxStream_[i]);
+    }
     if (evA_) cudaEventDestroy(evA_);
     if (evB_) cudaEventDestroy(evB_);
     if (stream_) cudaStreamDestroy(stream_);
@@ -164,6 +169,11 @@ bool Batch::create(int device, uint32_t nStreams, uint32_t widthMbs, uint32_t he
     copyBlocks_ = std::max(1, occC) * numSms_;
     deblockBlocks_ = std::max(1, occD) * numSms_;
     tapes_.assign(nStreams, DevTape());
+    for (int i = 0; i < 2; i++) {
+        CK(cudaStreamCreateWithFlags(&auxStream_[i], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&joinEv_[i], cudaEventDisableTiming));
+    }
+    CK(cudaEventCreateWithFlags(&forkEv_, cudaEventDisableTiming));
     CK(cudaStreamSynchronize(stream_));
     return true;
 }
@@ -302,8 +312,12 @@ bool Batch::launchPicture(const StreamJob *dJobs, uint32_t maxQ, uint32_t maxC, 
         cudaEventRecord(e, stream_);
     };
     mark(-1);
+    // The copy pass, pass A and the boundary strengths do not depend on each other (disjoint macroblocks of the current
+    // frame / records only): outside the per-kernel timing mode they run on three streams, DRAM-bound next to
+    // issue-bound next to latency-bound.  Fork after the previous picture's border, join before the intra pass / filter.
+    const bool fork = !timing_ && recon && deblock && auxStream_[0] != nullptr;
+    ReconParams rp;
     if (recon) {
-        ReconParams rp;
         rp.pool = pool_; rp.g = g_; rp.jobs = dJobs; rp.done = dDoneRecon_;
         rp.ticket = dCounters_ + 0; rp.errors = dCounters_ + 2; rp.serial = serial_;
         rp.chunksB = (maxB + kChunkB - 1) / kChunkB;
@@ -311,10 +325,33 @@ bool Batch::launchPicture(const StreamJob *dJobs, uint32_t maxQ, uint32_t maxC, 
         rp.virtualCtasA = rp.chunksA * (uint32_t)g_.nStreams;
         rp.chunksC = (maxC + 31) / 32;
         rp.chunksQ = (maxQ + 31) / 32;
+    }
+    DeblockParams dp;
+    if (deblock) {
+        dp.pool = pool_; dp.g = g_; dp.jobs = dJobs; dp.order = dOrder_; dp.done = dDoneDeblock_;
+        dp.ticket = dCounters_ + 1; dp.serial = serial_; dp.totalTickets = total;
+        dp.bsWords = dBsWords_; dp.work = dWork_;
+    }
+    auto launchStrength = [&](cudaStream_t st) {
+        const uint32_t chunks = ((uint32_t)g_.nMbs + kDeblockWarps * kBsChunk - 1) / (kDeblockWarps * kBsChunk) * (uint32_t)g_.nStreams;
+        strengthKernel<<<std::min<uint32_t>(chunks, (uint32_t)strengthBlocks_), kDeblockWarps * 32, 0, st>>>(dp);
+        launches_++;
+    };
+    if (fork) {
+        CK(cudaEventRecord(forkEv_, stream_));
+        CK(cudaStreamWaitEvent(auxStream_[1], forkEv_, 0));
+        launchStrength(auxStream_[1]);
+        CK(cudaEventRecord(joinEv_[1], auxStream_[1]));
+    }
+    if (recon) {
+        const bool copyAside = fork && (maxC || maxQ) && maxA;   // something to overlap with
         if (maxC || maxQ) {
+            cudaStream_t st = copyAside ? auxStream_[0] : stream_;
+            if (copyAside) CK(cudaStreamWaitEvent(st, forkEv_, 0));
             const uint32_t ctas = ((rp.chunksC + rp.chunksQ) * (uint32_t)g_.nStreams + kCopyWarps - 1) / kCopyWarps;
-            reconCopyKernel<<<std::min<uint32_t>(ctas, (uint32_t)copyBlocks_), kCopyWarps * 32, 0, stream_>>>(rp);
+            reconCopyKernel<<<std::min<uint32_t>(ctas, (uint32_t)copyBlocks_), kCopyWarps * 32, 0, st>>>(rp);
             launches_++;
+            if (copyAside) CK(cudaEventRecord(joinEv_[0], st));
             mark(5);
         }
         if (maxA) {
@@ -323,6 +360,7 @@ bool Batch::launchPicture(const StreamJob *dJobs, uint32_t maxQ, uint32_t maxC, 
             launches_++;
             mark(0);
         }
+        if (copyAside) CK(cudaStreamWaitEvent(stream_, joinEv_[0], 0));
         if (maxB) {
             reconIntraKernel<<<(rp.chunksB * (uint32_t)g_.nStreams + kReconWarps - 1) / kReconWarps, kReconWarps * 32, 0, stream_>>>(rp);
             launches_++;
@@ -330,14 +368,12 @@ bool Batch::launchPicture(const StreamJob *dJobs, uint32_t maxQ, uint32_t maxC, 
         }
     }
     if (deblock) {
-        DeblockParams dp;
-        dp.pool = pool_; dp.g = g_; dp.jobs = dJobs; dp.order = dOrder_; dp.done = dDoneDeblock_;
-        dp.ticket = dCounters_ + 1; dp.serial = serial_; dp.totalTickets = total;
-        dp.bsWords = dBsWords_; dp.work = dWork_;
-        const uint32_t chunks = ((uint32_t)g_.nMbs + kDeblockWarps * kBsChunk - 1) / (kDeblockWarps * kBsChunk) * (uint32_t)g_.nStreams;
-        strengthKernel<<<std::min<uint32_t>(chunks, (uint32_t)strengthBlocks_), kDeblockWarps * 32, 0, stream_>>>(dp);
-        launches_++;
-        mark(4);
+        if (fork) {
+            CK(cudaStreamWaitEvent(stream_, joinEv_[1], 0));
+        } else {
+            launchStrength(stream_);
+            mark(4);
+        }
         const uint32_t ctas = (total + kDeblockWarps * kFilterChunk - 1) / (kDeblockWarps * kFilterChunk);
         deblockKernel<<<std::min<uint32_t>(ctas, (uint32_t)deblockBlocks_), kDeblockWarps * 32, 0, stream_>>>(dp);
         launches_++;

@@ -78,7 +78,8 @@ private:
     int strengthBlocks_ = 0;
     uint32_t serial_ = 0;
     int reconBlocks_ = 0, deblockBlocks_ = 0, copyBlocks_ = 0;
-    cudaEvent_t syncEv_ = nullptr;
+    cudaEvent_t syncEv_ = nullptr, forkEv_ = nullptr, joinEv_[2] = {nullptr, nullptr};
+    cudaStream_t auxStream_[2] = {nullptr, nullptr};   // copy pass / boundary strengths next to pass A
     std::vector<DevTape> tapes_;
     StreamJob *dJobs_ = nullptr;
     uint32_t numPics_ = 0;

@@ -453,12 +453,15 @@ __global__ void __launch_bounds__(kCopyWarps * 32) reconCopyKernel(const ReconPa
                 mOffC = (uint32_t)((mby * 8 + kPadC) * g.pitchC + mbx * 8 + kPadC);
                 mDelta = ((long long)(refSlots & 0xFF) - (long long)job.curSlot) * (long long)g.frameStride;
             }
-            // lane -> luma chunk (row lane >> 2 (+8), 16-byte column lane & 3), chroma chunk (plane, row, half)
+            // lane -> two 16-byte luma chunks (row lane >> 2 and 8 below, column lane & 3) and two 8-byte chroma chunks
+            // (plane lane >> 4, row (lane >> 2) & 3 and 4 below, column lane & 3): x is arbitrary, so chroma is only 8-byte aligned
             const uint32_t lY = (uint32_t)(lane >> 2) * g.pitchY + (lane & 3) * 16, lY2 = lY + 8u * g.pitchY;
-            const size_t lC = (cp ? g.offCr : g.offCb) + (size_t)cr * g.pitchC + (lane & 1) * 16;
+            const size_t lC = (cp ? g.offCr : g.offCb) + (size_t)((lane >> 2) & 3) * g.pitchC + (lane & 3) * 8;
+            const size_t lC2 = lC + 4u * (size_t)g.pitchC;
 #pragma unroll 1
             for (int i0 = 0; i0 < n; i0 += 2) {
-                uint4 a[2], b[2], c[2];
+                uint4 a[2], b[2];
+                uint2 c[2], d[2];
                 uint8_t *dst[2], *dstC[2];
 #pragma unroll
                 for (int u = 0; u < 2; u++) {
@@ -466,16 +469,18 @@ __global__ void __launch_bounds__(kCopyWarps * 32) reconCopyKernel(const ReconPa
                     const uint32_t off = __shfl_sync(0xffffffffu, mOff, i), offC = __shfl_sync(0xffffffffu, mOffC, i);
                     const long long delta = __shfl_sync(0xffffffffu, mDelta, i);
                     dst[u] = cur + off;
-                    dstC[u] = cur + offC + lC;
+                    dstC[u] = cur + offC;
                     a[u] = __ldg(reinterpret_cast<const uint4 *>(dst[u] + delta + lY));
                     b[u] = __ldg(reinterpret_cast<const uint4 *>(dst[u] + delta + lY2));
-                    c[u] = __ldg(reinterpret_cast<const uint4 *>(dstC[u] + delta));
+                    c[u] = __ldg(reinterpret_cast<const uint2 *>(dstC[u] + delta + lC));
+                    d[u] = __ldg(reinterpret_cast<const uint2 *>(dstC[u] + delta + lC2));
                 }
 #pragma unroll
                 for (int u = 0; u < 2; u++) {
                     *reinterpret_cast<uint4 *>(dst[u] + lY) = a[u];
                     *reinterpret_cast<uint4 *>(dst[u] + lY2) = b[u];
-                    *reinterpret_cast<uint4 *>(dstC[u]) = c[u];
+                    *reinterpret_cast<uint2 *>(dstC[u] + lC) = c[u];
+                    *reinterpret_cast<uint2 *>(dstC[u] + lC2) = d[u];
                 }
             }
             continue;
@@ -771,12 +776,28 @@ __global__ void __launch_bounds__(kReconWarps * 32, 3) reconIntraKernel(const Re
     const int r8 = lane >> 1, c8 = (lane & 1) * 8;
     const int cp = lane >> 4, cr = (lane >> 1) & 7, cc = (lane & 1) * 4;
 
+    // lane j < n fetches entry j's address and record head: one chain of dependent loads per chunk
+    uint32_t mMb = 0, mMisc = 0;
+    uint4 mHead = make_uint4(0, 0, 0, 0);
+    if (lane < n) {
+        mMb = __ldg(job.order + ((uint32_t)job.nQ + job.nC + job.nA) + e0 + lane);
+        const uint32_t *rw = reinterpret_cast<const uint32_t *>(job.recs + mMb);
+        mHead = __ldg(reinterpret_cast<const uint4 *>(rw));
+        mMisc = (__ldg(rw + 5) & 0xFF) | ((__ldg(rw + 7) & 0xFF) << 8);
+    }
 #pragma unroll 1
     for (int i = 0; i < n; i++) {
-        const uint32_t mb = __ldg(job.order + ((uint32_t)job.nQ + job.nC + job.nA) + e0 + i);
+        const uint32_t mb = __shfl_sync(0xffffffffu, mMb, i);
         const int mby = (int)(mb / (uint32_t)g.widthMbs), mbx = (int)(mb - (uint32_t)mby * g.widthMbs);
         const b200_mb_rec *rec = job.recs + mb;
-        const MbHead h = loadHead(rec);
+        MbHead h;
+        {
+            const uint32_t hx = __shfl_sync(0xffffffffu, mHead.x, i);
+            h.mbType = hx & 0xFF; h.qpY = (hx >> 8) & 0xFF; h.qpC = (hx >> 16) & 0xFF; h.flags = hx >> 24;
+            h.mask = __shfl_sync(0xffffffffu, mHead.y, i);
+            h.coefIndex = __shfl_sync(0xffffffffu, mHead.z, i);
+        }
+        const uint32_t misc = __shfl_sync(0xffffffffu, mMisc, i);   // intraChromaMode | waitMask << 8
         const int16_t *coef = job.coefs + (size_t)h.coefIndex * 16;
         uint8_t *dstY = lumaAt(cur, g, mbx * 16 + c8, mby * 16 + r8);
         uint8_t *dstC = chromaAt(cur, g, cp, mbx * 8 + cc, mby * 8 + cr);
@@ -794,7 +815,7 @@ __global__ void __launch_bounds__(kReconWarps * 32, 3) reconIntraKernel(const Re
         const bool avA = flags & B200_MBF_AVAIL_A, avB = flags & B200_MBF_AVAIL_B;
         const bool avC = flags & B200_MBF_AVAIL_C, avD = flags & B200_MBF_AVAIL_D;
         // wait for the intra neighbours this macroblock reads (record byte 28: waitMask)
-        const int waitMask = __ldg(reinterpret_cast<const uint32_t *>(rec) + 7) & 0xFF;
+        const int waitMask = (misc >> 8) & 0xFF;
         if (lane < 4 && ((waitMask >> lane) & 1)) {
             const int nmb = lane == 0 ? (int)mb - 1 : lane == 1 ? (int)mb - g.widthMbs : lane == 2 ? (int)mb - g.widthMbs + 1 : (int)mb - g.widthMbs - 1;
             waitFlag(doneS + nmb, p.serial);
@@ -896,7 +917,7 @@ __global__ void __launch_bounds__(kReconWarps * 32, 3) reconIntraKernel(const Re
         }
         // h264bsdIntraChromaPrediction (:845-915)
         {
-            const int cmode = (__ldg(reinterpret_cast<const uint32_t *>(rec) + 5)) & 0xFF;
+            const int cmode = misc & 0xFF;
             const uint8_t(*tc)[12] = sm.itC[cp];
             int pv[4];
             if (cmode == 0) {

@@ -644,7 +644,7 @@ void PictureState::finalizeRecords() {
     auto passB = [&](int nb) { return nb >= 0 && recs[nb].mbType > B200_MB_P_8x8REF0 && recs[nb].mbType != B200_MB_I_PCM; };
     order.resize(picSizeInMbs);
     // plain copies first: P_Skip / P_L0_16x16 without residual whose vector is integer for luma and chroma; four of them
-    // side by side (x = 4q..4q+3) with a zero vector and one reference slot become one "quad" entry (full 64-byte rows)
+    // side by side with a zero vector and one reference slot become one "quad" entry (64-byte luma rows)
     auto plainCopy = [&](uint32_t a) {
         const b200_mb_rec &r = recs[a];
         return r.mbType <= B200_MB_P_16x16 && r.codedMask == 0 && ((r.u.mv[0][0] | r.u.mv[0][1]) & 7) == 0;
@@ -653,16 +653,21 @@ void PictureState::finalizeRecords() {
     cls.assign(picSizeInMbs, 0);
     for (uint32_t a = 0; a < picSizeInMbs; a++)
         if (!passB((int)a) && plainCopy(a)) cls[a] = 1;
-    for (uint32_t row = 0; row < heightMbs; row++)
-        for (uint32_t x = 0; x + 3 < widthMbs; x += 4) {
+    for (uint32_t row = 0; row < heightMbs; row++) {
+        // runs of zero-vector copies from one reference slot are cut into fours from their start (any x)
+        uint32_t x = 0;
+        while (x + 3 < widthMbs) {
             const uint32_t a = row * widthMbs + x;
-            bool ok = true;
-            for (uint32_t i = 0; i < 4 && ok; i++) {
-                const b200_mb_rec &r = recs[a + i];
-                ok = cls[a + i] == 1 && r.u.mv[0][0] == 0 && r.u.mv[0][1] == 0 && r.refSlot[0] == recs[a].refSlot[0];
+            uint32_t len = 0;
+            while (len < 4) {
+                const b200_mb_rec &r = recs[a + len];
+                if (cls[a + len] != 1 || r.u.mv[0][0] != 0 || r.u.mv[0][1] != 0 || r.refSlot[0] != recs[a].refSlot[0]) break;
+                len++;
             }
-            if (ok) { cls[a] = 2; cls[a + 1] = cls[a + 2] = cls[a + 3] = 3; }
+            if (len == 4) { cls[a] = 2; cls[a + 1] = cls[a + 2] = cls[a + 3] = 3; x += 4; }
+            else x += len ? len : 1;   // a short run stays single copies; the macroblock that ended it may start the next run
         }
+    }
     uint32_t n = 0;
     for (uint32_t a = 0; a < picSizeInMbs; a++)
         if (cls[a] == 2) order[n++] = (uint16_t)a;

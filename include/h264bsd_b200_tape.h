@@ -122,8 +122,8 @@ typedef struct b200_pic_hdr {
     uint32_t numPassB;     /* intra-predicted macroblocks (read unfiltered neighbours of the current picture) */
     uint32_t numCopy;      /* plain copies listed one by one: one 16x16 partition, no residual, motion vector a multiple of
                               8 quarter-pels in both components (integer for luma AND chroma) */
-    uint32_t numQuad;      /* groups of four horizontally adjacent plain copies (x = 4q .. 4q+3) with a zero vector and the
-                              same reference slot: one list entry (the address of the first) per group */
+    uint32_t numQuad;      /* groups of four horizontally adjacent plain copies (any x) with a zero vector and the same
+                              reference slot: one list entry (the address of the first) per group */
     uint32_t reserved;
 } b200_pic_hdr;
 
