@@ -26,6 +26,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 STREAM = os.path.join(ROOT, "tests", "golden", "test_1920x1080.h264")
+E2E_GROUP = 6   # pictures per streamed upload group in the end-to-end leg
 METRIC = "1080p macroblocks/s (H.264 Baseline macroblock reconstruction, bit-exact YUV)"
 UNIT = "MB/s"
 MB_REC_BYTES = 96   # + 2 bytes per macroblock in the per-picture order list: D = 98
@@ -361,8 +362,13 @@ def main():
 
         def gpu_side(st_):
             ta = time.time()
-            for s_ in range(ne):
-                eb.upload(s_, tapes[st_][s_])                            # H2D (page-locked): records + coefficients + order lists
+            # H2D (page-locked) of records + coefficients + order lists in groups of pictures on the copy stream: the upload of
+            # group g+1 overlaps the decode and the D2H of group g
+            for g0 in range(0, ps.num_pics, E2E_GROUP):
+                gn = min(E2E_GROUP, ps.num_pics - g0)
+                for s_ in range(ne):
+                    eb.upload_range(s_, tapes[st_][s_], g0, gn)
+                eb.upload_fence(g0 + gn)
             tb = time.time()
             for k in range(ps.num_pics):
                 eb.decode_picture(k)                                     # GPU: reconstruct + in-loop filter + border

@@ -48,7 +48,7 @@ LEGACY_SYMBOLS = [
 ]
 BATCH_SYMBOLS = [
     "h264bsdB200ParseStream", "h264bsdB200ReparseStream", "h264bsdB200FreeTape", "h264bsdB200DeviceCount", "h264bsdB200BatchCreate",
-    "h264bsdB200BatchDestroy", "h264bsdB200BatchUploadTape", "h264bsdB200BatchReplicateTape",
+    "h264bsdB200BatchDestroy", "h264bsdB200BatchUploadTape", "h264bsdB200BatchReplicateTape", "h264bsdB200BatchUploadTapeRange", "h264bsdB200BatchUploadFence",
     "h264bsdB200BatchDecodePicture", "h264bsdB200BatchRun", "h264bsdB200BatchSync", "h264bsdB200BatchNumPics",
     "h264bsdB200BatchTimerStart", "h264bsdB200BatchTimerStop", "h264bsdB200BatchReadFrame", "h264bsdB200BatchWriteFrame",
     "h264bsdB200BatchConvertFrame", "h264bsdB200BatchConvertBench", "h264bsdB200BatchCompareStreams",
@@ -97,6 +97,8 @@ def load():
     L.h264bsdB200BatchDestroy.restype = None; L.h264bsdB200BatchDestroy.argtypes = [vp]
     L.h264bsdB200BatchUploadTape.restype = C.c_int; L.h264bsdB200BatchUploadTape.argtypes = [vp, u32, C.POINTER(Tape)]
     L.h264bsdB200BatchReplicateTape.restype = C.c_int; L.h264bsdB200BatchReplicateTape.argtypes = [vp, u32]
+    L.h264bsdB200BatchUploadTapeRange.restype = C.c_int; L.h264bsdB200BatchUploadTapeRange.argtypes = [vp, u32, C.POINTER(Tape), u32, u32]
+    L.h264bsdB200BatchUploadFence.restype = C.c_int; L.h264bsdB200BatchUploadFence.argtypes = [vp, u32]
     L.h264bsdB200BatchDecodePicture.restype = C.c_int; L.h264bsdB200BatchDecodePicture.argtypes = [vp, u32]
     L.h264bsdB200BatchRun.restype = C.c_int; L.h264bsdB200BatchRun.argtypes = [vp, u32, u32]
     L.h264bsdB200BatchSync.restype = C.c_int; L.h264bsdB200BatchSync.argtypes = [vp]

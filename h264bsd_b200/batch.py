@@ -75,6 +75,13 @@ class Batch:
     def upload(self, stream, parsed):
         self._ck(self._L.h264bsdB200BatchUploadTape(self.h, stream, parsed.ptr), "upload")
 
+    def upload_range(self, stream, parsed, first_pic, num_pics):
+        """streamed upload of pictures [first_pic, first_pic + num_pics) on the copy stream (first_pic == 0 first)"""
+        self._ck(self._L.h264bsdB200BatchUploadTapeRange(self.h, stream, parsed.ptr, first_pic, num_pics), "upload_range")
+
+    def upload_fence(self, through_pic):
+        self._ck(self._L.h264bsdB200BatchUploadFence(self.h, through_pic), "upload_fence")
+
     def replicate(self, src=0):
         self._ck(self._L.h264bsdB200BatchReplicateTape(self.h, src), "replicate")
 

@@ -251,6 +251,10 @@ void h264bsdB200BatchDestroy(b200_batch *h) { delete reinterpret_cast<Batch *>(h
 
 #define B(h) reinterpret_cast<Batch *>(h)
 int h264bsdB200BatchUploadTape(b200_batch *h, uint32_t stream, const b200_tape *tape) { return h && B(h)->uploadTape(stream, tape) ? 0 : -1; }
+int h264bsdB200BatchUploadTapeRange(b200_batch *h, uint32_t stream, const b200_tape *tape, uint32_t firstPic, uint32_t numPics) {
+    return h && B(h)->uploadTapeRange(stream, tape, firstPic, numPics) ? 0 : -1;
+}
+int h264bsdB200BatchUploadFence(b200_batch *h, uint32_t throughPic) { return h && B(h)->uploadFence(throughPic) ? 0 : -1; }
 int h264bsdB200BatchReplicateTape(b200_batch *h, uint32_t srcStream) { return h && B(h)->replicateTape(srcStream) ? 0 : -1; }
 int h264bsdB200BatchDecodePicture(b200_batch *h, uint32_t picIndex) { return h && B(h)->decodePicture(picIndex) ? 0 : -1; }
 int h264bsdB200BatchRun(b200_batch *h, uint32_t firstPic, uint32_t numPics) { return h && B(h)->run(firstPic, numPics) ? 0 : -1; }

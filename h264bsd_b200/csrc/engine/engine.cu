@@ -64,6 +64,9 @@ void Batch::destroy() {
     evPool_.clear(); evStage_.clear();
     if (syncEv_) cudaEventDestroy(syncEv_);
     if (forkEv_) cudaEventDestroy(forkEv_);
+    for (auto &f : fences_) cudaEventDestroy(f.second);
+    for (cudaEvent_t e : fenceFree_) cudaEventDestroy(e);
+    if (uploadStream_) cudaStreamDestroy(uploadStream_);
     for (int i = 0; i < 2; i++) {
         if (joinEv_[i]) cudaEventDestroy(joinEv_[i]);
         if (auxStream_[i]) cudaStreamDestroy(auxStream_[i]);
@@ -207,6 +210,59 @@ bool Batch::uploadTape(uint32_t stream, const b200_tape *t) {
     return true;
 }
 
+// Streaming form of uploadTape: the work-list of pictures [firstPic, firstPic + numPics) of one stream, on the upload
+// stream, so that the H2D of later pictures overlaps the decode (and the D2H of the output) of earlier ones.  The call
+// with firstPic == 0 (re)sizes the device arrays and takes the picture headers; uploadFence(p) then makes every picture
+// below p wait for what has been queued so far.
+bool Batch::uploadTapeRange(uint32_t stream, const b200_tape *t, uint32_t firstPic, uint32_t numPics) {
+    if (!created_ || stream >= (uint32_t)g_.nStreams || !t || firstPic + numPics > t->numPics || !numPics) return false;
+    if (t->widthMbs != (uint32_t)g_.widthMbs || t->heightMbs != (uint32_t)g_.heightMbs || t->numSlots > (uint32_t)g_.numSlots) return false;
+    CK(cudaSetDevice(device_));
+    if (!uploadStream_) CK(cudaStreamCreateWithFlags(&uploadStream_, cudaStreamNonBlocking));
+    DevTape &d = tapes_[stream];
+    const size_t orderBytes = (size_t)t->numPics * g_.nMbs * sizeof(uint16_t);
+    if (firstPic == 0) {
+        if (!d.owned || d.capRecs < t->mbRecBytes || d.capCoefs < t->coefBytes || d.capOrder < orderBytes) {
+            CK(cudaStreamSynchronize(stream_));
+            CK(cudaStreamSynchronize(uploadStream_));
+            if (d.owned) { cudaFree(d.recs); cudaFree(d.coefs); cudaFree(d.order); }
+            d = DevTape();
+            d.capRecs = t->mbRecBytes + t->mbRecBytes / 8 + 256;
+            d.capCoefs = t->coefBytes + t->coefBytes / 4 + 256;
+            d.capOrder = orderBytes + 256;
+            CK(cudaMalloc(&d.recs, d.capRecs));
+            CK(cudaMalloc(&d.coefs, d.capCoefs));
+            CK(cudaMalloc(&d.order, d.capOrder));
+            d.owned = true;
+        }
+        d.recBytes = t->mbRecBytes; d.coefBytes = t->coefBytes; d.orderBytes = orderBytes;
+        d.pics.assign(t->pics, t->pics + t->numPics);
+        jobsDirty_ = true;
+    } else if (!d.owned || d.pics.size() != t->numPics) {
+        return false;
+    }
+    const uint32_t last = firstPic + numPics;
+    const uint64_t r0 = t->pics[firstPic].mbRecOffset, r1 = last < t->numPics ? t->pics[last].mbRecOffset : t->mbRecBytes;
+    const uint64_t c0 = t->pics[firstPic].coefOffset, c1 = last < t->numPics ? t->pics[last].coefOffset : t->coefBytes;
+    const size_t o0 = (size_t)firstPic * g_.nMbs * sizeof(uint16_t), o1 = (size_t)last * g_.nMbs * sizeof(uint16_t);
+    if (r1 > r0) CK(cudaMemcpyAsync(d.recs + r0, t->mbRecs + r0, r1 - r0, cudaMemcpyHostToDevice, uploadStream_));
+    if (c1 > c0) CK(cudaMemcpyAsync(d.coefs + c0, t->coefs + c0, c1 - c0, cudaMemcpyHostToDevice, uploadStream_));
+    CK(cudaMemcpyAsync(d.order + o0, reinterpret_cast<const uint8_t *>(t->mbOrder) + o0, o1 - o0, cudaMemcpyHostToDevice, uploadStream_));
+    h2dBytes_ += (r1 - r0) + (c1 - c0) + (o1 - o0);
+    return true;
+}
+
+bool Batch::uploadFence(uint32_t throughPic) {
+    if (!created_ || !uploadStream_) return false;
+    CK(cudaSetDevice(device_));
+    cudaEvent_t e = nullptr;
+    if (!fenceFree_.empty()) { e = fenceFree_.back(); fenceFree_.pop_back(); }
+    else CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CK(cudaEventRecord(e, uploadStream_));
+    fences_.push_back({throughPic, e});
+    return true;
+}
+
 // give every other stream its OWN copy in HBM of stream `src`'s tape (device-to-device)
 bool Batch::replicateTape(uint32_t src) {
     if (!created_ || src >= (uint32_t)g_.nStreams || !tapes_[src].recs) return false;
@@ -260,9 +316,14 @@ bool Batch::buildJobs() {
             picMaxA_[k] = std::max<uint32_t>(picMaxA_[k], j.nA);
             picMaxB_[k] = std::max<uint32_t>(picMaxB_[k], j.nB);
         }
-    cudaFree(dJobs_);
-    dJobs_ = nullptr;
-    CK(cudaMalloc(&dJobs_, sizeof(StreamJob) * jobs.size() + 64));
+    // (cudaFree synchronises the whole device, queued uploads included: keep the table when it is large enough)
+    if (jobsCap_ < jobs.size()) {
+        cudaFree(dJobs_);
+        dJobs_ = nullptr;
+        CK(cudaMalloc(&dJobs_, sizeof(StreamJob) * jobs.size() + 64));
+        jobsCap_ = jobs.size();
+    }
+    CK(cudaStreamSynchronize(stream_));   // nothing in flight may still read the previous table
     CK(cudaMemcpyAsync(dJobs_, jobs.data(), sizeof(StreamJob) * jobs.size(), cudaMemcpyHostToDevice, stream_));
     CK(cudaStreamSynchronize(stream_));
     jobsDirty_ = false;
@@ -398,6 +459,14 @@ bool Batch::decodePicture(uint32_t k) {
     CK(cudaSetDevice(device_));
     if (jobsDirty_ && !buildJobs()) return false;
     if (k >= numPics_) return false;
+    // streamed uploads: this picture needs every fence up to the first one that covers it
+    while (!fences_.empty()) {
+        const bool covers = fences_.front().first > k;
+        CK(cudaStreamWaitEvent(stream_, fences_.front().second, 0));
+        fenceFree_.push_back(fences_.front().second);
+        fences_.pop_front();
+        if (covers) break;
+    }
     return launchPicture(dJobs_ + (size_t)k * g_.nStreams, picMaxQ_[k], picMaxC_[k], picMaxA_[k], picMaxB_[k], true, true);
 }
 
@@ -424,6 +493,10 @@ bool Batch::sync() {
     CK(cudaEventSynchronize(syncEv_));
     if (copyStream_) {
         CK(cudaEventRecord(syncEv_, copyStream_));
+        CK(cudaEventSynchronize(syncEv_));
+    }
+    if (uploadStream_) {
+        CK(cudaEventRecord(syncEv_, uploadStream_));
         CK(cudaEventSynchronize(syncEv_));
     }
     return true;

@@ -1,6 +1,7 @@
 // engine.hpp -- host-visible interface of the B200 reconstruction engine (see engine.cu)
 #pragma once
 #include <cstdint>
+#include <deque>
 #include <vector>
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -24,6 +25,8 @@ public:
 
     bool uploadTape(uint32_t stream, const b200_tape *t);
     bool replicateTape(uint32_t srcStream);
+    bool uploadTapeRange(uint32_t stream, const b200_tape *t, uint32_t firstPic, uint32_t numPics);
+    bool uploadFence(uint32_t throughPic);
     bool decodePicture(uint32_t k);                // picture k of every stream
     bool run(uint32_t first, uint32_t count);
     bool debugStage(uint32_t k, bool recon, bool deblock);
@@ -79,6 +82,10 @@ private:
     uint32_t serial_ = 0;
     int reconBlocks_ = 0, deblockBlocks_ = 0, copyBlocks_ = 0;
     cudaEvent_t syncEv_ = nullptr, forkEv_ = nullptr, joinEv_[2] = {nullptr, nullptr};
+    size_t jobsCap_ = 0;
+    cudaStream_t uploadStream_ = nullptr;
+    std::deque<std::pair<uint32_t, cudaEvent_t>> fences_;   // (pictures below this index, upload-stream event)
+    std::vector<cudaEvent_t> fenceFree_;
     cudaStream_t auxStream_[2] = {nullptr, nullptr};   // copy pass / boundary strengths next to pass A
     std::vector<DevTape> tapes_;
     StreamJob *dJobs_ = nullptr;

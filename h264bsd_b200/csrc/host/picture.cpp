@@ -106,18 +106,18 @@ int PictureState::nC(uint32_t mbAddr, uint32_t blk, const uint8_t *cur) const {
         n = (cur[aIdx] + cur[bIdx] + 1) >> 1;
     } else if (!aMb) {
         n = cur[aIdx];
-        int b = mbB(mbAddr);
-        if (avail(mbAddr, b)) n = (n + aux[b].totalCoeff[bIdx] + 1) >> 1;
+        int b = curNb_[1];
+        if (b >= 0) n = (n + aux[b].totalCoeff[bIdx] + 1) >> 1;
     } else if (!bMb) {
         n = cur[bIdx];
-        int a = mbA(mbAddr);
-        if (avail(mbAddr, a)) n = (n + aux[a].totalCoeff[aIdx] + 1) >> 1;
+        int a = curNb_[0];
+        if (a >= 0) n = (n + aux[a].totalCoeff[aIdx] + 1) >> 1;
     } else {
         n = 0;
         bool haveA = false;
-        int a = mbA(mbAddr), b = mbB(mbAddr);
-        if (avail(mbAddr, a)) { n = aux[a].totalCoeff[aIdx]; haveA = true; }
-        if (avail(mbAddr, b)) n = haveA ? (n + aux[b].totalCoeff[bIdx] + 1) >> 1 : aux[b].totalCoeff[bIdx];
+        int a = curNb_[0], b = curNb_[1];
+        if (a >= 0) { n = aux[a].totalCoeff[aIdx]; haveA = true; }
+        if (b >= 0) n = haveA ? (n + aux[b].totalCoeff[bIdx] + 1) >> 1 : aux[b].totalCoeff[bIdx];
     }
     return n;
 }
@@ -261,11 +261,11 @@ PictureState::NbMv PictureState::interNeighbour(uint32_t cur, int x, int y, int 
         if (z >= curZ) return n;
         nb = (int)cur;
     } else if (y < 0) {
-        nb = x < 0 ? mbD(cur) : x > 3 ? mbC(cur) : mbB(cur);
+        nb = x < 0 ? curNb_[3] : x > 3 ? curNb_[2] : curNb_[1];
     } else {
-        nb = mbA(cur);
+        nb = curNb_[0];
     }
-    if (nb != (int)cur && !avail(cur, nb)) return n;
+    if (nb < 0) return n;   // not in the picture or in another slice
     n.avail = true;
     const b200_mb_rec &r = st[nb];
     if (isInterType(r.mbType)) {
@@ -410,11 +410,11 @@ bool PictureState::deriveInter(MbSyntax &mb, uint32_t mbAddr, const Dpb &dpb) {
 bool PictureState::deriveIntra(MbSyntax &mb, uint32_t mbAddr, bool constrainedIntra) {
     b200_mb_rec &r = st[mbAddr];
     auto availIntra = [&](int nb) {
-        if (!avail(mbAddr, nb)) return false;
+        if (nb < 0) return false;
         if (constrainedIntra && isInterType(st[nb].mbType)) return false;
         return true;
     };
-    int a = mbA(mbAddr), b = mbB(mbAddr), c = mbC(mbAddr), d = mbD(mbAddr);
+    int a = curNb_[0], b = curNb_[1], c = curNb_[2], d = curNb_[3];
     bool avA = availIntra(a), avB = availIntra(b), avC = availIntra(c), avD = availIntra(d);
     r.flags = (uint8_t)((avA ? B200_MBF_AVAIL_A : 0) | (avB ? B200_MBF_AVAIL_B : 0) |
                         (avC ? B200_MBF_AVAIL_C : 0) | (avD ? B200_MBF_AVAIL_D : 0));
@@ -567,6 +567,18 @@ SliceResult PictureState::decodeSlice(BitReader &br, const SliceHeader &sh, cons
         if (!sh.redundantPicCnt && aux[cur].decoded) return SliceResult::Error;
         aux[cur].sliceId = (uint16_t)sliceIdCounter;
         st[cur].sliceId = (uint16_t)sliceIdCounter;
+        {
+            // neighbours A, B, C, D of this macroblock that exist and belong to the same slice (h264bsdInitMbNeighbours +
+            // h264bsdIsNeighbourAvailable, neighbour.c:128-176, :370-382), resolved once per macroblock
+            const uint32_t x = cur % widthMbs;
+            const bool up = cur >= widthMbs;
+            const uint16_t sid = (uint16_t)sliceIdCounter;
+            auto same = [&](int nb) { return aux[nb].sliceId == sid ? nb : -1; };
+            curNb_[0] = x ? same((int)cur - 1) : -1;
+            curNb_[1] = up ? same((int)(cur - widthMbs)) : -1;
+            curNb_[2] = (up && x + 1 < widthMbs) ? same((int)(cur - widthMbs + 1)) : -1;
+            curNb_[3] = (up && x) ? same((int)(cur - widthMbs - 1)) : -1;
+        }
         bool parsed = false;
         if (!sh.isI()) {
             if (!prevSkipped) {
@@ -627,80 +639,88 @@ void PictureState::markSliceCorrupted(uint32_t firstMbInSlice, const Sps &sps) {
 }
 
 void PictureState::finalizeRecords() {
-    for (uint32_t a = 0; a < picSizeInMbs; a++) {
-        b200_mb_rec &r = recs[a];
-        uint32_t idc = r.reserved0;
-        uint8_t f = r.flags & (uint8_t)(B200_MBF_AVAIL_A | B200_MBF_AVAIL_B | B200_MBF_AVAIL_C | B200_MBF_AVAIL_D | B200_MBF_CONCEALED);
-        if (idc != 1) {
-            f |= B200_MBF_FILTER_INNER;
-            int l = mbA(a), t = mbB(a);
-            if (l >= 0 && (idc != 2 || aux[l].sliceId == aux[a].sliceId)) f |= B200_MBF_FILTER_LEFT;
-            if (t >= 0 && (idc != 2 || aux[t].sliceId == aux[a].sliceId)) f |= B200_MBF_FILTER_TOP;
-        }
-        r.flags = f;
-        r.sliceId = aux[a].sliceId;
-    }
-    // processing order + which neighbours an intra macroblock has to wait for
-    auto passB = [&](int nb) { return nb >= 0 && recs[nb].mbType > B200_MB_P_8x8REF0 && recs[nb].mbType != B200_MB_I_PCM; };
+    // One pass over the records (they are 96 bytes each; everything after it works on one byte per macroblock):
+    // deblocking edge flags (GetMbFilteringFlags, deblocking.c:289-320, needs the final slice ids) and the class of the
+    // macroblock for the processing order: 0 other pass-A, 1 plain copy, 4 pass-B (intra-predicted), zr = 1 + reference
+    // slot of a zero-vector plain copy.  Plain copy: P_Skip / P_L0_16x16 without residual whose vector is integer for
+    // luma and chroma.
+    std::vector<uint8_t> &cls = orderClass;
+    cls.resize(2 * (size_t)picSizeInMbs);
+    uint8_t *zr = cls.data() + picSizeInMbs;
     order.resize(picSizeInMbs);
-    // plain copies first: P_Skip / P_L0_16x16 without residual whose vector is integer for luma and chroma; four of them
-    // side by side with a zero vector and one reference slot become one "quad" entry (64-byte luma rows)
-    auto plainCopy = [&](uint32_t a) {
-        const b200_mb_rec &r = recs[a];
-        return r.mbType <= B200_MB_P_16x16 && r.codedMask == 0 && ((r.u.mv[0][0] | r.u.mv[0][1]) & 7) == 0;
-    };
-    std::vector<uint8_t> &cls = orderClass;   // 0 other, 1 single copy, 2 first of a quad, 3 rest of a quad
-    cls.assign(picSizeInMbs, 0);
-    for (uint32_t a = 0; a < picSizeInMbs; a++)
-        if (!passB((int)a) && plainCopy(a)) cls[a] = 1;
-    for (uint32_t row = 0; row < heightMbs; row++) {
-        // runs of zero-vector copies from one reference slot are cut into fours from their start (any x)
-        uint32_t x = 0;
-        while (x + 3 < widthMbs) {
-            const uint32_t a = row * widthMbs + x;
-            uint32_t len = 0;
-            while (len < 4) {
-                const b200_mb_rec &r = recs[a + len];
-                if (cls[a + len] != 1 || r.u.mv[0][0] != 0 || r.u.mv[0][1] != 0 || r.refSlot[0] != recs[a].refSlot[0]) break;
-                len++;
+    uint32_t a = 0, nB = 0;
+    for (uint32_t y = 0; y < heightMbs; y++)
+        for (uint32_t x = 0; x < widthMbs; x++, a++) {
+            b200_mb_rec &r = recs[a];
+            const uint32_t idc = r.reserved0;
+            uint8_t f = r.flags & (uint8_t)(B200_MBF_AVAIL_A | B200_MBF_AVAIL_B | B200_MBF_AVAIL_C | B200_MBF_AVAIL_D | B200_MBF_CONCEALED);
+            if (idc != 1) {
+                f |= B200_MBF_FILTER_INNER;
+                if (x && (idc != 2 || aux[a - 1].sliceId == aux[a].sliceId)) f |= B200_MBF_FILTER_LEFT;
+                if (y && (idc != 2 || aux[a - widthMbs].sliceId == aux[a].sliceId)) f |= B200_MBF_FILTER_TOP;
             }
-            if (len == 4) { cls[a] = 2; cls[a + 1] = cls[a + 2] = cls[a + 3] = 3; x += 4; }
+            r.flags = f;
+            r.sliceId = aux[a].sliceId;
+            r.waitMask = 0;
+            uint8_t c = 0, z = 0;
+            if (r.mbType > B200_MB_P_8x8REF0 && r.mbType != B200_MB_I_PCM) { c = 4; nB++; }
+            else if (r.mbType <= B200_MB_P_16x16 && r.codedMask == 0 && ((r.u.mv[0][0] | r.u.mv[0][1]) & 7) == 0) {
+                c = 1;
+                if ((r.u.mv[0][0] | r.u.mv[0][1]) == 0) z = (uint8_t)(1 + r.refSlot[0]);
+            }
+            cls[a] = c;
+            zr[a] = z;
+        }
+    // runs of zero-vector copies from one reference slot are cut into fours from their start (any x): one "quad" entry
+    // (64-byte luma rows); class 2 = first of a quad, 3 = rest of a quad
+    for (uint32_t row = 0; row < heightMbs; row++) {
+        uint32_t x = 0;
+        const uint8_t *z = zr + (size_t)row * widthMbs;
+        uint8_t *c = cls.data() + (size_t)row * widthMbs;
+        while (x + 3 < widthMbs) {
+            uint32_t len = 0;
+            while (len < 4 && z[x + len] && z[x + len] == z[x]) len++;
+            if (len == 4) { c[x] = 2; c[x + 1] = c[x + 2] = c[x + 3] = 3; x += 4; }
             else x += len ? len : 1;   // a short run stays single copies; the macroblock that ended it may start the next run
         }
     }
     uint32_t n = 0;
-    for (uint32_t a = 0; a < picSizeInMbs; a++)
+    for (a = 0; a < picSizeInMbs; a++)
         if (cls[a] == 2) order[n++] = (uint16_t)a;
     numQuad = n;
-    for (uint32_t a = 0; a < picSizeInMbs; a++)
+    for (a = 0; a < picSizeInMbs; a++)
         if (cls[a] == 1) order[n++] = (uint16_t)a;
     numCopy = n - numQuad;
-    uint32_t nA = 4 * numQuad + numCopy;
-    for (uint32_t a = 0; a < picSizeInMbs; a++)
-        if (!passB((int)a) && cls[a] == 0) { order[n++] = (uint16_t)a; nA++; }
-    numPassA = nA;
+    for (a = 0; a < picSizeInMbs; a++)
+        if (cls[a] == 0) order[n++] = (uint16_t)a;
     const uint32_t listB = n;   // where the pass-B entries start in the list
-    numPassB = picSizeInMbs - nA;
+    numPassB = nB;
+    numPassA = picSizeInMbs - nB;
     if (numPassB) {
         // bucket by wavefront key x + 2y (stable in address order inside a key)
         const uint32_t nKeys = widthMbs + 2 * heightMbs;
-        std::vector<uint32_t> cnt(nKeys + 1, 0);
-        for (uint32_t a = 0; a < picSizeInMbs; a++)
-            if (passB((int)a)) cnt[a % widthMbs + 2 * (a / widthMbs) + 1]++;
+        std::vector<uint32_t> &cnt = orderKeys;
+        cnt.assign(nKeys + 1, 0);
+        a = 0;
+        for (uint32_t y = 0; y < heightMbs; y++)
+            for (uint32_t x = 0; x < widthMbs; x++, a++)
+                if (cls[a] == 4) cnt[x + 2 * y + 1]++;
         for (uint32_t k = 0; k < nKeys; k++) cnt[k + 1] += cnt[k];
-        for (uint32_t a = 0; a < picSizeInMbs; a++)
-            if (passB((int)a)) order[listB + cnt[a % widthMbs + 2 * (a / widthMbs)]++] = (uint16_t)a;
-    }
-    for (uint32_t a = 0; a < picSizeInMbs; a++) {
-        b200_mb_rec &r = recs[a];
-        uint8_t w = 0;
-        if (passB((int)a)) {
-            if ((r.flags & B200_MBF_AVAIL_A) && passB(mbA(a))) w |= B200_MBF_AVAIL_A;
-            if ((r.flags & B200_MBF_AVAIL_B) && passB(mbB(a))) w |= B200_MBF_AVAIL_B;
-            if ((r.flags & B200_MBF_AVAIL_C) && passB(mbC(a))) w |= B200_MBF_AVAIL_C;
-            if ((r.flags & B200_MBF_AVAIL_D) && passB(mbD(a))) w |= B200_MBF_AVAIL_D;
-        }
-        r.waitMask = w;
+        a = 0;
+        for (uint32_t y = 0; y < heightMbs; y++)
+            for (uint32_t x = 0; x < widthMbs; x++, a++) {
+                if (cls[a] != 4) continue;
+                order[listB + cnt[x + 2 * y]++] = (uint16_t)a;
+                // the neighbours an intra macroblock has to wait for inside the intra pass: the available ones that are
+                // intra-predicted themselves
+                b200_mb_rec &r = recs[a];
+                uint8_t w = 0;
+                if ((r.flags & B200_MBF_AVAIL_A) && x && cls[a - 1] == 4) w |= B200_MBF_AVAIL_A;
+                if ((r.flags & B200_MBF_AVAIL_B) && y && cls[a - widthMbs] == 4) w |= B200_MBF_AVAIL_B;
+                if ((r.flags & B200_MBF_AVAIL_C) && y && x + 1 < widthMbs && cls[a - widthMbs + 1] == 4) w |= B200_MBF_AVAIL_C;
+                if ((r.flags & B200_MBF_AVAIL_D) && y && x && cls[a - widthMbs - 1] == 4) w |= B200_MBF_AVAIL_D;
+                r.waitMask = w;
+            }
     }
 }
 

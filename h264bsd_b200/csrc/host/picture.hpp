@@ -37,6 +37,7 @@ public:
     std::vector<uint16_t> order;    // processing order of the picture being built (see b200_tape.mbOrder)
     uint32_t numPassA = 0, numPassB = 0, numCopy = 0, numQuad = 0;
     std::vector<uint8_t> orderClass;   // scratch of finalizeRecords
+    std::vector<uint32_t> orderKeys;
     std::vector<uint32_t> sliceGroupMap;
     uint32_t sliceIdCounter = 0, numDecodedMbs = 0, lastMbAddr = 0;
 
@@ -64,6 +65,7 @@ private:
     int mbC(uint32_t a) const { return (a >= widthMbs && (a % widthMbs) < widthMbs - 1) ? (int)(a - widthMbs + 1) : -1; }
     int mbD(uint32_t a) const { return (a >= widthMbs && (a % widthMbs)) ? (int)(a - widthMbs - 1) : -1; }
     bool avail(uint32_t cur, int nb) const { return nb >= 0 && aux[nb].sliceId == aux[cur].sliceId; }
+    int curNb_[4] = {-1, -1, -1, -1};   // available neighbours A, B, C, D of the macroblock being decoded (decodeSlice)
 
     struct NbMv { bool avail; uint32_t refIdx; int16_t mv[2]; };
     NbMv interNeighbour(uint32_t cur, int x, int y, int curZ) const;

@@ -49,6 +49,11 @@ void h264bsdB200BatchDestroy(b200_batch *batch);
 int h264bsdB200BatchUploadTape(b200_batch *batch, uint32_t stream, const b200_tape *tape);
 /* give every other stream its own HBM copy of stream `srcStream`'s work-list (device -> device) */
 int h264bsdB200BatchReplicateTape(b200_batch *batch, uint32_t srcStream);
+/* streaming upload: the work-list of pictures [firstPic, firstPic+numPics) of one stream on a separate copy stream (call
+ * with firstPic == 0 first: it sizes the device arrays and takes the picture headers); UploadFence(p) makes the decode of
+ * every picture below p wait for everything queued so far, so that the H2D of later pictures overlaps earlier decodes */
+int h264bsdB200BatchUploadTapeRange(b200_batch *batch, uint32_t stream, const b200_tape *tape, uint32_t firstPic, uint32_t numPics);
+int h264bsdB200BatchUploadFence(b200_batch *batch, uint32_t throughPic);
 
 /* reconstruct + in-loop filter + border for picture `picIndex` of EVERY stream (asynchronous).
  * Replaces, per macroblock, h264bsdDecodeMacroblock's pixel half (macroblock_layer.c:965-1131) and,

@@ -193,3 +193,28 @@ def test_example_decoder_matches_oracle(tmp_path):
     assert r.returncode == 0, r.stderr
     assert f"{GOLD[name]['pictures']} pictures decoded" in r.stdout
     assert hashlib.md5(open(out, "rb").read()).hexdigest() == GOLD[name]["post_md5"]
+
+
+def test_streamed_upload_matches_golden(parsed):
+    """work-lists uploaded in groups of pictures on the copy stream while earlier pictures decode (the end-to-end path of
+    the bench): same pictures as the reference, for every stream, twice in a row (device arrays re-used)"""
+    name = "test_640x360.h264"
+    ps = parsed(name)
+    g = GOLD[name]
+    n = 6
+    b = Batch(n, ps.width_mbs, ps.height_mbs, ps.num_slots)
+    for rep in range(2):
+        for g0 in range(0, ps.num_pics, 4):
+            gn = min(4, ps.num_pics - g0)
+            for s in range(n):
+                b.upload_range(s, ps, g0, gn)
+            b.upload_fence(g0 + gn)
+        for k in range(ps.num_pics):
+            b.decode_picture(k)
+            if k % 7 == 0 or k == ps.num_pics - 1:
+                slot = ps.pics[k].curSlot
+                assert md5(b.read_frame(0, slot)) == g["post_frame_md5"][k], f"pass {rep} picture {k}"
+                assert b.compare_streams([slot] * n) == 0
+        b.sync()
+    assert b.idct_errors() == 0 and b.watchdog() == (0, 0)
+    b.close()
