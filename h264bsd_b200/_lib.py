@@ -48,11 +48,11 @@ LEGACY_SYMBOLS = [
 ]
 BATCH_SYMBOLS = [
     "h264bsdB200ParseStream", "h264bsdB200ReparseStream", "h264bsdB200FreeTape", "h264bsdB200DeviceCount", "h264bsdB200BatchCreate",
-    "h264bsdB200BatchDestroy", "h264bsdB200BatchUploadTape", "h264bsdB200BatchReplicateTape", "h264bsdB200BatchUploadTapeRange", "h264bsdB200BatchUploadFence",
+    "h264bsdB200BatchDestroy", "h264bsdB200BatchUploadTape", "h264bsdB200BatchReplicateTape", "h264bsdB200BatchUploadTapeRange", "h264bsdB200BatchUploadFence", "h264bsdB200BatchUploadTapesRange",
     "h264bsdB200BatchDecodePicture", "h264bsdB200BatchRun", "h264bsdB200BatchSync", "h264bsdB200BatchNumPics",
     "h264bsdB200BatchTimerStart", "h264bsdB200BatchTimerStop", "h264bsdB200BatchReadFrame", "h264bsdB200BatchWriteFrame",
     "h264bsdB200BatchConvertFrame", "h264bsdB200BatchConvertBench", "h264bsdB200BatchCompareStreams",
-    "h264bsdB200BatchDebugStage", "h264bsdB200BatchIdctErrors", "h264bsdB200BatchWatchdog", "h264bsdB200BatchReadPictureAll", "h264bsdB200HostAlloc", "h264bsdB200HostFree",
+    "h264bsdB200BatchDebugStage", "h264bsdB200BatchIdctErrors", "h264bsdB200BatchDeblockWorkMbs", "h264bsdB200BatchWatchdog", "h264bsdB200BatchReadPictureAll", "h264bsdB200HostAlloc", "h264bsdB200HostFree",
     "h264bsdB200PinTape", "h264bsdB200UnpinTape", "h264bsdB200BatchKernelTiming", "h264bsdB200BatchKernelTimes", "h264bsdB200BatchLaunches", "h264bsdB200BatchH2DBytes",
     "h264bsdB200BatchD2HBytes",
 ]
@@ -99,6 +99,7 @@ def load():
     L.h264bsdB200BatchReplicateTape.restype = C.c_int; L.h264bsdB200BatchReplicateTape.argtypes = [vp, u32]
     L.h264bsdB200BatchUploadTapeRange.restype = C.c_int; L.h264bsdB200BatchUploadTapeRange.argtypes = [vp, u32, C.POINTER(Tape), u32, u32]
     L.h264bsdB200BatchUploadFence.restype = C.c_int; L.h264bsdB200BatchUploadFence.argtypes = [vp, u32]
+    L.h264bsdB200BatchUploadTapesRange.restype = C.c_int; L.h264bsdB200BatchUploadTapesRange.argtypes = [vp, C.POINTER(C.POINTER(Tape)), u32, u32, u32]
     L.h264bsdB200BatchDecodePicture.restype = C.c_int; L.h264bsdB200BatchDecodePicture.argtypes = [vp, u32]
     L.h264bsdB200BatchRun.restype = C.c_int; L.h264bsdB200BatchRun.argtypes = [vp, u32, u32]
     L.h264bsdB200BatchSync.restype = C.c_int; L.h264bsdB200BatchSync.argtypes = [vp]
@@ -113,6 +114,7 @@ def load():
     L.h264bsdB200BatchCompareStreams.restype = C.c_int; L.h264bsdB200BatchCompareStreams.argtypes = [vp, u32p]
     L.h264bsdB200BatchDebugStage.restype = C.c_int; L.h264bsdB200BatchDebugStage.argtypes = [vp, u32, C.c_int, C.c_int]
     L.h264bsdB200BatchIdctErrors.restype = u32; L.h264bsdB200BatchIdctErrors.argtypes = [vp]
+    L.h264bsdB200BatchDeblockWorkMbs.restype = C.c_uint64; L.h264bsdB200BatchDeblockWorkMbs.argtypes = [vp]
     L.h264bsdB200BatchKernelTiming.restype = None; L.h264bsdB200BatchKernelTiming.argtypes = [vp, C.c_int]
     L.h264bsdB200BatchKernelTimes.restype = C.c_int; L.h264bsdB200BatchKernelTimes.argtypes = [vp, C.POINTER(C.c_float), u32p]
     L.h264bsdB200BatchReadPictureAll.restype = C.c_int; L.h264bsdB200BatchReadPictureAll.argtypes = [vp, u32, vp, C.c_size_t]

@@ -79,6 +79,12 @@ class Batch:
         """streamed upload of pictures [first_pic, first_pic + num_pics) on the copy stream (first_pic == 0 first)"""
         self._ck(self._L.h264bsdB200BatchUploadTapeRange(self.h, stream, parsed.ptr, first_pic, num_pics), "upload_range")
 
+    def upload_ranges(self, parsed_list, first_pic, num_pics):
+        """upload_range for streams 0..len-1 in one call, then the fence for these pictures"""
+        from . import _lib
+        arr = (C.POINTER(_lib.Tape) * len(parsed_list))(*[p.ptr for p in parsed_list])
+        self._ck(self._L.h264bsdB200BatchUploadTapesRange(self.h, arr, len(parsed_list), first_pic, num_pics), "upload_ranges")
+
     def upload_fence(self, through_pic):
         self._ck(self._L.h264bsdB200BatchUploadFence(self.h, through_pic), "upload_fence")
 
@@ -148,6 +154,9 @@ class Batch:
         self._ck(self._L.h264bsdB200BatchKernelTimes(self.h, ms, n), 'kernel_times')
         keys = ('recon', 'deblock', 'border', 'recon_intra', 'strength', 'recon_copy')
         return ({k: ms[i] for i, k in enumerate(keys)}, {k: n[i] for i, k in enumerate(keys)})
+
+    def deblock_work_mbs(self):
+        return int(self._L.h264bsdB200BatchDeblockWorkMbs(self.h))
 
     def watchdog(self):
         return (self._L.h264bsdB200BatchWatchdog(self.h, 0), self._L.h264bsdB200BatchWatchdog(self.h, 1))

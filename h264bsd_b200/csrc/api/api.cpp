@@ -254,6 +254,12 @@ int h264bsdB200BatchUploadTape(b200_batch *h, uint32_t stream, const b200_tape *
 int h264bsdB200BatchUploadTapeRange(b200_batch *h, uint32_t stream, const b200_tape *tape, uint32_t firstPic, uint32_t numPics) {
     return h && B(h)->uploadTapeRange(stream, tape, firstPic, numPics) ? 0 : -1;
 }
+int h264bsdB200BatchUploadTapesRange(b200_batch *h, const b200_tape *const *tapes, uint32_t nStreams, uint32_t firstPic, uint32_t numPics) {
+    if (!h || !tapes) return -1;
+    for (uint32_t s = 0; s < nStreams; s++)
+        if (!B(h)->uploadTapeRange(s, tapes[s], firstPic, numPics)) return -1;
+    return B(h)->uploadFence(firstPic + numPics) ? 0 : -1;
+}
 int h264bsdB200BatchUploadFence(b200_batch *h, uint32_t throughPic) { return h && B(h)->uploadFence(throughPic) ? 0 : -1; }
 int h264bsdB200BatchReplicateTape(b200_batch *h, uint32_t srcStream) { return h && B(h)->replicateTape(srcStream) ? 0 : -1; }
 int h264bsdB200BatchDecodePicture(b200_batch *h, uint32_t picIndex) { return h && B(h)->decodePicture(picIndex) ? 0 : -1; }
@@ -268,6 +274,7 @@ int h264bsdB200BatchConvertFrame(b200_batch *h, uint32_t stream, uint32_t slot, 
 int h264bsdB200BatchConvertBench(b200_batch *h, uint32_t stream, uint32_t slot, int mode, int reps, float *ms) { return h && B(h)->convertBench(stream, slot, mode, reps, ms) ? 0 : -1; }
 int h264bsdB200BatchCompareStreams(b200_batch *h, const uint32_t *slots) { return h ? B(h)->compareStreams(slots) : -1; }
 int h264bsdB200BatchDebugStage(b200_batch *h, uint32_t picIndex, int recon, int deblock) { return h && B(h)->debugStage(picIndex, recon != 0, deblock != 0) ? 0 : -1; }
+uint64_t h264bsdB200BatchDeblockWorkMbs(b200_batch *h) { return h ? B(h)->deblockWorkMbs() : 0; }
 uint32_t h264bsdB200BatchIdctErrors(b200_batch *h) { return h ? B(h)->idctErrors() : 0; }
 void h264bsdB200BatchKernelTiming(b200_batch *h, int enable) { if (h) B(h)->kernelTiming(enable != 0); }
 int h264bsdB200BatchKernelTimes(b200_batch *h, float *ms6, uint32_t *launches6) { return h && ms6 && B(h)->kernelTimes(ms6, launches6) ? 0 : -1; }

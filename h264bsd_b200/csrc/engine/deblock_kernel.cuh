@@ -25,6 +25,7 @@ struct DeblockParams {
     uint32_t totalTickets;
     uint32_t *bsWords;         // nStreams * nMbs * 4 words: packed boundary strengths (stage 1 -> stage 2)
     uint8_t *work;             // nStreams * nMbs: 1 = the macroblock has a non-zero boundary strength
+    unsigned long long *workCount;   // running total of macroblocks with work (statistics for the roofline accounting)
 };
 
 struct __align__(16) DeblockWarpSmem {
@@ -122,6 +123,9 @@ __device__ __forceinline__ int bsInter(const BsSide &q, int qb, const BsSide &p,
     return (rq != rp || abs(dx) >= 4 || abs(dy) >= 4) ? 1 : 0;
 }
 __global__ void __launch_bounds__(kDeblockWarps * 32) strengthKernel(const DeblockParams p) {
+    __shared__ unsigned sWork;
+    if (threadIdx.x == 0) sWork = 0;
+    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const PoolGeom &g = p.g;
     const uint32_t chunksPerStream = ((uint32_t)g.nMbs + kDeblockWarps * kBsChunk - 1) / (kDeblockWarps * kBsChunk);
@@ -163,10 +167,14 @@ __global__ void __launch_bounds__(kDeblockWarps * 32) strengthKernel(const Deblo
             if (e == 0) {
                 const size_t idx = (size_t)s * g.nMbs + mb;
                 *reinterpret_cast<uint4 *>(p.bsWords + idx * 4) = make_uint4(wv, wv1, wh, wh1);
-                p.work[idx] = (wv | wv1 | wh | wh1) ? 1 : 0;
+                const bool any = (wv | wv1 | wh | wh1) != 0;
+                p.work[idx] = any ? 1 : 0;
+                if (any && m0 + 2 * it < (uint32_t)g.nMbs) atomicAdd(&sWork, 1u);   // (not the clamped duplicates)
             }
         }
     }
+    __syncthreads();
+    if (threadIdx.x == 0 && sWork) atomicAdd(p.workCount, (unsigned long long)sWork);
 }
 
 // ---- stage 2: the filter proper, macroblocks with work only ---------------------------------------------------------

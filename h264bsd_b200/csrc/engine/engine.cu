@@ -392,6 +392,7 @@ bool Batch::launchPicture(const StreamJob *dJobs, uint32_t maxQ, uint32_t maxC, 
         dp.pool = pool_; dp.g = g_; dp.jobs = dJobs; dp.order = dOrder_; dp.done = dDoneDeblock_;
         dp.ticket = dCounters_ + 1; dp.serial = serial_; dp.totalTickets = total;
         dp.bsWords = dBsWords_; dp.work = dWork_;
+        dp.workCount = reinterpret_cast<unsigned long long *>(dCounters_ + 4);
     }
     auto launchStrength = [&](cudaStream_t st) {
         const uint32_t chunks = ((uint32_t)g_.nMbs + kDeblockWarps * kBsChunk - 1) / (kDeblockWarps * kBsChunk) * (uint32_t)g_.nStreams;
@@ -739,6 +740,16 @@ uint32_t Batch::watchdog(int which) {
     cudaStreamSynchronize(stream_);
     cudaMemcpyFromSymbol(v, gWatchdog, sizeof v);
     return v[which & 3];
+}
+
+uint64_t Batch::deblockWorkMbs() {
+    unsigned long long v = 0;
+    if (!created_) return 0;
+    cudaSetDevice(device_);
+    cudaMemcpyAsync(&v, dCounters_ + 4, sizeof v, cudaMemcpyDeviceToHost, stream_);
+    cudaStreamSynchronize(stream_);
+    if (auxStream_[1]) cudaStreamSynchronize(auxStream_[1]);
+    return v;
 }
 
 uint32_t Batch::idctErrors() {

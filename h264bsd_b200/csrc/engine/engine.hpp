@@ -27,6 +27,7 @@ public:
     bool replicateTape(uint32_t srcStream);
     bool uploadTapeRange(uint32_t stream, const b200_tape *t, uint32_t firstPic, uint32_t numPics);
     bool uploadFence(uint32_t throughPic);
+    uint64_t deblockWorkMbs();   // macroblocks with a non-zero boundary strength since creation
     bool decodePicture(uint32_t k);                // picture k of every stream
     bool run(uint32_t first, uint32_t count);
     bool debugStage(uint32_t k, bool recon, bool deblock);

@@ -54,6 +54,8 @@ int h264bsdB200BatchReplicateTape(b200_batch *batch, uint32_t srcStream);
  * every picture below p wait for everything queued so far, so that the H2D of later pictures overlaps earlier decodes */
 int h264bsdB200BatchUploadTapeRange(b200_batch *batch, uint32_t stream, const b200_tape *tape, uint32_t firstPic, uint32_t numPics);
 int h264bsdB200BatchUploadFence(b200_batch *batch, uint32_t throughPic);
+/* UploadTapeRange for streams 0..nStreams-1 (tapes[s] -> stream s) followed by UploadFence(firstPic + numPics) */
+int h264bsdB200BatchUploadTapesRange(b200_batch *batch, const b200_tape *const *tapes, uint32_t nStreams, uint32_t firstPic, uint32_t numPics);
 
 /* reconstruct + in-loop filter + border for picture `picIndex` of EVERY stream (asynchronous).
  * Replaces, per macroblock, h264bsdDecodeMacroblock's pixel half (macroblock_layer.c:965-1131) and,
@@ -83,6 +85,8 @@ int h264bsdB200BatchCompareStreams(b200_batch *batch, const uint32_t *slots);
 int h264bsdB200BatchDebugStage(b200_batch *batch, uint32_t picIndex, int recon, int deblock);
 /* blocks whose residual left [-512,511] since creation (h264bsd_transform.c:183-188 error return) */
 uint32_t h264bsdB200BatchIdctErrors(b200_batch *batch);
+/* macroblocks that had at least one non-zero boundary strength (the ones the in-loop filter touches) since creation */
+uint64_t h264bsdB200BatchDeblockWorkMbs(b200_batch *batch);
 /* per-stage device time: CUDA events around every launch on the engine's stream.  ms6/launches6 = {reconstruct pass A
  * (inter), in-loop filter, border, reconstruct pass B (intra), boundary strengths, copy pass}; reading resets the accumulators */
 void h264bsdB200BatchKernelTiming(b200_batch *batch, int enable);
