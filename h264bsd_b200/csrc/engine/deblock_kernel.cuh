@@ -12,7 +12,7 @@ namespace b200 {
 
 constexpr int kDeblockWarps = 8;
 constexpr int kBsChunk = 8;      // stage 1: consecutive macroblocks per warp
-constexpr int kFilterChunk = 4;  // stage 2: consecutive tickets per warp (different streams)
+constexpr int kFilterChunk = 8;  // stage 2: consecutive tickets per warp (different streams)
 
 struct DeblockParams {
     uint8_t *pool;
@@ -178,8 +178,8 @@ __global__ void __launch_bounds__(kDeblockWarps * 32) strengthKernel(const Deblo
 }
 
 // ---- stage 2: the filter proper, macroblocks with work only ---------------------------------------------------------
-// Tickets in wavefront order (x + 2y ascending, streams interleaved); a CTA takes kDeblockWarps * kFilterChunk
-// consecutive tickets, so a warp's consecutive tickets belong to different streams.  A macroblock waits for its left,
+// Tickets in wavefront order (x + 2y ascending, streams interleaved); a warp takes kFilterChunk consecutive tickets
+// (different streams).  A macroblock waits for its left,
 // top and top-right neighbours -- the macroblocks whose filtering the reference's raster order puts before it and whose
 // pels it reads or rewrites -- but only for those that have work themselves (the others never touch a pel).
 //
@@ -193,7 +193,6 @@ __device__ __forceinline__ int bsNibble(uint32_t word, int idx) { return (int)((
 __global__ void __launch_bounds__(kDeblockWarps * 32, 4) deblockKernel(const DeblockParams p) {
     __shared__ DeblockWarpSmem smemAll[kDeblockWarps];
     __shared__ DeblockTables tb;
-    __shared__ uint32_t sBase;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     DeblockWarpSmem &sm = smemAll[warp];
     const PoolGeom &g = p.g;
@@ -212,11 +211,12 @@ __global__ void __launch_bounds__(kDeblockWarps * 32, 4) deblockKernel(const Deb
     const int pitch = chroma ? 16 : 32;
     const int estep = chroma ? 2 : 4;                            // pels between edge e and e + 1 (luma numbering)
 
+    __syncthreads();   // the tables
     for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) sBase = atomicAdd(p.ticket, (uint32_t)(kDeblockWarps * kFilterChunk));
-        __syncthreads();
-        const uint32_t base = sBase;
+        // every warp takes its own tickets (no CTA barrier: a warp that waits for a neighbour does not hold up the others)
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(p.ticket, (uint32_t)kFilterChunk);
+        base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= p.totalTickets) break;
         // lane j < kFilterChunk walks the dependent loads of the warp's ticket j (order -> work flag -> record, strengths,
         // neighbours), all tickets at once: one chain of memory latencies per chunk instead of one per macroblock
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(kDeblockWarps * 32, 4) deblockKernel(const Deb
         uint4 mBw = make_uint4(0, 0, 0, 0);
         unsigned long long mFrame = 0;
         if (lane < kFilterChunk) {
-            const uint32_t t = base + warp * kFilterChunk + lane;
+            const uint32_t t = base + lane;
             if (t < p.totalTickets) {
                 const uint32_t k = t / (uint32_t)g.nStreams, s = t - k * (uint32_t)g.nStreams;
                 const uint32_t mb = p.order[k];

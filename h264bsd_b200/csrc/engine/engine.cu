@@ -161,7 +161,8 @@ bool Batch::create(int device, uint32_t nStreams, uint32_t widthMbs, uint32_t he
         if (r != CUDA_SUCCESS) { std::fprintf(stderr, "h264bsd_b200: chroma tensor map failed (%d)\n", (int)r); return false; }
     }
     int occR = 1, occD = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occR, reconInterKernel, kReconWarps * 32, 0));
+    CK(cudaFuncSetAttribute(reconInterKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(InterWarpSmem) * kReconWarps)));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occR, reconInterKernel, kReconWarps * 32, sizeof(InterWarpSmem) * kReconWarps));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occD, deblockKernel, kDeblockWarps * 32, 0));
     int occS = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, strengthKernel, kDeblockWarps * 32, 0));
@@ -418,7 +419,7 @@ bool Batch::launchPicture(const StreamJob *dJobs, uint32_t maxQ, uint32_t maxC, 
         }
         if (maxA) {
             const uint32_t grid = std::min<uint32_t>(rp.virtualCtasA, (uint32_t)reconBlocks_);
-            reconInterKernel<<<grid, kReconWarps * 32, 0, stream_>>>(rp, lumaMap_, chromaMap_);
+            reconInterKernel<<<grid, kReconWarps * 32, sizeof(InterWarpSmem) * kReconWarps, stream_>>>(rp, lumaMap_, chromaMap_);
             launches_++;
             mark(0);
         }

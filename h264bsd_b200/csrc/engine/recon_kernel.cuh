@@ -30,13 +30,13 @@ struct ReconParams {
 };
 
 struct __align__(128) InterWarpSmem {
-    uint8_t lumaWin[2][kLumaBoxW * kLumaBoxH + 16];           // 2 x 1024, double buffered
-    uint8_t chromaWin[2][2 * kChromaBoxW * kChromaBoxH + 64];  // 2 x 640
+    uint8_t lumaWin[3][kLumaBoxW * kLumaBoxH + 16];           // 3 x 1024: two for the prefetch double buffer, [2] for the
+    uint8_t chromaWin[3][2 * kChromaBoxW * kChromaBoxH + 64];  // 3 x 640   second partition of a two-partition step
     int16_t res[24][16];                                       // 768
     uint8_t pred[384];                                         // 384: multi-partition macroblocks only
     uint32_t meta[kChunkA][8];                                 // per entry: head words 0..3, refSlots, mv[0], mb address
-    uint64_t mbar[2];
-    uint32_t pad[12];
+    uint64_t mbar[3];
+    uint32_t pad[10];
 };
 struct __align__(16) IntraWarpSmem {
     int16_t res[24][16];
@@ -574,17 +574,19 @@ __device__ __forceinline__ void issueWindow(InterWarpSmem &sm, int buf, const Po
 
 __global__ void __launch_bounds__(kReconWarps * 32, 3)
 reconInterKernel(const ReconParams p, const __grid_constant__ CUtensorMap lumaMap, const __grid_constant__ CUtensorMap chromaMap) {
-    __shared__ InterWarpSmem smemAll[kReconWarps];
+    extern __shared__ __align__(128) uint8_t interSmemRaw[];   // kReconWarps x InterWarpSmem (more than the 48 KB static limit)
+    InterWarpSmem *smemAll = reinterpret_cast<InterWarpSmem *>(interSmemRaw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const PoolGeom &g = p.g;
     InterWarpSmem &sm = smemAll[warp];
     if (lane == 0) {
         mbarInit(&sm.mbar[0], 1);
         mbarInit(&sm.mbar[1], 1);
+        mbarInit(&sm.mbar[2], 1);
         fenceMbarInit();
     }
     __syncwarp();
-    uint32_t phase[2] = {0, 0};
+    uint32_t phaseBits = 0;   // bit b = phase parity of window buffer b
     // persistent CTAs striding over virtual CTAs: v -> (stream, chunk of the stream's pass-A list); consecutive
     // virtual CTAs belong to the same stream, so neighbouring macroblocks are in flight together (L2 locality)
     for (uint32_t v = blockIdx.x; v < p.virtualCtasA; v += gridDim.x) {
@@ -648,58 +650,92 @@ reconInterKernel(const ReconParams p, const __grid_constant__ CUtensorMap lumaMa
             *reinterpret_cast<uint32_t *>(dstC) = __ldg(reinterpret_cast<const uint32_t *>(src + 256 + cp * 64 + cr * 8 + cc));
             continue;
         }
-        int resY[8], resC[4];
-        if (h.mask) {
-            mbResidual(h, coef, sm.res, lane, p.errors);
-            laneResidual(sm.res, lane, resY, resC);
-        }
-        uint2 pv;      // this lane's 8 luma prediction samples
-        uint32_t pc;   // and 4 chroma prediction samples
-        if (it.single) {
-            mbarWait(&sm.mbar[buf], phase[buf]);
-            phase[buf] ^= 1;
-            const int xf = it.mvx & 3, yf = it.mvy & 3;
-            const uint8_t *win = sm.lumaWin[buf] + (it.ox & 15);
-            if ((xf | yf) == 0) {
-                pv = lds8(win + (r8 + 2) * kLumaBoxW + c8 + 2);   // h264bsdFillBlock copy (reconstruct.c:1852)
-            } else {
-                pv = lumaQpel8(win, c8, r8, xf, yf);
-            }
-            const int cxf = it.mvx & 7, cyf = it.mvy & 7;
-            const uint8_t *cw = sm.chromaWin[buf] + cp * (kChromaBoxW * kChromaBoxH) + cr * kChromaBoxW + cc + (it.cox & 15);
-            if ((cxf | cyf) == 0) {
-                pc = lds4(cw);
-            } else {
-                // PredictChroma (reconstruct.c:415-475)
-                const uint2 ra = lds8(cw), rb = lds8(cw + kChromaBoxW);
-                const int w00 = (8 - cxf) * (8 - cyf), w01 = cxf * (8 - cyf), w10 = (8 - cxf) * cyf, w11 = cxf * cyf;
-                pc = 0;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int A = (ra.x >> (8 * k)) & 0xFF, B = k < 3 ? (ra.x >> (8 * k + 8)) & 0xFF : ra.y & 0xFF;
-                    const int Cc = (rb.x >> (8 * k)) & 0xFF, D = k < 3 ? (rb.x >> (8 * k + 8)) & 0xFF : rb.y & 0xFF;
-                    pc |= (uint32_t)((w00 * A + w01 * B + w10 * Cc + w11 * D + 32) >> 6) << (8 * k);
+        if (h.mask) mbResidual(h, coef, sm.res, lane, p.errors);   // into shared memory; read back after the prediction
+        uint2 pv = make_uint2(0, 0);   // this lane's 8 luma prediction samples
+        uint32_t pc = 0;               // and 4 chroma prediction samples
+        // Partitions that are at least 8 wide (16x16, 16x8, 8x16, 8x8 sub-macroblocks) share one code path: every lane's
+        // 8-sample luma span and 4-sample chroma span lie inside ONE partition, so the lane only has to pick that
+        // partition's window, vector and origin.  Two partitions are staged at a time (windows `buf` and 2).
+        uint32_t subTypes = 0;
+        if (h.mbType >= B200_MB_P_8x8) subTypes = (__ldg(reinterpret_cast<const uint32_t *>(rec) + 3) >> 24) & 0xFF;
+        const bool wide = h.mbType <= B200_MB_P_8x16 || subTypes == 0;
+        if (wide) {
+            const int rounds = it.single ? 1 : (h.mbType >= B200_MB_P_8x8 ? 2 : 1);
+#pragma unroll 1
+            for (int rd = 0; rd < rounds; rd++) {
+                // per lane: window buffer, window origins, vector, position of the lane's spans inside the partition
+                int bufL = buf, oxL = it.ox, mvxL = it.mvx, mvyL = it.mvy, lx = c8, ly = r8;
+                int bufC = buf, coxC = it.cox, mvxC = it.mvx, mvyC = it.mvy, lcx = cc, lcy = cr;
+                bool actL = true, actC = true;
+                if (it.single) {
+                    mbarWait(&sm.mbar[buf], (phaseBits >> buf) & 1u);
+                    phaseBits ^= 1u << buf;
+                } else {
+                    // partitions A and B of this round (inter_prediction.c:361-482): first block, origin in pels
+                    int blkA, blkB, pxB, pyA, pyB;
+                    if (h.mbType == B200_MB_P_16x8) { blkA = 0; blkB = 8; pxB = 0; pyA = 0; pyB = 8; }
+                    else if (h.mbType == B200_MB_P_8x16) { blkA = 0; blkB = 4; pxB = 8; pyA = 0; pyB = 0; }
+                    else { blkA = 8 * rd; blkB = 8 * rd + 4; pxB = 8; pyA = pyB = 8 * rd; }
+                    const uint32_t *rw = reinterpret_cast<const uint32_t *>(rec);
+                    const uint32_t refSlots = __ldg(rw + 4), mvA = __ldg(rw + 8 + blkA), mvB = __ldg(rw + 8 + blkB);
+                    const int ax = (int)(int16_t)(mvA & 0xFFFF), ay = (int)(int16_t)(mvA >> 16);
+                    const int bx = (int)(int16_t)(mvB & 0xFFFF), by = (int)(int16_t)(mvB >> 16);
+                    int oxA, coxA, oxB, coxB;
+                    issueWindow(sm, buf, g, &lumaMap, &chromaMap, mbx * 16 + (ax >> 2), mby * 16 + pyA + (ay >> 2),
+                                mbx * 8 + (ax >> 3), mby * 8 + (pyA >> 1) + (ay >> 3), frameBase + ((refSlots >> (8 * (blkA >> 2))) & 0xFF), lane, &oxA, &coxA);
+                    issueWindow(sm, 2, g, &lumaMap, &chromaMap, mbx * 16 + pxB + (bx >> 2), mby * 16 + pyB + (by >> 2),
+                                mbx * 8 + (pxB >> 1) + (bx >> 3), mby * 8 + (pyB >> 1) + (by >> 3), frameBase + ((refSlots >> (8 * (blkB >> 2))) & 0xFF), lane, &oxB, &coxB);
+                    const bool inBL = h.mbType == B200_MB_P_16x8 ? r8 >= 8 : c8 == 8;
+                    const bool inBC = h.mbType == B200_MB_P_16x8 ? cr >= 4 : cc == 4;
+                    if (h.mbType >= B200_MB_P_8x8) { actL = (r8 >> 3) == rd; actC = (cr >> 2) == rd; }
+                    bufL = inBL ? 2 : buf; oxL = inBL ? oxB : oxA; mvxL = inBL ? bx : ax; mvyL = inBL ? by : ay;
+                    lx = c8 - (inBL ? pxB : 0); ly = r8 - (inBL ? pyB : pyA);
+                    bufC = inBC ? 2 : buf; coxC = inBC ? coxB : coxA; mvxC = inBC ? bx : ax; mvyC = inBC ? by : ay;
+                    lcx = cc - (inBC ? (pxB >> 1) : 0); lcy = cr - ((inBC ? pyB : pyA) >> 1);
+                    mbarWait(&sm.mbar[buf], (phaseBits >> buf) & 1u);
+                    phaseBits ^= 1u << buf;
+                    mbarWait(&sm.mbar[2], (phaseBits >> 2) & 1u);
+                    phaseBits ^= 4u;
                 }
+                if (actL) {
+                    const int xf = mvxL & 3, yf = mvyL & 3;
+                    const uint8_t *win = sm.lumaWin[bufL] + (oxL & 15);
+                    if ((xf | yf) == 0) pv = lds8(win + (ly + 2) * kLumaBoxW + lx + 2);   // h264bsdFillBlock copy (reconstruct.c:1852)
+                    else pv = lumaQpel8(win, lx, ly, xf, yf);
+                }
+                if (actC) {
+                    const int cxf = mvxC & 7, cyf = mvyC & 7;
+                    const uint8_t *cw = sm.chromaWin[bufC] + cp * (kChromaBoxW * kChromaBoxH) + lcy * kChromaBoxW + lcx + (coxC & 15);
+                    if ((cxf | cyf) == 0) {
+                        pc = lds4(cw);
+                    } else {
+                        // PredictChroma (reconstruct.c:415-475)
+                        const uint2 ra = lds8(cw), rb = lds8(cw + kChromaBoxW);
+                        const int w00 = (8 - cxf) * (8 - cyf), w01 = cxf * (8 - cyf), w10 = (8 - cxf) * cyf, w11 = cxf * cyf;
+                        pc = 0;
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const int A = (ra.x >> (8 * k)) & 0xFF, B = k < 3 ? (ra.x >> (8 * k + 8)) & 0xFF : ra.y & 0xFF;
+                            const int Cc = (rb.x >> (8 * k)) & 0xFF, D = k < 3 ? (rb.x >> (8 * k + 8)) & 0xFF : rb.y & 0xFF;
+                            pc |= (uint32_t)((w00 * A + w01 * B + w10 * Cc + w11 * D + 32) >> 6) << (8 * k);
+                        }
+                    }
+                }
+                if (rd + 1 < rounds) __syncwarp();   // the windows are overwritten by the next round's loads
             }
         } else {
-            // multi-partition macroblocks (inter_prediction.c:361-482): one window per partition, generic path
+            // sub-macroblocks with 8x4 / 4x8 / 4x4 partitions: one window per partition, sample by sample
             const uint32_t refSlots = __ldg(reinterpret_cast<const uint32_t *>(rec) + 4);
-            const uint32_t subTypes = (__ldg(reinterpret_cast<const uint32_t *>(rec) + 3) >> 24) & 0xFF;
             const uint32_t *mvw = reinterpret_cast<const uint32_t *>(rec) + 8;
-            const int nParts = h.mbType <= B200_MB_P_8x16 ? 2 : 16;
 #pragma unroll 1
-            for (int pi = 0; pi < nParts; pi++) {
-                int blk, pw, ph;
-                if (h.mbType == B200_MB_P_16x8) { blk = pi * 8; pw = 16; ph = 8; }
-                else if (h.mbType == B200_MB_P_8x16) { blk = pi * 4; pw = 8; ph = 16; }
-                else {
-                    blk = pi;
-                    const int sub = (subTypes >> (2 * (pi >> 2))) & 3, j = pi & 3;
-                    if (sub == 0) { if (j) continue; pw = 8; ph = 8; }
-                    else if (sub == 1) { if (j & 1) continue; pw = 8; ph = 4; }
-                    else if (sub == 2) { if (j & 2) continue; pw = 4; ph = 8; }
-                    else { pw = 4; ph = 4; }
-                }
+            for (int pi = 0; pi < 16; pi++) {
+                int pw, ph;
+                const int blk = pi;
+                const int sub = (subTypes >> (2 * (pi >> 2))) & 3, j = pi & 3;
+                if (sub == 0) { if (j) continue; pw = 8; ph = 8; }
+                else if (sub == 1) { if (j & 1) continue; pw = 8; ph = 4; }
+                else if (sub == 2) { if (j & 2) continue; pw = 4; ph = 8; }
+                else { pw = 4; ph = 4; }
                 const int px = cBlkX[blk] * 4, py = cBlkY[blk] * 4;
                 const uint32_t mvv = __ldg(mvw + blk);
                 const int mvx = (int)(int16_t)(mvv & 0xFFFF), mvy = (int)(int16_t)(mvv >> 16);
@@ -707,8 +743,8 @@ reconInterKernel(const ReconParams p, const __grid_constant__ CUtensorMap lumaMa
                 int ox, cox;
                 issueWindow(sm, buf, g, &lumaMap, &chromaMap, mbx * 16 + px + (mvx >> 2), mby * 16 + py + (mvy >> 2),
                             ((mbx * 16 + px) >> 1) + (mvx >> 3), ((mby * 16 + py) >> 1) + (mvy >> 3), refFrame, lane, &ox, &cox);
-                mbarWait(&sm.mbar[buf], phase[buf]);
-                phase[buf] ^= 1;
+                mbarWait(&sm.mbar[buf], (phaseBits >> buf) & 1u);
+                phaseBits ^= 1u << buf;
                 const int xf = mvx & 3, yf = mvy & 3;
                 const int lw = 31 - __clz(pw);
 #pragma unroll 1
@@ -734,6 +770,8 @@ reconInterKernel(const ReconParams p, const __grid_constant__ CUtensorMap lumaMa
         }
         // add residual + clip + store (h264bsdWriteOutputBlocks, image.c:172-344)
         if (h.mask) {
+            int resY[8], resC[4];
+            laneResidual(sm.res, lane, resY, resC);
             auto px = [](uint32_t w, int k) { return (int)((w >> (8 * k)) & 0xFF); };
             pv = make_uint2(pack4sat(px(pv.x, 0) + resY[0], px(pv.x, 1) + resY[1], px(pv.x, 2) + resY[2], px(pv.x, 3) + resY[3]),
                             pack4sat(px(pv.y, 0) + resY[4], px(pv.y, 1) + resY[5], px(pv.y, 2) + resY[6], px(pv.y, 3) + resY[7]));
