@@ -383,13 +383,19 @@ def main():
         def gpu_side(st_):
             ta = time.time()
             # H2D (page-locked) of records + coefficients + order lists in groups of pictures on the copy stream: the upload of
-            # group g+1 overlaps the decode and the D2H of group g
-            for g0 in range(0, ps.num_pics, E2E_GROUP):
-                eb.upload_ranges(tapes[st_], g0, min(E2E_GROUP, ps.num_pics - g0))
+            # group g+1 is queued before the kernels of group g, so it overlaps their decode and the D2H of their output
+            groups = [(g0, min(E2E_GROUP, ps.num_pics - g0)) for g0 in range(0, ps.num_pics, E2E_GROUP)]
+            eb.upload_ranges(tapes[st_], *groups[0])
             tb = time.time()
-            for k in range(ps.num_pics):
-                eb.decode_picture(k)                                     # GPU: reconstruct + in-loop filter + border
-                eb.read_picture_all(k, host_out[k & 1], fb)              # D2H: picture k of every stream, packed, page-locked
+            for gi, (g0, gn) in enumerate(groups):
+                if gi + 1 < len(groups):
+                    tu = time.time()
+                    eb.upload_ranges(tapes[st_], *groups[gi + 1])
+                    ta -= time.time() - tu                               # counted as upload, not as pictures
+                    tb += time.time() - tu
+                for k in range(g0, g0 + gn):
+                    eb.decode_picture(k)                                 # GPU: reconstruct + in-loop filter + border
+                    eb.read_picture_all(k, host_out[k & 1], fb)          # D2H: picture k of every stream, packed, page-locked
             eb.sync()
             phase["upload"] += tb - ta
             phase["pictures"] += time.time() - tb

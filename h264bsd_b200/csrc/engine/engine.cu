@@ -308,11 +308,11 @@ bool Batch::buildJobs() {
             j.coefs = reinterpret_cast<const int16_t *>(t.coefs + t.pics[k].coefOffset);
             j.order = reinterpret_cast<const uint16_t *>(t.order) + (size_t)k * g_.nMbs;
             j.curSlot = (uint16_t)t.pics[k].curSlot;
-            j.nQ = (uint16_t)t.pics[k].numQuad;
+            j.nR = (uint16_t)t.pics[k].numRun;
             j.nC = (uint16_t)t.pics[k].numCopy;
-            j.nA = (uint16_t)(t.pics[k].numPassA - 4 * t.pics[k].numQuad - t.pics[k].numCopy);
+            j.nA = (uint16_t)(t.pics[k].numPassA - t.pics[k].numRunMbs - t.pics[k].numCopy);
             j.nB = (uint16_t)t.pics[k].numPassB;
-            picMaxQ_[k] = std::max<uint32_t>(picMaxQ_[k], j.nQ);
+            picMaxQ_[k] = std::max<uint32_t>(picMaxQ_[k], j.nR);
             picMaxC_[k] = std::max<uint32_t>(picMaxC_[k], j.nC);
             picMaxA_[k] = std::max<uint32_t>(picMaxA_[k], j.nA);
             picMaxB_[k] = std::max<uint32_t>(picMaxB_[k], j.nB);
@@ -386,7 +386,7 @@ bool Batch::launchPicture(const StreamJob *dJobs, uint32_t maxQ, uint32_t maxC, 
         rp.chunksA = (maxA + kReconWarps * kChunkA - 1) / (kReconWarps * kChunkA);
         rp.virtualCtasA = rp.chunksA * (uint32_t)g_.nStreams;
         rp.chunksC = (maxC + 31) / 32;
-        rp.chunksQ = (maxQ + 31) / 32;
+        rp.chunksQ = (maxQ + kCopyRunsPerTask - 1) / kCopyRunsPerTask;
     }
     DeblockParams dp;
     if (deblock) {
@@ -543,9 +543,9 @@ bool Batch::submitHostPicture(uint32_t stream, const b200_pic_hdr &hdr, const b2
     job.coefs = reinterpret_cast<const int16_t *>(dStage_[b] + coefOff);
     job.order = reinterpret_cast<const uint16_t *>(dStage_[b] + orderOff);
     job.curSlot = (uint16_t)hdr.curSlot;
-    job.nQ = (uint16_t)hdr.numQuad;
+    job.nR = (uint16_t)hdr.numRun;
     job.nC = (uint16_t)hdr.numCopy;
-    job.nA = (uint16_t)(hdr.numPassA - 4 * hdr.numQuad - hdr.numCopy);
+    job.nA = (uint16_t)(hdr.numPassA - hdr.numRunMbs - hdr.numCopy);
     job.nB = (uint16_t)hdr.numPassB;
     std::memcpy(h, &job, sizeof job);
     std::memcpy(h + recOff, recs, recBytes);
@@ -553,7 +553,7 @@ bool Batch::submitHostPicture(uint32_t stream, const b200_pic_hdr &hdr, const b2
     std::memcpy(h + coefOff, coefs, coefBytes);
     CK(cudaMemcpyAsync(dStage_[b], h, coefOff + coefBytes, cudaMemcpyHostToDevice, stream_));
     h2dBytes_ += coefOff + coefBytes;
-    if (!launchPicture(reinterpret_cast<const StreamJob *>(dStage_[b]), hdr.numQuad, hdr.numCopy, hdr.numPassA - 4 * hdr.numQuad - hdr.numCopy, hdr.numPassB, true, true)) return false;
+    if (!launchPicture(reinterpret_cast<const StreamJob *>(dStage_[b]), hdr.numRun, hdr.numCopy, hdr.numPassA - hdr.numRunMbs - hdr.numCopy, hdr.numPassB, true, true)) return false;
     CK(cudaEventRecord(stageEv_[b], stream_));
     return true;
 }

@@ -30,10 +30,10 @@ struct PoolGeom {
 struct StreamJob {
     const b200_mb_rec *recs;  // nMbs records of this picture
     const int16_t *coefs;     // this picture's coefficient pool
-    const uint16_t *order;    // macroblock addresses: nQ zero-motion quads (first address), nC single plain copies, nA other
-                              // pass-A macroblocks, nB pass-B macroblocks in wavefront order (b200_tape.mbOrder)
+    const uint16_t *order;    // list entries: nR zero-motion runs (two entries each: first address, length), nC single plain
+                              // copies, nA other pass-A macroblocks, nB pass-B macroblocks in wavefront order (b200_tape.mbOrder)
     uint16_t curSlot;
-    uint16_t nQ, nC, nA, nB;
+    uint16_t nR, nC, nA, nB;
     uint16_t pad[3];
 };
 

@@ -26,7 +26,7 @@ struct ReconParams {
     uint32_t chunksA;          // pass A: virtual CTAs per stream (kReconWarps * kChunkA entries each)
     uint32_t virtualCtasA;     // chunksA * nStreams
     uint32_t chunksC;          // copy pass: warp tasks of 32 single copies per stream
-    uint32_t chunksQ;          // copy pass: warp tasks of 32 quads per stream (they come first)
+    uint32_t chunksQ;          // copy pass: warp tasks of kCopyRunsPerTask zero-motion runs per stream (they come first)
 };
 
 struct __align__(128) InterWarpSmem {
@@ -419,11 +419,13 @@ __device__ __forceinline__ uint2 lumaQpel8(const uint8_t *win, int x0, int y, in
 // copy pass: the macroblocks the host classified as plain copies (P_Skip / P_L0_16x16, no residual, vector integer
 // for luma and chroma -- two thirds of a typical P picture).  h264bsdPredictSamples degenerates to h264bsdFillBlock
 // (reconstruct.c:1852, :2244) and h264bsdWriteOutputBlocks to a store: 384 bytes in, 384 bytes out, no shared memory.
-// A warp owns 32 consecutive list entries: lane j fetches entry j's address, reference slot and vector (one
-// dependent-load chain per 32 macroblocks), then the warp copies four macroblocks per step, loads before stores.
+// Horizontal runs of zero-vector copies are moved as whole row segments; the other plain copies one macroblock at a time: a
+// warp owns 32 consecutive list entries, lane j fetches entry j's address, reference slot and vector (one dependent-load
+// chain per 32 macroblocks), then the warp copies four macroblocks per step, loads before stores.
 // =====================================================================================================
 constexpr int kCopyWarps = 8;
 constexpr int kCopyUnroll = 4;
+constexpr int kCopyRunsPerTask = 16;   // zero-motion runs per warp task
 
 __global__ void __launch_bounds__(kCopyWarps * 32) reconCopyKernel(const ReconParams p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -438,49 +440,55 @@ __global__ void __launch_bounds__(kCopyWarps * 32) reconCopyKernel(const ReconPa
         const uint32_t frameBase = s * (uint32_t)g.numSlots;
         uint8_t *cur = framePtr(p.pool, g, frameBase + job.curSlot);
         if (task < p.chunksQ) {
-            // ---- quads: four macroblocks side by side, zero vector, one reference frame: 16 rows of 64 bytes + 2 x 8 rows
-            // of 32 bytes, moved as 16-byte vectors (whole sectors), same offset in the reference and the current frame
-            const uint32_t e0 = task * 32u;
-            if (e0 >= job.nQ) continue;
-            const int n = (int)min(32u, (uint32_t)job.nQ - e0);
-            uint32_t mOff = 0, mOffC = 0;
+            // ---- runs: 2..32 macroblocks side by side, zero vector, one reference frame.  A run is 16 luma rows of 16 * len
+            // bytes and 2 x 8 chroma rows of 8 * len bytes at the same offset in the reference and the current frame; the warp
+            // walks them as 16-byte (8-byte) chunks in row-major order, so every row segment is one contiguous burst
+            const uint32_t e0 = task * (uint32_t)kCopyRunsPerTask;
+            if (e0 >= job.nR) continue;
+            const int n = (int)min((uint32_t)kCopyRunsPerTask, (uint32_t)job.nR - e0);
+            uint32_t mOff = 0, mOffC = 0, mLen = 1;
             long long mDelta = 0;   // reference frame - current frame
             if (lane < n) {
-                const uint32_t mb = __ldg(job.order + e0 + lane);
+                const uint32_t mb = __ldg(job.order + 2u * (e0 + lane));   // (address, length) pairs
+                mLen = __ldg(job.order + 2u * (e0 + lane) + 1u);
                 const uint32_t refSlots = __ldg(reinterpret_cast<const uint32_t *>(job.recs + mb) + 4);
                 const int mby = (int)__umulhi(mb, g.invWidthMbs), mbx = (int)(mb - (uint32_t)mby * g.widthMbs);
                 mOff = (uint32_t)((mby * 16 + kPadY) * g.pitchY + mbx * 16 + kPadY);
                 mOffC = (uint32_t)((mby * 8 + kPadC) * g.pitchC + mbx * 8 + kPadC);
                 mDelta = ((long long)(refSlots & 0xFF) - (long long)job.curSlot) * (long long)g.frameStride;
             }
-            // lane -> two 16-byte luma chunks (row lane >> 2 and 8 below, column lane & 3) and two 8-byte chroma chunks
-            // (plane lane >> 4, row (lane >> 2) & 3 and 4 below, column lane & 3): x is arbitrary, so chroma is only 8-byte aligned
-            const uint32_t lY = (uint32_t)(lane >> 2) * g.pitchY + (lane & 3) * 16, lY2 = lY + 8u * g.pitchY;
-            const size_t lC = (cp ? g.offCr : g.offCb) + (size_t)((lane >> 2) & 3) * g.pitchC + (lane & 3) * 8;
-            const size_t lC2 = lC + 4u * (size_t)g.pitchC;
 #pragma unroll 1
-            for (int i0 = 0; i0 < n; i0 += 2) {
-                uint4 a[2], b[2];
-                uint2 c[2], d[2];
-                uint8_t *dst[2], *dstC[2];
+            for (int i = 0; i < n; i++) {
+                const uint32_t len = __shfl_sync(0xffffffffu, mLen, i);
+                uint8_t *dY = cur + __shfl_sync(0xffffffffu, mOff, i);
+                uint8_t *dC = cur + g.offCb + __shfl_sync(0xffffffffu, mOffC, i);
+                const long long delta = __shfl_sync(0xffffffffu, mDelta, i);
+                const uint32_t inv = 65536u / len + 1u;        // chunk / len == (chunk * inv) >> 16 for chunk < 512, len <= 32
+                const uint32_t chunks = 16u * len;
+#pragma unroll 1
+                for (uint32_t c0 = 0; c0 < chunks; c0 += 64) {
+                    uint4 a[2];
+                    uint2 b[2];
+                    size_t oy[2], oc[2];
+                    bool ok[2];
 #pragma unroll
-                for (int u = 0; u < 2; u++) {
-                    const int i = min(i0 + u, n - 1);
-                    const uint32_t off = __shfl_sync(0xffffffffu, mOff, i), offC = __shfl_sync(0xffffffffu, mOffC, i);
-                    const long long delta = __shfl_sync(0xffffffffu, mDelta, i);
-                    dst[u] = cur + off;
-                    dstC[u] = cur + offC;
-                    a[u] = __ldg(reinterpret_cast<const uint4 *>(dst[u] + delta + lY));
-                    b[u] = __ldg(reinterpret_cast<const uint4 *>(dst[u] + delta + lY2));
-                    c[u] = __ldg(reinterpret_cast<const uint2 *>(dstC[u] + delta + lC));
-                    d[u] = __ldg(reinterpret_cast<const uint2 *>(dstC[u] + delta + lC2));
-                }
+                    for (int u = 0; u < 2; u++) {
+                        const uint32_t c = c0 + 32u * u + lane;
+                        ok[u] = c < chunks;
+                        const uint32_t row = (c * inv) >> 16, col = c - row * len;
+                        oy[u] = (size_t)row * g.pitchY + col * 16;
+                        oc[u] = (row >> 3) * (size_t)(g.offCr - g.offCb) + (size_t)(row & 7) * g.pitchC + col * 8;
+                        if (ok[u]) {
+                            a[u] = __ldg(reinterpret_cast<const uint4 *>(dY + delta + oy[u]));
+                            b[u] = __ldg(reinterpret_cast<const uint2 *>(dC + delta + oc[u]));
+                        }
+                    }
 #pragma unroll
-                for (int u = 0; u < 2; u++) {
-                    *reinterpret_cast<uint4 *>(dst[u] + lY) = a[u];
-                    *reinterpret_cast<uint4 *>(dst[u] + lY2) = b[u];
-                    *reinterpret_cast<uint2 *>(dstC[u] + lC) = c[u];
-                    *reinterpret_cast<uint2 *>(dstC[u] + lC2) = d[u];
+                    for (int u = 0; u < 2; u++)
+                        if (ok[u]) {
+                            *reinterpret_cast<uint4 *>(dY + oy[u]) = a[u];
+                            *reinterpret_cast<uint2 *>(dC + oc[u]) = b[u];
+                        }
                 }
             }
             continue;
@@ -493,7 +501,7 @@ __global__ void __launch_bounds__(kCopyWarps * 32) reconCopyKernel(const ReconPa
         uint32_t mMb = 0;
         unsigned long long mSrcY = 0, mSrcC = 0;
         if (lane < n) {
-            mMb = __ldg(job.order + job.nQ + e0 + lane);
+            mMb = __ldg(job.order + 2u * job.nR + e0 + lane);
             const uint32_t *rw = reinterpret_cast<const uint32_t *>(job.recs + mMb);
             const uint32_t refSlots = __ldg(rw + 4), mvv = __ldg(rw + 8);
             const int mvx = (int)(int16_t)(mvv & 0xFFFF), mvy = (int)(int16_t)(mvv >> 16);
@@ -595,7 +603,7 @@ reconInterKernel(const ReconParams p, const __grid_constant__ CUtensorMap lumaMa
     const uint32_t l0 = (chunk * kReconWarps + warp) * kChunkA;   // index into the stream's pass-A entries that are not plain copies
     if (l0 >= job.nA) continue;
     const int n = min((uint32_t)kChunkA, job.nA - l0);
-    const uint32_t e0 = (uint32_t)job.nQ + job.nC + l0;           // the plain copies went to reconCopyKernel
+    const uint32_t e0 = 2u * job.nR + job.nC + l0;               // the plain copies went to reconCopyKernel
     const uint32_t frameBase = s * (uint32_t)g.numSlots;
     uint8_t *cur = framePtr(p.pool, g, frameBase + job.curSlot);
     const int r8 = lane >> 1, c8 = (lane & 1) * 8;
@@ -818,7 +826,7 @@ __global__ void __launch_bounds__(kReconWarps * 32, 3) reconIntraKernel(const Re
     uint32_t mMb = 0, mMisc = 0;
     uint4 mHead = make_uint4(0, 0, 0, 0);
     if (lane < n) {
-        mMb = __ldg(job.order + ((uint32_t)job.nQ + job.nC + job.nA) + e0 + lane);
+        mMb = __ldg(job.order + (2u * job.nR + job.nC + job.nA) + e0 + lane);
         const uint32_t *rw = reinterpret_cast<const uint32_t *>(job.recs + mMb);
         mHead = __ldg(reinterpret_cast<const uint4 *>(rw));
         mMisc = (__ldg(rw + 5) & 0xFF) | ((__ldg(rw + 7) & 0xFF) << 8);

@@ -671,26 +671,32 @@ void PictureState::finalizeRecords() {
             cls[a] = c;
             zr[a] = z;
         }
-    // runs of zero-vector copies from one reference slot are cut into fours from their start (any x): one "quad" entry
-    // (64-byte luma rows); class 2 = first of a quad, 3 = rest of a quad
+    // horizontal runs of zero-vector copies from one reference slot (2..32 macroblocks) become one list entry pair: the
+    // copy kernel moves them as whole row segments; class 2 = first of a run, 3 = rest of a run
+    uint32_t n = 0;
+    numRunMbs = 0;
     for (uint32_t row = 0; row < heightMbs; row++) {
-        uint32_t x = 0;
         const uint8_t *z = zr + (size_t)row * widthMbs;
         uint8_t *c = cls.data() + (size_t)row * widthMbs;
-        while (x + 3 < widthMbs) {
-            uint32_t len = 0;
-            while (len < 4 && z[x + len] && z[x + len] == z[x]) len++;
-            if (len == 4) { c[x] = 2; c[x + 1] = c[x + 2] = c[x + 3] = 3; x += 4; }
-            else x += len ? len : 1;   // a short run stays single copies; the macroblock that ended it may start the next run
+        uint32_t x = 0;
+        while (x < widthMbs) {
+            if (!z[x]) { x++; continue; }
+            uint32_t len = 1;
+            while (x + len < widthMbs && len < 32 && z[x + len] == z[x]) len++;
+            if (len >= 2) {
+                c[x] = 2;
+                for (uint32_t i = 1; i < len; i++) c[x + i] = 3;
+                order[n++] = (uint16_t)(row * widthMbs + x);
+                order[n++] = (uint16_t)len;
+                numRunMbs += len;
+            }
+            x += len;
         }
     }
-    uint32_t n = 0;
-    for (a = 0; a < picSizeInMbs; a++)
-        if (cls[a] == 2) order[n++] = (uint16_t)a;
-    numQuad = n;
+    numRun = n / 2;
     for (a = 0; a < picSizeInMbs; a++)
         if (cls[a] == 1) order[n++] = (uint16_t)a;
-    numCopy = n - numQuad;
+    numCopy = n - 2 * numRun;
     for (a = 0; a < picSizeInMbs; a++)
         if (cls[a] == 0) order[n++] = (uint16_t)a;
     const uint32_t listB = n;   // where the pass-B entries start in the list

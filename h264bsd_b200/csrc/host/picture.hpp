@@ -35,7 +35,7 @@ public:
     std::vector<b200_mb_rec> recs;  // records of the picture being built (first decode of each MB)
     std::vector<int16_t> coefs;     // coefficient pool of the picture being built, 16 int16 per block
     std::vector<uint16_t> order;    // processing order of the picture being built (see b200_tape.mbOrder)
-    uint32_t numPassA = 0, numPassB = 0, numCopy = 0, numQuad = 0;
+    uint32_t numPassA = 0, numPassB = 0, numCopy = 0, numRun = 0, numRunMbs = 0;
     std::vector<uint8_t> orderClass;   // scratch of finalizeRecords
     std::vector<uint32_t> orderKeys;
     std::vector<uint32_t> sliceGroupMap;

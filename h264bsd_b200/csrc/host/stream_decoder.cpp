@@ -233,7 +233,8 @@ void StreamDecoder::finishPicture() {
     hdr.numPassA = pic_.numPassA;
     hdr.numPassB = pic_.numPassB;
     hdr.numCopy = pic_.numCopy;
-    hdr.numQuad = pic_.numQuad;
+    hdr.numRun = pic_.numRun;
+    hdr.numRunMbs = pic_.numRunMbs;
 
     int32_t poc = decodePicOrderCnt(poc_, *activeSps_, sliceHeader_, prevNal_);
     if (validSliceInAccessUnit_) {

@@ -122,9 +122,9 @@ typedef struct b200_pic_hdr {
     uint32_t numPassB;     /* intra-predicted macroblocks (read unfiltered neighbours of the current picture) */
     uint32_t numCopy;      /* plain copies listed one by one: one 16x16 partition, no residual, motion vector a multiple of
                               8 quarter-pels in both components (integer for luma AND chroma) */
-    uint32_t numQuad;      /* groups of four horizontally adjacent plain copies (any x) with a zero vector and the same
-                              reference slot: one list entry (the address of the first) per group */
-    uint32_t reserved;
+    uint32_t numRun;       /* horizontal runs of 2..32 plain copies with a zero vector and the same reference slot: two list
+                              entries (address of the first macroblock, length) per run */
+    uint32_t numRunMbs;    /* macroblocks covered by the runs */
 } b200_pic_hdr;
 
 /* A fully parsed stream in host memory (built by h264bsdB200ParseStream). */
@@ -142,10 +142,10 @@ typedef struct b200_tape {
     uint8_t *mbRecs;     /* mbRecBytes */
     uint8_t *coefs;      /* coefBytes  */
     /* processing order, widthMbs*heightMbs uint16 macroblock addresses per picture (picture p at p*nMbs):
-     * numQuad zero-motion groups (first address of each), numCopy single plain copies, the other
-     * numPassA - 4*numQuad - numCopy inter / I_PCM macroblocks (all three in raster order), then numPassB entries in
+     * numRun zero-motion runs (two entries each: first address, length), numCopy single plain copies, the other
+     * numPassA - numRunMbs - numCopy inter / I_PCM macroblocks (all three in raster order), then numPassB entries in
      * wavefront order (x + 2y ascending), so that every macroblock an intra MB depends on precedes it.  The list of a
-     * picture has numQuad + numCopy + (numPassA - 4*numQuad - numCopy) + numPassB <= widthMbs*heightMbs entries. */
+     * picture never has more than widthMbs*heightMbs entries. */
     uint16_t *mbOrder;
     uint32_t numOutputs;        /* pictures in output order, incl. those drained by the final flush */
     uint32_t reserved2;
