@@ -102,9 +102,11 @@ struct RecView {
 // (word j = segments 8j..8j+7; segments 0..15 = vertical edge left of raster block, 16..31 = horizontal edge above it)
 // plus one "has work" byte.  Two thirds of the macroblocks of a typical P picture have nothing to filter.
 //
-// Half a warp per macroblock: lane e owns raster block e and computes the strength of the edge on its left and of the
-// edge above it.  Every load of an iteration is independent of every other (one memory latency per pair of
-// macroblocks), and the loop is unrolled so that two pairs are in flight per warp.
+// Two paths.  A thread per macroblock decides the common case -- the macroblock and the neighbours it is filtered against
+// are all "uniform" (P_Skip / P_L0_16x16 without coded luma blocks: one vector, one reference, no coefficients) -- from four
+// words per record: every inner strength is 0 and each outer edge has ONE strength, 0 or 1.  The rest (intra, several
+// partitions, coded blocks; a third of a P picture) goes through the general routine: half a warp per macroblock, lane e
+// owns raster block e and computes the strength of the edge on its left and of the edge above it.
 struct BsSide {
     uint32_t w0, coded, refs, mv;
 };
@@ -114,65 +116,109 @@ __device__ __forceinline__ BsSide loadSide(const b200_mb_rec *rec, int blk) {
     r.w0 = __ldg(w); r.coded = __ldg(w + 1); r.refs = __ldg(w + 4); r.mv = __ldg(w + 8 + blk);
     return r;
 }
+__device__ __forceinline__ bool mvFar(uint32_t a, uint32_t b) {
+    const int dx = (int)(int16_t)(a & 0xFFFF) - (int)(int16_t)(b & 0xFFFF);
+    const int dy = (int)(int16_t)(a >> 16) - (int)(int16_t)(b >> 16);
+    return abs(dx) >= 4 || abs(dy) >= 4;
+}
 // EdgeBoundaryStrength (:395-411) / InnerBoundaryStrength (:332-355) for two non-intra 4x4 blocks
 __device__ __forceinline__ int bsInter(const BsSide &q, int qb, const BsSide &p, int pb) {
     if (((q.coded >> qb) | (p.coded >> pb)) & 1u) return 2;
-    const int dx = (int)(int16_t)(q.mv & 0xFFFF) - (int)(int16_t)(p.mv & 0xFFFF);
-    const int dy = (int)(int16_t)(q.mv >> 16) - (int)(int16_t)(p.mv >> 16);
     const uint32_t rq = (q.refs >> (8 * (qb >> 2))) & 0xFF, rp = (p.refs >> (8 * (pb >> 2))) & 0xFF;
-    return (rq != rp || abs(dx) >= 4 || abs(dy) >= 4) ? 1 : 0;
+    return (rq != rp || mvFar(q.mv, p.mv)) ? 1 : 0;
 }
+// the general routine for one macroblock per half-warp (all 32 lanes take part; `write` = this half-warp's result counts)
+__device__ __forceinline__ bool strengthGeneral(const DeblockParams &p, const PoolGeom &g, const b200_mb_rec *recs, uint32_t mb,
+                                                size_t idx, bool write, int lane) {
+    const int e = lane & 15, bx = e & 3, by = e >> 2;
+    const int qb = cRasterToBlk[e];
+    const int lb = cRasterToBlk[by * 4 + ((bx + 3) & 3)];   // block on the left (of the left neighbour when bx == 0)
+    const int tb = cRasterToBlk[((by + 3) & 3) * 4 + bx];   // block above (of the upper neighbour when by == 0)
+    const b200_mb_rec *rc = recs + mb;
+    const BsSide cur = loadSide(rc, qb);
+    const int flags = cur.w0 >> 24;
+    const bool fLeft = flags & B200_MBF_FILTER_LEFT, fTop = flags & B200_MBF_FILTER_TOP;
+    // GetMbFilteringFlags :289-320 was resolved on the host.  The neighbour records are fetched whether or not the edge is
+    // filtered (their addresses must not depend on the flags just loaded); a record that does not exist (first macroblock /
+    // first row) is replaced by the current one and ignored
+    const BsSide lef = loadSide((bx == 0 && mb > 0) ? rc - 1 : rc, lb);
+    const BsSide top = loadSide((by == 0 && mb >= (uint32_t)g.widthMbs) ? rc - g.widthMbs : rc, tb);
+    const bool curIntra = (cur.w0 & 0xFF) > B200_MB_P_8x8REF0;
+    int bv, bh;
+    if (bx == 0) bv = !fLeft ? 0 : (curIntra || (lef.w0 & 0xFF) > B200_MB_P_8x8REF0) ? 4 : bsInter(cur, qb, lef, lb);
+    else bv = curIntra ? 3 : bsInter(cur, qb, lef, lb);
+    if (by == 0) bh = !fTop ? 0 : (curIntra || (top.w0 & 0xFF) > B200_MB_P_8x8REF0) ? 4 : bsInter(cur, qb, top, tb);
+    else bh = curIntra ? 3 : bsInter(cur, qb, top, tb);
+    if (!(flags & B200_MBF_FILTER_INNER)) bv = bh = 0;
+    uint32_t wv = (uint32_t)bv << (4 * (lane & 7)), wh = (uint32_t)bh << (4 * (lane & 7));
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) {
+        wv |= __shfl_xor_sync(0xffffffffu, wv, d);
+        wh |= __shfl_xor_sync(0xffffffffu, wh, d);
+    }
+    const uint32_t wv1 = __shfl_down_sync(0xffffffffu, wv, 8), wh1 = __shfl_down_sync(0xffffffffu, wh, 8);
+    const bool any = (wv | wv1 | wh | wh1) != 0;
+    if (e == 0 && write) {
+        *reinterpret_cast<uint4 *>(p.bsWords + idx * 4) = make_uint4(wv, wv1, wh, wh1);
+        p.work[idx] = any ? 1 : 0;
+    }
+    return any && e == 0 && write;
+}
+
 __global__ void __launch_bounds__(kDeblockWarps * 32) strengthKernel(const DeblockParams p) {
     __shared__ unsigned sWork;
     if (threadIdx.x == 0) sWork = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const PoolGeom &g = p.g;
-    const uint32_t chunksPerStream = ((uint32_t)g.nMbs + kDeblockWarps * kBsChunk - 1) / (kDeblockWarps * kBsChunk);
+    const uint32_t chunksPerStream = ((uint32_t)g.nMbs + kDeblockWarps * 32 - 1) / (kDeblockWarps * 32);
     const uint32_t total = chunksPerStream * (uint32_t)g.nStreams;
-    const int e = lane & 15, bx = e & 3, by = e >> 2;
-    const int qb = cRasterToBlk[e];
-    const int lb = cRasterToBlk[by * 4 + ((bx + 3) & 3)];   // block on the left (of the left neighbour when bx == 0)
-    const int tb = cRasterToBlk[((by + 3) & 3) * 4 + bx];   // block above (of the upper neighbour when by == 0)
+    unsigned nWork = 0;
     for (uint32_t v = blockIdx.x; v < total; v += gridDim.x) {
         const uint32_t s = v / chunksPerStream, chunk = v - s * chunksPerStream;
         const StreamJob job = p.jobs[s];
-        const uint32_t m0 = (chunk * kDeblockWarps + warp) * kBsChunk + (lane >> 4);
-#pragma unroll 2
-        for (uint32_t it = 0; it < kBsChunk / 2; it++) {
-            const uint32_t mb = min(m0 + 2 * it, (uint32_t)g.nMbs - 1);   // clamped duplicates rewrite the same values
-            const b200_mb_rec *rc = job.recs + mb;
-            const BsSide cur = loadSide(rc, qb);
-            const int flags = cur.w0 >> 24;
-            const bool fLeft = flags & B200_MBF_FILTER_LEFT, fTop = flags & B200_MBF_FILTER_TOP;
-            // GetMbFilteringFlags :289-320 was resolved on the host.  The neighbour records are fetched whether or not the edge
-            // is filtered (their addresses must not depend on the flags just loaded: one memory round trip per iteration, not
-            // two); a record that does not exist (first macroblock / first row) is replaced by the current one and ignored
-            const BsSide lef = loadSide((bx == 0 && mb > 0) ? rc - 1 : rc, lb);
-            const BsSide top = loadSide((by == 0 && mb >= (uint32_t)g.widthMbs) ? rc - g.widthMbs : rc, tb);
-            const bool curIntra = (cur.w0 & 0xFF) > B200_MB_P_8x8REF0;
-            int bv, bh;
-            if (bx == 0) bv = !fLeft ? 0 : (curIntra || (lef.w0 & 0xFF) > B200_MB_P_8x8REF0) ? 4 : bsInter(cur, qb, lef, lb);
-            else bv = curIntra ? 3 : bsInter(cur, qb, lef, lb);
-            if (by == 0) bh = !fTop ? 0 : (curIntra || (top.w0 & 0xFF) > B200_MB_P_8x8REF0) ? 4 : bsInter(cur, qb, top, tb);
-            else bh = curIntra ? 3 : bsInter(cur, qb, top, tb);
-            if (!(flags & B200_MBF_FILTER_INNER)) bv = bh = 0;
-            uint32_t wv = (uint32_t)bv << (4 * (lane & 7)), wh = (uint32_t)bh << (4 * (lane & 7));
-#pragma unroll
-            for (int d = 1; d < 8; d <<= 1) {
-                wv |= __shfl_xor_sync(0xffffffffu, wv, d);
-                wh |= __shfl_xor_sync(0xffffffffu, wh, d);
+        const uint32_t m0 = (chunk * kDeblockWarps + warp) * 32u;
+        if (m0 >= (uint32_t)g.nMbs) continue;
+        const uint32_t mb = m0 + lane;
+        const bool valid = mb < (uint32_t)g.nMbs;
+        const size_t sBase = (size_t)s * g.nMbs;
+        // thread per macroblock: head, coded mask, reference slots and first vector of this record and of the one above
+        const uint32_t mbc = valid ? mb : (uint32_t)g.nMbs - 1;
+        const uint32_t *cw = reinterpret_cast<const uint32_t *>(job.recs + mbc);
+        const uint32_t *tw = mbc >= (uint32_t)g.widthMbs ? cw - 24 * g.widthMbs : cw;
+        const uint32_t c0 = __ldg(cw), c1 = __ldg(cw + 1), c4 = __ldg(cw + 4), c8 = __ldg(cw + 8);
+        const uint32_t t0 = __ldg(tw), t1 = __ldg(tw + 1), t4 = __ldg(tw + 4), t8 = __ldg(tw + 8);
+        // the record on the left is the neighbouring lane's (lane 0: one more load)
+        uint32_t l0 = __shfl_up_sync(0xffffffffu, c0, 1), l1 = __shfl_up_sync(0xffffffffu, c1, 1);
+        uint32_t l4 = __shfl_up_sync(0xffffffffu, c4, 1), l8 = __shfl_up_sync(0xffffffffu, c8, 1);
+        if (lane == 0 && mb > 0) { l0 = __ldg(cw - 24); l1 = __ldg(cw - 23); l4 = __ldg(cw - 20); l8 = __ldg(cw - 16); }
+        auto uniform = [](uint32_t w0, uint32_t w1) { return (w0 & 0xFF) <= B200_MB_P_16x16 && (w1 & 0xFFFFu) == 0; };
+        const int flags = c0 >> 24;
+        const bool fLeft = flags & B200_MBF_FILTER_LEFT, fTop = flags & B200_MBF_FILTER_TOP;
+        const bool fast = uniform(c0, c1) && (!fLeft || uniform(l0, l1)) && (!fTop || uniform(t0, t1));
+        if (valid && fast) {
+            uint32_t bl = 0, bt = 0;
+            if (flags & B200_MBF_FILTER_INNER) {
+                if (fLeft) bl = ((c4 ^ l4) & 0xFF) != 0 || mvFar(c8, l8);
+                if (fTop) bt = ((c4 ^ t4) & 0xFF) != 0 || mvFar(c8, t8);
             }
-            const uint32_t wv1 = __shfl_down_sync(0xffffffffu, wv, 8), wh1 = __shfl_down_sync(0xffffffffu, wh, 8);
-            if (e == 0) {
-                const size_t idx = (size_t)s * g.nMbs + mb;
-                *reinterpret_cast<uint4 *>(p.bsWords + idx * 4) = make_uint4(wv, wv1, wh, wh1);
-                const bool any = (wv | wv1 | wh | wh1) != 0;
-                p.work[idx] = any ? 1 : 0;
-                if (any && m0 + 2 * it < (uint32_t)g.nMbs) atomicAdd(&sWork, 1u);   // (not the clamped duplicates)
-            }
+            // left edge = segments 0, 4, 8, 12 (nibbles 0 and 4 of words 0 and 1); top edge = segments 16..19 (word 2)
+            *reinterpret_cast<uint4 *>(p.bsWords + (sBase + mb) * 4) = make_uint4(bl * 0x00010001u, bl * 0x00010001u, bt * 0x1111u, 0u);
+            p.work[sBase + mb] = (bl | bt) ? 1 : 0;
+            nWork += (bl | bt);
+        }
+        // everything else, two macroblocks at a time
+        uint32_t slow = __ballot_sync(0xffffffffu, valid && !fast);
+        while (slow) {
+            const int a = __ffs(slow) - 1;
+            slow &= slow - 1;
+            const int b = slow ? __ffs(slow) - 1 : -1;
+            if (b >= 0) slow &= slow - 1;
+            const uint32_t mbSel = m0 + (uint32_t)((lane < 16 || b < 0) ? a : b);
+            nWork += strengthGeneral(p, g, job.recs, mbSel, sBase + mbSel, lane < 16 || b >= 0, lane) ? 1u : 0u;
         }
     }
+    if (nWork) atomicAdd(&sWork, nWork);
     __syncthreads();
     if (threadIdx.x == 0 && sWork) atomicAdd(p.workCount, (unsigned long long)sWork);
 }

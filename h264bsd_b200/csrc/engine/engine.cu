@@ -396,7 +396,7 @@ bool Batch::launchPicture(const StreamJob *dJobs, uint32_t maxQ, uint32_t maxC, 
         dp.workCount = reinterpret_cast<unsigned long long *>(dCounters_ + 4);
     }
     auto launchStrength = [&](cudaStream_t st) {
-        const uint32_t chunks = ((uint32_t)g_.nMbs + kDeblockWarps * kBsChunk - 1) / (kDeblockWarps * kBsChunk) * (uint32_t)g_.nStreams;
+        const uint32_t chunks = ((uint32_t)g_.nMbs + kDeblockWarps * 32 - 1) / (kDeblockWarps * 32) * (uint32_t)g_.nStreams;
         strengthKernel<<<std::min<uint32_t>(chunks, (uint32_t)strengthBlocks_), kDeblockWarps * 32, 0, st>>>(dp);
         launches_++;
     };
