@@ -7,11 +7,13 @@ from . import _lib
 class ParsedStream:
     """A stream parsed on the host into a tape (h264bsdB200ParseStream)."""
 
-    def __init__(self, data, no_output_reordering=False):
+    def __init__(self, data=None, no_output_reordering=False):
         self._L = _lib.load()
         self.ptr = None
         self.pinned = False
-        self.reparse(data, no_output_reordering)
+        self.status = None
+        if data is not None:      # (None: an empty shell to be filled by reparse_many)
+            self.reparse(data, no_output_reordering)
 
     def reparse(self, data, no_output_reordering=False):
         """parse another stream into the same tape (arrays and page-lock are kept)"""
@@ -27,6 +29,31 @@ class ParsedStream:
         self.outputs = [t.outputPicIndex[i] for i in range(t.numOutputs)]
         self.pics = [t.pics[i] for i in range(t.numPics)]
         self.video_range = t.videoRange
+
+    def _refresh(self):
+        t = self.ptr.contents
+        self.pinned = t.pinned == 1
+        self.num_pics, self.width_mbs, self.height_mbs, self.num_slots = t.numPics, t.widthMbs, t.heightMbs, t.numSlots
+        self.status = t.status
+        self.rec_bytes, self.coef_bytes = t.mbRecBytes, t.coefBytes
+        self.video_range = t.videoRange
+
+    @staticmethod
+    def reparse_many(parsed, data, threads, no_output_reordering=False):
+        """re-parse `data` (one ctypes byte array shared by all, or a list of them) into every ParsedStream of `parsed` on
+        `threads` native host threads (one C call, no interpreter lock); light refresh of the Python-side fields"""
+        L = _lib.load()
+        n = len(parsed)
+        bufs = data if isinstance(data, (list, tuple)) else [data] * n
+        tapes = (C.POINTER(_lib.Tape) * n)(*[p.ptr for p in parsed])
+        ptrs = (C.c_void_p * n)(*[C.addressof(b) for b in bufs])
+        lens = (C.c_size_t * n)(*[len(b) for b in bufs])
+        bad = L.h264bsdB200ReparseStreams(tapes, n, ptrs, lens, 1 if no_output_reordering else 0, threads)
+        if bad:
+            raise MemoryError("h264bsdB200ReparseStreams failed for %d streams" % bad)
+        for i, p in enumerate(parsed):
+            p.ptr = tapes[i]
+            p._refresh()
 
     @property
     def mbs_per_pic(self):

@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(kDeblockWarps * 32) strengthKernel(const Deblo
 // and 2.  A step is skipped when no lane of the warp has a strength for it.
 __device__ __forceinline__ int bsNibble(uint32_t word, int idx) { return (int)((word >> (4 * idx)) & 15u); }
 
-__global__ void __launch_bounds__(kDeblockWarps * 32, 4) deblockKernel(const DeblockParams p) {
+__global__ void __launch_bounds__(kDeblockWarps * 32, 5) deblockKernel(const DeblockParams p) {
     __shared__ DeblockWarpSmem smemAll[kDeblockWarps];
     __shared__ DeblockTables tb;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -345,8 +345,8 @@ __global__ void __launch_bounds__(kDeblockWarps * 32, 4) deblockKernel(const Deb
             const uint32_t vWord = (grp >> 1) ? bw.y : bw.x;
 #pragma unroll 1
             for (int e = 0; e < 4; e++) {
+                if ((((bw.x | bw.y) >> (4 * e)) & 0x000F000Fu) == 0) continue;   // no strength on this edge in any row (warp-uniform)
                 const int bs = (chroma && (e & 1)) ? 0 : bsNibble(vWord, (grp & 1) * 4 + e);
-                if (!__any_sync(0xffffffffu, bs != 0)) continue;
                 if (bs) {
                     uint32_t *wp = reinterpret_cast<uint32_t *>(rowp + e * estep);
                     const uint32_t P = wp[-1], Q = wp[0];
@@ -364,8 +364,9 @@ __global__ void __launch_bounds__(kDeblockWarps * 32, 4) deblockKernel(const Deb
             // horizontal edges: segment 16 + e * 4 + grp is nibble (e & 1) * 4 + grp of word 2 + (e >> 1)
 #pragma unroll 1
             for (int e = 0; e < 4; e++) {
-                const int bs = (chroma && (e & 1)) ? 0 : bsNibble((e >> 1) ? bw.w : bw.z, (e & 1) * 4 + grp);
-                if (!__any_sync(0xffffffffu, bs != 0)) continue;
+                const uint32_t hWord = (e >> 1) ? bw.w : bw.z;
+                if (((hWord >> ((e & 1) * 16)) & 0xFFFFu) == 0) continue;         // no strength on this edge in any column
+                const int bs = (chroma && (e & 1)) ? 0 : bsNibble(hWord, (e & 1) * 4 + grp);
                 if (bs) {
                     uint8_t *q = colp + e * estep * pitch;
                     EdgeLine v;

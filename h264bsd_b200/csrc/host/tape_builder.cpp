@@ -8,6 +8,9 @@
 // so steady-state parsing touches no fresh pages and a page-locked tape stays page-locked.
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <thread>
+#include <vector>
 #include <vector>
 #include "stream_decoder.hpp"
 #include "h264bsd_b200.h"
@@ -144,4 +147,26 @@ extern "C" void h264bsdB200FreeTape(b200_tape *t) {
     std::free(t->mbOrder);
     std::free(t->outputPicIndex);
     std::free(t);
+}
+
+// Parse `n` streams into `n` (re-used) tapes on `threads` host threads: the per-stream parse is serial by nature, streams are
+// independent.  tapes[i] may be NULL (a new tape is made); returns the number of tapes that could not be built.
+extern "C" int h264bsdB200ReparseStreams(b200_tape **tapes, uint32_t n, const uint8_t *const *streams, const size_t *lens,
+                                         uint32_t noOutputReordering, uint32_t threads) {
+    if (!tapes || !streams || !lens || !n) return -1;
+    threads = threads ? (threads > n ? n : threads) : 1;
+    std::atomic<uint32_t> next(0), failed(0);
+    auto work = [&]() {
+        for (;;) {
+            const uint32_t i = next.fetch_add(1);
+            if (i >= n) break;
+            tapes[i] = h264bsdB200ReparseStream(tapes[i], streams[i], lens[i], noOutputReordering);
+            if (!tapes[i]) failed.fetch_add(1);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (uint32_t t = 1; t < threads; t++) pool.emplace_back(work);
+    work();
+    for (auto &t : pool) t.join();
+    return (int)failed.load();
 }

@@ -26,6 +26,9 @@ b200_tape *h264bsdB200ParseStream(const uint8_t *stream, size_t len, uint32_t no
 /* same, re-using `tape`'s arrays (NULL: allocate a new tape).  Steady-state parsing then touches no fresh pages and a
  * page-locked tape stays page-locked unless an array had to grow (tape->pinned == 2: pin again). */
 b200_tape *h264bsdB200ReparseStream(b200_tape *tape, const uint8_t *stream, size_t len, uint32_t noOutputReordering);
+/* ReparseStream for n independent streams on `threads` host threads (tapes[i] may be NULL); returns the number of failures */
+int h264bsdB200ReparseStreams(b200_tape **tapes, uint32_t n, const uint8_t *const *streams, const size_t *lens,
+                              uint32_t noOutputReordering, uint32_t threads);
 void h264bsdB200FreeTape(b200_tape *tape);
 
 /* ---- GPU (fail loudly -- NULL / -1 and a message on stderr -- when no CUDA device is usable) ---- */

@@ -271,3 +271,21 @@ def test_example_links_against_public_headers(tmp_path):
     if not torch.cuda.is_available():
         r = subprocess.run([exe, os.path.join(_oracle.GOLDEN, "test_640x360.h264")], capture_output=True, text=True)
         assert r.returncode != 0 and "no CUDA device" in r.stderr
+
+
+def test_reparse_many_matches_single_parse():
+    """h264bsdB200ReparseStreams: n streams on native threads give the tapes a single parse gives (and tapes are re-usable)"""
+    data = _oracle.stream_bytes("test_640x360.h264")
+    bits = (C.c_uint8 * len(data)).from_buffer_copy(data)
+    ref = ParsedStream(data)
+    many = [ParsedStream() for _ in range(5)]
+    for _ in range(2):
+        ParsedStream.reparse_many(many, bits, 3)
+        for p in many:
+            assert p.status == 0 and p.num_pics == ref.num_pics and p.rec_bytes == ref.rec_bytes and p.coef_bytes == ref.coef_bytes
+            a = np.ctypeslib.as_array(C.cast(p.ptr.contents.mbRecs, C.POINTER(C.c_uint8)), shape=(ref.rec_bytes,))
+            b = np.ctypeslib.as_array(C.cast(ref.ptr.contents.mbRecs, C.POINTER(C.c_uint8)), shape=(ref.rec_bytes,))
+            assert (a == b).all()
+    for p in many:
+        p.close()
+    ref.close()
