@@ -346,7 +346,6 @@ def main():
     # frames at the same time (they share the host cores); value = all streams / slowest rank
     e2e = None
     if not args.no_e2e:
-        from concurrent.futures import ThreadPoolExecutor
         from h264bsd_b200 import _lib
         L = _lib.load()
         cores_here = max(1, host_cores() // world)
@@ -359,23 +358,20 @@ def main():
         assert all(host_out)
         bits = (C.c_uint8 * len(data)).from_buffer_copy(data)             # the bitstream bytes every stream decodes
         tapes = [[None] * ne, [None] * ne]     # two sets: the host parses pass i+1 while the GPU side works on pass i
-        pool = ThreadPoolExecutor(max_workers=1)   # one Python thread per pass; the parse threads are native (no interpreter lock)
+        phase = {"parse_wait": 0.0, "upload": 0.0, "pictures": 0.0}
 
-        phase = {"parse_wait": 0.0, "upload": 0.0, "pictures": 0.0, "parse_wall": 0.0}
-
-        def parse_pass(st_):                   # host: NAL / CAVLC / MV prediction / DPB, one task per stream on the usable cores
-            tp = time.time()
+        def start_parse(st_):                  # host: NAL / CAVLC / MV prediction / DPB, one task per stream on the usable cores
             if tapes[st_][0] is None:
                 tapes[st_] = [ParsedStream() for _ in range(ne)]
-            ParsedStream.reparse_many(tapes[st_], bits, threads)      # same arrays every pass: no fresh pages, page-lock kept
-            for t_ in tapes[st_]:
+            # native threads in the background (no interpreter lock); same arrays every pass: no fresh pages, page-lock kept
+            return ParsedStream.reparse_many_begin(tapes[st_], bits, threads)
+
+        def finish_parse(token):
+            ParsedStream.reparse_many_wait(token)
+            for t_ in token[1]:
+                assert t_.status == 0
                 if not t_.pinned:
                     t_.pin()
-            phase["parse_wall"] += time.time() - tp
-            return [t_.status for t_ in tapes[st_]]
-
-        def start_parse(st_):
-            return [pool.submit(parse_pass, st_)]
 
         def gpu_side(st_):
             ta = time.time()
@@ -388,8 +384,7 @@ def main():
                 if gi + 1 < len(groups):
                     tu = time.time()
                     eb.upload_ranges(tapes[st_], *groups[gi + 1])
-                    ta -= time.time() - tu                               # counted as upload, not as pictures
-                    tb += time.time() - tu
+                    tb += time.time() - tu                               # counted as upload, not as pictures
                 for k in range(g0, g0 + gn):
                     eb.decode_picture(k)                                 # GPU: reconstruct + in-loop filter + border
                     eb.read_picture_all(k, host_out[k & 1], fb)          # D2H: picture k of every stream, packed, page-locked
@@ -398,24 +393,22 @@ def main():
             phase["pictures"] += time.time() - tb
 
         reps = max(2, min(args.steps, 3))
-        fut = start_parse(0)
-        assert not any(any(f.result()) for f in fut)
+        finish_parse(start_parse(0))
         gpu_side(0)                                                       # warm-up pass (allocations, page-locking)
-        fut = start_parse(1)
-        assert not any(any(f.result()) for f in fut)
+        finish_parse(start_parse(1))
         gpu_side(1)
         barrier()
         h2d0, d2h0 = eb.h2d_bytes(), eb.d2h_bytes()
         for k_ in phase:
             phase[k_] = 0.0
         t0 = time.time()
-        fut = start_parse(0)                                              # pass 0 is parsed inside the timed region too
+        tok = start_parse(0)                                              # pass 0 is parsed inside the timed region too
         for i in range(reps):
             tw = time.time()
-            assert not any(any(f.result()) for f in fut)
+            finish_parse(tok)
             phase["parse_wait"] += time.time() - tw
             if i + 1 < reps:
-                fut = start_parse((i + 1) & 1)
+                tok = start_parse((i + 1) & 1)
             gpu_side(i & 1)
         dt = (time.time() - t0) / reps
         h2d, d2h = (eb.h2d_bytes() - h2d0) // reps, (eb.d2h_bytes() - d2h0) // reps

@@ -47,7 +47,7 @@ LEGACY_SYMBOLS = [
     "h264bsdConvertToRGBA", "h264bsdConvertToBGRA", "h264bsdConvertToYCbCrA",
 ]
 BATCH_SYMBOLS = [
-    "h264bsdB200ParseStream", "h264bsdB200ReparseStream", "h264bsdB200ReparseStreams", "h264bsdB200FreeTape", "h264bsdB200DeviceCount", "h264bsdB200BatchCreate",
+    "h264bsdB200ParseStream", "h264bsdB200ReparseStream", "h264bsdB200ReparseStreams", "h264bsdB200ReparseStreamsBegin", "h264bsdB200ReparseStreamsWait", "h264bsdB200FreeTape", "h264bsdB200DeviceCount", "h264bsdB200BatchCreate",
     "h264bsdB200BatchDestroy", "h264bsdB200BatchUploadTape", "h264bsdB200BatchReplicateTape", "h264bsdB200BatchUploadTapeRange", "h264bsdB200BatchUploadFence", "h264bsdB200BatchUploadTapesRange",
     "h264bsdB200BatchDecodePicture", "h264bsdB200BatchRun", "h264bsdB200BatchSync", "h264bsdB200BatchNumPics",
     "h264bsdB200BatchTimerStart", "h264bsdB200BatchTimerStop", "h264bsdB200BatchReadFrame", "h264bsdB200BatchWriteFrame",
@@ -92,6 +92,9 @@ def load():
     L.h264bsdB200ParseStream.restype = C.POINTER(Tape); L.h264bsdB200ParseStream.argtypes = [vp, C.c_size_t, u32]
     L.h264bsdB200ReparseStream.restype = C.POINTER(Tape); L.h264bsdB200ReparseStream.argtypes = [C.POINTER(Tape), vp, C.c_size_t, u32]
     L.h264bsdB200ReparseStreams.restype = C.c_int
+    L.h264bsdB200ReparseStreamsBegin.restype = C.c_void_p
+    L.h264bsdB200ReparseStreamsBegin.argtypes = [C.POINTER(C.POINTER(Tape)), u32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), u32, u32]
+    L.h264bsdB200ReparseStreamsWait.restype = C.c_int; L.h264bsdB200ReparseStreamsWait.argtypes = [C.c_void_p]
     L.h264bsdB200ReparseStreams.argtypes = [C.POINTER(C.POINTER(Tape)), u32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), u32, u32]
     L.h264bsdB200FreeTape.restype = None; L.h264bsdB200FreeTape.argtypes = [C.POINTER(Tape)]
     L.h264bsdB200DeviceCount.restype = C.c_int; L.h264bsdB200DeviceCount.argtypes = []

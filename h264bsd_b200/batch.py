@@ -55,6 +55,30 @@ class ParsedStream:
             p.ptr = tapes[i]
             p._refresh()
 
+    @staticmethod
+    def reparse_many_begin(parsed, data, threads, no_output_reordering=False):
+        """reparse_many in the background (native threads only); returns a token for reparse_many_wait"""
+        L = _lib.load()
+        n = len(parsed)
+        bufs = data if isinstance(data, (list, tuple)) else [data] * n
+        tapes = (C.POINTER(_lib.Tape) * n)(*[p.ptr for p in parsed])
+        ptrs = (C.c_void_p * n)(*[C.addressof(b) for b in bufs])
+        lens = (C.c_size_t * n)(*[len(b) for b in bufs])
+        job = L.h264bsdB200ReparseStreamsBegin(tapes, n, ptrs, lens, 1 if no_output_reordering else 0, threads)
+        if not job:
+            raise MemoryError("h264bsdB200ReparseStreamsBegin failed")
+        return (job, parsed, tapes, ptrs, lens, bufs)     # keeps the arrays alive
+
+    @staticmethod
+    def reparse_many_wait(token):
+        job, parsed, tapes = token[0], token[1], token[2]
+        bad = _lib.load().h264bsdB200ReparseStreamsWait(job)
+        if bad:
+            raise MemoryError("h264bsdB200ReparseStreams failed for %d streams" % bad)
+        for i, p in enumerate(parsed):
+            p.ptr = tapes[i]
+            p._refresh()
+
     @property
     def mbs_per_pic(self):
         return self.width_mbs * self.height_mbs

@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(kDeblockWarps * 32) strengthKernel(const Deblo
 // and 2.  A step is skipped when no lane of the warp has a strength for it.
 __device__ __forceinline__ int bsNibble(uint32_t word, int idx) { return (int)((word >> (4 * idx)) & 15u); }
 
-__global__ void __launch_bounds__(kDeblockWarps * 32, 5) deblockKernel(const DeblockParams p) {
+__global__ void __launch_bounds__(kDeblockWarps * 32, 4) deblockKernel(const DeblockParams p) {
     __shared__ DeblockWarpSmem smemAll[kDeblockWarps];
     __shared__ DeblockTables tb;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

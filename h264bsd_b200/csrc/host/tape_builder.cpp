@@ -8,6 +8,7 @@
 // so steady-state parsing touches no fresh pages and a page-locked tape stays page-locked.
 #include <cstdlib>
 #include <cstring>
+#include <new>
 #include <atomic>
 #include <thread>
 #include <vector>
@@ -169,4 +170,25 @@ extern "C" int h264bsdB200ReparseStreams(b200_tape **tapes, uint32_t n, const ui
     work();
     for (auto &t : pool) t.join();
     return (int)failed.load();
+}
+
+// The same, in the background: Begin returns at once, Wait joins and returns the number of failures.  The arrays passed to
+// Begin must stay alive until Wait.
+struct b200_parse_job {
+    std::thread th;
+    int failed = 0;
+};
+extern "C" b200_parse_job *h264bsdB200ReparseStreamsBegin(b200_tape **tapes, uint32_t n, const uint8_t *const *streams, const size_t *lens,
+                                                         uint32_t noOutputReordering, uint32_t threads) {
+    b200_parse_job *j = new (std::nothrow) b200_parse_job();
+    if (!j) return nullptr;
+    j->th = std::thread([=]() { j->failed = h264bsdB200ReparseStreams(tapes, n, streams, lens, noOutputReordering, threads); });
+    return j;
+}
+extern "C" int h264bsdB200ReparseStreamsWait(b200_parse_job *j) {
+    if (!j) return -1;
+    j->th.join();
+    const int f = j->failed;
+    delete j;
+    return f;
 }

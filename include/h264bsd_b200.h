@@ -29,6 +29,12 @@ b200_tape *h264bsdB200ReparseStream(b200_tape *tape, const uint8_t *stream, size
 /* ReparseStream for n independent streams on `threads` host threads (tapes[i] may be NULL); returns the number of failures */
 int h264bsdB200ReparseStreams(b200_tape **tapes, uint32_t n, const uint8_t *const *streams, const size_t *lens,
                               uint32_t noOutputReordering, uint32_t threads);
+/* the same in the background: Begin returns at once; Wait joins and returns the number of failures (the arrays passed to
+ * Begin must stay alive until Wait) */
+typedef struct b200_parse_job b200_parse_job;
+b200_parse_job *h264bsdB200ReparseStreamsBegin(b200_tape **tapes, uint32_t n, const uint8_t *const *streams, const size_t *lens,
+                                               uint32_t noOutputReordering, uint32_t threads);
+int h264bsdB200ReparseStreamsWait(b200_parse_job *job);
 void h264bsdB200FreeTape(b200_tape *tape);
 
 /* ---- GPU (fail loudly -- NULL / -1 and a message on stderr -- when no CUDA device is usable) ---- */
