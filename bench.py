@@ -349,12 +349,8 @@ def main():
         from h264bsd_b200 import _lib
         L = _lib.load()
         cores_here = max(1, host_cores() // world)
-        # one usable core is left to the thread that drives the GPU (a busy 17th thread gets the whole cgroup throttled); the
-        # stream count is a multiple of the parse threads so that the last round of parse tasks is a full one
-        threads = max(1, cores_here - 1)
-        want = max(1, min(args.e2e_streams if args.e2e_streams > 0 else 128, count))
-        ne = max(threads, (want // threads) * threads) if want >= threads else want
-        threads = min(threads, ne)
+        ne = max(1, min(args.e2e_streams if args.e2e_streams > 0 else 128, count))
+        threads = max(1, min(ne, cores_here))
         b.close()
         eb = Batch(ne, ps.width_mbs, ps.height_mbs, ps.num_slots, device=local)
         fb = ps.frame_bytes

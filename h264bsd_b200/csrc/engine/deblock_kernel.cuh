@@ -393,12 +393,11 @@ __global__ void __launch_bounds__(kDeblockWarps * 32, 4) deblockKernel(const Deb
                 if (cr >= 2 || mby > 0) *reinterpret_cast<uint2 *>(gc) = *reinterpret_cast<const uint2 *>(&sm.c[cpl][cr][8]);
                 if (cr >= 2 && mbx > 0) *reinterpret_cast<uint32_t *>(gc - 4) = *reinterpret_cast<const uint32_t *>(&sm.c[cpl][cr][4]);
             }
-            // publish: all lanes' stores happen-before the release by lane 0
+            // publish: the warp barrier orders every lane's stores before lane 0's release, and a release at gpu scope is
+            // cumulative (the same pattern as a CTA semaphore: barrier, then st.release by one thread); no separate fence --
+            // __threadfence() would add a second, sequentially-consistent MEMBAR + L1 invalidate per macroblock
             __syncwarp();
-            if (lane == 0) {
-                __threadfence();
-                stRelease(doneS + mb, p.serial);
-            }
+            if (lane == 0) stRelease(doneS + mb, p.serial);
         }
     }
 }

@@ -424,10 +424,10 @@ __device__ __forceinline__ uint2 lumaQpel8(const uint8_t *win, int x0, int y, in
 // chain per 32 macroblocks), then the warp copies four macroblocks per step, loads before stores.
 // =====================================================================================================
 constexpr int kCopyWarps = 8;
-constexpr int kCopyUnroll = 4;
-constexpr int kCopyRunsPerTask = 16;   // zero-motion runs per warp task
+constexpr int kCopyUnroll = 2;
+constexpr int kCopyRunsPerTask = 4;    // zero-motion runs per warp task
 
-__global__ void __launch_bounds__(kCopyWarps * 32) reconCopyKernel(const ReconParams p) {
+__global__ void __launch_bounds__(kCopyWarps * 32, 5) reconCopyKernel(const ReconParams p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const PoolGeom &g = p.g;
     const int r8 = lane >> 1, c8 = (lane & 1) * 8;
@@ -1002,7 +1002,7 @@ __global__ void __launch_bounds__(kReconWarps * 32, 3) reconIntraKernel(const Re
         }
         // publish: all lanes' stores happen-before the release by lane 0
         __syncwarp();
-        if (lane == 0) { __threadfence(); stRelease(doneS + mb, p.serial); }
+        if (lane == 0) stRelease(doneS + mb, p.serial);   // release at gpu scope, cumulative over the barrier above (no extra fence)
     }
 }
 
