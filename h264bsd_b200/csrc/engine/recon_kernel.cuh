@@ -424,10 +424,10 @@ __device__ __forceinline__ uint2 lumaQpel8(const uint8_t *win, int x0, int y, in
 // chain per 32 macroblocks), then the warp copies four macroblocks per step, loads before stores.
 // =====================================================================================================
 constexpr int kCopyWarps = 8;
-constexpr int kCopyUnroll = 2;
-constexpr int kCopyRunsPerTask = 4;    // zero-motion runs per warp task
+constexpr int kCopyUnroll = 4;
+constexpr int kCopyRunsPerTask = 16;   // zero-motion runs per warp task
 
-__global__ void __launch_bounds__(kCopyWarps * 32, 5) reconCopyKernel(const ReconParams p) {
+__global__ void __launch_bounds__(kCopyWarps * 32) reconCopyKernel(const ReconParams p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const PoolGeom &g = p.g;
     const int r8 = lane >> 1, c8 = (lane & 1) * 8;
@@ -862,9 +862,16 @@ __global__ void __launch_bounds__(kReconWarps * 32, 3) reconIntraKernel(const Re
         const bool avC = flags & B200_MBF_AVAIL_C, avD = flags & B200_MBF_AVAIL_D;
         // wait for the intra neighbours this macroblock reads (record byte 28: waitMask)
         const int waitMask = (misc >> 8) & 0xFF;
-        if (lane < 4 && ((waitMask >> lane) & 1)) {
+        {
+            // a neighbour that is an earlier entry of this warp's own chunk needs no flag: program order + the warp barrier
             const int nmb = lane == 0 ? (int)mb - 1 : lane == 1 ? (int)mb - g.widthMbs : lane == 2 ? (int)mb - g.widthMbs + 1 : (int)mb - g.widthMbs - 1;
-            waitFlag(doneS + nmb, p.serial);
+            bool mine = false;
+#pragma unroll
+            for (int j = 0; j < kChunkB - 1; j++) {
+                const uint32_t mj = __shfl_sync(0xffffffffu, mMb, j);
+                mine |= j < i && (int)mj == nmb;
+            }
+            if (lane < 4 && ((waitMask >> lane) & 1) && !mine) waitFlag(doneS + nmb, p.serial);
         }
         __syncwarp();
         // neighbouring pels (h264bsdGetNeighbourPels :545-614), straight from L2
@@ -1000,9 +1007,19 @@ __global__ void __launch_bounds__(kReconWarps * 32, 3) reconIntraKernel(const Re
             for (int k = 0; k < 4; k++) oc |= (uint32_t)clip255(pv[k] + resC[k]) << (8 * k);
             *reinterpret_cast<uint32_t *>(dstC) = oc;
         }
-        // publish: all lanes' stores happen-before the release by lane 0
-        __syncwarp();
-        if (lane == 0) stRelease(doneS + mb, p.serial);   // release at gpu scope, cumulative over the barrier above (no extra fence)
+        __syncwarp();   // this macroblock's pels are written before the next entry (possibly its neighbour) starts
+    }
+    // publish the whole chunk with one fence: the warp barrier above orders every lane's stores before lane 0's fence, which is
+    // cumulative at gpu scope; then one relaxed flag store per entry (the pattern of a CTA semaphore release).  Warps of other
+    // chunks only ever wait for entries of earlier chunks, so deferring the flags to the end of the chunk cannot deadlock.
+    uint32_t mbs[kChunkB];
+#pragma unroll
+    for (int j = 0; j < kChunkB; j++) mbs[j] = __shfl_sync(0xffffffffu, mMb, j);
+    if (lane == 0) {
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < kChunkB; j++)
+            if (j < n) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(doneS + mbs[j]), "r"(p.serial) : "memory");
     }
 }
 
