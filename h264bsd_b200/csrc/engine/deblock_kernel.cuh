@@ -393,27 +393,13 @@ __global__ void __launch_bounds__(kDeblockWarps * 32, 4) deblockKernel(const Deb
                 if (cr >= 2 || mby > 0) *reinterpret_cast<uint2 *>(gc) = *reinterpret_cast<const uint2 *>(&sm.c[cpl][cr][8]);
                 if (cr >= 2 && mbx > 0) *reinterpret_cast<uint32_t *>(gc - 4) = *reinterpret_cast<const uint32_t *>(&sm.c[cpl][cr][4]);
             }
-            __syncwarp();   // the tile is reused by the next ticket
-        }
-        // publish the chunk with ONE fence: the warp barrier orders every lane's stores before lane 0's fence, which is
-        // cumulative at gpu scope; then one relaxed flag store per filtered macroblock (the pattern of a CTA semaphore release;
-        // __threadfence() + st.release per macroblock were two MEMBARs + two L1 invalidates each).  A warp only waits for
-        // tickets of earlier chunks and its own tickets are different streams, so deferring the flags cannot deadlock.
-        {
-            const unsigned long long mine = (unsigned long long)mS * (unsigned long long)g.nMbs + mMb;
-            unsigned long long flagIdx[kFilterChunk];
-            uint32_t has[kFilterChunk];
-#pragma unroll
-            for (int j = 0; j < kFilterChunk; j++) {
-                flagIdx[j] = __shfl_sync(0xffffffffu, mine, j);
-                has[j] = __shfl_sync(0xffffffffu, mWork, j);
-            }
-            if (lane == 0) {
-                asm volatile("fence.acq_rel.gpu;" ::: "memory");
-#pragma unroll
-                for (int j = 0; j < kFilterChunk; j++)
-                    if (has[j]) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p.done + flagIdx[j]), "r"(p.serial) : "memory");
-            }
+            // publish: the warp barrier orders every lane's stores before lane 0's release, and a release at gpu scope is
+            // cumulative (the same pattern as a CTA semaphore: barrier, then st.release by one thread); no separate fence --
+            // __threadfence() would add a second, sequentially-consistent MEMBAR + L1 invalidate per macroblock.  (Publishing
+            // a whole chunk with one fence was tried: the later flags make the waiters spin longer and, with one stream, a
+            // warp would wait for its own unpublished tickets.)
+            __syncwarp();
+            if (lane == 0) stRelease(doneS + mb, p.serial);
         }
     }
 }

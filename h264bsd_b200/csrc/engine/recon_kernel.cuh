@@ -1007,19 +1007,9 @@ __global__ void __launch_bounds__(kReconWarps * 32, 3) reconIntraKernel(const Re
             for (int k = 0; k < 4; k++) oc |= (uint32_t)clip255(pv[k] + resC[k]) << (8 * k);
             *reinterpret_cast<uint32_t *>(dstC) = oc;
         }
-        __syncwarp();   // this macroblock's pels are written before the next entry (possibly its neighbour) starts
-    }
-    // publish the whole chunk with one fence: the warp barrier above orders every lane's stores before lane 0's fence, which is
-    // cumulative at gpu scope; then one relaxed flag store per entry (the pattern of a CTA semaphore release).  Warps of other
-    // chunks only ever wait for entries of earlier chunks, so deferring the flags to the end of the chunk cannot deadlock.
-    uint32_t mbs[kChunkB];
-#pragma unroll
-    for (int j = 0; j < kChunkB; j++) mbs[j] = __shfl_sync(0xffffffffu, mMb, j);
-    if (lane == 0) {
-        asm volatile("fence.acq_rel.gpu;" ::: "memory");
-#pragma unroll
-        for (int j = 0; j < kChunkB; j++)
-            if (j < n) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(doneS + mbs[j]), "r"(p.serial) : "memory");
+        // publish: the warp barrier orders every lane's stores before lane 0's release at gpu scope (cumulative; no extra fence)
+        __syncwarp();
+        if (lane == 0) stRelease(doneS + mb, p.serial);
     }
 }
 
