@@ -12,7 +12,7 @@ namespace b200 {
 
 constexpr int kDeblockWarps = 8;
 constexpr int kBsChunk = 8;      // stage 1: consecutive macroblocks per warp
-constexpr int kFilterChunk = 8;  // stage 2: consecutive tickets per warp (different streams)
+constexpr int kFilterChunk = 8;  // stage 2: most consecutive tickets per warp (DeblockParams::filterChunk <= kFilterChunk)
 
 struct DeblockParams {
     uint8_t *pool;
@@ -25,6 +25,7 @@ struct DeblockParams {
     uint32_t totalTickets;
     uint32_t *bsWords;         // nStreams * nMbs * 4 words: packed boundary strengths (stage 1 -> stage 2)
     uint8_t *work;             // nStreams * nMbs: 1 = the macroblock has a non-zero boundary strength
+    uint32_t filterChunk;      // stage 2: tickets a warp takes at a time
     unsigned long long *workCount;   // running total of macroblocks with work (statistics for the roofline accounting)
 };
 
@@ -261,7 +262,7 @@ __global__ void __launch_bounds__(kDeblockWarps * 32, 4) deblockKernel(const Deb
     for (;;) {
         // every warp takes its own tickets (no CTA barrier: a warp that waits for a neighbour does not hold up the others)
         uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(p.ticket, (uint32_t)kFilterChunk);
+        if (lane == 0) base = atomicAdd(p.ticket, p.filterChunk);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= p.totalTickets) break;
         // lane j < kFilterChunk walks the dependent loads of the warp's ticket j (order -> work flag -> record, strengths,
@@ -269,7 +270,7 @@ __global__ void __launch_bounds__(kDeblockWarps * 32, 4) deblockKernel(const Deb
         uint32_t mMb = 0, mS = 0, mW0 = 0, mW3 = 0, mQp = 0, mWork = 0;
         uint4 mBw = make_uint4(0, 0, 0, 0);
         unsigned long long mFrame = 0;
-        if (lane < kFilterChunk) {
+        if (lane < (int)p.filterChunk) {
             const uint32_t t = base + lane;
             if (t < p.totalTickets) {
                 const uint32_t k = t / (uint32_t)g.nStreams, s = t - k * (uint32_t)g.nStreams;
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(kDeblockWarps * 32, 4) deblockKernel(const Deb
             }
         }
 #pragma unroll 1
-        for (int j = 0; j < kFilterChunk; j++) {
+        for (int j = 0; j < (int)p.filterChunk; j++) {
             const uint32_t workBits = __shfl_sync(0xffffffffu, mWork, j);
             if (!workBits) continue;
             const uint32_t mb = __shfl_sync(0xffffffffu, mMb, j), s = __shfl_sync(0xffffffffu, mS, j);

@@ -172,6 +172,11 @@ bool Batch::create(int device, uint32_t nStreams, uint32_t widthMbs, uint32_t he
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occC, reconCopyKernel, kCopyWarps * 32, 0));
     copyBlocks_ = std::max(1, occC) * numSms_;
     deblockBlocks_ = std::max(1, occD) * numSms_;
+    // tuning knobs (defaults are the measured best on the 512-stream 1080p batch)
+    if (const char *e = std::getenv("B200_CHUNK_B")) chunkB_ = std::max(1, std::min((int)kChunkB, std::atoi(e)));
+    if (const char *e = std::getenv("B200_CHUNK_A")) chunkA_ = std::max(1, std::min((int)kChunkA, std::atoi(e)));
+    if (const char *e = std::getenv("B200_COPY_RUNS")) copyRuns_ = std::max(1, std::min((int)kCopyRunsPerTask, std::atoi(e)));
+    if (const char *e = std::getenv("B200_FILTER_CHUNK")) filterChunk_ = std::max(1, std::min((int)kFilterChunk, std::atoi(e)));
     tapes_.assign(nStreams, DevTape());
     for (int i = 0; i < 2; i++) {
         CK(cudaStreamCreateWithFlags(&auxStream_[i], cudaStreamNonBlocking));
@@ -382,11 +387,14 @@ bool Batch::launchPicture(const StreamJob *dJobs, uint32_t maxQ, uint32_t maxC, 
     if (recon) {
         rp.pool = pool_; rp.g = g_; rp.jobs = dJobs; rp.done = dDoneRecon_;
         rp.ticket = dCounters_ + 0; rp.errors = dCounters_ + 2; rp.serial = serial_;
-        rp.chunksB = (maxB + kChunkB - 1) / kChunkB;
-        rp.chunksA = (maxA + kReconWarps * kChunkA - 1) / (kReconWarps * kChunkA);
+        rp.chunkB = (uint32_t)chunkB_;
+        rp.chunksB = (maxB + rp.chunkB - 1) / rp.chunkB;
+        rp.chunkA = (uint32_t)chunkA_;
+        rp.copyRuns = (uint32_t)copyRuns_;
+        rp.chunksA = (maxA + kReconWarps * rp.chunkA - 1) / (kReconWarps * rp.chunkA);
         rp.virtualCtasA = rp.chunksA * (uint32_t)g_.nStreams;
         rp.chunksC = (maxC + 31) / 32;
-        rp.chunksQ = (maxQ + kCopyRunsPerTask - 1) / kCopyRunsPerTask;
+        rp.chunksQ = (maxQ + rp.copyRuns - 1) / rp.copyRuns;
     }
     DeblockParams dp;
     if (deblock) {
@@ -394,6 +402,7 @@ bool Batch::launchPicture(const StreamJob *dJobs, uint32_t maxQ, uint32_t maxC, 
         dp.ticket = dCounters_ + 1; dp.serial = serial_; dp.totalTickets = total;
         dp.bsWords = dBsWords_; dp.work = dWork_;
         dp.workCount = reinterpret_cast<unsigned long long *>(dCounters_ + 4);
+        dp.filterChunk = (uint32_t)filterChunk_;
     }
     auto launchStrength = [&](cudaStream_t st) {
         const uint32_t chunks = ((uint32_t)g_.nMbs + kDeblockWarps * 32 - 1) / (kDeblockWarps * 32) * (uint32_t)g_.nStreams;
@@ -437,7 +446,7 @@ bool Batch::launchPicture(const StreamJob *dJobs, uint32_t maxQ, uint32_t maxC, 
             launchStrength(stream_);
             mark(4);
         }
-        const uint32_t ctas = (total + kDeblockWarps * kFilterChunk - 1) / (kDeblockWarps * kFilterChunk);
+        const uint32_t ctas = (total + kDeblockWarps * filterChunk_ - 1) / (kDeblockWarps * filterChunk_);
         deblockKernel<<<std::min<uint32_t>(ctas, (uint32_t)deblockBlocks_), kDeblockWarps * 32, 0, stream_>>>(dp);
         launches_++;
         mark(1);

@@ -12,7 +12,7 @@ namespace b200 {
 
 constexpr int kReconWarps = 8;
 constexpr int kChunkA = 8;   // consecutive pass-A list entries per warp (TMA of entry i+1 overlaps the math of entry i)
-constexpr int kChunkB = 4;   // consecutive pass-B (wavefront) entries per warp task
+constexpr int kChunkB = 8;   // most consecutive pass-B (wavefront) entries per warp task (ReconParams::chunkB <= kChunkB)
 
 struct ReconParams {
     uint8_t *pool;
@@ -22,7 +22,10 @@ struct ReconParams {
     uint32_t *ticket;          // CTA ticket counter of pass B (zeroed before launch)
     uint32_t *errors;          // [0] IDCT range errors (h264bsd_transform.c:183-188)
     uint32_t serial;           // value that marks "done in this launch"
-    uint32_t chunksB;          // pass B: warp tasks (kChunkB entries) per stream
+    uint32_t chunksB;          // pass B: warp tasks (chunkB entries) per stream
+    uint32_t chunkB;           // pass B: list entries per warp task
+    uint32_t chunkA;           // pass A: list entries per warp (<= kChunkA)
+    uint32_t copyRuns;         // copy pass: runs per warp task (<= kCopyRunsPerTask)
     uint32_t chunksA;          // pass A: virtual CTAs per stream (kReconWarps * kChunkA entries each)
     uint32_t virtualCtasA;     // chunksA * nStreams
     uint32_t chunksC;          // copy pass: warp tasks of 32 single copies per stream
@@ -443,9 +446,9 @@ __global__ void __launch_bounds__(kCopyWarps * 32) reconCopyKernel(const ReconPa
             // ---- runs: 2..32 macroblocks side by side, zero vector, one reference frame.  A run is 16 luma rows of 16 * len
             // bytes and 2 x 8 chroma rows of 8 * len bytes at the same offset in the reference and the current frame; the warp
             // walks them as 16-byte (8-byte) chunks in row-major order, so every row segment is one contiguous burst
-            const uint32_t e0 = task * (uint32_t)kCopyRunsPerTask;
+            const uint32_t e0 = task * p.copyRuns;
             if (e0 >= job.nR) continue;
-            const int n = (int)min((uint32_t)kCopyRunsPerTask, (uint32_t)job.nR - e0);
+            const int n = (int)min(p.copyRuns, (uint32_t)job.nR - e0);
             uint32_t mOff = 0, mOffC = 0, mLen = 1;
             long long mDelta = 0;   // reference frame - current frame
             if (lane < n) {
@@ -600,9 +603,9 @@ reconInterKernel(const ReconParams p, const __grid_constant__ CUtensorMap lumaMa
     for (uint32_t v = blockIdx.x; v < p.virtualCtasA; v += gridDim.x) {
     const uint32_t s = v / p.chunksA, chunk = v - s * p.chunksA;
     const StreamJob job = p.jobs[s];
-    const uint32_t l0 = (chunk * kReconWarps + warp) * kChunkA;   // index into the stream's pass-A entries that are not plain copies
+    const uint32_t l0 = (chunk * kReconWarps + warp) * p.chunkA;   // index into the stream's pass-A entries that are not plain copies
     if (l0 >= job.nA) continue;
-    const int n = min((uint32_t)kChunkA, job.nA - l0);
+    const int n = min(p.chunkA, job.nA - l0);
     const uint32_t e0 = 2u * job.nR + job.nC + l0;               // the plain copies went to reconCopyKernel
     const uint32_t frameBase = s * (uint32_t)g.numSlots;
     uint8_t *cur = framePtr(p.pool, g, frameBase + job.curSlot);
@@ -813,9 +816,9 @@ __global__ void __launch_bounds__(kReconWarps * 32, 3) reconIntraKernel(const Re
     const uint32_t chunk = t / (uint32_t)g.nStreams, s = t - chunk * (uint32_t)g.nStreams;
     if (chunk >= p.chunksB) return;
     const StreamJob job = p.jobs[s];
-    const uint32_t e0 = chunk * kChunkB;
+    const uint32_t e0 = chunk * p.chunkB;
     if (e0 >= job.nB) return;
-    const int n = min((uint32_t)kChunkB, job.nB - e0);
+    const int n = min(p.chunkB, job.nB - e0);
     IntraWarpSmem &sm = smemAll[warp];
     uint32_t *doneS = p.done + (size_t)s * g.nMbs;
     uint8_t *cur = framePtr(p.pool, g, s * (uint32_t)g.numSlots + job.curSlot);
