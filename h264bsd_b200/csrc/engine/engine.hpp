@@ -85,7 +85,7 @@ private:
     cudaEvent_t syncEv_ = nullptr, forkEv_ = nullptr, joinEv_[2] = {nullptr, nullptr};
     size_t jobsCap_ = 0;
     int chunkB_ = 1, filterChunk_ = 8;   // list entries per intra warp task / tickets per filter warp step
-    int chunkA_ = 8, copyRuns_ = 16;     // list entries per pass-A warp / runs per copy warp task
+    int chunkA_ = 8, copyRuns_ = 4;      // list entries per pass-A warp / runs per copy warp task
     cudaStream_t uploadStream_ = nullptr;
     std::deque<std::pair<uint32_t, cudaEvent_t>> fences_;   // (pictures below this index, upload-stream event)
     std::vector<cudaEvent_t> fenceFree_;
