@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libh264bsd_b200.so")
+# B200_LIB: another build of the same library (kernel experiments); the product always loads the in-tree default
+LIB_PATH = os.environ.get("B200_LIB") or os.path.join(_HERE, "libh264bsd_b200.so")
 
 STORAGE_BYTES = 4648
 

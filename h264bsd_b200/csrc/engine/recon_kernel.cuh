@@ -803,7 +803,7 @@ reconInterKernel(const ReconParams p, const __grid_constant__ CUtensorMap lumaMa
 // the warps of a CTA belong to different streams (they never wait for each other), and a warp only ever waits for
 // chunks whose CTA took an earlier ticket.
 // =====================================================================================================
-__global__ void __launch_bounds__(kReconWarps * 32, 4) reconIntraKernel(const ReconParams p) {
+__global__ void __launch_bounds__(kReconWarps * 32, 5) reconIntraKernel(const ReconParams p) {
     __shared__ IntraWarpSmem smemAll[kReconWarps];
     __shared__ uint32_t sI4Table[9 * 16];
     __shared__ uint32_t sTicket;
