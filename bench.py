@@ -335,6 +335,13 @@ def main():
                               "reconIntraKernel": {"ms_per_launch": per_launch("recon_intra"), "share_of_step": stage_ms["recon_intra"] / step_ms,
                                                    "achieved_gbs": gbs(float(per_pic_intra_bytes.mean()) * count, per_launch("recon_intra"))},
                               "borderKernel": {"ms_per_launch": per_launch("border"), "share_of_step": stage_ms["border"] / step_ms}}}
+    # config 5 (BASELINE.json): the YUV -> ARGB output kernel, one 1080p frame of every stream per launch, 5.5 bytes per pel
+    conv_reps = 3
+    conv_ms = b.convert_bench_all(last_slot, 1, conv_reps) / conv_reps
+    conv_bytes = count * (ps.width_mbs * 16) * (ps.height_mbs * 16) * 5.5
+    roof["other_kernels"]["convertKernel"] = {"achieved_gbs": gbs(conv_bytes, conv_ms), "ms_per_launch": conv_ms,
+                                             "frac": gbs(conv_bytes, conv_ms) / peak,
+                                             "note": "BGRA of the last output frame of all streams in one launch; not part of the timed step"}
     prof = os.path.join(ROOT, "profiles", "r01_recon_traffic.json")
     if os.path.exists(prof):
         try:

@@ -52,7 +52,7 @@ BATCH_SYMBOLS = [
     "h264bsdB200BatchDestroy", "h264bsdB200BatchUploadTape", "h264bsdB200BatchReplicateTape", "h264bsdB200BatchUploadTapeRange", "h264bsdB200BatchUploadFence", "h264bsdB200BatchUploadTapesRange",
     "h264bsdB200BatchDecodePicture", "h264bsdB200BatchRun", "h264bsdB200BatchSync", "h264bsdB200BatchNumPics",
     "h264bsdB200BatchTimerStart", "h264bsdB200BatchTimerStop", "h264bsdB200BatchReadFrame", "h264bsdB200BatchWriteFrame",
-    "h264bsdB200BatchConvertFrame", "h264bsdB200BatchConvertBench", "h264bsdB200BatchCompareStreams",
+    "h264bsdB200BatchConvertFrame", "h264bsdB200BatchConvertBench", "h264bsdB200BatchConvertBenchAll", "h264bsdB200BatchCompareStreams",
     "h264bsdB200BatchDebugStage", "h264bsdB200BatchIdctErrors", "h264bsdB200BatchDeblockWorkMbs", "h264bsdB200BatchWatchdog", "h264bsdB200BatchReadPictureAll", "h264bsdB200HostAlloc", "h264bsdB200HostFree",
     "h264bsdB200PinTape", "h264bsdB200UnpinTape", "h264bsdB200BatchKernelTiming", "h264bsdB200BatchKernelTimes", "h264bsdB200BatchLaunches", "h264bsdB200BatchH2DBytes",
     "h264bsdB200BatchD2HBytes",
@@ -116,6 +116,8 @@ def load():
     L.h264bsdB200BatchWriteFrame.restype = C.c_int; L.h264bsdB200BatchWriteFrame.argtypes = [vp, u32, u32, vp]
     L.h264bsdB200BatchConvertFrame.restype = C.c_int; L.h264bsdB200BatchConvertFrame.argtypes = [vp, u32, u32, C.c_int, vp]
     L.h264bsdB200BatchConvertBench.restype = C.c_int
+    L.h264bsdB200BatchConvertBenchAll.restype = C.c_int
+    L.h264bsdB200BatchConvertBenchAll.argtypes = [vp, u32, C.c_int, C.c_int, C.POINTER(C.c_float)]
     L.h264bsdB200BatchConvertBench.argtypes = [vp, u32, u32, C.c_int, C.c_int, C.POINTER(C.c_float)]
     L.h264bsdB200BatchCompareStreams.restype = C.c_int; L.h264bsdB200BatchCompareStreams.argtypes = [vp, u32p]
     L.h264bsdB200BatchDebugStage.restype = C.c_int; L.h264bsdB200BatchDebugStage.argtypes = [vp, u32, C.c_int, C.c_int]

@@ -185,6 +185,11 @@ class Batch:
         self._ck(self._L.h264bsdB200BatchConvertBench(self.h, stream, slot, mode, reps, C.byref(ms)), "convert_bench")
         return ms.value
 
+    def convert_bench_all(self, slot, mode, reps):
+        ms = C.c_float(0)
+        self._ck(self._L.h264bsdB200BatchConvertBenchAll(self.h, slot, mode, reps, C.byref(ms)), "convert_bench_all")
+        return ms.value
+
     def compare_streams(self, slots):
         arr = (C.c_uint32 * self.n_streams)(*slots)
         r = self._L.h264bsdB200BatchCompareStreams(self.h, arr)

@@ -271,6 +271,7 @@ int h264bsdB200BatchReadFrame(b200_batch *h, uint32_t stream, uint32_t slot, uin
 int h264bsdB200BatchReadPictureAll(b200_batch *h, uint32_t picIndex, uint8_t *dst, size_t strideBytes) { return h && B(h)->readPictureAll(picIndex, dst, strideBytes) ? 0 : -1; }
 int h264bsdB200BatchWriteFrame(b200_batch *h, uint32_t stream, uint32_t slot, const uint8_t *src) { return h && B(h)->writeFrame(stream, slot, src) ? 0 : -1; }
 int h264bsdB200BatchConvertFrame(b200_batch *h, uint32_t stream, uint32_t slot, int mode, uint32_t *dst) { return h && B(h)->convertFrame(stream, slot, mode, dst) ? 0 : -1; }
+int h264bsdB200BatchConvertBenchAll(b200_batch *h, uint32_t slot, int mode, int reps, float *ms) { return h && B(h)->convertBenchAll(slot, mode, reps, ms) ? 0 : -1; }
 int h264bsdB200BatchConvertBench(b200_batch *h, uint32_t stream, uint32_t slot, int mode, int reps, float *ms) { return h && B(h)->convertBench(stream, slot, mode, reps, ms) ? 0 : -1; }
 int h264bsdB200BatchCompareStreams(b200_batch *h, const uint32_t *slots) { return h ? B(h)->compareStreams(slots) : -1; }
 int h264bsdB200BatchDebugStage(b200_batch *h, uint32_t picIndex, int recon, int deblock) { return h && B(h)->debugStage(picIndex, recon != 0, deblock != 0) ? 0 : -1; }

@@ -454,10 +454,14 @@ __global__ void __launch_bounds__(256) borderKernel(const BorderParams p) {
 // ---- YUV -> 32-bit pixels (h264bsdConvertToRGBA/BGRA/YCbCrA, decoder.c:1163-1370) --------------------------
 // mode 0: A<<24|B<<16|G<<8|R   1: A<<24|R<<16|G<<8|B   2: A<<24|Cr<<16|Cb<<8|Y ; nearest chroma, coded size
 __global__ void __launch_bounds__(256) convertKernel(const uint8_t *yPlane, int pitchY, const uint8_t *cbPlane, const uint8_t *crPlane,
-                                                     int pitchC, int W, int mode, uint32_t *out) {
+                                                     int pitchC, int W, int mode, uint32_t *out,
+                                                     unsigned long long inStride = 0, unsigned long long outStride = 0) {
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;  // four pels per thread
     const int y = blockIdx.y;
     if (x4 >= W) return;
+    // blockIdx.z = picture of a batch: the same planes `inStride` bytes further, output `outStride` pixels further
+    yPlane += blockIdx.z * inStride; cbPlane += blockIdx.z * inStride; crPlane += blockIdx.z * inStride;
+    out += blockIdx.z * outStride;
     const uint32_t yv = *reinterpret_cast<const uint32_t *>(yPlane + (size_t)y * pitchY + x4);
     const uint32_t cbv = *reinterpret_cast<const uint16_t *>(cbPlane + (size_t)(y >> 1) * pitchC + (x4 >> 1));
     const uint32_t crv = *reinterpret_cast<const uint16_t *>(crPlane + (size_t)(y >> 1) * pitchC + (x4 >> 1));

@@ -56,6 +56,7 @@ void Batch::destroy() {
     tapes_.clear();
     cudaFree(dBsWords_); cudaFree(dWork_); cudaFree(dPack_[0]); cudaFree(dPack_[1]);
     if (copyStream_) { cudaStreamSynchronize(copyStream_); cudaStreamDestroy(copyStream_); copyStream_ = nullptr; }
+    cudaFree(dConvertAll_);
     cudaFree(pool_); cudaFree(dOrder_); cudaFree(dDoneRecon_); cudaFree(dDoneDeblock_); cudaFree(dCounters_);
     cudaFree(dJobs_); cudaFree(dStage_[0]); cudaFree(dStage_[1]); cudaFree(dConvert_); cudaFree(dSlots_);
     if (hStage_[0]) cudaFreeHost(hStage_[0]);
@@ -636,6 +637,26 @@ bool Batch::convertBench(uint32_t stream, uint32_t slot, int mode, int reps, flo
     CK(cudaEventRecord(evA_, stream_));
     for (int i = 0; i < reps; i++) convertKernel<<<grid, 256, 0, stream_>>>(f + (size_t)kPadY * g_.pitchY + kPadY, g_.pitchY, f + g_.offCb + (size_t)kPadC * g_.pitchC + kPadC,
                                               f + g_.offCr + (size_t)kPadC * g_.pitchC + kPadC, g_.pitchC, g_.W, mode, dConvert_);
+    CK(cudaEventRecord(evB_, stream_));
+    CK(cudaEventSynchronize(evB_));
+    CK(cudaEventElapsedTime(ms, evA_, evB_));
+    launches_ += reps;
+    return true;
+}
+
+// config 5 at batch size: frame `slot` of EVERY stream -> 32-bit pixels in one launch (blockIdx.z = stream), `reps` times
+bool Batch::convertBenchAll(uint32_t slot, int mode, int reps, float *ms) {
+    if (!created_ || slot >= (uint32_t)g_.numSlots || reps <= 0) return false;
+    CK(cudaSetDevice(device_));
+    const size_t pixels = (size_t)g_.W * g_.H;
+    if (!dConvertAll_) CK(cudaMalloc(&dConvertAll_, pixels * 4 * g_.nStreams));
+    const uint8_t *f = pool_ + (unsigned long long)slot * g_.frameStride;
+    dim3 grid((g_.W / 4 + 255) / 256, g_.H, g_.nStreams);
+    CK(cudaEventRecord(evA_, stream_));
+    for (int i = 0; i < reps; i++)
+        convertKernel<<<grid, 256, 0, stream_>>>(f + (size_t)kPadY * g_.pitchY + kPadY, g_.pitchY, f + g_.offCb + (size_t)kPadC * g_.pitchC + kPadC,
+                                                 f + g_.offCr + (size_t)kPadC * g_.pitchC + kPadC, g_.pitchC, g_.W, mode, dConvertAll_,
+                                                 (unsigned long long)g_.numSlots * g_.frameStride, (unsigned long long)pixels);
     CK(cudaEventRecord(evB_, stream_));
     CK(cudaEventSynchronize(evB_));
     CK(cudaEventElapsedTime(ms, evA_, evB_));

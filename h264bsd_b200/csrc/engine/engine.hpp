@@ -27,6 +27,7 @@ public:
     bool replicateTape(uint32_t srcStream);
     bool uploadTapeRange(uint32_t stream, const b200_tape *t, uint32_t firstPic, uint32_t numPics);
     bool uploadFence(uint32_t throughPic);
+    bool convertBenchAll(uint32_t slot, int mode, int reps, float *ms);
     uint64_t deblockWorkMbs();   // macroblocks with a non-zero boundary strength since creation
     bool decodePicture(uint32_t k);                // picture k of every stream
     bool run(uint32_t first, uint32_t count);
@@ -84,6 +85,7 @@ private:
     int reconBlocks_ = 0, deblockBlocks_ = 0, copyBlocks_ = 0;
     cudaEvent_t syncEv_ = nullptr, forkEv_ = nullptr, joinEv_[2] = {nullptr, nullptr};
     size_t jobsCap_ = 0;
+    uint32_t *dConvertAll_ = nullptr;
     int chunkB_ = 1, filterChunk_ = 8;   // list entries per intra warp task / tickets per filter warp step
     int chunkA_ = 8, copyRuns_ = 4;      // list entries per pass-A warp / runs per copy warp task
     cudaStream_t uploadStream_ = nullptr;

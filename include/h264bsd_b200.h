@@ -88,6 +88,8 @@ int h264bsdB200BatchWriteFrame(b200_batch *batch, uint32_t stream, uint32_t slot
 /* h264bsdConvertTo{RGBA(0),BGRA(1),YCbCrA(2)} of a frame slot (decoder.c:1163-1370) into host memory */
 int h264bsdB200BatchConvertFrame(b200_batch *batch, uint32_t stream, uint32_t slot, int mode, uint32_t *dst);
 int h264bsdB200BatchConvertBench(b200_batch *batch, uint32_t stream, uint32_t slot, int mode, int reps, float *ms);
+/* the same for frame `slot` of every stream in one launch (device output only): the YUV->ARGB kernel at batch size */
+int h264bsdB200BatchConvertBenchAll(b200_batch *batch, uint32_t slot, int mode, int reps, float *ms);
 /* number of streams whose frame in slots[s] differs from stream 0's frame in slots[0]; <0 on error */
 int h264bsdB200BatchCompareStreams(b200_batch *batch, const uint32_t *slots);
 /* run only some stages of a picture (test hook) */
