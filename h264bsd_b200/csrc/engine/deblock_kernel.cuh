@@ -453,33 +453,57 @@ __global__ void __launch_bounds__(256) borderKernel(const BorderParams p) {
 
 // ---- YUV -> 32-bit pixels (h264bsdConvertToRGBA/BGRA/YCbCrA, decoder.c:1163-1370) --------------------------
 // mode 0: A<<24|B<<16|G<<8|R   1: A<<24|R<<16|G<<8|B   2: A<<24|Cr<<16|Cb<<8|Y ; nearest chroma, coded size
-__global__ void __launch_bounds__(256) convertKernel(const uint8_t *yPlane, int pitchY, const uint8_t *cbPlane, const uint8_t *crPlane,
-                                                     int pitchC, int W, int mode, uint32_t *out,
-                                                     unsigned long long inStride = 0, unsigned long long outStride = 0) {
-    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;  // four pels per thread
+template <int PELS>   // pels per thread: 4, or 8 when the width allows it (8-byte luma load, two 16-byte stores)
+__global__ void __launch_bounds__(256) convertKernelT(const uint8_t *yPlane, int pitchY, const uint8_t *cbPlane, const uint8_t *crPlane,
+                                                      int pitchC, int W, int mode, uint32_t *out,
+                                                      unsigned long long inStride, unsigned long long outStride) {
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * PELS;
     const int y = blockIdx.y;
-    if (x4 >= W) return;
+    if (x0 >= W) return;
     // blockIdx.z = picture of a batch: the same planes `inStride` bytes further, output `outStride` pixels further
     yPlane += blockIdx.z * inStride; cbPlane += blockIdx.z * inStride; crPlane += blockIdx.z * inStride;
     out += blockIdx.z * outStride;
-    const uint32_t yv = *reinterpret_cast<const uint32_t *>(yPlane + (size_t)y * pitchY + x4);
-    const uint32_t cbv = *reinterpret_cast<const uint16_t *>(cbPlane + (size_t)(y >> 1) * pitchC + (x4 >> 1));
-    const uint32_t crv = *reinterpret_cast<const uint16_t *>(crPlane + (size_t)(y >> 1) * pitchC + (x4 >> 1));
-    uint32_t o[4];
+    uint32_t yw[PELS / 4], cbv, crv;
+    if (PELS == 8) {
+        const uint2 t = *reinterpret_cast<const uint2 *>(yPlane + (size_t)y * pitchY + x0);
+        yw[0] = t.x; yw[PELS / 4 - 1] = t.y;
+        cbv = *reinterpret_cast<const uint32_t *>(cbPlane + (size_t)(y >> 1) * pitchC + (x0 >> 1));
+        crv = *reinterpret_cast<const uint32_t *>(crPlane + (size_t)(y >> 1) * pitchC + (x0 >> 1));
+    } else {
+        yw[0] = *reinterpret_cast<const uint32_t *>(yPlane + (size_t)y * pitchY + x0);
+        cbv = *reinterpret_cast<const uint16_t *>(cbPlane + (size_t)(y >> 1) * pitchC + (x0 >> 1));
+        crv = *reinterpret_cast<const uint16_t *>(crPlane + (size_t)(y >> 1) * pitchC + (x0 >> 1));
+    }
+    uint32_t o[PELS];
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int l = (yv >> (8 * i)) & 0xFF, cb = (cbv >> (8 * (i >> 1))) & 0xFF, cr = (crv >> (8 * (i >> 1))) & 0xFF;
+    for (int i = 0; i < PELS; i++) {
+        const int l = (yw[i >> 2] >> (8 * (i & 3))) & 0xFF, cb = (cbv >> (8 * (i >> 1))) & 0xFF, cr = (crv >> (8 * (i >> 1))) & 0xFF;
         if (mode == 2) {
             o[i] = 0xFF000000u | ((uint32_t)cr << 16) | ((uint32_t)cb << 8) | (uint32_t)l;
         } else {
             const int c = l - 16, d = cb - 128, e = cr - 128;
             const uint32_t r = (uint32_t)clip255((298 * c + 409 * e + 128) >> 8);
             const uint32_t gg = (uint32_t)clip255((298 * c - 100 * d - 208 * e + 128) >> 8);
-            const uint32_t b = (uint32_t)clip255((298 * c + 516 * d + 128) >> 8);
-            o[i] = mode == 0 ? (0xFF000000u | (b << 16) | (gg << 8) | r) : (0xFF000000u | (r << 16) | (gg << 8) | b);
+            const uint32_t bb = (uint32_t)clip255((298 * c + 516 * d + 128) >> 8);
+            o[i] = mode == 0 ? (0xFF000000u | (bb << 16) | (gg << 8) | r) : (0xFF000000u | (r << 16) | (gg << 8) | bb);
         }
     }
-    *reinterpret_cast<uint4 *>(out + (size_t)y * W + x4) = make_uint4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+    for (int i = 0; i < PELS; i += 4)
+        *reinterpret_cast<uint4 *>(out + (size_t)y * W + x0 + i) = make_uint4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+}
+// launch helper: picks the 8-pel variant when rows and pitches allow 8-byte luma / 4-byte chroma loads
+inline void launchConvert(cudaStream_t st, int nPictures, int H, const uint8_t *yPlane, int pitchY, const uint8_t *cbPlane, const uint8_t *crPlane,
+                          int pitchC, int W, int mode, uint32_t *out, unsigned long long inStride, unsigned long long outStride) {
+    const bool wide = (W % 8 == 0) && (pitchY % 8 == 0) && (pitchC % 4 == 0) && ((uintptr_t)yPlane % 8 == 0) && ((uintptr_t)cbPlane % 4 == 0) &&
+                      ((uintptr_t)crPlane % 4 == 0) && (inStride % 8 == 0);
+    if (wide) {
+        dim3 grid((W / 8 + 255) / 256, H, nPictures);
+        convertKernelT<8><<<grid, 256, 0, st>>>(yPlane, pitchY, cbPlane, crPlane, pitchC, W, mode, out, inStride, outStride);
+    } else {
+        dim3 grid((W / 4 + 255) / 256, H, nPictures);
+        convertKernelT<4><<<grid, 256, 0, st>>>(yPlane, pitchY, cbPlane, crPlane, pitchC, W, mode, out, inStride, outStride);
+    }
 }
 
 // ---- compare frame `slot` of every stream with stream 0's (picture area only) -------------------------------

@@ -616,9 +616,8 @@ bool Batch::convertFrame(uint32_t stream, uint32_t slot, int mode, uint32_t *dst
     const size_t bytes = (size_t)g_.W * g_.H * 4;
     if (!dConvert_) CK(cudaMalloc(&dConvert_, bytes));
     const uint8_t *f = pool_ + ((unsigned long long)stream * g_.numSlots + slot) * g_.frameStride;
-    dim3 grid((g_.W / 4 + 255) / 256, g_.H);
-    convertKernel<<<grid, 256, 0, stream_>>>(f + (size_t)kPadY * g_.pitchY + kPadY, g_.pitchY, f + g_.offCb + (size_t)kPadC * g_.pitchC + kPadC,
-                                              f + g_.offCr + (size_t)kPadC * g_.pitchC + kPadC, g_.pitchC, g_.W, mode, dConvert_);
+    launchConvert(stream_, 1, g_.H, f + (size_t)kPadY * g_.pitchY + kPadY, g_.pitchY, f + g_.offCb + (size_t)kPadC * g_.pitchC + kPadC,
+                  f + g_.offCr + (size_t)kPadC * g_.pitchC + kPadC, g_.pitchC, g_.W, mode, dConvert_, 0, 0);
     launches_++;
     CK(cudaMemcpyAsync(dstHost, dConvert_, bytes, cudaMemcpyDeviceToHost, stream_));
     CK(cudaStreamSynchronize(stream_));
@@ -633,10 +632,10 @@ bool Batch::convertBench(uint32_t stream, uint32_t slot, int mode, int reps, flo
     const size_t bytes = (size_t)g_.W * g_.H * 4;
     if (!dConvert_) CK(cudaMalloc(&dConvert_, bytes));
     const uint8_t *f = pool_ + ((unsigned long long)stream * g_.numSlots + slot) * g_.frameStride;
-    dim3 grid((g_.W / 4 + 255) / 256, g_.H);
     CK(cudaEventRecord(evA_, stream_));
-    for (int i = 0; i < reps; i++) convertKernel<<<grid, 256, 0, stream_>>>(f + (size_t)kPadY * g_.pitchY + kPadY, g_.pitchY, f + g_.offCb + (size_t)kPadC * g_.pitchC + kPadC,
-                                              f + g_.offCr + (size_t)kPadC * g_.pitchC + kPadC, g_.pitchC, g_.W, mode, dConvert_);
+    for (int i = 0; i < reps; i++)
+        launchConvert(stream_, 1, g_.H, f + (size_t)kPadY * g_.pitchY + kPadY, g_.pitchY, f + g_.offCb + (size_t)kPadC * g_.pitchC + kPadC,
+                      f + g_.offCr + (size_t)kPadC * g_.pitchC + kPadC, g_.pitchC, g_.W, mode, dConvert_, 0, 0);
     CK(cudaEventRecord(evB_, stream_));
     CK(cudaEventSynchronize(evB_));
     CK(cudaEventElapsedTime(ms, evA_, evB_));
@@ -651,12 +650,11 @@ bool Batch::convertBenchAll(uint32_t slot, int mode, int reps, float *ms) {
     const size_t pixels = (size_t)g_.W * g_.H;
     if (!dConvertAll_) CK(cudaMalloc(&dConvertAll_, pixels * 4 * g_.nStreams));
     const uint8_t *f = pool_ + (unsigned long long)slot * g_.frameStride;
-    dim3 grid((g_.W / 4 + 255) / 256, g_.H, g_.nStreams);
     CK(cudaEventRecord(evA_, stream_));
     for (int i = 0; i < reps; i++)
-        convertKernel<<<grid, 256, 0, stream_>>>(f + (size_t)kPadY * g_.pitchY + kPadY, g_.pitchY, f + g_.offCb + (size_t)kPadC * g_.pitchC + kPadC,
-                                                 f + g_.offCr + (size_t)kPadC * g_.pitchC + kPadC, g_.pitchC, g_.W, mode, dConvertAll_,
-                                                 (unsigned long long)g_.numSlots * g_.frameStride, (unsigned long long)pixels);
+        launchConvert(stream_, g_.nStreams, g_.H, f + (size_t)kPadY * g_.pitchY + kPadY, g_.pitchY, f + g_.offCb + (size_t)kPadC * g_.pitchC + kPadC,
+                      f + g_.offCr + (size_t)kPadC * g_.pitchC + kPadC, g_.pitchC, g_.W, mode, dConvertAll_,
+                      (unsigned long long)g_.numSlots * g_.frameStride, (unsigned long long)pixels);
     CK(cudaEventRecord(evB_, stream_));
     CK(cudaEventSynchronize(evB_));
     CK(cudaEventElapsedTime(ms, evA_, evB_));
@@ -677,9 +675,8 @@ bool convertHostI420(int mode, uint32_t width, uint32_t height, const uint8_t *y
     CK(cudaMalloc(&dIn, inBytes));
     CK(cudaMalloc(&dOut, outBytes));
     CK(cudaMemcpy(dIn, yuv, inBytes, cudaMemcpyHostToDevice));
-    dim3 grid((width / 4 + 255) / 256, height);
-    convertKernel<<<grid, 256>>>(dIn, (int)width, dIn + (size_t)width * height, dIn + (size_t)width * height * 5 / 4, (int)width / 2,
-                                 (int)width, mode, dOut);
+    launchConvert(nullptr, 1, (int)height, dIn, (int)width, dIn + (size_t)width * height, dIn + (size_t)width * height * 5 / 4, (int)width / 2,
+                  (int)width, mode, dOut, 0, 0);
     CK(cudaGetLastError());
     CK(cudaMemcpy(out, dOut, outBytes, cudaMemcpyDeviceToHost));
     cudaFree(dIn);
