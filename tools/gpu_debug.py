@@ -72,21 +72,14 @@ def main():
         else:
             print(f"pic {k} RECON ok", flush=True)
         # deblock in isolation from the oracle's unfiltered picture
-        print('   a', flush=True); b.write_frame(0, h.curSlot, pre)
-        print('   b', flush=True); orc.deblock(k)
-        print('   c', flush=True); post = orc.frame(h.curSlot).copy()
-        import time, ctypes; t0 = time.time(); b.debug_stage(k, False, True)
-        if os.environ.get('HB_DUMP') and k == 1:
-            time.sleep(3)
-            b._L.h264bsdB200BatchHeartbeat.restype = ctypes.POINTER(ctypes.c_uint32); b._L.h264bsdB200BatchHeartbeat.argtypes = [ctypes.c_void_p]
-            hb = b._L.h264bsdB200BatchHeartbeat(b.h)
-            rows = [(w, hb[w*4], hb[w*4+1]) for w in range(920) if hb[w*4+1] not in (0, 99)]
-            print('   heartbeat (warp, ticket, stage) not finished:', rows[:40], flush=True)
-            print('   deblock starts', hb[65000*4], 'border starts', hb[65001*4], 'sample', [(hb[w*4], hb[w*4+1]) for w in range(0, 920, 97)], flush=True)
-            order = sorted(range(920), key=lambda m: (m % wm + 2*(m//wm), m))
-            for w, tk, st in rows[:10]: print('     ticket', tk, 'mb', order[tk] if tk < 920 else None, flush=True)
-            os._exit(0)
-        print('   d', flush=True); b.sync(); print('   e', flush=True); print('   deblock kernel wall', round(time.time()-t0, 4), 'watchdog', b.watchdog(), flush=True)
+        b.write_frame(0, h.curSlot, pre)
+        orc.deblock(k)
+        post = orc.frame(h.curSlot).copy()
+        import time
+        t0 = time.time()
+        b.debug_stage(k, False, True)
+        b.sync()
+        print('   deblock kernel wall', round(time.time() - t0, 4), 'watchdog', b.watchdog(), flush=True)
         got = b.read_frame(0, h.curSlot)
         bad = mb_diff(got, post, wm, hm)
         if bad:
