@@ -57,17 +57,38 @@ struct PictureState::MbSyntax {
 
 void PictureState::resize(uint32_t w, uint32_t h) {
     widthMbs = w; heightMbs = h; picSizeInMbs = w * h;
-    st.assign(picSizeInMbs, b200_mb_rec());
-    for (auto &r : st) std::memset(&r, 0, sizeof r);
+    ownSt_.clear();
+    ownRecs_.clear();
+    st = recs = nullptr;
+    bound_ = false;
     aux.assign(picSizeInMbs, MbAux());
-    recs.assign(picSizeInMbs, b200_mb_rec());
-    for (auto &r : recs) std::memset(&r, 0, sizeof r);
     sliceGroupMap.assign(picSizeInMbs, 0);
     coefs.clear();
     sliceIdCounter = numDecodedMbs = lastMbAddr = 0;
 }
 
+void PictureState::bindOutput() {
+    if (bound_) return;
+    bound_ = true;
+    b200_mb_rec *out = provider ? provider->pictureRecords(picSizeInMbs) : nullptr;
+    if (!out) {
+        if (ownRecs_.size() != picSizeInMbs) {
+            ownRecs_.resize(picSizeInMbs);
+            std::memset(ownRecs_.data(), 0, sizeof(b200_mb_rec) * picSizeInMbs);
+        }
+        out = ownRecs_.data();
+    }
+    st = recs = out;
+}
+
+void PictureState::splitState() {
+    if (st != recs) return;
+    ownSt_.assign(recs, recs + picSizeInMbs);
+    st = ownSt_.data();
+}
+
 void PictureState::beginPicture() {
+    bound_ = false;
     numDecodedMbs = 0;
     sliceIdCounter = 0;
     for (auto &a : aux) { a.sliceId = 0; a.decoded = 0; }
@@ -479,8 +500,13 @@ bool PictureState::finishMacroblock(MbSyntax &mb, uint32_t mbAddr, int &qpY, con
     r.chromaQpIndexOffset = (int8_t)pps.chromaQpIndexOffset;
     r.codedMask = 0;
     r.coefIndex = 0;
+    r.waitMask = 0;
+    r.reserved1[0] = r.reserved1[1] = r.reserved1[2] = 0;   // (the record may live in memory nobody cleared: every byte is set)
 
     if (mb.mbType == B200_MB_I_PCM) {
+        r.subMbTypes = 0;
+        std::memset(r.refSlot, 0, 4);
+        std::memset(r.refIdx, 0, 4);
         r.qpY = 0;
         r.qpC = kQpC[std::min(51, std::max(0, 0 + pps.chromaQpIndexOffset))];
         for (int i = 0; i < 24; i++) ax.totalCoeff[i] = 16;
@@ -493,7 +519,7 @@ bool PictureState::finishMacroblock(MbSyntax &mb, uint32_t mbAddr, int &qpY, con
         size_t at = coefs.size();
         coefs.resize(at + 12 * 16);
         std::memcpy(&coefs[at], mb.pcm, 384);
-        recs[mbAddr] = r;
+        if (recs != st) recs[mbAddr] = r;
         return true;
     }
 
@@ -528,6 +554,7 @@ bool PictureState::finishMacroblock(MbSyntax &mb, uint32_t mbAddr, int &qpY, con
         std::memset(r.refSlot, 0, 4);
         std::memset(r.refIdx, 0, 4);
         r.subMbTypes = 0;
+        std::memset(&r.u, 0, sizeof r.u);
         if (!deriveIntra(mb, mbAddr, pps.constrainedIntraPred)) return false;
     }
     if (!first) return true;
@@ -544,7 +571,7 @@ bool PictureState::finishMacroblock(MbSyntax &mb, uint32_t mbAddr, int &qpY, con
         for (int i = 0; i < 24; i++)
             if (mask & (1u << i)) { std::memcpy(dst, mb.level[i], 32); dst += 16; }
     }
-    recs[mbAddr] = r;
+    if (recs != st) recs[mbAddr] = r;
     return true;
 }
 
@@ -555,6 +582,8 @@ SliceResult PictureState::decodeSlice(BitReader &br, const SliceHeader &sh, cons
     static thread_local bool mbInit = false;
     if (!mbInit) { std::memset(&mb, 0, sizeof mb); mbInit = true; }
 
+    bindOutput();
+    if (sh.redundantPicCnt) splitState();   // a macroblock decoded again updates the state, not the record (first decode wins)
     uint32_t cur = sh.firstMb;
     uint32_t skipRun = 0;
     bool prevSkipped = false;
@@ -639,6 +668,7 @@ void PictureState::markSliceCorrupted(uint32_t firstMbInSlice, const Sps &sps) {
 }
 
 void PictureState::finalizeRecords() {
+    bindOutput();
     // One pass over the records (they are 96 bytes each; everything after it works on one byte per macroblock):
     // deblocking edge flags (GetMbFilteringFlags, deblocking.c:289-320, needs the final slice ids) and the class of the
     // macroblock for the processing order: 0 other pass-A, 1 plain copy, 4 pass-B (intra-predicted), zr = 1 + reference
@@ -735,6 +765,7 @@ void PictureState::finalizeRecords() {
 // slices when a reference exists); otherwise mid-grey I_PCM.  NOT the reference's spatial intra
 // concealment (conceal.c:266-639) -- see DESIGN.md.
 uint32_t PictureState::concealMissing(const Dpb &dpb, bool pSlice) {
+    bindOutput();
     uint32_t n = 0;
     int slot = pSlice ? dpb.refSlot(0) : -1;
     for (uint32_t a = 0; a < picSizeInMbs; a++) {
@@ -757,7 +788,7 @@ uint32_t PictureState::concealMissing(const Dpb &dpb, bool pSlice) {
             std::memset(&coefs[at], 128, 384);
         }
         st[a] = r;
-        recs[a] = r;
+        if (recs != st) recs[a] = r;
         aux[a].decoded = 1;
         std::memset(aux[a].totalCoeff, 0, 27);
     }

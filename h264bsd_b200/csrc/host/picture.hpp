@@ -24,15 +24,27 @@ struct MbAux {
 
 enum class SliceResult { Ok, Error };
 
+// Who wants the records may lend the memory they are built in (the tape does: the records of a picture are then written
+// once, in place, instead of state array -> record array -> tape).  nullptr = build them in the decoder's own arrays.
+class RecordProvider {
+public:
+    virtual ~RecordProvider() {}
+    virtual b200_mb_rec *pictureRecords(uint32_t nMbs) { (void)nMbs; return nullptr; }
+};
+
 class PictureState {
 public:
     void resize(uint32_t widthMbs, uint32_t heightMbs);
     void beginPicture();  // h264bsdResetStorage: sliceId/decoded cleared, the rest persists
     uint32_t widthMbs = 0, heightMbs = 0, picSizeInMbs = 0;
 
-    std::vector<b200_mb_rec> st;    // persistent per-MB state (last decode of each MB, incl. redundant slices)
+    // st: per-MB state of the picture being decoded (last decode of each MB, incl. redundant slices); recs: the records of
+    // the picture being built (first decode of each MB).  They are the SAME memory -- lent by the provider or ownRecs_ --
+    // until a redundant slice shows up in the picture (then st moves to ownSt_).  Bound lazily per picture (bindOutput).
+    b200_mb_rec *st = nullptr;
+    b200_mb_rec *recs = nullptr;
+    RecordProvider *provider = nullptr;
     std::vector<MbAux> aux;
-    std::vector<b200_mb_rec> recs;  // records of the picture being built (first decode of each MB)
     std::vector<int16_t> coefs;     // coefficient pool of the picture being built, 16 int16 per block
     std::vector<uint16_t> order;    // processing order of the picture being built (see b200_tape.mbOrder)
     uint32_t numPassA = 0, numPassB = 0, numCopy = 0, numRun = 0, numRunMbs = 0;
@@ -65,6 +77,10 @@ private:
     int mbC(uint32_t a) const { return (a >= widthMbs && (a % widthMbs) < widthMbs - 1) ? (int)(a - widthMbs + 1) : -1; }
     int mbD(uint32_t a) const { return (a >= widthMbs && (a % widthMbs)) ? (int)(a - widthMbs - 1) : -1; }
     bool avail(uint32_t cur, int nb) const { return nb >= 0 && aux[nb].sliceId == aux[cur].sliceId; }
+    void bindOutput();       // first touch of a picture: where do its records live
+    void splitState();       // a redundant slice: st must no longer alias recs
+    std::vector<b200_mb_rec> ownSt_, ownRecs_;
+    bool bound_ = false;
     int curNb_[4] = {-1, -1, -1, -1};   // available neighbours A, B, C, D of the macroblock being decoded (decodeSlice)
 
     struct NbMv { bool avail; uint32_t refIdx; int16_t mv[2]; };

@@ -9,6 +9,7 @@ namespace b200 {
 StreamDecoder::StreamDecoder(PictureSink *sink, bool noOutputReordering)
     : sink_(sink), noReorderingRequested_(noOutputReordering) {
     cavlcInit();
+    pic_.provider = sink;   // the sink may lend the memory the records of a picture are built in
 }
 
 // h264bsdExtractNalUnit (h264bsd_byte_stream.c:81-237): same start-code scan and the same
@@ -246,7 +247,7 @@ void StreamDecoder::finishPicture() {
         hdr.outSlot[i] = (uint8_t)dpb_.pendingOutput(i).slot;
         hdr.outPicIndex[i] = dpb_.pendingOutput(i).picIndex;
     }
-    if (sink_) sink_->submitPicture(hdr, pic_.recs.data(), pic_.coefs.data(), pic_.order.data());
+    if (sink_) sink_->submitPicture(hdr, pic_.recs, pic_.coefs.data(), pic_.order.data());
     picIndex_++;
     pic_.beginPicture();  // h264bsdResetStorage
     picStarted_ = false;

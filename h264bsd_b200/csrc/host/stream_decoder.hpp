@@ -18,12 +18,13 @@ namespace b200 {
 // same values as the enum in the public header (h264bsd_decoder.h:45-52)
 enum DecodeResult : uint32_t { RDY = 0, PIC_RDY, HDRS_RDY, ERROR, PARAM_SET_ERROR, MEMALLOC_ERROR };
 
-class PictureSink {
+class PictureSink : public RecordProvider {
 public:
     virtual ~PictureSink() {}
     // parameter sets activated: frame geometry and number of frame slots are now known
     virtual bool configure(uint32_t widthMbs, uint32_t heightMbs, uint32_t numSlots) = 0;
-    // a complete picture; `recs` (widthMbs*heightMbs records), `coefs` and `order` are only valid during the call
+    // a complete picture; `recs` (widthMbs*heightMbs records; the memory pictureRecords() lent, if it lent any), `coefs` and
+    // `order` are only valid during the call
     virtual bool submitPicture(const b200_pic_hdr &hdr, const b200_mb_rec *recs, const int16_t *coefs, const uint16_t *order) = 0;
 };
 

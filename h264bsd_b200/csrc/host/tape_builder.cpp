@@ -40,16 +40,27 @@ public:
         if (slots > t_->numSlots) t_->numSlots = slots;
         return true;
     }
+    // the records of the next picture are built in place at the end of the tape's record array
+    b200_mb_rec *pictureRecords(uint32_t nMbs) override {
+        const size_t nrec = (size_t)nMbs * sizeof(b200_mb_rec);
+        if (t_->pinned == 1 && t_->mbRecBytes + nrec > t_->capRecs) {
+            h264bsdB200UnpinTape(t_);   // never realloc a page-locked block
+            repin = true;
+        }
+        if (!ensure(t_->mbRecs, t_->capRecs, t_->mbRecBytes + nrec)) { ok = false; return nullptr; }
+        return reinterpret_cast<b200_mb_rec *>(t_->mbRecs + t_->mbRecBytes);
+    }
     bool submitPicture(const b200_pic_hdr &hdr, const b200_mb_rec *r, const int16_t *c, const uint16_t *o) override {
         const size_t nMbs = (size_t)hdr.widthMbs * hdr.heightMbs;
         const size_t nrec = nMbs * sizeof(b200_mb_rec), ncoef = (size_t)hdr.numCoefBlocks * B200_COEF_BLOCK_BYTES, nord = nMbs * 2;
         uint64_t orderBytes = (uint64_t)t_->numPics * nMbs * 2;
         uint64_t picBytes = (uint64_t)t_->numPics * sizeof(b200_pic_hdr);
-        if (t_->pinned == 1 && (t_->mbRecBytes + nrec > t_->capRecs || t_->coefBytes + ncoef > t_->capCoefs || orderBytes + nord > t_->capOrder)) {
+        const bool inPlace = t_->mbRecs && reinterpret_cast<const uint8_t *>(r) == t_->mbRecs + t_->mbRecBytes;
+        if (t_->pinned == 1 && ((!inPlace && t_->mbRecBytes + nrec > t_->capRecs) || t_->coefBytes + ncoef > t_->capCoefs || orderBytes + nord > t_->capOrder)) {
             h264bsdB200UnpinTape(t_);   // never realloc a page-locked block
             repin = true;
         }
-        if (!ensure(t_->mbRecs, t_->capRecs, t_->mbRecBytes + nrec) || !ensure(t_->coefs, t_->capCoefs, t_->coefBytes + ncoef) ||
+        if ((!inPlace && !ensure(t_->mbRecs, t_->capRecs, t_->mbRecBytes + nrec)) || !ensure(t_->coefs, t_->capCoefs, t_->coefBytes + ncoef) ||
             !ensure(t_->mbOrder, t_->capOrder, orderBytes + nord) || !ensure(t_->pics, t_->capPics, picBytes + sizeof(b200_pic_hdr))) {
             ok = false;
             return false;
@@ -57,7 +68,7 @@ public:
         b200_pic_hdr h = hdr;
         h.mbRecOffset = t_->mbRecBytes;
         h.coefOffset = t_->coefBytes;
-        std::memcpy(t_->mbRecs + t_->mbRecBytes, r, nrec);
+        if (!inPlace) std::memcpy(t_->mbRecs + t_->mbRecBytes, r, nrec);
         std::memcpy(t_->coefs + t_->coefBytes, c, ncoef);
         std::memcpy((uint8_t *)t_->mbOrder + orderBytes, o, nord);
         t_->pics[t_->numPics] = h;
