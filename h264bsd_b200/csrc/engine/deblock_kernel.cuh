@@ -11,7 +11,6 @@
 namespace b200 {
 
 constexpr int kDeblockWarps = 8;
-constexpr int kBsChunk = 8;      // stage 1: consecutive macroblocks per warp
 constexpr int kFilterChunk = 8;  // stage 2: most consecutive tickets per warp (DeblockParams::filterChunk <= kFilterChunk)
 
 struct DeblockParams {
@@ -225,7 +224,7 @@ __global__ void __launch_bounds__(kDeblockWarps * 32) strengthKernel(const Deblo
 }
 
 // ---- stage 2: the filter proper, macroblocks with work only ---------------------------------------------------------
-// Tickets in wavefront order (x + 2y ascending, streams interleaved); a warp takes kFilterChunk consecutive tickets
+// Tickets in wavefront order (x + 2y ascending, streams interleaved); a warp takes filterChunk consecutive tickets
 // (different streams).  A macroblock waits for its left,
 // top and top-right neighbours -- the macroblocks whose filtering the reference's raster order puts before it and whose
 // pels it reads or rewrites -- but only for those that have work themselves (the others never touch a pel).
@@ -265,7 +264,7 @@ __global__ void __launch_bounds__(kDeblockWarps * 32, 4) deblockKernel(const Deb
         if (lane == 0) base = atomicAdd(p.ticket, p.filterChunk);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= p.totalTickets) break;
-        // lane j < kFilterChunk walks the dependent loads of the warp's ticket j (order -> work flag -> record, strengths,
+        // lane j < filterChunk walks the dependent loads of the warp's ticket j (order -> work flag -> record, strengths,
         // neighbours), all tickets at once: one chain of memory latencies per chunk instead of one per macroblock
         uint32_t mMb = 0, mS = 0, mW0 = 0, mW3 = 0, mQp = 0, mWork = 0;
         uint4 mBw = make_uint4(0, 0, 0, 0);

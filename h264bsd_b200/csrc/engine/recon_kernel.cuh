@@ -29,7 +29,7 @@ struct ReconParams {
     uint32_t chunksA;          // pass A: virtual CTAs per stream (kReconWarps * kChunkA entries each)
     uint32_t virtualCtasA;     // chunksA * nStreams
     uint32_t chunksC;          // copy pass: warp tasks of 32 single copies per stream
-    uint32_t chunksQ;          // copy pass: warp tasks of kCopyRunsPerTask zero-motion runs per stream (they come first)
+    uint32_t chunksQ;          // copy pass: warp tasks of copyRuns zero-motion runs per stream (they come first)
 };
 
 struct __align__(128) InterWarpSmem {
@@ -428,7 +428,7 @@ __device__ __forceinline__ uint2 lumaQpel8(const uint8_t *win, int x0, int y, in
 // =====================================================================================================
 constexpr int kCopyWarps = 8;
 constexpr int kCopyUnroll = 4;
-constexpr int kCopyRunsPerTask = 16;   // zero-motion runs per warp task
+constexpr int kCopyRunsPerTask = 16;   // most zero-motion runs per warp task (ReconParams::copyRuns)
 
 __global__ void __launch_bounds__(kCopyWarps * 32) reconCopyKernel(const ReconParams p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
