@@ -410,43 +410,49 @@ struct BorderParams {
     PoolGeom g;
     const StreamJob *jobs;
 };
-// one warp per row of one plane (incl. border rows) of one stream's current frame
+// Warp tasks per stream: "side" tasks fill the left / right border of 32 picture rows of one plane (each row's edge pel);
+// "cap" tasks fill a 128-byte column chunk of every border row above (below) a plane with the first (last) row, already
+// extended by its own side pels -- the source word is read once and stored `pad` times, whole 128-byte lines.
 __global__ void __launch_bounds__(256) borderKernel(const BorderParams p) {
     const PoolGeom &g = p.g;
     const int lane = threadIdx.x & 31;
-    const int rowsTotal = g.rowsY + 2 * g.rowsC;
+    const int sideY = (g.H + 31) / 32, sideC = (g.H / 2 + 31) / 32;
+    const int capY = (g.pitchY + 127) / 128, capC = (g.pitchC + 127) / 128;
+    const int perStream = sideY + 2 * sideC + 2 * capY + 4 * capC;
     const long long task = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (task >= (long long)rowsTotal * g.nStreams) return;
-    const int s = (int)(task / rowsTotal);
-    int r = (int)(task - (long long)s * rowsTotal);
+    if (task >= (long long)perStream * g.nStreams) return;
+    const int s = (int)(task / perStream);
+    int t = (int)(task - (long long)s * perStream);
     uint8_t *frame = framePtr(p.pool, g, (uint32_t)s * g.numSlots + p.jobs[s].curSlot);
-    uint8_t *plane;
-    int w, h, pad, pitch;
-    if (r < g.rowsY) { plane = frame; w = g.W; h = g.H; pad = kPadY; pitch = g.pitchY; }
-    else {
-        r -= g.rowsY;
-        const int pl = r >= g.rowsC;
-        if (pl) r -= g.rowsC;
-        plane = frame + (pl ? g.offCr : g.offCb);
-        w = g.W / 2; h = g.H / 2; pad = kPadC; pitch = g.pitchC;
-    }
-    const int sy = clip3(0, h - 1, r - pad);          // source picture row
-    const uint8_t *src = plane + (size_t)(sy + pad) * pitch + pad;
-    uint8_t *dst = plane + (size_t)r * pitch;
-    const bool inside = (r - pad) == sy;
-    const uint32_t lv = src[0] * 0x01010101u, rv = src[w - 1] * 0x01010101u;
-    if (inside) {
-        for (int i = lane; i < pad / 4; i += 32) reinterpret_cast<uint32_t *>(dst)[i] = lv;
-        for (int i = (pad + w) / 4 + lane; i < pitch / 4; i += 32) reinterpret_cast<uint32_t *>(dst)[i] = rv;
-    } else {
-        for (int i = lane; i < pitch / 4; i += 32) {
-            uint32_t v;
-            const int x = i * 4 - pad;
-            if (x < 0) v = lv;
-            else if (x >= w) v = rv;
-            else v = *reinterpret_cast<const uint32_t *>(src + x);
-            reinterpret_cast<uint32_t *>(dst)[i] = v;
+    if (t < sideY + 2 * sideC) {
+        const bool luma = t < sideY;
+        int pl = 0;
+        if (!luma) { t -= sideY; pl = t / sideC; t -= pl * sideC; }
+        uint8_t *plane = luma ? frame : frame + (pl ? g.offCr : g.offCb);
+        const int w = luma ? g.W : g.W / 2, h = luma ? g.H : g.H / 2, pad = luma ? kPadY : kPadC, pitch = luma ? g.pitchY : g.pitchC;
+        const int r0 = t * 32, rows = min(32, h - r0), shift = luma ? 3 : 2, wpp = pad / 4;
+        for (int i = lane; i < rows * wpp; i += 32) {
+            uint8_t *rowp = plane + (size_t)(r0 + (i >> shift) + pad) * pitch;   // start of the row incl. its left border
+            const uint32_t lv = rowp[pad] * 0x01010101u, rv = rowp[pad + w - 1] * 0x01010101u;
+            reinterpret_cast<uint32_t *>(rowp)[i & (wpp - 1)] = lv;
+            reinterpret_cast<uint32_t *>(rowp + pad + w)[i & (wpp - 1)] = rv;
         }
+    } else {
+        t -= sideY + 2 * sideC;
+        const bool luma = t < 2 * capY;
+        int pl = 0;
+        if (!luma) { t -= 2 * capY; pl = t / (2 * capC); t -= pl * 2 * capC; }
+        const int caps = luma ? capY : capC;
+        const bool bottom = t >= caps;
+        const int word = (t - (bottom ? caps : 0)) * 32 + lane;
+        uint8_t *plane = luma ? frame : frame + (pl ? g.offCr : g.offCb);
+        const int w = luma ? g.W : g.W / 2, h = luma ? g.H : g.H / 2, pad = luma ? kPadY : kPadC, pitch = luma ? g.pitchY : g.pitchC;
+        if (word * 4 >= pitch) return;
+        const uint8_t *src = plane + (size_t)((bottom ? h - 1 : 0) + pad) * pitch + pad;   // first pel of the source row
+        const int x = word * 4 - pad;
+        const uint32_t v = x < 0 ? src[0] * 0x01010101u : x >= w ? src[w - 1] * 0x01010101u : *reinterpret_cast<const uint32_t *>(src + x);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(plane + (size_t)(bottom ? pad + h : 0) * pitch) + word;
+        for (int r = 0; r < pad; r++) dst[(size_t)r * (pitch / 4)] = v;
     }
 }
 

@@ -178,6 +178,7 @@ bool Batch::create(int device, uint32_t nStreams, uint32_t widthMbs, uint32_t he
     if (const char *e = std::getenv("B200_CHUNK_A")) chunkA_ = std::max(1, std::min((int)kChunkA, std::atoi(e)));
     if (const char *e = std::getenv("B200_COPY_RUNS")) copyRuns_ = std::max(1, std::min((int)kCopyRunsPerTask, std::atoi(e)));
     if (const char *e = std::getenv("B200_FILTER_CHUNK")) filterChunk_ = std::max(1, std::min((int)kFilterChunk, std::atoi(e)));
+    borderTasks_ = (g_.H + 31) / 32 + 2 * ((g_.H / 2 + 31) / 32) + 2 * ((g_.pitchY + 127) / 128) + 4 * ((g_.pitchC + 127) / 128);
     tapes_.assign(nStreams, DevTape());
     for (int i = 0; i < 2; i++) {
         CK(cudaStreamCreateWithFlags(&auxStream_[i], cudaStreamNonBlocking));
@@ -455,9 +456,8 @@ bool Batch::launchPicture(const StreamJob *dJobs, uint32_t maxQ, uint32_t maxC, 
     {
         BorderParams bp;
         bp.pool = pool_; bp.g = g_; bp.jobs = dJobs;
-        const long long rows = (long long)(g_.rowsY + 2 * g_.rowsC) * g_.nStreams;
-        const int blocks = (int)((rows + 7) / 8);
-        borderKernel<<<blocks, 256, 0, stream_>>>(bp);
+        const long long tasks = (long long)borderTasks_ * g_.nStreams;
+        borderKernel<<<(int)((tasks + 7) / 8), 256, 0, stream_>>>(bp);
         launches_++;
         mark(2);
     }
@@ -603,8 +603,7 @@ bool Batch::writeFrame(uint32_t stream, uint32_t slot, const uint8_t *src) {
     CK(cudaMemcpyAsync(dJob, &job, sizeof job, cudaMemcpyHostToDevice, stream_));
     BorderParams bp;
     bp.pool = f; bp.g = g_; bp.g.nStreams = 1; bp.jobs = dJob;
-    const long long rows = (long long)(g_.rowsY + 2 * g_.rowsC);
-    borderKernel<<<(int)((rows + 7) / 8), 256, 0, stream_>>>(bp);
+    borderKernel<<<(borderTasks_ + 7) / 8, 256, 0, stream_>>>(bp);
     CK(cudaStreamSynchronize(stream_));
     cudaFree(dJob);
     return true;

@@ -85,6 +85,7 @@ private:
     int reconBlocks_ = 0, deblockBlocks_ = 0, copyBlocks_ = 0;
     cudaEvent_t syncEv_ = nullptr, forkEv_ = nullptr, joinEv_[2] = {nullptr, nullptr};
     size_t jobsCap_ = 0;
+    int borderTasks_ = 0;   // warp tasks of borderKernel per stream
     uint32_t *dConvertAll_ = nullptr;
     int chunkB_ = 1, filterChunk_ = 8;   // list entries per intra warp task / tickets per filter warp step
     int chunkA_ = 8, copyRuns_ = 4;      // list entries per pass-A warp / runs per copy warp task
