@@ -1,0 +1,55 @@
+#!/usr/bin/env python
+"""Writes tests/golden/synth_md5.json: for every seed of tests/synth_h264.py the md5 of the stream itself (so that a
+change of the generator or of Python's `random` shows up as such) and the md5 of what the UNMODIFIED reference
+decoder (oracle/_ref/libh264bsd_ref.so, built by oracle/Makefile from /root/reference) makes of it: all output
+pictures at full coded size, output order, plus the pictures before the in-loop filter in decoding order.
+Run in the container that has /root/reference; the tests then need neither it nor oracle/_ref."""
+import ctypes as C
+import hashlib
+import json
+import os
+import sys
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+import _oracle          # noqa: E402
+import synth_h264       # noqa: E402
+
+SEEDS = range(0, 160)
+
+
+def reference_decode(data):
+    """(number of output pictures or -1, frame bytes, output frames, pre-filter frames, decoded pictures)"""
+    L = _oracle.reference()
+    info = (C.c_uint32 * 8)()
+    cap = 1 << 25
+    post = np.zeros(cap, np.uint8)
+    pre = np.zeros(cap, np.uint8)
+    buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+    n = L.ref_decode_stream(buf, len(data), post.ctypes.data, cap, pre.ctypes.data, cap, None, 0, info)
+    fb = info[0] * info[1] * 384
+    assert max(n, 0) * fb <= cap and info[7] * fb <= cap
+    return n, fb, post[:max(n, 0) * fb], pre[:info[7] * fb], int(info[7]), (int(info[0]), int(info[1]))
+
+
+def main():
+    if _oracle.reference() is None:
+        sys.exit("oracle/_ref/libh264bsd_ref.so is not built (make -C oracle ref)")
+    out = {}
+    for seed in SEEDS:
+        data = synth_h264.make_stream(seed)
+        n, fb, post, pre, ndec, dims = reference_decode(data)
+        assert n >= 0, f"seed {seed}: the reference reports a decode error -- the generator wrote an invalid stream"
+        out[str(seed)] = {"stream_md5": hashlib.md5(data).hexdigest(), "bytes": len(data), "width_mbs": dims[0],
+                          "height_mbs": dims[1], "outputs": n, "decoded": ndec,
+                          "post_md5": hashlib.md5(post.tobytes()).hexdigest(), "pre_md5": hashlib.md5(pre.tobytes()).hexdigest()}
+    path = os.path.join(_oracle.GOLDEN, "synth_md5.json")
+    with open(path, "w") as f:
+        json.dump(out, f, indent=0, sort_keys=True)
+    print("wrote", path, len(out), "seeds")
+
+
+if __name__ == "__main__":
+    main()

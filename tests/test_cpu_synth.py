@@ -1,0 +1,92 @@
+"""Host syntax decoder + CPU oracle against the reference decoder on synthetic streams that walk through the
+Baseline syntax the three encoder-made fixtures never touch (tests/synth_h264.py: FMO, ASO, several slices and
+reference frames, list reordering, I_PCM, every partition shape and intra mode, vectors far outside the picture,
+level escape codes, long-term IDR, frame_num wrap, POC types 0-2 ...).  No GPU: this pins the *record* half of
+record-then-replay and the oracle the GPU suite is checked against."""
+import hashlib
+import json
+import os
+import numpy as np
+import pytest
+import _oracle
+import synth_h264
+from h264bsd_b200.batch import ParsedStream
+
+GOLD = json.load(open(os.path.join(_oracle.GOLDEN, "synth_md5.json")))
+SEEDS = sorted(int(s) for s in GOLD)
+
+
+def md5(a):
+    return hashlib.md5(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def decode_with_oracle(data):
+    ps = ParsedStream(data)
+    try:
+        assert ps.status == 0, f"host parser reports status {ps.status} after {ps.num_pics} pictures"
+        post, pre, errs = _oracle.oracle_run_tape(ps, want_pre=True)
+        assert errs == 0
+        return len(ps.outputs), ps.num_pics, (ps.width_mbs, ps.height_mbs), post, pre
+    finally:
+        ps.close()
+
+
+@pytest.mark.parametrize("chunk", range(8))
+def test_synthetic_streams_match_reference_golden(chunk):
+    """committed md5s of the reference decoder's output (tests/make_synth_golden.py); needs no reference build"""
+    for seed in SEEDS[chunk::8]:
+        g = GOLD[str(seed)]
+        data = synth_h264.make_stream(seed)
+        if hashlib.md5(data).hexdigest() != g["stream_md5"]:
+            pytest.skip("tests/synth_h264.py (or Python's random) no longer writes the streams the golden file was made from: "
+                        "re-run tests/make_synth_golden.py")
+        n_out, n_dec, dims, post, pre = decode_with_oracle(data)
+        assert dims == (g["width_mbs"], g["height_mbs"]), f"seed {seed}"
+        assert (n_out, n_dec) == (g["outputs"], g["decoded"]), f"seed {seed}: picture counts"
+        assert md5(pre) == g["pre_md5"], f"seed {seed}: pictures before the in-loop filter differ from the reference"
+        assert md5(post) == g["post_md5"], f"seed {seed}: output pictures differ from the reference"
+
+
+def test_golden_streams_cover_the_syntax():
+    """the point of the synthetic set is coverage; fail if the generator stops producing it"""
+    import ctypes as C
+    rec = np.dtype([("mbType", "u1"), ("pad0", "u1", 14), ("sub", "u1"), ("refSlot", "u1", 4), ("icm", "u1"), ("idc", "u1"),
+                    ("sliceId", "<u2"), ("refIdx", "u1", 4), ("pad1", "u1", 4), ("mv", "<i2", (16, 2))])
+    assert rec.itemsize == 96
+    types, subs, modes, idcs = set(), set(), set(), set()
+    multi_ref = multi_slice = far_mv = reordered = 0
+    for seed in SEEDS[:60]:
+        ps = ParsedStream(synth_h264.make_stream(seed))
+        t = ps.ptr.contents
+        a = np.frombuffer(C.string_at(t.mbRecs, t.mbRecBytes), rec)
+        types |= set(np.unique(a["mbType"]).tolist())
+        p8 = a[(a["mbType"] == 4) | (a["mbType"] == 5)]
+        for q in range(4):
+            subs |= set(np.unique((p8["sub"] >> (2 * q)) & 3).tolist())
+        i4 = a[a["mbType"] == 6]
+        modes |= set(np.unique(i4["mv"].view("u1").reshape(len(i4), 64)[:, :16]).tolist())
+        idcs |= set(np.unique(a["idc"]).tolist())
+        inter = a[a["mbType"] <= 5]
+        multi_ref += int((inter["refIdx"] > 0).any(axis=1).sum())
+        far_mv += int((np.abs(inter["mv"][:, :, 0]) > 1000).any(axis=1).sum())
+        n = ps.mbs_per_pic
+        multi_slice += sum(1 for k in range(ps.num_pics) if len(np.unique(a["sliceId"][k * n:(k + 1) * n])) > 1)
+        reordered += int(ps.outputs != sorted(ps.outputs))
+        ps.close()
+    assert types == set(range(32)), sorted(set(range(32)) - types)
+    assert subs == {0, 1, 2, 3} and modes == set(range(9)) and idcs == {0, 1, 2}
+    assert multi_ref > 50 and multi_slice > 50 and far_mv > 50 and reordered > 0
+
+
+@pytest.mark.skipif(_oracle.reference() is None, reason="oracle/_ref not built (needs the reference sources)")
+def test_fresh_seeds_against_the_compiled_reference():
+    """seeds outside the golden file, decoded by the reference here and now"""
+    from make_synth_golden import reference_decode
+    for seed in range(10_000, 10_120):
+        data = synth_h264.make_stream(seed)
+        n, fb, rpost, rpre, ndec, dims = reference_decode(data)
+        assert n >= 0, f"seed {seed}: reference decode error (generator bug)"
+        n_out, n_dec, odims, post, pre = decode_with_oracle(data)
+        assert (n_out, n_dec, odims) == (n, ndec, dims), f"seed {seed}"
+        assert np.array_equal(pre, rpre), f"seed {seed}: pre-filter pictures"
+        assert np.array_equal(post, rpost), f"seed {seed}: output pictures"

@@ -1,0 +1,63 @@
+"""GPU suite, part two: the CUDA engine on the synthetic streams of tests/synth_h264.py (every macroblock type and
+partition shape, several reference frames, vectors far outside the picture, I_PCM, FMO / ASO slice orders, pictures
+down to one macroblock), through the C-ABI, against the committed md5s of the reference decoder and -- picture by
+picture, before and after the in-loop filter -- against the CPU oracle.  Bit-exact or fail."""
+import hashlib
+import json
+import os
+import numpy as np
+import pytest
+import _oracle
+import synth_h264
+from h264bsd_b200.batch import Batch, ParsedStream
+from h264bsd_b200.decoder import decode_stream
+
+pytestmark = pytest.mark.gpu
+
+GOLD = json.load(open(os.path.join(_oracle.GOLDEN, "synth_md5.json")))
+SEEDS = sorted(int(s) for s in GOLD)
+
+
+def _stream(seed):
+    data = synth_h264.make_stream(seed)
+    if hashlib.md5(data).hexdigest() != GOLD[str(seed)]["stream_md5"]:
+        pytest.skip("generator drifted from tests/golden/synth_md5.json: re-run tests/make_synth_golden.py")
+    return data
+
+
+@pytest.mark.parametrize("chunk", range(8))
+def test_batched_engine_matches_oracle_picture_by_picture(chunk):
+    """two instances of every stream; each picture after reconstruction and after the filter equals the oracle's"""
+    for seed in SEEDS[chunk::8]:
+        ps = ParsedStream(_stream(seed))
+        assert ps.status == 0
+        orc = _oracle.OracleDecoder(ps)
+        b = Batch(2, ps.width_mbs, ps.height_mbs, ps.num_slots)
+        b.upload(0, ps)
+        b.replicate(0)
+        for k in range(ps.num_pics):
+            slot = ps.pics[k].curSlot
+            b.debug_stage(k, True, False)
+            orc.recon(k)
+            assert np.array_equal(b.read_frame(1, slot), orc.frame(slot)), f"seed {seed}: reconstruction of picture {k}"
+            b.debug_stage(k, False, True)
+            orc.deblock(k)
+            assert np.array_equal(b.read_frame(1, slot), orc.frame(slot)), f"seed {seed}: in-loop filter of picture {k}"
+            assert b.compare_streams([slot, slot]) == 0, f"seed {seed}: the two instances differ at picture {k}"
+        assert b.idct_errors() == 0 and b.watchdog() == (0, 0), f"seed {seed}"
+        b.close()
+        orc.close()
+        ps.close()
+
+
+@pytest.mark.parametrize("chunk", range(4))
+def test_legacy_api_matches_reference_golden(chunk):
+    """h264bsdInit/Decode/NextOutputPicture over the synthetic streams: output pictures, output order"""
+    for seed in SEEDS[chunk::4]:
+        g = GOLD[str(seed)]
+        frames = decode_stream(_stream(seed))
+        assert len(frames) == g["outputs"], f"seed {seed}"
+        h = hashlib.md5()
+        for f in frames:
+            h.update(np.ascontiguousarray(f).tobytes())
+        assert h.hexdigest() == g["post_md5"], f"seed {seed}: output pictures differ from the reference"
