@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(kDeblockWarps * 32, 4) deblockKernel(const Deb
                 const uint32_t mb = p.order[k];
                 const size_t sIdx = (size_t)s * g.nMbs;
                 if (p.work[sIdx + mb]) {   // else nothing to filter: this macroblock touches no pel
-                    const int mby = (int)__umulhi(mb, g.invWidthMbs), mbx = (int)(mb - (uint32_t)mby * g.widthMbs);
+                    const int mby = mbRowOf(mb, g), mbx = (int)(mb - (uint32_t)mby * g.widthMbs);
                     const StreamJob job = p.jobs[s];
                     const uint32_t *cw = reinterpret_cast<const uint32_t *>(job.recs + mb);
                     mW0 = __ldg(cw); mW3 = __ldg(cw + 3);
@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(kDeblockWarps * 32, 4) deblockKernel(const Deb
             bw.z = __shfl_sync(0xffffffffu, mBw.z, j); bw.w = __shfl_sync(0xffffffffu, mBw.w, j);
             uint8_t *frame = p.pool + __shfl_sync(0xffffffffu, mFrame, j);
             const size_t sIdx = (size_t)s * g.nMbs;
-            const int mby = (int)__umulhi(mb, g.invWidthMbs), mbx = (int)(mb - (uint32_t)mby * g.widthMbs);
+            const int mby = mbRowOf(mb, g), mbx = (int)(mb - (uint32_t)mby * g.widthMbs);
             uint32_t *doneS = p.done + sIdx;
             const int qp = (w0 >> 8) & 0xFF, qpL = qpn & 0xFF, qpT = (qpn >> 8) & 0xFF;
             if (lane < 3 && ((workBits >> (lane + 1)) & 1)) {

@@ -110,7 +110,7 @@ bool Batch::create(int device, uint32_t nStreams, uint32_t widthMbs, uint32_t he
     g.offCr = g.offCb + (unsigned long long)g.pitchC * g.rowsC;
     g.frameStride = (g.offCr + (unsigned long long)g.pitchC * g.rowsC + 255) & ~255ull;
     g.numSlots = (int)numSlots; g.nStreams = (int)nStreams;
-    g.invWidthMbs = (unsigned)((0x100000000ull + widthMbs - 1) / widthMbs);
+    g.invWidthMbs = (unsigned)((0x80000000ull + widthMbs - 1) / widthMbs);
     const unsigned long long nFrames = (unsigned long long)nStreams * numSlots;
     CK(cudaMalloc(&pool_, nFrames * g.frameStride));
     CK(cudaMemsetAsync(pool_, 128, nFrames * g.frameStride, stream_));

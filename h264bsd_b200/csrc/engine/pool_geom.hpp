@@ -23,7 +23,8 @@ struct PoolGeom {
     unsigned long long offCb, offCr;   // plane offsets inside a frame
     unsigned long long frameStride;
     int numSlots, nStreams;
-    unsigned invWidthMbs;     // ceil(2^32 / widthMbs): mb / widthMbs == __umulhi(mb, invWidthMbs) for mb < 65536
+    unsigned invWidthMbs;     // ceil(2^31 / widthMbs): mb / widthMbs == __umulhi(2 * mb + 1, invWidthMbs) for mb < 65536 and every
+                              // width from 1 (see mbRowOf in device_common.cuh)
 };
 
 // what one stream contributes to one launch (one picture)

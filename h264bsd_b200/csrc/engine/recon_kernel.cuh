@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(kCopyWarps * 32) reconCopyKernel(const ReconPa
                 const uint32_t mb = __ldg(job.order + 2u * (e0 + lane));   // (address, length) pairs
                 mLen = __ldg(job.order + 2u * (e0 + lane) + 1u);
                 const uint32_t refSlots = __ldg(reinterpret_cast<const uint32_t *>(job.recs + mb) + 4);
-                const int mby = (int)__umulhi(mb, g.invWidthMbs), mbx = (int)(mb - (uint32_t)mby * g.widthMbs);
+                const int mby = mbRowOf(mb, g), mbx = (int)(mb - (uint32_t)mby * g.widthMbs);
                 mOff = (uint32_t)((mby * 16 + kPadY) * g.pitchY + mbx * 16 + kPadY);
                 mOffC = (uint32_t)((mby * 8 + kPadC) * g.pitchC + mbx * 8 + kPadC);
                 mDelta = ((long long)(refSlots & 0xFF) - (long long)job.curSlot) * (long long)g.frameStride;
@@ -508,7 +508,7 @@ __global__ void __launch_bounds__(kCopyWarps * 32) reconCopyKernel(const ReconPa
             const uint32_t *rw = reinterpret_cast<const uint32_t *>(job.recs + mMb);
             const uint32_t refSlots = __ldg(rw + 4), mvv = __ldg(rw + 8);
             const int mvx = (int)(int16_t)(mvv & 0xFFFF), mvy = (int)(int16_t)(mvv >> 16);
-            const int mby = (int)__umulhi(mMb, g.invWidthMbs), mbx = (int)(mMb - (uint32_t)mby * g.widthMbs);
+            const int mby = mbRowOf(mMb, g), mbx = (int)(mMb - (uint32_t)mby * g.widthMbs);
             const int x = clip3(-kPadY, g.W + kPadY - 16, mbx * 16 + (mvx >> 2)), y = clip3(-kPadY, g.H + kPadY - 16, mby * 16 + (mvy >> 2));
             const int cx = clip3(-kPadC, g.W / 2 + kPadC - 8, mbx * 8 + (mvx >> 3)), cy = clip3(-kPadC, g.H / 2 + kPadC - 8, mby * 8 + (mvy >> 3));
             const unsigned long long ref = (unsigned long long)(frameBase + (refSlots & 0xFF)) * g.frameStride;
@@ -543,7 +543,7 @@ __global__ void __launch_bounds__(kCopyWarps * 32) reconCopyKernel(const ReconPa
 #pragma unroll
             for (int u = 0; u < kCopyUnroll; u++) {
                 const uint32_t mb = mbs[u];
-                const int mby = (int)__umulhi(mb, g.invWidthMbs), mbx = (int)(mb - (uint32_t)mby * g.widthMbs);
+                const int mby = mbRowOf(mb, g), mbx = (int)(mb - (uint32_t)mby * g.widthMbs);
                 *reinterpret_cast<uint2 *>(lumaAt(cur, g, mbx * 16 + c8, mby * 16 + r8)) = pv[u];
                 *reinterpret_cast<uint32_t *>(chromaAt(cur, g, cp, mbx * 8 + cc, mby * 8 + cr)) = pc[u];
             }
@@ -633,7 +633,7 @@ reconInterKernel(const ReconParams p, const __grid_constant__ CUtensorMap lumaMa
         if (it.single) {
             const uint32_t mvv = m[5], refSlots = m[4];
             it.mvx = (int)(int16_t)(mvv & 0xFFFF); it.mvy = (int)(int16_t)(mvv >> 16);
-            const int mby = (int)__umulhi(it.mb, g.invWidthMbs), mbx = (int)(it.mb - (uint32_t)mby * g.widthMbs);
+            const int mby = mbRowOf(it.mb, g), mbx = (int)(it.mb - (uint32_t)mby * g.widthMbs);
             issueWindow(sm, buf, g, &lumaMap, &chromaMap, mbx * 16 + (it.mvx >> 2), mby * 16 + (it.mvy >> 2),
                         mbx * 8 + (it.mvx >> 3), mby * 8 + (it.mvy >> 3), frameBase + (refSlots & 0xFF), lane, &it.ox, &it.cox);
         }
@@ -648,7 +648,7 @@ reconInterKernel(const ReconParams p, const __grid_constant__ CUtensorMap lumaMa
         if (i + 1 < n) nxt = prepare(i + 1, buf ^ 1);   // the other buffer's previous user finished before this point
         const MbHead &h = it.h;
         const uint32_t mb = it.mb;
-        const int mby = (int)__umulhi(mb, g.invWidthMbs), mbx = (int)(mb - (uint32_t)mby * g.widthMbs);
+        const int mby = mbRowOf(mb, g), mbx = (int)(mb - (uint32_t)mby * g.widthMbs);
         const b200_mb_rec *rec = job.recs + mb;
         const int16_t *coef = job.coefs + (size_t)h.coefIndex * 16;
         uint8_t *dstY = lumaAt(cur, g, mbx * 16 + c8, mby * 16 + r8);
