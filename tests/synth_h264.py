@@ -484,8 +484,9 @@ class PictureWriter:
                 "cac": 16000 // (29 << (qpc // 6)), "cdc": (16000 * 2) // (18 << (qpc // 6))}
 
     # -- one slice
-    def write_slice(self, bw, mbs, is_p, qp, num_ref_active, refs_avail):
-        """slice_data() for the macroblocks `mbs` (decoding order); returns nothing, updates the model"""
+    def write_slice(self, bw, mbs, is_p, qp, num_ref_active, valid_refs):
+        """slice_data() for the macroblocks `mbs` (decoding order); updates the model.  valid_refs: the ref_idx values that
+        point at a real picture (None: none does -> no inter prediction in this slice)"""
         r = self.r
         self.slice_counter += 1
         sid = self.slice_counter
@@ -493,7 +494,7 @@ class PictureWriter:
         wrote_any = False
         i = 0
         n = len(mbs)
-        p_skip_prob = r.choice([0.0, 0.2, 0.5, 0.8]) if is_p else 0
+        p_skip_prob = r.choice([0.0, 0.2, 0.5, 0.8]) if (is_p and valid_refs and 0 in valid_refs) else 0
         while i < n:
             a = mbs[i]
             m = self.mb[a]
@@ -506,7 +507,7 @@ class PictureWriter:
             if is_p:
                 bw.ue(skip_run)
                 skip_run = 0
-            qp = self._coded_mb(bw, a, sid, is_p, qp, num_ref_active, refs_avail)
+            qp = self._coded_mb(bw, a, sid, is_p, qp, num_ref_active, valid_refs)
             wrote_any = True
             i += 1
         if is_p and skip_run:
@@ -538,12 +539,12 @@ class PictureWriter:
             out[w] = n
         return out
 
-    def _coded_mb(self, bw, a, sid, is_p, qp, num_ref_active, refs_avail):
+    def _coded_mb(self, bw, a, sid, is_p, qp, num_ref_active, valid_refs):
         r = self.r
         m = self.mb[a]
         mbx, mby = a % self.W, a // self.W
         off = 5 if is_p else 0
-        if is_p and r.random() < self.k["p_inter"]:
+        if is_p and valid_refs and r.random() < self.k["p_inter"]:
             kind = INTER
         else:
             c = r.random()
@@ -565,14 +566,13 @@ class PictureWriter:
             return qp     # QP'Y of an I_PCM macroblock is 0 for the filter, the running QP is unchanged
         if kind == INTER:
             shape = r.choice([0, 0, 1, 2, 3, 3, 4]) if num_ref_active >= 1 else 0
-            if shape == 4 and r.random() < 0.5:
+            if shape == 4 and (r.random() < 0.5 or 0 not in valid_refs):
                 shape = 3
             bw.ue(shape)
             m.kind = INTER
-            nref = min(num_ref_active, refs_avail)
 
             def pick_ref():
-                return 0 if nref <= 1 or r.random() < 0.5 else r.randrange(nref)
+                return valid_refs[0] if r.random() < 0.5 else r.choice(valid_refs)
 
             def put_ref(v):
                 if num_ref_active > 1:
@@ -867,9 +867,94 @@ def random_fmo(r, W, H, allow):
 
 
 # ---------------------------------------------------------------------------------------------- stream
+def _picnum(f, frame_num, max_fn):
+    return f["fn"] if f["fn"] <= frame_num else f["fn"] - max_fn
+
+
+def _sliding_window(refs, nrf, frame_num, max_fn):
+    """8.2.5.3: with all reference frames in use the short-term frame with the smallest FrameNumWrap goes"""
+    if len(refs) >= max(nrf, 1):
+        st = [f for f in refs if f["lt"] is None]
+        if st:
+            refs.remove(min(st, key=lambda f: _picnum(f, frame_num, max_fn)))
+
+
+def _random_mmco(r, refs, max_lt, nrf, frame_num, max_fn, must_drop=()):
+    """memory_management_control_operation list (7.3.3.3 / 8.2.5.4) that leaves room for the current picture and
+    un-marks the short-term frames `must_drop`.  Returns (ops, refs after them, max long-term index after them,
+    long-term index of the current picture or None, had operation 5)."""
+    keep = [f for f in refs if not any(f is d for d in must_drop)]
+    ops = [(1, frame_num - _picnum(f, frame_num, max_fn) - 1) for f in must_drop]
+    refs = [dict(f) for f in keep]
+    cur_lt = None
+    had5 = False
+    while len(refs) >= max(nrf, 1):          # room for the current picture (none of the operations below adds a frame)
+        f = r.choice(refs)
+        ops.append((1, frame_num - _picnum(f, frame_num, max_fn) - 1) if f["lt"] is None else (2, f["lt"]))
+        refs.remove(f)
+
+    def drop_lt(idx):
+        for f in [f for f in refs if f["lt"] == idx]:
+            refs.remove(f)
+
+    for _ in range(r.randint(1, 4)):
+        st = [f for f in refs if f["lt"] is None]
+        lt = [f for f in refs if f["lt"] is not None]
+        # the reference accepts at most one each of operations 4, 5, 6 and not 5 together with 1..3
+        # (h264bsd_slice_header.c:697-699)
+        kinds = [o[0] for o in ops]
+        choices = [] if 4 in kinds else [4]
+        if not had5:
+            st_real = [f for f in st if not f.get("ne")]      # (a gap filler cannot become a long-term frame)
+            choices += [1] * bool(st) + [2] * bool(lt) + [3] * bool(st_real and max_lt is not None)
+            if r.random() < 0.15 and not ops and frame_num != 1:   # operation 5 only as the first one: what it does to a picture
+                choices.append(5)                        # that operation 6 has already marked is not worth guessing;
+                # not with frame_num 1: the next picture has frame_num 1 again and the reference tells pictures apart by
+                # frame_num / POC syntax / nal_ref_idc only, not by pic_parameter_set_id (h264bsd_storage.c:626-745)
+        if max_lt is not None and cur_lt is None:
+            choices.append(6)
+        if not choices:
+            break
+        op = r.choice(choices)
+        if op == 1:
+            f = r.choice(st)
+            ops.append((1, frame_num - _picnum(f, frame_num, max_fn) - 1))
+            refs.remove(f)
+        elif op == 2:
+            f = r.choice(lt)
+            ops.append((2, f["lt"]))
+            refs.remove(f)
+        elif op == 3:
+            f = r.choice(st_real)
+            idx = r.randint(0, max_lt)
+            ops.append((3, frame_num - _picnum(f, frame_num, max_fn) - 1, idx))
+            for g in [g for g in refs if g["lt"] == idx and g is not f]:
+                refs.remove(g)
+            f["lt"] = idx
+        elif op == 4:
+            v = r.randint(0, min(nrf, 3))
+            ops.append((4, v))
+            for g in [g for g in refs if g["lt"] is not None and g["lt"] >= v]:
+                refs.remove(g)
+            max_lt = v - 1 if v else None
+        elif op == 5:
+            ops.append((5,))
+            refs.clear()
+            max_lt = None
+            had5 = True
+            frame_num = 0
+        else:
+            idx = r.randint(0, max_lt)
+            ops.append((6, idx))
+            drop_lt(idx)
+            cur_lt = idx
+            break
+    return ops, refs, max_lt, cur_lt, had5
+
+
 def make_stream(seed, **force):
     """One random valid stream.  `force` overrides knobs: W, H, pictures, fmo (bool), multi_slice (bool), aso (bool),
-    num_ref_frames, poc_type, i_only (bool), p_skip (float), dense (float), vui (bool)."""
+    num_ref_frames, poc_type, i_only (bool), dense (float), vui (bool), mmco (bool), gaps (bool), redundant (bool)."""
     r = random.Random(seed)
     out = bytearray()
 
@@ -888,15 +973,14 @@ def make_stream(seed, **force):
            "poc_type": force.get("poc_type", r.choice([0, 0, 1, 2, 2])), "log2_max_poc_lsb": r.choice([4, 5, 8, 16]),
            "delta_always_zero": r.randint(0, 1), "offset_non_ref": r.randint(-3, 3), "offset_top_bottom": r.randint(-2, 2),
            "offset_ref_frame": [r.randint(1, 6) for _ in range(r.randint(0, 3))],
-           "num_ref_frames": nrf, "gaps_allowed": 0, "W": W, "H": H, "dpb_size": dpb_size,
-           "vui": force.get("vui", r.random() < 0.4), "crop": None}
+           "num_ref_frames": nrf, "gaps_allowed": 1 if (nrf >= 1 and force.get("gaps", r.random() < 0.2)) else 0,
+           "W": W, "H": H, "dpb_size": dpb_size, "vui": force.get("vui", r.random() < 0.4), "crop": None}
     if r.random() < 0.4:
         cl, cr_ = r.randint(0, 3), r.randint(0, 3)
         ct, cb = r.randint(0, 3), r.randint(0, 3)
         if cl + cr_ < 8 * W and ct + cb < 8 * H:
             sps["crop"] = (cl, cr_, ct, cb)
     out += write_sps(r, sps)
-    dpb_size = sps["dpb_size"]          # (the bitstream restriction may have lowered it)
     max_fn = 1 << sps["log2_max_frame_num"]
 
     # ---- picture parameter sets
@@ -906,7 +990,7 @@ def make_stream(seed, **force):
         pps = {"id": pid, "sps_id": sps["id"], "pic_order_present": r.randint(0, 1), "fmo": random_fmo(r, W, H, allow_fmo),
                "num_ref_idx_default": r.randint(1, 4), "pic_init_qp": r.randint(10, 45), "chroma_qp_offset": r.randint(-12, 12),
                "deblock_ctrl": r.randint(0, 1), "constrained_intra": 1 if r.random() < 0.3 else 0,
-               "redundant_present": 0}
+               "redundant_present": 1 if force.get("redundant", r.random() < 0.25) else 0}
         ppss.append(pps)
         out += write_pps(r, pps, size)
 
@@ -914,40 +998,47 @@ def make_stream(seed, **force):
     n_pics = force.get("pictures") or r.randint(2, 9)
     if sps["log2_max_frame_num"] == 4 and r.random() < 0.3 and size <= 12:
         n_pics = r.randint(18, 40)                 # frame_num wraps around
-    short = []          # reference frames: dicts {fn, lt}  (lt = long-term index or None)
+    use_mmco = nrf >= 2 and force.get("mmco", r.random() < 0.4)
+    refs = []           # reference frames in the DPB: {fn: frame_num, lt: long-term index or None, ne: "non-existing" (gap filler)}
+    max_lt = None       # MaxLongTermFrameIdx ("no long-term frame indices" = None)
     prev_ref_fn = 0
-    frame_num = 0
     idr_id = r.randint(0, 100)
-    poc_base = 0        # type 0: POC counter since the last IDR
+    poc_base = 0        # POC type 0: highest POC since the last IDR / operation 5
+    poc_seen = []
     prev_was_nonref = False
+    after5 = False      # the previous picture carried memory_management_control_operation 5
     knobs = {"p_inter": r.choice([0.5, 0.8, 0.95, 1.0]), "pcm": r.choice([0, 0.02, 0.1]),
              "dense": force.get("dense", r.choice([0.0, 0.1, 0.5])), "qp_lo": None, "qp_hi": None}
     if r.random() < 0.35:
         knobs["qp_lo"], knobs["qp_hi"] = r.choice([(0, 12), (20, 35), (40, 51), (0, 51)])
-    poc_order = []
     for pic in range(n_pics):
         idr = pic == 0 or (r.random() < 0.1)
-        refs = [f for f in short]
-        can_p = (not idr) and (not i_only) and len(refs) > 0
-        is_ref = True if idr else (nrf > 0 and (r.random() < 0.8 or prev_was_nonref or sps["poc_type"] == 2 and prev_was_nonref))
-        if nrf == 0:
-            is_ref = idr     # (an IDR picture always has nal_ref_idc != 0)
+        is_ref = True if idr else (nrf > 0 and (r.random() < 0.8 or prev_was_nonref))
         pps = r.choice(ppss)
+        gap = 0
         if idr:
             frame_num = 0
             idr_id = (idr_id + 1) % 65536
             poc_base = 0
-            poc_order = []
+            poc_seen = []
         else:
-            frame_num = (prev_ref_fn + 1) % max_fn
-        # reference list of this picture (8.2.4.2.1): short-term by PicNum descending, long-term by index ascending
-        def picnum(f):
-            return f["fn"] if f["fn"] <= frame_num else f["fn"] - max_fn
-        st = sorted([f for f in refs if f["lt"] is None], key=picnum, reverse=True)
+            st_now = [f for f in refs if f["lt"] is None]
+            if sps["gaps_allowed"] and r.random() < 0.3 and (st_now or len(refs) < nrf) and not after5:
+                gap = r.randint(1, 3)
+            # the decoder fills a gap in frame_num with "non-existing" short-term frames, sliding window each (8.2.5.2)
+            for g in range(gap):
+                fn = (prev_ref_fn + 1 + g) % max_fn
+                _sliding_window(refs, nrf, fn, max_fn)
+                refs.append({"fn": fn, "lt": None, "ne": True})
+            frame_num = (prev_ref_fn + 1 + gap) % max_fn
+        can_p = (not idr) and (not i_only) and any(not f.get("ne") for f in refs)
+
+        # initial reference list (8.2.4.2.1): short-term by PicNum descending, long-term by index ascending
+        st = sorted([f for f in refs if f["lt"] is None], key=lambda f: _picnum(f, frame_num, max_fn), reverse=True)
         lt = sorted([f for f in refs if f["lt"] is not None], key=lambda f: f["lt"])
         init_list = st + lt
 
-        # slices: split every slice group's macroblocks (raster order) into runs
+        # slices: every slice group's macroblocks (raster order) cut into runs
         fmo = pps["fmo"]
         cycle = 0
         if fmo["groups"] > 1 and fmo["type"] in (3, 4, 5):
@@ -963,29 +1054,39 @@ def make_stream(seed, **force):
                 mbs = mbs[k:]
         if force.get("aso", r.random() < 0.3):
             r.shuffle(slices)
-        # POC
-        if sps["poc_type"] == 0:
-            if r.random() < 0.25 and not idr:
-                poc = poc_base + 2 * r.choice([1, 2, 3])          # leaves gaps that a later picture may fill
-            else:
-                poc = poc_base + 2
-            lower = [p for p in range(2, poc, 2) if p not in poc_order]
-            if lower and r.random() < 0.3 and not idr:
+        # POC type 0: mostly ascending, sometimes out of decoding order (output reordering)
+        poc = 0
+        if sps["poc_type"] == 0 and not idr:
+            poc = poc_base + 2 * (r.choice([1, 2, 3]) if r.random() < 0.25 else 1)
+            lower = [p for p in range(2, poc, 2) if p not in poc_seen]
+            if lower and r.random() < 0.3:
                 poc = r.choice(lower[-2:])
-            if idr:
-                poc = 0
-            poc_order.append(poc)
-            poc_base = max(poc_base, poc)
+        poc_seen.append(poc)
+        poc_base = max(poc_base, poc)
         poc1_delta = r.choice([0, 0, 0, 2, 4])
-        pw = PictureWriter(r, W, H, pps, knobs)
-        pic_qp_delta_base = None
+        # decoded reference picture marking, the same in every slice header of the picture
         lt_idr = idr and nrf >= 2 and r.random() < 0.3
         no_out = r.randint(0, 1)
-        for mbs in slices:
+        mmco = None
+        # a short-term frame that sliding-window marking would long have dropped must go before frame_num comes round to
+        # its own value again (frame numbers of the reference frames are distinct, 7.4.3)
+        stale = [f for f in refs if f["lt"] is None and 0 < (f["fn"] - frame_num) % max_fn <= 4] if not idr else []
+        if stale:
+            is_ref = True
+        # sliding-window marking needs a short-term frame to drop when all reference frames are in use (8.2.5.3)
+        no_slide = len(refs) >= max(nrf, 1) and not any(f["lt"] is None for f in refs)
+        if is_ref and not idr and ((use_mmco and r.random() < 0.5) or stale or no_slide):
+            mmco = _random_mmco(r, refs, max_lt, nrf, frame_num, max_fn, stale)
+        pw = PictureWriter(r, W, H, pps, knobs)
+        if "trace" in force:
+            force["trace"].append(dict(pic=pic, idr=idr, ref=is_ref, frame_num=frame_num, poc=poc, refs=[dict(f) for f in refs],
+                                       mmco=mmco[0] if mmco else None, slices=len(slices), pps=pps["id"]))
+
+        def emit_slice(mbs, redundant_cnt):
             is_p = can_p and r.random() < 0.8
             bw = BitWriter()
             bw.ue(mbs[0])
-            bw.ue((0 if is_p else 2) + (5 if (r.random() < 0.2 and len(slices) == 1) else 0))
+            bw.ue((0 if is_p else 2) + (5 if (r.random() < 0.2 and len(slices) == 1 and not pps["redundant_present"]) else 0))
             bw.ue(pps["id"])
             bw.u(sps["log2_max_frame_num"], frame_num)
             if idr:
@@ -1000,6 +1101,8 @@ def make_stream(seed, **force):
                 bw.se(max(0, -sps["offset_top_bottom"]) if idr else poc1_delta)
                 if pps["pic_order_present"]:
                     bw.se(0)
+            if pps["redundant_present"]:
+                bw.ue(redundant_cnt)
             num_active = pps["num_ref_idx_default"]
             cur_list = list(init_list)
             if is_p:
@@ -1010,14 +1113,14 @@ def make_stream(seed, **force):
                 else:
                     bw.u(1, 0)
                 # ref_pic_list_reordering (7.3.3.1 / 8.2.4.3)
-                if r.random() < 0.4 and len(init_list) >= 1 and num_active <= len(init_list):
+                real = [f for f in init_list if not f.get("ne")]       # (a gap filler cannot be named, h264bsd_dpb.c:288)
+                if r.random() < 0.4 and num_active <= len(init_list) and real:
                     bw.u(1, 1)
                     pred = frame_num
-                    idx = 0
-                    for _ in range(r.randint(1, min(num_active, 3))):
-                        f = r.choice(init_list)
+                    for idx in range(r.randint(1, min(num_active, 3))):
+                        f = r.choice(real)
                         if f["lt"] is None:
-                            pn = picnum(f)
+                            pn = _picnum(f, frame_num, max_fn)
                             diff = pred - pn
                             if diff > 0:
                                 bw.ue(0); bw.ue(diff - 1)
@@ -1028,10 +1131,8 @@ def make_stream(seed, **force):
                             pred = pn
                         else:
                             bw.ue(2); bw.ue(f["lt"])
-                        # the chosen picture moves to position idx, the others shift (the list has one spare entry)
-                        tmp = cur_list[:idx] + [f] + [g for g in cur_list[idx:] if g is not f]
-                        cur_list = tmp
-                        idx += 1
+                        # the chosen picture moves to position idx, the rest shifts back
+                        cur_list = cur_list[:idx] + [f] + [g for g in cur_list[idx:] if g is not f]
                     bw.ue(3)
                 else:
                     bw.u(1, 0)
@@ -1039,6 +1140,12 @@ def make_stream(seed, **force):
                 if idr:
                     bw.u(1, no_out)
                     bw.u(1, 1 if lt_idr else 0)
+                elif mmco:
+                    bw.u(1, 1)
+                    for op in mmco[0]:
+                        for v in op:
+                            bw.ue(v)
+                    bw.ue(0)
                 else:
                     bw.u(1, 0)          # sliding window
             qp_target = r.randint(max(0, pps["pic_init_qp"] - 10), min(51, pps["pic_init_qp"] + 6))
@@ -1056,24 +1163,53 @@ def make_stream(seed, **force):
                 while (1 << nbits) * fmo["rate"] < size + fmo["rate"]:
                     nbits += 1
                 bw.u(nbits, cycle)
-            refs_avail = min(len(cur_list), num_active) if is_p else 0
-            pw.write_slice(bw, mbs, is_p, qp_target, num_active, refs_avail)
-            out += nal((r.choice([1, 2, 3]) if is_ref else 0), 5 if idr else 1, bw.out)
-        # decoded reference picture marking
+            valid = [i for i in range(min(num_active, len(cur_list))) if not cur_list[i].get("ne")] if is_p else []
+            if is_p and not valid:
+                valid = None        # no usable entry in this list order: P_Skip / inter would fail -> intra macroblocks only
+            pw.write_slice(bw, mbs, is_p, qp_target, num_active, valid)
+            return nal((r.choice([1, 2, 3]) if is_ref else 0), 5 if idr else 1, bw.out)
+
+        dropped = None
+        if pps["redundant_present"] and len(slices) > 1 and r.random() < 0.6:
+            dropped = r.randrange(len(slices))          # this primary slice is "lost"; a redundant one stands in
+        for i, mbs in enumerate(slices):
+            if i != dropped:
+                out += emit_slice(mbs, 0)
+        if pps["redundant_present"]:
+            extra = []
+            if dropped is not None:
+                if force.get("redundant_overlap"):
+                    # macroblocks decoded a second time while the picture is still incomplete: the reference keeps the pels
+                    # of the first decode but filters with the state of the second (h264bsd_macroblock_layer.c:1003-1007,
+                    # :1108-1111); the tape has one record per macroblock -- documented deviation, off by default
+                    extra = [slices[i] for i in range(len(slices)) if i != dropped and r.random() < 0.4]
+                extra.append(slices[dropped])
+            extra += [mbs for mbs in slices if r.random() < 0.3]     # after the picture is complete: skipped
+            for mbs in extra:
+                out += emit_slice(mbs, r.randint(1, 3))
+
+        # decoded reference picture marking (8.2.5)
         if idr:
-            short = []
-        if is_ref:
-            if idr and lt_idr:
-                short.append({"fn": frame_num, "lt": 0})
+            refs = []
+            max_lt = 0 if lt_idr else None
+            refs.append({"fn": 0, "lt": 0 if lt_idr else None})
+            prev_ref_fn = 0
+        elif is_ref:
+            if mmco:
+                _, refs, max_lt, cur_lt, had5 = mmco
+                refs.append({"fn": 0 if had5 else frame_num, "lt": cur_lt})
+                prev_ref_fn = 0 if had5 else frame_num
+                if had5:
+                    poc_base = 0
+                    poc_seen = [0]
             else:
-                if not idr and len(short) >= max(nrf, 1):
-                    st_only = [f for f in short if f["lt"] is None]
-                    if st_only:
-                        victim = min(st_only, key=picnum)
-                        short = [f for f in short if f is not victim]
-                short.append({"fn": frame_num, "lt": None})
-            prev_ref_fn = frame_num
+                _sliding_window(refs, nrf, frame_num, max_fn)
+                refs.append({"fn": frame_num, "lt": None})
+                prev_ref_fn = frame_num
+        elif gap:
+            prev_ref_fn = (frame_num - 1) % max_fn       # the last gap filler is the "previous reference frame" now (8.2.5.2)
         prev_was_nonref = not is_ref
+        after5 = bool(mmco and mmco[4])
         if r.random() < 0.05:
             out += nal(0, 9, bytes([0x10]))          # access unit delimiter
         if r.random() < 0.05:
