@@ -27,10 +27,10 @@ public:
         unsigned sh = (unsigned)(pos_ & 7);
         uint64_t v = 0;
         if (byte + 8 <= size_) {
-            const uint8_t *q = p_ + byte;
-            v = ((uint64_t)q[0] << 56) | ((uint64_t)q[1] << 48) | ((uint64_t)q[2] << 40) |
-                ((uint64_t)q[3] << 32) | ((uint64_t)q[4] << 24) | ((uint64_t)q[5] << 16) |
-                ((uint64_t)q[6] << 8) | (uint64_t)q[7];
+            __builtin_memcpy(&v, p_ + byte, 8);     // one unaligned load, bytes to MSB-first order
+#if __BYTE_ORDER__ == __ORDER_LITTLE_ENDIAN__
+            v = __builtin_bswap64(v);
+#endif
         } else {
             for (unsigned i = 0; i < 8; i++) {
                 uint64_t b = (byte + i < size_) ? p_[byte + i] : 0;
@@ -40,6 +40,24 @@ public:
         return (uint32_t)((v << sh) >> 32);
     }
     uint32_t show(unsigned n) const { return n ? show32() >> (32 - n) : 0; }
+    // the stream from bit position `bitpos` on, MSB first: at least 57 bits are stream bits (zero past the end), the rest 0
+    uint64_t window(uint64_t bitpos) const {
+        const uint64_t byte = bitpos >> 3;
+        uint64_t v = 0;
+        if (byte + 8 <= size_) {
+            __builtin_memcpy(&v, p_ + byte, 8);
+#if __BYTE_ORDER__ == __ORDER_LITTLE_ENDIAN__
+            v = __builtin_bswap64(v);
+#endif
+        } else {
+            for (unsigned i = 0; i < 8; i++) {
+                uint64_t b = (byte + i < size_) ? p_[byte + i] : 0;
+                v |= b << (56 - 8 * i);
+            }
+        }
+        return v << (bitpos & 7);
+    }
+    uint64_t bitsTotal() const { return bitsTotal_; }
 
     // h264bsdFlushBits: returns false when the read crossed the end of the NAL
     bool skip(unsigned n) {

@@ -89,8 +89,13 @@ const uint8_t kRunCode[7][15] = {{1, 0},
                                  {3, 0, 1, 3, 2, 5, 4},
                                  {7, 6, 5, 4, 3, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1}};
 
-// ---- expanded prefix LUTs.  entry: bits 0-4 length (0 = invalid), 5-6 trailingOnes, 7-11 totalCoeff
-uint16_t gTok[3][1 << 16];
+// ---- expanded prefix LUTs.  entry: bits 0-4 length (0 = invalid), 5-6 trailingOnes, 7-11 totalCoeff.
+// coeff_token in two levels of 8 bits (a flat 16-bit table is 128 KB per VLC table, and a short code followed by arbitrary
+// bits lands anywhere in it): gTok1 by the first 8 bits holds the codes of up to 8 bits, or kTokLong | sub-table number;
+// gTok2 by the next 8 bits holds the longer ones.
+constexpr uint16_t kTokLong = 0x8000;
+uint16_t gTok1[3][256];
+uint16_t gTok2[3][16][256];
 uint16_t gTokDc[1 << 8];
 // entry: low nibble = length (0 invalid), high nibble = value
 uint8_t gTz[15][1 << 9];
@@ -99,15 +104,24 @@ uint8_t gRun[7][1 << 11];  // value up to 14 -> (value<<4)|len  len up to 11 fit
 std::once_flag gOnce;
 
 void buildTables() {
+    std::memset(gTok1, 0, sizeof gTok1);
+    std::memset(gTok2, 0, sizeof gTok2);
     for (int t = 0; t < 3; t++) {
-        std::memset(gTok[t], 0, sizeof gTok[t]);
+        int nSub = 0;
         for (int t1 = 0; t1 < 4; t1++)
             for (int tc = 0; tc < 17; tc++) {
                 int len = kTokLen[t][t1][tc];
                 if (!len) continue;
-                uint32_t first = (uint32_t)kTokCode[t][t1][tc] << (16 - len);
+                uint32_t first = (uint32_t)kTokCode[t][t1][tc] << (16 - len);   // left-aligned in 16 bits
                 uint16_t e = (uint16_t)(len | (t1 << 5) | (tc << 7));
-                for (uint32_t k = 0; k < (1u << (16 - len)); k++) gTok[t][first + k] = e;
+                if (len <= 8) {
+                    for (uint32_t k = 0; k < (1u << (8 - len)); k++) gTok1[t][(first >> 8) + k] = e;
+                } else {
+                    uint16_t &l1 = gTok1[t][first >> 8];
+                    if (!(l1 & kTokLong)) l1 = (uint16_t)(kTokLong | nSub++);
+                    uint16_t *sub = gTok2[t][l1 & 0xFF];
+                    for (uint32_t k = 0; k < (1u << (16 - len)); k++) sub[(first & 0xFF) + k] = e;
+                }
             }
     }
     std::memset(gTokDc, 0, sizeof gTokDc);
@@ -151,6 +165,13 @@ void buildTables() {
 
 void cavlcInit() { std::call_once(gOnce, buildTables); }
 
+// coeff_token for VLC table t from the next 16 stream bits
+static inline uint32_t tokLookup(int t, uint32_t prefix16) {
+    uint32_t e = gTok1[t][prefix16 >> 8];
+    if (e & kTokLong) e = gTok2[t][e & 0xFF][prefix16 & 0xFF];
+    return e;
+}
+
 // test hook: decode one coeff_token for a 16-bit left-aligned prefix.  returns len | t1<<5 | tc<<7, 0 = invalid
 extern "C" uint32_t b200_cavlc_probe(int kind, int index, uint32_t prefix16) {
     cavlcInit();
@@ -164,7 +185,7 @@ extern "C" uint32_t b200_cavlc_probe(int kind, int index, uint32_t prefix16) {
                 if (t1 > tc) return 0;
                 return 6 | (t1 << 5) | (tc << 7);
             }
-            return gTok[index < 2 ? 0 : index < 4 ? 1 : 2][prefix16];
+            return tokLookup(index < 2 ? 0 : index < 4 ? 1 : 2, prefix16);
         case 1:  // total_zeros 4x4, index = totalCoeff
             return gTz[index - 1][prefix16 >> 7];
         case 2:  // total_zeros chroma DC
@@ -175,14 +196,25 @@ extern "C" uint32_t b200_cavlc_probe(int kind, int index, uint32_t prefix16) {
     return 0;
 }
 
-CavlcResult cavlcResidualBlock(BitReader &br, int16_t *out, int nC, int maxNumCoeff) {
-    CavlcResult bad{-1, 0};
-    uint32_t bits = br.show32();
+CavlcResult cavlcResidualBlock(BitReader &stream, int16_t *out, int nC, int maxNumCoeff) {
+    const CavlcResult bad{-1, 0};
+    // A 64-bit window of the stream, refilled when fewer than 32 of its bits are left.  Reading past the end of the NAL
+    // yields zeros (h264bsdShowBits32) and is an error (END_OF_STREAM): checked once, at the end -- a block that crossed the
+    // end is rejected whatever it decoded to, and an error ends the slice, so nothing of it is used.
+    uint64_t pos = stream.pos();
+    uint64_t win = stream.window(pos);
+    unsigned used = 0;
+    auto peek = [&]() -> uint32_t {
+        if (used > 25) { pos += used; win = stream.window(pos); used = 0; }
+        return (uint32_t)((win << used) >> 32);
+    };
+
+    uint32_t bits = peek();
     uint32_t e;
     if (nC < 0) {
         e = gTokDc[bits >> 24];
     } else if (nC < 8) {
-        e = gTok[nC < 2 ? 0 : nC < 4 ? 1 : 2][bits >> 16];
+        e = tokLookup(nC < 2 ? 0 : nC < 4 ? 1 : 2, bits >> 16);
     } else {
         uint32_t c = bits >> 26;
         if (c == 3) {
@@ -192,39 +224,42 @@ CavlcResult cavlcResidualBlock(BitReader &br, int16_t *out, int nC, int maxNumCo
             e = (t1 > tc) ? 0 : (6 | (t1 << 5) | (tc << 7));
         }
     }
-    unsigned len = e & 31;
-    if (!len) return bad;
-    int totalCoeff = (int)(e >> 7);
-    int trailingOnes = (int)((e >> 5) & 3);
-    if (!br.skip(len)) return bad;
+    const unsigned tokLen = e & 31;
+    if (!tokLen) return bad;
+    const int totalCoeff = (int)(e >> 7);
+    const int trailingOnes = (int)((e >> 5) & 3);
+    used += tokLen;
     if (totalCoeff > maxNumCoeff) return bad;
-    if (totalCoeff == 0) return CavlcResult{0, 0};
+    if (totalCoeff == 0) {
+        if (pos + used > stream.bitsTotal()) return bad;
+        stream.seek(pos + used);
+        return CavlcResult{0, 0};
+    }
 
     int level[16];
     int i = 0;
     if (trailingOnes) {
-        uint32_t signs;
-        if (!br.get((unsigned)trailingOnes, signs)) return bad;
+        const uint32_t signs = peek() >> (32 - trailingOnes);
+        used += (unsigned)trailingOnes;
         for (int k = trailingOnes - 1; k >= 0; k--) level[i++] = (signs >> k) & 1 ? -1 : 1;
     }
     int suffixLength = (totalCoeff > 10 && trailingOnes < 3) ? 1 : 0;
     for (; i < totalCoeff; i++) {
-        uint32_t w = br.show32();
+        uint32_t w = peek();
         if ((w >> 16) == 0) return bad;  // level_prefix > 15 does not exist in Baseline
-        int prefix = __builtin_clz(w);
-        if (!br.skip((unsigned)prefix + 1)) return bad;
+        const int prefix = __builtin_clz(w);
+        used += (unsigned)prefix + 1;
         int levelCode = (prefix < 15 ? prefix : 15) << suffixLength;
         int suffixSize = suffixLength;
         if (prefix == 14 && suffixLength == 0) suffixSize = 4;
         if (prefix == 15) suffixSize = 12;
         if (suffixSize) {
-            uint32_t s;
-            if (!br.get((unsigned)suffixSize, s)) return bad;
-            levelCode += (int)s;
+            levelCode += (int)(peek() >> (32 - suffixSize));
+            used += (unsigned)suffixSize;
         }
         if (prefix == 15 && suffixLength == 0) levelCode += 15;
         if (i == trailingOnes && trailingOnes < 3) levelCode += 2;
-        int mag = (levelCode + 2) >> 1;
+        const int mag = (levelCode + 2) >> 1;
         if (suffixLength == 0) suffixLength = 1;
         if (mag > (3 << (suffixLength - 1)) && suffixLength < 6) suffixLength++;
         level[i] = (levelCode & 1) ? -mag : mag;
@@ -232,38 +267,44 @@ CavlcResult cavlcResidualBlock(BitReader &br, int16_t *out, int nC, int maxNumCo
 
     int zerosLeft = 0;
     if (totalCoeff < maxNumCoeff) {
-        uint32_t w = br.show32();
-        uint8_t t = (maxNumCoeff == 4) ? gTzDc[totalCoeff - 1][w >> 29] : gTz[totalCoeff - 1][w >> 23];
+        const uint32_t w = peek();
+        const uint8_t t = (maxNumCoeff == 4) ? gTzDc[totalCoeff - 1][w >> 29] : gTz[totalCoeff - 1][w >> 23];
         if (!(t & 15)) return bad;
-        if (!br.skip(t & 15)) return bad;
+        used += t & 15;
         zerosLeft = t >> 4;
     }
-    int run[16];
-    for (i = 0; i < totalCoeff - 1; i++) {
-        if (zerosLeft > 0) {
-            uint32_t w = br.show32();
-            uint8_t t = gRun[(zerosLeft > 7 ? 7 : zerosLeft) - 1][w >> 21];
-            if (!(t & 15)) return bad;
-            int r = t >> 4;
-            if (r > zerosLeft) return bad;
-            if (!br.skip(t & 15)) return bad;
-            run[i] = r;
-            zerosLeft -= r;
-        } else {
-            run[i] = 0;
-        }
-    }
-    // place levels: the last decoded level sits after `zerosLeft` leading zeros
-    int pos = zerosLeft;
+    // place levels from the highest frequency down: the first decoded level sits at position totalCoeff - 1 + total_zeros
+    int at = totalCoeff - 1 + zerosLeft;
+    if (at >= maxNumCoeff) return bad;
     uint32_t map = 0;
-    for (i = totalCoeff - 1; i >= 0; i--) {
-        if (i < totalCoeff - 1) pos += run[i] + 1;
-        if (pos >= maxNumCoeff) return bad;
-        int v = level[i];
+    for (i = 0; i < totalCoeff; i++) {
+        const int v = level[i];
         if (v > 32767 || v < -32768) return bad;
-        out[pos] = (int16_t)v;
-        map |= 1u << pos;
+        out[at] = (int16_t)v;
+        map |= 1u << at;
+        if (i == totalCoeff - 1) break;
+        int r = 0;
+        if (zerosLeft > 0) {
+            const uint32_t w = peek();
+            unsigned len;
+            if (zerosLeft > 6) {
+                // Table 9-10, last column: 111..001 -> 0..6, then one more leading zero per step
+                if (w >> 29) { r = 7 - (int)(w >> 29); len = 3; }
+                else { const int z = __builtin_clz(w | 1u); r = z + 4; len = (unsigned)z + 1; if (r > 14) return bad; }
+            } else {
+                const uint8_t t = gRun[zerosLeft - 1][w >> 21];
+                if (!(t & 15)) return bad;
+                r = t >> 4;
+                len = t & 15;
+            }
+            if (r > zerosLeft) return bad;
+            used += len;
+            zerosLeft -= r;
+        }
+        at -= r + 1;
     }
+    if (pos + used > stream.bitsTotal()) return bad;
+    stream.seek(pos + used);
     return CavlcResult{totalCoeff, map};
 }
 

@@ -43,11 +43,12 @@ struct PictureState::MbSyntax {
     uint32_t subType[4];
     int16_t subMvd[4][4][2];
     uint8_t totalCoeff[27];
+    uint32_t codedBlocks;   // bit i: level[i] holds levels (TotalCoeff != 0); bits 24 / 25 = B200_CM_LUMA_DC / B200_CM_CHROMA_DC
     alignas(16) int16_t level[26][16];  // [0..23] blocks, [24] luma DC, [25] chroma DC (Cb 0..3, Cr 4..7)
     uint8_t pcm[384];
     void clear() {
         // levels are cleared selectively after use; everything else here
-        cbp = 0; qpDelta = 0; chromaMode = 0;
+        cbp = 0; qpDelta = 0; chromaMode = 0; codedBlocks = 0;
         std::memset(prevFlag, 0, sizeof prevFlag); std::memset(remMode, 0, sizeof remMode);
         std::memset(refIdx, 0, sizeof refIdx); std::memset(mvd, 0, sizeof mvd);
         std::memset(subType, 0, sizeof subType); std::memset(subMvd, 0, sizeof subMvd);
@@ -64,6 +65,9 @@ void PictureState::resize(uint32_t w, uint32_t h) {
     aux.assign(picSizeInMbs, MbAux());
     sliceGroupMap.assign(picSizeInMbs, 0);
     coefs.clear();
+    orderClass.assign(2 * (size_t)picSizeInMbs, 0);
+    lateFixup_ = false;
+    numIntraPred_ = 0;
     sliceIdCounter = numDecodedMbs = lastMbAddr = 0;
 }
 
@@ -82,6 +86,7 @@ void PictureState::bindOutput() {
 }
 
 void PictureState::splitState() {
+    lateFixup_ = true;      // a macroblock decoded twice: classes and flags are settled by the full pass of finalizeRecords
     if (st != recs) return;
     ownSt_.assign(recs, recs + picSizeInMbs);
     st = ownSt_.data();
@@ -93,6 +98,9 @@ void PictureState::beginPicture() {
     sliceIdCounter = 0;
     for (auto &a : aux) { a.sliceId = 0; a.decoded = 0; }
     coefs.clear();
+    orderClass.resize(2 * (size_t)picSizeInMbs);
+    lateFixup_ = false;
+    numIntraPred_ = 0;
 }
 
 bool PictureState::allDecoded(bool redundant) const {
@@ -144,10 +152,12 @@ int PictureState::nC(uint32_t mbAddr, uint32_t blk, const uint8_t *cur) const {
 }
 
 // h264bsdDecodeMacroblockLayer (h264bsd_macroblock_layer.c:134-243)
-bool PictureState::parseMacroblockLayer(BitReader &br, MbSyntax &mb, uint32_t mbAddr, bool iSlice, uint32_t numRefIdxActive) {
+bool PictureState::parseMacroblockLayer(BitReader &stream, MbSyntax &mb, uint32_t mbAddr, bool iSlice, uint32_t numRefIdxActive) {
     uint32_t v;
     int32_t s;
     mb.clear();
+    BitReader br = stream;      // local copy: the position stays in a register; handed back before the residual and at the end
+                                // (after an error the position is not used again)
     bool ok = br.ue(v);
     uint32_t off = iSlice ? 6 : 1;
     if (!ok || v + off > 31) return false;
@@ -160,6 +170,7 @@ bool PictureState::parseMacroblockLayer(BitReader &br, MbSyntax &mb, uint32_t mb
             if (!br.get(8, v)) return false;
             mb.pcm[i] = (uint8_t)v;
         }
+        stream = br;
         return true;
     }
     bool inter = isInterType(mb.mbType);
@@ -223,8 +234,10 @@ bool PictureState::parseMacroblockLayer(BitReader &br, MbSyntax &mb, uint32_t mb
     if (mb.cbp || i16) {
         if (!br.se(s) || s < -26 || s > 25) return false;
         mb.qpDelta = s;
-        if (!parseResidual(br, mb, mbAddr)) return false;
+        stream = br;
+        return parseResidual(stream, mb, mbAddr);
     }
+    stream = br;
     return true;
 }
 
@@ -236,6 +249,7 @@ bool PictureState::parseResidual(BitReader &br, MbSyntax &mb, uint32_t mbAddr) {
         CavlcResult r = cavlcResidualBlock(br, mb.level[24], nC(mbAddr, 0, mb.totalCoeff), 16);
         if (r.totalCoeff < 0) return false;
         mb.totalCoeff[24] = (uint8_t)r.totalCoeff;
+        if (r.totalCoeff) mb.codedBlocks |= B200_CM_LUMA_DC;
     }
     uint32_t blk = 0;
     for (int i8 = 0; i8 < 4; i8++) {
@@ -246,6 +260,7 @@ bool PictureState::parseResidual(BitReader &br, MbSyntax &mb, uint32_t mbAddr) {
                                     : cavlcResidualBlock(br, mb.level[blk], n, 16);
                 if (r.totalCoeff < 0) return false;
                 mb.totalCoeff[blk] = (uint8_t)r.totalCoeff;
+                if (r.totalCoeff) mb.codedBlocks |= 1u << blk;
             }
         } else {
             blk += 4;
@@ -256,15 +271,18 @@ bool PictureState::parseResidual(BitReader &br, MbSyntax &mb, uint32_t mbAddr) {
         CavlcResult r = cavlcResidualBlock(br, mb.level[25], -1, 4);
         if (r.totalCoeff < 0) return false;
         mb.totalCoeff[25] = (uint8_t)r.totalCoeff;
+        if (r.totalCoeff) mb.codedBlocks |= B200_CM_CHROMA_DC;
         r = cavlcResidualBlock(br, mb.level[25] + 4, -1, 4);
         if (r.totalCoeff < 0) return false;
         mb.totalCoeff[26] = (uint8_t)r.totalCoeff;
+        if (r.totalCoeff) mb.codedBlocks |= B200_CM_CHROMA_DC;
     }
     if (chroma & 2) {
         for (blk = 16; blk < 24; blk++) {
             CavlcResult r = cavlcResidualBlock(br, mb.level[blk] + 1, nC(mbAddr, blk, mb.totalCoeff), 15);
             if (r.totalCoeff < 0) return false;
             mb.totalCoeff[blk] = (uint8_t)r.totalCoeff;
+            if (r.totalCoeff) mb.codedBlocks |= 1u << blk;
         }
     }
     return true;
@@ -486,92 +504,175 @@ bool PictureState::deriveIntra(MbSyntax &mb, uint32_t mbAddr, bool constrainedIn
     return true;
 }
 
+// Class of a macroblock for the processing order (0 other pass-A, 1 plain copy, 4 pass-B; zr = 1 + reference slot of a
+// zero-vector plain copy), its deblocking edge flags (GetMbFilteringFlags, deblocking.c:289-320) and, for an intra-predicted
+// macroblock, the neighbours it has to wait for inside the intra pass -- settled right after the record is written, while it
+// is in cache.  Everything it looks at is final at this point: a left / upper neighbour of the same slice has been decoded
+// before this macroblock (curNb_), one that is decoded later belongs to a later slice.  Pictures where that does not hold
+// (a macroblock decoded twice by redundant slices, corrupted slices, concealment) take the full pass of finalizeRecords.
+inline void PictureState::classify(uint32_t a, b200_mb_rec &r) {
+    uint8_t *cls = orderClass.data(), *zr = cls + picSizeInMbs;
+    const uint32_t idc = r.reserved0;
+    uint8_t f = r.flags & (uint8_t)(B200_MBF_AVAIL_A | B200_MBF_AVAIL_B | B200_MBF_AVAIL_C | B200_MBF_AVAIL_D);
+    if (idc != 1) {
+        f |= B200_MBF_FILTER_INNER;
+        if (curX_ && (idc != 2 || curNb_[0] >= 0)) f |= B200_MBF_FILTER_LEFT;
+        if (a >= widthMbs && (idc != 2 || curNb_[1] >= 0)) f |= B200_MBF_FILTER_TOP;
+    }
+    uint8_t c = 0, z = 0, w = 0;
+    if (r.mbType > B200_MB_P_8x8REF0 && r.mbType != B200_MB_I_PCM) {
+        c = 4;
+        numIntraPred_++;
+        if ((f & B200_MBF_AVAIL_A) && cls[a - 1] == 4) w |= B200_MBF_AVAIL_A;
+        if ((f & B200_MBF_AVAIL_B) && cls[a - widthMbs] == 4) w |= B200_MBF_AVAIL_B;
+        if ((f & B200_MBF_AVAIL_C) && cls[a - widthMbs + 1] == 4) w |= B200_MBF_AVAIL_C;
+        if ((f & B200_MBF_AVAIL_D) && cls[a - widthMbs - 1] == 4) w |= B200_MBF_AVAIL_D;
+    } else if (r.mbType <= B200_MB_P_16x16 && r.codedMask == 0 && ((r.u.mv[0][0] | r.u.mv[0][1]) & 7) == 0) {
+        c = 1;
+        if ((r.u.mv[0][0] | r.u.mv[0][1]) == 0) z = (uint8_t)(1 + r.refSlot[0]);
+    }
+    r.flags = f;
+    r.waitMask = w;
+    cls[a] = c;
+    zr[a] = z;
+}
+
 // the syntax-level half of h264bsdDecodeMacroblock (h264bsd_macroblock_layer.c:965-1131)
 bool PictureState::finishMacroblock(MbSyntax &mb, uint32_t mbAddr, int &qpY, const SliceHeader &sh, const Pps &pps, const Dpb &dpb) {
     b200_mb_rec &r = st[mbAddr];
     MbAux &ax = aux[mbAddr];
-    r.mbType = (uint8_t)mb.mbType;
+    const uint32_t type = mb.mbType;
     ax.decoded++;
-    bool first = ax.decoded == 1;
-    // SetMbParams (h264bsd_slice_data.c:254-273) -- done by the caller for sliceId; the rest here
+    const bool first = ax.decoded == 1;
+    // every byte of the record is set (it may live in memory nobody cleared).  SetMbParams (h264bsd_slice_data.c:254-273):
+    // the slice id is set by the caller
+    r.mbType = (uint8_t)type;
     r.reserved0 = (uint8_t)sh.disableDeblockingFilterIdc;
     r.filterOffsetA = (int8_t)sh.alphaOffset;
     r.filterOffsetB = (int8_t)sh.betaOffset;
     r.chromaQpIndexOffset = (int8_t)pps.chromaQpIndexOffset;
-    r.codedMask = 0;
-    r.coefIndex = 0;
+    r.coefIndex = (uint32_t)(coefs.size() / 16);
     r.waitMask = 0;
-    r.reserved1[0] = r.reserved1[1] = r.reserved1[2] = 0;   // (the record may live in memory nobody cleared: every byte is set)
+    r.reserved1[0] = r.reserved1[1] = r.reserved1[2] = 0;
+    r.flags = 0;
+    r.intraChromaMode = 0;
+    r.subMbTypes = 0;
 
-    if (mb.mbType == B200_MB_I_PCM) {
-        r.subMbTypes = 0;
+    if (type == B200_MB_P_SKIP) {
+        std::memset(ax.totalCoeff, 0, 27);
+        r.qpY = (uint8_t)qpY;
+        r.qpC = kQpC[std::min(51, std::max(0, qpY + pps.chromaQpIndexOffset))];
+        r.codedMask = 0;
+        if (!deriveInter(mb, mbAddr, dpb)) return false;
+        if (first && recs != st) recs[mbAddr] = r;
+        if (first && !lateFixup_) classify(mbAddr, recs[mbAddr]);
+        return true;
+    }
+
+    if (type == B200_MB_I_PCM) {
         std::memset(r.refSlot, 0, 4);
         std::memset(r.refIdx, 0, 4);
         r.qpY = 0;
         r.qpC = kQpC[std::min(51, std::max(0, 0 + pps.chromaQpIndexOffset))];
-        for (int i = 0; i < 24; i++) ax.totalCoeff[i] = 16;
-        r.flags = 0;
-        r.intraChromaMode = 0;
+        std::memset(ax.totalCoeff, 16, 24);
         std::memset(&r.u, 0, sizeof r.u);
         r.codedMask = 0xFFFFFFu;
-        if (!first) return true;
-        r.coefIndex = (uint32_t)(coefs.size() / 16);
-        size_t at = coefs.size();
-        coefs.resize(at + 12 * 16);
-        std::memcpy(&coefs[at], mb.pcm, 384);
+        if (!first) { r.coefIndex = 0; return true; }
+        std::memcpy(coefs.grow(12 * 16), mb.pcm, 384);
         if (recs != st) recs[mbAddr] = r;
+        if (!lateFixup_) classify(mbAddr, recs[mbAddr]);
         return true;
     }
 
-    if (mb.mbType != B200_MB_P_SKIP) {
-        std::memcpy(ax.totalCoeff, mb.totalCoeff, 27);
-        if (mb.qpDelta) {
-            qpY += mb.qpDelta;
-            if (qpY < 0) qpY += 52;
-            else if (qpY >= 52) qpY -= 52;
-        }
-    } else {
-        std::memset(ax.totalCoeff, 0, 27);
+    std::memcpy(ax.totalCoeff, mb.totalCoeff, 27);
+    if (mb.qpDelta) {
+        qpY += mb.qpDelta;
+        if (qpY < 0) qpY += 52;
+        else if (qpY >= 52) qpY -= 52;
     }
     r.qpY = (uint8_t)qpY;
     r.qpC = kQpC[std::min(51, std::max(0, qpY + pps.chromaQpIndexOffset))];
 
-    uint32_t mask = 0;
-    bool i16 = !isInterType(mb.mbType) && mb.mbType != B200_MB_I_4x4;
-    if (mb.mbType != B200_MB_P_SKIP) {
-        for (int i = 0; i < 24; i++)
-            if (ax.totalCoeff[i]) mask |= 1u << i;
-        if (i16 && ax.totalCoeff[24]) mask |= B200_CM_LUMA_DC;
-        if (ax.totalCoeff[25] || ax.totalCoeff[26]) mask |= B200_CM_CHROMA_DC;
-    }
+    const bool inter = isInterType(type);
+    const bool i16 = !inter && type != B200_MB_I_4x4;
+    uint32_t mask = mb.codedBlocks;      // blocks with TotalCoeff != 0, collected by parseResidual
+    if (!i16) mask &= ~B200_CM_LUMA_DC;
     r.codedMask = mask;
 
-    if (isInterType(mb.mbType)) {
-        r.flags = 0;
-        r.intraChromaMode = 0;
+    if (inter) {
         if (!deriveInter(mb, mbAddr, dpb)) return false;
     } else {
         std::memset(r.refSlot, 0, 4);
         std::memset(r.refIdx, 0, 4);
-        r.subMbTypes = 0;
-        std::memset(&r.u, 0, sizeof r.u);
         if (!deriveIntra(mb, mbAddr, pps.constrainedIntraPred)) return false;
     }
-    if (!first) return true;
+    if (!first) { r.coefIndex = 0; return true; }
 
     // emit coefficients: [luma DC][chroma DC][coded blocks ascending]
-    r.coefIndex = (uint32_t)(coefs.size() / 16);
     if (mask) {
-        uint32_t nblk = (uint32_t)__builtin_popcount(mask);
-        size_t at = coefs.size();
-        coefs.resize(at + (size_t)nblk * 16);
-        int16_t *dst = &coefs[at];
+        int16_t *dst = coefs.grow((size_t)__builtin_popcount(mask) * 16);
         if (mask & B200_CM_LUMA_DC) { std::memcpy(dst, mb.level[24], 32); dst += 16; }
         if (mask & B200_CM_CHROMA_DC) { std::memcpy(dst, mb.level[25], 16); std::memset(dst + 8, 0, 16); dst += 16; }
-        for (int i = 0; i < 24; i++)
-            if (mask & (1u << i)) { std::memcpy(dst, mb.level[i], 32); dst += 16; }
+        for (uint32_t m = mask & 0xFFFFFFu; m; m &= m - 1) {
+            std::memcpy(dst, mb.level[__builtin_ctz(m)], 32);
+            dst += 16;
+        }
     }
     if (recs != st) recs[mbAddr] = r;
+    if (!lateFixup_) classify(mbAddr, recs[mbAddr]);
+    return true;
+}
+
+// P_Skip, the most frequent macroblock: what finishMacroblock + deriveInter do for it, without the general machinery.
+// slot0 = frame slot of reference index 0 in this slice's list (-1: no such picture -> error, inter_prediction.c:527-531).
+inline bool PictureState::finishSkip(uint32_t mbAddr, int qpY, const SliceHeader &sh, const Pps &pps, int slot0) {
+    b200_mb_rec &r = st[mbAddr];
+    MbAux &ax = aux[mbAddr];
+    ax.decoded++;
+    const bool first = ax.decoded == 1;
+    std::memset(ax.totalCoeff, 0, 27);
+    r.mbType = B200_MB_P_SKIP;
+    r.qpY = (uint8_t)qpY;
+    r.qpC = kQpC[std::min(51, std::max(0, qpY + pps.chromaQpIndexOffset))];
+    r.flags = 0;
+    r.codedMask = 0;
+    r.coefIndex = (uint32_t)(coefs.size() / 16);
+    r.filterOffsetA = (int8_t)sh.alphaOffset;
+    r.filterOffsetB = (int8_t)sh.betaOffset;
+    r.chromaQpIndexOffset = (int8_t)pps.chromaQpIndexOffset;
+    r.subMbTypes = 0;
+    r.intraChromaMode = 0;
+    r.reserved0 = (uint8_t)sh.disableDeblockingFilterIdc;
+    r.waitMask = 0;
+    r.reserved1[0] = r.reserved1[1] = r.reserved1[2] = 0;
+    // clause 8.4.1.1: zero vector unless both neighbours A and B exist and neither is (reference 0, vector 0)
+    uint32_t mvWord = 0;
+    const int a = curNb_[0], b = curNb_[1];
+    if (a >= 0 && b >= 0) {
+        const b200_mb_rec &ra = st[a], &rb = st[b];
+        // A: the 4x4 block right of the left edge in row 0 (block 5 of A); B: block below the top edge, column 0 (block 10 of B)
+        uint32_t mvA, mvB;
+        std::memcpy(&mvA, ra.u.mv[5], 4);
+        std::memcpy(&mvB, rb.u.mv[10], 4);
+        const bool interA = isInterType(ra.mbType), interB = isInterType(rb.mbType);
+        const bool zero = (interA && ra.refIdx[1] == 0 && mvA == 0) || (interB && rb.refIdx[2] == 0 && mvB == 0);
+        if (!zero) {
+            NbMv na{true, interA ? ra.refIdx[1] : 0xFFFFFFFFu, {0, 0}}, nb{true, interB ? rb.refIdx[2] : 0xFFFFFFFFu, {0, 0}};
+            if (interA) { na.mv[0] = ra.u.mv[5][0]; na.mv[1] = ra.u.mv[5][1]; }
+            if (interB) { nb.mv[0] = rb.u.mv[10][0]; nb.mv[1] = rb.u.mv[10][1]; }
+            int16_t p[2];
+            predictMv(mbAddr, 0, 0, 4, 4, 0, 0, p, &na, &nb);
+            if (!mvInRange(p[0], p[1])) return false;
+            std::memcpy(&mvWord, p, 4);
+        }
+    }
+    if (slot0 < 0) return false;
+    uint32_t *mv = reinterpret_cast<uint32_t *>(&r.u);
+    for (int z = 0; z < 16; z++) mv[z] = mvWord;
+    std::memset(r.refIdx, 0, 4);
+    std::memset(r.refSlot, slot0, 4);
+    if (first && recs != st) recs[mbAddr] = r;
+    if (first && !lateFixup_) classify(mbAddr, recs[mbAddr]);
     return true;
 }
 
@@ -591,53 +692,55 @@ SliceResult PictureState::decodeSlice(BitReader &br, const SliceHeader &sh, cons
     lastMbAddr = 0;
     uint32_t mbCount = 0;
     int qpY = (int)pps.picInitQp + sh.sliceQpDelta;
+    const bool iSlice = sh.isI();
+    const uint16_t sid = (uint16_t)sliceIdCounter;
+    uint32_t x = cur % widthMbs;
+    const int slot0 = iSlice ? -1 : dpb.refSlot(0);
     bool more;
     do {
-        if (!sh.redundantPicCnt && aux[cur].decoded) return SliceResult::Error;
-        aux[cur].sliceId = (uint16_t)sliceIdCounter;
-        st[cur].sliceId = (uint16_t)sliceIdCounter;
+        MbAux &ax = aux[cur];
+        if (!sh.redundantPicCnt && ax.decoded) return SliceResult::Error;
+        ax.sliceId = sid;
+        st[cur].sliceId = sid;
         {
             // neighbours A, B, C, D of this macroblock that exist and belong to the same slice (h264bsdInitMbNeighbours +
             // h264bsdIsNeighbourAvailable, neighbour.c:128-176, :370-382), resolved once per macroblock
-            const uint32_t x = cur % widthMbs;
             const bool up = cur >= widthMbs;
-            const uint16_t sid = (uint16_t)sliceIdCounter;
-            auto same = [&](int nb) { return aux[nb].sliceId == sid ? nb : -1; };
-            curNb_[0] = x ? same((int)cur - 1) : -1;
-            curNb_[1] = up ? same((int)(cur - widthMbs)) : -1;
-            curNb_[2] = (up && x + 1 < widthMbs) ? same((int)(cur - widthMbs + 1)) : -1;
-            curNb_[3] = (up && x) ? same((int)(cur - widthMbs - 1)) : -1;
+            const MbAux *am = aux.data();
+            curX_ = x;
+            curNb_[0] = (x && am[cur - 1].sliceId == sid) ? (int)cur - 1 : -1;
+            curNb_[1] = (up && am[cur - widthMbs].sliceId == sid) ? (int)(cur - widthMbs) : -1;
+            curNb_[2] = (up && x + 1 < widthMbs && am[cur - widthMbs + 1].sliceId == sid) ? (int)(cur - widthMbs + 1) : -1;
+            curNb_[3] = (up && x && am[cur - widthMbs - 1].sliceId == sid) ? (int)(cur - widthMbs - 1) : -1;
         }
-        bool parsed = false;
-        if (!sh.isI()) {
-            if (!prevSkipped) {
-                if (!br.ue(skipRun)) return SliceResult::Error;
-                if (skipRun > picSizeInMbs - cur) return SliceResult::Error;
-                if (skipRun) prevSkipped = true;
-            }
+        if (!iSlice && !prevSkipped) {
+            if (!br.ue(skipRun)) return SliceResult::Error;
+            if (skipRun > picSizeInMbs - cur) return SliceResult::Error;
+            if (skipRun) prevSkipped = true;
         }
+        bool ok;
         if (skipRun) {
             skipRun--;
-            // P_Skip: only what finishMacroblock / deriveInter read (slice_data.c:160-166 clears mbPred there)
-            mb.mbType = B200_MB_P_SKIP;
-            mb.cbp = 0; mb.qpDelta = 0;
-            mb.refIdx[0] = 0; mb.mvd[0][0] = mb.mvd[0][1] = 0;
+            ok = finishSkip(cur, qpY, sh, pps, slot0);
         } else {
             prevSkipped = false;
-            bool ok = parseMacroblockLayer(br, mb, cur, sh.isI(), sh.numRefIdxL0Active);
-            parsed = true;
-            if (!ok) {
+            if (!parseMacroblockLayer(br, mb, cur, iSlice, sh.numRefIdxL0Active)) {
                 std::memset(mb.level, 0, sizeof mb.level);
                 return SliceResult::Error;
             }
+            ok = finishMacroblock(mb, cur, qpY, sh, pps, dpb);
+            // the level arrays go back to all-zero for the next macroblock: only the blocks that received levels
+            if (mb.mbType != B200_MB_I_PCM) {
+                for (uint32_t m = mb.codedBlocks; m; m &= m - 1) std::memset(mb.level[__builtin_ctz(m)], 0, 32);
+            }
         }
-        bool ok = finishMacroblock(mb, cur, qpY, sh, pps, dpb);
-        if (parsed && mb.mbType != B200_MB_I_PCM && (mb.cbp || !isInterType(mb.mbType))) std::memset(mb.level, 0, sizeof mb.level);
         if (!ok) return SliceResult::Error;
-        if (aux[cur].decoded == 1) mbCount++;
-        more = br.moreRbspData() || skipRun;
-        if (sh.isI()) lastMbAddr = cur;
-        cur = nextMbAddress(cur);
+        if (ax.decoded == 1) mbCount++;
+        more = skipRun || br.moreRbspData();
+        if (iSlice) lastMbAddr = cur;
+        const uint32_t next = nextMbAddress(cur);
+        x = (next == cur + 1) ? (x + 1 == widthMbs ? 0 : x + 1) : next % widthMbs;
+        cur = next;
         if (more && !cur) return SliceResult::Error;
     } while (more);
     if (numDecodedMbs + mbCount > picSizeInMbs) return SliceResult::Error;
@@ -647,6 +750,7 @@ SliceResult PictureState::decodeSlice(BitReader &br, const SliceHeader &sh, cons
 
 // h264bsdMarkSliceCorrupted (h264bsd_slice_data.c:298-354)
 void PictureState::markSliceCorrupted(uint32_t firstMbInSlice, const Sps &sps) {
+    lateFixup_ = true;
     uint32_t cur = firstMbInSlice;
     uint32_t sliceId = sliceIdCounter;
     if (lastMbAddr) {
@@ -678,7 +782,9 @@ void PictureState::finalizeRecords() {
     cls.resize(2 * (size_t)picSizeInMbs);
     uint8_t *zr = cls.data() + picSizeInMbs;
     order.resize(picSizeInMbs);
-    uint32_t a = 0, nB = 0;
+    uint32_t a = 0, nB = lateFixup_ ? 0 : numIntraPred_;
+    // (the common picture -- every macroblock decoded once, nothing concealed -- had this done per macroblock by classify())
+    if (lateFixup_)
     for (uint32_t y = 0; y < heightMbs; y++)
         for (uint32_t x = 0; x < widthMbs; x++, a++) {
             b200_mb_rec &r = recs[a];
@@ -747,6 +853,7 @@ void PictureState::finalizeRecords() {
             for (uint32_t x = 0; x < widthMbs; x++, a++) {
                 if (cls[a] != 4) continue;
                 order[listB + cnt[x + 2 * y]++] = (uint16_t)a;
+                if (!lateFixup_) continue;
                 // the neighbours an intra macroblock has to wait for inside the intra pass: the available ones that are
                 // intra-predicted themselves
                 b200_mb_rec &r = recs[a];
@@ -766,6 +873,7 @@ void PictureState::finalizeRecords() {
 // concealment (conceal.c:266-639) -- see DESIGN.md.
 uint32_t PictureState::concealMissing(const Dpb &dpb, bool pSlice) {
     bindOutput();
+    lateFixup_ = true;
     uint32_t n = 0;
     int slot = pSlice ? dpb.refSlot(0) : -1;
     for (uint32_t a = 0; a < picSizeInMbs; a++) {
@@ -783,9 +891,7 @@ uint32_t PictureState::concealMissing(const Dpb &dpb, bool pSlice) {
         } else {
             r.mbType = B200_MB_I_PCM;
             r.coefIndex = (uint32_t)(coefs.size() / 16);
-            size_t at = coefs.size();
-            coefs.resize(at + 12 * 16);
-            std::memset(&coefs[at], 128, 384);
+            std::memset(coefs.grow(12 * 16), 128, 384);
         }
         st[a] = r;
         if (recs != st) recs[a] = r;

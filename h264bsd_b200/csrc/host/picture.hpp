@@ -7,6 +7,8 @@
 // h264bsd_intra_prediction.c:627-833,:1886-1937).
 #pragma once
 #include <cstdint>
+#include <cstdlib>
+#include <new>
 #include <vector>
 #include "bits.hpp"
 #include "params.hpp"
@@ -45,7 +47,28 @@ public:
     b200_mb_rec *recs = nullptr;
     RecordProvider *provider = nullptr;
     std::vector<MbAux> aux;
-    std::vector<int16_t> coefs;     // coefficient pool of the picture being built, 16 int16 per block
+    // coefficient pool of the picture being built, 16 int16 per block; grows without value-initialising what it hands out
+    struct CoefPool {
+        ~CoefPool() { std::free(p_); }
+        const int16_t *data() const { return p_; }
+        size_t size() const { return n_; }          // in int16
+        void clear() { n_ = 0; }
+        int16_t *grow(size_t count) {
+            if (n_ + count > cap_) {
+                size_t cap = cap_ ? cap_ : 4096;
+                while (cap < n_ + count) cap *= 2;
+                int16_t *q = static_cast<int16_t *>(std::realloc(p_, cap * sizeof(int16_t)));
+                if (!q) throw std::bad_alloc();
+                p_ = q; cap_ = cap;
+            }
+            int16_t *at = p_ + n_;
+            n_ += count;
+            return at;
+        }
+    private:
+        int16_t *p_ = nullptr;
+        size_t n_ = 0, cap_ = 0;
+    } coefs;
     std::vector<uint16_t> order;    // processing order of the picture being built (see b200_tape.mbOrder)
     uint32_t numPassA = 0, numPassB = 0, numCopy = 0, numRun = 0, numRunMbs = 0;
     std::vector<uint8_t> orderClass;   // scratch of finalizeRecords
@@ -69,6 +92,8 @@ private:
     bool finishMacroblock(MbSyntax &mb, uint32_t mbAddr, int &qpY, const SliceHeader &sh, const Pps &pps, const Dpb &dpb);
     bool deriveInter(MbSyntax &mb, uint32_t mbAddr, const Dpb &dpb);
     bool deriveIntra(MbSyntax &mb, uint32_t mbAddr, bool constrainedIntra);
+    void classify(uint32_t mbAddr, b200_mb_rec &rec);
+    bool finishSkip(uint32_t mbAddr, int qpY, const SliceHeader &sh, const Pps &pps, int slot0);
     int nC(uint32_t mbAddr, uint32_t blk, const uint8_t *curTotalCoeff) const;
     uint32_t nextMbAddress(uint32_t cur) const;
 
@@ -82,6 +107,9 @@ private:
     std::vector<b200_mb_rec> ownSt_, ownRecs_;
     bool bound_ = false;
     int curNb_[4] = {-1, -1, -1, -1};   // available neighbours A, B, C, D of the macroblock being decoded (decodeSlice)
+    uint32_t curX_ = 0;                 // its column
+    bool lateFixup_ = false;            // this picture needs the full pass of finalizeRecords (see classify)
+    uint32_t numIntraPred_ = 0;         // intra-predicted macroblocks classified so far
 
     struct NbMv { bool avail; uint32_t refIdx; int16_t mv[2]; };
     NbMv interNeighbour(uint32_t cur, int x, int y, int curZ) const;
