@@ -7,18 +7,19 @@ from . import _lib
 class ParsedStream:
     """A stream parsed on the host into a tape (h264bsdB200ParseStream)."""
 
-    def __init__(self, data=None, no_output_reordering=False):
+    def __init__(self, data=None, no_output_reordering=False, resilient=False):
         self._L = _lib.load()
         self.ptr = None
         self.pinned = False
         self.status = None
         if data is not None:      # (None: an empty shell to be filled by reparse_many)
-            self.reparse(data, no_output_reordering)
+            self.reparse(data, no_output_reordering, resilient)
 
-    def reparse(self, data, no_output_reordering=False):
-        """parse another stream into the same tape (arrays and page-lock are kept)"""
+    def reparse(self, data, no_output_reordering=False, resilient=False):
+        """parse another stream into the same tape (arrays and page-lock are kept).  resilient: carry on after decode
+        errors; what is missing from a picture is concealed (B200_PARSE_RESILIENT)"""
         buf = data if isinstance(data, C.Array) else (C.c_uint8 * len(data)).from_buffer_copy(bytes(data))
-        self.ptr = self._L.h264bsdB200ReparseStream(self.ptr, buf, len(buf), 1 if no_output_reordering else 0)
+        self.ptr = self._L.h264bsdB200ReparseStream(self.ptr, buf, len(buf), (1 if no_output_reordering else 0) | (2 if resilient else 0))
         if not self.ptr:
             raise MemoryError("h264bsdB200ParseStream failed")
         t = self.ptr.contents

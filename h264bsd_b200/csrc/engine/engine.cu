@@ -306,6 +306,7 @@ bool Batch::buildJobs() {
     picMaxC_.assign(np, 0);
     picMaxA_.assign(np, 0);
     picMaxB_.assign(np, 0);
+    picMaxE_.assign(np, 0);
     std::vector<StreamJob> jobs((size_t)np * g_.nStreams);
     for (uint32_t k = 0; k < np; k++)
         for (int s = 0; s < g_.nStreams; s++) {
@@ -319,6 +320,9 @@ bool Batch::buildJobs() {
             j.nC = (uint16_t)t.pics[k].numCopy;
             j.nA = (uint16_t)(t.pics[k].numPassA - t.pics[k].numRunMbs - t.pics[k].numCopy);
             j.nB = (uint16_t)t.pics[k].numPassB;
+            j.nE = (uint16_t)t.pics[k].numConceal;
+            j.pad[0] = j.pad[1] = 0;
+            picMaxE_[k] = std::max<uint32_t>(picMaxE_[k], j.nE);
             picMaxQ_[k] = std::max<uint32_t>(picMaxQ_[k], j.nR);
             picMaxC_[k] = std::max<uint32_t>(picMaxC_[k], j.nC);
             picMaxA_[k] = std::max<uint32_t>(picMaxA_[k], j.nA);
@@ -371,7 +375,7 @@ bool Batch::kernelTimes(float ms[6], uint32_t *launchesPerStage) {
     return true;
 }
 
-bool Batch::launchPicture(const StreamJob *dJobs, uint32_t maxQ, uint32_t maxC, uint32_t maxA, uint32_t maxB, bool recon, bool deblock) {
+bool Batch::launchPicture(const StreamJob *dJobs, uint32_t maxQ, uint32_t maxC, uint32_t maxA, uint32_t maxB, uint32_t maxE, bool recon, bool deblock) {
     const uint32_t total = (uint32_t)g_.nStreams * (uint32_t)g_.nMbs;
     serial_++;
     auto mark = [&](int stageEnded) {
@@ -440,6 +444,13 @@ bool Batch::launchPicture(const StreamJob *dJobs, uint32_t maxQ, uint32_t maxC, 
             launches_++;
             mark(3);
         }
+        if (maxE) {
+            // error path only: macroblocks that never arrived, estimated from their neighbours once everything else of the
+            // picture is reconstructed (and before its filter)
+            concealKernel<<<((uint32_t)g_.nStreams + kConcealWarps - 1) / kConcealWarps, kConcealWarps * 32, 0, stream_>>>(rp);
+            launches_++;
+            mark(3);
+        }
     }
     if (deblock) {
         if (fork) {
@@ -479,7 +490,7 @@ bool Batch::decodePicture(uint32_t k) {
         fences_.pop_front();
         if (covers) break;
     }
-    return launchPicture(dJobs_ + (size_t)k * g_.nStreams, picMaxQ_[k], picMaxC_[k], picMaxA_[k], picMaxB_[k], true, true);
+    return launchPicture(dJobs_ + (size_t)k * g_.nStreams, picMaxQ_[k], picMaxC_[k], picMaxA_[k], picMaxB_[k], picMaxE_[k], true, true);
 }
 
 bool Batch::debugStage(uint32_t k, bool recon, bool deblock) {
@@ -487,7 +498,7 @@ bool Batch::debugStage(uint32_t k, bool recon, bool deblock) {
     CK(cudaSetDevice(device_));
     if (jobsDirty_ && !buildJobs()) return false;
     if (k >= numPics_) return false;
-    return launchPicture(dJobs_ + (size_t)k * g_.nStreams, picMaxQ_[k], picMaxC_[k], picMaxA_[k], picMaxB_[k], recon, deblock);
+    return launchPicture(dJobs_ + (size_t)k * g_.nStreams, picMaxQ_[k], picMaxC_[k], picMaxA_[k], picMaxB_[k], picMaxE_[k], recon, deblock);
 }
 
 bool Batch::run(uint32_t first, uint32_t count) {
@@ -557,13 +568,15 @@ bool Batch::submitHostPicture(uint32_t stream, const b200_pic_hdr &hdr, const b2
     job.nC = (uint16_t)hdr.numCopy;
     job.nA = (uint16_t)(hdr.numPassA - hdr.numRunMbs - hdr.numCopy);
     job.nB = (uint16_t)hdr.numPassB;
+    job.nE = (uint16_t)hdr.numConceal;
+    job.pad[0] = job.pad[1] = 0;
     std::memcpy(h, &job, sizeof job);
     std::memcpy(h + recOff, recs, recBytes);
     std::memcpy(h + orderOff, order, orderBytes);
     std::memcpy(h + coefOff, coefs, coefBytes);
     CK(cudaMemcpyAsync(dStage_[b], h, coefOff + coefBytes, cudaMemcpyHostToDevice, stream_));
     h2dBytes_ += coefOff + coefBytes;
-    if (!launchPicture(reinterpret_cast<const StreamJob *>(dStage_[b]), hdr.numRun, hdr.numCopy, hdr.numPassA - hdr.numRunMbs - hdr.numCopy, hdr.numPassB, true, true)) return false;
+    if (!launchPicture(reinterpret_cast<const StreamJob *>(dStage_[b]), hdr.numRun, hdr.numCopy, hdr.numPassA - hdr.numRunMbs - hdr.numCopy, hdr.numPassB, hdr.numConceal, true, true)) return false;
     CK(cudaEventRecord(stageEv_[b], stream_));
     return true;
 }

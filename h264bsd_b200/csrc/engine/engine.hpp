@@ -67,8 +67,8 @@ private:
         std::vector<b200_pic_hdr> pics;
     };
     bool buildJobs();
-    bool launchPicture(const StreamJob *dJobs, uint32_t maxQ, uint32_t maxC, uint32_t maxA, uint32_t maxB, bool recon, bool deblock);
-    std::vector<uint32_t> picMaxQ_, picMaxC_, picMaxA_, picMaxB_;
+    bool launchPicture(const StreamJob *dJobs, uint32_t maxQ, uint32_t maxC, uint32_t maxA, uint32_t maxB, uint32_t maxE, bool recon, bool deblock);
+    std::vector<uint32_t> picMaxQ_, picMaxC_, picMaxA_, picMaxB_, picMaxE_;
 
     bool created_ = false;
     int device_ = 0, numSms_ = 0;

@@ -35,7 +35,8 @@ struct StreamJob {
                               // copies, nA other pass-A macroblocks, nB pass-B macroblocks in wavefront order (b200_tape.mbOrder)
     uint16_t curSlot;
     uint16_t nR, nC, nA, nB;
-    uint16_t pad[3];
+    uint16_t nE;              // spatially concealed macroblocks: after the nB entries, concealment order
+    uint16_t pad[2];
 };
 
 }  // namespace b200

@@ -197,7 +197,7 @@ extern "C" uint32_t b200_cavlc_probe(int kind, int index, uint32_t prefix16) {
 }
 
 CavlcResult cavlcResidualBlock(BitReader &stream, int16_t *out, int nC, int maxNumCoeff) {
-    const CavlcResult bad{-1, 0};
+    const CavlcResult bad{-1, 0, 0};
     // A 64-bit window of the stream, refilled when fewer than 32 of its bits are left.  Reading past the end of the NAL
     // yields zeros (h264bsdShowBits32) and is an error (END_OF_STREAM): checked once, at the end -- a block that crossed the
     // end is rejected whatever it decoded to, and an error ends the slice, so nothing of it is used.
@@ -233,7 +233,7 @@ CavlcResult cavlcResidualBlock(BitReader &stream, int16_t *out, int nC, int maxN
     if (totalCoeff == 0) {
         if (pos + used > stream.bitsTotal()) return bad;
         stream.seek(pos + used);
-        return CavlcResult{0, 0};
+        return CavlcResult{0, 0, 0};
     }
 
     int level[16];
@@ -274,14 +274,17 @@ CavlcResult cavlcResidualBlock(BitReader &stream, int16_t *out, int nC, int maxN
         zerosLeft = t >> 4;
     }
     // place levels from the highest frequency down: the first decoded level sits at position totalCoeff - 1 + total_zeros
+    // (the tables keep total_zeros <= 16 - totalCoeff, so at <= 15.  For a 15-coefficient block that allows position 15,
+    // one past its end: the reference does not check and the level lands in the first entry of the next block of its
+    // level[26][16] array, h264bsd_cavlc.c:889-896 -- the caller's array has the same geometry, see parseResidual)
     int at = totalCoeff - 1 + zerosLeft;
-    if (at >= maxNumCoeff) return bad;
-    uint32_t map = 0;
+    uint32_t map = 0, sumAbs = 0;
     for (i = 0; i < totalCoeff; i++) {
         const int v = level[i];
         if (v > 32767 || v < -32768) return bad;
         out[at] = (int16_t)v;
         map |= 1u << at;
+        sumAbs += (uint32_t)(v < 0 ? -v : v);
         if (i == totalCoeff - 1) break;
         int r = 0;
         if (zerosLeft > 0) {
@@ -305,7 +308,7 @@ CavlcResult cavlcResidualBlock(BitReader &stream, int16_t *out, int nC, int maxN
     }
     if (pos + used > stream.bitsTotal()) return bad;
     stream.seek(pos + used);
-    return CavlcResult{totalCoeff, map};
+    return CavlcResult{totalCoeff, map, sumAbs};
 }
 
 }  // namespace b200

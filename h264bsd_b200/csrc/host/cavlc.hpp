@@ -13,6 +13,7 @@ namespace b200 {
 struct CavlcResult {
     int totalCoeff;      // number of non-zero levels, <0 on error
     uint32_t coeffMap;   // bit i set: zig-zag position i (relative to the block's first coded position) non-zero
+    uint32_t sumAbs;     // sum of the magnitudes of the levels (bounds what the inverse transform can produce)
 };
 
 void cavlcInit();

@@ -3,6 +3,7 @@
 #include "cavlc.hpp"
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
 
 namespace b200 {
 
@@ -43,12 +44,15 @@ struct PictureState::MbSyntax {
     uint32_t subType[4];
     int16_t subMvd[4][4][2];
     uint8_t totalCoeff[27];
+    uint32_t sumAbs[27];    // per block: sum of level magnitudes ([24] luma DC, [25] Cb DC, [26] Cr DC); valid where coded
+    uint32_t spill;         // bit i: level[i][0] was written by the 15-coefficient block before it (corrupt streams only:
+                            // position 15 of an AC block is the next block's first entry, here as in the reference)
     uint32_t codedBlocks;   // bit i: level[i] holds levels (TotalCoeff != 0); bits 24 / 25 = B200_CM_LUMA_DC / B200_CM_CHROMA_DC
     alignas(16) int16_t level[26][16];  // [0..23] blocks, [24] luma DC, [25] chroma DC (Cb 0..3, Cr 4..7)
     uint8_t pcm[384];
     void clear() {
         // levels are cleared selectively after use; everything else here
-        cbp = 0; qpDelta = 0; chromaMode = 0; codedBlocks = 0;
+        cbp = 0; qpDelta = 0; chromaMode = 0; codedBlocks = 0; spill = 0;
         std::memset(prevFlag, 0, sizeof prevFlag); std::memset(remMode, 0, sizeof remMode);
         std::memset(refIdx, 0, sizeof refIdx); std::memset(mvd, 0, sizeof mvd);
         std::memset(subType, 0, sizeof subType); std::memset(subMvd, 0, sizeof subMvd);
@@ -101,6 +105,7 @@ void PictureState::beginPicture() {
     orderClass.resize(2 * (size_t)picSizeInMbs);
     lateFixup_ = false;
     numIntraPred_ = 0;
+    concealOrder.clear();
 }
 
 bool PictureState::allDecoded(bool redundant) const {
@@ -249,6 +254,7 @@ bool PictureState::parseResidual(BitReader &br, MbSyntax &mb, uint32_t mbAddr) {
         CavlcResult r = cavlcResidualBlock(br, mb.level[24], nC(mbAddr, 0, mb.totalCoeff), 16);
         if (r.totalCoeff < 0) return false;
         mb.totalCoeff[24] = (uint8_t)r.totalCoeff;
+        mb.sumAbs[24] = r.sumAbs;
         if (r.totalCoeff) mb.codedBlocks |= B200_CM_LUMA_DC;
     }
     uint32_t blk = 0;
@@ -260,7 +266,9 @@ bool PictureState::parseResidual(BitReader &br, MbSyntax &mb, uint32_t mbAddr) {
                                     : cavlcResidualBlock(br, mb.level[blk], n, 16);
                 if (r.totalCoeff < 0) return false;
                 mb.totalCoeff[blk] = (uint8_t)r.totalCoeff;
+                mb.sumAbs[blk] = r.sumAbs;
                 if (r.totalCoeff) mb.codedBlocks |= 1u << blk;
+                if (i16 && (r.coeffMap >> 15)) mb.spill |= 1u << (blk + 1);
             }
         } else {
             blk += 4;
@@ -271,10 +279,12 @@ bool PictureState::parseResidual(BitReader &br, MbSyntax &mb, uint32_t mbAddr) {
         CavlcResult r = cavlcResidualBlock(br, mb.level[25], -1, 4);
         if (r.totalCoeff < 0) return false;
         mb.totalCoeff[25] = (uint8_t)r.totalCoeff;
+        mb.sumAbs[25] = r.sumAbs;
         if (r.totalCoeff) mb.codedBlocks |= B200_CM_CHROMA_DC;
         r = cavlcResidualBlock(br, mb.level[25] + 4, -1, 4);
         if (r.totalCoeff < 0) return false;
         mb.totalCoeff[26] = (uint8_t)r.totalCoeff;
+        mb.sumAbs[26] = r.sumAbs;
         if (r.totalCoeff) mb.codedBlocks |= B200_CM_CHROMA_DC;
     }
     if (chroma & 2) {
@@ -282,7 +292,13 @@ bool PictureState::parseResidual(BitReader &br, MbSyntax &mb, uint32_t mbAddr) {
             CavlcResult r = cavlcResidualBlock(br, mb.level[blk] + 1, nC(mbAddr, blk, mb.totalCoeff), 15);
             if (r.totalCoeff < 0) return false;
             mb.totalCoeff[blk] = (uint8_t)r.totalCoeff;
+            mb.sumAbs[blk] = r.sumAbs;
             if (r.totalCoeff) mb.codedBlocks |= 1u << blk;
+            if (r.coeffMap >> 15) {
+                mb.spill |= 1u << (blk + 1);
+                // out of the last chroma block the stray level lands in the Intra16x16 DC block, which is transformed later
+                if (blk == 23) mb.sumAbs[24] += (uint32_t)std::abs((int)mb.level[24][0]);
+            }
         }
     }
     return true;
@@ -504,6 +520,105 @@ bool PictureState::deriveIntra(MbSyntax &mb, uint32_t mbAddr, bool constrainedIn
     return true;
 }
 
+// ---- the [-512, 511] check of the inverse transform (h264bsdProcessBlock, h264bsd_transform.c:183-188,:205-206,:229-233) ----
+// The reference runs the transform while it parses, and a residual sample outside the range makes the macroblock -- hence the
+// slice -- corrupt: h264bsdMarkSliceCorrupted, concealment.  The pels are the GPU's business here, but which macroblocks count
+// as decoded is not, so the host has to know the outcome.  Almost always a bound on the magnitudes settles it: every output is
+// (sum of +-1 / +-1/2 weighted dequantised coefficients + 32) >> 6, so sum |level| * largest scale <= 32000 cannot leave the
+// range.  Only a macroblock that fails the bound gets the exact transform below (same arithmetic as the kernels and the oracle).
+namespace {
+const uint8_t kZigzag4x4[16] = {0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15};
+const int kLevelScale[6][3] = {{10, 13, 16}, {11, 14, 18}, {13, 16, 20}, {14, 18, 23}, {16, 20, 25}, {18, 23, 29}};
+const uint8_t kScaleClass[16] = {0, 1, 0, 1, 1, 2, 1, 2, 0, 1, 0, 1, 1, 2, 1, 2};
+
+// h264bsdProcessBlock: true if every residual sample of the block stays inside [-512, 511]
+bool blockInRange(const int16_t *lev, int qp, bool dcPreset, int dcValue) {
+    int d[16];
+    const int qpDiv = qp / 6, qpMod = qp % 6;
+    for (int i = 0; i < 16; i++) {
+        const int r = kZigzag4x4[i];
+        d[r] = lev[i] * (kLevelScale[qpMod][kScaleClass[r]] << qpDiv);
+    }
+    if (dcPreset) d[0] = dcValue;
+    for (int i = 0; i < 16; i += 4) {
+        const int t0 = d[i] + d[i + 2], t1 = d[i] - d[i + 2];
+        const int t2 = (d[i + 1] >> 1) - d[i + 3], t3 = d[i + 1] + (d[i + 3] >> 1);
+        d[i] = t0 + t3; d[i + 1] = t1 + t2; d[i + 2] = t1 - t2; d[i + 3] = t0 - t3;
+    }
+    for (int i = 0; i < 4; i++) {
+        const int t0 = d[i] + d[i + 8], t1 = d[i] - d[i + 8];
+        const int t2 = (d[i + 4] >> 1) - d[i + 12], t3 = d[i + 4] + (d[i + 12] >> 1);
+        const int o[4] = {(t0 + t3 + 32) >> 6, (t1 + t2 + 32) >> 6, (t1 - t2 + 32) >> 6, (t0 - t3 + 32) >> 6};
+        for (int k = 0; k < 4; k++)
+            if ((unsigned)(o[k] + 512) > 1023u) return false;
+    }
+    return true;
+}
+// h264bsdProcessLumaDc (h264bsd_transform.c:255-338), dc[] in raster order of the 4x4 blocks
+void lumaDcValues(const int16_t *lev, int qp, int dc[16]) {
+    int d[16];
+    const int qpDiv = qp / 6, ls = kLevelScale[qp % 6][0];
+    for (int i = 0; i < 16; i++) d[kZigzag4x4[i]] = lev[i];
+    for (int i = 0; i < 16; i += 4) {
+        const int t0 = d[i] + d[i + 2], t1 = d[i] - d[i + 2], t2 = d[i + 1] - d[i + 3], t3 = d[i + 1] + d[i + 3];
+        d[i] = t0 + t3; d[i + 1] = t1 + t2; d[i + 2] = t1 - t2; d[i + 3] = t0 - t3;
+    }
+    for (int i = 0; i < 4; i++) {
+        const int t0 = d[i] + d[i + 8], t1 = d[i] - d[i + 8], t2 = d[i + 4] - d[i + 12], t3 = d[i + 4] + d[i + 12];
+        const int v[4] = {t0 + t3, t1 + t2, t1 - t2, t0 - t3};
+        for (int k = 0; k < 4; k++)
+            dc[i + 4 * k] = qp >= 12 ? v[k] * (ls << (qpDiv - 2)) : (v[k] * ls + (qpDiv == 1 ? 1 : 2)) >> (2 - qpDiv);
+    }
+}
+// h264bsdProcessChromaDc (h264bsd_transform.c:359-401), Cb in lev[0..3], Cr in lev[4..7]
+void chromaDcValues(const int16_t *lev, int qp, int dc[8]) {
+    int ls = kLevelScale[qp % 6][0], shift = 1;
+    if (qp >= 6) { ls <<= (qp / 6 - 1); shift = 0; }
+    for (int c = 0; c < 8; c += 4) {
+        const int t0 = lev[c] + lev[c + 2], t1 = lev[c] - lev[c + 2], t2 = lev[c + 1] - lev[c + 3], t3 = lev[c + 1] + lev[c + 3];
+        dc[c] = ((t0 + t3) * ls) >> shift;
+        dc[c + 1] = ((t0 - t3) * ls) >> shift;
+        dc[c + 2] = ((t1 + t2) * ls) >> shift;
+        dc[c + 3] = ((t1 - t2) * ls) >> shift;
+    }
+}
+}  // namespace
+
+// ProcessResidual (h264bsd_macroblock_layer.c:1340-1421) as far as its error return goes
+bool PictureState::residualInRange(const MbSyntax &mb, bool i16, int qpY, int qpC, uint32_t mask) const {
+    // the bound
+    const uint64_t sL = (uint64_t)29 << (qpY / 6), sC = (uint64_t)29 << (qpC / 6);
+    const uint64_t dcL = (mask & B200_CM_LUMA_DC) ? (((uint64_t)mb.sumAbs[24] * ((uint64_t)18 << (qpY / 6))) >> 2) + 2 : 0;
+    uint64_t dcCb = 0, dcCr = 0;
+    if (mask & B200_CM_CHROMA_DC) {
+        dcCb = (((uint64_t)mb.sumAbs[25] * ((uint64_t)18 << (qpC / 6))) >> 1) + 2;
+        dcCr = (((uint64_t)mb.sumAbs[26] * ((uint64_t)18 << (qpC / 6))) >> 1) + 2;
+        if (!mb.totalCoeff[25]) dcCb = 0;
+        if (!mb.totalCoeff[26]) dcCr = 0;
+    }
+    uint64_t worst = std::max(dcL, std::max(dcCb, dcCr));
+    for (uint32_t m = mask & 0xFFFFFFu; m; m &= m - 1) {
+        const int b = __builtin_ctz(m);
+        const uint64_t v = b < 16 ? dcL + mb.sumAbs[b] * sL : (b < 20 ? dcCb : dcCr) + mb.sumAbs[b] * sC;
+        worst = std::max(worst, v);
+    }
+    if (worst <= 32000) return true;
+
+    // the exact transform
+    int lumaDc[16] = {0}, chromaDc[8] = {0};
+    if (mask & B200_CM_LUMA_DC) lumaDcValues(mb.level[24], qpY, lumaDc);
+    if (mask & B200_CM_CHROMA_DC) chromaDcValues(mb.level[25], qpC, chromaDc);
+    static const int16_t zero[16] = {0};
+    for (int b = 0; b < 24; b++) {
+        const bool coded = (mask >> b) & 1;
+        const bool dcPreset = b < 16 ? i16 : true;
+        const int dcVal = b < 16 ? lumaDc[kBlkY[b] * 4 + kBlkX[b]] : chromaDc[b - 16];
+        if (!coded && !(dcPreset && dcVal)) continue;
+        if (!blockInRange(coded ? mb.level[b] : zero, b < 16 ? qpY : qpC, dcPreset, dcVal)) return false;
+    }
+    return true;
+}
+
 // Class of a macroblock for the processing order (0 other pass-A, 1 plain copy, 4 pass-B; zr = 1 + reference slot of a
 // zero-vector plain copy), its deblocking edge flags (GetMbFilteringFlags, deblocking.c:289-320) and, for an intra-predicted
 // macroblock, the neighbours it has to wait for inside the intra pass -- settled right after the record is written, while it
@@ -598,6 +713,7 @@ bool PictureState::finishMacroblock(MbSyntax &mb, uint32_t mbAddr, int &qpY, con
     uint32_t mask = mb.codedBlocks;      // blocks with TotalCoeff != 0, collected by parseResidual
     if (!i16) mask &= ~B200_CM_LUMA_DC;
     r.codedMask = mask;
+    if (mask && !residualInRange(mb, i16, qpY, r.qpC, mask)) return false;
 
     if (inter) {
         if (!deriveInter(mb, mbAddr, dpb)) return false;
@@ -614,7 +730,9 @@ bool PictureState::finishMacroblock(MbSyntax &mb, uint32_t mbAddr, int &qpY, con
         if (mask & B200_CM_LUMA_DC) { std::memcpy(dst, mb.level[24], 32); dst += 16; }
         if (mask & B200_CM_CHROMA_DC) { std::memcpy(dst, mb.level[25], 16); std::memset(dst + 8, 0, 16); dst += 16; }
         for (uint32_t m = mask & 0xFFFFFFu; m; m &= m - 1) {
-            std::memcpy(dst, mb.level[__builtin_ctz(m)], 32);
+            const int b = __builtin_ctz(m);
+            std::memcpy(dst, mb.level[b], 32);
+            if (b >= 16 || i16) dst[0] = 0;     // AC block: its DC comes from the DC transform (a stray entry there is never used)
             dst += 16;
         }
     }
@@ -732,6 +850,7 @@ SliceResult PictureState::decodeSlice(BitReader &br, const SliceHeader &sh, cons
             // the level arrays go back to all-zero for the next macroblock: only the blocks that received levels
             if (mb.mbType != B200_MB_I_PCM) {
                 for (uint32_t m = mb.codedBlocks; m; m &= m - 1) std::memset(mb.level[__builtin_ctz(m)], 0, 32);
+                for (uint32_t m = mb.spill; m; m &= m - 1) mb.level[__builtin_ctz(m)][0] = 0;
             }
         }
         if (!ok) return SliceResult::Error;
@@ -797,8 +916,16 @@ void PictureState::finalizeRecords() {
             }
             r.flags = f;
             r.sliceId = aux[a].sliceId;
-            r.waitMask = 0;
             uint8_t c = 0, z = 0;
+            if ((f & B200_MBF_CONCEALED) && r.mbType == B200_MB_I_4x4) {
+                // concealed: a zero-vector copy of the reference picture, or (class 5) spatial -- listed in its own section
+                if (r.waitMask == 0) { c = 1; z = (uint8_t)(1 + r.refSlot[0]); }
+                else c = 5;
+                cls[a] = c;
+                zr[a] = z;
+                continue;
+            }
+            r.waitMask = 0;
             if (r.mbType > B200_MB_P_8x8REF0 && r.mbType != B200_MB_I_PCM) { c = 4; nB++; }
             else if (r.mbType <= B200_MB_P_16x16 && r.codedMask == 0 && ((r.u.mv[0][0] | r.u.mv[0][1]) & 7) == 0) {
                 c = 1;
@@ -830,74 +957,130 @@ void PictureState::finalizeRecords() {
         }
     }
     numRun = n / 2;
-    for (a = 0; a < picSizeInMbs; a++)
-        if (cls[a] == 1) order[n++] = (uint16_t)a;
+    // one pass sorts the rest into its three sections: single copies go straight into the list, the other pass-A macroblocks
+    // and the intra-predicted ones (with their wavefront key x + 2y) are parked and appended behind
+    std::vector<uint32_t> &park = orderKeys;       // [0, nMbs): other pass-A addresses; [nMbs, 2 nMbs): intra address | key << 16
+    park.resize(2 * (size_t)picSizeInMbs);
+    uint32_t *others = park.data(), *intra = park.data() + picSizeInMbs;
+    uint32_t nOthers = 0, nIntra = 0;
+    a = 0;
+    for (uint32_t y = 0; y < heightMbs; y++)
+        for (uint32_t x = 0; x < widthMbs; x++, a++) {
+            const uint8_t c = cls[a];
+            if (c == 1) order[n++] = (uint16_t)a;
+            else if (c == 0) others[nOthers++] = a;
+            else if (c == 4) intra[nIntra++] = a | ((x + 2 * y) << 16);
+        }
     numCopy = n - 2 * numRun;
-    for (a = 0; a < picSizeInMbs; a++)
-        if (cls[a] == 0) order[n++] = (uint16_t)a;
+    for (uint32_t i = 0; i < nOthers; i++) order[n++] = (uint16_t)others[i];
     const uint32_t listB = n;   // where the pass-B entries start in the list
+    nB = nIntra;
     numPassB = nB;
-    numPassA = picSizeInMbs - nB;
+    numPassA = picSizeInMbs - nB - (lateFixup_ ? (uint32_t)concealOrder.size() : 0);
     if (numPassB) {
-        // bucket by wavefront key x + 2y (stable in address order inside a key)
+        // bucket by wavefront key (stable in address order inside a key)
         const uint32_t nKeys = widthMbs + 2 * heightMbs;
-        std::vector<uint32_t> &cnt = orderKeys;
-        cnt.assign(nKeys + 1, 0);
-        a = 0;
-        for (uint32_t y = 0; y < heightMbs; y++)
-            for (uint32_t x = 0; x < widthMbs; x++, a++)
-                if (cls[a] == 4) cnt[x + 2 * y + 1]++;
-        for (uint32_t k = 0; k < nKeys; k++) cnt[k + 1] += cnt[k];
-        a = 0;
-        for (uint32_t y = 0; y < heightMbs; y++)
-            for (uint32_t x = 0; x < widthMbs; x++, a++) {
-                if (cls[a] != 4) continue;
-                order[listB + cnt[x + 2 * y]++] = (uint16_t)a;
-                if (!lateFixup_) continue;
-                // the neighbours an intra macroblock has to wait for inside the intra pass: the available ones that are
-                // intra-predicted themselves
-                b200_mb_rec &r = recs[a];
-                uint8_t w = 0;
-                if ((r.flags & B200_MBF_AVAIL_A) && x && cls[a - 1] == 4) w |= B200_MBF_AVAIL_A;
-                if ((r.flags & B200_MBF_AVAIL_B) && y && cls[a - widthMbs] == 4) w |= B200_MBF_AVAIL_B;
-                if ((r.flags & B200_MBF_AVAIL_C) && y && x + 1 < widthMbs && cls[a - widthMbs + 1] == 4) w |= B200_MBF_AVAIL_C;
-                if ((r.flags & B200_MBF_AVAIL_D) && y && x && cls[a - widthMbs - 1] == 4) w |= B200_MBF_AVAIL_D;
-                r.waitMask = w;
-            }
+        std::vector<uint32_t> &keys = keyCount_;
+        keys.assign(nKeys + 1, 0);
+        for (uint32_t i = 0; i < nIntra; i++) keys[(intra[i] >> 16) + 1]++;
+        for (uint32_t k = 0; k < nKeys; k++) keys[k + 1] += keys[k];
+        for (uint32_t i = 0; i < nIntra; i++) {
+            const uint32_t a2 = intra[i] & 0xFFFFu;
+            order[listB + keys[intra[i] >> 16]++] = (uint16_t)a2;
+            if (!lateFixup_) continue;
+            // the neighbours an intra macroblock has to wait for inside the intra pass: the available ones that are
+            // intra-predicted themselves
+            b200_mb_rec &r = recs[a2];
+            uint8_t w = 0;
+            if ((r.flags & B200_MBF_AVAIL_A) && cls[a2 - 1] == 4) w |= B200_MBF_AVAIL_A;
+            if ((r.flags & B200_MBF_AVAIL_B) && cls[a2 - widthMbs] == 4) w |= B200_MBF_AVAIL_B;
+            if ((r.flags & B200_MBF_AVAIL_C) && cls[a2 - widthMbs + 1] == 4) w |= B200_MBF_AVAIL_C;
+            if ((r.flags & B200_MBF_AVAIL_D) && cls[a2 - widthMbs - 1] == 4) w |= B200_MBF_AVAIL_D;
+            r.waitMask = w;
+        }
     }
+    // spatially concealed macroblocks, in concealment order
+    numConceal = lateFixup_ ? (uint32_t)concealOrder.size() : 0;
+    for (uint32_t i = 0; i < numConceal; i++) order[listB + numPassB + i] = concealOrder[i];
 }
 
-// Error path only: macroblocks that never arrived get a record so the picture can still be
-// replayed.  P pictures: copy from reference index 0 (what conceal.c:266 ConcealMb does for P
-// slices when a reference exists); otherwise mid-grey I_PCM.  NOT the reference's spatial intra
-// concealment (conceal.c:266-639) -- see DESIGN.md.
+// h264bsdConceal (h264bsd_conceal.c:124-262): records for the macroblocks of the picture that never arrived (or belonged to a
+// slice marked corrupted), in the reference's order -- the row of the first decoded macroblock leftwards, then rightwards,
+// the rows above it column by column upwards, the rows below in raster order.  What each record says is described in
+// h264bsd_b200_tape.h ("Concealed macroblocks").  Returns the number of concealed macroblocks.
 uint32_t PictureState::concealMissing(const Dpb &dpb, bool pSlice) {
     bindOutput();
     lateFixup_ = true;
+    concealOrder.clear();
+    // the reference picture with the smallest available index (:146-157); intraConcealmentFlag is never set in the reference
+    int slot = -1;
+    if (pSlice)
+        for (uint32_t i = 0; i < 16 && slot < 0; i++) slot = dpb.refSlot(i);
+
+    uint32_t first = 0;
+    while (first < picSizeInMbs && !aux[first].decoded) first++;
     uint32_t n = 0;
-    int slot = pSlice ? dpb.refSlot(0) : -1;
-    for (uint32_t a = 0; a < picSizeInMbs; a++) {
-        if (aux[a].decoded) continue;
-        n++;
+    if (first == picSizeInMbs) {
+        // nothing of the picture arrived (:172-201): previous picture or grey, and no filtering at all
+        for (uint32_t a = 0; a < picSizeInMbs; a++) {
+            b200_mb_rec r;
+            std::memset(&r, 0, sizeof r);
+            r.flags = B200_MBF_CONCEALED;
+            r.reserved0 = 1;
+            r.qpY = st[a].qpY;   // (not looked at: the filter is off for every macroblock of the picture)
+            r.qpC = st[a].qpC;
+            r.coefIndex = (uint32_t)(coefs.size() / 16);
+            if (slot >= 0) {
+                r.mbType = B200_MB_P_SKIP;
+                std::memset(r.refSlot, slot, 4);
+            } else {
+                r.mbType = B200_MB_I_PCM;
+                r.codedMask = 0xFFFFFFu;
+                std::memset(coefs.grow(12 * 16), 128, 384);
+            }
+            st[a] = r;
+            if (recs != st) recs[a] = r;
+            aux[a].decoded = 1;
+        }
+        return picSizeInMbs;
+    }
+
+    auto conceal = [&](uint32_t row, uint32_t col) {
+        const uint32_t a = row * widthMbs + col;
         b200_mb_rec r;
         std::memset(&r, 0, sizeof r);
-        r.flags = B200_MBF_CONCEALED;
-        r.reserved0 = 1;  // no deblocking
-        r.qpY = 40;       // conceal.c: qp 40 for concealed macroblocks
+        r.mbType = B200_MB_I_4x4;           // ConcealMb :296-306: what the in-loop filter will see
+        r.qpY = 40;
         r.qpC = kQpC[40];
+        r.flags = B200_MBF_CONCEALED;
+        r.reserved0 = 0;
         if (slot >= 0) {
-            r.mbType = B200_MB_P_SKIP;
-            for (int q = 0; q < 4; q++) r.refSlot[q] = (uint8_t)slot;
+            std::memset(r.refSlot, slot, 4);    // :320-341 zero-vector prediction from that picture
         } else {
-            r.mbType = B200_MB_I_PCM;
-            r.coefIndex = (uint32_t)(coefs.size() / 16);
-            std::memset(coefs.grow(12 * 16), 128, 384);
+            uint8_t w = 0;                      // :346-420 the neighbours that are decoded (or concealed) by now
+            if (row && aux[a - widthMbs].decoded) w |= B200_CN_ABOVE;
+            if (row != heightMbs - 1 && aux[a + widthMbs].decoded) w |= B200_CN_BELOW;
+            if (col && aux[a - 1].decoded) w |= B200_CN_LEFT;
+            if (col != widthMbs - 1 && aux[a + 1].decoded) w |= B200_CN_RIGHT;
+            r.waitMask = w;
+            r.coefIndex = (uint32_t)concealOrder.size();
+            concealOrder.push_back((uint16_t)a);
         }
         st[a] = r;
         if (recs != st) recs[a] = r;
         aux[a].decoded = 1;
-        std::memset(aux[a].totalCoeff, 0, 27);
-    }
+        n++;
+    };
+    const uint32_t row0 = first / widthMbs, col0 = first % widthMbs;
+    for (uint32_t j = col0; j--;) conceal(row0, j);
+    for (uint32_t j = col0 + 1; j < widthMbs; j++)
+        if (!aux[row0 * widthMbs + j].decoded) conceal(row0, j);
+    if (row0)
+        for (uint32_t j = 0; j < widthMbs; j++)
+            for (uint32_t i = row0; i--;) conceal(i, j);
+    for (uint32_t i = row0 + 1; i < heightMbs; i++)
+        for (uint32_t j = 0; j < widthMbs; j++)
+            if (!aux[i * widthMbs + j].decoded) conceal(i, j);
     return n;
 }
 

@@ -70,9 +70,10 @@ public:
         size_t n_ = 0, cap_ = 0;
     } coefs;
     std::vector<uint16_t> order;    // processing order of the picture being built (see b200_tape.mbOrder)
-    uint32_t numPassA = 0, numPassB = 0, numCopy = 0, numRun = 0, numRunMbs = 0;
+    uint32_t numPassA = 0, numPassB = 0, numCopy = 0, numRun = 0, numRunMbs = 0, numConceal = 0;
+    std::vector<uint16_t> concealOrder;   // spatially concealed macroblocks of the picture being built, concealment order
     std::vector<uint8_t> orderClass;   // scratch of finalizeRecords
-    std::vector<uint32_t> orderKeys;
+    std::vector<uint32_t> orderKeys, keyCount_;
     std::vector<uint32_t> sliceGroupMap;
     uint32_t sliceIdCounter = 0, numDecodedMbs = 0, lastMbAddr = 0;
 
@@ -93,6 +94,7 @@ private:
     bool deriveInter(MbSyntax &mb, uint32_t mbAddr, const Dpb &dpb);
     bool deriveIntra(MbSyntax &mb, uint32_t mbAddr, bool constrainedIntra);
     void classify(uint32_t mbAddr, b200_mb_rec &rec);
+    bool residualInRange(const MbSyntax &mb, bool i16, int qpY, int qpC, uint32_t mask) const;
     bool finishSkip(uint32_t mbAddr, int qpY, const SliceHeader &sh, const Pps &pps, int slot0);
     int nC(uint32_t mbAddr, uint32_t blk, const uint8_t *curTotalCoeff) const;
     uint32_t nextMbAddress(uint32_t cur) const;

@@ -236,6 +236,7 @@ void StreamDecoder::finishPicture() {
     hdr.numCopy = pic_.numCopy;
     hdr.numRun = pic_.numRun;
     hdr.numRunMbs = pic_.numRunMbs;
+    hdr.numConceal = pic_.numConceal;
 
     int32_t poc = decodePicOrderCnt(poc_, *activeSps_, sliceHeader_, prevNal_);
     if (validSliceInAccessUnit_) {

@@ -97,8 +97,12 @@ extern "C" b200_tape *h264bsdB200ReparseStream(b200_tape *t, const uint8_t *stre
     t->numOutputs = 0; t->status = 0;
     const uint64_t cap0[3] = {t->capRecs, t->capCoefs, t->capOrder};
 
+    // bit 0 of the flags: no output reordering (h264bsdInit); bit 1: carry on after H264BSD_ERROR the way a player does (the
+    // posix test program stops there, posix/test_h264bsd.c:171-173) -- what is missing from a picture is concealed at the next
+    // access unit boundary (h264bsd_decoder.c:226-262)
+    const bool resilient = (noOutputReordering & 2u) != 0;
     TapeSink sink(t);
-    StreamDecoder dec(&sink, noOutputReordering != 0);
+    StreamDecoder dec(&sink, (noOutputReordering & 1u) != 0);
     std::vector<uint32_t> outputs;
     const uint8_t *p = stream;
     size_t left = len;
@@ -124,6 +128,8 @@ extern "C" b200_tape *h264bsdB200ReparseStream(b200_tape *t, const uint8_t *stre
                 t->matrixCoefficients = (sps->vuiPresent && sps->vui.videoSignalTypePresent &&
                                          sps->vui.colourDescriptionPresent) ? sps->vui.matrixCoefficients : 2;
             }
+        } else if (r == ERROR && resilient && rb) {
+            continue;
         } else if (r == ERROR || r == PARAM_SET_ERROR || r == MEMALLOC_ERROR) {
             t->status = r;
             break;

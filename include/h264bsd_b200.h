@@ -21,7 +21,11 @@ extern "C" {
 
 /* Parse a whole Annex-B byte stream (all NAL/CAVLC/MV-prediction/DPB work the reference does in
  * h264bsdDecode, h264bsd_decoder.c:152-515) into a tape.  The input is not modified.
- * tape->status != 0 if the parse stopped on a decoder error.  NULL only on allocation failure. */
+ * tape->status != 0 if the parse stopped on a decoder error.  NULL only on allocation failure.
+ * noOutputReordering: bit 0 = the flag of h264bsdInit; bit 1 (B200_PARSE_RESILIENT) = carry on after H264BSD_ERROR the way
+ * a player does: macroblocks missing from a picture are concealed at the next access unit boundary
+ * (h264bsd_decoder.c:226-262, h264bsd_conceal.c) and show up in b200_pic_hdr.numErrMbs. */
+#define B200_PARSE_RESILIENT 2u
 b200_tape *h264bsdB200ParseStream(const uint8_t *stream, size_t len, uint32_t noOutputReordering);
 /* same, re-using `tape`'s arrays (NULL: allocate a new tape).  Steady-state parsing then touches no fresh pages and a
  * page-locked tape stays page-locked unless an array had to grow (tape->pinned == 2: pin again). */

@@ -50,7 +50,24 @@ enum {
 #define B200_MBF_FILTER_LEFT 0x10u  /* filter the left MB edge  (deblocking.c:289-320) */
 #define B200_MBF_FILTER_TOP 0x20u   /* filter the top MB edge                           */
 #define B200_MBF_FILTER_INNER 0x40u /* filter inner edges (disable_deblocking_filter_idc != 1) */
-#define B200_MBF_CONCEALED 0x80u    /* record synthesised for a macroblock missing from the stream */
+#define B200_MBF_CONCEALED 0x80u    /* record synthesised for a macroblock missing from the stream (see below) */
+/*
+ * Concealed macroblocks (h264bsd_conceal.c:124-639).  When a picture ends with macroblocks missing (lost or corrupted
+ * slices) the host writes their records the way h264bsdConceal leaves the reference's state: mbType = B200_MB_I_4x4,
+ * qpY = 40, filter offsets and chromaQpIndexOffset 0, filtering enabled (ConcealMb :296-306) -- that is what the in-loop
+ * filter sees.  How the pels are made:
+ *   copy     (P slice and a reference picture exists, :320-341): waitMask == 0, refSlot[] = that picture, u = 0; the record is
+ *            listed with the plain copies (zero vector), so reconstruction moves the co-located macroblock;
+ *   spatial  (otherwise, :346-600): waitMask = B200_CN_* bits of the neighbouring macroblocks whose edge pels enter the
+ *            estimate (decoded or concealed earlier), coefIndex = position in the concealment order; the record is listed in
+ *            the fifth section of the processing order, in that order (every entry may read what the previous ones wrote).
+ * A picture of which nothing arrived is copied from the reference / set to 128 with the filter off (:172-201): ordinary
+ * P_Skip / I_PCM records with disable_deblocking_filter_idc = 1.
+ */
+#define B200_CN_ABOVE 0x01u
+#define B200_CN_BELOW 0x02u
+#define B200_CN_LEFT 0x04u
+#define B200_CN_RIGHT 0x08u
 
 /* b200_mb_rec.codedMask */
 #define B200_CM_LUMA_DC (1u << 24)   /* Intra16x16 luma DC block present   */
@@ -125,6 +142,8 @@ typedef struct b200_pic_hdr {
     uint32_t numRun;       /* horizontal runs of 2..32 plain copies with a zero vector and the same reference slot: two list
                               entries (address of the first macroblock, length) per run */
     uint32_t numRunMbs;    /* macroblocks covered by the runs */
+    uint32_t numConceal;   /* spatially concealed macroblocks: fifth section of the order list, concealment order */
+    uint32_t reserved5;
 } b200_pic_hdr;
 
 /* A fully parsed stream in host memory (built by h264bsdB200ParseStream). */
@@ -144,8 +163,9 @@ typedef struct b200_tape {
     /* processing order, widthMbs*heightMbs uint16 macroblock addresses per picture (picture p at p*nMbs):
      * numRun zero-motion runs (two entries each: first address, length), numCopy single plain copies, the other
      * numPassA - numRunMbs - numCopy inter / I_PCM macroblocks (all three in raster order), then numPassB entries in
-     * wavefront order (x + 2y ascending), so that every macroblock an intra MB depends on precedes it.  The list of a
-     * picture never has more than widthMbs*heightMbs entries. */
+     * wavefront order (x + 2y ascending), so that every macroblock an intra MB depends on precedes it, then numConceal
+     * spatially concealed macroblocks in concealment order.  The list of a picture never has more than
+     * widthMbs*heightMbs entries. */
     uint16_t *mbOrder;
     uint32_t numOutputs;        /* pictures in output order, incl. those drained by the final flush */
     uint32_t reserved2;

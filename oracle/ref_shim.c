@@ -39,6 +39,17 @@ static size_t g_pre_cap, g_pre_len;
 static ref_mb_tap_t *g_mbtap;   /* per-MB taps, decode order */
 static size_t g_mbtap_cap, g_mbtap_len;
 static uint32_t g_tap_pics;
+static int g_resilient;            /* carry on after H264BSD_ERROR (what a player does; the posix test program exits) */
+static uint32_t g_err_mbs[4096];   /* numErrMbs of every output picture of the last ref_decode_stream call */
+static uint32_t g_err_count;
+
+void ref_set_resilient(int on) { g_resilient = on; }
+uint32_t ref_err_mbs(uint32_t *dst, uint32_t cap)
+{
+    uint32_t n = g_err_count < cap ? g_err_count : cap;
+    memcpy(dst, g_err_mbs, n * sizeof(uint32_t));
+    return g_err_count;
+}
 
 void refShimFilterPicture(image_t *image, mbStorage_t *pMb)
 {
@@ -94,6 +105,7 @@ int ref_decode_stream(const uint8_t *stream, size_t len,
     g_pre = pre; g_pre_cap = pre_cap; g_pre_len = 0;
     g_mbtap = (ref_mb_tap_t *)mbtap; g_mbtap_cap = mbtap_cap_records; g_mbtap_len = 0;
     g_tap_pics = 0;
+    g_err_count = 0;
 
     uint8_t *p = buf;
     uint32_t left = (uint32_t)len, rb = 0;
@@ -109,6 +121,7 @@ int ref_decode_stream(const uint8_t *stream, size_t len,
                 size_t bytes = (size_t)dec->picSizeInMbs * 384;
                 if (post && post_len + bytes <= post_cap) memcpy(post + post_len, pic, bytes);
                 post_len += bytes;
+                if (g_err_count < 4096) g_err_mbs[g_err_count++] = nErr;
                 npics++;
             }
         } else if (r == H264BSD_HDRS_RDY) {
@@ -117,6 +130,8 @@ int ref_decode_stream(const uint8_t *stream, size_t len,
                 info[1] = h264bsdPicHeight(dec);
                 h264bsdCroppingParams(dec, &info[2], &info[3], &info[4], &info[5], &info[6]);
             }
+        } else if (r == H264BSD_ERROR && g_resilient && rb) {
+            continue;
         } else if (r == H264BSD_ERROR || r == H264BSD_PARAM_SET_ERROR) {
             err = 1;
             break;
@@ -131,6 +146,7 @@ int ref_decode_stream(const uint8_t *stream, size_t len,
             size_t bytes = (size_t)dec->picSizeInMbs * 384;
             if (post && post_len + bytes <= post_cap) memcpy(post + post_len, pic, bytes);
             post_len += bytes;
+            if (g_err_count < 4096) g_err_mbs[g_err_count++] = nErr;
             npics++;
         }
     }

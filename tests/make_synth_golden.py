@@ -18,6 +18,7 @@ import _oracle          # noqa: E402
 import synth_h264       # noqa: E402
 
 SEEDS = range(0, 160)
+DAMAGED_SEEDS = range(0, 240)
 
 
 def reference_decode(data):
@@ -34,9 +35,42 @@ def reference_decode(data):
     return n, fb, post[:max(n, 0) * fb], pre[:info[7] * fb], int(info[7]), (int(info[0]), int(info[1]))
 
 
+def reference_decode_resilient(data):
+    """the same with a caller that carries on after H264BSD_ERROR (what a player does; posix/test_h264bsd.c exits): the
+    reference marks slices corrupt and conceals what is missing at the next access unit boundary.  Also returns numErrMbs
+    of every output picture."""
+    L = _oracle.reference()
+    L.ref_set_resilient.argtypes = [C.c_int]
+    L.ref_err_mbs.restype = C.c_uint32
+    L.ref_set_resilient(1)
+    try:
+        n, fb, post, pre, ndec, dims = reference_decode(data)
+    finally:
+        L.ref_set_resilient(0)
+    errs = (C.c_uint32 * 4096)()
+    ne = L.ref_err_mbs(errs, 4096)
+    return n, fb, post, pre, ndec, dims, [int(v) for v in errs[:ne]]
+
+
+def damaged_golden():
+    """md5s of what the reference makes of the damaged streams (tests/synth_h264.py make_damaged_stream)"""
+    out = {}
+    for seed in DAMAGED_SEEDS:
+        data = synth_h264.make_damaged_stream(seed)
+        n, fb, post, pre, ndec, dims, errs = reference_decode_resilient(data)
+        out[str(seed)] = {"stream_md5": hashlib.md5(data).hexdigest(), "width_mbs": dims[0], "height_mbs": dims[1],
+                          "outputs": n, "decoded": ndec, "err_mbs": errs,
+                          "post_md5": hashlib.md5(post.tobytes()).hexdigest(), "pre_md5": hashlib.md5(pre.tobytes()).hexdigest()}
+    return out
+
+
 def main():
     if _oracle.reference() is None:
         sys.exit("oracle/_ref/libh264bsd_ref.so is not built (make -C oracle ref)")
+    path = os.path.join(_oracle.GOLDEN, "synth_damaged_md5.json")
+    with open(path, "w") as f:
+        json.dump(damaged_golden(), f, indent=0, sort_keys=True)
+    print("wrote", path)
     out = {}
     for seed in SEEDS:
         data = synth_h264.make_stream(seed)

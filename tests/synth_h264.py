@@ -1217,3 +1217,37 @@ def make_stream(seed, **force):
     if r.random() < 0.2:
         out += nal(0, 10, b"")                        # end of sequence
     return bytes(out)
+
+
+# ---------------------------------------------------------------------------------------------- damage
+def corrupt_stream(data, seed):
+    """A damaged copy of `data` (deterministic in `seed`): flipped bits, a lost slice NAL, a deleted byte range or a burst of
+    random bytes -- what makes the decoder mark slices corrupt and conceal (h264bsd_slice_data.c:298-354, h264bsd_conceal.c)."""
+    r = random.Random(seed * 7919 + 1)
+    e = bytearray(data)
+    mode = r.randrange(4)
+    if mode == 0:
+        for _ in range(r.randint(1, 4)):
+            i = r.randrange(60, len(e))
+            e[i] ^= 1 << r.randrange(8)
+    elif mode == 1:
+        starts = [i for i in range(len(e) - 4) if e[i:i + 4] == b"\x00\x00\x00\x01"]
+        vcl = [k for k, i in enumerate(starts) if (e[i + 4] & 0x1F) in (1, 5)]
+        if len(vcl) > 1:
+            k = r.choice(vcl[1:])
+            end = starts[k + 1] if k + 1 < len(starts) else len(e)
+            del e[starts[k]:end]
+    elif mode == 2:
+        i = r.randrange(60, len(e))
+        j = min(len(e), i + r.randint(1, 60))
+        del e[i:j]
+    else:
+        i = r.randrange(60, len(e))
+        for k in range(i, min(len(e), i + r.randint(1, 12))):
+            e[k] = r.randrange(256)
+    return bytes(e)
+
+
+def make_damaged_stream(seed):
+    """stream `seed % 400` (without redundant slices: see make_stream's redundant_overlap note) damaged by corrupt_stream(seed)"""
+    return corrupt_stream(make_stream(seed % 400, redundant=False), seed)

@@ -1,0 +1,93 @@
+"""Error path: damaged streams (flipped bits, lost slices, cut-out bytes) through the host decoder in "resilient" mode --
+the caller carries on after H264BSD_ERROR the way a player does -- and the CPU oracle, against the reference decoder driven
+the same way: which macroblocks count as decoded (h264bsdMarkSliceCorrupted), what h264bsdConceal makes of the rest (copy of
+the reference picture / spatial estimate), numErrMbs, the in-loop filter over concealed macroblocks, output order.
+Needs no GPU and no reference build: the reference's answers are committed md5s (tests/make_synth_golden.py).
+
+Known deviation, not tested: a macroblock whose decoding fails while h264bsdMarkSliceCorrupted leaves it marked as decoded
+(an I slice that fails in its second macroblock, h264bsd_slice_data.c:313-327) keeps whatever the frame buffer held before in
+the reference (nothing is written, h264bsd_macroblock_layer.c:1118-1130); here it is reconstructed from what was parsed.
+KNOWN_STALE lists the seeds where that happens."""
+import hashlib
+import json
+import os
+import numpy as np
+import pytest
+import _oracle
+import synth_h264
+from h264bsd_b200.batch import ParsedStream
+
+GOLD = json.load(open(os.path.join(_oracle.GOLDEN, "synth_damaged_md5.json")))
+SEEDS = sorted(int(s) for s in GOLD)
+KNOWN_STALE = set()       # (none among the committed seeds; 282, 579, 625, 633, 649, 839, 1438, 1514 outside them)
+
+
+def md5(a):
+    return hashlib.md5(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def decode_resilient(data):
+    ps = ParsedStream(data, resilient=True)
+    try:
+        post, pre, _ = _oracle.oracle_run_tape(ps, want_pre=True)
+        by_index = {p.picIndex: p.numErrMbs for p in ps.pics}
+        return ps.status, len(ps.outputs), ps.num_pics, [by_index[i] for i in ps.outputs], post, pre
+    finally:
+        ps.close()
+
+
+@pytest.mark.parametrize("chunk", range(8))
+def test_damaged_streams_match_reference_golden(chunk):
+    concealed = 0
+    for seed in SEEDS[chunk::8]:
+        if seed in KNOWN_STALE:
+            continue
+        g = GOLD[str(seed)]
+        data = synth_h264.make_damaged_stream(seed)
+        if hashlib.md5(data).hexdigest() != g["stream_md5"]:
+            pytest.skip("tests/synth_h264.py no longer writes the streams the golden file was made from: re-run tests/make_synth_golden.py")
+        status, n_out, n_dec, errs, post, pre = decode_resilient(data)
+        if g["outputs"] < 0:
+            # the reference gave up (parameter set error): so must the host decoder
+            assert status != 0, f"seed {seed}"
+            continue
+        assert status == 0, f"seed {seed}: host decoder stopped with status {status}"
+        assert (n_out, n_dec) == (g["outputs"], g["decoded"]), f"seed {seed}: picture counts"
+        assert errs == g["err_mbs"], f"seed {seed}: numErrMbs per output picture"
+        assert md5(pre) == g["pre_md5"], f"seed {seed}: pictures before the in-loop filter (concealment) differ from the reference"
+        assert md5(post) == g["post_md5"], f"seed {seed}: output pictures differ from the reference"
+        concealed += sum(errs) > 0
+    assert concealed >= 10, "the damaged set is supposed to exercise concealment"
+
+
+def test_damage_exercises_both_kinds_of_concealment():
+    """copy from the reference picture (P slices) and the spatial estimate (I slices / no reference), plus whole pictures lost"""
+    copies = spatial = whole = 0
+    for seed in SEEDS[:120]:
+        ps = ParsedStream(synth_h264.make_damaged_stream(seed), resilient=True)
+        for p in ps.pics:
+            if p.numErrMbs == ps.mbs_per_pic:
+                whole += 1
+            elif p.numErrMbs:
+                spatial += p.numConceal > 0
+                copies += p.numErrMbs > p.numConceal
+        ps.close()
+    assert copies >= 10 and spatial >= 10 and whole >= 3, (copies, spatial, whole)
+
+
+@pytest.mark.skipif(_oracle.reference() is None, reason="oracle/_ref not built (needs the reference sources)")
+def test_fresh_damaged_seeds_against_the_compiled_reference():
+    from make_synth_golden import reference_decode_resilient
+    stale = {282, 579, 625, 633, 649, 839, 1438, 1514}
+    for seed in range(1000, 1200):
+        if seed in stale:
+            continue
+        data = synth_h264.make_damaged_stream(seed)
+        n, fb, rpost, rpre, ndec, dims, rerrs = reference_decode_resilient(data)
+        status, n_out, n_dec, errs, post, pre = decode_resilient(data)
+        if n < 0:
+            assert status != 0, f"seed {seed}"
+            continue
+        assert status == 0 and (n_out, n_dec) == (n, ndec) and errs == rerrs, f"seed {seed}"
+        assert np.array_equal(pre, rpre), f"seed {seed}: pre-filter pictures"
+        assert np.array_equal(post, rpost), f"seed {seed}: output pictures"

@@ -61,3 +61,47 @@ def test_legacy_api_matches_reference_golden(chunk):
         for f in frames:
             h.update(np.ascontiguousarray(f).tobytes())
         assert h.hexdigest() == g["post_md5"], f"seed {seed}: output pictures differ from the reference"
+
+
+DAMAGED = json.load(open(os.path.join(_oracle.GOLDEN, "synth_damaged_md5.json")))
+
+
+@pytest.mark.xfail(strict=False, reason="error-concealment path (concealKernel, concealed-copy records) was written after round 1's GPU "
+                                        "budget was spent: not yet run on hardware -- the first run decides (DESIGN.md, known gaps)")
+@pytest.mark.parametrize("chunk", range(4))
+def test_damaged_streams_concealment_matches_oracle(chunk):
+    """damaged streams in resilient mode: lost macroblocks copied from the reference picture or estimated from their
+    neighbours (concealKernel), then filtered as intra / QP 40 -- every picture against the CPU oracle, the output against the
+    reference decoder's md5"""
+    seeds = sorted(int(s) for s in DAMAGED)[chunk::4]
+    concealed = 0
+    for seed in seeds:
+        g = DAMAGED[str(seed)]
+        data = synth_h264.make_damaged_stream(seed)
+        if hashlib.md5(data).hexdigest() != g["stream_md5"]:
+            pytest.skip("generator drifted from tests/golden/synth_damaged_md5.json")
+        ps = ParsedStream(data, resilient=True)
+        if ps.status != 0 or ps.num_pics == 0:
+            ps.close()
+            continue
+        orc = _oracle.OracleDecoder(ps)
+        b = Batch(1, ps.width_mbs, ps.height_mbs, ps.num_slots)
+        b.upload(0, ps)
+        post = hashlib.md5()
+        out_of = {}
+        for k in range(ps.num_pics):
+            slot = ps.pics[k].curSlot
+            b.debug_stage(k, True, False)
+            orc.recon(k)
+            assert np.array_equal(b.read_frame(0, slot), orc.frame(slot)), f"seed {seed}: reconstruction / concealment of picture {k}"
+            b.debug_stage(k, False, True)
+            orc.deblock(k)
+            f = b.read_frame(0, slot)
+            assert np.array_equal(f, orc.frame(slot)), f"seed {seed}: in-loop filter of picture {k}"
+            out_of[ps.pics[k].picIndex] = f.copy()      # (a slot is not reused before its picture has been output)
+            concealed += ps.pics[k].numErrMbs > 0
+        assert b.watchdog() == (0, 0), f"seed {seed}"
+        b.close()
+        orc.close()
+        ps.close()
+    assert concealed > 0
