@@ -34,8 +34,12 @@ static bool ensure(T *&p, uint64_t &capBytes, uint64_t needBytes) {
 class TapeSink : public PictureSink {
 public:
     explicit TapeSink(b200_tape *t) : t_(t) {}
-    bool ok = true, repin = false;
+    bool ok = true, repin = false, sizeChanged = false;
     bool configure(uint32_t w, uint32_t h, uint32_t slots) override {
+        // a tape holds pictures of one size (the batched engine lays out its frame pool once): a stream that activates a
+        // sequence parameter set with another size ends the tape here (B200_TAPE_SIZE_CHANGE); such streams are for the
+        // h264bsdDecode API, which re-allocates on H264BSD_HDRS_RDY like the reference
+        if (t_->numPics && (w != t_->widthMbs || h != t_->heightMbs)) { sizeChanged = true; return false; }
         t_->widthMbs = w; t_->heightMbs = h;
         if (slots > t_->numSlots) t_->numSlots = slots;
         return true;
@@ -136,6 +140,7 @@ extern "C" b200_tape *h264bsdB200ReparseStream(b200_tape *t, const uint8_t *stre
         }
     }
     if (!sink.ok) t->status = MEMALLOC_ERROR;
+    if (sink.sizeChanged) t->status = B200_TAPE_SIZE_CHANGE;
     if (!t->status) {
         dec.flushBuffer();
         while (const OutPic *o = dec.nextOutput()) outputs.push_back(o->picIndex);

@@ -146,6 +146,10 @@ typedef struct b200_pic_hdr {
     uint32_t reserved5;
 } b200_pic_hdr;
 
+/* tape.status when the stream switches to another picture size: the tape ends with the last picture of the old size
+ * (a tape -- and the frame pool of the batched engine -- holds one size; h264bsdDecode handles such streams) */
+#define B200_TAPE_SIZE_CHANGE 100u
+
 /* A fully parsed stream in host memory (built by h264bsdB200ParseStream). */
 typedef struct b200_tape {
     uint32_t numPics;
@@ -170,7 +174,7 @@ typedef struct b200_tape {
     uint32_t numOutputs;        /* pictures in output order, incl. those drained by the final flush */
     uint32_t reserved2;
     uint32_t *outputPicIndex;   /* numOutputs decode-order indices */
-    uint32_t status;            /* 0 ok, else the H264BSD_* code the parse stopped on */
+    uint32_t status;            /* 0 ok, else the H264BSD_* code the parse stopped on, or B200_TAPE_SIZE_CHANGE */
     uint32_t pinned;            /* 0 pageable, 1 arrays page-locked (h264bsdB200PinTape), 2 page-lock stale after growth */
     /* allocation sizes of the arrays (they are kept when a tape is re-used, h264bsdB200ReparseStream) */
     uint64_t capRecs, capCoefs, capOrder, capPics;

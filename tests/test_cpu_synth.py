@@ -90,3 +90,19 @@ def test_fresh_seeds_against_the_compiled_reference():
         assert (n_out, n_dec, odims) == (n, ndec, dims), f"seed {seed}"
         assert np.array_equal(pre, rpre), f"seed {seed}: pre-filter pictures"
         assert np.array_equal(post, rpost), f"seed {seed}: output pictures"
+
+
+def test_sequence_change_same_size_and_other_size():
+    """two coded video sequences back to back: with the same picture size the tape simply goes on (and matches the reference,
+    new IDR, new parameter sets); a change of picture size ends the tape (B200_TAPE_SIZE_CHANGE) with the first sequence intact"""
+    a, b = synth_h264.make_stream(3, W=4, H=3), synth_h264.make_stream(7, W=4, H=3)
+    n_a = decode_with_oracle(a)[1]
+    n_out, n_dec, dims, post, pre = decode_with_oracle(a + b)
+    assert dims == (4, 3) and n_dec == n_a + decode_with_oracle(b)[1]
+    if _oracle.reference() is not None:
+        from make_synth_golden import reference_decode
+        n, fb, rpost, rpre, ndec, rdims = reference_decode(a + b)
+        assert (n, ndec) == (n_out, n_dec) and np.array_equal(post, rpost) and np.array_equal(pre, rpre)
+    ps = ParsedStream(a + synth_h264.make_stream(7, W=6, H=2))
+    assert ps.status == 100 and (ps.width_mbs, ps.height_mbs) == (4, 3) and ps.num_pics == n_a
+    ps.close()
