@@ -39,4 +39,7 @@ struct StreamJob {
     uint16_t pad[2];
 };
 
+static_assert(sizeof(StreamJob) == 40, "StreamJob is copied to the device as is");
+static_assert(sizeof(b200_mb_rec) == B200_MB_REC_BYTES, "record layout");
+
 }  // namespace b200

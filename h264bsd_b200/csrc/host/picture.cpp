@@ -51,11 +51,10 @@ struct PictureState::MbSyntax {
     alignas(16) int16_t level[26][16];  // [0..23] blocks, [24] luma DC, [25] chroma DC (Cb 0..3, Cr 4..7)
     uint8_t pcm[384];
     void clear() {
-        // levels are cleared selectively after use; everything else here
+        // what a macroblock may read without having parsed it: the level arrays are cleared selectively after use, the
+        // prediction syntax (prevFlag / remMode / mvd / subType / subMvd) is written for exactly the entries that are read
         cbp = 0; qpDelta = 0; chromaMode = 0; codedBlocks = 0; spill = 0;
-        std::memset(prevFlag, 0, sizeof prevFlag); std::memset(remMode, 0, sizeof remMode);
-        std::memset(refIdx, 0, sizeof refIdx); std::memset(mvd, 0, sizeof mvd);
-        std::memset(subType, 0, sizeof subType); std::memset(subMvd, 0, sizeof subMvd);
+        std::memset(refIdx, 0, sizeof refIdx);
         std::memset(totalCoeff, 0, sizeof totalCoeff);
     }
 };
@@ -673,17 +672,7 @@ bool PictureState::finishMacroblock(MbSyntax &mb, uint32_t mbAddr, int &qpY, con
     r.intraChromaMode = 0;
     r.subMbTypes = 0;
 
-    if (type == B200_MB_P_SKIP) {
-        std::memset(ax.totalCoeff, 0, 27);
-        r.qpY = (uint8_t)qpY;
-        r.qpC = kQpC[std::min(51, std::max(0, qpY + pps.chromaQpIndexOffset))];
-        r.codedMask = 0;
-        if (!deriveInter(mb, mbAddr, dpb)) return false;
-        if (first && recs != st) recs[mbAddr] = r;
-        if (first && !lateFixup_) classify(mbAddr, recs[mbAddr]);
-        return true;
-    }
-
+    // (P_Skip never comes here: finishSkip)
     if (type == B200_MB_I_PCM) {
         std::memset(r.refSlot, 0, 4);
         std::memset(r.refIdx, 0, 4);
