@@ -19,6 +19,11 @@ import synth_h264       # noqa: E402
 
 SEEDS = range(0, 160)
 DAMAGED_SEEDS = range(0, 240)
+# larger pictures, mostly still scenes: rows wider than a copy run (32 macroblocks), runs cut by slice and slice-group borders
+LARGE = [(1, dict(W=45, H=18, still=True, pictures=4)), (2, dict(W=45, H=18, still=True, pictures=4)),
+         (11, dict(W=40, H=23, still=True, pictures=3)), (12, dict(W=40, H=23, still=True, pictures=3)),
+         (21, dict(W=64, H=4, still=True, pictures=5)), (32, dict(W=45, H=36, still=True, pictures=2)),
+         (31, dict(W=45, H=36, pictures=2)), (51, dict(W=120, H=3, still=True, pictures=3))]
 
 
 def reference_decode(data):
@@ -79,6 +84,13 @@ def main():
         out[str(seed)] = {"stream_md5": hashlib.md5(data).hexdigest(), "bytes": len(data), "width_mbs": dims[0],
                           "height_mbs": dims[1], "outputs": n, "decoded": ndec,
                           "post_md5": hashlib.md5(post.tobytes()).hexdigest(), "pre_md5": hashlib.md5(pre.tobytes()).hexdigest()}
+    for i, (seed, kw) in enumerate(LARGE):
+        data = synth_h264.make_stream(seed, **kw)
+        n, fb, post, pre, ndec, dims = reference_decode(data)
+        assert n >= 0, f"large stream {i}: the reference reports a decode error"
+        out[f"L{i}"] = {"stream_md5": hashlib.md5(data).hexdigest(), "bytes": len(data), "width_mbs": dims[0], "height_mbs": dims[1],
+                        "outputs": n, "decoded": ndec, "seed": seed, "knobs": kw,
+                        "post_md5": hashlib.md5(post.tobytes()).hexdigest(), "pre_md5": hashlib.md5(pre.tobytes()).hexdigest()}
     path = os.path.join(_oracle.GOLDEN, "synth_md5.json")
     with open(path, "w") as f:
         json.dump(out, f, indent=0, sort_keys=True)

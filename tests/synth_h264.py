@@ -429,6 +429,8 @@ class PictureWriter:
 
     def _pick_mv(self, mbx, mby):
         r = self.r
+        if self.k.get("still") and r.random() < 0.92:      # a still scene: long runs of zero-vector copies
+            return (0, 0)
         c = r.random()
         if c < 0.25:
             return (0, 0)
@@ -495,6 +497,8 @@ class PictureWriter:
         i = 0
         n = len(mbs)
         p_skip_prob = r.choice([0.0, 0.2, 0.5, 0.8]) if (is_p and valid_refs and 0 in valid_refs) else 0
+        if p_skip_prob and self.k.get("still"):
+            p_skip_prob = 0.85
         while i < n:
             a = mbs[i]
             m = self.mb[a]
@@ -617,6 +621,8 @@ class PictureWriter:
                         self._set_mv(m, x, y, w, h, mv, refs[q])
             cbp_l = r.choice([0, 0, 15, r.randrange(16)])
             cbp_c = r.choice([0, 0, 1, 2])
+            if self.k.get("still") and r.random() < 0.7:
+                cbp_l = cbp_c = 0
             cbp = cbp_l | (cbp_c << 4)
             bw.ue(CBP_CODE_INTER[cbp])
         else:
@@ -954,7 +960,8 @@ def _random_mmco(r, refs, max_lt, nrf, frame_num, max_fn, must_drop=()):
 
 def make_stream(seed, **force):
     """One random valid stream.  `force` overrides knobs: W, H, pictures, fmo (bool), multi_slice (bool), aso (bool),
-    num_ref_frames, poc_type, i_only (bool), dense (float), vui (bool), mmco (bool), gaps (bool), redundant (bool)."""
+    num_ref_frames, poc_type, i_only (bool), dense (float), vui (bool), mmco (bool), gaps (bool), redundant (bool),
+    still (bool: mostly zero vectors and P_Skip -- long runs of plain copies)."""
     r = random.Random(seed)
     out = bytearray()
 
@@ -1011,6 +1018,7 @@ def make_stream(seed, **force):
              "dense": force.get("dense", r.choice([0.0, 0.1, 0.5])), "qp_lo": None, "qp_hi": None}
     if r.random() < 0.35:
         knobs["qp_lo"], knobs["qp_hi"] = r.choice([(0, 12), (20, 35), (40, 51), (0, 51)])
+    knobs["still"] = force.get("still", False)
     for pic in range(n_pics):
         idr = pic == 0 or (r.random() < 0.1)
         is_ref = True if idr else (nrf > 0 and (r.random() < 0.8 or prev_was_nonref))
