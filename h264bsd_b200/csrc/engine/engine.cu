@@ -12,6 +12,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include "recon_kernel.cuh"
+#include "conceal_kernel.cuh"
 #include "deblock_kernel.cuh"
 #include "engine.hpp"
 
@@ -99,18 +100,8 @@ bool Batch::create(int device, uint32_t nStreams, uint32_t widthMbs, uint32_t he
     CK(cudaEventCreate(&evB_));
     created_ = true;
 
+    g_ = makePoolGeom(widthMbs, heightMbs, numSlots, nStreams);
     PoolGeom &g = g_;
-    g.widthMbs = (int)widthMbs; g.heightMbs = (int)heightMbs; g.nMbs = (int)(widthMbs * heightMbs);
-    g.W = 16 * (int)widthMbs; g.H = 16 * (int)heightMbs;
-    g.pitchY = g.W + 2 * kPadY;
-    g.pitchC = (g.W / 2 + 2 * kPadC + 15) & ~15;
-    g.rowsY = g.H + 2 * kPadY;
-    g.rowsC = g.H / 2 + 2 * kPadC;
-    g.offCb = (unsigned long long)g.pitchY * g.rowsY;
-    g.offCr = g.offCb + (unsigned long long)g.pitchC * g.rowsC;
-    g.frameStride = (g.offCr + (unsigned long long)g.pitchC * g.rowsC + 255) & ~255ull;
-    g.numSlots = (int)numSlots; g.nStreams = (int)nStreams;
-    g.invWidthMbs = (unsigned)((0x80000000ull + widthMbs - 1) / widthMbs);
     const unsigned long long nFrames = (unsigned long long)nStreams * numSlots;
     CK(cudaMalloc(&pool_, nFrames * g.frameStride));
     CK(cudaMemsetAsync(pool_, 128, nFrames * g.frameStride, stream_));

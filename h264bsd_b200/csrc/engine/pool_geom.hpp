@@ -39,6 +39,42 @@ struct StreamJob {
     uint16_t pad[2];
 };
 
+// launch parameters of the reconstruction kernels (recon_kernel.cuh, conceal_kernel.cuh)
+struct ReconParams {
+    uint8_t *pool;
+    PoolGeom g;
+    const StreamJob *jobs;     // nStreams
+    uint32_t *done;            // nStreams * nMbs completion flags (pass B only)
+    uint32_t *ticket;          // CTA ticket counter of pass B (zeroed before launch)
+    uint32_t *errors;          // [0] IDCT range errors (h264bsd_transform.c:183-188)
+    uint32_t serial;           // value that marks "done in this launch"
+    uint32_t chunksB;          // pass B: warp tasks (chunkB entries) per stream
+    uint32_t chunkB;           // pass B: list entries per warp task
+    uint32_t chunkA;           // pass A: list entries per warp (<= kChunkA)
+    uint32_t copyRuns;         // copy pass: runs per warp task (<= kCopyRunsPerTask)
+    uint32_t chunksA;          // pass A: virtual CTAs per stream (kReconWarps * kChunkA entries each)
+    uint32_t virtualCtasA;     // chunksA * nStreams
+    uint32_t chunksC;          // copy pass: warp tasks of 32 single copies per stream
+    uint32_t chunksQ;          // copy pass: warp tasks of copyRuns zero-motion runs per stream (they come first)
+};
+
+// geometry of a pool of nStreams x numSlots frames of widthMbs x heightMbs macroblocks (layout in device_common.cuh)
+inline PoolGeom makePoolGeom(uint32_t widthMbs, uint32_t heightMbs, uint32_t numSlots, uint32_t nStreams) {
+    PoolGeom g;
+    g.widthMbs = (int)widthMbs; g.heightMbs = (int)heightMbs; g.nMbs = (int)(widthMbs * heightMbs);
+    g.W = 16 * (int)widthMbs; g.H = 16 * (int)heightMbs;
+    g.pitchY = g.W + 2 * kPadY;
+    g.pitchC = (g.W / 2 + 2 * kPadC + 15) & ~15;
+    g.rowsY = g.H + 2 * kPadY;
+    g.rowsC = g.H / 2 + 2 * kPadC;
+    g.offCb = (unsigned long long)g.pitchY * g.rowsY;
+    g.offCr = g.offCb + (unsigned long long)g.pitchC * g.rowsC;
+    g.frameStride = (g.offCr + (unsigned long long)g.pitchC * g.rowsC + 255) & ~255ull;
+    g.numSlots = (int)numSlots; g.nStreams = (int)nStreams;
+    g.invWidthMbs = (unsigned)((0x80000000ull + widthMbs - 1) / widthMbs);
+    return g;
+}
+
 static_assert(sizeof(StreamJob) == 40, "StreamJob is copied to the device as is");
 static_assert(sizeof(b200_mb_rec) == B200_MB_REC_BYTES, "record layout");
 

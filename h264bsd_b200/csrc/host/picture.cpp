@@ -376,23 +376,13 @@ bool PictureState::deriveInter(MbSyntax &mb, uint32_t mbAddr, const Dpb &dpb) {
     };
     r.subMbTypes = 0;
     switch (mb.mbType) {
-        case B200_MB_P_SKIP:
-        case B200_MB_P_16x16: {
-            uint32_t refIdx = mb.refIdx[0];
-            int16_t mv[2] = {0, 0};
-            bool zero = false;
+        case B200_MB_P_16x16: {     // (P_Skip has its own path: finishSkip)
+            const uint32_t refIdx = mb.refIdx[0];
             const NbMv a = interNeighbour(mbAddr, -1, 0, 0), b = interNeighbour(mbAddr, 0, -1, 0);
-            if (mb.mbType == B200_MB_P_SKIP) {
-                zero = !a.avail || !b.avail || (a.refIdx == 0 && a.mv[0] == 0 && a.mv[1] == 0) ||
-                       (b.refIdx == 0 && b.mv[0] == 0 && b.mv[1] == 0);
-            }
-            if (!zero) {
-                int16_t p[2];
-                predictMv(mbAddr, 0, 0, 4, 4, refIdx, 0, p, &a, &b);
-                mv[0] = (int16_t)(mb.mvd[0][0] + p[0]);
-                mv[1] = (int16_t)(mb.mvd[0][1] + p[1]);
-                if (!mvInRange(mv[0], mv[1])) return false;
-            }
+            int16_t p[2];
+            predictMv(mbAddr, 0, 0, 4, 4, refIdx, 0, p, &a, &b);
+            const int16_t mv[2] = {(int16_t)(mb.mvd[0][0] + p[0]), (int16_t)(mb.mvd[0][1] + p[1])};
+            if (!mvInRange(mv[0], mv[1])) return false;
             int slot = dpb.refSlot(refIdx);
             if (slot < 0) return false;
             for (int z = 0; z < 16; z++) { r.u.mv[z][0] = mv[0]; r.u.mv[z][1] = mv[1]; }
