@@ -151,7 +151,7 @@ extern "C" b200_tape *h264bsdB200ReparseStream(b200_tape *t, const uint8_t *stre
         return nullptr;
     }
     t->capOutputs = (uint32_t)(capOut / sizeof(uint32_t));
-    std::memcpy(t->outputPicIndex, outputs.data(), sizeof(uint32_t) * outputs.size());
+    if (!outputs.empty()) std::memcpy(t->outputPicIndex, outputs.data(), sizeof(uint32_t) * outputs.size());
     t->numOutputs = (uint32_t)outputs.size();
     (void)cap0;
     if (sink.repin) t->pinned = 2;   // the arrays moved: the caller may page-lock again
