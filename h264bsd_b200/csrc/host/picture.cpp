@@ -871,17 +871,16 @@ void PictureState::markSliceCorrupted(uint32_t firstMbInSlice, const Sps &sps) {
 
 void PictureState::finalizeRecords() {
     bindOutput();
-    // One pass over the records (they are 96 bytes each; everything after it works on one byte per macroblock):
-    // deblocking edge flags (GetMbFilteringFlags, deblocking.c:289-320, needs the final slice ids) and the class of the
-    // macroblock for the processing order: 0 other pass-A, 1 plain copy, 4 pass-B (intra-predicted), zr = 1 + reference
-    // slot of a zero-vector plain copy.  Plain copy: P_Skip / P_L0_16x16 without residual whose vector is integer for
-    // luma and chroma.
+    // Class of every macroblock for the processing order -- 0 other pass-A, 1 plain copy (P_Skip / P_L0_16x16 without residual
+    // whose vector is integer for luma and chroma), 4 pass-B (intra-predicted), 5 spatially concealed; zr = 1 + reference slot
+    // of a zero-vector plain copy -- and its deblocking edge flags (GetMbFilteringFlags, deblocking.c:289-320).  The common
+    // picture had both settled per macroblock by classify().  A picture with macroblocks decoded twice, corrupted slices or
+    // concealment takes the pass over the records below instead (the slice ids are final only now).
     std::vector<uint8_t> &cls = orderClass;
     cls.resize(2 * (size_t)picSizeInMbs);
     uint8_t *zr = cls.data() + picSizeInMbs;
     order.resize(picSizeInMbs);
     uint32_t a = 0, nB = lateFixup_ ? 0 : numIntraPred_;
-    // (the common picture -- every macroblock decoded once, nothing concealed -- had this done per macroblock by classify())
     if (lateFixup_)
     for (uint32_t y = 0; y < heightMbs; y++)
         for (uint32_t x = 0; x < widthMbs; x++, a++) {
@@ -959,7 +958,7 @@ void PictureState::finalizeRecords() {
     if (numPassB) {
         // bucket by wavefront key (stable in address order inside a key)
         const uint32_t nKeys = widthMbs + 2 * heightMbs;
-        std::vector<uint32_t> &keys = keyCount_;
+        std::vector<uint32_t> &keys = orderKeyCount;
         keys.assign(nKeys + 1, 0);
         for (uint32_t i = 0; i < nIntra; i++) keys[(intra[i] >> 16) + 1]++;
         for (uint32_t k = 0; k < nKeys; k++) keys[k + 1] += keys[k];

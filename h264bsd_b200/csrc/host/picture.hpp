@@ -73,7 +73,7 @@ public:
     uint32_t numPassA = 0, numPassB = 0, numCopy = 0, numRun = 0, numRunMbs = 0, numConceal = 0;
     std::vector<uint16_t> concealOrder;   // spatially concealed macroblocks of the picture being built, concealment order
     std::vector<uint8_t> orderClass;   // scratch of finalizeRecords
-    std::vector<uint32_t> orderKeys, keyCount_;
+    std::vector<uint32_t> orderKeys, orderKeyCount;
     std::vector<uint32_t> sliceGroupMap;
     uint32_t sliceIdCounter = 0, numDecodedMbs = 0, lastMbAddr = 0;
 
