@@ -135,7 +135,7 @@ typedef struct b200_pic_hdr {
     uint8_t outSlot[20];   /* ... their frame slots, output order ... */
     uint32_t outPicIndex[20]; /* ... and the decode-order index of the picture held in that slot */
     uint32_t picId;        /* application picId (h264bsdDecode argument) */
-    uint32_t numPassA;     /* macroblocks reconstructed without looking at the current picture: inter + I_PCM */
+    uint32_t numPassA;     /* macroblocks reconstructed without looking at the current picture: inter + I_PCM (+ concealed copies) */
     uint32_t numPassB;     /* intra-predicted macroblocks (read unfiltered neighbours of the current picture) */
     uint32_t numCopy;      /* plain copies listed one by one: one 16x16 partition, no residual, motion vector a multiple of
                               8 quarter-pels in both components (integer for luma AND chroma) */
