@@ -2,6 +2,7 @@
 import ctypes as C
 import os
 import re
+import subprocess
 import numpy as np
 import pytest
 import _oracle
@@ -338,3 +339,17 @@ def test_processing_order_lists(name):
         wm = r[:, 28]
         assert (wm[~intra] == 0).all()
     ps.close()
+
+
+POSIX_B200 = os.path.join(ROOT, "oracle", "_ref", "test_h264bsd_b200")
+
+
+@pytest.mark.skipif(not os.path.exists(POSIX_B200), reason="oracle/_ref/test_h264bsd_b200 not built (make -C oracle ref, needs the reference sources)")
+def test_reference_posix_front_end_links_unchanged_and_fails_loudly_without_gpu():
+    """the reference's own posix/test_h264bsd.c, unmodified, compiled against include/ and linked with the shared library
+    (oracle/Makefile: posix).  Without a GPU it must say so and stop -- no silent CPU path."""
+    r = subprocess.run([POSIX_B200, os.path.join(ROOT, "tests", "golden", "test_640x360.h264")], capture_output=True, text=True)
+    if _lib.load().h264bsdB200DeviceCount() <= 0:
+        assert r.returncode != 0 and "no CUDA device" in r.stderr
+    else:
+        assert "73 pictures decoded" in r.stdout

@@ -218,3 +218,21 @@ def test_streamed_upload_matches_golden(parsed):
         b.sync()
     assert b.idct_errors() == 0 and b.watchdog() == (0, 0)
     b.close()
+
+
+POSIX_B200 = os.path.join(_oracle.ROOT, "oracle", "_ref", "test_h264bsd_b200")
+
+
+@pytest.mark.skipif(not os.path.exists(POSIX_B200), reason="oracle/_ref/test_h264bsd_b200 not built (make -C oracle ref, needs the reference sources)")
+def test_reference_posix_front_end_unchanged(tmp_path):
+    """BASELINE.json configs[0], literally: the reference's own posix/test_h264bsd.c -- compiled unmodified against include/ and
+    linked with libh264bsd_b200.so (oracle/Makefile: posix) -- decodes test_640x360.h264, prints what the reference build
+    prints, and its "-o" dump has the md5 of the reference build's dump"""
+    import subprocess
+    gold = json.load(open(os.path.join(_oracle.GOLDEN, "posix_front_end.json")))["test_640x360.h264"]
+    out = tmp_path / "dump.yuv"
+    r = subprocess.run([POSIX_B200, "-o", str(out), os.path.join(_oracle.GOLDEN, "test_640x360.h264")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.strip().splitlines()[-1] == gold["stdout_tail"]
+    data = out.read_bytes()
+    assert len(data) == gold["o_dump_bytes"] and hashlib.md5(data).hexdigest() == gold["o_dump_md5"]
