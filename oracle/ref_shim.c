@@ -43,7 +43,10 @@ static int g_resilient;            /* carry on after H264BSD_ERROR (what a playe
 static uint32_t g_err_mbs[4096];   /* numErrMbs of every output picture of the last ref_decode_stream call */
 static uint32_t g_err_count;
 
+static uint32_t g_video_info[4];   /* h264bsdVideoRange, h264bsdMatrixCoefficients, sample aspect ratio w, h at the end of the last decode */
+
 void ref_set_resilient(int on) { g_resilient = on; }
+void ref_video_info(uint32_t out[4]) { memcpy(out, g_video_info, sizeof g_video_info); }
 uint32_t ref_err_mbs(uint32_t *dst, uint32_t cap)
 {
     uint32_t n = g_err_count < cap ? g_err_count : cap;
@@ -151,6 +154,12 @@ int ref_decode_stream(const uint8_t *stream, size_t len,
         }
     }
     if (info) info[7] = g_tap_pics;
+    memset(g_video_info, 0, sizeof g_video_info);
+    if (dec->activeSps) {
+        g_video_info[0] = h264bsdVideoRange(dec);
+        g_video_info[1] = h264bsdMatrixCoefficients(dec);
+        h264bsdSampleAspectRatio(dec, &g_video_info[2], &g_video_info[3]);
+    }
     g_pre = NULL; g_mbtap = NULL;
     h264bsdShutdown(dec);
     h264bsdFree(dec);

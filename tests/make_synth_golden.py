@@ -40,6 +40,18 @@ def reference_decode(data):
     return n, fb, post[:max(n, 0) * fb], pre[:info[7] * fb], int(info[7]), (int(info[0]), int(info[1]))
 
 
+def reference_stream_info(data):
+    """what the reference's getters say after the whole stream: h264bsdCroppingParams (flag, left, width, top, height),
+    h264bsdVideoRange, h264bsdMatrixCoefficients"""
+    L = _oracle.reference()
+    info = (C.c_uint32 * 8)()
+    buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+    L.ref_decode_stream(buf, len(data), None, 0, None, 0, None, 0, info)
+    v = (C.c_uint32 * 4)()
+    L.ref_video_info(v)
+    return {"crop": [int(x) for x in info[2:7]], "video_range": int(v[0]), "matrix_coefficients": int(v[1])}
+
+
 def reference_decode_resilient(data):
     """the same with a caller that carries on after H264BSD_ERROR (what a player does; posix/test_h264bsd.c exits): the
     reference marks slices corrupt and conceals what is missing at the next access unit boundary.  Also returns numErrMbs
@@ -82,7 +94,7 @@ def main():
         n, fb, post, pre, ndec, dims = reference_decode(data)
         assert n >= 0, f"seed {seed}: the reference reports a decode error -- the generator wrote an invalid stream"
         out[str(seed)] = {"stream_md5": hashlib.md5(data).hexdigest(), "bytes": len(data), "width_mbs": dims[0],
-                          "height_mbs": dims[1], "outputs": n, "decoded": ndec,
+                          "height_mbs": dims[1], "outputs": n, "decoded": ndec, "info": reference_stream_info(data),
                           "post_md5": hashlib.md5(post.tobytes()).hexdigest(), "pre_md5": hashlib.md5(pre.tobytes()).hexdigest()}
     for i, (seed, kw) in enumerate(LARGE):
         data = synth_h264.make_stream(seed, **kw)

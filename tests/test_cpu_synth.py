@@ -32,6 +32,19 @@ def decode_with_oracle(data):
         ps.close()
 
 
+def stream_info(data):
+    """the tape's copy of what h264bsdCroppingParams / h264bsdVideoRange / h264bsdMatrixCoefficients return"""
+    ps = ParsedStream(data)
+    t = ps.ptr.contents
+    if t.cropFlag:
+        crop = [1, t.cropLeft, t.cropWidth, t.cropTop, t.cropHeight]
+    else:
+        crop = [0, 0, 0, 0, 0]
+    info = {"crop": crop, "video_range": int(t.videoRange), "matrix_coefficients": int(t.matrixCoefficients)}
+    ps.close()
+    return info
+
+
 @pytest.mark.parametrize("chunk", range(8))
 def test_synthetic_streams_match_reference_golden(chunk):
     """committed md5s of the reference decoder's output (tests/make_synth_golden.py); needs no reference build"""
@@ -43,6 +56,7 @@ def test_synthetic_streams_match_reference_golden(chunk):
                         "re-run tests/make_synth_golden.py")
         n_out, n_dec, dims, post, pre = decode_with_oracle(data)
         assert dims == (g["width_mbs"], g["height_mbs"]), f"seed {seed}"
+        assert stream_info(data) == g["info"], f"seed {seed}: cropping / video range / matrix coefficients"
         assert (n_out, n_dec) == (g["outputs"], g["decoded"]), f"seed {seed}: picture counts"
         assert md5(pre) == g["pre_md5"], f"seed {seed}: pictures before the in-loop filter differ from the reference"
         assert md5(post) == g["post_md5"], f"seed {seed}: output pictures differ from the reference"
