@@ -781,6 +781,7 @@ SliceResult PictureState::decodeSlice(BitReader &br, const SliceHeader &sh, cons
     if (!mbInit) { std::memset(&mb, 0, sizeof mb); mbInit = true; }
 
     bindOutput();
+    failedMb_ = -1;
     if (sh.redundantPicCnt) splitState();   // a macroblock decoded again updates the state, not the record (first decode wins)
     uint32_t cur = sh.firstMb;
     uint32_t skipRun = 0;
@@ -832,7 +833,12 @@ SliceResult PictureState::decodeSlice(BitReader &br, const SliceHeader &sh, cons
                 for (uint32_t m = mb.spill; m; m &= m - 1) mb.level[__builtin_ctz(m)][0] = 0;
             }
         }
-        if (!ok) return SliceResult::Error;
+        if (!ok) {
+            // the macroblock counts as decoded once more, but its record is half-made: see markSliceCorrupted
+            failedMb_ = (int)cur;
+            failedPrevDecoded_ = (uint8_t)(ax.decoded - 1);
+            return SliceResult::Error;
+        }
         if (ax.decoded == 1) mbCount++;
         more = skipRun || br.moreRbspData();
         if (iSlice) lastMbAddr = cur;
@@ -867,6 +873,15 @@ void PictureState::markSliceCorrupted(uint32_t firstMbInSlice, const Sps &sps) {
         else break;
         cur = nextMbAddress(cur);
     } while (cur);
+    // An I slice that fails in the macroblock right after its first one: the walk above starts below the slice
+    // (lastMbAddr - 1 < firstMbInSlice) and stops at once, so the reference leaves the FAILED macroblock marked as decoded;
+    // nothing of it was written (h264bsd_macroblock_layer.c:1118-1130), it keeps whatever the frame buffer held.  There is no
+    // such thing as "what the buffer held" here and the failed macroblock's record is half-made: it is given up like the rest
+    // of its slice and concealed (documented deviation).
+    if (failedMb_ >= 0) {
+        if (aux[failedMb_].decoded > failedPrevDecoded_) aux[failedMb_].decoded = failedPrevDecoded_;
+        failedMb_ = -1;
+    }
 }
 
 void PictureState::finalizeRecords() {

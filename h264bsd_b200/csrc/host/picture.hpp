@@ -112,6 +112,8 @@ private:
     uint32_t curX_ = 0;                 // its column
     bool lateFixup_ = false;            // this picture needs the full pass of finalizeRecords (see classify)
     uint32_t numIntraPred_ = 0;         // intra-predicted macroblocks classified so far
+    int failedMb_ = -1;                 // macroblock whose derivation failed after it was counted as decoded (decodeSlice)
+    uint8_t failedPrevDecoded_ = 0;     // ... and its decode count before that
 
     struct NbMv { bool avail; uint32_t refIdx; int16_t mv[2]; };
     NbMv interNeighbour(uint32_t cur, int x, int y, int curZ) const;

@@ -4,10 +4,10 @@ the same way: which macroblocks count as decoded (h264bsdMarkSliceCorrupted), wh
 the reference picture / spatial estimate), numErrMbs, the in-loop filter over concealed macroblocks, output order.
 Needs no GPU and no reference build: the reference's answers are committed md5s (tests/make_synth_golden.py).
 
-Known deviation, not tested: a macroblock whose decoding fails while h264bsdMarkSliceCorrupted leaves it marked as decoded
-(an I slice that fails in its second macroblock, h264bsd_slice_data.c:313-327) keeps whatever the frame buffer held before in
-the reference (nothing is written, h264bsd_macroblock_layer.c:1118-1130); here it is reconstructed from what was parsed.
-KNOWN_STALE lists the seeds where that happens."""
+Known deviation, not tested: an I slice that fails in the macroblock right after its first one.  h264bsdMarkSliceCorrupted
+(h264bsd_slice_data.c:313-327) then gives up nothing and the reference leaves the failed macroblock marked as decoded though
+it never wrote it (h264bsd_macroblock_layer.c:1118-1130): it keeps whatever the frame buffer held.  Here that macroblock is
+concealed like the rest of its slice.  KNOWN_STALE lists the seeds where that happens."""
 import hashlib
 import json
 import os
@@ -19,7 +19,7 @@ from h264bsd_b200.batch import ParsedStream
 
 GOLD = json.load(open(os.path.join(_oracle.GOLDEN, "synth_damaged_md5.json")))
 SEEDS = sorted(int(s) for s in GOLD)
-KNOWN_STALE = set()       # (none among the committed seeds; 282, 579, 625, 633, 649, 839, 1438, 1514 outside them)
+KNOWN_STALE = set()       # (none among the committed seeds)
 
 
 def md5(a):
@@ -78,7 +78,7 @@ def test_damage_exercises_both_kinds_of_concealment():
 @pytest.mark.skipif(_oracle.reference() is None, reason="oracle/_ref not built (needs the reference sources)")
 def test_fresh_damaged_seeds_against_the_compiled_reference():
     from make_synth_golden import reference_decode_resilient
-    stale = {282, 579, 625, 633, 649, 839, 1438, 1514}
+    stale = set()       # (none in this range; e.g. 282, 579, 625, 633, 649, 839, 1438, 1514 elsewhere)
     for seed in range(1000, 1200):
         if seed in stale:
             continue
