@@ -1,7 +1,7 @@
 // conceal_emu.cpp -- TEST INFRASTRUCTURE.  The shipped source of concealKernel (h264bsd_b200/csrc/engine/conceal_kernel.cuh)
 // compiled for the host with warp_emu.hpp and exposed to the tests:
 //   emu_geom()     the pool geometry the engine would use (makePoolGeom)
-//   emu_conceal()  one launch of concealKernel over a one-stream pool in host memory
+//   emu_conceal()  one launch of concealKernel over a pool of nStreams streams in host memory
 #include "warp_emu.hpp"
 #include "conceal_kernel.cuh"
 
@@ -14,16 +14,20 @@ extern "C" void emu_geom(uint32_t widthMbs, uint32_t heightMbs, uint32_t numSlot
 }
 
 extern "C" void emu_conceal(uint8_t *pool, uint32_t widthMbs, uint32_t heightMbs, uint32_t numSlots, uint32_t curSlot,
-                            const b200_mb_rec *recs, const uint16_t *order, uint32_t nR, uint32_t nC, uint32_t nA, uint32_t nB, uint32_t nE) {
+                            const b200_mb_rec *recs, const uint16_t *order, uint32_t nR, uint32_t nC, uint32_t nA, uint32_t nB, uint32_t nE,
+                            uint32_t nStreams) {
+    // every stream of the batch gets the same job (its own frames: stream s owns slots [s * numSlots, (s + 1) * numSlots))
     StreamJob job;
     std::memset(&job, 0, sizeof job);
     job.recs = recs; job.order = order; job.curSlot = (uint16_t)curSlot;
     job.nR = (uint16_t)nR; job.nC = (uint16_t)nC; job.nA = (uint16_t)nA; job.nB = (uint16_t)nB; job.nE = (uint16_t)nE;
+    std::vector<StreamJob> jobs(nStreams, job);
     ReconParams p;
     std::memset(&p, 0, sizeof p);
     p.pool = pool;
-    p.g = makePoolGeom(widthMbs, heightMbs, numSlots, 1);
-    p.jobs = &job;
+    p.g = makePoolGeom(widthMbs, heightMbs, numSlots, nStreams);
+    p.jobs = jobs.data();
     // the engine's launch: ceil(nStreams / kConcealWarps) blocks of kConcealWarps warps
-    warp_emu::runBlock(0, kConcealWarps, [&]() { concealKernel(p); });
+    for (uint32_t b = 0; b < (nStreams + kConcealWarps - 1) / kConcealWarps; b++)
+        warp_emu::runBlock(b, kConcealWarps, [&]() { concealKernel(p); });
 }

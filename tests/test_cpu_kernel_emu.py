@@ -25,8 +25,11 @@ def emu():
                            os.path.join(EMU_DIR, "conceal_emu.cpp"), "-o", EMU_SO, "-lpthread"])
     L = C.CDLL(EMU_SO)
     L.emu_geom.argtypes = [C.c_uint32] * 3 + [C.POINTER(C.c_uint64)]
-    L.emu_conceal.argtypes = [C.c_void_p] + [C.c_uint32] * 4 + [C.c_void_p, C.c_void_p] + [C.c_uint32] * 5
+    L.emu_conceal.argtypes = [C.c_void_p] + [C.c_uint32] * 4 + [C.c_void_p, C.c_void_p] + [C.c_uint32] * 6
     return L
+
+
+N_STREAMS = 6      # two blocks of four warps, the second half empty
 
 
 def to_pool(frame, W, H, geom, slot, pool):
@@ -63,7 +66,7 @@ def test_conceal_kernel_source_matches_oracle_on_the_host(emu):
         g = (C.c_uint64 * 8)()
         emu.emu_geom(ps.width_mbs, ps.height_mbs, ps.num_slots, g)
         geom = [int(v) for v in g]
-        pool = np.full(geom[6] * ps.num_slots, 128, np.uint8)
+        pool = np.full(geom[6] * ps.num_slots * N_STREAMS, 128, np.uint8)
         orc = _oracle.OracleDecoder(ps)
         t = ps.ptr.contents
         order = C.cast(t.mbOrder, C.c_void_p).value
@@ -73,13 +76,15 @@ def test_conceal_kernel_source_matches_oracle_on_the_host(emu):
                 h0 = copy.copy(h)
                 h0.numConceal = 0          # everything but the spatial estimates
                 orc.L.px_recon_picture(orc.ctx, C.byref(h0), orc._recs + h.mbRecOffset, orc._coefs + h.coefOffset)
-                to_pool(orc.frame(h.curSlot), W, H, geom, h.curSlot, pool)
+                for st in range(N_STREAMS):
+                    to_pool(orc.frame(h.curSlot), W, H, geom, st * ps.num_slots + h.curSlot, pool)
                 n_a = h.numPassA - h.numRunMbs - h.numCopy
                 emu.emu_conceal(pool.ctypes.data, ps.width_mbs, ps.height_mbs, ps.num_slots, h.curSlot, orc._recs + h.mbRecOffset,
-                                order + 2 * k * ps.mbs_per_pic, h.numRun, h.numCopy, n_a, h.numPassB, h.numConceal)
+                                order + 2 * k * ps.mbs_per_pic, h.numRun, h.numCopy, n_a, h.numPassB, h.numConceal, N_STREAMS)
                 orc.recon(k)
-                assert np.array_equal(from_pool(W, H, geom, h.curSlot, pool), orc.frame(h.curSlot)), \
-                    f"seed {seed}: picture {k}: concealKernel (emulated) differs from the oracle"
+                for st in range(N_STREAMS):
+                    assert np.array_equal(from_pool(W, H, geom, st * ps.num_slots + h.curSlot, pool), orc.frame(h.curSlot)), \
+                        f"seed {seed}: picture {k}, stream {st}: concealKernel (emulated) differs from the oracle"
                 checked += 1
                 mbs += h.numConceal
             else:
