@@ -12,6 +12,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include "recon_kernel.cuh"
+#include "copy_kernel.cuh"
 #include "conceal_kernel.cuh"
 #include "deblock_kernel.cuh"
 #include "engine.hpp"

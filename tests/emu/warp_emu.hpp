@@ -20,8 +20,10 @@
 
 struct uint2 { uint32_t x, y; };
 inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
+struct alignas(16) uint4 { uint32_t x, y, z, w; };
 struct EmuDim3 { unsigned x = 0, y = 0, z = 0; };
 inline thread_local EmuDim3 threadIdx, blockIdx;
+inline EmuDim3 gridDim;       // set by the caller before runBlock
 using std::min;
 using std::max;
 
@@ -40,7 +42,7 @@ struct Barrier {
     }
 };
 inline Barrier gBarrier;
-inline int gExchange[32];
+inline unsigned long long gExchange[32];
 
 // run `body` as block `block` of `warpsPerBlock` warps, one warp after the other
 inline void runBlock(unsigned block, unsigned warpsPerBlock, const std::function<void()> &body) {
@@ -59,13 +61,22 @@ inline void runBlock(unsigned block, unsigned warpsPerBlock, const std::function
 
 // every lane of the (full) warp must call these the same number of times -- true of the kernels run here, whose control flow
 // is warp-uniform
-inline int __shfl_sync(unsigned, int v, int srcLane) {
-    warp_emu::gExchange[threadIdx.x & 31] = v;
+template <typename T> inline T __shfl_sync(unsigned, T v, int srcLane) {
+    static_assert(sizeof(T) <= 8, "shuffles move at most 64 bits");
+    unsigned long long raw = 0;
+    std::memcpy(&raw, &v, sizeof(T));
+    warp_emu::gExchange[threadIdx.x & 31] = raw;
     warp_emu::gBarrier.wait();
-    const int r = warp_emu::gExchange[srcLane & 31];
+    raw = warp_emu::gExchange[srcLane & 31];
     warp_emu::gBarrier.wait();
+    T r;
+    std::memcpy(&r, &raw, sizeof(T));
     return r;
 }
 inline void __syncwarp() { warp_emu::gBarrier.wait(); }
 template <typename T> inline T __ldg(const T *p) { return *p; }
 inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
+// funnel shift right: the low 32 bits of (hi:lo) >> (shift & 31)
+inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift) {
+    return (unsigned)(((((unsigned long long)hi) << 32) | lo) >> (shift & 31));
+}

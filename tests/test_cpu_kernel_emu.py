@@ -1,7 +1,7 @@
-"""The shipped source of the spatial concealment kernel (h264bsd_b200/csrc/engine/conceal_kernel.cuh) compiled for the host
-and run lane by lane (tests/emu/warp_emu.hpp: 32 threads per warp, a barrier per shuffle) against the CPU oracle, on the
-pictures of the damaged streams that need it.  Checks the kernel's indexing and arithmetic where no GPU is at hand; the GPU
-suite checks the same pictures on the hardware."""
+"""The shipped sources of two device kernels -- the spatial concealment kernel (conceal_kernel.cuh) and the copy pass
+(copy_kernel.cuh) -- compiled for the host and run lane by lane (tests/emu/warp_emu.hpp: 32 threads per warp, a barrier per
+shuffle) against the CPU oracle.  Checks a kernel's indexing and arithmetic where no GPU is at hand (the concealment path was
+written without one); the GPU suite checks the same pictures on the hardware."""
 import copy
 import ctypes as C
 import os
@@ -26,7 +26,27 @@ def emu():
     L = C.CDLL(EMU_SO)
     L.emu_geom.argtypes = [C.c_uint32] * 3 + [C.POINTER(C.c_uint64)]
     L.emu_conceal.argtypes = [C.c_void_p] + [C.c_uint32] * 4 + [C.c_void_p, C.c_void_p] + [C.c_uint32] * 6
+    L.emu_copy.argtypes = [C.c_void_p] + [C.c_uint32] * 4 + [C.c_void_p, C.c_void_p] + [C.c_uint32] * 5
     return L
+
+
+def aligned_pool(nbytes, fill=128):
+    """the frame pool comes from cudaMalloc (256-byte aligned); the copy kernel moves 16-byte vectors"""
+    raw = np.full(nbytes + 256, fill, np.uint8)
+    off = (-raw.ctypes.data) % 256
+    return raw[off:off + nbytes]
+
+
+def to_pool_with_border(frame, W, H, geom, slot, pool):
+    """a finished frame as the engine keeps it: picture plus replicated border (borderKernel)"""
+    pitchY, pitchC, rowsY, rowsC, offCb, offCr, stride, pads = geom
+    padY, padC = pads & 0xFFFFFFFF, pads >> 32
+    base = slot * stride
+    Y = pool[base:base + pitchY * rowsY].reshape(rowsY, pitchY)
+    Y[:, :W + 2 * padY] = np.pad(frame[:W * H].reshape(H, W), padY, mode="edge")
+    for off, src in ((offCb, frame[W * H:W * H + W * H // 4]), (offCr, frame[W * H + W * H // 4:])):
+        P = pool[base + off:base + off + pitchC * rowsC].reshape(rowsC, pitchC)
+        P[:, :W // 2 + 2 * padC] = np.pad(src.reshape(H // 2, W // 2), padC, mode="edge")
 
 
 N_STREAMS = 6      # two blocks of four warps, the second half empty
@@ -95,3 +115,81 @@ def test_conceal_kernel_source_matches_oracle_on_the_host(emu):
         if checked >= 40:
             break
     assert checked >= 20 and mbs >= 100, (checked, mbs)
+
+
+def copy_list_mbs(order, k, h, nmb):
+    """macroblock addresses in the run and single-copy sections of picture k's processing order"""
+    o = np.ctypeslib.as_array(order, shape=((k + 1) * nmb,))[k * nmb:]
+    mbs = []
+    for i in range(h.numRun):
+        mbs += list(range(int(o[2 * i]), int(o[2 * i]) + int(o[2 * i + 1])))
+    mbs += [int(a) for a in o[2 * h.numRun:2 * h.numRun + h.numCopy]]
+    return mbs
+
+
+def mb_pixels(frame, W, H, mb):
+    wm = W // 16
+    x, y = (mb % wm) * 16, (mb // wm) * 16
+    Y = frame[:W * H].reshape(H, W)[y:y + 16, x:x + 16]
+    C2 = frame[W * H:].reshape(2, H // 2, W // 2)[:, y // 2:y // 2 + 8, x // 2:x // 2 + 8]
+    return np.concatenate([Y.reshape(-1), C2.reshape(-1)])
+
+
+@pytest.mark.parametrize("kind", ["still", "damaged"])
+def test_copy_kernel_source_matches_oracle_on_the_host(emu, kind):
+    """zero-motion runs, single integer-vector copies (vectors far outside the picture included) and -- in the damaged
+    streams -- concealed macroblocks copied from the reference picture: every listed macroblock against the oracle, three
+    streams on a two-block grid, runs per task as the engine's default and at its maximum"""
+    if kind == "still":
+        streams = [synth_h264.make_stream(s, still=True, W=w, H=hh, pictures=3) for s, w, hh in ((3, 11, 4), (4, 40, 3), (6, 7, 6), (9, 37, 2))]
+        streams += [synth_h264.make_stream(s) for s in range(0, 24)]
+        resilient = False
+    else:
+        streams = [synth_h264.make_damaged_stream(s) for s in range(0, 80)]
+        resilient = True
+    n_streams = 3
+    pics = mbs_checked = concealed_copies = 0
+    for data in streams:
+        ps = ParsedStream(data, resilient=resilient)
+        if ps.status != 0 or ps.num_pics == 0:
+            ps.close()
+            continue
+        W, H, nmb = ps.width_mbs * 16, ps.height_mbs * 16, ps.mbs_per_pic
+        g = (C.c_uint64 * 8)()
+        emu.emu_geom(ps.width_mbs, ps.height_mbs, ps.num_slots, g)
+        geom = [int(v) for v in g]
+        orc = _oracle.OracleDecoder(ps)
+        t = ps.ptr.contents
+        order = C.cast(t.mbOrder, C.c_void_p).value
+        rec = np.dtype([("mbType", "u1"), ("pad0", "u1", 2), ("flags", "u1"), ("rest", "u1", 92)])
+        recs = np.frombuffer(C.string_at(t.mbRecs, t.mbRecBytes), rec)
+        for k in range(ps.num_pics):
+            h = ps.pics[k]
+            if h.numRun + h.numCopy:
+                # the frame slots as they are when picture k is reconstructed: finished pictures, borders replicated
+                pool = aligned_pool(geom[6] * ps.num_slots * n_streams)
+                for st in range(n_streams):
+                    for slot in range(ps.num_slots):
+                        to_pool_with_border(orc.frame(slot), W, H, geom, st * ps.num_slots + slot, pool)
+                copy_runs = 4 if (pics & 1) == 0 else 16
+                emu.emu_copy(pool.ctypes.data, ps.width_mbs, ps.height_mbs, ps.num_slots, h.curSlot, orc._recs + h.mbRecOffset,
+                             order + 2 * k * nmb, h.numRun, h.numCopy, n_streams, copy_runs, 2)
+                orc.recon(k)
+                want = orc.frame(h.curSlot)
+                listed = copy_list_mbs(t.mbOrder, k, h, nmb)
+                for st in range(n_streams):
+                    got = from_pool(W, H, geom, st * ps.num_slots + h.curSlot, pool)
+                    for mb in listed:
+                        assert np.array_equal(mb_pixels(got, W, H, mb), mb_pixels(want, W, H, mb)), \
+                            f"picture {k}, stream {st}, macroblock {mb}: reconCopyKernel (emulated) differs from the oracle"
+                pics += 1
+                mbs_checked += len(listed)
+                concealed_copies += int(sum(1 for mb in listed if recs[k * nmb + mb]["flags"] & 0x80))
+            else:
+                orc.recon(k)
+            orc.deblock(k)
+        orc.close()
+        ps.close()
+    assert pics >= 10 and mbs_checked >= 300, (pics, mbs_checked)
+    if kind == "damaged":
+        assert concealed_copies >= 20, concealed_copies
