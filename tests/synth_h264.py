@@ -440,7 +440,7 @@ class PictureWriter:
             return (r.randint(-24, 24), r.randint(-24, 24))
         if c < 0.90:                                                       # around / across the picture edges
             px, py = 64 * self.W, 64 * self.H
-            return (r.choice([-1, 1]) * r.randint(0, px + 90) - (64 * mbx if r.random() < .5 else 0),
+            return (max(-8192, min(8191, r.choice([-1, 1]) * r.randint(0, px + 90) - (64 * mbx if r.random() < .5 else 0))),
                     max(-2048, min(2047, r.choice([-1, 1]) * r.randint(0, py + 90))))
         if c < 0.97:
             return (r.randint(-8192, 8191), r.randint(-2048, 2047))
@@ -961,7 +961,8 @@ def _random_mmco(r, refs, max_lt, nrf, frame_num, max_fn, must_drop=()):
 def make_stream(seed, **force):
     """One random valid stream.  `force` overrides knobs: W, H, pictures, fmo (bool), multi_slice (bool), aso (bool),
     num_ref_frames, poc_type, i_only (bool), dense (float), vui (bool), mmco (bool), gaps (bool), redundant (bool),
-    still (bool: mostly zero vectors and P_Skip -- long runs of plain copies)."""
+    still (bool: mostly zero vectors and P_Skip -- long runs of plain copies), resend (bool: parameter sets repeated / changed
+    between pictures)."""
     r = random.Random(seed)
     out = bytearray()
 
@@ -987,7 +988,8 @@ def make_stream(seed, **force):
         ct, cb = r.randint(0, 3), r.randint(0, 3)
         if cl + cr_ < 8 * W and ct + cb < 8 * H:
             sps["crop"] = (cl, cr_, ct, cb)
-    out += write_sps(r, sps)
+    sps_nal = write_sps(r, sps)
+    out += sps_nal
     max_fn = 1 << sps["log2_max_frame_num"]
 
     # ---- picture parameter sets
@@ -1019,9 +1021,27 @@ def make_stream(seed, **force):
     if r.random() < 0.35:
         knobs["qp_lo"], knobs["qp_hi"] = r.choice([(0, 12), (20, 35), (40, 51), (0, 51)])
     knobs["still"] = force.get("still", False)
+    resend = force.get("resend", r.random() < 0.3)
     for pic in range(n_pics):
         idr = pic == 0 or (r.random() < 0.1)
         is_ref = True if idr else (nrf > 0 and (r.random() < 0.8 or prev_was_nonref))
+        # parameter sets again, as streams meant for random access carry them: the same SPS (no effect, h264bsdCompareSeqParamSets),
+        # a picture parameter set with the same or with new content (takes effect with the next picture that names it)
+        if resend and pic > 0 and r.random() < (0.6 if idr else 0.25):
+            if r.random() < 0.5:
+                out += sps_nal
+            for q in ppss:
+                if r.random() < 0.6:
+                    if r.random() < 0.5:
+                        q["pic_init_qp"] = r.randint(10, 45)
+                        q["chroma_qp_offset"] = r.randint(-12, 12)
+                        q["deblock_ctrl"] = r.randint(0, 1)
+                        q["pic_order_present"] = r.randint(0, 1)
+                        q["num_ref_idx_default"] = r.randint(1, 4)
+                        q["constrained_intra"] = 1 if r.random() < 0.3 else 0
+                        if allow_fmo and r.random() < 0.5:
+                            q["fmo"] = random_fmo(r, W, H, True)
+                    out += write_pps(r, q, size)
         pps = r.choice(ppss)
         gap = 0
         if idr:
