@@ -138,3 +138,21 @@ def test_sequence_change_same_size_and_other_size():
     ps = ParsedStream(a + synth_h264.make_stream(7, W=6, H=2))
     assert ps.status == 100 and (ps.width_mbs, ps.height_mbs) == (4, 3) and ps.num_pics == n_a
     ps.close()
+
+
+@pytest.mark.skipif(_oracle.reference() is None, reason="oracle/_ref not built (needs the reference sources)")
+def test_concatenated_sequences_against_the_compiled_reference():
+    """two or three coded video sequences of one picture size back to back: parameter sets replaced under the same ids, a new
+    IDR with other POC / frame_num / DPB parameters, pictures of the old sequence still waiting for output"""
+    import random
+    from make_synth_golden import reference_decode
+    r = random.Random(5)
+    for i in range(40):
+        W, H = r.choice([1, 2, 3, 4, 6]), r.choice([1, 2, 3, 5])
+        seeds = [r.randrange(10 ** 6) for _ in range(r.choice([2, 2, 3]))]
+        data = b"".join(synth_h264.make_stream(s, W=W, H=H) for s in seeds)
+        n, fb, rpost, rpre, ndec, dims = reference_decode(data)
+        assert n >= 0, f"{seeds}: reference decode error"
+        n_out, n_dec, odims, post, pre = decode_with_oracle(data)
+        assert (n_out, n_dec, odims) == (n, ndec, dims), f"{seeds}"
+        assert np.array_equal(pre, rpre) and np.array_equal(post, rpost), f"{seeds}: pictures differ from the reference"
