@@ -45,7 +45,10 @@ static uint32_t g_err_count;
 
 static uint32_t g_video_info[4];   /* h264bsdVideoRange, h264bsdMatrixCoefficients, sample aspect ratio w, h at the end of the last decode */
 
+static int g_no_reordering;        /* h264bsdInit's noOutputReordering argument for the next ref_decode_stream */
+
 void ref_set_resilient(int on) { g_resilient = on; }
+void ref_set_no_reordering(int on) { g_no_reordering = on; }
 void ref_video_info(uint32_t out[4]) { memcpy(out, g_video_info, sizeof g_video_info); }
 uint32_t ref_err_mbs(uint32_t *dst, uint32_t cap)
 {
@@ -103,7 +106,7 @@ int ref_decode_stream(const uint8_t *stream, size_t len,
     uint8_t *buf = (uint8_t *)malloc(len ? len : 1);
     if (!dec || !buf) return -1;
     memcpy(buf, stream, len);  /* decode mutates its input: byte_stream.c:193-233 */
-    if (h264bsdInit(dec, HANTRO_FALSE) != HANTRO_OK) return -1;
+    if (h264bsdInit(dec, g_no_reordering ? HANTRO_TRUE : HANTRO_FALSE) != HANTRO_OK) return -1;
 
     g_pre = pre; g_pre_cap = pre_cap; g_pre_len = 0;
     g_mbtap = (ref_mb_tap_t *)mbtap; g_mbtap_cap = mbtap_cap_records; g_mbtap_len = 0;

@@ -156,3 +156,27 @@ def test_concatenated_sequences_against_the_compiled_reference():
         n_out, n_dec, odims, post, pre = decode_with_oracle(data)
         assert (n_out, n_dec, odims) == (n, ndec, dims), f"{seeds}"
         assert np.array_equal(pre, rpre) and np.array_equal(post, rpost), f"{seeds}: pictures differ from the reference"
+
+
+@pytest.mark.skipif(_oracle.reference() is None, reason="oracle/_ref not built (needs the reference sources)")
+def test_no_output_reordering_mode_against_the_compiled_reference():
+    """h264bsdInit(storage, noOutputReordering = 1): pictures leave in decoding order, the DPB keeps reference frames only"""
+    import ctypes as C
+    from make_synth_golden import reference_decode
+    L = _oracle.reference()
+    L.ref_set_no_reordering.argtypes = [C.c_int]
+    for seed in range(40_000, 40_080):
+        data = synth_h264.make_stream(seed)
+        L.ref_set_no_reordering(1)
+        try:
+            n, fb, rpost, rpre, ndec, dims = reference_decode(data)
+        finally:
+            L.ref_set_no_reordering(0)
+        assert n >= 0, f"seed {seed}: reference decode error"
+        ps = ParsedStream(data, no_output_reordering=True)
+        try:
+            assert ps.status == 0 and (len(ps.outputs), ps.num_pics) == (n, ndec), f"seed {seed}"
+            post, pre, _ = _oracle.oracle_run_tape(ps, want_pre=True)
+        finally:
+            ps.close()
+        assert np.array_equal(pre, rpre) and np.array_equal(post, rpost), f"seed {seed}: pictures differ from the reference"
