@@ -353,3 +353,26 @@ def test_reference_posix_front_end_links_unchanged_and_fails_loudly_without_gpu(
         assert r.returncode != 0 and "no CUDA device" in r.stderr
     else:
         assert "73 pictures decoded" in r.stdout
+
+
+def test_tape_reuse_across_different_streams():
+    """a tape re-used for another stream (other size, other slot count, damaged or not) holds exactly what a fresh parse gives:
+    the records are built in place in memory nobody cleared, so every byte of a record must be written"""
+    import hashlib
+    import synth_h264
+
+    def signature(ps):
+        t = ps.ptr.contents
+        return (ps.status, ps.num_pics, ps.width_mbs, ps.height_mbs, ps.num_slots, tuple(ps.outputs),
+                hashlib.md5(C.string_at(t.mbRecs, t.mbRecBytes)).hexdigest(), hashlib.md5(C.string_at(t.coefs, t.coefBytes)).hexdigest(),
+                hashlib.md5(C.string_at(t.mbOrder, ps.num_pics * ps.mbs_per_pic * 2)).hexdigest())
+
+    reused = ParsedStream(synth_h264.make_stream(0))
+    for seed in range(1, 60):
+        damaged = seed % 3 == 0
+        data = synth_h264.make_damaged_stream(seed) if damaged else synth_h264.make_stream(seed)
+        fresh = ParsedStream(data, resilient=damaged)
+        reused.reparse(data, resilient=damaged)
+        assert signature(fresh) == signature(reused), f"seed {seed}"
+        fresh.close()
+    reused.close()
