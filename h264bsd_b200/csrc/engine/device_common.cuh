@@ -14,28 +14,16 @@
 #include "h264bsd_b200_tape.h"
 #include "pool_geom.hpp"
 #include "frame_addr.cuh"
+#include "device_ptx.cuh"
 
 namespace b200 {
 
 
 // ---- inter-warp completion flags (one 32-bit word per stream x macroblock) -----------------------
-__device__ __forceinline__ uint32_t ldAcquire(const uint32_t *p) {
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void stRelease(uint32_t *p, uint32_t v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 // Watchdog: a wait that lasts implausibly long (seconds) records a code and gives up, so that a protocol bug
 // shows up as a reported error (Batch::watchdog) instead of a hung GPU.
 __device__ uint32_t gWatchdog[4];
 constexpr unsigned long long kWatchdogNs = 4000000000ull;  // 4 s
-__device__ __forceinline__ unsigned long long globalTimerNs() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
 __device__ __forceinline__ void waitFlag(const uint32_t *p, uint32_t serial) {
     unsigned ns = 20, spins = 0;
     unsigned long long t0 = 0;
@@ -51,28 +39,6 @@ __device__ __forceinline__ void waitFlag(const uint32_t *p, uint32_t serial) {
 }
 
 // ---- TMA / mbarrier -------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smemAddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbarInit(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fenceMbarInit() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fenceProxyAsync() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void mbarExpectTx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbarTryWait(uint64_t *bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smemAddr(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
 __device__ __forceinline__ void mbarWait(uint64_t *bar, uint32_t parity) {
     unsigned spins = 0;
     unsigned long long t0 = 0;
@@ -84,19 +50,6 @@ __device__ __forceinline__ void mbarWait(uint64_t *bar, uint32_t parity) {
         }
     }
 }
-__device__ __forceinline__ void tmaLoad3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-        ::"r"(smemAddr(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smemAddr(bar))
-        : "memory");
-}
-__device__ __forceinline__ void tmaLoad4d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, int c3, uint64_t *bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-        ::"r"(smemAddr(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smemAddr(bar))
-        : "memory");
-}
-
 // ---- constant tables ------------------------------------------------------------------------------
 // 4x4 block order inside a macroblock (h264bsdBlockX/Y, intra_prediction.c:86-89), in 4-pel units
 __device__ __constant__ uint8_t cBlkX[16] = {0, 1, 0, 1, 2, 3, 2, 3, 0, 1, 0, 1, 2, 3, 2, 3};

@@ -1,0 +1,65 @@
+// device_ptx.cuh -- every line of inline PTX of the engine's ticketed kernels: acquire / release accesses, the global timer,
+// mbarrier and TMA tile loads.  (dp4a / cvt.pack live next to their only users in recon_kernel.cuh.)  A classic include guard
+// instead of #pragma once on purpose: tests/emu/ defines the guard and supplies host stand-ins for these few functions, so
+// that the kernels built on them compile for the host as they are.
+#ifndef B200_DEVICE_PTX_CUH
+#define B200_DEVICE_PTX_CUH
+#include <cstdint>
+#include <cuda.h>
+
+namespace b200 {
+
+// ---- inter-warp completion flags (one 32-bit word per stream x macroblock) -----------------------
+__device__ __forceinline__ uint32_t ldAcquire(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void stRelease(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globalTimerNs() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// ---- TMA / mbarrier -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smemAddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fenceMbarInit() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fenceProxyAsync() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbarExpectTx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbarTryWait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smemAddr(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void tmaLoad3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smemAddr(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smemAddr(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tmaLoad4d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, int c3, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(smemAddr(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smemAddr(bar))
+        : "memory");
+}
+
+}  // namespace b200
+
+#endif  // B200_DEVICE_PTX_CUH
