@@ -497,20 +497,6 @@ __global__ void __launch_bounds__(256) convertKernelT(const uint8_t *yPlane, int
     for (int i = 0; i < PELS; i += 4)
         *reinterpret_cast<uint4 *>(out + (size_t)y * W + x0 + i) = make_uint4(o[i], o[i + 1], o[i + 2], o[i + 3]);
 }
-// launch helper: picks the 8-pel variant when rows and pitches allow 8-byte luma / 4-byte chroma loads
-inline void launchConvert(cudaStream_t st, int nPictures, int H, const uint8_t *yPlane, int pitchY, const uint8_t *cbPlane, const uint8_t *crPlane,
-                          int pitchC, int W, int mode, uint32_t *out, unsigned long long inStride, unsigned long long outStride) {
-    const bool wide = (W % 8 == 0) && (pitchY % 8 == 0) && (pitchC % 4 == 0) && ((uintptr_t)yPlane % 8 == 0) && ((uintptr_t)cbPlane % 4 == 0) &&
-                      ((uintptr_t)crPlane % 4 == 0) && (inStride % 8 == 0);
-    if (wide) {
-        dim3 grid((W / 8 + 255) / 256, H, nPictures);
-        convertKernelT<8><<<grid, 256, 0, st>>>(yPlane, pitchY, cbPlane, crPlane, pitchC, W, mode, out, inStride, outStride);
-    } else {
-        dim3 grid((W / 4 + 255) / 256, H, nPictures);
-        convertKernelT<4><<<grid, 256, 0, st>>>(yPlane, pitchY, cbPlane, crPlane, pitchC, W, mode, out, inStride, outStride);
-    }
-}
-
 // ---- compare frame `slot` of every stream with stream 0's (picture area only) -------------------------------
 __global__ void __launch_bounds__(256) compareKernel(const uint8_t *pool, PoolGeom g, const uint32_t *slots, uint32_t *mismatch) {
     const int s = blockIdx.y + 1;

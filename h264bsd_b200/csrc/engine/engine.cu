@@ -614,6 +614,20 @@ bool Batch::writeFrame(uint32_t stream, uint32_t slot, const uint8_t *src) {
     return true;
 }
 
+// launch helper: picks the 8-pel variant when rows and pitches allow 8-byte luma / 4-byte chroma loads
+static void launchConvert(cudaStream_t st, int nPictures, int H, const uint8_t *yPlane, int pitchY, const uint8_t *cbPlane, const uint8_t *crPlane,
+                          int pitchC, int W, int mode, uint32_t *out, unsigned long long inStride, unsigned long long outStride) {
+    const bool wide = (W % 8 == 0) && (pitchY % 8 == 0) && (pitchC % 4 == 0) && ((uintptr_t)yPlane % 8 == 0) && ((uintptr_t)cbPlane % 4 == 0) &&
+                      ((uintptr_t)crPlane % 4 == 0) && (inStride % 8 == 0);
+    if (wide) {
+        dim3 grid((W / 8 + 255) / 256, H, nPictures);
+        convertKernelT<8><<<grid, 256, 0, st>>>(yPlane, pitchY, cbPlane, crPlane, pitchC, W, mode, out, inStride, outStride);
+    } else {
+        dim3 grid((W / 4 + 255) / 256, H, nPictures);
+        convertKernelT<4><<<grid, 256, 0, st>>>(yPlane, pitchY, cbPlane, crPlane, pitchC, W, mode, out, inStride, outStride);
+    }
+}
+
 bool Batch::convertFrame(uint32_t stream, uint32_t slot, int mode, uint32_t *dstHost) {
     if (!created_ || stream >= (uint32_t)g_.nStreams || slot >= (uint32_t)g_.numSlots || mode < 0 || mode > 2) return false;
     CK(cudaSetDevice(device_));

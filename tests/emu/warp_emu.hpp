@@ -1,11 +1,14 @@
-// warp_emu.hpp -- TEST INFRASTRUCTURE.  Just enough of the CUDA execution model to run a kernel that uses nothing but
-// thread / block indices, warp shuffles, warp barriers and plain memory accesses on the host: the 32 lanes of a warp are 32
-// host threads that meet at a barrier for every __shfl_sync / __syncwarp.  One warp at a time (warps of such kernels do not
-// talk to each other).  Slow and simple on purpose: it is there to check a kernel's indexing and arithmetic against the CPU
-// oracle where no GPU is at hand, not to stand in for the hardware's memory model.
+// warp_emu.hpp -- TEST INFRASTRUCTURE.  Just enough of the CUDA execution model to run the engine's kernels on the host:
+// a thread block is blockDim.x host threads, the 32 lanes of a warp meet at a barrier for every shuffle / vote / __syncwarp,
+// all threads of the block at __syncthreads; __shared__ variables are plain statics (one block runs at a time, blocks one
+// after the other -- every kernel run here hands out its work by tickets and waits only for work with smaller tickets, so a
+// block never waits for a later one).  Slow and simple on purpose: it is there to check a kernel's indexing, arithmetic and
+// ordering protocol against the CPU oracle where no GPU is at hand, not to stand in for the hardware's memory model.
 #pragma once
 #include <atomic>
+#include <chrono>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <algorithm>
 #include <functional>
@@ -15,25 +18,32 @@
 #define __global__
 #define __device__
 #define __host__
+#define __constant__
+#define __shared__ static
 #define __forceinline__ inline
 #define __launch_bounds__(...)
+#define __align__(n) alignas(n)
+#define __grid_constant__
 
 struct uint2 { uint32_t x, y; };
 inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
 struct alignas(16) uint4 { uint32_t x, y, z, w; };
-struct EmuDim3 { unsigned x = 0, y = 0, z = 0; };
+inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+struct EmuDim3 { unsigned x = 1, y = 1, z = 1; };
 inline thread_local EmuDim3 threadIdx, blockIdx;
-inline EmuDim3 gridDim;       // set by the caller before runBlock
+inline EmuDim3 gridDim, blockDim;       // set by runGrid
 using std::min;
 using std::max;
+using std::abs;
 
 namespace warp_emu {
+constexpr int kMaxWarps = 32;
 struct Barrier {
     std::atomic<int> arrived{0};
     std::atomic<unsigned> generation{0};
-    void wait() {
+    void wait(int parties) {
         const unsigned gen = generation.load(std::memory_order_acquire);
-        if (arrived.fetch_add(1, std::memory_order_acq_rel) == 31) {
+        if (arrived.fetch_add(1, std::memory_order_acq_rel) == parties - 1) {
             arrived.store(0, std::memory_order_relaxed);
             generation.fetch_add(1, std::memory_order_acq_rel);
         } else {
@@ -41,42 +51,91 @@ struct Barrier {
         }
     }
 };
-inline Barrier gBarrier;
-inline unsigned long long gExchange[32];
+inline Barrier gWarpBarrier[kMaxWarps], gBlockBarrier;
+inline unsigned long long gExchange[kMaxWarps][32];
+inline int warpOf() { return (int)(threadIdx.x >> 5); }
+inline int laneOf() { return (int)(threadIdx.x & 31); }
+inline void warpSync() { gWarpBarrier[warpOf()].wait(32); }
 
-// run `body` as block `block` of `warpsPerBlock` warps, one warp after the other
-inline void runBlock(unsigned block, unsigned warpsPerBlock, const std::function<void()> &body) {
-    for (unsigned w = 0; w < warpsPerBlock; w++) {
-        std::vector<std::thread> lanes;
-        for (unsigned l = 0; l < 32; l++)
-            lanes.emplace_back([=, &body]() {
-                threadIdx.x = w * 32 + l;
-                blockIdx.x = block;
+// `body` as a grid of `blocks` blocks of `threads` threads (a multiple of 32), one block after the other
+inline void runGrid(unsigned blocks, unsigned threads, const std::function<void()> &body) {
+    gridDim.x = blocks;
+    blockDim.x = threads;
+    for (unsigned b = 0; b < blocks; b++) {
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < threads; t++)
+            pool.emplace_back([=, &body]() {
+                threadIdx.x = t;
+                blockIdx.x = b;
                 body();
             });
-        for (auto &t : lanes) t.join();
+        for (auto &t : pool) t.join();
     }
 }
-}  // namespace warp_emu
-
-// every lane of the (full) warp must call these the same number of times -- true of the kernels run here, whose control flow
-// is warp-uniform
-template <typename T> inline T __shfl_sync(unsigned, T v, int srcLane) {
+template <typename T> inline unsigned long long pack(T v) {
     static_assert(sizeof(T) <= 8, "shuffles move at most 64 bits");
     unsigned long long raw = 0;
     std::memcpy(&raw, &v, sizeof(T));
-    warp_emu::gExchange[threadIdx.x & 31] = raw;
-    warp_emu::gBarrier.wait();
-    raw = warp_emu::gExchange[srcLane & 31];
-    warp_emu::gBarrier.wait();
+    return raw;
+}
+template <typename T> inline T unpack(unsigned long long raw) {
     T r;
     std::memcpy(&r, &raw, sizeof(T));
     return r;
 }
-inline void __syncwarp() { warp_emu::gBarrier.wait(); }
+// every lane of the (full) warp deposits `v`, then reads lane pick(lane)'s value
+template <typename T, typename F> inline T exchange(T v, F pick) {
+    const int w = warpOf(), l = laneOf();
+    gExchange[w][l] = pack(v);
+    warpSync();
+    const T r = unpack<T>(gExchange[w][pick(l)]);
+    warpSync();
+    return r;
+}
+}  // namespace warp_emu
+
+// Warp-level primitives: every lane of the (full) warp must call them together -- true of the kernels run here.
+template <typename T> inline T __shfl_sync(unsigned, T v, int srcLane) { return warp_emu::exchange(v, [=](int) { return srcLane & 31; }); }
+template <typename T> inline T __shfl_up_sync(unsigned, T v, unsigned d) { return warp_emu::exchange(v, [=](int l) { return l >= (int)d ? l - (int)d : l; }); }
+template <typename T> inline T __shfl_down_sync(unsigned, T v, unsigned d) { return warp_emu::exchange(v, [=](int l) { return l + (int)d < 32 ? l + (int)d : l; }); }
+template <typename T> inline T __shfl_xor_sync(unsigned, T v, int m) { return warp_emu::exchange(v, [=](int l) { return (l ^ m) & 31; }); }
+inline unsigned __ballot_sync(unsigned, int pred) {
+    const int w = warp_emu::warpOf(), l = warp_emu::laneOf();
+    warp_emu::gExchange[w][l] = pred ? 1 : 0;
+    warp_emu::warpSync();
+    unsigned r = 0;
+    for (int i = 0; i < 32; i++) r |= (unsigned)(warp_emu::gExchange[w][i] & 1) << i;
+    warp_emu::warpSync();
+    return r;
+}
+inline void __syncwarp() { warp_emu::warpSync(); }
+inline void __syncthreads() { warp_emu::gBlockBarrier.wait((int)blockDim.x); }
+inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+inline void __nanosleep(unsigned) { std::this_thread::yield(); }
 template <typename T> inline T __ldg(const T *p) { return *p; }
+template <typename T> inline T __ldcg(const T *p) { return *reinterpret_cast<const volatile T *>(p); }
+inline uint4 __ldcg(const uint4 *p) { uint4 v; std::memcpy(&v, p, sizeof v); return v; }
+inline uint2 __ldcg(const uint2 *p) { uint2 v; std::memcpy(&v, p, sizeof v); return v; }
 inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
+inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 // funnel shift right: the low 32 bits of (hi:lo) >> (shift & 31)
 inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift) {
     return (unsigned)(((((unsigned long long)hi) << 32) | lo) >> (shift & 31));
 }
+inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+
+// ---- host stand-ins for device_ptx.cuh (its include guard is taken, so the kernels pick these up instead) ----
+#define B200_DEVICE_PTX_CUH
+#include "cuda.h"
+namespace b200 {
+inline uint32_t ldAcquire(const uint32_t *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+inline void stRelease(uint32_t *p, uint32_t v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+inline unsigned long long globalTimerNs() {
+    return (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+// (mbarrier / TMA: not needed by the kernels run on the host so far)
+inline bool mbarTryWait(uint64_t *, uint32_t) { std::abort(); }
+}  // namespace b200

@@ -14,19 +14,22 @@ from h264bsd_b200.batch import ParsedStream
 
 ROOT = _oracle.ROOT
 EMU_DIR = os.path.join(ROOT, "tests", "emu")
-EMU_SO = os.path.join(EMU_DIR, "_build", "libconceal_emu.so")
+EMU_SO = os.path.join(EMU_DIR, "_build", "libkernels_emu.so")
 
 
 @pytest.fixture(scope="module")
 def emu():
     os.makedirs(os.path.dirname(EMU_SO), exist_ok=True)
-    subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-Wall", "-Wno-unknown-pragmas", "-I" + EMU_DIR,
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-Wall", "-Wno-unknown-pragmas",
+                           "-I" + os.path.join(EMU_DIR, "stubs"), "-I" + EMU_DIR,
                            "-I" + os.path.join(ROOT, "h264bsd_b200", "csrc", "engine"), "-I" + os.path.join(ROOT, "include"),
-                           os.path.join(EMU_DIR, "conceal_emu.cpp"), "-o", EMU_SO, "-lpthread"])
+                           os.path.join(EMU_DIR, "kernels_emu.cpp"), "-o", EMU_SO, "-lpthread"])
     L = C.CDLL(EMU_SO)
     L.emu_geom.argtypes = [C.c_uint32] * 3 + [C.POINTER(C.c_uint64)]
     L.emu_conceal.argtypes = [C.c_void_p] + [C.c_uint32] * 4 + [C.c_void_p, C.c_void_p] + [C.c_uint32] * 6
     L.emu_copy.argtypes = [C.c_void_p] + [C.c_uint32] * 4 + [C.c_void_p, C.c_void_p] + [C.c_uint32] * 5
+    L.emu_deblock.argtypes = [C.c_void_p] + [C.c_uint32] * 4 + [C.c_void_p] + [C.c_uint32] * 3
+    L.emu_deblock.restype = C.c_uint32
     return L
 
 
@@ -193,3 +196,48 @@ def test_copy_kernel_source_matches_oracle_on_the_host(emu, kind):
     assert pics >= 10 and mbs_checked >= 300, (pics, mbs_checked)
     if kind == "damaged":
         assert concealed_copies >= 20, concealed_copies
+
+
+@pytest.mark.parametrize("kind", ["valid", "damaged"])
+def test_filter_kernels_source_match_oracle_on_the_host(emu, kind):
+    """strengthKernel + deblockKernel (boundary strengths, then the ticketed wavefront filter with its flag waits) on whole
+    pictures: multi-slice / FMO pictures with all three filter modes and offsets, and damaged pictures whose concealed
+    macroblocks are filtered as Intra4x4 / QP 40.  Two streams, two blocks of eight concurrent warps."""
+    if kind == "valid":
+        streams = [(synth_h264.make_stream(s), False) for s in range(0, 40)]
+    else:
+        streams = [(synth_h264.make_damaged_stream(s), True) for s in range(0, 60)]
+    n_streams = 2
+    pics = concealed = 0
+    for data, resilient in streams:
+        ps = ParsedStream(data, resilient=resilient)
+        if ps.status != 0 or ps.num_pics == 0 or ps.mbs_per_pic > 40:
+            ps.close()
+            continue
+        W, H = ps.width_mbs * 16, ps.height_mbs * 16
+        g = (C.c_uint64 * 8)()
+        emu.emu_geom(ps.width_mbs, ps.height_mbs, ps.num_slots, g)
+        geom = [int(v) for v in g]
+        orc = _oracle.OracleDecoder(ps)
+        for k in range(min(ps.num_pics, 4)):
+            h = ps.pics[k]
+            orc.recon(k)
+            pool = aligned_pool(geom[6] * ps.num_slots * n_streams)
+            for st in range(n_streams):
+                to_pool(orc.frame(h.curSlot), W, H, geom, st * ps.num_slots + h.curSlot, pool)
+            wd = emu.emu_deblock(pool.ctypes.data, ps.width_mbs, ps.height_mbs, ps.num_slots, h.curSlot, orc._recs + h.mbRecOffset,
+                                 n_streams, 8 if (pics & 1) else 3, 2)
+            orc.deblock(k)
+            assert wd == 0, "a flag wait ran into the watchdog"
+            for st in range(n_streams):
+                assert np.array_equal(from_pool(W, H, geom, st * ps.num_slots + h.curSlot, pool), orc.frame(h.curSlot)), \
+                    f"picture {k}, stream {st}: strengthKernel + deblockKernel (emulated) differ from the oracle"
+            pics += 1
+            concealed += h.numErrMbs > 0
+        orc.close()
+        ps.close()
+        if pics >= 60:
+            break
+    assert pics >= 30, pics
+    if kind == "damaged":
+        assert concealed >= 5, concealed
