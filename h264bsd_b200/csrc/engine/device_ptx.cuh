@@ -1,5 +1,5 @@
 // device_ptx.cuh -- every line of inline PTX of the engine's ticketed kernels: acquire / release accesses, the global timer,
-// mbarrier and TMA tile loads.  (dp4a / cvt.pack live next to their only users in recon_kernel.cuh.)  A classic include guard
+// mbarrier and TMA tile loads, dp4a and cvt.pack.  A classic include guard
 // instead of #pragma once on purpose: tests/emu/ defines the guard and supplies host stand-ins for these few functions, so
 // that the kernels built on them compile for the host as they are.
 #ifndef B200_DEVICE_PTX_CUH
@@ -58,6 +58,21 @@ __device__ __forceinline__ void tmaLoad4d(void *dst, const CUtensorMap *map, int
         "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
         ::"r"(smemAddr(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smemAddr(bar))
         : "memory");
+}
+
+// ---- integer SIMD used by the motion compensation (recon_kernel.cuh) ---------------------------------
+// dp4a with unsigned pels and signed taps: the 6-tap filter (1,-5,20,20,-5,1) is two dot products
+__device__ __forceinline__ int dp4aUS(uint32_t pels, int taps, int acc) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(pels), "r"(taps), "r"(acc));
+    return d;
+}
+// four ints saturated to bytes, p0 in the low byte: two cvt.pack (I2IP) instead of four clamps, shifts and ors
+__device__ __forceinline__ uint32_t pack4sat(int p0, int p1, int p2, int p3) {
+    uint32_t hi, r;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, 0;" : "=r"(hi) : "r"(p3), "r"(p2));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(p1), "r"(p0), "r"(hi));
+    return r;
 }
 
 }  // namespace b200

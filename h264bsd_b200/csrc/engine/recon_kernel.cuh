@@ -301,12 +301,6 @@ __device__ __forceinline__ uint32_t lds4(const uint8_t *p) {
 
 
 // ---- 8-wide luma prediction for one lane (row y, columns x0..x0+7 of a 16x16 partition) --------------------
-// dp4a with unsigned pels and signed taps: the 6-tap filter (1,-5,20,20,-5,1) is two dot products
-__device__ __forceinline__ int dp4aUS(uint32_t pels, int taps, int acc) {
-    int d;
-    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(pels), "r"(taps), "r"(acc));
-    return d;
-}
 constexpr int kTapsLo = 0x1414FB01;  // bytes (1, -5, 20, 20)
 constexpr int kTapsHi = 0x000001FB;  // bytes (-5, 1, 0, 0)
 
@@ -343,12 +337,6 @@ __device__ __forceinline__ void vcol8(const uint8_t *colp, int *vs) {
     }
 }
 // four values -> four bytes with unsigned saturation, element 0 in the low byte (I2IP.U8.S32.SAT, two instructions)
-__device__ __forceinline__ uint32_t pack4sat(int p0, int p1, int p2, int p3) {
-    uint32_t hi, r;
-    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, 0;" : "=r"(hi) : "r"(p3), "r"(p2));
-    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(p1), "r"(p0), "r"(hi));
-    return r;
-}
 // clip255((v + 16) >> 5) / clip255((v + 512) >> 10) of eight sums, packed
 __device__ __forceinline__ uint2 pack8shift(const int *v, int rnd, int sh) {
     return make_uint2(pack4sat((v[0] + rnd) >> sh, (v[1] + rnd) >> sh, (v[2] + rnd) >> sh, (v[3] + rnd) >> sh),
