@@ -450,7 +450,9 @@ reconInterKernel(const ReconParams p, const __grid_constant__ CUtensorMap lumaMa
     const int r8 = lane >> 1, c8 = (lane & 1) * 8;
     const int cp = lane >> 4, cr = (lane >> 1) & 7, cc = (lane & 1) * 4;
 
-    // the chunk's records are fetched by the first n lanes in parallel (one dependent-load chain per chunk, not per MB)
+    // the chunk's records are fetched by the first n lanes in parallel (one dependent-load chain per chunk, not per MB).
+    // (Barrier first: a lane may still be reading the previous chunk's records -- an I_PCM macroblock ends its turn without one.)
+    __syncwarp();
     if (lane < n) {
         const uint32_t mb = __ldg(job.order + e0 + lane);
         const uint32_t *rw = reinterpret_cast<const uint32_t *>(job.recs + mb);

@@ -124,6 +124,19 @@ inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift) {
     return (unsigned)(((((unsigned long long)hi) << 32) | lo) >> (shift & 31));
 }
+// __byte_perm: result byte i = byte (selector nibble i) of the eight bytes {y, x}; selectors 0..7 only
+inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
+    const unsigned long long src = ((unsigned long long)y << 32) | x;
+    unsigned r = 0;
+    for (int i = 0; i < 4; i++) r |= (unsigned)((src >> (8 * ((s >> (4 * i)) & 7))) & 0xFF) << (8 * i);
+    return r;
+}
+// per-byte unsigned average, rounded up
+inline unsigned __vavgu4(unsigned a, unsigned b) {
+    unsigned r = 0;
+    for (int i = 0; i < 4; i++) r |= ((((a >> (8 * i)) & 0xFF) + ((b >> (8 * i)) & 0xFF) + 1) >> 1) << (8 * i);
+    return r;
+}
 inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 
@@ -136,6 +149,62 @@ inline void stRelease(uint32_t *p, uint32_t v) { __atomic_store_n(p, v, __ATOMIC
 inline unsigned long long globalTimerNs() {
     return (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
-// (mbarrier / TMA: not needed by the kernels run on the host so far)
-inline bool mbarTryWait(uint64_t *, uint32_t) { std::abort(); }
+// mbarrier / TMA.  The barrier word: bit 0 = parity of the current phase, bits 32.. = bytes still expected in it.  A tile load
+// copies at once (elements outside the tensor read as zero, as with OOB_FILL_NONE) and then reports its bytes; the load that
+// brings the count to zero completes the phase (release), which is what a parity wait observes (acquire).  What this cannot
+// show is a missing wait on a transfer that the hardware would still have in flight -- here it has always landed.
+inline uint32_t smemAddr(const void *) { return 0; }
+inline void mbarInit(uint64_t *bar, uint32_t) { __atomic_store_n(bar, 0ull, __ATOMIC_RELEASE); }
+inline void fenceMbarInit() {}
+inline void fenceProxyAsync() {}
+inline void mbarExpectTx(uint64_t *bar, uint32_t bytes) { __atomic_fetch_add(bar, (uint64_t)bytes << 32, __ATOMIC_ACQ_REL); }
+inline bool mbarTryWait(uint64_t *bar, uint32_t parity) {
+    const bool done = (__atomic_load_n(bar, __ATOMIC_ACQUIRE) & 1u) != (parity & 1u);
+    if (!done) std::this_thread::yield();
+    return done;
+}
+inline void mbarCompleteTx(uint64_t *bar, uint32_t bytes) {
+    const uint64_t left = __atomic_sub_fetch(bar, (uint64_t)bytes << 32, __ATOMIC_ACQ_REL);
+    if ((left >> 32) == 0) __atomic_fetch_xor(bar, 1ull, __ATOMIC_ACQ_REL);
+}
+inline void tmaTile(uint8_t *dst, const CUtensorMap *m, const int *c) {
+    const uint32_t *b = m->box;
+    const uint32_t n1 = m->rank > 1 ? b[1] : 1, n2 = m->rank > 2 ? b[2] : 1, n3 = m->rank > 3 ? b[3] : 1;
+    for (uint32_t i3 = 0; i3 < n3; i3++)
+        for (uint32_t i2 = 0; i2 < n2; i2++)
+            for (uint32_t i1 = 0; i1 < n1; i1++)
+                for (uint32_t i0 = 0; i0 < b[0]; i0++) {
+                    const long long x[4] = {c[0] + (long long)i0, c[1] + (long long)i1, m->rank > 2 ? c[2] + (long long)i2 : 0,
+                                            m->rank > 3 ? c[3] + (long long)i3 : 0};
+                    bool in = true;
+                    for (uint32_t d = 0; d < m->rank; d++) in = in && x[d] >= 0 && (uint64_t)x[d] < m->dims[d];
+                    uint8_t v = 0;
+                    if (in) {
+                        uint64_t off = (uint64_t)x[0];
+                        for (uint32_t d = 1; d < m->rank; d++) off += (uint64_t)x[d] * m->strides[d - 1];
+                        v = m->base[off];
+                    }
+                    *dst++ = v;
+                }
+}
+inline void tmaLoad3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar) {
+    const int c[4] = {c0, c1, c2, 0};
+    tmaTile(static_cast<uint8_t *>(dst), map, c);
+    mbarCompleteTx(bar, map->box[0] * map->box[1] * map->box[2]);
+}
+inline void tmaLoad4d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, int c3, uint64_t *bar) {
+    const int c[4] = {c0, c1, c2, c3};
+    tmaTile(static_cast<uint8_t *>(dst), map, c);
+    mbarCompleteTx(bar, map->box[0] * map->box[1] * map->box[2] * map->box[3]);
+}
+// dp4a.u32.s32: acc + sum of (unsigned byte of pels) x (signed byte of taps)
+inline int dp4aUS(uint32_t pels, int taps, int acc) {
+    for (int i = 0; i < 4; i++) acc += (int)((pels >> (8 * i)) & 0xFF) * (int)(int8_t)(((uint32_t)taps >> (8 * i)) & 0xFF);
+    return acc;
+}
+// cvt.pack.sat.u8.s32 twice: four ints saturated to bytes, p0 in the low byte
+inline uint32_t pack4sat(int p0, int p1, int p2, int p3) {
+    auto sat = [](int v) { return (uint32_t)(v < 0 ? 0 : v > 255 ? 255 : v); };
+    return sat(p0) | (sat(p1) << 8) | (sat(p2) << 16) | (sat(p3) << 24);
+}
 }  // namespace b200

@@ -20,8 +20,15 @@ EMU_SO = os.path.join(EMU_DIR, "_build", "libkernels_emu.so")
 @pytest.fixture(scope="module")
 def emu():
     os.makedirs(os.path.dirname(EMU_SO), exist_ok=True)
+    # reconInterKernel's dynamic shared memory is `extern __shared__ ...[]`; with __shared__ standing for `static` on the host that
+    # line -- and only that line -- has to read plain `extern` (the array itself is defined in kernels_emu.cpp)
+    src = open(os.path.join(ROOT, "h264bsd_b200", "csrc", "engine", "recon_kernel.cuh")).read()
+    line = "extern __shared__ __align__(128) uint8_t interSmemRaw[];"
+    assert src.count(line) == 1
+    with open(os.path.join(EMU_DIR, "_build", "recon_kernel_emu.cuh"), "w") as f:
+        f.write(src.replace(line, "extern uint8_t interSmemRaw[];"))
     subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-Wall", "-Wno-unknown-pragmas",
-                           "-I" + os.path.join(EMU_DIR, "stubs"), "-I" + EMU_DIR,
+                           "-I" + os.path.join(EMU_DIR, "stubs"), "-I" + EMU_DIR, "-I" + os.path.join(EMU_DIR, "_build"),
                            "-I" + os.path.join(ROOT, "h264bsd_b200", "csrc", "engine"), "-I" + os.path.join(ROOT, "include"),
                            os.path.join(EMU_DIR, "kernels_emu.cpp"), "-o", EMU_SO, "-lpthread"])
     L = C.CDLL(EMU_SO)
@@ -30,6 +37,13 @@ def emu():
     L.emu_copy.argtypes = [C.c_void_p] + [C.c_uint32] * 4 + [C.c_void_p, C.c_void_p] + [C.c_uint32] * 5
     L.emu_deblock.argtypes = [C.c_void_p] + [C.c_uint32] * 4 + [C.c_void_p] + [C.c_uint32] * 3
     L.emu_deblock.restype = C.c_uint32
+    L.emu_engine_create.argtypes = [C.c_uint32] * 4
+    L.emu_engine_create.restype = C.c_void_p
+    L.emu_engine_destroy.argtypes = [C.c_void_p]
+    L.emu_engine_pool.argtypes = [C.c_void_p]
+    L.emu_engine_pool.restype = C.POINTER(C.c_uint8)
+    L.emu_engine_picture.argtypes = [C.c_void_p] * 4 + [C.c_uint32] * 6 + [C.c_int] * 2 + [C.c_uint32] * 5
+    L.emu_engine_picture.restype = C.c_uint32
     return L
 
 
@@ -241,3 +255,65 @@ def test_filter_kernels_source_match_oracle_on_the_host(emu, kind):
     assert pics >= 30, pics
     if kind == "damaged":
         assert concealed >= 5, concealed
+
+
+def run_engine_on_the_host(emu, ps, n_streams=2, knobs=(8, 1, 4, 8), blocks=2, max_pics=None, stages=False):
+    """replay a tape through the emulated engine (every kernel of Batch::launchPicture, pool kept across pictures) next to the
+    oracle; returns the number of pictures compared"""
+    W, H, nmb = ps.width_mbs * 16, ps.height_mbs * 16, ps.mbs_per_pic
+    g = (C.c_uint64 * 8)()
+    emu.emu_geom(ps.width_mbs, ps.height_mbs, ps.num_slots, g)
+    geom = [int(v) for v in g]
+    eng = emu.emu_engine_create(ps.width_mbs, ps.height_mbs, ps.num_slots, n_streams)
+    pool = np.ctypeslib.as_array(emu.emu_engine_pool(eng), shape=(geom[6] * ps.num_slots * n_streams,))
+    orc = _oracle.OracleDecoder(ps)
+    t = ps.ptr.contents
+    order = C.cast(t.mbOrder, C.c_void_p).value
+    n = ps.num_pics if max_pics is None else min(ps.num_pics, max_pics)
+    try:
+        for k in range(n):
+            h = ps.pics[k]
+            args = (eng, orc._recs + h.mbRecOffset, orc._coefs + h.coefOffset, order + 2 * k * nmb, h.curSlot,
+                    h.numRun, h.numCopy, h.numPassA - h.numRunMbs - h.numCopy, h.numPassB, h.numConceal)
+            if stages:
+                assert emu.emu_engine_picture(*args, 1, 0, *knobs, blocks) == 0
+                orc.recon(k)
+                for st in range(n_streams):
+                    assert np.array_equal(from_pool(W, H, geom, st * ps.num_slots + h.curSlot, pool), orc.frame(h.curSlot)), \
+                        f"picture {k}, stream {st}: reconstruction (emulated kernels) differs from the oracle"
+                assert emu.emu_engine_picture(*args, 0, 1, *knobs, blocks) == 0
+                orc.deblock(k)
+            else:
+                assert emu.emu_engine_picture(*args, 1, 1, *knobs, blocks) == 0, "watchdog or IDCT range error"
+                orc.recon(k)
+                orc.deblock(k)
+            for st in range(n_streams):
+                assert np.array_equal(from_pool(W, H, geom, st * ps.num_slots + h.curSlot, pool), orc.frame(h.curSlot)), \
+                    f"picture {k}, stream {st}: the emulated engine differs from the oracle"
+    finally:
+        emu.emu_engine_destroy(eng)
+        orc.close()
+    return n
+
+
+@pytest.mark.parametrize("kind", ["valid", "damaged", "large"])
+def test_whole_engine_source_matches_oracle_on_the_host(emu, kind):
+    """every kernel of the per-picture launch sequence -- copy pass, TMA-staged inter pass, ticketed intra pass, concealment,
+    boundary strengths, wavefront filter, border -- as shipped, on the host, pictures chained through the frame pool the way
+    the engine chains them: synthetic streams (all macroblock types, several reference frames, vectors far outside the
+    picture), damaged streams (concealment), and the larger still-scene streams (long copy runs)"""
+    if kind == "valid":
+        jobs = [(synth_h264.make_stream(s), False, None, True) for s in range(0, 30)]
+    elif kind == "damaged":
+        jobs = [(synth_h264.make_damaged_stream(s), True, None, False) for s in range(0, 40)]
+    else:
+        jobs = [(synth_h264.make_stream(2, W=45, H=18, still=True, pictures=4), False, 3, False),
+                (synth_h264.make_stream(21, W=64, H=4, still=True, pictures=5), False, 4, False)]
+    pics = 0
+    for i, (data, resilient, max_pics, stages) in enumerate(jobs):
+        ps = ParsedStream(data, resilient=resilient)
+        if ps.status == 0 and ps.num_pics and (kind == "large" or ps.mbs_per_pic <= 40):
+            knobs = (8, 1, 4, 8) if i % 2 == 0 else (3, 2, 16, 2)       # chunkA, chunkB, copyRuns, filterChunk
+            pics += run_engine_on_the_host(emu, ps, knobs=knobs, blocks=2 + i % 2, max_pics=max_pics or 6, stages=stages)
+        ps.close()
+    assert pics >= (5 if kind == "large" else 40), pics
