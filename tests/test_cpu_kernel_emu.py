@@ -17,8 +17,8 @@ EMU_DIR = os.path.join(ROOT, "tests", "emu")
 EMU_SO = os.path.join(EMU_DIR, "_build", "libkernels_emu.so")
 
 
-@pytest.fixture(scope="module")
-def emu():
+def build_and_load():
+    """compile tests/emu/kernels_emu.cpp (the engine's kernel sources + warp_emu.hpp) with g++ and bind its entry points"""
     os.makedirs(os.path.dirname(EMU_SO), exist_ok=True)
     # reconInterKernel's dynamic shared memory is `extern __shared__ ...[]`; with __shared__ standing for `static` on the host that
     # line -- and only that line -- has to read plain `extern` (the array itself is defined in kernels_emu.cpp)
@@ -45,6 +45,11 @@ def emu():
     L.emu_engine_picture.argtypes = [C.c_void_p] * 4 + [C.c_uint32] * 6 + [C.c_int] * 2 + [C.c_uint32] * 5
     L.emu_engine_picture.restype = C.c_uint32
     return L
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return build_and_load()
 
 
 def aligned_pool(nbytes, fill=128):
