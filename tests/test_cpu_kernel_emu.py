@@ -322,3 +322,13 @@ def test_whole_engine_source_matches_oracle_on_the_host(emu, kind):
             pics += run_engine_on_the_host(emu, ps, knobs=knobs, blocks=2 + i % 2, max_pics=max_pics or 6, stages=stages)
         ps.close()
     assert pics >= (5 if kind == "large" else 40), pics
+
+
+def test_whole_engine_source_on_the_reference_stream(emu):
+    """the first pictures of the reference's own test_640x360.h264 (an IDR picture and P pictures of an encoder: long zero-motion
+    runs, every interpolation position) through the emulated engine, three streams on four blocks"""
+    ps = ParsedStream(_oracle.stream_bytes("test_640x360.h264"))
+    try:
+        assert run_engine_on_the_host(emu, ps, n_streams=3, knobs=(8, 1, 4, 8), blocks=4, max_pics=6) == 6
+    finally:
+        ps.close()
