@@ -23,7 +23,9 @@ DAMAGED_SEEDS = range(0, 240)
 LARGE = [(1, dict(W=45, H=18, still=True, pictures=4)), (2, dict(W=45, H=18, still=True, pictures=4)),
          (11, dict(W=40, H=23, still=True, pictures=3)), (12, dict(W=40, H=23, still=True, pictures=3)),
          (21, dict(W=64, H=4, still=True, pictures=5)), (32, dict(W=45, H=36, still=True, pictures=2)),
-         (31, dict(W=45, H=36, pictures=2)), (51, dict(W=120, H=3, still=True, pictures=3))]
+         (31, dict(W=45, H=36, pictures=2)), (51, dict(W=120, H=3, still=True, pictures=3)),
+         # 1080p-size pictures (level 4): the list sizes, ticket counts and chunking of the real workload with slices / FMO
+         (77, dict(W=120, H=68, still=True, pictures=2)), (78, dict(W=120, H=68, pictures=2))]
 
 
 def reference_decode(data):

@@ -115,7 +115,7 @@ BLK_Y = [0, 0, 1, 1, 0, 0, 1, 1, 2, 2, 3, 3, 2, 2, 3, 3]
 BLK_AT = [[0, 1, 4, 5], [2, 3, 6, 7], [8, 9, 12, 13], [10, 11, 14, 15]]   # [y][x]
 # Table A-1: level_idc -> (MaxDPB bytes, MaxFS) as the reference uses them (h264bsd_seq_param_set.c:380-488)
 LEVELS = {10: (152064, 99), 11: (345600, 396), 12: (912384, 396), 13: (912384, 396), 20: (912384, 396),
-          21: (1824768, 792), 22: (3110400, 1620), 30: (3110400, 1620), 31: (6912000, 3600)}
+          21: (1824768, 792), 22: (3110400, 1620), 30: (3110400, 1620), 31: (6912000, 3600), 40: (12582912, 8192)}
 
 INTER, I4, I16, PCM = 0, 1, 2, 3
 
@@ -970,7 +970,7 @@ def make_stream(seed, **force):
     W = force.get("W") or r.choice([1, 2, 3, 4, 5, 6, 8, 11])
     H = force.get("H") or r.choice([1, 2, 3, 4, 5, 6, 9])
     size = W * H
-    level = r.choice([l for l, (dpb, fs) in LEVELS.items() if fs >= size])
+    level = r.choice([l for l, (dpb, fs) in LEVELS.items() if fs >= size and l < 40] or [40])     # (level 4 only for pictures that need it)
     dpb_size = min(LEVELS[level][0] // (size * 384), 16)
     i_only = force.get("i_only", r.random() < 0.08)
     nrf = force.get("num_ref_frames")
