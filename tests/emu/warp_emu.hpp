@@ -146,8 +146,9 @@ inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v)
 namespace b200 {
 inline uint32_t ldAcquire(const uint32_t *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 inline void stRelease(uint32_t *p, uint32_t v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+// (a twentieth of real time: 256 yielding host threads on a busy machine are slow, the kernels' 4 s watchdog becomes 80 s)
 inline unsigned long long globalTimerNs() {
-    return (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    return (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count() / 20;
 }
 // mbarrier / TMA.  The barrier word: bit 0 = parity of the current phase, bits 32.. = bytes still expected in it.  A tile load
 // copies at once (elements outside the tensor read as zero, as with OOB_FILL_NONE) and then reports its bytes; the load that
