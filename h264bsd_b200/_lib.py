@@ -21,7 +21,7 @@ class PicHdr(C.Structure):
         ("mbRecOffset", C.c_uint64), ("coefOffset", C.c_uint64), ("numErrMbs", C.c_uint32), ("numOut", C.c_uint32),
         ("outSlot", C.c_uint8 * 20), ("outPicIndex", C.c_uint32 * 20), ("picId", C.c_uint32), ("numPassA", C.c_uint32),
         ("numPassB", C.c_uint32), ("numCopy", C.c_uint32), ("numRun", C.c_uint32), ("numRunMbs", C.c_uint32),
-        ("numConceal", C.c_uint32), ("reserved5", C.c_uint32),
+        ("numConceal", C.c_uint32), ("reserved5", C.c_uint32), ("filterRecOffset", C.c_uint64),
     ]
 
 

@@ -57,8 +57,9 @@ struct LegacyDecoder : public PictureSink {
             if (cudaMallocHost(&hostFrames[i], batch.frameBytes()) != cudaSuccess) { failed = true; return false; }
         return true;
     }
-    bool submitPicture(const b200_pic_hdr &hdr, const b200_mb_rec *recs, const int16_t *coefs, const uint16_t *order) override {
-        if (!batch.submitHostPicture(0, hdr, recs, coefs, order)) { failed = true; return false; }
+    bool submitPicture(const b200_pic_hdr &hdr, const b200_mb_rec *recs, const int16_t *coefs, const uint16_t *order,
+                       const b200_mb_rec *filterRecs) override {
+        if (!batch.submitHostPicture(0, hdr, recs, coefs, order, filterRecs)) { failed = true; return false; }
         return true;
     }
 };

@@ -299,7 +299,8 @@ bool Batch::buildJobs() {
     picMaxA_.assign(np, 0);
     picMaxB_.assign(np, 0);
     picMaxE_.assign(np, 0);
-    std::vector<StreamJob> jobs((size_t)np * g_.nStreams);
+    jobsFilterAt_ = (size_t)np * g_.nStreams;
+    std::vector<StreamJob> jobs(2 * jobsFilterAt_);
     for (uint32_t k = 0; k < np; k++)
         for (int s = 0; s < g_.nStreams; s++) {
             const DevTape &t = tapes_[s];
@@ -319,6 +320,10 @@ bool Batch::buildJobs() {
             picMaxC_[k] = std::max<uint32_t>(picMaxC_[k], j.nC);
             picMaxA_[k] = std::max<uint32_t>(picMaxA_[k], j.nA);
             picMaxB_[k] = std::max<uint32_t>(picMaxB_[k], j.nB);
+            // what the filter kernels get: the same job, with the picture's filter records where it has any
+            StreamJob &jf = jobs[jobsFilterAt_ + (size_t)k * g_.nStreams + s];
+            jf = j;
+            if (t.pics[k].filterRecOffset) jf.recs = reinterpret_cast<const b200_mb_rec *>(t.recs + t.pics[k].filterRecOffset);
         }
     // (cudaFree synchronises the whole device, queued uploads included: keep the table when it is large enough)
     if (jobsCap_ < jobs.size()) {
@@ -367,7 +372,7 @@ bool Batch::kernelTimes(float ms[6], uint32_t *launchesPerStage) {
     return true;
 }
 
-bool Batch::launchPicture(const StreamJob *dJobs, uint32_t maxQ, uint32_t maxC, uint32_t maxA, uint32_t maxB, uint32_t maxE, bool recon, bool deblock) {
+bool Batch::launchPicture(const StreamJob *dJobs, const StreamJob *dJobsFilter, uint32_t maxQ, uint32_t maxC, uint32_t maxA, uint32_t maxB, uint32_t maxE, bool recon, bool deblock) {
     const uint32_t total = (uint32_t)g_.nStreams * (uint32_t)g_.nMbs;
     serial_++;
     auto mark = [&](int stageEnded) {
@@ -396,7 +401,7 @@ bool Batch::launchPicture(const StreamJob *dJobs, uint32_t maxQ, uint32_t maxC, 
     }
     DeblockParams dp;
     if (deblock) {
-        dp.pool = pool_; dp.g = g_; dp.jobs = dJobs; dp.order = dOrder_; dp.done = dDoneDeblock_;
+        dp.pool = pool_; dp.g = g_; dp.jobs = dJobsFilter; dp.order = dOrder_; dp.done = dDoneDeblock_;
         dp.ticket = dCounters_ + 1; dp.serial = serial_; dp.totalTickets = total;
         dp.bsWords = dBsWords_; dp.work = dWork_;
         dp.workCount = reinterpret_cast<unsigned long long *>(dCounters_ + 4);
@@ -482,7 +487,7 @@ bool Batch::decodePicture(uint32_t k) {
         fences_.pop_front();
         if (covers) break;
     }
-    return launchPicture(dJobs_ + (size_t)k * g_.nStreams, picMaxQ_[k], picMaxC_[k], picMaxA_[k], picMaxB_[k], picMaxE_[k], true, true);
+    return launchPicture(dJobs_ + (size_t)k * g_.nStreams, dJobs_ + jobsFilterAt_ + (size_t)k * g_.nStreams, picMaxQ_[k], picMaxC_[k], picMaxA_[k], picMaxB_[k], picMaxE_[k], true, true);
 }
 
 bool Batch::debugStage(uint32_t k, bool recon, bool deblock) {
@@ -490,7 +495,7 @@ bool Batch::debugStage(uint32_t k, bool recon, bool deblock) {
     CK(cudaSetDevice(device_));
     if (jobsDirty_ && !buildJobs()) return false;
     if (k >= numPics_) return false;
-    return launchPicture(dJobs_ + (size_t)k * g_.nStreams, picMaxQ_[k], picMaxC_[k], picMaxA_[k], picMaxB_[k], picMaxE_[k], recon, deblock);
+    return launchPicture(dJobs_ + (size_t)k * g_.nStreams, dJobs_ + jobsFilterAt_ + (size_t)k * g_.nStreams, picMaxQ_[k], picMaxC_[k], picMaxA_[k], picMaxB_[k], picMaxE_[k], recon, deblock);
 }
 
 bool Batch::run(uint32_t first, uint32_t count) {
@@ -527,13 +532,14 @@ bool Batch::timerStop(float *ms) {
 }
 
 // streaming (single picture, host buffers): the legacy API path
-bool Batch::submitHostPicture(uint32_t stream, const b200_pic_hdr &hdr, const b200_mb_rec *recs, const int16_t *coefs, const uint16_t *order) {
+bool Batch::submitHostPicture(uint32_t stream, const b200_pic_hdr &hdr, const b200_mb_rec *recs, const int16_t *coefs, const uint16_t *order,
+                              const b200_mb_rec *filterRecs) {
     if (!created_ || g_.nStreams != 1 || stream != 0) return false;
     CK(cudaSetDevice(device_));
     const size_t recBytes = (size_t)g_.nMbs * sizeof(b200_mb_rec);
     const size_t coefBytes = (size_t)hdr.numCoefBlocks * B200_COEF_BLOCK_BYTES;
     const size_t orderBytes = (size_t)g_.nMbs * sizeof(uint16_t);
-    const size_t need = recBytes + coefBytes + orderBytes + 1024;
+    const size_t need = recBytes + coefBytes + orderBytes + (filterRecs ? recBytes + 256 : 0) + 1024;
     const int b = stageIdx_ ^= 1;
     if (stageCap_[b] < need) {
         // growing a staging buffer: make sure nothing in flight still reads it
@@ -562,13 +568,23 @@ bool Batch::submitHostPicture(uint32_t stream, const b200_pic_hdr &hdr, const b2
     job.nB = (uint16_t)hdr.numPassB;
     job.nE = (uint16_t)hdr.numConceal;
     job.pad[0] = job.pad[1] = 0;
+    // the job the filter kernels get sits 64 bytes behind: the same, unless the picture has records of its own for the filter
+    StreamJob jobF = job;
+    size_t end = coefOff + coefBytes;
+    if (filterRecs) {
+        const size_t fOff = (end + 255) & ~(size_t)255;
+        jobF.recs = reinterpret_cast<const b200_mb_rec *>(dStage_[b] + fOff);
+        std::memcpy(h + fOff, filterRecs, recBytes);
+        end = fOff + recBytes;
+    }
     std::memcpy(h, &job, sizeof job);
+    std::memcpy(h + 64, &jobF, sizeof jobF);
     std::memcpy(h + recOff, recs, recBytes);
     std::memcpy(h + orderOff, order, orderBytes);
     std::memcpy(h + coefOff, coefs, coefBytes);
-    CK(cudaMemcpyAsync(dStage_[b], h, coefOff + coefBytes, cudaMemcpyHostToDevice, stream_));
-    h2dBytes_ += coefOff + coefBytes;
-    if (!launchPicture(reinterpret_cast<const StreamJob *>(dStage_[b]), hdr.numRun, hdr.numCopy, hdr.numPassA - hdr.numRunMbs - hdr.numCopy, hdr.numPassB, hdr.numConceal, true, true)) return false;
+    CK(cudaMemcpyAsync(dStage_[b], h, end, cudaMemcpyHostToDevice, stream_));
+    h2dBytes_ += end;
+    if (!launchPicture(reinterpret_cast<const StreamJob *>(dStage_[b]), reinterpret_cast<const StreamJob *>(dStage_[b] + 64), hdr.numRun, hdr.numCopy, hdr.numPassA - hdr.numRunMbs - hdr.numCopy, hdr.numPassB, hdr.numConceal, true, true)) return false;
     CK(cudaEventRecord(stageEv_[b], stream_));
     return true;
 }

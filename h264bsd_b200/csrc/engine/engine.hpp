@@ -36,7 +36,8 @@ public:
     bool timerStart();
     bool timerStop(float *ms);
 
-    bool submitHostPicture(uint32_t stream, const b200_pic_hdr &hdr, const b200_mb_rec *recs, const int16_t *coefs, const uint16_t *order);
+    bool submitHostPicture(uint32_t stream, const b200_pic_hdr &hdr, const b200_mb_rec *recs, const int16_t *coefs, const uint16_t *order,
+                           const b200_mb_rec *filterRecs = nullptr);
     bool readFrame(uint32_t stream, uint32_t slot, uint8_t *dst);
     // picture k's frame of EVERY stream -> dst + s * strideBytes (asynchronous; dst should be pinned; sync() to wait)
     bool readPictureAll(uint32_t k, uint8_t *dst, size_t strideBytes);
@@ -67,7 +68,7 @@ private:
         std::vector<b200_pic_hdr> pics;
     };
     bool buildJobs();
-    bool launchPicture(const StreamJob *dJobs, uint32_t maxQ, uint32_t maxC, uint32_t maxA, uint32_t maxB, uint32_t maxE, bool recon, bool deblock);
+    bool launchPicture(const StreamJob *dJobs, const StreamJob *dJobsFilter, uint32_t maxQ, uint32_t maxC, uint32_t maxA, uint32_t maxB, uint32_t maxE, bool recon, bool deblock);
     std::vector<uint32_t> picMaxQ_, picMaxC_, picMaxA_, picMaxB_, picMaxE_;
 
     bool created_ = false;
@@ -94,7 +95,8 @@ private:
     std::vector<cudaEvent_t> fenceFree_;
     cudaStream_t auxStream_[2] = {nullptr, nullptr};   // copy pass / boundary strengths next to pass A
     std::vector<DevTape> tapes_;
-    StreamJob *dJobs_ = nullptr;
+    StreamJob *dJobs_ = nullptr;        // per picture and stream; the second half of the table is what the filter kernels get
+    size_t jobsFilterAt_ = 0;           // (the same jobs, except where a picture has records of its own for the filter)
     uint32_t numPics_ = 0;
     bool jobsDirty_ = true;
     // streaming staging (legacy single-stream API)

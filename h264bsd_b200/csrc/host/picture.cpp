@@ -909,6 +909,20 @@ void PictureState::finalizeRecords() {
             }
             r.flags = f;
             r.sliceId = aux[a].sliceId;
+            if (st != recs) {
+                // a macroblock decoded again by a redundant slice: the filter sees the state of its LAST decode (st), with the
+                // edge flags that state asks for
+                b200_mb_rec &fr = st[a];
+                const uint32_t idcF = fr.reserved0;
+                uint8_t ff = fr.flags & (uint8_t)(B200_MBF_AVAIL_A | B200_MBF_AVAIL_B | B200_MBF_AVAIL_C | B200_MBF_AVAIL_D | B200_MBF_CONCEALED);
+                if (idcF != 1) {
+                    ff |= B200_MBF_FILTER_INNER;
+                    if (x && (idcF != 2 || aux[a - 1].sliceId == aux[a].sliceId)) ff |= B200_MBF_FILTER_LEFT;
+                    if (y && (idcF != 2 || aux[a - widthMbs].sliceId == aux[a].sliceId)) ff |= B200_MBF_FILTER_TOP;
+                }
+                fr.flags = ff;
+                fr.sliceId = aux[a].sliceId;
+            }
             uint8_t c = 0, z = 0;
             if ((f & B200_MBF_CONCEALED) && r.mbType == B200_MB_I_4x4) {
                 // concealed: a zero-vector copy of the reference picture, or (class 5) spatial -- listed in its own section

@@ -248,7 +248,7 @@ void StreamDecoder::finishPicture() {
         hdr.outSlot[i] = (uint8_t)dpb_.pendingOutput(i).slot;
         hdr.outPicIndex[i] = dpb_.pendingOutput(i).picIndex;
     }
-    if (sink_) sink_->submitPicture(hdr, pic_.recs, pic_.coefs.data(), pic_.order.data());
+    if (sink_) sink_->submitPicture(hdr, pic_.recs, pic_.coefs.data(), pic_.order.data(), pic_.st != pic_.recs ? pic_.st : nullptr);
     picIndex_++;
     pic_.beginPicture();  // h264bsdResetStorage
     picStarted_ = false;

@@ -25,7 +25,9 @@ public:
     virtual bool configure(uint32_t widthMbs, uint32_t heightMbs, uint32_t numSlots) = 0;
     // a complete picture; `recs` (widthMbs*heightMbs records; the memory pictureRecords() lent, if it lent any), `coefs` and
     // `order` are only valid during the call
-    virtual bool submitPicture(const b200_pic_hdr &hdr, const b200_mb_rec *recs, const int16_t *coefs, const uint16_t *order) = 0;
+    // filterRecs: nullptr, or a second record array for the in-loop filter alone (b200_pic_hdr.filterRecOffset)
+    virtual bool submitPicture(const b200_pic_hdr &hdr, const b200_mb_rec *recs, const int16_t *coefs, const uint16_t *order,
+                               const b200_mb_rec *filterRecs) = 0;
 };
 
 class StreamDecoder {

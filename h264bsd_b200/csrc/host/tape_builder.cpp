@@ -54,7 +54,7 @@ public:
         if (!ensure(t_->mbRecs, t_->capRecs, t_->mbRecBytes + nrec)) { ok = false; return nullptr; }
         return reinterpret_cast<b200_mb_rec *>(t_->mbRecs + t_->mbRecBytes);
     }
-    bool submitPicture(const b200_pic_hdr &hdr, const b200_mb_rec *r, const int16_t *c, const uint16_t *o) override {
+    bool submitPicture(const b200_pic_hdr &hdr, const b200_mb_rec *r, const int16_t *c, const uint16_t *o, const b200_mb_rec *filterRecs) override {
         const size_t nMbs = (size_t)hdr.widthMbs * hdr.heightMbs;
         const size_t nrec = nMbs * sizeof(b200_mb_rec), ncoef = (size_t)hdr.numCoefBlocks * B200_COEF_BLOCK_BYTES, nord = nMbs * 2;
         uint64_t orderBytes = (uint64_t)t_->numPics * nMbs * 2;
@@ -75,8 +75,20 @@ public:
         if (!inPlace) std::memcpy(t_->mbRecs + t_->mbRecBytes, r, nrec);
         std::memcpy(t_->coefs + t_->coefBytes, c, ncoef);
         std::memcpy((uint8_t *)t_->mbOrder + orderBytes, o, nord);
-        t_->pics[t_->numPics] = h;
         t_->mbRecBytes += nrec;
+        if (filterRecs) {
+            // the records the in-loop filter reads instead (rare: redundant slices decoded macroblocks a second time): right
+            // behind the picture's own records
+            if (t_->pinned == 1 && t_->mbRecBytes + nrec > t_->capRecs) {
+                h264bsdB200UnpinTape(t_);
+                repin = true;
+            }
+            if (!ensure(t_->mbRecs, t_->capRecs, t_->mbRecBytes + nrec)) { ok = false; return false; }
+            std::memcpy(t_->mbRecs + t_->mbRecBytes, filterRecs, nrec);
+            h.filterRecOffset = t_->mbRecBytes;
+            t_->mbRecBytes += nrec;
+        }
+        t_->pics[t_->numPics] = h;
         t_->coefBytes += ncoef;
         t_->numPics++;
         return true;

@@ -144,6 +144,10 @@ typedef struct b200_pic_hdr {
     uint32_t numRunMbs;    /* macroblocks covered by the runs */
     uint32_t numConceal;   /* spatially concealed macroblocks: fifth section of the order list, concealment order */
     uint32_t reserved5;
+    uint64_t filterRecOffset; /* 0: the in-loop filter reads the records at mbRecOffset.  Else byte offset of a second record
+                              array for the filter alone: a picture in which redundant slices decoded macroblocks a second
+                              time keeps the pels of the first decode but is filtered with the state of the last one, as in
+                              the reference (h264bsd_macroblock_layer.c:1003-1007,:1108-1111) */
 } b200_pic_hdr;
 
 /* tape.status when the stream switches to another picture size: the tape ends with the last picture of the old size

@@ -77,7 +77,7 @@ class OracleDecoder:
 
     def deblock(self, k):
         h = self._pics[k]
-        self.L.px_deblock_picture(self.ctx, C.byref(h), self._recs + h.mbRecOffset)
+        self.L.px_deblock_picture(self.ctx, C.byref(h), self._recs + (h.filterRecOffset or h.mbRecOffset))
 
     def close(self):
         if self.ctx:

@@ -138,7 +138,7 @@ extern "C" uint8_t *emu_engine_pool(EmuEngine *e) { return e->pool; }
 
 // One picture of every stream (all streams replay the same work-list).  chunkA / chunkB / copyRuns / filterChunk: the engine's
 // tuning knobs; blocks: cap on the grid of the persistent kernels.  Returns watchdog[0] | watchdog[1] << 8 | IDCT errors << 16.
-extern "C" uint32_t emu_engine_picture(EmuEngine *e, const b200_mb_rec *recs, const int16_t *coefs, const uint16_t *order, uint32_t curSlot,
+extern "C" uint32_t emu_engine_picture(EmuEngine *e, const b200_mb_rec *recs, const b200_mb_rec *filterRecs, const int16_t *coefs, const uint16_t *order, uint32_t curSlot,
                                        uint32_t nR, uint32_t nC, uint32_t nA, uint32_t nB, uint32_t nE, int recon, int deblock,
                                        uint32_t chunkA, uint32_t chunkB, uint32_t copyRuns, uint32_t filterChunk, uint32_t blocks) {
     const PoolGeom &g = e->g;
@@ -147,6 +147,8 @@ extern "C" uint32_t emu_engine_picture(EmuEngine *e, const b200_mb_rec *recs, co
     job.recs = recs; job.coefs = coefs; job.order = order; job.curSlot = (uint16_t)curSlot;
     job.nR = (uint16_t)nR; job.nC = (uint16_t)nC; job.nA = (uint16_t)nA; job.nB = (uint16_t)nB; job.nE = (uint16_t)nE;
     std::vector<StreamJob> jobs(g.nStreams, job);
+    job.recs = filterRecs ? filterRecs : recs;               // what the filter kernels get (Batch::buildJobs)
+    std::vector<StreamJob> jobsFilter(g.nStreams, job);
     const uint32_t total = (uint32_t)g.nStreams * (uint32_t)g.nMbs;
     e->serial++;
     gWatchdog[0] = gWatchdog[1] = 0;
@@ -172,7 +174,7 @@ extern "C" uint32_t emu_engine_picture(EmuEngine *e, const b200_mb_rec *recs, co
     if (deblock) {
         DeblockParams dp;
         std::memset(&dp, 0, sizeof dp);
-        dp.pool = e->pool; dp.g = g; dp.jobs = jobs.data(); dp.order = e->order.data(); dp.done = e->doneDeblock.data();
+        dp.pool = e->pool; dp.g = g; dp.jobs = jobsFilter.data(); dp.order = e->order.data(); dp.done = e->doneDeblock.data();
         dp.ticket = e->counters.data() + 1; dp.serial = e->serial; dp.totalTickets = total;
         dp.bsWords = e->bsWords.data(); dp.work = e->work.data();
         dp.workCount = reinterpret_cast<unsigned long long *>(e->counters.data() + 4);

@@ -1206,10 +1206,9 @@ def make_stream(seed, **force):
         if pps["redundant_present"]:
             extra = []
             if dropped is not None:
-                if force.get("redundant_overlap"):
-                    # macroblocks decoded a second time while the picture is still incomplete: the reference keeps the pels
-                    # of the first decode but filters with the state of the second (h264bsd_macroblock_layer.c:1003-1007,
-                    # :1108-1111); the tape has one record per macroblock -- documented deviation, off by default
+                # macroblocks decoded a second time while the picture is still incomplete: the reference keeps the pels of the
+                # first decode but filters with the state of the second (h264bsd_macroblock_layer.c:1003-1007,:1108-1111)
+                if force.get("redundant_overlap", True):
                     extra = [slices[i] for i in range(len(slices)) if i != dropped and r.random() < 0.4]
                 extra.append(slices[dropped])
             extra += [mbs for mbs in slices if r.random() < 0.3]     # after the picture is complete: skipped
@@ -1277,5 +1276,7 @@ def corrupt_stream(data, seed):
 
 
 def make_damaged_stream(seed):
-    """stream `seed % 400` (without redundant slices: see make_stream's redundant_overlap note) damaged by corrupt_stream(seed)"""
+    """stream `seed % 400` damaged by corrupt_stream(seed).  Without redundant slices: a macroblock that was decoded, served as
+    intra neighbour and is then given up because a redundant slice over it turns out corrupt is the one case the tape cannot
+    express (DESIGN.md, deviations)"""
     return corrupt_stream(make_stream(seed % 400, redundant=False), seed)

@@ -49,7 +49,7 @@ def test_record_layout():
                     ('fa', 'i1'), ('fb', 'i1'), ('cqo', 'i1'), ('sub', 'u1'), ('refSlot', 'u1', 4), ('icm', 'u1'), ('idc', 'u1'),
                     ('sliceId', '<u2'), ('refIdx', 'u1', 4), ('r1', 'u1', 4), ('mv', '<i2', (16, 2))])
     assert rec.itemsize == 96
-    assert C.sizeof(_lib.PicHdr) == 192
+    assert C.sizeof(_lib.PicHdr) == 200
 
 
 def test_parse_360p_statistics():

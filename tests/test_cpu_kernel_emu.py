@@ -42,7 +42,7 @@ def build_and_load():
     L.emu_engine_destroy.argtypes = [C.c_void_p]
     L.emu_engine_pool.argtypes = [C.c_void_p]
     L.emu_engine_pool.restype = C.POINTER(C.c_uint8)
-    L.emu_engine_picture.argtypes = [C.c_void_p] * 4 + [C.c_uint32] * 6 + [C.c_int] * 2 + [C.c_uint32] * 5
+    L.emu_engine_picture.argtypes = [C.c_void_p] * 5 + [C.c_uint32] * 6 + [C.c_int] * 2 + [C.c_uint32] * 5
     L.emu_engine_picture.restype = C.c_uint32
     return L
 
@@ -244,7 +244,8 @@ def test_filter_kernels_source_match_oracle_on_the_host(emu, kind):
             pool = aligned_pool(geom[6] * ps.num_slots * n_streams)
             for st in range(n_streams):
                 to_pool(orc.frame(h.curSlot), W, H, geom, st * ps.num_slots + h.curSlot, pool)
-            wd = emu.emu_deblock(pool.ctypes.data, ps.width_mbs, ps.height_mbs, ps.num_slots, h.curSlot, orc._recs + h.mbRecOffset,
+            wd = emu.emu_deblock(pool.ctypes.data, ps.width_mbs, ps.height_mbs, ps.num_slots, h.curSlot,
+                                 orc._recs + (h.filterRecOffset or h.mbRecOffset),     # the filter's own records where a picture has them
                                  n_streams, 8 if (pics & 1) else 3, 2)
             orc.deblock(k)
             assert wd == 0, "a flag wait ran into the watchdog"
@@ -278,7 +279,8 @@ def run_engine_on_the_host(emu, ps, n_streams=2, knobs=(8, 1, 4, 8), blocks=2, m
     try:
         for k in range(n):
             h = ps.pics[k]
-            args = (eng, orc._recs + h.mbRecOffset, orc._coefs + h.coefOffset, order + 2 * k * nmb, h.curSlot,
+            args = (eng, orc._recs + h.mbRecOffset, (orc._recs + h.filterRecOffset) if h.filterRecOffset else None,
+                    orc._coefs + h.coefOffset, order + 2 * k * nmb, h.curSlot,
                     h.numRun, h.numCopy, h.numPassA - h.numRunMbs - h.numCopy, h.numPassB, h.numConceal)
             if stages:
                 assert emu.emu_engine_picture(*args, 1, 0, *knobs, blocks) == 0
