@@ -179,7 +179,9 @@ def algorithmic_bytes(ps):
     D = 96-byte record; deblock 768 + D (it re-reads the record) per MB."""
     import numpy as np
     t = ps.ptr.contents
-    recs = np.ctypeslib.as_array(t.mbRecs, shape=(t.mbRecBytes,)).reshape(-1, MB_REC_BYTES)
+    area = np.ctypeslib.as_array(t.mbRecs, shape=(t.mbRecBytes,))
+    pic_bytes = ps.mbs_per_pic * MB_REC_BYTES      # (a picture's records; a picture may be followed by filter-only records)
+    recs = np.concatenate([area[p.mbRecOffset:p.mbRecOffset + pic_bytes] for p in ps.pics]).reshape(-1, MB_REC_BYTES)
     types = recs[:, 0]
     masks = recs[:, 4:8].copy().view("<u4")[:, 0] & 0x3FFFFFF
     pop = np.zeros(len(masks), np.int64)
