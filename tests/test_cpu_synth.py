@@ -90,7 +90,9 @@ def test_golden_streams_cover_the_syntax():
     for seed in SEEDS[:60]:
         ps = ParsedStream(synth_h264.make_stream(seed))
         t = ps.ptr.contents
-        a = np.frombuffer(C.string_at(t.mbRecs, t.mbRecBytes), rec)
+        n = ps.mbs_per_pic
+        area = C.string_at(t.mbRecs, t.mbRecBytes)      # (a picture's records may be followed by records for the filter alone)
+        a = np.concatenate([np.frombuffer(area, rec, count=n, offset=p.mbRecOffset) for p in ps.pics])
         types |= set(np.unique(a["mbType"]).tolist())
         p8 = a[(a["mbType"] == 4) | (a["mbType"] == 5)]
         for q in range(4):
@@ -101,7 +103,6 @@ def test_golden_streams_cover_the_syntax():
         inter = a[a["mbType"] <= 5]
         multi_ref += int((inter["refIdx"] > 0).any(axis=1).sum())
         far_mv += int((np.abs(inter["mv"][:, :, 0]) > 1000).any(axis=1).sum())
-        n = ps.mbs_per_pic
         multi_slice += sum(1 for k in range(ps.num_pics) if len(np.unique(a["sliceId"][k * n:(k + 1) * n])) > 1)
         reordered += int(ps.outputs != sorted(ps.outputs))
         ps.close()

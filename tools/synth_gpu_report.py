@@ -48,7 +48,8 @@ def main():
             print(f"seed {seed}: parser status {ps.status}"); continue
         W, H = ps.width_mbs, ps.height_mbs
         t = ps.ptr.contents
-        recs = np.frombuffer(C.string_at(t.mbRecs, t.mbRecBytes), REC)
+        area = C.string_at(t.mbRecs, t.mbRecBytes)
+        recs = np.concatenate([np.frombuffer(area, REC, count=W * H, offset=p.mbRecOffset) for p in ps.pics])
         orc = _oracle.OracleDecoder(ps)
         try:
             b = Batch(1, W, H, ps.num_slots)
