@@ -60,6 +60,22 @@ __device__ __forceinline__ void tmaLoad4d(void *dst, const CUtensorMap *map, int
         : "memory");
 }
 
+// ---- 1-D bulk copies (copy_bulk_kernel.cuh): addresses and size are multiples of 16 bytes ----------------------------
+__device__ __forceinline__ void bulkLoad(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smemAddr(dst)), "l"(src), "r"(bytes), "r"(smemAddr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulkStore(void *dst, const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smemAddr(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulkCommit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// until at most N of this thread's most recent bulk groups are still reading their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulkWaitRead() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+// until all of this thread's bulk groups are complete (their writes performed)
+__device__ __forceinline__ void bulkWaitAll() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ---- integer SIMD used by the motion compensation (recon_kernel.cuh) ---------------------------------
 // dp4a with unsigned pels and signed taps: the 6-tap filter (1,-5,20,20,-5,1) is two dot products
 __device__ __forceinline__ int dp4aUS(uint32_t pels, int taps, int acc) {

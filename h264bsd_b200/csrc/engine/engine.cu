@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 #include "recon_kernel.cuh"
 #include "copy_kernel.cuh"
+#include "copy_bulk_kernel.cuh"
 #include "conceal_kernel.cuh"
 #include "deblock_kernel.cuh"
 #include "engine.hpp"
@@ -164,6 +165,15 @@ bool Batch::create(int device, uint32_t nStreams, uint32_t widthMbs, uint32_t he
     int occC = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occC, reconCopyKernel, kCopyWarps * 32, 0));
     copyBlocks_ = std::max(1, occC) * numSms_;
+    // experimental bulk-copy variant of the run section (copy_bulk_kernel.cuh): off unless B200_COPY_BULK=1
+    if (const char *e = std::getenv("B200_COPY_BULK")) copyBulk_ = std::atoi(e) != 0;
+    if (copyBulk_) {
+        int occQ = 0;
+        CK(cudaFuncSetAttribute(reconCopyBulkKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(BulkWarpSmem) * kBulkWarps)));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occQ, reconCopyBulkKernel, kBulkWarps * 32, sizeof(BulkWarpSmem) * kBulkWarps));
+        copyBulkBlocks_ = std::max(1, occQ) * numSms_;
+        if (const char *e = std::getenv("B200_COPY_BULK_RUNS")) copyBulkRuns_ = std::max(1, std::min((int)kBulkRunsPerTask, std::atoi(e)));
+    }
     deblockBlocks_ = std::max(1, occD) * numSms_;
     // tuning knobs (defaults are the measured best on the 512-stream 1080p batch)
     if (const char *e = std::getenv("B200_CHUNK_B")) chunkB_ = std::max(1, std::min((int)kChunkB, std::atoi(e)));
@@ -423,9 +433,27 @@ bool Batch::launchPicture(const StreamJob *dJobs, const StreamJob *dJobsFilter, 
         if (maxC || maxQ) {
             cudaStream_t st = copyAside ? auxStream_[0] : stream_;
             if (copyAside) CK(cudaStreamWaitEvent(st, forkEv_, 0));
-            const uint32_t ctas = ((rp.chunksC + rp.chunksQ) * (uint32_t)g_.nStreams + kCopyWarps - 1) / kCopyWarps;
-            reconCopyKernel<<<std::min<uint32_t>(ctas, (uint32_t)copyBlocks_), kCopyWarps * 32, 0, st>>>(rp);
-            launches_++;
+            if (copyBulk_) {
+                // runs by the bulk-copy engine, single copies by reconCopyKernel (a launch without run tasks)
+                ReconParams rq = rp, rs = rp;
+                rq.copyRuns = (uint32_t)copyBulkRuns_;
+                rq.chunksQ = (maxQ + rq.copyRuns - 1) / rq.copyRuns;
+                rs.chunksQ = 0;
+                if (maxQ) {
+                    const uint32_t ctas = (rq.chunksQ * (uint32_t)g_.nStreams + kBulkWarps - 1) / kBulkWarps;
+                    reconCopyBulkKernel<<<std::min<uint32_t>(ctas, (uint32_t)copyBulkBlocks_), kBulkWarps * 32, sizeof(BulkWarpSmem) * kBulkWarps, st>>>(rq);
+                    launches_++;
+                }
+                if (maxC) {
+                    const uint32_t ctas = (rs.chunksC * (uint32_t)g_.nStreams + kCopyWarps - 1) / kCopyWarps;
+                    reconCopyKernel<<<std::min<uint32_t>(ctas, (uint32_t)copyBlocks_), kCopyWarps * 32, 0, st>>>(rs);
+                    launches_++;
+                }
+            } else {
+                const uint32_t ctas = ((rp.chunksC + rp.chunksQ) * (uint32_t)g_.nStreams + kCopyWarps - 1) / kCopyWarps;
+                reconCopyKernel<<<std::min<uint32_t>(ctas, (uint32_t)copyBlocks_), kCopyWarps * 32, 0, st>>>(rp);
+                launches_++;
+            }
             if (copyAside) CK(cudaEventRecord(joinEv_[0], st));
             mark(5);
         }

@@ -90,6 +90,8 @@ private:
     uint32_t *dConvertAll_ = nullptr;
     int chunkB_ = 1, filterChunk_ = 8;   // list entries per intra warp task / tickets per filter warp step
     int chunkA_ = 8, copyRuns_ = 4;      // list entries per pass-A warp / runs per copy warp task
+    bool copyBulk_ = false;              // B200_COPY_BULK=1: zero-motion runs by reconCopyBulkKernel (experimental)
+    int copyBulkBlocks_ = 0, copyBulkRuns_ = 16;
     cudaStream_t uploadStream_ = nullptr;
     std::deque<std::pair<uint32_t, cudaEvent_t>> fences_;   // (pictures below this index, upload-stream event)
     std::vector<cudaEvent_t> fenceFree_;

@@ -2,17 +2,20 @@
 // (h264bsd_b200/csrc/engine/conceal_kernel.cuh, copy_kernel.cuh, deblock_kernel.cuh) compiled for the host with warp_emu.hpp and exposed to the tests:
 //   emu_geom()     the pool geometry the engine would use (makePoolGeom)
 //   emu_conceal()  one launch of concealKernel over a pool of nStreams streams in host memory
-//   emu_copy()     one launch of reconCopyKernel, the grid the engine would use cut down to `blocks`
+//   emu_copy()     one launch of reconCopyKernel, the grid the engine would use cut down to `blocks`; copyRuns with bit 31 set:
+//                  the B200_COPY_BULK=1 sequence instead (reconCopyBulkKernel for the runs, reconCopyKernel for the single copies)
 //   emu_deblock()  strengthKernel + deblockKernel over a pool of nStreams streams (Batch::launchPicture's deblock half)
 //   emu_engine_*() the whole per-picture launch sequence of Batch::launchPicture over a persistent pool
 #include "warp_emu.hpp"
 #include "recon_kernel_emu.cuh"   // = recon_kernel.cuh with the dynamic shared array declared plain extern (made by the test)
 #include "copy_kernel.cuh"
+#include "copy_bulk_kernel.cuh"
 #include "conceal_kernel.cuh"
 #include "deblock_kernel.cuh"
 
 namespace b200 {
 alignas(128) uint8_t interSmemRaw[sizeof(InterWarpSmem) * kReconWarps];   // the dynamic shared memory of reconInterKernel
+alignas(128) uint8_t bulkSmemRaw[sizeof(BulkWarpSmem) * kBulkWarps];      // ... of reconCopyBulkKernel
 }
 
 using namespace b200;
@@ -41,6 +44,22 @@ extern "C" void emu_conceal(uint8_t *pool, uint32_t widthMbs, uint32_t heightMbs
     warp_emu::runGrid((nStreams + kConcealWarps - 1) / kConcealWarps, kConcealWarps * 32, [&]() { concealKernel(p); });
 }
 
+// the copy pass with B200_COPY_BULK=1 (Batch::launchPicture): runs by the bulk kernel, single copies by a launch without run tasks
+static void launchCopyBulk(const ReconParams &rp, uint32_t nR, uint32_t nC, uint32_t blocks) {
+    ReconParams rq = rp, rs = rp;
+    rq.copyRuns = std::min<uint32_t>(rp.copyRuns, kBulkRunsPerTask);
+    rq.chunksQ = (nR + rq.copyRuns - 1) / rq.copyRuns;
+    rs.chunksQ = 0;
+    if (nR) {
+        const uint32_t ctas = (rq.chunksQ * (uint32_t)rp.g.nStreams + kBulkWarps - 1) / kBulkWarps;
+        warp_emu::runGrid(std::min(ctas, blocks), kBulkWarps * 32, [&]() { reconCopyBulkKernel(rq); });
+    }
+    if (nC) {
+        const uint32_t ctas = (rs.chunksC * (uint32_t)rp.g.nStreams + kCopyWarps - 1) / kCopyWarps;
+        warp_emu::runGrid(std::min(ctas, blocks), kCopyWarps * 32, [&]() { reconCopyKernel(rs); });
+    }
+}
+
 extern "C" void emu_copy(uint8_t *pool, uint32_t widthMbs, uint32_t heightMbs, uint32_t numSlots, uint32_t curSlot,
                          const b200_mb_rec *recs, const uint16_t *order, uint32_t nR, uint32_t nC, uint32_t nStreams, uint32_t copyRuns,
                          uint32_t blocks) {
@@ -54,10 +73,13 @@ extern "C" void emu_copy(uint8_t *pool, uint32_t widthMbs, uint32_t heightMbs, u
     p.pool = pool;
     p.g = makePoolGeom(widthMbs, heightMbs, numSlots, nStreams);
     p.jobs = jobs.data();
+    const bool bulk = (copyRuns & 0x80000000u) != 0;
+    copyRuns &= 0x7FFFFFFFu;
     p.copyRuns = copyRuns;                                   // as Batch::launchPicture sets them
     p.chunksC = (nC + 31) / 32;
     p.chunksQ = (nR + copyRuns - 1) / copyRuns;
-    warp_emu::runGrid(blocks, kCopyWarps * 32, [&]() { reconCopyKernel(p); });   // a persistent grid: tasks are strided over it
+    if (bulk) launchCopyBulk(p, nR, nC, blocks);
+    else warp_emu::runGrid(blocks, kCopyWarps * 32, [&]() { reconCopyKernel(p); });   // a persistent grid: tasks are strided over it
 }
 
 // The in-loop filter of one picture: boundary strengths, then the ticketed wavefront filter -- parameters as Batch::create /
@@ -158,12 +180,15 @@ extern "C" uint32_t emu_engine_picture(EmuEngine *e, const b200_mb_rec *recs, co
         rp.pool = e->pool; rp.g = g; rp.jobs = jobs.data(); rp.done = e->doneRecon.data();
         rp.ticket = e->counters.data() + 0; rp.errors = e->counters.data() + 2; rp.serial = e->serial;
         rp.chunkB = chunkB; rp.chunksB = (nB + chunkB - 1) / chunkB;
+        const bool bulk = (copyRuns & 0x80000000u) != 0;   // the B200_COPY_BULK=1 sequence
+        copyRuns &= 0x7FFFFFFFu;
         rp.chunkA = chunkA; rp.copyRuns = copyRuns;
         rp.chunksA = (nA + kReconWarps * chunkA - 1) / (kReconWarps * chunkA);
         rp.virtualCtasA = rp.chunksA * (uint32_t)g.nStreams;
         rp.chunksC = (nC + 31) / 32;
         rp.chunksQ = (nR + copyRuns - 1) / copyRuns;
-        if (nC || nR) {
+        if ((nC || nR) && bulk) launchCopyBulk(rp, nR, nC, blocks);
+        else if (nC || nR) {
             const uint32_t ctas = ((rp.chunksC + rp.chunksQ) * (uint32_t)g.nStreams + kCopyWarps - 1) / kCopyWarps;
             warp_emu::runGrid(std::min(ctas, blocks), kCopyWarps * 32, [&]() { reconCopyKernel(rp); });
         }

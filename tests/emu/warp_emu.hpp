@@ -8,6 +8,7 @@
 #include <atomic>
 #include <chrono>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
@@ -24,6 +25,8 @@
 #define __launch_bounds__(...)
 #define __align__(n) alignas(n)
 #define __grid_constant__
+// dynamic shared memory of a kernel: a plain array the harness defines (kernels_emu.cpp)
+#define B200_DYNAMIC_SMEM(name) extern uint8_t name[]
 
 struct uint2 { uint32_t x, y; };
 inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
@@ -198,6 +201,35 @@ inline void tmaLoad4d(void *dst, const CUtensorMap *map, int c0, int c1, int c2,
     tmaTile(static_cast<uint8_t *>(dst), map, c);
     mbarCompleteTx(bar, map->box[0] * map->box[1] * map->box[2] * map->box[3]);
 }
+// 1-D bulk copies (cp.async.bulk).  Both ends must be 16-byte aligned and the size a multiple of 16, or the hardware faults: checked
+// here.  A load lands at once and reports its bytes to the mbarrier.  A store is DEFERRED: it joins the calling thread's open bulk
+// group and reads its shared-memory source only when a wait lets the group go (bulkWaitRead<N>: all but the N most recent groups;
+// bulkWaitAll: all) -- so a staging buffer that is refilled before the wait that protects it shows up as wrong pels, and stores
+// still pending when the thread leaves the kernel are lost (its list dies with it).
+struct BulkStoreOp { void *dst; const void *src; uint32_t bytes; };
+inline thread_local std::vector<std::vector<BulkStoreOp>> tBulkGroups;
+inline thread_local std::vector<BulkStoreOp> tBulkOpen;
+inline void bulkCheck(const void *a, const void *b, uint32_t bytes) {
+    if (((uintptr_t)a | (uintptr_t)b | bytes) & 15u) { std::fprintf(stderr, "warp_emu: misaligned cp.async.bulk (%p, %p, %u)\n", a, b, bytes); std::abort(); }
+}
+inline void bulkLoad(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    bulkCheck(dst, src, bytes);
+    std::memcpy(dst, src, bytes);
+    mbarCompleteTx(bar, bytes);
+}
+inline void bulkStore(void *dst, const void *src, uint32_t bytes) {
+    bulkCheck(dst, src, bytes);
+    tBulkOpen.push_back(BulkStoreOp{dst, src, bytes});
+}
+inline void bulkCommit() { tBulkGroups.push_back(std::move(tBulkOpen)); tBulkOpen.clear(); }
+inline void bulkDrain(size_t keep) {
+    while (tBulkGroups.size() > keep) {
+        for (const BulkStoreOp &op : tBulkGroups.front()) std::memcpy(op.dst, op.src, op.bytes);
+        tBulkGroups.erase(tBulkGroups.begin());
+    }
+}
+template <int N> inline void bulkWaitRead() { bulkDrain((size_t)N); }
+inline void bulkWaitAll() { bulkDrain(0); }
 // dp4a.u32.s32: acc + sum of (unsigned byte of pels) x (signed byte of taps)
 inline int dp4aUS(uint32_t pels, int taps, int acc) {
     for (int i = 0; i < 4; i++) acc += (int)((pels >> (8 * i)) & 0xFF) * (int)(int8_t)(((uint32_t)taps >> (8 * i)) & 0xFF);

@@ -133,3 +133,62 @@ def test_damaged_streams_concealment_matches_oracle(chunk):
         orc.close()
         ps.close()
     assert concealed > 0
+
+
+def _bulk_copy_body():
+    """runs in a process of its own (see the test below): B200_COPY_BULK=1 is read when a Batch is created"""
+    md5s = json.load(open(os.path.join(_oracle.GOLDEN, "md5.json")))
+    checked = 0
+    # (1) still scenes with long runs that start at odd and even columns, three instances, every picture against the oracle
+    for seed, w, hh in ((3, 11, 4), (4, 40, 3), (6, 7, 6), (9, 37, 2), (11, 33, 5)):
+        ps = ParsedStream(synth_h264.make_stream(seed, still=True, W=w, H=hh, pictures=4))
+        assert ps.status == 0
+        orc = _oracle.OracleDecoder(ps)
+        b = Batch(3, ps.width_mbs, ps.height_mbs, ps.num_slots)
+        b.upload(0, ps)
+        b.replicate(0)
+        for k in range(ps.num_pics):
+            slot = ps.pics[k].curSlot
+            b.decode_picture(k)
+            orc.recon(k)
+            orc.deblock(k)
+            for st in range(3):
+                assert np.array_equal(b.read_frame(st, slot), orc.frame(slot)), f"still seed {seed}, picture {k}, instance {st}"
+            checked += ps.pics[k].numRun > 0
+        assert b.watchdog() == (0, 0)
+        b.close(); orc.close(); ps.close()
+    assert checked >= 8, checked
+    # (2) a real stream, four instances, every picture against the reference's md5; one launch more per picture that has both
+    # runs and single copies is how the variant shows it was the one that ran
+    ps = ParsedStream(_oracle.stream_bytes("test_640x360.h264"))
+    g = md5s["test_640x360.h264"]
+    both = sum(1 for k in range(ps.num_pics) if ps.pics[k].numRun and ps.pics[k].numCopy)
+    counts = {}
+    for bulk in ("0", "1"):
+        os.environ["B200_COPY_BULK"] = bulk
+        b = Batch(4, ps.width_mbs, ps.height_mbs, ps.num_slots)
+        b.upload(0, ps)
+        b.replicate(0)
+        for k in range(ps.num_pics):
+            b.decode_picture(k)
+            slot = ps.pics[k].curSlot
+            assert hashlib.md5(b.read_frame(3, slot).tobytes()).hexdigest() == g["post_frame_md5"][k], f"bulk={bulk}, picture {k}"
+        assert b.idct_errors() == 0 and b.watchdog() == (0, 0)
+        counts[bulk] = b.launches()
+        b.close()
+    assert counts["1"] == counts["0"] + both and both > 0, (counts, both)
+    print(f"bulk copy ok: {checked} still pictures, {ps.num_pics} pictures of test_640x360.h264, launches {counts}")
+
+
+@pytest.mark.xfail(strict=False, reason="reconCopyBulkKernel (B200_COPY_BULK=1, off by default) was written after round 1's GPU budget was spent: "
+                                        "checked on the host by emulation (tests/test_cpu_kernel_emu.py), never run on hardware -- the first run "
+                                        "decides; it runs in a process of its own so that a fault cannot take the suite's CUDA context with it")
+def test_experimental_bulk_copy_variant_matches_oracle():
+    """the copy pass with the zero-motion runs moved by cp.async.bulk (copy_bulk_kernel.cuh) instead of through registers"""
+    import subprocess
+    import sys
+    env = dict(os.environ, B200_COPY_BULK="1")
+    r = subprocess.run([sys.executable, "-c", "import conftest, test_gpu_synth as t; t._bulk_copy_body()"], cwd=os.path.dirname(os.path.abspath(__file__)),
+                       env=env, capture_output=True, text=True, timeout=600)
+    print(r.stdout[-2000:], r.stderr[-4000:])
+    assert r.returncode == 0, r.stderr[-2000:]
