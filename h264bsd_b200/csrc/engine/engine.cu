@@ -164,6 +164,9 @@ bool Batch::create(int device, uint32_t nStreams, uint32_t widthMbs, uint32_t he
     reconBlocks_ = std::max(1, occR) * numSms_;
     int occC = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occC, reconCopyKernel, kCopyWarps * 32, 0));
+    if (const char *e = std::getenv("B200_COPY_VARIANT")) copyVariant_ = std::max(0, std::min(2, std::atoi(e)));
+    if (copyVariant_ == 1) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occC, reconCopyKernelOcc4, kCopyWarps * 32, 0));
+    if (copyVariant_ == 2) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occC, reconCopyKernelDeep, kCopyWarps * 32, 0));
     copyBlocks_ = std::max(1, occC) * numSms_;
     // experimental bulk-copy variant of the run section (copy_bulk_kernel.cuh): off unless B200_COPY_BULK=1
     if (const char *e = std::getenv("B200_COPY_BULK")) copyBulk_ = std::atoi(e) != 0;
@@ -433,6 +436,7 @@ bool Batch::launchPicture(const StreamJob *dJobs, const StreamJob *dJobsFilter, 
         if (maxC || maxQ) {
             cudaStream_t st = copyAside ? auxStream_[0] : stream_;
             if (copyAside) CK(cudaStreamWaitEvent(st, forkEv_, 0));
+            auto *copyKernel = copyVariant_ == 1 ? reconCopyKernelOcc4 : copyVariant_ == 2 ? reconCopyKernelDeep : reconCopyKernel;
             if (copyBulk_) {
                 // runs by the bulk-copy engine, single copies by reconCopyKernel (a launch without run tasks)
                 ReconParams rq = rp, rs = rp;
@@ -446,12 +450,12 @@ bool Batch::launchPicture(const StreamJob *dJobs, const StreamJob *dJobsFilter, 
                 }
                 if (maxC) {
                     const uint32_t ctas = (rs.chunksC * (uint32_t)g_.nStreams + kCopyWarps - 1) / kCopyWarps;
-                    reconCopyKernel<<<std::min<uint32_t>(ctas, (uint32_t)copyBlocks_), kCopyWarps * 32, 0, st>>>(rs);
+                    copyKernel<<<std::min<uint32_t>(ctas, (uint32_t)copyBlocks_), kCopyWarps * 32, 0, st>>>(rs);
                     launches_++;
                 }
             } else {
                 const uint32_t ctas = ((rp.chunksC + rp.chunksQ) * (uint32_t)g_.nStreams + kCopyWarps - 1) / kCopyWarps;
-                reconCopyKernel<<<std::min<uint32_t>(ctas, (uint32_t)copyBlocks_), kCopyWarps * 32, 0, st>>>(rp);
+                copyKernel<<<std::min<uint32_t>(ctas, (uint32_t)copyBlocks_), kCopyWarps * 32, 0, st>>>(rp);
                 launches_++;
             }
             if (copyAside) CK(cudaEventRecord(joinEv_[0], st));

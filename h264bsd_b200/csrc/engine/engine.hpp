@@ -92,6 +92,7 @@ private:
     int chunkA_ = 8, copyRuns_ = 4;      // list entries per pass-A warp / runs per copy warp task
     bool copyBulk_ = false;              // B200_COPY_BULK=1: zero-motion runs by reconCopyBulkKernel (experimental)
     int copyBulkBlocks_ = 0, copyBulkRuns_ = 16;
+    int copyVariant_ = 0;                // B200_COPY_VARIANT: 0 reconCopyKernel, 1 ...Occ4, 2 ...Deep (unmeasured A/B variants)
     cudaStream_t uploadStream_ = nullptr;
     std::deque<std::pair<uint32_t, cudaEvent_t>> fences_;   // (pictures below this index, upload-stream event)
     std::vector<cudaEvent_t> fenceFree_;

@@ -3,7 +3,8 @@
 //   emu_geom()     the pool geometry the engine would use (makePoolGeom)
 //   emu_conceal()  one launch of concealKernel over a pool of nStreams streams in host memory
 //   emu_copy()     one launch of reconCopyKernel, the grid the engine would use cut down to `blocks`; copyRuns with bit 31 set:
-//                  the B200_COPY_BULK=1 sequence instead (reconCopyBulkKernel for the runs, reconCopyKernel for the single copies)
+//                  the B200_COPY_BULK=1 sequence instead (reconCopyBulkKernel for the runs, reconCopyKernel for the single copies);
+//                  bit 30: reconCopyKernelDeep (B200_COPY_VARIANT=2)
 //   emu_deblock()  strengthKernel + deblockKernel over a pool of nStreams streams (Batch::launchPicture's deblock half)
 //   emu_engine_*() the whole per-picture launch sequence of Batch::launchPicture over a persistent pool
 #include "warp_emu.hpp"
@@ -73,12 +74,13 @@ extern "C" void emu_copy(uint8_t *pool, uint32_t widthMbs, uint32_t heightMbs, u
     p.pool = pool;
     p.g = makePoolGeom(widthMbs, heightMbs, numSlots, nStreams);
     p.jobs = jobs.data();
-    const bool bulk = (copyRuns & 0x80000000u) != 0;
-    copyRuns &= 0x7FFFFFFFu;
+    const bool bulk = (copyRuns & 0x80000000u) != 0, deep = (copyRuns & 0x40000000u) != 0;   // bit 30: B200_COPY_VARIANT=2
+    copyRuns &= 0x3FFFFFFFu;
     p.copyRuns = copyRuns;                                   // as Batch::launchPicture sets them
     p.chunksC = (nC + 31) / 32;
     p.chunksQ = (nR + copyRuns - 1) / copyRuns;
     if (bulk) launchCopyBulk(p, nR, nC, blocks);
+    else if (deep) warp_emu::runGrid(blocks, kCopyWarps * 32, [&]() { reconCopyKernelDeep(p); });
     else warp_emu::runGrid(blocks, kCopyWarps * 32, [&]() { reconCopyKernel(p); });   // a persistent grid: tasks are strided over it
 }
 

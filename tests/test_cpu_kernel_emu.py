@@ -158,16 +158,18 @@ def mb_pixels(frame, W, H, mb):
 
 
 BULK = 0x80000000   # copyRuns bit that selects the B200_COPY_BULK=1 launch sequence in the emulated engine
+DEEP = 0x40000000   # ... reconCopyKernelDeep (B200_COPY_VARIANT=2; emu_copy only)
 
 
-@pytest.mark.parametrize("variant", ["lanes", "bulk"])
+@pytest.mark.parametrize("variant", ["lanes", "bulk", "deep"])
 @pytest.mark.parametrize("kind", ["still", "damaged"])
 def test_copy_kernel_source_matches_oracle_on_the_host(emu, kind, variant):
     """zero-motion runs, single integer-vector copies (vectors far outside the picture included) and -- in the damaged
     streams -- concealed macroblocks copied from the reference picture: every listed macroblock against the oracle, three
     streams on a two-block grid, runs per task as the engine's default and at its maximum.  variant "bulk": the experimental
     reconCopyBulkKernel (cp.async.bulk through shared memory, B200_COPY_BULK=1) moves the runs -- the emulation checks the
-    16-byte alignment of every bulk copy and defers the stores until the wait that releases their staging buffer"""
+    16-byte alignment of every bulk copy and defers the stores until the wait that releases their staging buffer.  variant
+    "deep": reconCopyKernelDeep (B200_COPY_VARIANT=2), the same body with the loads of four steps before the first store"""
     if kind == "still":
         streams = [synth_h264.make_stream(s, still=True, W=w, H=hh, pictures=3) for s, w, hh in ((3, 11, 4), (4, 40, 3), (6, 7, 6), (9, 37, 2))]
         streams += [synth_h264.make_stream(s) for s in range(0, 24)]
@@ -199,7 +201,7 @@ def test_copy_kernel_source_matches_oracle_on_the_host(emu, kind, variant):
                 for st in range(n_streams):
                     for slot in range(ps.num_slots):
                         to_pool_with_border(orc.frame(slot), W, H, geom, st * ps.num_slots + slot, pool)
-                copy_runs = (4 if (pics & 1) == 0 else 16) | (BULK if variant == "bulk" else 0)
+                copy_runs = (4 if (pics & 1) == 0 else 16) | {"lanes": 0, "bulk": BULK, "deep": DEEP}[variant]
                 emu.emu_copy(pool.ctypes.data, ps.width_mbs, ps.height_mbs, ps.num_slots, h.curSlot, orc._recs + h.mbRecOffset,
                              order + 2 * k * nmb, h.numRun, h.numCopy, n_streams, copy_runs, 2)
                 orc.recon(k)
