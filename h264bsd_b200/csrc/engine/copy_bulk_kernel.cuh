@@ -16,6 +16,7 @@
 #pragma once
 #include "frame_addr.cuh"
 #include "device_ptx.cuh"
+#include "device_common.cuh"
 
 #ifndef B200_DYNAMIC_SMEM
 #define B200_DYNAMIC_SMEM(name) extern __shared__ __align__(128) uint8_t name[]
@@ -59,6 +60,7 @@ __global__ void __launch_bounds__(kBulkWarps * 32) reconCopyBulkKernel(const Rec
     const uint32_t totalTasks = p.chunksQ * (uint32_t)g.nStreams;
     uint32_t q = 0;   // pieces this warp has issued so far: piece q is staged in buffer q % kBulkBufs, phase (q / kBulkBufs) & 1
     uint32_t w = 0;   // pieces this warp has stored so far
+    bool dead = false;
     for (uint32_t t = blockIdx.x * kBulkWarps + warp; t < totalTasks; t += gridDim.x * kBulkWarps) {
         const uint32_t s = t / p.chunksQ, task = t - s * p.chunksQ;
         const StreamJob job = p.jobs[s];
@@ -138,12 +140,29 @@ __global__ void __launch_bounds__(kBulkWarps * 32) reconCopyBulkKernel(const Rec
             uint2 e = make_uint2(0u, 0u);
             if (pc.edge) e = __ldg(reinterpret_cast<const uint2 *>(pc.edge + pc.delta));
             const uint32_t b = w % kBulkBufs, parity = (w / kBulkBufs) & 1u;
-            while (!mbarTryWait(&sm.bar[b], parity)) {}
+            // the piece has landed -- or, should the protocol be wrong on hardware, the watchdog ends this warp's work: the error
+            // is reported (h264bsdB200BatchWatchdog) instead of a hung GPU
+            bool landed = false;
+            unsigned spins = 0;
+            unsigned long long t0 = 0;
+            while (!(landed = mbarTryWait(&sm.bar[b], parity))) {
+                if ((++spins & 255u) == 0) {
+                    const unsigned long long now = globalTimerNs();
+                    if (!t0) t0 = now;
+                    else if (now - t0 > kWatchdogNs) break;
+                }
+            }
+            if (__ballot_sync(0xffffffffu, landed) == 0u) {
+                if (lane == 0) atomicAdd(&gWatchdog[1], 1u);
+                dead = true;
+                break;
+            }
             if (pc.bytes) bulkStore(pc.dst, sm.buf[b] + pc.smemOff, pc.bytes);
             bulkCommit();
             if (pc.edge) *reinterpret_cast<uint2 *>(pc.edge) = e;
             w++;
         }
+        if (dead) break;
     }
     bulkWaitAll();   // the stores have reached memory before the warp leaves
 }

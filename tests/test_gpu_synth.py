@@ -192,6 +192,6 @@ def test_experimental_copy_variants_match_oracle():
     import sys
     env = dict(os.environ, B200_COPY_BULK="1")
     r = subprocess.run([sys.executable, "-c", "import conftest, test_gpu_synth as t; t._bulk_copy_body()"], cwd=os.path.dirname(os.path.abspath(__file__)),
-                       env=env, capture_output=True, text=True, timeout=600)
+                       env=env, capture_output=True, text=True, timeout=150)
     print(r.stdout[-2000:], r.stderr[-4000:])
     assert r.returncode == 0, r.stderr[-2000:]
