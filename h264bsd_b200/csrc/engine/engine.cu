@@ -178,6 +178,16 @@ bool Batch::create(int device, uint32_t nStreams, uint32_t widthMbs, uint32_t he
         if (const char *e = std::getenv("B200_COPY_BULK_RUNS")) copyBulkRuns_ = std::max(1, std::min((int)kBulkRunsPerTask, std::atoi(e)));
     }
     deblockBlocks_ = std::max(1, occD) * numSms_;
+    // B200_GRID_DIV=G: every persistent grid capped at 1/G of the CTAs that fit the machine, for G batches that run side by side
+    // on their own streams (tools/group_bench.py: kernels with complementary limits sharing the SMs); 1 = the measured default
+    if (const char *e = std::getenv("B200_GRID_DIV")) {
+        const int d = std::max(1, std::min(16, std::atoi(e)));
+        strengthBlocks_ = std::max(numSms_, strengthBlocks_ / d);
+        reconBlocks_ = std::max(numSms_, reconBlocks_ / d);
+        copyBlocks_ = std::max(numSms_, copyBlocks_ / d);
+        deblockBlocks_ = std::max(numSms_, deblockBlocks_ / d);
+        if (copyBulkBlocks_) copyBulkBlocks_ = std::max(numSms_, copyBulkBlocks_ / d);
+    }
     // tuning knobs (defaults are the measured best on the 512-stream 1080p batch)
     if (const char *e = std::getenv("B200_CHUNK_B")) chunkB_ = std::max(1, std::min((int)kChunkB, std::atoi(e)));
     if (const char *e = std::getenv("B200_CHUNK_A")) chunkA_ = std::max(1, std::min((int)kChunkA, std::atoi(e)));

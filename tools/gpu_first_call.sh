@@ -20,6 +20,8 @@ timeout 300 python tools/parse_scale.py 1 8 16 > gpurun_out/first_parse_scale.tx
 cat gpurun_out/first_parse_scale.txt
 echo "== 4. copy-pass variants"
 bash tools/ab_copy.sh
+echo "== 4b. stream groups side by side"
+bash tools/ab_groups.sh
 echo "== 5. launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/first_launches.csv \
     python bench.py --steps 1 --warmup 1 --no-e2e --cpu-seconds 1 > gpurun_out/first_launches.log 2>&1
