@@ -1,6 +1,6 @@
 #!/bin/bash
-# Everything round 1 left unmeasured, in ONE gpurun call (about 10 minutes of box time):
-#   gpurun --timeout 1500 -- 'bash tools/gpu_first_call.sh'
+# Everything round 1 left unmeasured, in ONE gpurun call (about 25 minutes of box time):
+#   gpurun --timeout 2400 -- 'bash tools/gpu_first_call.sh'
 # 1. the GPU suite with the xfail-marked tests reported as what they really do (concealKernel, the copy-pass variants)
 # 2. bench.py (end-to-end figure with the faster host parser; device figure must not have moved: default kernels' SASS is unchanged)
 # 3. host parser scaling on the box's host cores
