@@ -1,0 +1,120 @@
+"""TEST INFRASTRUCTURE: what tests/test_cpu_engine_hostemu.py runs, in a process of its own, against the host build of the engine
+(B200_LIB points the bindings at tests/emu/_build/libh264bsd_b200_hostemu.so).  Small synthetic streams: the emulation is slow."""
+import hashlib
+import json
+import os
+import numpy as np
+import _oracle
+import synth_h264
+from h264bsd_b200 import _lib
+from h264bsd_b200.batch import Batch, ParsedStream
+from h264bsd_b200.decoder import H264bsdDecoder, PIC_RDY, ERROR, PARAM_SET_ERROR, MEMALLOC_ERROR
+
+assert "hostemu" in _lib.LIB_PATH, "these bodies are for the host build of the engine only"
+GOLD = json.load(open(os.path.join(_oracle.GOLDEN, "synth_md5.json")))
+DAMAGED = json.load(open(os.path.join(_oracle.GOLDEN, "synth_damaged_md5.json")))
+
+
+def small(g, limit=40):
+    return g["width_mbs"] * g["height_mbs"] <= limit
+
+
+def batched():
+    """Batch: upload, replicate, decode_picture, debug_stage, read_frame, read_picture_all, compare_streams"""
+    seeds = [int(s) for s in sorted(GOLD, key=lambda s: (len(s), s)) if not s.startswith("L") and small(GOLD[s])][:6]
+    pics = 0
+    for i, seed in enumerate(seeds):
+        data = synth_h264.make_stream(seed)
+        assert hashlib.md5(data).hexdigest() == GOLD[str(seed)]["stream_md5"]
+        ps = ParsedStream(data)
+        assert ps.status == 0
+        os.environ["B200_COPY_BULK"] = "1" if i % 3 == 1 else "0"        # read by Batch::create
+        os.environ["B200_COPY_VARIANT"] = "2" if i % 3 == 2 else "0"
+        orc = _oracle.OracleDecoder(ps)
+        b = Batch(2, ps.width_mbs, ps.height_mbs, ps.num_slots)
+        b.upload(0, ps)
+        b.replicate(0)
+        fb = ps.frame_bytes
+        both = np.zeros(2 * fb, np.uint8)
+        for k in range(ps.num_pics):
+            slot = ps.pics[k].curSlot
+            if k % 2:
+                b.debug_stage(k, True, False)
+                orc.recon(k)
+                assert np.array_equal(b.read_frame(1, slot), orc.frame(slot)), f"seed {seed}: reconstruction of picture {k}"
+                b.debug_stage(k, False, True)
+                orc.deblock(k)
+            else:
+                b.decode_picture(k)
+                orc.recon(k)
+                orc.deblock(k)
+            assert np.array_equal(b.read_frame(1, slot), orc.frame(slot)), f"seed {seed}: picture {k}"
+            assert b.compare_streams([slot, slot]) == 0, f"seed {seed}: the two instances differ at picture {k}"
+            b.read_picture_all(k, both.ctypes.data, fb)
+            b.sync()
+            assert np.array_equal(both[:fb], orc.frame(slot)) and np.array_equal(both[fb:], orc.frame(slot)), f"seed {seed}: packed read-back of picture {k}"
+            pics += 1
+        assert b.idct_errors() == 0 and b.watchdog() == (0, 0), f"seed {seed}"
+        b.close(); orc.close(); ps.close()
+    # damaged streams: concealKernel, concealed copies, filter over concealed macroblocks
+    concealed = 0
+    for seed in [int(s) for s in sorted(DAMAGED, key=int) if small(DAMAGED[s]) and DAMAGED[s]["outputs"] > 0 and sum(DAMAGED[s]["err_mbs"]) > 0][:4]:
+        ps = ParsedStream(synth_h264.make_damaged_stream(seed), resilient=True)
+        if ps.status != 0 or ps.num_pics == 0:
+            ps.close()
+            continue
+        orc = _oracle.OracleDecoder(ps)
+        b = Batch(1, ps.width_mbs, ps.height_mbs, ps.num_slots)
+        b.upload(0, ps)
+        for k in range(ps.num_pics):
+            slot = ps.pics[k].curSlot
+            b.decode_picture(k)
+            orc.recon(k)
+            orc.deblock(k)
+            assert np.array_equal(b.read_frame(0, slot), orc.frame(slot)), f"damaged seed {seed}: picture {k}"
+            concealed += ps.pics[k].numErrMbs > 0
+        assert b.watchdog() == (0, 0)
+        b.close(); orc.close(); ps.close()
+    assert pics >= 12 and concealed >= 2, (pics, concealed)
+    print(f"batched ok: {pics} pictures, {concealed} with concealment")
+
+
+def legacy_decode(data, resilient):
+    d = H264bsdDecoder(False)
+    frames = []
+    d.queueInput(data)
+    while d.inputBytesRemaining() > 0:
+        r = d.decode()
+        if r == PIC_RDY:
+            while (f := d.nextOutputPicture()) is not None:
+                frames.append(f)
+        elif r in (ERROR, PARAM_SET_ERROR, MEMALLOC_ERROR) and not resilient:
+            raise RuntimeError(f"h264bsdDecode returned {r}")
+    d.flush()
+    while (f := d.nextOutputPicture()) is not None:
+        frames.append(f)
+    d.release()
+    return frames
+
+
+def legacy():
+    """h264bsdInit / Decode / NextOutputPicture / Shutdown"""
+    def digest(frames):
+        h = hashlib.md5()
+        for f in frames:
+            h.update(np.ascontiguousarray(f).tobytes())
+        return h.hexdigest()
+    n = 0
+    for seed in [int(s) for s in sorted(GOLD, key=lambda s: (len(s), s)) if not s.startswith("L") and small(GOLD[s])][:8]:
+        g = GOLD[str(seed)]
+        frames = legacy_decode(synth_h264.make_stream(seed), False)
+        assert len(frames) == g["outputs"] and digest(frames) == g["post_md5"], f"seed {seed}: output pictures differ from the reference"
+        n += 1
+    nd = 0
+    for seed in [int(s) for s in sorted(DAMAGED, key=int) if small(DAMAGED[s]) and DAMAGED[s]["outputs"] > 0 and sum(DAMAGED[s]["err_mbs"]) > 0][:4]:
+        g = DAMAGED[str(seed)]
+        frames = legacy_decode(synth_h264.make_damaged_stream(seed), True)
+        assert len(frames) == g["outputs"] and digest(frames) == g["post_md5"], f"damaged seed {seed}: output pictures differ from the reference"
+        nd += 1
+    assert n >= 4 and nd >= 2, (n, nd)
+    print(f"legacy ok: {n} valid and {nd} damaged streams")

@@ -61,6 +61,7 @@ inline int laneOf() { return (int)(threadIdx.x & 31); }
 inline void warpSync() { gWarpBarrier[warpOf()].wait(32); }
 
 // `body` as a grid of `blocks` blocks of `threads` threads (a multiple of 32), one block after the other
+inline unsigned gBlockY = 0, gBlockZ = 0;   // blockIdx.y / .z of the blocks runGrid starts (set by runGrid3, stubs_rt/cuda_runtime.h)
 inline void runGrid(unsigned blocks, unsigned threads, const std::function<void()> &body) {
     gridDim.x = blocks;
     blockDim.x = threads;
@@ -70,6 +71,8 @@ inline void runGrid(unsigned blocks, unsigned threads, const std::function<void(
             pool.emplace_back([=, &body]() {
                 threadIdx.x = t;
                 blockIdx.x = b;
+                blockIdx.y = gBlockY;
+                blockIdx.z = gBlockZ;
                 body();
             });
         for (auto &t : pool) t.join();
