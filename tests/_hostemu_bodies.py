@@ -56,6 +56,11 @@ def batched():
             assert np.array_equal(both[:fb], orc.frame(slot)) and np.array_equal(both[fb:], orc.frame(slot)), f"seed {seed}: packed read-back of picture {k}"
             pics += 1
             filter_recs += ps.pics[k].filterRecOffset != 0
+            if k == 1 and i < 2:
+                # colour conversion (convertKernel) against the oracle's h264bsdConvertToRGBA / BGRA / YCbCrA
+                W, H = ps.width_mbs * 16, ps.height_mbs * 16
+                for mode in (0, 1, 2):
+                    assert np.array_equal(b.convert_frame(1, slot, mode), _oracle.oracle_convert(mode, W, H, orc.frame(slot))), f"seed {seed}: conversion mode {mode}"
         assert b.idct_errors() == 0 and b.watchdog() == (0, 0), f"seed {seed}"
         b.close()
         if i in (1, 3):
@@ -127,6 +132,16 @@ def legacy():
         frames = legacy_decode(synth_h264.make_stream(seed), False)
         assert len(frames) == g["outputs"] and digest(frames) == g["post_md5"], f"seed {seed}: output pictures differ from the reference"
         n += 1
+    # h264bsdNextOutputPictureRGBA: the first output picture of a stream, converted on the device
+    data = synth_h264.make_stream(0)
+    first = legacy_decode(data, False)[0]
+    d = H264bsdDecoder(False)
+    d.queueInput(data)
+    while d.decode() != PIC_RDY:
+        pass
+    rgba = d.nextOutputPictureRGBA()
+    d.release()
+    assert np.array_equal(rgba, _oracle.oracle_convert(0, GOLD["0"]["width_mbs"] * 16, GOLD["0"]["height_mbs"] * 16, first)), "NextOutputPictureRGBA"
     nd = 0
     for seed in [int(s) for s in sorted(DAMAGED, key=int) if small(DAMAGED[s]) and DAMAGED[s]["outputs"] > 0 and sum(DAMAGED[s]["err_mbs"]) > 0][:2]:
         g = DAMAGED[str(seed)]
