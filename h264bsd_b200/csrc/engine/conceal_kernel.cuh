@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(kConcealWarps * 32) concealKernel(const ReconP
     const StreamJob job = p.jobs[s];
     if (!job.nE) return;
     uint8_t *cur = framePtr(p.pool, g, s * (uint32_t)g.numSlots + job.curSlot);
-    const uint16_t *list = job.order + 2u * job.nR + job.nC + job.nA + job.nB;
+    const uint16_t *list = job.orderB + job.nB;
 #pragma unroll 1
     for (uint32_t e = 0; e < job.nE; e++) {
         const uint32_t mb = __ldg(list + e);
@@ -36,8 +36,11 @@ __global__ void __launch_bounds__(kConcealWarps * 32) concealKernel(const ReconP
         const int hor = (int)(mask & 1u) + (int)((mask >> 1) & 1u), ver = (int)((mask >> 2) & 1u) + (int)((mask >> 3) & 1u);
 #pragma unroll 1
         for (int pl = 0; pl < 3; pl++) {
-            const int n = pl ? 8 : 16, grp = n >> 2, pitch = pl ? g.pitchC : g.pitchY;
-            uint8_t *p0 = pl ? chromaAt(cur, g, pl - 1, mbx * 8, mby * 8) : lumaAt(cur, g, mbx * 16, mby * 16);
+            const int n = pl ? 8 : 16, grp = n >> 2;
+            // where sample (x, y) of this plane lies (x, y relative to the macroblock; -1 and n reach into the neighbours)
+            auto at = [&](int x, int y) -> uint8_t * {
+                return pl ? chromaAt(cur, g, pl - 1, mbx * 8 + x, mby * 8 + y) : lumaAt(cur, g, mbx * 16 + x, mby * 16 + y);
+            };
             // lanes 0..15: side = lane / 4 (above, below, left, right), group = lane % 4: the sum of that group's edge pels
             // (plain loads: the pels may have been written by this warp a moment ago)
             int sum = 0;
@@ -46,8 +49,7 @@ __global__ void __launch_bounds__(kConcealWarps * 32) concealKernel(const ReconP
                 if (lane < 16 && ((mask >> side) & 1u)) {
                     for (int k = 0; k < grp; k++) {
                         const int t = gi * grp + k;
-                        const uint8_t *q = side == 0 ? p0 - pitch + t : side == 1 ? p0 + (size_t)n * pitch + t
-                                         : side == 2 ? p0 + (size_t)t * pitch - 1 : p0 + (size_t)t * pitch + n;
+                        const uint8_t *q = side == 0 ? at(t, -1) : side == 1 ? at(t, n) : side == 2 ? at(-1, t) : at(n, t);
                         sum += *reinterpret_cast<const volatile uint8_t *>(q);
                     }
                 }
@@ -79,12 +81,12 @@ __global__ void __launch_bounds__(kConcealWarps * 32) concealKernel(const ReconP
                 const int rt = rowTerm(row >> 2);
                 const uint32_t c0 = (uint32_t)clip255(colTerm(half * 2) + rt) * 0x01010101u;
                 const uint32_t c1 = (uint32_t)clip255(colTerm(half * 2 + 1) + rt) * 0x01010101u;
-                *reinterpret_cast<uint2 *>(p0 + (size_t)row * pitch + half * 8) = make_uint2(c0, c1);
+                *reinterpret_cast<uint2 *>(at(half * 8, row)) = make_uint2(c0, c1);
             } else {
                 // 8 rows x 8 pels: lane = 4 * row + cell, 2 pels = one grid cell
                 const int row = lane >> 2, cell = lane & 3;
                 const uint32_t c0 = (uint32_t)clip255(colTerm(cell) + rowTerm(row >> 1));
-                *reinterpret_cast<uint16_t *>(p0 + (size_t)row * pitch + cell * 2) = (uint16_t)(c0 * 0x0101u);
+                *reinterpret_cast<uint16_t *>(at(cell * 2, row)) = (uint16_t)(c0 * 0x0101u);
             }
         }
         __syncwarp();   // orders this entry's stores before the next entry's loads (same warp)

@@ -318,15 +318,19 @@ __global__ void __launch_bounds__(kDeblockWarps * 32, 4) deblockKernel(const Deb
             }
             __syncwarp();
             // stage 20 luma rows and 2 x 10 chroma rows (incl. 4 / 2 rows of the upper and 4 columns of the left neighbour)
-            uint8_t *gy = nullptr, *gc = nullptr;
+            // (strip layout: the 20 luma rows are 320 contiguous bytes of the macroblock's strip, the 4 columns of the left
+            // neighbour the last 4 bytes of the same rows one strip earlier; chroma rows hold 8 Cb | 8 Cr)
+            uint8_t *gy = nullptr, *gc = nullptr, *gyl = nullptr, *gcl = nullptr;
             if (lane < 20) {
                 const int cpl = lane >= 10, cr = lane - cpl * 10;
-                gy = lumaAt(frame, g, mbx * 16, mby * 16 - 4 + lane);
-                gc = chromaAt(frame, g, cpl, mbx * 8, mby * 8 - 2 + cr);
+                gy = mbLuma(frame, g, mbx, mby) + (lane - 4) * 16;
+                gyl = gy - (size_t)g.rowsY * 16 + 12;
+                gc = mbChroma(frame, g, mbx, mby) + (cr - 2) * 16 + cpl * 8;
+                gcl = gc - (size_t)g.rowsC * 16 + 4;
                 const uint4 own = __ldcg(reinterpret_cast<const uint4 *>(gy));
-                const uint32_t lef = __ldcg(reinterpret_cast<const uint32_t *>(gy - 4));
+                const uint32_t lef = __ldcg(reinterpret_cast<const uint32_t *>(gyl));
                 const uint2 cown = __ldcg(reinterpret_cast<const uint2 *>(gc));
-                const uint32_t clef = __ldcg(reinterpret_cast<const uint32_t *>(gc - 4));
+                const uint32_t clef = __ldcg(reinterpret_cast<const uint32_t *>(gcl));
                 *reinterpret_cast<uint4 *>(&sm.y[lane][16]) = own;
                 *reinterpret_cast<uint32_t *>(&sm.y[lane][12]) = lef;
                 *reinterpret_cast<uint2 *>(&sm.c[cpl][cr][8]) = cown;
@@ -389,9 +393,9 @@ __global__ void __launch_bounds__(kDeblockWarps * 32, 4) deblockKernel(const Deb
             if (lane < 20) {
                 const int cpl = lane >= 10, cr = lane - cpl * 10;
                 if (lane >= 4 || mby > 0) *reinterpret_cast<uint4 *>(gy) = *reinterpret_cast<const uint4 *>(&sm.y[lane][16]);
-                if (lane >= 4 && mbx > 0) *reinterpret_cast<uint32_t *>(gy - 4) = *reinterpret_cast<const uint32_t *>(&sm.y[lane][12]);
+                if (lane >= 4 && mbx > 0) *reinterpret_cast<uint32_t *>(gyl) = *reinterpret_cast<const uint32_t *>(&sm.y[lane][12]);
                 if (cr >= 2 || mby > 0) *reinterpret_cast<uint2 *>(gc) = *reinterpret_cast<const uint2 *>(&sm.c[cpl][cr][8]);
-                if (cr >= 2 && mbx > 0) *reinterpret_cast<uint32_t *>(gc - 4) = *reinterpret_cast<const uint32_t *>(&sm.c[cpl][cr][4]);
+                if (cr >= 2 && mbx > 0) *reinterpret_cast<uint32_t *>(gcl) = *reinterpret_cast<const uint32_t *>(&sm.c[cpl][cr][4]);
             }
             // publish: the warp barrier orders every lane's stores before lane 0's release, and a release at gpu scope is
             // cumulative (the same pattern as a CTA semaphore: barrier, then st.release by one thread); no separate fence --
@@ -410,64 +414,76 @@ struct BorderParams {
     PoolGeom g;
     const StreamJob *jobs;
 };
-// Warp tasks per stream: "side" tasks fill the left / right border of 32 picture rows of one plane (each row's edge pel);
-// "cap" tasks fill a 128-byte column chunk of every border row above (below) a plane with the first (last) row, already
-// extended by its own side pels -- the source word is read once and stored `pad` times, whole 128-byte lines.
+// Warp tasks per stream (borderTasksPerStream): a "cap" task fills the 32 (16) rows above and below one picture strip with
+// the strip's first / last picture row (one 16-byte row per lane and store); a "side" task fills 128 rows of one of the four
+// border strips of a plane with each row's edge pel (rows above / below the picture take the corner pel).
+__host__ __device__ inline int borderTasksPerStream(const PoolGeom &g) {
+    return g.widthMbs + 4 * ((g.rowsY + 127) / 128) + 4 * ((g.rowsC + 127) / 128);
+}
 __global__ void __launch_bounds__(256) borderKernel(const BorderParams p) {
     const PoolGeom &g = p.g;
     const int lane = threadIdx.x & 31;
-    const int sideY = (g.H + 31) / 32, sideC = (g.H / 2 + 31) / 32;
-    const int capY = (g.pitchY + 127) / 128, capC = (g.pitchC + 127) / 128;
-    const int perStream = sideY + 2 * sideC + 2 * capY + 4 * capC;
+    const int sideY = (g.rowsY + 127) / 128, sideC = (g.rowsC + 127) / 128;
+    const int perStream = g.widthMbs + 4 * sideY + 4 * sideC;
     const long long task = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (task >= (long long)perStream * g.nStreams) return;
     const int s = (int)(task / perStream);
     int t = (int)(task - (long long)s * perStream);
     uint8_t *frame = framePtr(p.pool, g, (uint32_t)s * g.numSlots + p.jobs[s].curSlot);
-    if (t < sideY + 2 * sideC) {
-        const bool luma = t < sideY;
-        int pl = 0;
-        if (!luma) { t -= sideY; pl = t / sideC; t -= pl * sideC; }
-        uint8_t *plane = luma ? frame : frame + (pl ? g.offCr : g.offCb);
-        const int w = luma ? g.W : g.W / 2, h = luma ? g.H : g.H / 2, pad = luma ? kPadY : kPadC, pitch = luma ? g.pitchY : g.pitchC;
-        const int r0 = t * 32, rows = min(32, h - r0), shift = luma ? 3 : 2, wpp = pad / 4;
-        for (int i = lane; i < rows * wpp; i += 32) {
-            uint8_t *rowp = plane + (size_t)(r0 + (i >> shift) + pad) * pitch;   // start of the row incl. its left border
-            const uint32_t lv = rowp[pad] * 0x01010101u, rv = rowp[pad + w - 1] * 0x01010101u;
-            reinterpret_cast<uint32_t *>(rowp)[i & (wpp - 1)] = lv;
-            reinterpret_cast<uint32_t *>(rowp + pad + w)[i & (wpp - 1)] = rv;
+    if (t < g.widthMbs) {
+        // cap: picture strip t
+        uint8_t *ys = frame + (size_t)(t + kPadMbs) * g.rowsY * 16, *cs = frame + g.offC + (size_t)(t + kPadMbs) * g.rowsC * 16;
+        const uint4 top = *reinterpret_cast<const uint4 *>(ys + (size_t)kPadY * 16);
+        const uint4 bot = *reinterpret_cast<const uint4 *>(ys + (size_t)(kPadY + g.H - 1) * 16);
+        *reinterpret_cast<uint4 *>(ys + (size_t)lane * 16) = top;
+        *reinterpret_cast<uint4 *>(ys + (size_t)(kPadY + g.H + lane) * 16) = bot;
+        const bool low = lane >= 16;
+        const uint4 c = *reinterpret_cast<const uint4 *>(cs + (size_t)(low ? kPadC + g.H / 2 - 1 : kPadC) * 16);
+        *reinterpret_cast<uint4 *>(cs + (size_t)(low ? kPadC + g.H / 2 + lane - 16 : lane) * 16) = c;
+        return;
+    }
+    t -= g.widthMbs;
+    const bool luma = t < 4 * sideY;
+    if (!luma) t -= 4 * sideY;
+    const int blocks = luma ? sideY : sideC, which = t / blocks, blk = t - which * blocks;   // which: 0, 1 left strips; 2, 3 right strips
+    const int strip = which < 2 ? which : g.widthMbs + which;
+    const int rows = luma ? g.rowsY : g.rowsC, pad = luma ? kPadY : kPadC, h = luma ? g.H : g.H / 2;
+    const int edgeX = which < 2 ? 0 : (luma ? g.W : g.W / 2) - 1;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int r = blk * 128 + k * 32 + lane;
+        if (r >= rows) break;
+        const int y = clip3(0, h - 1, r - pad);
+        uint4 v;
+        if (luma) {
+            const uint32_t w = *lumaAt(frame, g, edgeX, y) * 0x01010101u;
+            v = make_uint4(w, w, w, w);
+            *reinterpret_cast<uint4 *>(frame + ((size_t)strip * g.rowsY + r) * 16) = v;
+        } else {
+            const uint32_t cb = *chromaAt(frame, g, 0, edgeX, y) * 0x01010101u, cr = *chromaAt(frame, g, 1, edgeX, y) * 0x01010101u;
+            v = make_uint4(cb, cb, cr, cr);
+            *reinterpret_cast<uint4 *>(frame + g.offC + ((size_t)strip * g.rowsC + r) * 16) = v;
         }
-    } else {
-        t -= sideY + 2 * sideC;
-        const bool luma = t < 2 * capY;
-        int pl = 0;
-        if (!luma) { t -= 2 * capY; pl = t / (2 * capC); t -= pl * 2 * capC; }
-        const int caps = luma ? capY : capC;
-        const bool bottom = t >= caps;
-        const int word = (t - (bottom ? caps : 0)) * 32 + lane;
-        uint8_t *plane = luma ? frame : frame + (pl ? g.offCr : g.offCb);
-        const int w = luma ? g.W : g.W / 2, h = luma ? g.H : g.H / 2, pad = luma ? kPadY : kPadC, pitch = luma ? g.pitchY : g.pitchC;
-        if (word * 4 >= pitch) return;
-        const uint8_t *src = plane + (size_t)((bottom ? h - 1 : 0) + pad) * pitch + pad;   // first pel of the source row
-        const int x = word * 4 - pad;
-        const uint32_t v = x < 0 ? src[0] * 0x01010101u : x >= w ? src[w - 1] * 0x01010101u : *reinterpret_cast<const uint32_t *>(src + x);
-        uint32_t *dst = reinterpret_cast<uint32_t *>(plane + (size_t)(bottom ? pad + h : 0) * pitch) + word;
-        for (int r = 0; r < pad; r++) dst[(size_t)r * (pitch / 4)] = v;
     }
 }
 
 // ---- YUV -> 32-bit pixels (h264bsdConvertToRGBA/BGRA/YCbCrA, decoder.c:1163-1370) --------------------------
 // mode 0: A<<24|B<<16|G<<8|R   1: A<<24|R<<16|G<<8|B   2: A<<24|Cr<<16|Cb<<8|Y ; nearest chroma, coded size
-template <int PELS>   // pels per thread: 4, or 8 when the width allows it (8-byte luma load, two 16-byte stores)
+__device__ __forceinline__ uint32_t convertPel(int l, int cb, int cr, int mode) {
+    if (mode == 2) return 0xFF000000u | ((uint32_t)cr << 16) | ((uint32_t)cb << 8) | (uint32_t)l;
+    const int c = l - 16, d = cb - 128, e = cr - 128;
+    const uint32_t r = (uint32_t)clip255((298 * c + 409 * e + 128) >> 8);
+    const uint32_t gg = (uint32_t)clip255((298 * c - 100 * d - 208 * e + 128) >> 8);
+    const uint32_t bb = (uint32_t)clip255((298 * c + 516 * d + 128) >> 8);
+    return mode == 0 ? (0xFF000000u | (bb << 16) | (gg << 8) | r) : (0xFF000000u | (r << 16) | (gg << 8) | bb);
+}
+// planar I420 input (caller-owned host pictures, h264bsdConvertTo*): 4 pels per thread, or 8 when the width allows it
+template <int PELS>
 __global__ void __launch_bounds__(256) convertKernelT(const uint8_t *yPlane, int pitchY, const uint8_t *cbPlane, const uint8_t *crPlane,
-                                                      int pitchC, int W, int mode, uint32_t *out,
-                                                      unsigned long long inStride, unsigned long long outStride) {
+                                                      int pitchC, int W, int mode, uint32_t *out) {
     const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * PELS;
     const int y = blockIdx.y;
     if (x0 >= W) return;
-    // blockIdx.z = picture of a batch: the same planes `inStride` bytes further, output `outStride` pixels further
-    yPlane += blockIdx.z * inStride; cbPlane += blockIdx.z * inStride; crPlane += blockIdx.z * inStride;
-    out += blockIdx.z * outStride;
     uint32_t yw[PELS / 4], cbv, crv;
     if (PELS == 8) {
         const uint2 t = *reinterpret_cast<const uint2 *>(yPlane + (size_t)y * pitchY + x0);
@@ -481,43 +497,142 @@ __global__ void __launch_bounds__(256) convertKernelT(const uint8_t *yPlane, int
     }
     uint32_t o[PELS];
 #pragma unroll
-    for (int i = 0; i < PELS; i++) {
-        const int l = (yw[i >> 2] >> (8 * (i & 3))) & 0xFF, cb = (cbv >> (8 * (i >> 1))) & 0xFF, cr = (crv >> (8 * (i >> 1))) & 0xFF;
-        if (mode == 2) {
-            o[i] = 0xFF000000u | ((uint32_t)cr << 16) | ((uint32_t)cb << 8) | (uint32_t)l;
-        } else {
-            const int c = l - 16, d = cb - 128, e = cr - 128;
-            const uint32_t r = (uint32_t)clip255((298 * c + 409 * e + 128) >> 8);
-            const uint32_t gg = (uint32_t)clip255((298 * c - 100 * d - 208 * e + 128) >> 8);
-            const uint32_t bb = (uint32_t)clip255((298 * c + 516 * d + 128) >> 8);
-            o[i] = mode == 0 ? (0xFF000000u | (bb << 16) | (gg << 8) | r) : (0xFF000000u | (r << 16) | (gg << 8) | bb);
-        }
-    }
+    for (int i = 0; i < PELS; i++)
+        o[i] = convertPel((yw[i >> 2] >> (8 * (i & 3))) & 0xFF, (cbv >> (8 * (i >> 1))) & 0xFF, (crv >> (8 * (i >> 1))) & 0xFF, mode);
 #pragma unroll
     for (int i = 0; i < PELS; i += 4)
         *reinterpret_cast<uint4 *>(out + (size_t)y * W + x0 + i) = make_uint4(o[i], o[i + 1], o[i + 2], o[i + 3]);
 }
+// a frame of the pool (strip layout) -> W x H pixels, 8 pels per thread (half a strip row: 8-byte luma load, 4 + 4 chroma
+// bytes, two 16-byte stores).  blockIdx.z = picture of a batch: the frame `inStride` bytes further, output `outStride` pixels
+// further.  With a cropping rectangle (cropW x cropH at (cropX, cropY), all even) only that part is written, densely.
+__global__ void __launch_bounds__(256) convertFrameKernel(const uint8_t *frame0, PoolGeom g, int mode, uint32_t *out,
+                                                          unsigned long long inStride, unsigned long long outStride,
+                                                          int cropX, int cropY, int cropW, int cropH) {
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    const int y = blockIdx.y;
+    if (x0 >= g.W) return;
+    uint8_t *frame = const_cast<uint8_t *>(frame0) + blockIdx.z * inStride;
+    out += blockIdx.z * outStride;
+    const uint2 yv = *reinterpret_cast<const uint2 *>(lumaAt(frame, g, x0, y));
+    const uint32_t cbv = *reinterpret_cast<const uint32_t *>(chromaAt(frame, g, 0, x0 >> 1, y >> 1));
+    const uint32_t crv = *reinterpret_cast<const uint32_t *>(chromaAt(frame, g, 1, x0 >> 1, y >> 1));
+    uint32_t o[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        o[i] = convertPel(((i < 4 ? yv.x : yv.y) >> (8 * (i & 3))) & 0xFF, (cbv >> (8 * (i >> 1))) & 0xFF, (crv >> (8 * (i >> 1))) & 0xFF, mode);
+    if (cropW == g.W && cropH == g.H) {
+        uint4 *dst = reinterpret_cast<uint4 *>(out + (size_t)y * g.W + x0);
+        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    } else if (y >= cropY && y < cropY + cropH) {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            if (x0 + i >= cropX && x0 + i < cropX + cropW) out[(size_t)(y - cropY) * cropW + (x0 + i - cropX)] = o[i];
+    }
+}
+
+// ---- strip layout <-> planar I420 / NV12 of the coded size (or of a cropping rectangle) ----------------------------------
+// What h264bsdNextOutputPicture hands out (decoder.c:599-623) is contiguous planar I420: one thread moves two luma rows of
+// a strip (a whole 32-byte sector in, two 16-byte row pieces out) or one chroma row (8 Cb + 8 Cr in, 8 bytes to each plane;
+// nv12: 16 interleaved bytes to the one chroma plane).  blockIdx.y = stream: its current frame (slot from the job) -> staging +
+// stream * outStride.  crop: cropX, cropY, cropW, cropH in luma pels, cropX a multiple of 16 and the rest even; the output
+// planes then have cropW x cropH (cropW/2 x cropH/2) pels.
+struct PackParams {
+    const uint8_t *pool;
+    PoolGeom g;
+    const StreamJob *jobs;     // curSlot per stream (nullptr: slot `slot` of every stream)
+    uint32_t slot;
+    uint8_t *out;
+    unsigned long long outStride;
+    int cropX, cropY, cropW, cropH;
+    int nv12;
+};
+__global__ void __launch_bounds__(256) packKernel(const PackParams p) {
+    const PoolGeom &g = p.g;
+    const uint32_t s = blockIdx.y;
+    const uint32_t slot = p.jobs ? p.jobs[s].curSlot : p.slot;
+    uint8_t *f = const_cast<uint8_t *>(p.pool) + (unsigned long long)(s * (uint32_t)g.numSlots + slot) * g.frameStride;
+    uint8_t *out = p.out + (size_t)s * p.outStride;
+    const int unitsY = g.widthMbs * (g.H / 2), unitsC = g.widthMbs * (g.H / 2);
+    const size_t planeY = (size_t)p.cropW * p.cropH, planeC = planeY / 4;
+    const int cx0 = p.cropX, cx1 = p.cropX + p.cropW;   // luma columns kept
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < unitsY + unitsC; i += gridDim.x * blockDim.x) {
+        if (i < unitsY) {
+            const int yp = i / g.widthMbs, mbx = i - yp * g.widthMbs, y = 2 * yp, x = mbx * 16;
+            if (y < p.cropY || y >= p.cropY + p.cropH || x + 16 <= cx0 || x >= cx1) continue;
+            const uint4 *src = reinterpret_cast<const uint4 *>(lumaAt(f, g, x, y));
+            const uint4 a = src[0], b = src[1];
+            uint8_t *d = out + (size_t)(y - p.cropY) * p.cropW + (x - cx0);
+            if (x >= cx0 && x + 16 <= cx1 && (p.cropW & 15) == 0) {
+                *reinterpret_cast<uint4 *>(d) = a;
+                *reinterpret_cast<uint4 *>(d + p.cropW) = b;
+            } else {
+                const uint8_t *ab = reinterpret_cast<const uint8_t *>(&a), *bb = reinterpret_cast<const uint8_t *>(&b);
+                for (int k = 0; k < 16; k++)
+                    if (x + k >= cx0 && x + k < cx1) { d[k] = ab[k]; d[p.cropW + k] = bb[k]; }
+            }
+        } else {
+            const int j = i - unitsY, yc = j / g.widthMbs, mbx = j - yc * g.widthMbs, x = mbx * 8;
+            if (2 * yc < p.cropY || 2 * yc >= p.cropY + p.cropH || 2 * x + 16 <= cx0 || 2 * x >= cx1) continue;
+            const uint4 v = *reinterpret_cast<const uint4 *>(chromaAt(f, g, 0, x, yc));   // 8 Cb | 8 Cr
+            const int cw = p.cropW / 2, ccx0 = cx0 / 2, row = yc - p.cropY / 2;
+            const uint8_t *vb = reinterpret_cast<const uint8_t *>(&v);
+            if (p.nv12) {
+                uint8_t *d = out + planeY + (size_t)row * p.cropW + 2 * (x - ccx0);
+                for (int k = 0; k < 8; k++)
+                    if (x + k >= ccx0 && x + k < ccx0 + cw) { d[2 * k] = vb[k]; d[2 * k + 1] = vb[8 + k]; }
+            } else if (x >= ccx0 && x + 8 <= ccx0 + cw && (cw & 7) == 0) {
+                *reinterpret_cast<uint2 *>(out + planeY + (size_t)row * cw + (x - ccx0)) = make_uint2(v.x, v.y);
+                *reinterpret_cast<uint2 *>(out + planeY + planeC + (size_t)row * cw + (x - ccx0)) = make_uint2(v.z, v.w);
+            } else {
+                for (int k = 0; k < 8; k++)
+                    if (x + k >= ccx0 && x + k < ccx0 + cw) {
+                        out[planeY + (size_t)row * cw + (x + k - ccx0)] = vb[k];
+                        out[planeY + planeC + (size_t)row * cw + (x + k - ccx0)] = vb[8 + k];
+                    }
+            }
+        }
+    }
+}
+// the reverse, coded size only (test hook: put an I420 picture into a frame slot)
+__global__ void __launch_bounds__(256) unpackKernel(uint8_t *frame, PoolGeom g, const uint8_t *in) {
+    const int unitsY = g.widthMbs * g.H, unitsC = g.widthMbs * (g.H / 2);
+    const size_t planeY = (size_t)g.W * g.H, planeC = planeY / 4;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < unitsY + unitsC; i += gridDim.x * blockDim.x) {
+        if (i < unitsY) {
+            const int y = i / g.widthMbs, mbx = i - y * g.widthMbs;
+            uint4 v;
+            memcpy(&v, in + (size_t)y * g.W + mbx * 16, 16);
+            *reinterpret_cast<uint4 *>(lumaAt(frame, g, mbx * 16, y)) = v;
+        } else {
+            const int j = i - unitsY, yc = j / g.widthMbs, mbx = j - yc * g.widthMbs;
+            uint2 cb, cr;
+            memcpy(&cb, in + planeY + (size_t)yc * (g.W / 2) + mbx * 8, 8);
+            memcpy(&cr, in + planeY + planeC + (size_t)yc * (g.W / 2) + mbx * 8, 8);
+            *reinterpret_cast<uint4 *>(chromaAt(frame, g, 0, mbx * 8, yc)) = make_uint4(cb.x, cb.y, cr.x, cr.y);
+        }
+    }
+}
+
 // ---- compare frame `slot` of every stream with stream 0's (picture area only) -------------------------------
 __global__ void __launch_bounds__(256) compareKernel(const uint8_t *pool, PoolGeom g, const uint32_t *slots, uint32_t *mismatch) {
     const int s = blockIdx.y + 1;
     const uint8_t *a = pool + (unsigned long long)(0 * g.numSlots + slots[0]) * g.frameStride;
     const uint8_t *b = pool + (unsigned long long)((unsigned)s * g.numSlots + slots[s]) * g.frameStride;
-    const int wordsY = g.W / 4, wordsC = g.W / 8;
-    const long long total = (long long)wordsY * g.H + 2ll * wordsC * (g.H / 2);
+    const int unitsY = g.widthMbs * g.H, unitsC = g.widthMbs * (g.H / 2);   // 16-byte strip rows inside the picture
     uint32_t bad = 0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < unitsY + unitsC; i += gridDim.x * blockDim.x) {
         size_t off;
-        if (i < (long long)wordsY * g.H) {
-            const int y = (int)(i / wordsY), x = (int)(i - (long long)y * wordsY);
-            off = (size_t)(y + kPadY) * g.pitchY + kPadY + x * 4;
+        if (i < unitsY) {
+            const int strip = i / g.H, row = i - strip * g.H;
+            off = ((size_t)(strip + kPadMbs) * g.rowsY + row + kPadY) * 16;
         } else {
-            long long j = i - (long long)wordsY * g.H;
-            const int pl = j >= (long long)wordsC * (g.H / 2);
-            if (pl) j -= (long long)wordsC * (g.H / 2);
-            const int y = (int)(j / wordsC), x = (int)(j - (long long)y * wordsC);
-            off = (pl ? g.offCr : g.offCb) + (size_t)(y + kPadC) * g.pitchC + kPadC + x * 4;
+            const int j = i - unitsY, strip = j / (g.H / 2), row = j - strip * (g.H / 2);
+            off = g.offC + ((size_t)(strip + kPadMbs) * g.rowsC + row + kPadC) * 16;
         }
-        bad += *reinterpret_cast<const uint32_t *>(a + off) != *reinterpret_cast<const uint32_t *>(b + off);
+        const uint4 x = *reinterpret_cast<const uint4 *>(a + off), y = *reinterpret_cast<const uint4 *>(b + off);
+        bad += (x.x != y.x) | (x.y != y.y) | (x.z != y.z) | (x.w != y.w);
     }
     if (bad) atomicAdd(mismatch + s, bad);
 }

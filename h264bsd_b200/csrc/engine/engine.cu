@@ -12,8 +12,6 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include "recon_kernel.cuh"
-#include "copy_kernel.cuh"
-#include "copy_bulk_kernel.cuh"
 #include "conceal_kernel.cuh"
 #include "deblock_kernel.cuh"
 #include "engine.hpp"
@@ -52,33 +50,41 @@ Batch::~Batch() { destroy(); }
 void Batch::destroy() {
     if (!created_) return;
     cudaSetDevice(device_);
-    cudaStreamSynchronize(stream_);
+    if (stream_) cudaStreamSynchronize(stream_);
+    if (copyStream_) cudaStreamSynchronize(copyStream_);
+    if (uploadStream_) cudaStreamSynchronize(uploadStream_);
+    if (auxStream_) cudaStreamSynchronize(auxStream_);
     for (auto &t : tapes_) {
         if (t.owned) { cudaFree(t.recs); cudaFree(t.coefs); cudaFree(t.order); }
     }
-    tapes_.clear();
     cudaFree(dBsWords_); cudaFree(dWork_); cudaFree(dPack_[0]); cudaFree(dPack_[1]);
-    if (copyStream_) { cudaStreamSynchronize(copyStream_); cudaStreamDestroy(copyStream_); copyStream_ = nullptr; }
-    cudaFree(dConvertAll_);
+    cudaFree(dConvertAll_); cudaFree(dFrameStage_);
     cudaFree(pool_); cudaFree(dOrder_); cudaFree(dDoneRecon_); cudaFree(dDoneDeblock_); cudaFree(dCounters_);
     cudaFree(dJobs_); cudaFree(dStage_[0]); cudaFree(dStage_[1]); cudaFree(dConvert_); cudaFree(dSlots_);
     if (hStage_[0]) cudaFreeHost(hStage_[0]);
     if (hStage_[1]) cudaFreeHost(hStage_[1]);
     for (cudaEvent_t e : evPool_) cudaEventDestroy(e);
-    evPool_.clear(); evStage_.clear();
-    if (syncEv_) cudaEventDestroy(syncEv_);
-    if (forkEv_) cudaEventDestroy(forkEv_);
     for (auto &f : fences_) cudaEventDestroy(f.second);
     for (cudaEvent_t e : fenceFree_) cudaEventDestroy(e);
-    if (uploadStream_) cudaStreamDestroy(uploadStream_);
-    for (int i = 0; i < 2; i++) {
-        if (joinEv_[i]) cudaEventDestroy(joinEv_[i]);
-        if (auxStream_[i]) cudaStreamDestroy(auxStream_[i]);
-    }
-    if (evA_) cudaEventDestroy(evA_);
-    if (evB_) cudaEventDestroy(evB_);
-    if (stream_) cudaStreamDestroy(stream_);
+    for (cudaEvent_t e : {syncEv_, forkEv_, joinEv_, evA_, evB_, stageEv_[0], stageEv_[1], packEv_[0], packEv_[1], packedEv_[0], packedEv_[1]})
+        if (e) cudaEventDestroy(e);
+    for (cudaStream_t st : {copyStream_, uploadStream_, auxStream_, stream_})
+        if (st) cudaStreamDestroy(st);
+    // every pointer, capacity, event and stream back to its default: a second create() on this object (a stream that activates
+    // another sequence parameter set, api.cpp LegacyDecoder::configure) must not see anything of the first
     created_ = false;
+    *this = Batch();
+}
+
+static bool encodeStripMap(EncodeTiledFn enc, CUtensorMap *m, uint8_t *base, const PoolGeom &g, int rows, unsigned long long nFrames, int nx, int nr) {
+    // dims (x in strip, strip, row, frame); the strip stride is larger than the row stride on purpose (pool_geom.hpp)
+    cuuint64_t dims[4] = {16, (cuuint64_t)g.strips, (cuuint64_t)rows, nFrames};
+    cuuint64_t strides[3] = {(cuuint64_t)rows * 16, 16, g.frameStride};
+    cuuint32_t box[4] = {16, (cuuint32_t)nx, (cuuint32_t)nr, 1}, es[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { std::fprintf(stderr, "h264bsd_b200: tensor map (%d strips x %d rows) failed (%d)\n", nx, nr, (int)r); return false; }
+    return true;
 }
 
 bool Batch::create(int device, uint32_t nStreams, uint32_t widthMbs, uint32_t heightMbs, uint32_t numSlots) {
@@ -88,6 +94,9 @@ bool Batch::create(int device, uint32_t nStreams, uint32_t widthMbs, uint32_t he
         return false;
     }
     if (device < 0 || device >= n || !nStreams || !widthMbs || !heightMbs || !numSlots || numSlots > 32) return false;
+    // macroblock addresses are 16 bits on the device (order lists); checked before anything is allocated
+    if ((unsigned long long)widthMbs * heightMbs > 65535ull || widthMbs > 16383 || heightMbs > 16383) return false;
+    if (created_) destroy();
     device_ = device;
     CK(cudaSetDevice(device));
     cudaDeviceProp prop;
@@ -116,7 +125,6 @@ bool Batch::create(int device, uint32_t nStreams, uint32_t widthMbs, uint32_t he
         std::sort(keyed.begin(), keyed.end());
         for (int i = 0; i < g.nMbs; i++) order[i] = (uint16_t)keyed[i].second;
     }
-    if (g.nMbs > 65535) return false;
     CK(cudaMalloc(&dOrder_, sizeof(uint16_t) * g.nMbs));
     CK(cudaMemcpyAsync(dOrder_, order.data(), sizeof(uint16_t) * g.nMbs, cudaMemcpyHostToDevice, stream_));
     const size_t flagBytes = sizeof(uint32_t) * (size_t)nStreams * g.nMbs;
@@ -126,79 +134,46 @@ bool Batch::create(int device, uint32_t nStreams, uint32_t widthMbs, uint32_t he
     CK(cudaMemsetAsync(dDoneDeblock_, 0, flagBytes, stream_));
     CK(cudaMalloc(&dBsWords_, flagBytes * 4));
     CK(cudaMalloc(&dWork_, (size_t)nStreams * g.nMbs));
+    // counters: [0] pass-B tickets, [1] filter tickets, [2] pass-A tickets (zeroed per picture); [3] IDCT range errors,
+    // [4..5] macroblocks with filter work, [6..7] macroblocks done by pass A (running totals)
     CK(cudaMalloc(&dCounters_, sizeof(uint32_t) * 8));
     CK(cudaMemsetAsync(dCounters_, 0, sizeof(uint32_t) * 8, stream_));
     CK(cudaMalloc(&dSlots_, sizeof(uint32_t) * nStreams));
     serial_ = 0;
 
-    // TMA descriptors over the whole pool: luma {x, y, frame}, chroma {x, y, plane, frame}
+    // TMA descriptors over the whole pool, one per box shape of pass A
     EncodeTiledFn enc = getEncodeTiled();
     if (!enc) {
         std::fprintf(stderr, "h264bsd_b200: cuTensorMapEncodeTiled unavailable\n");
         return false;
     }
+    static_assert(sizeof(PassAMaps) == sizeof(CUtensorMap) * 10, "Batch::maps_ holds a PassAMaps");
     {
-        cuuint64_t dims[3] = {(cuuint64_t)g.pitchY, (cuuint64_t)g.rowsY, nFrames};
-        cuuint64_t strides[2] = {(cuuint64_t)g.pitchY, g.frameStride};
-        cuuint32_t box[3] = {kLumaBoxW, kLumaBoxH, 1}, es[3] = {1, 1, 1};
-        CUresult r = enc(&lumaMap_, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, pool_, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) { std::fprintf(stderr, "h264bsd_b200: luma tensor map failed (%d)\n", (int)r); return false; }
+        PassAMaps *m = reinterpret_cast<PassAMaps *>(maps_);
+        for (int nx = 1; nx <= 3; nx++)
+            for (int v = 0; v < 2; v++)
+                if (!encodeStripMap(enc, &m->luma[nx - 1][v], pool_, g, g.rowsY, nFrames, nx, v ? 21 : 16)) return false;
+        for (int nx = 1; nx <= 2; nx++)
+            for (int v = 0; v < 2; v++)
+                if (!encodeStripMap(enc, &m->chroma[nx - 1][v], pool_ + g.offC, g, g.rowsC, nFrames, nx, v ? 9 : 8)) return false;
     }
-    {
-        cuuint64_t dims[4] = {(cuuint64_t)g.pitchC, (cuuint64_t)g.rowsC, 2, nFrames};
-        cuuint64_t strides[3] = {(cuuint64_t)g.pitchC, (cuuint64_t)g.pitchC * g.rowsC, g.frameStride};
-        cuuint32_t box[4] = {kChromaBoxW, kChromaBoxH, 2, 1}, es[4] = {1, 1, 1, 1};
-        CUresult r = enc(&chromaMap_, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, pool_ + g.offCb, dims, strides, box, es,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) { std::fprintf(stderr, "h264bsd_b200: chroma tensor map failed (%d)\n", (int)r); return false; }
-    }
-    int occR = 1, occD = 0;
-    CK(cudaFuncSetAttribute(reconInterKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(InterWarpSmem) * kReconWarps)));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occR, reconInterKernel, kReconWarps * 32, sizeof(InterWarpSmem) * kReconWarps));
+    int occA = 1, occD = 0, occS = 0;
+    CK(cudaFuncSetAttribute(passAKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(PassAWarpSmem) * kReconWarps)));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occA, passAKernel, kReconWarps * 32, sizeof(PassAWarpSmem) * kReconWarps));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occD, deblockKernel, kDeblockWarps * 32, 0));
-    int occS = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, strengthKernel, kDeblockWarps * 32, 0));
     strengthBlocks_ = std::max(1, occS) * numSms_;
-    reconBlocks_ = std::max(1, occR) * numSms_;
-    int occC = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occC, reconCopyKernel, kCopyWarps * 32, 0));
-    if (const char *e = std::getenv("B200_COPY_VARIANT")) copyVariant_ = std::max(0, std::min(2, std::atoi(e)));
-    if (copyVariant_ == 1) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occC, reconCopyKernelOcc4, kCopyWarps * 32, 0));
-    if (copyVariant_ == 2) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occC, reconCopyKernelDeep, kCopyWarps * 32, 0));
-    copyBlocks_ = std::max(1, occC) * numSms_;
-    // experimental bulk-copy variant of the run section (copy_bulk_kernel.cuh): off unless B200_COPY_BULK=1
-    if (const char *e = std::getenv("B200_COPY_BULK")) copyBulk_ = std::atoi(e) != 0;
-    if (copyBulk_) {
-        int occQ = 0;
-        CK(cudaFuncSetAttribute(reconCopyBulkKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(BulkWarpSmem) * kBulkWarps)));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occQ, reconCopyBulkKernel, kBulkWarps * 32, sizeof(BulkWarpSmem) * kBulkWarps));
-        copyBulkBlocks_ = std::max(1, occQ) * numSms_;
-        if (const char *e = std::getenv("B200_COPY_BULK_RUNS")) copyBulkRuns_ = std::max(1, std::min((int)kBulkRunsPerTask, std::atoi(e)));
-    }
+    passABlocks_ = std::max(1, occA) * numSms_;
     deblockBlocks_ = std::max(1, occD) * numSms_;
-    // B200_GRID_DIV=G: every persistent grid capped at 1/G of the CTAs that fit the machine, for G batches that run side by side
-    // on their own streams (tools/group_bench.py: kernels with complementary limits sharing the SMs); 1 = the measured default
-    if (const char *e = std::getenv("B200_GRID_DIV")) {
-        const int d = std::max(1, std::min(16, std::atoi(e)));
-        strengthBlocks_ = std::max(numSms_, strengthBlocks_ / d);
-        reconBlocks_ = std::max(numSms_, reconBlocks_ / d);
-        copyBlocks_ = std::max(numSms_, copyBlocks_ / d);
-        deblockBlocks_ = std::max(numSms_, deblockBlocks_ / d);
-        if (copyBulkBlocks_) copyBulkBlocks_ = std::max(numSms_, copyBulkBlocks_ / d);
-    }
+    // pass A: a warp task is a column piece of at most 32 macroblocks; pieces of a column are made equally long
+    chunksPerCol_ = (heightMbs + 31) / 32;
+    chunkRows_ = (heightMbs + chunksPerCol_ - 1) / chunksPerCol_;
     // tuning knobs (defaults are the measured best on the 512-stream 1080p batch)
     if (const char *e = std::getenv("B200_CHUNK_B")) chunkB_ = std::max(1, std::min((int)kChunkB, std::atoi(e)));
-    if (const char *e = std::getenv("B200_CHUNK_A")) chunkA_ = std::max(1, std::min((int)kChunkA, std::atoi(e)));
-    if (const char *e = std::getenv("B200_COPY_RUNS")) copyRuns_ = std::max(1, std::min((int)kCopyRunsPerTask, std::atoi(e)));
     if (const char *e = std::getenv("B200_FILTER_CHUNK")) filterChunk_ = std::max(1, std::min((int)kFilterChunk, std::atoi(e)));
-    borderTasks_ = (g_.H + 31) / 32 + 2 * ((g_.H / 2 + 31) / 32) + 2 * ((g_.pitchY + 127) / 128) + 4 * ((g_.pitchC + 127) / 128);
     tapes_.assign(nStreams, DevTape());
-    for (int i = 0; i < 2; i++) {
-        CK(cudaStreamCreateWithFlags(&auxStream_[i], cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&joinEv_[i], cudaEventDisableTiming));
-    }
+    CK(cudaStreamCreateWithFlags(&auxStream_, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&joinEv_, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&forkEv_, cudaEventDisableTiming));
     CK(cudaStreamSynchronize(stream_));
     return true;
@@ -310,6 +285,10 @@ bool Batch::replicateTape(uint32_t src) {
     return true;
 }
 
+// where the pass-B (intra) entries start inside a picture's processing-order list (b200_tape.mbOrder: runs, single copies and
+// the other pass-A macroblocks come first; pass A reads the records in raster order and does not use those sections)
+static inline uint32_t orderBOffset(const b200_pic_hdr &h) { return 2u * h.numRun + h.numPassA - h.numRunMbs; }
+
 bool Batch::buildJobs() {
     uint32_t np = 0xFFFFFFFFu;
     for (const auto &t : tapes_) {
@@ -317,9 +296,6 @@ bool Batch::buildJobs() {
         np = std::min<uint32_t>(np, (uint32_t)t.pics.size());
     }
     numPics_ = np;
-    picMaxQ_.assign(np, 0);
-    picMaxC_.assign(np, 0);
-    picMaxA_.assign(np, 0);
     picMaxB_.assign(np, 0);
     picMaxE_.assign(np, 0);
     jobsFilterAt_ = (size_t)np * g_.nStreams;
@@ -330,18 +306,12 @@ bool Batch::buildJobs() {
             StreamJob &j = jobs[(size_t)k * g_.nStreams + s];
             j.recs = reinterpret_cast<const b200_mb_rec *>(t.recs + t.pics[k].mbRecOffset);
             j.coefs = reinterpret_cast<const int16_t *>(t.coefs + t.pics[k].coefOffset);
-            j.order = reinterpret_cast<const uint16_t *>(t.order) + (size_t)k * g_.nMbs;
+            j.orderB = reinterpret_cast<const uint16_t *>(t.order) + (size_t)k * g_.nMbs + orderBOffset(t.pics[k]);
             j.curSlot = (uint16_t)t.pics[k].curSlot;
-            j.nR = (uint16_t)t.pics[k].numRun;
-            j.nC = (uint16_t)t.pics[k].numCopy;
-            j.nA = (uint16_t)(t.pics[k].numPassA - t.pics[k].numRunMbs - t.pics[k].numCopy);
             j.nB = (uint16_t)t.pics[k].numPassB;
             j.nE = (uint16_t)t.pics[k].numConceal;
-            j.pad[0] = j.pad[1] = 0;
+            j.pad = 0;
             picMaxE_[k] = std::max<uint32_t>(picMaxE_[k], j.nE);
-            picMaxQ_[k] = std::max<uint32_t>(picMaxQ_[k], j.nR);
-            picMaxC_[k] = std::max<uint32_t>(picMaxC_[k], j.nC);
-            picMaxA_[k] = std::max<uint32_t>(picMaxA_[k], j.nA);
             picMaxB_[k] = std::max<uint32_t>(picMaxB_[k], j.nB);
             // what the filter kernels get: the same job, with the picture's filter records where it has any
             StreamJob &jf = jobs[jobsFilterAt_ + (size_t)k * g_.nStreams + s];
@@ -395,7 +365,7 @@ bool Batch::kernelTimes(float ms[6], uint32_t *launchesPerStage) {
     return true;
 }
 
-bool Batch::launchPicture(const StreamJob *dJobs, const StreamJob *dJobsFilter, uint32_t maxQ, uint32_t maxC, uint32_t maxA, uint32_t maxB, uint32_t maxE, bool recon, bool deblock) {
+bool Batch::launchPicture(const StreamJob *dJobs, const StreamJob *dJobsFilter, uint32_t maxB, uint32_t maxE, bool recon, bool deblock) {
     const uint32_t total = (uint32_t)g_.nStreams * (uint32_t)g_.nMbs;
     serial_++;
     auto mark = [&](int stageEnded) {
@@ -405,22 +375,18 @@ bool Batch::launchPicture(const StreamJob *dJobs, const StreamJob *dJobsFilter, 
         cudaEventRecord(e, stream_);
     };
     mark(-1);
-    // The copy pass, pass A and the boundary strengths do not depend on each other (disjoint macroblocks of the current
-    // frame / records only): outside the per-kernel timing mode they run on three streams, DRAM-bound next to
-    // issue-bound next to latency-bound.  Fork after the previous picture's border, join before the intra pass / filter.
-    const bool fork = !timing_ && recon && deblock && auxStream_[0] != nullptr;
+    // The boundary strengths read records only: outside the per-kernel timing mode they run on a second stream next to
+    // pass A.  Fork after the previous picture's border, join before the filter.
+    const bool fork = !timing_ && recon && deblock && auxStream_ != nullptr;
     ReconParams rp;
     if (recon) {
         rp.pool = pool_; rp.g = g_; rp.jobs = dJobs; rp.done = dDoneRecon_;
-        rp.ticket = dCounters_ + 0; rp.errors = dCounters_ + 2; rp.serial = serial_;
+        rp.ticket = dCounters_ + 0; rp.ticketA = dCounters_ + 2; rp.errors = dCounters_ + 3; rp.serial = serial_;
         rp.chunkB = (uint32_t)chunkB_;
         rp.chunksB = (maxB + rp.chunkB - 1) / rp.chunkB;
-        rp.chunkA = (uint32_t)chunkA_;
-        rp.copyRuns = (uint32_t)copyRuns_;
-        rp.chunksA = (maxA + kReconWarps * rp.chunkA - 1) / (kReconWarps * rp.chunkA);
-        rp.virtualCtasA = rp.chunksA * (uint32_t)g_.nStreams;
-        rp.chunksC = (maxC + 31) / 32;
-        rp.chunksQ = (maxQ + rp.copyRuns - 1) / rp.copyRuns;
+        rp.chunkRows = chunkRows_;
+        rp.chunksPerCol = chunksPerCol_;
+        rp.totalChunks = chunksPerCol_ * (uint32_t)g_.widthMbs * (uint32_t)g_.nStreams;
     }
     DeblockParams dp;
     if (deblock) {
@@ -437,47 +403,18 @@ bool Batch::launchPicture(const StreamJob *dJobs, const StreamJob *dJobsFilter, 
     };
     if (fork) {
         CK(cudaEventRecord(forkEv_, stream_));
-        CK(cudaStreamWaitEvent(auxStream_[1], forkEv_, 0));
-        launchStrength(auxStream_[1]);
-        CK(cudaEventRecord(joinEv_[1], auxStream_[1]));
+        CK(cudaStreamWaitEvent(auxStream_, forkEv_, 0));
+        launchStrength(auxStream_);
+        CK(cudaEventRecord(joinEv_, auxStream_));
     }
     if (recon) {
-        const bool copyAside = fork && (maxC || maxQ) && maxA;   // something to overlap with
-        if (maxC || maxQ) {
-            cudaStream_t st = copyAside ? auxStream_[0] : stream_;
-            if (copyAside) CK(cudaStreamWaitEvent(st, forkEv_, 0));
-            auto *copyKernel = copyVariant_ == 1 ? reconCopyKernelOcc4 : copyVariant_ == 2 ? reconCopyKernelDeep : reconCopyKernel;
-            if (copyBulk_) {
-                // runs by the bulk-copy engine, single copies by reconCopyKernel (a launch without run tasks)
-                ReconParams rq = rp, rs = rp;
-                rq.copyRuns = (uint32_t)copyBulkRuns_;
-                rq.chunksQ = (maxQ + rq.copyRuns - 1) / rq.copyRuns;
-                rs.chunksQ = 0;
-                if (maxQ) {
-                    const uint32_t ctas = (rq.chunksQ * (uint32_t)g_.nStreams + kBulkWarps - 1) / kBulkWarps;
-                    reconCopyBulkKernel<<<std::min<uint32_t>(ctas, (uint32_t)copyBulkBlocks_), kBulkWarps * 32, sizeof(BulkWarpSmem) * kBulkWarps, st>>>(rq);
-                    launches_++;
-                }
-                if (maxC) {
-                    const uint32_t ctas = (rs.chunksC * (uint32_t)g_.nStreams + kCopyWarps - 1) / kCopyWarps;
-                    copyKernel<<<std::min<uint32_t>(ctas, (uint32_t)copyBlocks_), kCopyWarps * 32, 0, st>>>(rs);
-                    launches_++;
-                }
-            } else {
-                const uint32_t ctas = ((rp.chunksC + rp.chunksQ) * (uint32_t)g_.nStreams + kCopyWarps - 1) / kCopyWarps;
-                copyKernel<<<std::min<uint32_t>(ctas, (uint32_t)copyBlocks_), kCopyWarps * 32, 0, st>>>(rp);
-                launches_++;
-            }
-            if (copyAside) CK(cudaEventRecord(joinEv_[0], st));
-            mark(5);
-        }
-        if (maxA) {
-            const uint32_t grid = std::min<uint32_t>(rp.virtualCtasA, (uint32_t)reconBlocks_);
-            reconInterKernel<<<grid, kReconWarps * 32, sizeof(InterWarpSmem) * kReconWarps, stream_>>>(rp, lumaMap_, chromaMap_);
+        {
+            const uint32_t ctas = (rp.totalChunks + kReconWarps - 1) / kReconWarps;
+            const PassAMaps &maps = *reinterpret_cast<const PassAMaps *>(maps_);
+            passAKernel<<<std::min<uint32_t>(ctas, (uint32_t)passABlocks_), kReconWarps * 32, sizeof(PassAWarpSmem) * kReconWarps, stream_>>>(rp, maps);
             launches_++;
             mark(0);
         }
-        if (copyAside) CK(cudaStreamWaitEvent(stream_, joinEv_[0], 0));
         if (maxB) {
             reconIntraKernel<<<(rp.chunksB * (uint32_t)g_.nStreams + kReconWarps - 1) / kReconWarps, kReconWarps * 32, 0, stream_>>>(rp);
             launches_++;
@@ -493,7 +430,7 @@ bool Batch::launchPicture(const StreamJob *dJobs, const StreamJob *dJobsFilter, 
     }
     if (deblock) {
         if (fork) {
-            CK(cudaStreamWaitEvent(stream_, joinEv_[1], 0));
+            CK(cudaStreamWaitEvent(stream_, joinEv_, 0));
         } else {
             launchStrength(stream_);
             mark(4);
@@ -506,12 +443,12 @@ bool Batch::launchPicture(const StreamJob *dJobs, const StreamJob *dJobsFilter, 
     {
         BorderParams bp;
         bp.pool = pool_; bp.g = g_; bp.jobs = dJobs;
-        const long long tasks = (long long)borderTasks_ * g_.nStreams;
+        const long long tasks = (long long)borderTasksPerStream(g_) * g_.nStreams;
         borderKernel<<<(int)((tasks + 7) / 8), 256, 0, stream_>>>(bp);
         launches_++;
         mark(2);
     }
-    CK(cudaMemsetAsync(dCounters_, 0, 2 * sizeof(uint32_t), stream_));
+    CK(cudaMemsetAsync(dCounters_, 0, 3 * sizeof(uint32_t), stream_));
     CK(cudaGetLastError());
     return true;
 }
@@ -529,7 +466,7 @@ bool Batch::decodePicture(uint32_t k) {
         fences_.pop_front();
         if (covers) break;
     }
-    return launchPicture(dJobs_ + (size_t)k * g_.nStreams, dJobs_ + jobsFilterAt_ + (size_t)k * g_.nStreams, picMaxQ_[k], picMaxC_[k], picMaxA_[k], picMaxB_[k], picMaxE_[k], true, true);
+    return launchPicture(dJobs_ + (size_t)k * g_.nStreams, dJobs_ + jobsFilterAt_ + (size_t)k * g_.nStreams, picMaxB_[k], picMaxE_[k], true, true);
 }
 
 bool Batch::debugStage(uint32_t k, bool recon, bool deblock) {
@@ -537,7 +474,7 @@ bool Batch::debugStage(uint32_t k, bool recon, bool deblock) {
     CK(cudaSetDevice(device_));
     if (jobsDirty_ && !buildJobs()) return false;
     if (k >= numPics_) return false;
-    return launchPicture(dJobs_ + (size_t)k * g_.nStreams, dJobs_ + jobsFilterAt_ + (size_t)k * g_.nStreams, picMaxQ_[k], picMaxC_[k], picMaxA_[k], picMaxB_[k], picMaxE_[k], recon, deblock);
+    return launchPicture(dJobs_ + (size_t)k * g_.nStreams, dJobs_ + jobsFilterAt_ + (size_t)k * g_.nStreams, picMaxB_[k], picMaxE_[k], recon, deblock);
 }
 
 bool Batch::run(uint32_t first, uint32_t count) {
@@ -580,7 +517,9 @@ bool Batch::submitHostPicture(uint32_t stream, const b200_pic_hdr &hdr, const b2
     CK(cudaSetDevice(device_));
     const size_t recBytes = (size_t)g_.nMbs * sizeof(b200_mb_rec);
     const size_t coefBytes = (size_t)hdr.numCoefBlocks * B200_COEF_BLOCK_BYTES;
-    const size_t orderBytes = (size_t)g_.nMbs * sizeof(uint16_t);
+    // of the processing-order list only the intra and concealment sections are needed
+    const uint32_t ordOff = orderBOffset(hdr), ordN = hdr.numPassB + hdr.numConceal;
+    const size_t orderBytes = (size_t)ordN * sizeof(uint16_t);
     const size_t need = recBytes + coefBytes + orderBytes + (filterRecs ? recBytes + 256 : 0) + 1024;
     const int b = stageIdx_ ^= 1;
     if (stageCap_[b] < need) {
@@ -589,6 +528,7 @@ bool Batch::submitHostPicture(uint32_t stream, const b200_pic_hdr &hdr, const b2
         if (hStage_[b]) cudaFreeHost(hStage_[b]);
         cudaFree(dStage_[b]);
         hStage_[b] = nullptr; dStage_[b] = nullptr;
+        stageCap_[b] = 0;
         const size_t cap = need + need / 2;
         CK(cudaMallocHost(&hStage_[b], cap));
         CK(cudaMalloc(&dStage_[b], cap));
@@ -602,14 +542,11 @@ bool Batch::submitHostPicture(uint32_t stream, const b200_pic_hdr &hdr, const b2
     const size_t recOff = 256, orderOff = (recOff + recBytes + 255) & ~(size_t)255, coefOff = (orderOff + orderBytes + 255) & ~(size_t)255;
     job.recs = reinterpret_cast<const b200_mb_rec *>(dStage_[b] + recOff);
     job.coefs = reinterpret_cast<const int16_t *>(dStage_[b] + coefOff);
-    job.order = reinterpret_cast<const uint16_t *>(dStage_[b] + orderOff);
+    job.orderB = reinterpret_cast<const uint16_t *>(dStage_[b] + orderOff);
     job.curSlot = (uint16_t)hdr.curSlot;
-    job.nR = (uint16_t)hdr.numRun;
-    job.nC = (uint16_t)hdr.numCopy;
-    job.nA = (uint16_t)(hdr.numPassA - hdr.numRunMbs - hdr.numCopy);
     job.nB = (uint16_t)hdr.numPassB;
     job.nE = (uint16_t)hdr.numConceal;
-    job.pad[0] = job.pad[1] = 0;
+    job.pad = 0;
     // the job the filter kernels get sits 64 bytes behind: the same, unless the picture has records of its own for the filter
     StreamJob jobF = job;
     size_t end = coefOff + coefBytes;
@@ -622,27 +559,47 @@ bool Batch::submitHostPicture(uint32_t stream, const b200_pic_hdr &hdr, const b2
     std::memcpy(h, &job, sizeof job);
     std::memcpy(h + 64, &jobF, sizeof jobF);
     std::memcpy(h + recOff, recs, recBytes);
-    std::memcpy(h + orderOff, order, orderBytes);
-    std::memcpy(h + coefOff, coefs, coefBytes);
+    if (orderBytes) std::memcpy(h + orderOff, order + ordOff, orderBytes);
+    if (coefBytes) std::memcpy(h + coefOff, coefs, coefBytes);
     CK(cudaMemcpyAsync(dStage_[b], h, end, cudaMemcpyHostToDevice, stream_));
     h2dBytes_ += end;
-    if (!launchPicture(reinterpret_cast<const StreamJob *>(dStage_[b]), reinterpret_cast<const StreamJob *>(dStage_[b] + 64), hdr.numRun, hdr.numCopy, hdr.numPassA - hdr.numRunMbs - hdr.numCopy, hdr.numPassB, hdr.numConceal, true, true)) return false;
+    if (!launchPicture(reinterpret_cast<const StreamJob *>(dStage_[b]), reinterpret_cast<const StreamJob *>(dStage_[b] + 64), hdr.numPassB, hdr.numConceal, true, true)) return false;
     CK(cudaEventRecord(stageEv_[b], stream_));
     return true;
+}
+
+bool Batch::ensureFrameStage(size_t bytes) {
+    if (frameStageCap_ >= bytes) return true;
+    CK(cudaStreamSynchronize(stream_));
+    cudaFree(dFrameStage_);
+    dFrameStage_ = nullptr; frameStageCap_ = 0;
+    CK(cudaMalloc(&dFrameStage_, bytes));
+    frameStageCap_ = bytes;
+    return true;
+}
+
+// strip layout -> planar: streams [firstStream, firstStream + nStreams), the frame slot of each stream's job (or `slot`)
+void Batch::launchPack(cudaStream_t st, const StreamJob *jobs, uint32_t slot, uint32_t firstStream, uint32_t nStreams, uint8_t *out, size_t outStride,
+                       int cropX, int cropY, int cropW, int cropH, int nv12) {
+    PackParams pp;
+    pp.pool = pool_ + (unsigned long long)firstStream * g_.numSlots * g_.frameStride;
+    pp.g = g_; pp.jobs = jobs; pp.slot = slot; pp.out = out; pp.outStride = outStride;
+    pp.cropX = cropX; pp.cropY = cropY; pp.cropW = cropW; pp.cropH = cropH; pp.nv12 = nv12;
+    const int units = g_.widthMbs * g_.H;
+    dim3 grid((unsigned)std::min(64, (units + 255) / 256), nStreams);
+    packKernel<<<grid, 256, 0, st>>>(pp);
+    launches_++;
 }
 
 bool Batch::readFrame(uint32_t stream, uint32_t slot, uint8_t *dst) {
     if (!created_ || stream >= (uint32_t)g_.nStreams || slot >= (uint32_t)g_.numSlots) return false;
     CK(cudaSetDevice(device_));
-    const uint8_t *f = pool_ + ((unsigned long long)stream * g_.numSlots + slot) * g_.frameStride;
-    const size_t ySize = (size_t)g_.W * g_.H, cSize = ySize / 4;
-    CK(cudaMemcpy2DAsync(dst, g_.W, f + (size_t)kPadY * g_.pitchY + kPadY, g_.pitchY, g_.W, g_.H, cudaMemcpyDeviceToHost, stream_));
-    CK(cudaMemcpy2DAsync(dst + ySize, g_.W / 2, f + g_.offCb + (size_t)kPadC * g_.pitchC + kPadC, g_.pitchC, g_.W / 2, g_.H / 2,
-                         cudaMemcpyDeviceToHost, stream_));
-    CK(cudaMemcpy2DAsync(dst + ySize + cSize, g_.W / 2, f + g_.offCr + (size_t)kPadC * g_.pitchC + kPadC, g_.pitchC, g_.W / 2, g_.H / 2,
-                         cudaMemcpyDeviceToHost, stream_));
+    const size_t fb = frameBytes();
+    if (!ensureFrameStage(fb)) return false;
+    launchPack(stream_, nullptr, slot, stream, 1, dFrameStage_, fb, 0, 0, g_.W, g_.H, 0);
+    CK(cudaMemcpyAsync(dst, dFrameStage_, fb, cudaMemcpyDeviceToHost, stream_));
     CK(cudaStreamSynchronize(stream_));
-    d2hBytes_ += ySize + 2 * cSize;
+    d2hBytes_ += fb;
     return true;
 }
 
@@ -650,50 +607,37 @@ bool Batch::readFrame(uint32_t stream, uint32_t slot, uint8_t *dst) {
 bool Batch::writeFrame(uint32_t stream, uint32_t slot, const uint8_t *src) {
     if (!created_ || stream >= (uint32_t)g_.nStreams || slot >= (uint32_t)g_.numSlots) return false;
     CK(cudaSetDevice(device_));
+    const size_t fb = frameBytes();
+    if (!ensureFrameStage(fb + 256)) return false;
     uint8_t *f = pool_ + ((unsigned long long)stream * g_.numSlots + slot) * g_.frameStride;
-    const size_t ySize = (size_t)g_.W * g_.H, cSize = ySize / 4;
-    CK(cudaMemcpy2DAsync(f + (size_t)kPadY * g_.pitchY + kPadY, g_.pitchY, src, g_.W, g_.W, g_.H, cudaMemcpyHostToDevice, stream_));
-    CK(cudaMemcpy2DAsync(f + g_.offCb + (size_t)kPadC * g_.pitchC + kPadC, g_.pitchC, src + ySize, g_.W / 2, g_.W / 2, g_.H / 2,
-                         cudaMemcpyHostToDevice, stream_));
-    CK(cudaMemcpy2DAsync(f + g_.offCr + (size_t)kPadC * g_.pitchC + kPadC, g_.pitchC, src + ySize + cSize, g_.W / 2, g_.W / 2, g_.H / 2,
-                         cudaMemcpyHostToDevice, stream_));
-    // border: a one-stream BorderParams view whose "stream 0" is this frame
+    CK(cudaMemcpyAsync(dFrameStage_, src, fb, cudaMemcpyHostToDevice, stream_));
+    unpackKernel<<<64, 256, 0, stream_>>>(f, g_, dFrameStage_);
+    // border: a one-stream BorderParams view whose "stream 0" is this frame (the job sits behind the picture in the staging)
     StreamJob job;
     std::memset(&job, 0, sizeof job);
-    job.curSlot = 0;
-    StreamJob *dJob = nullptr;
-    CK(cudaMalloc(&dJob, sizeof job));
+    StreamJob *dJob = reinterpret_cast<StreamJob *>(dFrameStage_ + ((fb + 63) & ~(size_t)63));
     CK(cudaMemcpyAsync(dJob, &job, sizeof job, cudaMemcpyHostToDevice, stream_));
     BorderParams bp;
     bp.pool = f; bp.g = g_; bp.g.nStreams = 1; bp.jobs = dJob;
-    borderKernel<<<(borderTasks_ + 7) / 8, 256, 0, stream_>>>(bp);
+    borderKernel<<<(borderTasksPerStream(g_) + 7) / 8, 256, 0, stream_>>>(bp);
     CK(cudaStreamSynchronize(stream_));
-    cudaFree(dJob);
     return true;
-}
-
-// launch helper: picks the 8-pel variant when rows and pitches allow 8-byte luma / 4-byte chroma loads
-static void launchConvert(cudaStream_t st, int nPictures, int H, const uint8_t *yPlane, int pitchY, const uint8_t *cbPlane, const uint8_t *crPlane,
-                          int pitchC, int W, int mode, uint32_t *out, unsigned long long inStride, unsigned long long outStride) {
-    const bool wide = (W % 8 == 0) && (pitchY % 8 == 0) && (pitchC % 4 == 0) && ((uintptr_t)yPlane % 8 == 0) && ((uintptr_t)cbPlane % 4 == 0) &&
-                      ((uintptr_t)crPlane % 4 == 0) && (inStride % 8 == 0);
-    if (wide) {
-        dim3 grid((W / 8 + 255) / 256, H, nPictures);
-        convertKernelT<8><<<grid, 256, 0, st>>>(yPlane, pitchY, cbPlane, crPlane, pitchC, W, mode, out, inStride, outStride);
-    } else {
-        dim3 grid((W / 4 + 255) / 256, H, nPictures);
-        convertKernelT<4><<<grid, 256, 0, st>>>(yPlane, pitchY, cbPlane, crPlane, pitchC, W, mode, out, inStride, outStride);
-    }
 }
 
 bool Batch::convertFrame(uint32_t stream, uint32_t slot, int mode, uint32_t *dstHost) {
     if (!created_ || stream >= (uint32_t)g_.nStreams || slot >= (uint32_t)g_.numSlots || mode < 0 || mode > 2) return false;
     CK(cudaSetDevice(device_));
     const size_t bytes = (size_t)g_.W * g_.H * 4;
-    if (!dConvert_) CK(cudaMalloc(&dConvert_, bytes));
+    if (convertCap_ < bytes) {
+        CK(cudaStreamSynchronize(stream_));
+        cudaFree(dConvert_);
+        dConvert_ = nullptr; convertCap_ = 0;
+        CK(cudaMalloc(&dConvert_, bytes));
+        convertCap_ = bytes;
+    }
     const uint8_t *f = pool_ + ((unsigned long long)stream * g_.numSlots + slot) * g_.frameStride;
-    launchConvert(stream_, 1, g_.H, f + (size_t)kPadY * g_.pitchY + kPadY, g_.pitchY, f + g_.offCb + (size_t)kPadC * g_.pitchC + kPadC,
-                  f + g_.offCr + (size_t)kPadC * g_.pitchC + kPadC, g_.pitchC, g_.W, mode, dConvert_, 0, 0);
+    dim3 grid((g_.W / 8 + 255) / 256, g_.H, 1);
+    convertFrameKernel<<<grid, 256, 0, stream_>>>(f, g_, mode, dConvert_, 0, 0, 0, 0, g_.W, g_.H);
     launches_++;
     CK(cudaMemcpyAsync(dstHost, dConvert_, bytes, cudaMemcpyDeviceToHost, stream_));
     CK(cudaStreamSynchronize(stream_));
@@ -706,12 +650,17 @@ bool Batch::convertBench(uint32_t stream, uint32_t slot, int mode, int reps, flo
     if (!created_ || stream >= (uint32_t)g_.nStreams || slot >= (uint32_t)g_.numSlots) return false;
     CK(cudaSetDevice(device_));
     const size_t bytes = (size_t)g_.W * g_.H * 4;
-    if (!dConvert_) CK(cudaMalloc(&dConvert_, bytes));
+    if (convertCap_ < bytes) {
+        CK(cudaStreamSynchronize(stream_));
+        cudaFree(dConvert_);
+        dConvert_ = nullptr; convertCap_ = 0;
+        CK(cudaMalloc(&dConvert_, bytes));
+        convertCap_ = bytes;
+    }
     const uint8_t *f = pool_ + ((unsigned long long)stream * g_.numSlots + slot) * g_.frameStride;
+    dim3 grid((g_.W / 8 + 255) / 256, g_.H, 1);
     CK(cudaEventRecord(evA_, stream_));
-    for (int i = 0; i < reps; i++)
-        launchConvert(stream_, 1, g_.H, f + (size_t)kPadY * g_.pitchY + kPadY, g_.pitchY, f + g_.offCb + (size_t)kPadC * g_.pitchC + kPadC,
-                      f + g_.offCr + (size_t)kPadC * g_.pitchC + kPadC, g_.pitchC, g_.W, mode, dConvert_, 0, 0);
+    for (int i = 0; i < reps; i++) convertFrameKernel<<<grid, 256, 0, stream_>>>(f, g_, mode, dConvert_, 0, 0, 0, 0, g_.W, g_.H);
     CK(cudaEventRecord(evB_, stream_));
     CK(cudaEventSynchronize(evB_));
     CK(cudaEventElapsedTime(ms, evA_, evB_));
@@ -726,11 +675,11 @@ bool Batch::convertBenchAll(uint32_t slot, int mode, int reps, float *ms) {
     const size_t pixels = (size_t)g_.W * g_.H;
     if (!dConvertAll_) CK(cudaMalloc(&dConvertAll_, pixels * 4 * g_.nStreams));
     const uint8_t *f = pool_ + (unsigned long long)slot * g_.frameStride;
+    dim3 grid((g_.W / 8 + 255) / 256, g_.H, g_.nStreams);
+    const unsigned long long inStride = (unsigned long long)g_.numSlots * g_.frameStride;
     CK(cudaEventRecord(evA_, stream_));
     for (int i = 0; i < reps; i++)
-        launchConvert(stream_, g_.nStreams, g_.H, f + (size_t)kPadY * g_.pitchY + kPadY, g_.pitchY, f + g_.offCb + (size_t)kPadC * g_.pitchC + kPadC,
-                      f + g_.offCr + (size_t)kPadC * g_.pitchC + kPadC, g_.pitchC, g_.W, mode, dConvertAll_,
-                      (unsigned long long)g_.numSlots * g_.frameStride, (unsigned long long)pixels);
+        convertFrameKernel<<<grid, 256, 0, stream_>>>(f, g_, mode, dConvertAll_, inStride, (unsigned long long)pixels, 0, 0, g_.W, g_.H);
     CK(cudaEventRecord(evB_, stream_));
     CK(cudaEventSynchronize(evB_));
     CK(cudaEventElapsedTime(ms, evA_, evB_));
@@ -738,7 +687,8 @@ bool Batch::convertBenchAll(uint32_t slot, int mode, int reps, float *ms) {
     return true;
 }
 
-// h264bsdConvertTo{RGBA,BGRA,YCbCrA} for caller-owned host buffers (contiguous I420 in, u32 pixels out)
+// h264bsdConvertTo{RGBA,BGRA,YCbCrA} for caller-owned host buffers (contiguous I420 in, u32 pixels out).  The device buffers
+// are kept between calls (grown when a larger picture comes): a caller converts every picture of a stream with the same size.
 bool convertHostI420(int mode, uint32_t width, uint32_t height, const uint8_t *yuv, uint32_t *out) {
     if (deviceCount() <= 0) {
         std::fprintf(stderr, "h264bsd_b200: no CUDA device visible -- this engine has no CPU fallback\n");
@@ -746,48 +696,37 @@ bool convertHostI420(int mode, uint32_t width, uint32_t height, const uint8_t *y
     }
     if (!width || !height || (width & 3)) return false;
     const size_t inBytes = (size_t)width * height * 3 / 2, outBytes = (size_t)width * height * 4;
-    uint8_t *dIn = nullptr;
-    uint32_t *dOut = nullptr;
-    CK(cudaMalloc(&dIn, inBytes));
-    CK(cudaMalloc(&dOut, outBytes));
+    static thread_local uint8_t *dIn = nullptr;
+    static thread_local uint32_t *dOut = nullptr;
+    static thread_local size_t capIn = 0, capOut = 0;
+    if (capIn < inBytes) { cudaFree(dIn); dIn = nullptr; capIn = 0; CK(cudaMalloc(&dIn, inBytes)); capIn = inBytes; }
+    if (capOut < outBytes) { cudaFree(dOut); dOut = nullptr; capOut = 0; CK(cudaMalloc(&dOut, outBytes)); capOut = outBytes; }
     CK(cudaMemcpy(dIn, yuv, inBytes, cudaMemcpyHostToDevice));
-    launchConvert(nullptr, 1, (int)height, dIn, (int)width, dIn + (size_t)width * height, dIn + (size_t)width * height * 5 / 4, (int)width / 2,
-                  (int)width, mode, dOut, 0, 0);
+    const uint8_t *yPlane = dIn, *cbPlane = dIn + (size_t)width * height, *crPlane = dIn + (size_t)width * height * 5 / 4;
+    const int W = (int)width, pitchC = W / 2;
+    const bool wide = (W % 8 == 0) && ((uintptr_t)cbPlane % 4 == 0) && ((uintptr_t)crPlane % 4 == 0) && (pitchC % 4 == 0);
+    if (wide) {
+        dim3 grid((W / 8 + 255) / 256, height);
+        convertKernelT<8><<<grid, 256, 0, nullptr>>>(yPlane, W, cbPlane, crPlane, pitchC, W, mode, dOut);
+    } else {
+        dim3 grid((W / 4 + 255) / 256, height);
+        convertKernelT<4><<<grid, 256, 0, nullptr>>>(yPlane, W, cbPlane, crPlane, pitchC, W, mode, dOut);
+    }
     CK(cudaGetLastError());
     CK(cudaMemcpy(out, dOut, outBytes, cudaMemcpyDeviceToHost));
-    cudaFree(dIn);
-    cudaFree(dOut);
     return true;
 }
 
-// copy picture k of every stream (frame slot of that picture, border stripped) into one contiguous device staging
-// buffer and send it to the host in a single transfer: dst + s * strideBytes receives stream s's coded-size I420 frame
-__global__ void __launch_bounds__(256) packKernel(const uint8_t *pool, PoolGeom g, const StreamJob *jobs, uint8_t *staging) {
-    const uint32_t s = blockIdx.y;
-    const uint8_t *f = pool + (unsigned long long)(s * (uint32_t)g.numSlots + jobs[s].curSlot) * g.frameStride;
-    uint8_t *out = staging + (size_t)s * g.nMbs * 384;
-    const int wordsY = g.W / 4, wordsC = g.W / 8;
-    const long long total = (long long)wordsY * g.H + 2ll * wordsC * (g.H / 2);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        size_t off;
-        if (i < (long long)wordsY * g.H) {
-            const int y = (int)(i / wordsY), x = (int)(i - (long long)y * wordsY);
-            off = (size_t)(y + kPadY) * g.pitchY + kPadY + x * 4;
-        } else {
-            long long j = i - (long long)wordsY * g.H;
-            const int pl = j >= (long long)wordsC * (g.H / 2);
-            if (pl) j -= (long long)wordsC * (g.H / 2);
-            const int y = (int)(j / wordsC), x = (int)(j - (long long)y * wordsC);
-            off = (pl ? g.offCr : g.offCb) + (size_t)(y + kPadC) * g.pitchC + kPadC + x * 4;
-        }
-        reinterpret_cast<uint32_t *>(out)[i] = *reinterpret_cast<const uint32_t *>(f + off);
-    }
-}
-
-bool Batch::readPictureAll(uint32_t k, uint8_t *dst, size_t strideBytes) {
+// picture k's frame of every stream (frame slot of that picture), de-stripped into one contiguous device staging buffer and
+// sent to the host in a single transfer: dst + s * strideBytes receives stream s's I420 (or NV12) picture -- the coded size, or
+// the cropping rectangle (cropW x cropH luma pels at (cropX, cropY))
+bool Batch::readPictureAllEx(uint32_t k, uint8_t *dst, size_t strideBytes, int cropX, int cropY, int cropW, int cropH, int nv12) {
     if (!created_ || k >= numPics_) return false;
+    if (!cropW) { cropX = cropY = 0; cropW = g_.W; cropH = g_.H; }
+    if (cropX < 0 || cropY < 0 || cropW <= 0 || cropH <= 0 || cropX + cropW > g_.W || cropY + cropH > g_.H || ((cropX | cropY | cropW | cropH) & 1)) return false;
     CK(cudaSetDevice(device_));
-    const size_t fb = frameBytes();
+    const size_t fb = frameBytes(), ob = (size_t)cropW * cropH * 3 / 2;
+    if (strideBytes < ob) return false;
     if (!dPack_[0]) {
         CK(cudaMalloc(&dPack_[0], fb * g_.nStreams));
         CK(cudaMalloc(&dPack_[1], fb * g_.nStreams));
@@ -800,22 +739,21 @@ bool Batch::readPictureAll(uint32_t k, uint8_t *dst, size_t strideBytes) {
     const int b = packIdx_ ^= 1;
     // the transfer that last used this staging buffer must be done before it is overwritten (device-side wait)
     if (packUsed_[b]) CK(cudaStreamWaitEvent(stream_, packEv_[b], 0));
-    dim3 grid(32, g_.nStreams);
-    packKernel<<<grid, 256, 0, stream_>>>(pool_, g_, dJobs_ + (size_t)k * g_.nStreams, dPack_[b]);
-    launches_++;
+    launchPack(stream_, dJobs_ + (size_t)k * g_.nStreams, 0, 0, (uint32_t)g_.nStreams, dPack_[b], ob, cropX, cropY, cropW, cropH, nv12);
     // the transfer runs on its own stream so that the next picture's kernels overlap it
     CK(cudaEventRecord(packedEv_[b], stream_));
     CK(cudaStreamWaitEvent(copyStream_, packedEv_[b], 0));
-    if (strideBytes == fb) {
-        CK(cudaMemcpyAsync(dst, dPack_[b], fb * g_.nStreams, cudaMemcpyDeviceToHost, copyStream_));
+    if (strideBytes == ob) {
+        CK(cudaMemcpyAsync(dst, dPack_[b], ob * g_.nStreams, cudaMemcpyDeviceToHost, copyStream_));
     } else {
-        CK(cudaMemcpy2DAsync(dst, strideBytes, dPack_[b], fb, fb, g_.nStreams, cudaMemcpyDeviceToHost, copyStream_));
+        CK(cudaMemcpy2DAsync(dst, strideBytes, dPack_[b], ob, ob, g_.nStreams, cudaMemcpyDeviceToHost, copyStream_));
     }
     CK(cudaEventRecord(packEv_[b], copyStream_));
     packUsed_[b] = true;
-    d2hBytes_ += fb * g_.nStreams;
+    d2hBytes_ += ob * g_.nStreams;
     return true;
 }
+bool Batch::readPictureAll(uint32_t k, uint8_t *dst, size_t strideBytes) { return readPictureAllEx(k, dst, strideBytes, 0, 0, 0, 0, 0); }
 
 // number of streams whose frame in slots[s] differs from stream 0's frame in slots[0]
 int Batch::compareStreams(const uint32_t *slots) {
@@ -850,9 +788,9 @@ uint64_t Batch::deblockWorkMbs() {
     unsigned long long v = 0;
     if (!created_) return 0;
     cudaSetDevice(device_);
+    if (auxStream_) cudaStreamSynchronize(auxStream_);
     cudaMemcpyAsync(&v, dCounters_ + 4, sizeof v, cudaMemcpyDeviceToHost, stream_);
     cudaStreamSynchronize(stream_);
-    if (auxStream_[1]) cudaStreamSynchronize(auxStream_[1]);
     return v;
 }
 
@@ -860,7 +798,7 @@ uint32_t Batch::idctErrors() {
     uint32_t v = 0;
     if (!created_) return 0;
     cudaSetDevice(device_);
-    cudaMemcpyAsync(&v, dCounters_ + 2, sizeof v, cudaMemcpyDeviceToHost, stream_);
+    cudaMemcpyAsync(&v, dCounters_ + 3, sizeof v, cudaMemcpyDeviceToHost, stream_);
     cudaStreamSynchronize(stream_);
     return v;
 }

@@ -47,7 +47,9 @@ public:
     int compareStreams(const uint32_t *slots);
     // per-stage device time (CUDA events on the engine's stream around every launch)
     void kernelTiming(bool enable);
-    bool kernelTimes(float ms[6], uint32_t *launchesPerStage);  // recon pass A, deblock filter, border, recon pass B, boundary strengths, copy pass
+    bool kernelTimes(float ms[6], uint32_t *launchesPerStage);  // recon pass A, deblock filter, border, recon pass B, boundary strengths, (unused)
+    // picture k's frame of every stream, cropped / as NV12 (see packKernel); cropW == 0: the coded size
+    bool readPictureAllEx(uint32_t k, uint8_t *dst, size_t strideBytes, int cropX, int cropY, int cropW, int cropH, int nv12);
     uint32_t idctErrors();
     uint32_t watchdog(int which);  // 0: flag waits that gave up, 1: TMA waits that gave up
 
@@ -61,6 +63,7 @@ public:
     int device() const { return device_; }
 
 private:
+    Batch &operator=(Batch &&) = default;   // destroy() only: back to the default state (nothing dangles after a re-create)
     struct DevTape {
         uint8_t *recs = nullptr, *coefs = nullptr, *order = nullptr;
         size_t recBytes = 0, coefBytes = 0, orderBytes = 0, capRecs = 0, capCoefs = 0, capOrder = 0;
@@ -68,8 +71,11 @@ private:
         std::vector<b200_pic_hdr> pics;
     };
     bool buildJobs();
-    bool launchPicture(const StreamJob *dJobs, const StreamJob *dJobsFilter, uint32_t maxQ, uint32_t maxC, uint32_t maxA, uint32_t maxB, uint32_t maxE, bool recon, bool deblock);
-    std::vector<uint32_t> picMaxQ_, picMaxC_, picMaxA_, picMaxB_, picMaxE_;
+    bool launchPicture(const StreamJob *dJobs, const StreamJob *dJobsFilter, uint32_t maxB, uint32_t maxE, bool recon, bool deblock);
+    bool ensureFrameStage(size_t bytes);
+    void launchPack(cudaStream_t st, const StreamJob *jobs, uint32_t slot, uint32_t firstStream, uint32_t nStreams, uint8_t *out, size_t outStride,
+                    int cropX, int cropY, int cropW, int cropH, int nv12);
+    std::vector<uint32_t> picMaxB_, picMaxE_;
 
     bool created_ = false;
     int device_ = 0, numSms_ = 0;
@@ -77,26 +83,22 @@ private:
     cudaEvent_t evA_ = nullptr, evB_ = nullptr;
     PoolGeom g_{};
     uint8_t *pool_ = nullptr;
-    CUtensorMap lumaMap_, chromaMap_;
+    CUtensorMap maps_[10];             // PassAMaps (recon_kernel.cuh): luma [nx 1..3][16 / 21 rows], chroma [nx 1..2][8 / 9 rows]
     uint16_t *dOrder_ = nullptr;
     uint32_t *dDoneRecon_ = nullptr, *dDoneDeblock_ = nullptr, *dCounters_ = nullptr, *dSlots_ = nullptr, *dBsWords_ = nullptr;
     uint8_t *dWork_ = nullptr;
     int strengthBlocks_ = 0;
     uint32_t serial_ = 0;
-    int reconBlocks_ = 0, deblockBlocks_ = 0, copyBlocks_ = 0;
-    cudaEvent_t syncEv_ = nullptr, forkEv_ = nullptr, joinEv_[2] = {nullptr, nullptr};
+    int passABlocks_ = 0, deblockBlocks_ = 0;
+    uint32_t chunkRows_ = 32, chunksPerCol_ = 1;
+    cudaEvent_t syncEv_ = nullptr, forkEv_ = nullptr, joinEv_ = nullptr;
     size_t jobsCap_ = 0;
-    int borderTasks_ = 0;   // warp tasks of borderKernel per stream
     uint32_t *dConvertAll_ = nullptr;
     int chunkB_ = 1, filterChunk_ = 8;   // list entries per intra warp task / tickets per filter warp step
-    int chunkA_ = 8, copyRuns_ = 4;      // list entries per pass-A warp / runs per copy warp task
-    bool copyBulk_ = false;              // B200_COPY_BULK=1: zero-motion runs by reconCopyBulkKernel (experimental)
-    int copyBulkBlocks_ = 0, copyBulkRuns_ = 16;
-    int copyVariant_ = 0;                // B200_COPY_VARIANT: 0 reconCopyKernel, 1 ...Occ4, 2 ...Deep (unmeasured A/B variants)
     cudaStream_t uploadStream_ = nullptr;
     std::deque<std::pair<uint32_t, cudaEvent_t>> fences_;   // (pictures below this index, upload-stream event)
     std::vector<cudaEvent_t> fenceFree_;
-    cudaStream_t auxStream_[2] = {nullptr, nullptr};   // copy pass / boundary strengths next to pass A
+    cudaStream_t auxStream_ = nullptr;   // boundary strengths next to pass A
     std::vector<DevTape> tapes_;
     StreamJob *dJobs_ = nullptr;        // per picture and stream; the second half of the table is what the filter kernels get
     size_t jobsFilterAt_ = 0;           // (the same jobs, except where a picture has records of its own for the filter)
@@ -108,6 +110,9 @@ private:
     cudaEvent_t stageEv_[2] = {nullptr, nullptr};
     int stageIdx_ = 0;
     uint32_t *dConvert_ = nullptr;
+    size_t convertCap_ = 0;
+    uint8_t *dFrameStage_ = nullptr;    // one picture, planar: readFrame / writeFrame
+    size_t frameStageCap_ = 0;
     uint64_t launches_ = 0, h2dBytes_ = 0, d2hBytes_ = 0;
     bool timing_ = false;
     std::vector<cudaEvent_t> evPool_;

@@ -1,6 +1,5 @@
 // recon_kernel.cuh -- macroblock reconstruction: inverse zig-zag + dequant + IDCT, intra /
-// inter prediction, add residual, write.  One warp per macroblock, persistent CTAs, tickets
-// handed out in wavefront order so that a warp only ever waits on warps that already started.
+// inter prediction, add residual, write.  One warp per macroblock.
 //
 // Restates, as sm_100a device code: h264bsd_transform.c:97-401 (residual),
 // h264bsd_intra_prediction.c:478-1830, h264bsd_inter_prediction.c:361-482 +
@@ -11,19 +10,34 @@
 namespace b200 {
 
 constexpr int kReconWarps = 8;
-constexpr int kChunkA = 8;   // consecutive pass-A list entries per warp (TMA of entry i+1 overlaps the math of entry i)
 constexpr int kChunkB = 8;   // most consecutive pass-B (wavefront) entries per warp task (ReconParams::chunkB <= kChunkB)
 
-
-struct __align__(128) InterWarpSmem {
-    uint8_t lumaWin[3][kLumaBoxW * kLumaBoxH + 16];           // 3 x 1024: two for the prefetch double buffer, [2] for the
-    uint8_t chromaWin[3][2 * kChromaBoxW * kChromaBoxH + 64];  // 3 x 640   second partition of a two-partition step
-    int16_t res[24][16];                                       // 768
-    uint8_t pred[384];                                         // 384: multi-partition macroblocks only
-    uint32_t meta[kChunkA][8];                                 // per entry: head words 0..3, refSlots, mv[0], mb address
-    uint64_t mbar[3];
-    uint32_t pad[10];
+// Tensor maps of pass A (Batch::create): strip-major planes -> raster windows (pool_geom.hpp).  A luma box is nx strips wide
+// (16 nx pels) and 16 rows (integer vertical vector) or 21 rows (16 + 5 for the six-tap filter) high; a chroma box nx strips
+// (8 nx pels of Cb and of Cr) by 8 or 9 rows.
+struct PassAMaps {
+    CUtensorMap luma[3][2];     // [nx - 1][0: 16 rows, 1: 21 rows]
+    CUtensorMap chroma[2][2];   // [nx - 1][0: 8 rows,  1: 9 rows]
 };
+
+constexpr int kLumaBufBytes = 1024;     // >= 48 x 21
+constexpr int kChromaBufBytes = 384;    // >= 32 x 9
+constexpr int kCoefBufBytes = 896;      // >= 26 blocks of 32 bytes (I_PCM: 12)
+
+struct __align__(128) PassAWarpSmem {
+    uint8_t luma[2][kLumaBufBytes];       // reference windows: the macroblock being computed / the next one (TMA, mbarrier double buffer)
+    uint8_t chroma[2][kChromaBufBytes];
+    uint8_t coef[2][kCoefBufBytes];       // the macroblock's levels (cp.async.bulk, same mbarrier)
+    int32_t resY[16][16];                 // residual of the macroblock being computed, raster
+    int32_t resC[2][8][8];
+    uint64_t mbar[2];
+    uint8_t list[32];                     // compaction scratch: lanes of the chunk's copies / the macroblock's active 4x4 blocks
+    int32_t dcC[8];                       // chroma DC values of the macroblock being computed
+    uint8_t pred[384];                    // sub-macroblocks with 8x4 / 4x8 / 4x4 partitions only
+    uint8_t pad[48];
+};
+static_assert(sizeof(PassAWarpSmem) % 128 == 0, "per-warp shared memory keeps the TMA destinations 128-byte aligned");
+
 struct __align__(16) IntraWarpSmem {
     int16_t res[24][16];
     uint8_t itY[17][24];   // rows -1..15, cols -1..19 (+pad)
@@ -100,42 +114,182 @@ __device__ __forceinline__ int chromaDcPick(const int16_t *lev, int qp, int pick
 }
 
 // ---- motion compensation from the staged window -----------------------------------------------------
-// window sample at picture position (xInt + dx, yInt + dy): `win` points at the sample (xInt-2, yInt-2) inside the box
-__device__ __forceinline__ int W_(const uint8_t *win, int dx, int dy) { return win[(dy + 2) * kLumaBoxW + dx + 2]; }
+// A window lies in shared memory as a raster of `pitch` bytes per row (16, 32 or 48: the box is 1..3 strips wide).  G0 is
+// the address of the partition's integer sample (0, 0) inside it; with a fractional vector component the window starts two
+// samples before and ends three after the partition on that axis.
 __device__ __forceinline__ int tap6(int a, int b, int c, int d, int e, int f) { return a - 5 * b + 20 * c + 20 * d - 5 * e + f; }
-__device__ __forceinline__ int hsum(const uint8_t *win, int x, int y) {
-    return tap6(W_(win, x - 2, y), W_(win, x - 1, y), W_(win, x, y), W_(win, x + 1, y), W_(win, x + 2, y), W_(win, x + 3, y));
+__device__ __forceinline__ int hsum(const uint8_t *G0, int pitch, int x, int y) {
+    const uint8_t *q = G0 + y * pitch + x;
+    return tap6(q[-2], q[-1], q[0], q[1], q[2], q[3]);
 }
-__device__ __forceinline__ int vsum(const uint8_t *win, int x, int y) {
-    return tap6(W_(win, x, y - 2), W_(win, x, y - 1), W_(win, x, y), W_(win, x, y + 1), W_(win, x, y + 2), W_(win, x, y + 3));
+__device__ __forceinline__ int vsum(const uint8_t *G0, int pitch, int x, int y) {
+    const uint8_t *q = G0 + y * pitch + x;
+    return tap6(q[-2 * pitch], q[-pitch], q[0], q[pitch], q[2 * pitch], q[3 * pitch]);
 }
-// clause 8.4.2.2.1; dispatch table of h264bsdPredictSamples (reconstruct.c:1848-1927)
-__device__ __forceinline__ int lumaQpel(const uint8_t *win, int x, int y, int xf, int yf) {
-    if ((xf | yf) == 0) return W_(win, x, y);
+// clause 8.4.2.2.1; dispatch table of h264bsdPredictSamples (reconstruct.c:1848-1927), one sample
+__device__ __forceinline__ int lumaQpel(const uint8_t *G0, int pitch, int x, int y, int xf, int yf) {
+    if ((xf | yf) == 0) return G0[y * pitch + x];
     if (yf == 0) {
-        int b = clip255((hsum(win, x, y) + 16) >> 5);
+        int b = clip255((hsum(G0, pitch, x, y) + 16) >> 5);
         if (xf == 2) return b;
-        return (b + W_(win, x + (xf >> 1), y) + 1) >> 1;
+        return (b + G0[y * pitch + x + (xf >> 1)] + 1) >> 1;
     }
     if (xf == 0) {
-        int h = clip255((vsum(win, x, y) + 16) >> 5);
+        int h = clip255((vsum(G0, pitch, x, y) + 16) >> 5);
         if (yf == 2) return h;
-        return (h + W_(win, x, y + (yf >> 1)) + 1) >> 1;
+        return (h + G0[(y + (yf >> 1)) * pitch + x] + 1) >> 1;
     }
     if (xf != 2 && yf != 2) {
-        int b = clip255((hsum(win, x, y + (yf >> 1)) + 16) >> 5);
-        int h = clip255((vsum(win, x + (xf >> 1), y) + 16) >> 5);
+        int b = clip255((hsum(G0, pitch, x, y + (yf >> 1)) + 16) >> 5);
+        int h = clip255((vsum(G0, pitch, x + (xf >> 1), y) + 16) >> 5);
         return (b + h + 1) >> 1;
     }
-    int j = clip255((tap6(hsum(win, x, y - 2), hsum(win, x, y - 1), hsum(win, x, y), hsum(win, x, y + 1),
-                          hsum(win, x, y + 2), hsum(win, x, y + 3)) + 512) >> 10);
+    int j = clip255((tap6(hsum(G0, pitch, x, y - 2), hsum(G0, pitch, x, y - 1), hsum(G0, pitch, x, y), hsum(G0, pitch, x, y + 1),
+                          hsum(G0, pitch, x, y + 2), hsum(G0, pitch, x, y + 3)) + 512) >> 10);
     if (xf == 2 && yf == 2) return j;
     if (xf == 2) {
-        int b = clip255((hsum(win, x, y + (yf >> 1)) + 16) >> 5);
+        int b = clip255((hsum(G0, pitch, x, y + (yf >> 1)) + 16) >> 5);
         return (j + b + 1) >> 1;
     }
-    int h = clip255((vsum(win, x + (xf >> 1), y) + 16) >> 5);
+    int h = clip255((vsum(G0, pitch, x + (xf >> 1), y) + 16) >> 5);
     return (j + h + 1) >> 1;
+}
+
+// 8 consecutive bytes from an arbitrarily aligned shared-memory address
+__device__ __forceinline__ uint2 lds8(const uint8_t *p) {
+    const uint32_t a = smemAddr(p), sh = (a & 3u) * 8u;
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(p - (a & 3u));
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+    return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
+}
+__device__ __forceinline__ uint32_t lds4(const uint8_t *p) {
+    const uint32_t a = smemAddr(p), sh = (a & 3u) * 8u;
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(p - (a & 3u));
+    return __funnelshift_r(w[0], w[1], sh);
+}
+
+// ---- 8-wide luma prediction for one lane (row y, columns x0..x0+7 of a partition) --------------------
+constexpr int kTapsLo = 0x1414FB01;  // bytes (1, -5, 20, 20)
+constexpr int kTapsHi = 0x000001FB;  // bytes (-5, 1, 0, 0)
+
+// horizontal 6-tap sums (+ acc0) for 8 outputs; rowp points at sample x0-2 of the row (13 samples are read).  The taps of
+// output k are bytes k..k+5 of the row: two dot products, over bytes k..k+3 and k+4..k+7 (the last two times zero)
+__device__ __forceinline__ void hrow8(const uint8_t *rowp, int *hs, int acc0) {
+    const uint32_t a = smemAddr(rowp), sh0 = (a & 3u) * 8u;
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(rowp - (a & 3u));
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+    // aligned view: byte k of the row = byte (k + (a&3)) of (w0,w1,w2,w3)
+    const uint32_t v0 = __funnelshift_r(w0, w1, sh0), v1 = __funnelshift_r(w1, w2, sh0), v2 = __funnelshift_r(w2, w3, sh0), v3 = w3 >> sh0;
+    uint32_t q[12];   // q[k] = bytes k..k+3
+    q[0] = v0; q[4] = v1; q[8] = v2;
+#pragma unroll
+    for (int k = 1; k < 4; k++) {
+        q[k] = __funnelshift_r(v0, v1, 8 * k);
+        q[4 + k] = __funnelshift_r(v1, v2, 8 * k);
+        q[8 + k] = __funnelshift_r(v2, v3, 8 * k);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) hs[k] = dp4aUS(q[k + 4], kTapsHi, dp4aUS(q[k], kTapsLo, acc0));
+}
+// vertical 6-tap sums (+ acc0) for 8 outputs; colp points at sample (x0, y-2).  The six rows are read as 8-byte spans and
+// transposed four columns at a time (byte permutes), so that a column's taps sit in one word for the dot products
+__device__ __forceinline__ void vcol8(const uint8_t *colp, int pitch, int *vs, int acc0) {
+    uint2 r[6];
+#pragma unroll
+    for (int t = 0; t < 6; t++) r[t] = lds8(colp + t * pitch);
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        const uint32_t a0 = half ? r[0].y : r[0].x, a1 = half ? r[1].y : r[1].x, a2 = half ? r[2].y : r[2].x;
+        const uint32_t a3 = half ? r[3].y : r[3].x, a4 = half ? r[4].y : r[4].x, a5 = half ? r[5].y : r[5].x;
+        const uint32_t t0 = __byte_perm(a0, a1, 0x5140), t1 = __byte_perm(a2, a3, 0x5140);
+        const uint32_t t2 = __byte_perm(a0, a1, 0x7362), t3 = __byte_perm(a2, a3, 0x7362);
+        const uint32_t c0 = __byte_perm(t0, t1, 0x5410), c1 = __byte_perm(t0, t1, 0x7632);
+        const uint32_t c2 = __byte_perm(t2, t3, 0x5410), c3 = __byte_perm(t2, t3, 0x7632);
+        // rows 4 and 5 of column k in the two low bytes (the two high bytes meet zero taps)
+        vs[4 * half + 0] = dp4aUS(__byte_perm(a4, a5, 0x0040), kTapsHi, dp4aUS(c0, kTapsLo, acc0));
+        vs[4 * half + 1] = dp4aUS(__byte_perm(a4, a5, 0x0051), kTapsHi, dp4aUS(c1, kTapsLo, acc0));
+        vs[4 * half + 2] = dp4aUS(__byte_perm(a4, a5, 0x0062), kTapsHi, dp4aUS(c2, kTapsLo, acc0));
+        vs[4 * half + 3] = dp4aUS(__byte_perm(a4, a5, 0x0073), kTapsHi, dp4aUS(c3, kTapsLo, acc0));
+    }
+}
+// clip255(v >> sh) of eight sums, packed (the rounding constant is already in the sums)
+__device__ __forceinline__ uint2 pack8shift(const int *v, int sh) {
+    return make_uint2(pack4sat(v[0] >> sh, v[1] >> sh, v[2] >> sh, v[3] >> sh), pack4sat(v[4] >> sh, v[5] >> sh, v[6] >> sh, v[7] >> sh));
+}
+__device__ __forceinline__ uint2 avg8(uint2 a, uint2 b) { return make_uint2(__vavgu4(a.x, b.x), __vavgu4(a.y, b.y)); }
+
+// clause 8.4.2.2.1 for 8 horizontally adjacent samples: (x0, y) = position of the first sample inside the partition; the
+// same arithmetic as lumaQpel, 8 at a time, on packed bytes: the rounded averages (a + b + 1) >> 1 are per-byte averages of
+// clipped values
+__device__ __forceinline__ uint2 lumaQpel8(const uint8_t *G0, int pitch, int x0, int y, int xf, int yf) {
+    const uint8_t *at = G0 + y * pitch + x0;   // the lane's first integer sample
+    if ((xf | yf) == 0) return lds8(at);       // h264bsdFillBlock copy (reconstruct.c:1852)
+    const bool jfam = (xf == 2 || yf == 2) && xf != 0 && yf != 0;
+    if (!jfam) {
+        const bool useH = xf != 0, useV = yf != 0;
+        uint2 b = make_uint2(0, 0), h = make_uint2(0, 0);
+        if (useH) {
+            int t[8];
+            hrow8(at + (yf == 3 ? pitch : 0) - 2, t, 16);
+            b = pack8shift(t, 5);
+        }
+        if (useV) {
+            int t[8];
+            vcol8(at - 2 * pitch + (xf == 3 ? 1 : 0), pitch, t, 16);
+            h = pack8shift(t, 5);
+        }
+        if (useH && useV) return avg8(b, h);
+        if (useH) return xf == 2 ? b : avg8(b, lds8(at + (xf >> 1)));
+        return yf == 2 ? h : avg8(h, lds8(at + (yf >> 1) * pitch));
+    }
+    int acc[8], bsel[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { acc[k] = 512; bsel[k] = 0; }
+    const int brow = 2 + (yf == 3 ? 1 : 0);
+#pragma unroll 1
+    for (int t = 0; t < 6; t++) {
+        int hs[8];
+        hrow8(at + (t - 2) * pitch - 2, hs, 0);
+        const int c = (t == 0 || t == 5) ? 1 : (t == 1 || t == 4) ? -5 : 20;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            acc[k] += c * hs[k];
+            if (t == brow) bsel[k] = hs[k] + 16;
+        }
+    }
+    const uint2 j = pack8shift(acc, 10);
+    if (xf == 2 && yf == 2) return j;
+    if (xf == 2) return avg8(j, pack8shift(bsel, 5));
+    int hv[8];
+    vcol8(at - 2 * pitch + (xf == 3 ? 1 : 0), pitch, hv, 16);
+    return avg8(j, pack8shift(hv, 5));
+}
+
+// ---- chroma: bilinear 1/8-pel (PredictChroma, reconstruct.c:415-475) ----------------------------------------
+// A chroma window row in shared memory is [strip 0: 8 Cb | 8 Cr][strip 1: 8 Cb | 8 Cr]; pA points at the 8-byte group of the
+// lane's plane that holds window column col0, sh = col0 & 7: five consecutive samples of the plane starting at col0
+__device__ __forceinline__ void chromaRow5(const uint8_t *pA, uint32_t sh, uint32_t &lo, uint32_t &hi) {
+    const uint2 A = *reinterpret_cast<const uint2 *>(pA), B = *reinterpret_cast<const uint2 *>(pA + 16);
+    const bool up = sh >= 4u;
+    const uint32_t w0 = up ? A.y : A.x, w1 = up ? B.x : A.y, w2 = up ? B.y : B.x, s = (sh & 3u) * 8u;
+    lo = __funnelshift_r(w0, w1, s);
+    hi = __funnelshift_r(w1, w2, s);
+}
+// four samples of plane cp: window columns cxo + lcx .. + 3, row lcy; the four weights times four pels are one dot product
+__device__ __forceinline__ uint32_t chromaPred4(const uint8_t *cbuf, int pitchC, int cxo, int cp, int lcx, int lcy, int cxf, int cyf) {
+    const int col0 = cxo + lcx;
+    const uint8_t *pA = cbuf + lcy * pitchC + (col0 >> 3) * 16 + cp * 8;
+    const uint32_t sh = (uint32_t)col0 & 7u;
+    uint32_t lo0, hi0;
+    chromaRow5(pA, sh, lo0, hi0);
+    if ((cxf | cyf) == 0) return lo0;
+    uint32_t lo1, hi1;
+    chromaRow5(pA + pitchC, sh, lo1, hi1);   // (with cyf == 0 this row may lie outside the box: it meets zero weights)
+    const int wts = ((8 - cxf) * (8 - cyf)) | ((cxf * (8 - cyf)) << 8) | (((8 - cxf) * cyf) << 16) | ((cxf * cyf) << 24);
+    const uint32_t s0 = __funnelshift_r(lo0, hi0, 24), s1 = __funnelshift_r(lo1, hi1, 24);
+    const int v0 = dp4aUS(__byte_perm(lo0, lo1, 0x5410), wts, 32) >> 6, v1 = dp4aUS(__byte_perm(lo0, lo1, 0x6521), wts, 32) >> 6;
+    const int v2 = dp4aUS(__byte_perm(lo0, lo1, 0x7632), wts, 32) >> 6, v3 = dp4aUS(__byte_perm(s0, s1, 0x5410), wts, 32) >> 6;
+    return (uint32_t)v0 | ((uint32_t)v1 << 8) | ((uint32_t)v2 << 16) | ((uint32_t)v3 << 24);
 }
 
 // ---- Intra4x4 sample prediction (intra_prediction.c:1493-1830, clause 8.3.1.2) -----------------------
@@ -275,7 +429,7 @@ __device__ __forceinline__ void mbResidual(const MbHead &h, const int16_t *coef,
 
 // this lane's residuals: luma row r8 cols c8..c8+7, chroma plane cp row cr cols cc..cc+3
 __device__ __forceinline__ void laneResidual(const int16_t (*res)[16], int lane, int *resY, int *resC) {
-    const int r8 = lane >> 1, cp = lane >> 4, cr = (lane >> 1) & 7;
+    const int r8 = lane >> 1, cp = (lane >> 1) & 1, cr = lane >> 2;
     const int by = r8 >> 2, ry = r8 & 3, bx = (lane & 1) * 2;
     const int16_t *ra = res[cRasterToBlk[by * 4 + bx]] + ry * 4;
     const int16_t *rb = res[cRasterToBlk[by * 4 + bx + 1]] + ry * 4;
@@ -286,358 +440,377 @@ __device__ __forceinline__ void laneResidual(const int16_t (*res)[16], int lane,
     for (int i = 0; i < 4; i++) resC[i] = rc[i];
 }
 
-// 8 consecutive bytes from an arbitrarily aligned shared-memory address
-__device__ __forceinline__ uint2 lds8(const uint8_t *p) {
-    const uint32_t a = smemAddr(p), sh = (a & 3u) * 8u;
-    const uint32_t *w = reinterpret_cast<const uint32_t *>(p - (a & 3u));
-    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
-    return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
-}
-__device__ __forceinline__ uint32_t lds4(const uint8_t *p) {
-    const uint32_t a = smemAddr(p), sh = (a & 3u) * 8u;
-    const uint32_t *w = reinterpret_cast<const uint32_t *>(p - (a & 3u));
-    return __funnelshift_r(w[0], w[1], sh);
-}
+// =====================================================================================================
+// pass A: every macroblock that does not look at the current picture -- inter-predicted ones, I_PCM, concealed copies.
+// One kernel, in the order the macroblocks lie in memory: a warp task ("chunk") is up to 32 vertically adjacent macroblocks
+// of one strip.  Lane l reads record l of the chunk and the warp sorts them by two ballots:
+//   copies  P_Skip / P_L0_16x16 without residual and with a zero vector (60 % of the fixture's macroblocks) and concealed
+//           copies: h264bsdPredictSamples degenerates to h264bsdFillBlock (reconstruct.c:1852) and h264bsdWriteOutputBlocks to
+//           a store.  In the strip layout that is 384 contiguous bytes from the same place of the reference frame, and
+//           neighbouring copies of a chunk continue each other: the warp moves all of them as one list of 16-byte units,
+//           four loads in flight per lane before the first store;
+//   inter   everything else with a vector: reference windows by TMA (one luma and one chroma box per partition, landing
+//           in shared memory as rasters), levels by cp.async.bulk on the same mbarrier, both for macroblock i + 1 while
+//           macroblock i is computed; residual by a 4-lanes-per-block transform with warp shuffles; 6-tap / bilinear
+//           filters on packed bytes (dp4a); add, clip, and one 256-byte + one 128-byte store per macroblock.
+// Copies wait on DRAM while inter macroblocks keep the issue slots busy -- in one kernel they overlap by themselves, and a
+// window's halo is in L2 because the neighbouring macroblocks, whatever their kind, are in flight at the same time.
+// =====================================================================================================
 
-
-// ---- 8-wide luma prediction for one lane (row y, columns x0..x0+7 of a 16x16 partition) --------------------
-constexpr int kTapsLo = 0x1414FB01;  // bytes (1, -5, 20, 20)
-constexpr int kTapsHi = 0x000001FB;  // bytes (-5, 1, 0, 0)
-
-// unclipped horizontal 6-tap sums for 8 outputs; rowp points at sample x0-2 of the row (13 samples are read)
-__device__ __forceinline__ void hrow8(const uint8_t *rowp, int *hs) {
-    const uint32_t a = smemAddr(rowp), sh0 = (a & 3u) * 8u;
-    const uint32_t *w = reinterpret_cast<const uint32_t *>(rowp - (a & 3u));
-    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
-    // aligned view: byte k of the row = byte (k + (a&3)) of (w0,w1,w2,w3)
-    const uint32_t v0 = __funnelshift_r(w0, w1, sh0), v1 = __funnelshift_r(w1, w2, sh0), v2 = __funnelshift_r(w2, w3, sh0), v3 = w3 >> sh0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        const uint32_t lo = (k & 3) == 0 ? (k == 0 ? v0 : v1) : __funnelshift_r(k < 4 ? v0 : v1, k < 4 ? v1 : v2, 8 * (k & 3));
-        const uint32_t hi = (k & 3) == 0 ? (k == 0 ? v1 : v2) : __funnelshift_r(k < 4 ? v1 : v2, k < 4 ? v2 : v3, 8 * (k & 3));
-        hs[k] = dp4aUS(hi, kTapsHi, dp4aUS(lo, kTapsLo, 0));
+// ---- residual of an inter macroblock: 4 lanes per 4x4 block, 8 blocks per round, coded blocks only ---------------------
+// h264bsdProcessBlock (transform.c:97-234) with the row transform inside a lane (lane r of a group owns row r of the block)
+// and the column transform across the group's four lanes by two shuffle exchanges; h264bsdProcessChromaDc (:359-401) by
+// lanes 16..23 first.  `cbuf` = the macroblock's levels in shared memory (b200_mb_rec layout: [chroma DC][coded blocks]).
+__device__ __forceinline__ void residualShfl(PassAWarpSmem &sm, const uint8_t *cbuf, uint32_t mask, int qpY, int qpC, int lane, uint32_t *errors) {
+    {   // every block that is not visited below has a zero residual
+        uint4 *z = reinterpret_cast<uint4 *>(&sm.resY[0][0]);   // resY and resC are contiguous: 96 x 16 bytes
+        const uint4 zero = make_uint4(0, 0, 0, 0);
+        z[lane] = zero; z[lane + 32] = zero; z[lane + 64] = zero;
     }
-}
-// unclipped vertical 6-tap sums for 8 outputs; colp points at sample (x0, y-2); rows are kLumaBoxW apart
-__device__ __forceinline__ void vcol8(const uint8_t *colp, int *vs) {
-    uint2 r[6];
-#pragma unroll
-    for (int t = 0; t < 6; t++) r[t] = lds8(colp + t * kLumaBoxW);
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        const int sel = k & 3;
-        const uint32_t a0 = k < 4 ? r[0].x : r[0].y, a1 = k < 4 ? r[1].x : r[1].y, a2 = k < 4 ? r[2].x : r[2].y;
-        const uint32_t a3 = k < 4 ? r[3].x : r[3].y, a4 = k < 4 ? r[4].x : r[4].y, a5 = k < 4 ? r[5].x : r[5].y;
-        // gather byte `sel` of four rows into one word
-        const uint32_t t01 = __byte_perm(a0, a1, sel | ((4 + sel) << 4));
-        const uint32_t t23 = __byte_perm(a2, a3, sel | ((4 + sel) << 4));
-        const uint32_t lo = __byte_perm(t01, t23, 0x5410);
-        const uint32_t hi = __byte_perm(a4, a5, sel | ((4 + sel) << 4)) & 0xFFFFu;
-        vs[k] = dp4aUS(hi, kTapsHi, dp4aUS(lo, kTapsLo, 0));
+    int dc = 0;
+    if ((mask & B200_CM_CHROMA_DC) && lane >= 16 && lane < 24) {
+        const int k = lane - 16;
+        dc = chromaDcPick(reinterpret_cast<const int16_t *>(cbuf) + (k >> 2) * 4, qpC, k & 3);
     }
-}
-// four values -> four bytes with unsigned saturation, element 0 in the low byte (I2IP.U8.S32.SAT, two instructions)
-// clip255((v + 16) >> 5) / clip255((v + 512) >> 10) of eight sums, packed
-__device__ __forceinline__ uint2 pack8shift(const int *v, int rnd, int sh) {
-    return make_uint2(pack4sat((v[0] + rnd) >> sh, (v[1] + rnd) >> sh, (v[2] + rnd) >> sh, (v[3] + rnd) >> sh),
-                      pack4sat((v[4] + rnd) >> sh, (v[5] + rnd) >> sh, (v[6] + rnd) >> sh, (v[7] + rnd) >> sh));
-}
-__device__ __forceinline__ uint2 avg8(uint2 a, uint2 b) { return make_uint2(__vavgu4(a.x, b.x), __vavgu4(a.y, b.y)); }
-
-// clause 8.4.2.2.1 for 8 horizontally adjacent samples: `win` points at window sample (xInt-2, yInt-2) (see W_);
-// (x0, y) = position of the first sample inside the partition; the same arithmetic as lumaQpel, 8 at a time, on packed
-// bytes: the rounded averages (a + b + 1) >> 1 are per-byte averages of clipped values
-__device__ __forceinline__ uint2 lumaQpel8(const uint8_t *win, int x0, int y, int xf, int yf) {
-    const bool jfam = (xf == 2 || yf == 2) && xf != 0 && yf != 0;
-    if (!jfam) {
-        const bool useH = xf != 0, useV = yf != 0;
-        uint2 b = make_uint2(0, 0), h = make_uint2(0, 0);
-        if (useH) {
-            int t[8];
-            hrow8(win + (y + 2 + (yf == 3 ? 1 : 0)) * kLumaBoxW + x0, t);
-            b = pack8shift(t, 16, 5);
-        }
-        if (useV) {
-            int t[8];
-            vcol8(win + y * kLumaBoxW + x0 + 2 + (xf == 3 ? 1 : 0), t);
-            h = pack8shift(t, 16, 5);
-        }
-        if (useH && useV) return avg8(b, h);
-        if (useH) return xf == 2 ? b : avg8(b, lds8(win + (y + 2) * kLumaBoxW + x0 + 2 + (xf >> 1)));
-        return yf == 2 ? h : avg8(h, lds8(win + (y + 2 + (yf >> 1)) * kLumaBoxW + x0 + 2));
-    }
-    int acc[8], bsel[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) { acc[k] = 0; bsel[k] = 0; }
-    const int brow = 2 + (yf == 3 ? 1 : 0);
+    if (lane >= 16 && lane < 24) sm.dcC[lane - 16] = dc;
+    const uint32_t coded = mask & 0xFFFFFFu;
+    const uint32_t act = coded | (__ballot_sync(0xffffffffu, dc != 0) & 0xFF0000u);
+    if ((act >> lane) & 1u) sm.list[__popc(act & ((1u << lane) - 1u))] = (uint8_t)lane;
+    __syncwarp();
+    const int nAct = __popc(act), nDc = (int)((mask >> 25) & 1u);
+    const int r = lane & 3, g4 = lane >> 2;
+    const uint32_t zz = r == 0 ? 0x6510u : r == 1 ? 0xC742u : r == 2 ? 0xDB83u : 0xFEA9u;   // zig-zag positions of raster row r
+    const int orow = ((r & 1) << 1) | (r >> 1);   // the row this lane holds after the column transform
 #pragma unroll 1
-    for (int t = 0; t < 6; t++) {
-        int hs[8];
-        hrow8(win + (y + t) * kLumaBoxW + x0, hs);
-        const int c = (t == 0 || t == 5) ? 1 : (t == 1 || t == 4) ? -5 : 20;
+    for (int base = 0; base < nAct; base += 8) {
+        const bool valid = base + g4 < nAct;
+        const int b = valid ? sm.list[base + g4] : 0;
+        const bool isCoded = valid && ((coded >> b) & 1u);
+        const int qp = b < 16 ? qpY : qpC;
+        const int qpDiv = qp / 6, qpMod = qp - 6 * qpDiv;
+        const int sA = levelScale(qpMod, r & 1) << qpDiv, sB = levelScale(qpMod, 1 + (r & 1)) << qpDiv;
+        int d0 = 0, d1 = 0, d2 = 0, d3 = 0;
+        if (isCoded) {
+            const int16_t *lev = reinterpret_cast<const int16_t *>(cbuf) + (nDc + __popc(coded & ((1u << b) - 1u))) * 16;
+            d0 = lev[zz & 15u] * sA; d1 = lev[(zz >> 4) & 15u] * sB; d2 = lev[(zz >> 8) & 15u] * sA; d3 = lev[zz >> 12] * sB;
+        }
+        if (r == 0) {
+            if (b >= 16) d0 = sm.dcC[b - 16];   // chroma: the DC comes from the 2x2 transform (macroblock_layer.c:1371-1374)
+            d0 += 32;                           // the DC term reaches all sixteen outputs with weight 1: rounding for the final >> 6
+        }
+        // row transform
+        const int t0 = d0 + d2, t1 = d0 - d2, t2 = (d1 >> 1) - d3, t3 = d1 + (d3 >> 1);
+        int e[4] = {t0 + t3, t1 + t2, t1 - t2, t0 - t3};
+        // column transform: rows 0/2 and 1/3 meet first (f0 = E0 + E2 in lane 0, f1 = E0 - E2 in lane 2, f2 = (E1 >> 1) - E3 in
+        // lane 1, f3 = E1 + (E3 >> 1) in lane 3), then 0/3 and 1/2 (rows 0 and 3 out of lanes 0 and 3, rows 1 and 2 out of lanes 2 and 1)
+        int o[4];
+        bool bad = false;
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            acc[k] += c * hs[k];
-            if (t == brow) bsel[k] = hs[k];
+        for (int c = 0; c < 4; c++) {
+            const int pv = __shfl_xor_sync(0xffffffffu, e[c], 2);
+            const int h = (r & 1) ? (e[c] >> 1) : e[c];
+            const int f = (r == 2 ? -h : h) + (r == 1 ? -pv : pv);
+            const int q = __shfl_xor_sync(0xffffffffu, f, 3);
+            o[c] = ((r & 1) ? q - f : f + q) >> 6;
+            bad |= (unsigned)(o[c] + 512) > 1023u;
+        }
+        if (valid) {
+            if (bad) atomicAdd(errors, 1u);
+            int32_t *dst;
+            if (b < 16) dst = &sm.resY[(((b >> 1) & 1) + ((b >> 3) & 1) * 2) * 4 + orow][((b & 1) + ((b >> 2) & 1) * 2) * 4];
+            else dst = &sm.resC[(b - 16) >> 2][((b >> 1) & 1) * 4 + orow][(b & 1) * 4];
+            *reinterpret_cast<uint4 *>(dst) = make_uint4((uint32_t)o[0], (uint32_t)o[1], (uint32_t)o[2], (uint32_t)o[3]);
         }
     }
-    const uint2 j = pack8shift(acc, 512, 10);
-    if (xf == 2 && yf == 2) return j;
-    if (xf == 2) return avg8(j, pack8shift(bsel, 16, 5));
-    int hv[8];
-    vcol8(win + y * kLumaBoxW + x0 + 2 + (xf == 3 ? 1 : 0), hv);
-    return avg8(j, pack8shift(hv, 16, 5));
-}
-
-// =====================================================================================================
-// pass A: inter-predicted (and I_PCM) macroblocks.  They read only finished reference frames, so there
-// is no ordering between them: plain grid, blockIdx.y = stream, a warp owns kChunkA consecutive entries
-// of the stream's raster-ordered list and prefetches the next entry's reference window by TMA while it
-// works on the current one.
-// =====================================================================================================
-struct InterInfo {
-    uint32_t mb;
-    MbHead h;
-    bool single;     // one 16x16 partition (P_Skip / P_L0_16x16): window prefetched
-    int mvx, mvy;
-    int ox, cox;     // clamped window origins (bordered-plane coordinates), luma / chroma
-};
-
-__device__ __forceinline__ void issueWindow(InterWarpSmem &sm, int buf, const PoolGeom &g, const CUtensorMap *lumaMap, const CUtensorMap *chromaMap,
-                                            int xInt, int yInt, int cxInt, int cyInt, uint32_t refFrame, int lane, int *oxOut, int *coxOut) {
-    // clamp the window origin into the bordered plane: a window wholly outside the picture on an axis equals the
-    // window at the clamped origin because the border is a replication; the box starts 16-byte aligned
-    const int ox = clip3(-kPadY, g.W + kPadY - kLumaWin, xInt - 2) + kPadY;
-    const int oy = clip3(-kPadY, g.H + kPadY - kLumaWin, yInt - 2) + kPadY;
-    const int cox = clip3(-kPadC, g.W / 2 + kPadC - kChromaWin, cxInt) + kPadC;
-    const int coy = clip3(-kPadC, g.H / 2 + kPadC - kChromaWin, cyInt) + kPadC;
-    if (lane == 0) {
-        fenceProxyAsync();
-        mbarExpectTx(&sm.mbar[buf], kLumaBoxW * kLumaBoxH + 2 * kChromaBoxW * kChromaBoxH);
-        tmaLoad3d(sm.lumaWin[buf], lumaMap, ox & ~15, oy, (int)refFrame, &sm.mbar[buf]);
-        tmaLoad4d(sm.chromaWin[buf], chromaMap, cox & ~15, coy, 0, (int)refFrame, &sm.mbar[buf]);
-    }
-    *oxOut = ox;
-    *coxOut = cox;
+    __syncwarp();
 }
 
 __global__ void __launch_bounds__(kReconWarps * 32, 3)
-reconInterKernel(const ReconParams p, const __grid_constant__ CUtensorMap lumaMap, const __grid_constant__ CUtensorMap chromaMap) {
-    extern __shared__ __align__(128) uint8_t interSmemRaw[];   // kReconWarps x InterWarpSmem (more than the 48 KB static limit)
-    InterWarpSmem *smemAll = reinterpret_cast<InterWarpSmem *>(interSmemRaw);
+passAKernel(const ReconParams p, const __grid_constant__ PassAMaps maps) {
+    extern __shared__ __align__(128) uint8_t interSmemRaw[];   // kReconWarps x PassAWarpSmem (more than the 48 KB static limit)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const PoolGeom &g = p.g;
-    InterWarpSmem &sm = smemAll[warp];
+    PassAWarpSmem &sm = reinterpret_cast<PassAWarpSmem *>(interSmemRaw)[warp];
     if (lane == 0) {
         mbarInit(&sm.mbar[0], 1);
         mbarInit(&sm.mbar[1], 1);
-        mbarInit(&sm.mbar[2], 1);
         fenceMbarInit();
     }
     __syncwarp();
-    uint32_t phaseBits = 0;   // bit b = phase parity of window buffer b
-    // persistent CTAs striding over virtual CTAs: v -> (stream, chunk of the stream's pass-A list); consecutive
-    // virtual CTAs belong to the same stream, so neighbouring macroblocks are in flight together (L2 locality)
-    for (uint32_t v = blockIdx.x; v < p.virtualCtasA; v += gridDim.x) {
-    const uint32_t s = v / p.chunksA, chunk = v - s * p.chunksA;
-    const StreamJob job = p.jobs[s];
-    const uint32_t l0 = (chunk * kReconWarps + warp) * p.chunkA;   // index into the stream's pass-A entries that are not plain copies
-    if (l0 >= job.nA) continue;
-    const int n = min(p.chunkA, job.nA - l0);
-    const uint32_t e0 = 2u * job.nR + job.nC + l0;               // the plain copies went to reconCopyKernel
-    const uint32_t frameBase = s * (uint32_t)g.numSlots;
-    uint8_t *cur = framePtr(p.pool, g, frameBase + job.curSlot);
+    uint32_t phaseBits = 0;   // bit b = phase parity of mbarrier b
+    const uint32_t nWarps = gridDim.x * kReconWarps;
+    const uint32_t chunksPerStream = p.chunksPerCol * (uint32_t)g.widthMbs;
+    // this lane's spans inside a macroblock: 8 luma samples (row r8, columns c8..c8+7 = bytes 8 lane.. of the 256), 4 chroma
+    // samples (plane cp, row cr, columns cc..cc+3 = bytes 4 lane.. of the 128)
     const int r8 = lane >> 1, c8 = (lane & 1) * 8;
-    const int cp = lane >> 4, cr = (lane >> 1) & 7, cc = (lane & 1) * 4;
+    const int cr = lane >> 2, cp = (lane >> 1) & 1, cc = (lane & 1) * 4;
 
-    // the chunk's records are fetched by the first n lanes in parallel (one dependent-load chain per chunk, not per MB).
-    // (Barrier first: a lane may still be reading the previous chunk's records -- an I_PCM macroblock ends its turn without one.)
-    __syncwarp();
-    if (lane < n) {
-        const uint32_t mb = __ldg(job.order + e0 + lane);
-        const uint32_t *rw = reinterpret_cast<const uint32_t *>(job.recs + mb);
-        const uint4 hw = __ldg(reinterpret_cast<const uint4 *>(rw));
-        const uint32_t refSlots = __ldg(rw + 4), mv0 = __ldg(rw + 8);
-        uint32_t *m = sm.meta[lane];
-        m[0] = hw.x; m[1] = hw.y; m[2] = hw.z; m[3] = hw.w; m[4] = refSlots; m[5] = mv0; m[6] = mb;
-    }
-    __syncwarp();
-    auto prepare = [&](int i, int buf) -> InterInfo {
-        InterInfo it;
-        const uint32_t *m = sm.meta[i];
-        it.mb = m[6];
-        it.h.mbType = m[0] & 0xFF; it.h.qpY = (m[0] >> 8) & 0xFF; it.h.qpC = (m[0] >> 16) & 0xFF; it.h.flags = m[0] >> 24;
-        it.h.mask = m[1]; it.h.coefIndex = m[2];
-        it.single = it.h.mbType <= B200_MB_P_16x16;
-        it.mvx = it.mvy = 0; it.ox = it.cox = 0;
-        if (it.single) {
-            const uint32_t mvv = m[5], refSlots = m[4];
-            it.mvx = (int)(int16_t)(mvv & 0xFFFF); it.mvy = (int)(int16_t)(mvv >> 16);
-            const int mby = mbRowOf(it.mb, g), mbx = (int)(it.mb - (uint32_t)mby * g.widthMbs);
-            issueWindow(sm, buf, g, &lumaMap, &chromaMap, mbx * 16 + (it.mvx >> 2), mby * 16 + (it.mvy >> 2),
-                        mbx * 8 + (it.mvx >> 3), mby * 8 + (it.mvy >> 3), frameBase + (refSlots & 0xFF), lane, &it.ox, &it.cox);
+    // a warp's first chunk is its own number, the following ones come from a ticket counter (asked for one chunk ahead)
+    uint32_t chunk = blockIdx.x * kReconWarps + warp;
+    while (chunk < p.totalChunks) {
+        uint32_t nextChunk = 0;
+        if (lane == 0) nextChunk = atomicAdd(p.ticketA, 1u) + nWarps;
+        const uint32_t s = chunk / chunksPerStream, c2 = chunk - s * chunksPerStream;
+        const int mbx = (int)(c2 / p.chunksPerCol), row0 = (int)((c2 - (uint32_t)mbx * p.chunksPerCol) * p.chunkRows);
+        const int n = min((int)p.chunkRows, g.heightMbs - row0);
+        const StreamJob job = p.jobs[s];
+        const uint32_t frameBase = s * (uint32_t)g.numSlots;
+        uint8_t *cur = framePtr(p.pool, g, frameBase + job.curSlot);
+        uint8_t *lbase = mbLuma(cur, g, mbx, row0), *cbase = mbChroma(cur, g, mbx, row0);   // macroblock l of the chunk: + 256 l / + 128 l
+
+        // lane l: head, reference slots, wait mask and first vector of record l
+        uint32_t mW0 = 0, mMask = 0, mCoef = 0, mW3 = 0, mRef = 0, mMv = 0;
+        bool isCopy = false, isInter = false;
+        const b200_mb_rec *rec0 = job.recs + (size_t)row0 * g.widthMbs + mbx;   // record of macroblock l: + l * widthMbs
+        if (lane < n) {
+            const uint32_t *rw = reinterpret_cast<const uint32_t *>(rec0 + (size_t)lane * g.widthMbs);
+            const uint4 hw = __ldg(reinterpret_cast<const uint4 *>(rw));
+            mRef = __ldg(rw + 4);
+            const uint32_t w7 = __ldg(rw + 7);
+            mMv = __ldg(rw + 8);
+            mW0 = hw.x; mMask = hw.y; mCoef = hw.z; mW3 = hw.w;
+            const uint32_t type = mW0 & 0xFFu;
+            // a concealed macroblock carries the state the filter wants to see (Intra4x4); its pels are a copy of the reference
+            // picture (no neighbours to wait for) or come from concealKernel (h264bsd_b200_tape.h)
+            const bool concealed = ((mW0 >> 24) & B200_MBF_CONCEALED) && type == B200_MB_I_4x4;
+            if (concealed) isCopy = (w7 & 0xFFu) == 0;
+            else if (type <= B200_MB_P_16x16 && mMask == 0 && mMv == 0) isCopy = true;
+            else isInter = type <= B200_MB_P_8x8REF0 || type == B200_MB_I_PCM;
         }
-        return it;
-    };
+        const uint32_t copyMask = __ballot_sync(0xffffffffu, isCopy);
+        uint32_t interMask = __ballot_sync(0xffffffffu, isInter);
 
-    InterInfo nxt = prepare(0, 0);
-#pragma unroll 1
-    for (int i = 0; i < n; i++) {
-        const int buf = i & 1;
-        const InterInfo it = nxt;
-        if (i + 1 < n) nxt = prepare(i + 1, buf ^ 1);   // the other buffer's previous user finished before this point
-        const MbHead &h = it.h;
-        const uint32_t mb = it.mb;
-        const int mby = mbRowOf(mb, g), mbx = (int)(mb - (uint32_t)mby * g.widthMbs);
-        const b200_mb_rec *rec = job.recs + mb;
-        const int16_t *coef = job.coefs + (size_t)h.coefIndex * 16;
-        uint8_t *dstY = lumaAt(cur, g, mbx * 16 + c8, mby * 16 + r8);
-        uint8_t *dstC = chromaAt(cur, g, cp, mbx * 8 + cc, mby * 8 + cr);
-
-        if (h.mbType == B200_MB_I_PCM) {
-            // h264bsdWriteMacroblock (image.c:81-144): 384 raw bytes
-            const uint8_t *src = reinterpret_cast<const uint8_t *>(coef);
-            *reinterpret_cast<uint2 *>(dstY) = __ldg(reinterpret_cast<const uint2 *>(src + r8 * 16 + c8));
-            *reinterpret_cast<uint32_t *>(dstC) = __ldg(reinterpret_cast<const uint32_t *>(src + 256 + cp * 64 + cr * 8 + cc));
-            continue;
-        }
-        if (h.mask) mbResidual(h, coef, sm.res, lane, p.errors);   // into shared memory; read back after the prediction
-        uint2 pv = make_uint2(0, 0);   // this lane's 8 luma prediction samples
-        uint32_t pc = 0;               // and 4 chroma prediction samples
-        // Partitions that are at least 8 wide (16x16, 16x8, 8x16, 8x8 sub-macroblocks) share one code path: every lane's
-        // 8-sample luma span and 4-sample chroma span lie inside ONE partition, so the lane only has to pick that
-        // partition's window, vector and origin.  Two partitions are staged at a time (windows `buf` and 2).
-        uint32_t subTypes = 0;
-        if (h.mbType >= B200_MB_P_8x8) subTypes = (__ldg(reinterpret_cast<const uint32_t *>(rec) + 3) >> 24) & 0xFF;
-        const bool wide = h.mbType <= B200_MB_P_8x16 || subTypes == 0;
-        if (wide) {
-            const int rounds = it.single ? 1 : (h.mbType >= B200_MB_P_8x8 ? 2 : 1);
-#pragma unroll 1
-            for (int rd = 0; rd < rounds; rd++) {
-                // per lane: window buffer, window origins, vector, position of the lane's spans inside the partition
-                int bufL = buf, oxL = it.ox, mvxL = it.mvx, mvyL = it.mvy, lx = c8, ly = r8;
-                int bufC = buf, coxC = it.cox, mvxC = it.mvx, mvyC = it.mvy, lcx = cc, lcy = cr;
-                bool actL = true, actC = true;
-                if (it.single) {
-                    mbarWait(&sm.mbar[buf], (phaseBits >> buf) & 1u);
-                    phaseBits ^= 1u << buf;
-                } else {
-                    // partitions A and B of this round (inter_prediction.c:361-482): first block, origin in pels
-                    int blkA, blkB, pxB, pyA, pyB;
-                    if (h.mbType == B200_MB_P_16x8) { blkA = 0; blkB = 8; pxB = 0; pyA = 0; pyB = 8; }
-                    else if (h.mbType == B200_MB_P_8x16) { blkA = 0; blkB = 4; pxB = 8; pyA = 0; pyB = 0; }
-                    else { blkA = 8 * rd; blkB = 8 * rd + 4; pxB = 8; pyA = pyB = 8 * rd; }
-                    const uint32_t *rw = reinterpret_cast<const uint32_t *>(rec);
-                    const uint32_t refSlots = __ldg(rw + 4), mvA = __ldg(rw + 8 + blkA), mvB = __ldg(rw + 8 + blkB);
-                    const int ax = (int)(int16_t)(mvA & 0xFFFF), ay = (int)(int16_t)(mvA >> 16);
-                    const int bx = (int)(int16_t)(mvB & 0xFFFF), by = (int)(int16_t)(mvB >> 16);
-                    int oxA, coxA, oxB, coxB;
-                    issueWindow(sm, buf, g, &lumaMap, &chromaMap, mbx * 16 + (ax >> 2), mby * 16 + pyA + (ay >> 2),
-                                mbx * 8 + (ax >> 3), mby * 8 + (pyA >> 1) + (ay >> 3), frameBase + ((refSlots >> (8 * (blkA >> 2))) & 0xFF), lane, &oxA, &coxA);
-                    issueWindow(sm, 2, g, &lumaMap, &chromaMap, mbx * 16 + pxB + (bx >> 2), mby * 16 + pyB + (by >> 2),
-                                mbx * 8 + (pxB >> 1) + (bx >> 3), mby * 8 + (pyB >> 1) + (by >> 3), frameBase + ((refSlots >> (8 * (blkB >> 2))) & 0xFF), lane, &oxB, &coxB);
-                    const bool inBL = h.mbType == B200_MB_P_16x8 ? r8 >= 8 : c8 == 8;
-                    const bool inBC = h.mbType == B200_MB_P_16x8 ? cr >= 4 : cc == 4;
-                    if (h.mbType >= B200_MB_P_8x8) { actL = (r8 >> 3) == rd; actC = (cr >> 2) == rd; }
-                    bufL = inBL ? 2 : buf; oxL = inBL ? oxB : oxA; mvxL = inBL ? bx : ax; mvyL = inBL ? by : ay;
-                    lx = c8 - (inBL ? pxB : 0); ly = r8 - (inBL ? pyB : pyA);
-                    bufC = inBC ? 2 : buf; coxC = inBC ? coxB : coxA; mvxC = inBC ? bx : ax; mvyC = inBC ? by : ay;
-                    lcx = cc - (inBC ? (pxB >> 1) : 0); lcy = cr - ((inBC ? pyB : pyA) >> 1);
-                    mbarWait(&sm.mbar[buf], (phaseBits >> buf) & 1u);
-                    phaseBits ^= 1u << buf;
-                    mbarWait(&sm.mbar[2], (phaseBits >> 2) & 1u);
-                    phaseBits ^= 4u;
-                }
-                if (actL) {
-                    const int xf = mvxL & 3, yf = mvyL & 3;
-                    const uint8_t *win = sm.lumaWin[bufL] + (oxL & 15);
-                    if ((xf | yf) == 0) pv = lds8(win + (ly + 2) * kLumaBoxW + lx + 2);   // h264bsdFillBlock copy (reconstruct.c:1852)
-                    else pv = lumaQpel8(win, lx, ly, xf, yf);
-                }
-                if (actC) {
-                    const int cxf = mvxC & 7, cyf = mvyC & 7;
-                    const uint8_t *cw = sm.chromaWin[bufC] + cp * (kChromaBoxW * kChromaBoxH) + lcy * kChromaBoxW + lcx + (coxC & 15);
-                    if ((cxf | cyf) == 0) {
-                        pc = lds4(cw);
-                    } else {
-                        // PredictChroma (reconstruct.c:415-475)
-                        const uint2 ra = lds8(cw), rb = lds8(cw + kChromaBoxW);
-                        const int w00 = (8 - cxf) * (8 - cyf), w01 = cxf * (8 - cyf), w10 = (8 - cxf) * cyf, w11 = cxf * cyf;
-                        pc = 0;
-#pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            const int A = (ra.x >> (8 * k)) & 0xFF, B = k < 3 ? (ra.x >> (8 * k + 8)) & 0xFF : ra.y & 0xFF;
-                            const int Cc = (rb.x >> (8 * k)) & 0xFF, D = k < 3 ? (rb.x >> (8 * k + 8)) & 0xFF : rb.y & 0xFF;
-                            pc |= (uint32_t)((w00 * A + w01 * B + w10 * Cc + w11 * D + 32) >> 6) << (8 * k);
-                        }
-                    }
-                }
-                if (rd + 1 < rounds) __syncwarp();   // the windows are overwritten by the next round's loads
+        // ---- what is staged for the macroblock whose turn comes next ------------------------------------------------
+        uint32_t nW0 = 0, nMask = 0, nW3 = 0, nRef = 0, nMv = 0, nGeom = 0;
+        int nL = 0;
+        bool nArmed = false;
+        // window of a partition at picture position (px, py), size w x h, vector (mvx, mvy): clamp the origin into the bordered
+        // plane (a window wholly outside the picture on an axis equals the window at the clamped origin because the border is a
+        // replication), pick the boxes, and have lane 0 issue the loads.  Returns xo | nx << 4 | cxo << 8 | nxC << 12.
+        auto issueWindow = [&](int buf, int px, int py, int w, int h, int mvx, int mvy, uint32_t refFrame, uint32_t extraBytes,
+                               const void *extraSrc) -> uint32_t {
+            const int xf = mvx & 3, yf = mvy & 3, nc = w + (xf ? 5 : 0), nr = h + (yf ? 5 : 0);
+            const int x0 = clip3(-kPadY, g.W + kPadY - nc, px + (mvx >> 2) - (xf ? 2 : 0)) + kPadY;
+            const int y0 = clip3(-kPadY, g.H + kPadY - nr, py + (mvy >> 2) - (yf ? 2 : 0)) + kPadY;
+            const int xo = x0 & 15, nx = (xo + nc + 15) >> 4;
+            const int cxf = mvx & 7, cyf = mvy & 7, ncC = (w >> 1) + (cxf ? 1 : 0), nrC = (h >> 1) + (cyf ? 1 : 0);
+            const int cx0 = clip3(-kPadC, g.W / 2 + kPadC - ncC, (px >> 1) + (mvx >> 3)) + kPadC;
+            const int cy0 = clip3(-kPadC, g.H / 2 + kPadC - nrC, (py >> 1) + (mvy >> 3)) + kPadC;
+            const int cxo = cx0 & 7, nxC = (cxo + ncC + 7) >> 3;
+            if (lane == 0) {
+                fenceProxyAsync();
+                mbarExpectTx(&sm.mbar[buf], (uint32_t)(16 * nx * (yf ? 21 : 16) + 16 * nxC * (cyf ? 9 : 8)) + extraBytes);
+                tmaLoad4d(sm.luma[buf], &maps.luma[nx - 1][yf ? 1 : 0], 0, x0 >> 4, y0, (int)refFrame, &sm.mbar[buf]);
+                tmaLoad4d(sm.chroma[buf], &maps.chroma[nxC - 1][cyf ? 1 : 0], 0, cx0 >> 3, cy0, (int)refFrame, &sm.mbar[buf]);
+                if (extraBytes) bulkLoad(sm.coef[buf], extraSrc, extraBytes, &sm.mbar[buf]);
             }
-        } else {
-            // sub-macroblocks with 8x4 / 4x8 / 4x4 partitions: one window per partition, sample by sample
-            const uint32_t refSlots = __ldg(reinterpret_cast<const uint32_t *>(rec) + 4);
-            const uint32_t *mvw = reinterpret_cast<const uint32_t *>(rec) + 8;
+            return (uint32_t)xo | ((uint32_t)nx << 4) | ((uint32_t)cxo << 8) | ((uint32_t)nxC << 12);
+        };
+        // stage macroblock l of the chunk into buffer `buf`: its levels always, its windows when it has one partition
+        auto prepare = [&](int l, int buf) {
+            nL = l;
+            nW0 = __shfl_sync(0xffffffffu, mW0, l); nMask = __shfl_sync(0xffffffffu, mMask, l);
+            nW3 = __shfl_sync(0xffffffffu, mW3, l); nRef = __shfl_sync(0xffffffffu, mRef, l);
+            nMv = __shfl_sync(0xffffffffu, mMv, l);
+            const uint32_t coefIndex = __shfl_sync(0xffffffffu, mCoef, l);
+            const uint32_t type = nW0 & 0xFFu;
+            const uint32_t coefBytes = type == B200_MB_I_PCM ? 384u : 32u * (uint32_t)__popc(nMask & 0x3FFFFFFu);
+            const void *coefSrc = job.coefs + (size_t)coefIndex * 16;
+            nArmed = true;
+            if (type <= B200_MB_P_16x16) {
+                nGeom = issueWindow(buf, mbx * 16, (row0 + l) * 16, 16, 16, (int)(int16_t)(nMv & 0xFFFFu), (int)(int16_t)(nMv >> 16),
+                                    frameBase + (nRef & 0xFFu), coefBytes, coefSrc);
+            } else if (coefBytes) {
+                if (lane == 0) {
+                    fenceProxyAsync();
+                    mbarExpectTx(&sm.mbar[buf], coefBytes);
+                    bulkLoad(sm.coef[buf], coefSrc, coefBytes, &sm.mbar[buf]);
+                }
+            } else {
+                nArmed = false;
+            }
+        };
+        if (interMask) prepare(__ffs(interMask) - 1, 0);
+
+        // ---- copies ---------------------------------------------------------------------------------------------------
+        if (copyMask) {
+            if (isCopy) sm.list[__popc(copyMask & ((1u << lane) - 1u))] = (uint8_t)lane;
+            __syncwarp();
+            const uint32_t units = 24u * (uint32_t)__popc(copyMask);   // 16 luma + 8 chroma 16-byte units per macroblock
+            const long long stride = (long long)g.frameStride;
 #pragma unroll 1
-            for (int pi = 0; pi < 16; pi++) {
-                int pw, ph;
-                const int blk = pi;
-                const int sub = (subTypes >> (2 * (pi >> 2))) & 3, j = pi & 3;
-                if (sub == 0) { if (j) continue; pw = 8; ph = 8; }
-                else if (sub == 1) { if (j & 1) continue; pw = 8; ph = 4; }
-                else if (sub == 2) { if (j & 2) continue; pw = 4; ph = 8; }
-                else { pw = 4; ph = 4; }
-                const int px = cBlkX[blk] * 4, py = cBlkY[blk] * 4;
-                const uint32_t mvv = __ldg(mvw + blk);
-                const int mvx = (int)(int16_t)(mvv & 0xFFFF), mvy = (int)(int16_t)(mvv >> 16);
-                const uint32_t refFrame = frameBase + ((refSlots >> (8 * (blk >> 2))) & 0xFF);
-                int ox, cox;
-                issueWindow(sm, buf, g, &lumaMap, &chromaMap, mbx * 16 + px + (mvx >> 2), mby * 16 + py + (mvy >> 2),
-                            ((mbx * 16 + px) >> 1) + (mvx >> 3), ((mby * 16 + py) >> 1) + (mvy >> 3), refFrame, lane, &ox, &cox);
+            for (uint32_t u0 = 0; u0 < units; u0 += 128u) {
+                uint4 v[4];
+                uint8_t *dst[4];
+                bool ok[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t u = u0 + 32u * j + lane;
+                    ok[j] = u < units;
+                    const uint32_t q = ok[j] ? (u * 2731u) >> 16 : 0u, w = u - 24u * q;   // u / 24, u % 24 (u < 768)
+                    const uint32_t e = sm.list[q];
+                    const uint32_t slot = __shfl_sync(0xffffffffu, mRef, (int)e) & 0xFFu;
+                    dst[j] = w < 16u ? lbase + e * 256u + w * 16u : cbase + e * 128u + (w - 16u) * 16u;
+                    if (ok[j]) v[j] = __ldg(reinterpret_cast<const uint4 *>(dst[j] + ((long long)slot - (long long)job.curSlot) * stride));
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (ok[j]) *reinterpret_cast<uint4 *>(dst[j]) = v[j];
+            }
+            __syncwarp();   // the list is used again by the residual
+        }
+
+        // ---- inter macroblocks, one after the other -------------------------------------------------------------------------
+        int it = 0;
+#pragma unroll 1
+        while (interMask) {
+            interMask &= interMask - 1;
+            const int buf = it & 1;
+            it++;
+            const int l = nL;
+            const uint32_t w0 = nW0, mask = nMask, w3 = nW3, refSlots = nRef, mvv = nMv, geom = nGeom;
+            const bool armed = nArmed;
+            const uint32_t type = w0 & 0xFFu;
+            const int qpY = (w0 >> 8) & 0xFF, qpC = (w0 >> 16) & 0xFF;
+            const bool single = type <= B200_MB_P_16x16;
+            // one partition: the next macroblock is staged now, while this one is computed; several partitions: both window
+            // buffers are needed for this macroblock, the next one is staged when it is through
+            if (single && interMask) prepare(__ffs(interMask) - 1, buf ^ 1);
+            if (armed) {
                 mbarWait(&sm.mbar[buf], (phaseBits >> buf) & 1u);
                 phaseBits ^= 1u << buf;
-                const int xf = mvx & 3, yf = mvy & 3;
-                const int lw = 31 - __clz(pw);
-#pragma unroll 1
-                for (int q = lane; q < pw * ph; q += 32) {
-                    const int x = q & (pw - 1), y = q >> lw;
-                    sm.pred[(py + y) * 16 + px + x] = (uint8_t)lumaQpel(sm.lumaWin[buf] + (ox & 15), x, y, xf, yf);
-                }
-                const int cw = pw >> 1, chh = ph >> 1, ncp = cw * chh, lcw = lw - 1;
-                const int cxf = mvx & 7, cyf = mvy & 7;
-#pragma unroll 1
-                for (int q = lane; q < 2 * ncp; q += 32) {
-                    const int pl = q >= ncp, qq = q - pl * ncp;
-                    const int x = qq & (cw - 1), y = qq >> lcw;
-                    const uint8_t *wp = sm.chromaWin[buf] + pl * (kChromaBoxW * kChromaBoxH) + y * kChromaBoxW + x + (cox & 15);
-                    const int A = wp[0], B = wp[1], Cc = wp[kChromaBoxW], D = wp[kChromaBoxW + 1];
-                    sm.pred[256 + pl * 64 + ((py >> 1) + y) * 8 + (px >> 1) + x] =
-                        (uint8_t)(((8 - cxf) * (8 - cyf) * A + cxf * (8 - cyf) * B + (8 - cxf) * cyf * Cc + cxf * cyf * D + 32) >> 6);
-                }
-                __syncwarp();
             }
-            pv = *reinterpret_cast<const uint2 *>(sm.pred + r8 * 16 + c8);
-            pc = *reinterpret_cast<const uint32_t *>(sm.pred + 256 + cp * 64 + cr * 8 + cc);
+            uint8_t *dstY = lbase + l * 256 + lane * 8, *dstC = cbase + l * 128 + lane * 4;
+            if (type == B200_MB_I_PCM) {
+                // h264bsdWriteMacroblock (image.c:81-144): 384 raw bytes, 256 Y then 64 Cb then 64 Cr
+                const uint8_t *src = sm.coef[buf];
+                *reinterpret_cast<uint2 *>(dstY) = *reinterpret_cast<const uint2 *>(src + lane * 8);
+                *reinterpret_cast<uint32_t *>(dstC) = *reinterpret_cast<const uint32_t *>(src + 256 + cp * 64 + cr * 8 + cc);
+                __syncwarp();
+                if (interMask) prepare(__ffs(interMask) - 1, buf ^ 1);
+                continue;
+            }
+            if (mask) residualShfl(sm, sm.coef[buf], mask, qpY, qpC, lane, p.errors);
+            uint2 pv = make_uint2(0, 0);   // this lane's 8 luma prediction samples
+            uint32_t pc = 0;               // and 4 chroma prediction samples
+            const int mby = row0 + l;
+            if (single) {
+                const int mvx = (int)(int16_t)(mvv & 0xFFFFu), mvy = (int)(int16_t)(mvv >> 16);
+                const int xf = mvx & 3, yf = mvy & 3;
+                const int pitch = (int)((geom >> 4) & 3u) * 16, pitchC = (int)((geom >> 12) & 3u) * 16;
+                const uint8_t *G0 = sm.luma[buf] + (geom & 15u) + (yf ? 2 * pitch : 0) + (xf ? 2 : 0);
+                pv = lumaQpel8(G0, pitch, c8, r8, xf, yf);
+                pc = chromaPred4(sm.chroma[buf], pitchC, (int)((geom >> 8) & 7u), cp, cc, cr, mvx & 7, mvy & 7);
+            } else {
+                const uint32_t *rw = reinterpret_cast<const uint32_t *>(rec0 + (size_t)l * g.widthMbs);
+                const uint32_t subTypes = type >= B200_MB_P_8x8 ? (w3 >> 24) & 0xFFu : 0u;
+                if (type <= B200_MB_P_8x16 || subTypes == 0) {
+                    // Partitions that are at least 8 wide (16x8, 8x16, 8x8 sub-macroblocks): every lane's 8-sample luma span and
+                    // 4-sample chroma span lie inside ONE partition, so the lane only has to pick that partition's window,
+                    // vector and origin.  Two partitions are staged at a time (inter_prediction.c:361-482).
+                    const int rounds = type >= B200_MB_P_8x8 ? 2 : 1;
+#pragma unroll 1
+                    for (int rd = 0; rd < rounds; rd++) {
+                        int blkA, blkB, pxB, pyA, pyB, pw, ph;
+                        if (type == B200_MB_P_16x8) { blkA = 0; blkB = 8; pxB = 0; pyA = 0; pyB = 8; pw = 16; ph = 8; }
+                        else if (type == B200_MB_P_8x16) { blkA = 0; blkB = 4; pxB = 8; pyA = 0; pyB = 0; pw = 8; ph = 16; }
+                        else { blkA = 8 * rd; blkB = 8 * rd + 4; pxB = 8; pyA = pyB = 8 * rd; pw = 8; ph = 8; }
+                        const uint32_t mvA = __ldg(rw + 8 + blkA), mvB = __ldg(rw + 8 + blkB);
+                        const int ax = (int)(int16_t)(mvA & 0xFFFFu), ay = (int)(int16_t)(mvA >> 16);
+                        const int bx = (int)(int16_t)(mvB & 0xFFFFu), by = (int)(int16_t)(mvB >> 16);
+                        const uint32_t geomA = issueWindow(buf, mbx * 16, mby * 16 + pyA, pw, ph, ax, ay,
+                                                           frameBase + ((refSlots >> (8 * (blkA >> 2))) & 0xFFu), 0, nullptr);
+                        const uint32_t geomB = issueWindow(buf ^ 1, mbx * 16 + pxB, mby * 16 + pyB, pw, ph, bx, by,
+                                                           frameBase + ((refSlots >> (8 * (blkB >> 2))) & 0xFFu), 0, nullptr);
+                        const bool inBL = type == B200_MB_P_16x8 ? r8 >= 8 : c8 == 8;
+                        const bool inBC = type == B200_MB_P_16x8 ? cr >= 4 : cc == 4;
+                        const bool actL = type < B200_MB_P_8x8 || (r8 >> 3) == rd, actC = type < B200_MB_P_8x8 || (cr >> 2) == rd;
+                        mbarWait(&sm.mbar[buf], (phaseBits >> buf) & 1u);
+                        mbarWait(&sm.mbar[buf ^ 1], (phaseBits >> (buf ^ 1)) & 1u);
+                        phaseBits ^= 3u;
+                        if (actL) {
+                            const uint32_t gm = inBL ? geomB : geomA;
+                            const int mvx = inBL ? bx : ax, mvy = inBL ? by : ay, xf = mvx & 3, yf = mvy & 3;
+                            const int pitch = (int)((gm >> 4) & 3u) * 16;
+                            const uint8_t *G0 = sm.luma[inBL ? buf ^ 1 : buf] + (gm & 15u) + (yf ? 2 * pitch : 0) + (xf ? 2 : 0);
+                            pv = lumaQpel8(G0, pitch, c8 - (inBL ? pxB : 0), r8 - (inBL ? pyB : pyA), xf, yf);
+                        }
+                        if (actC) {
+                            const uint32_t gm = inBC ? geomB : geomA;
+                            const int mvx = inBC ? bx : ax, mvy = inBC ? by : ay;
+                            pc = chromaPred4(sm.chroma[inBC ? buf ^ 1 : buf], (int)((gm >> 12) & 3u) * 16, (int)((gm >> 8) & 7u), cp,
+                                             cc - (inBC ? (pxB >> 1) : 0), cr - ((inBC ? pyB : pyA) >> 1), mvx & 7, mvy & 7);
+                        }
+                        __syncwarp();   // the windows are overwritten by the next round's (or the next macroblock's) loads
+                    }
+                } else {
+                    // sub-macroblocks with 8x4 / 4x8 / 4x4 partitions: one window per partition, sample by sample
+#pragma unroll 1
+                    for (int pi = 0; pi < 16; pi++) {
+                        int pw, ph;
+                        const int sub = (subTypes >> (2 * (pi >> 2))) & 3, j = pi & 3;
+                        if (sub == 0) { if (j) continue; pw = 8; ph = 8; }
+                        else if (sub == 1) { if (j & 1) continue; pw = 8; ph = 4; }
+                        else if (sub == 2) { if (j & 2) continue; pw = 4; ph = 8; }
+                        else { pw = 4; ph = 4; }
+                        const int px = cBlkX[pi] * 4, py = cBlkY[pi] * 4;
+                        const uint32_t mvw = __ldg(rw + 8 + pi);
+                        const int mvx = (int)(int16_t)(mvw & 0xFFFFu), mvy = (int)(int16_t)(mvw >> 16);
+                        const uint32_t gm = issueWindow(buf, mbx * 16 + px, mby * 16 + py, pw, ph, mvx, mvy,
+                                                        frameBase + ((refSlots >> (8 * (pi >> 2))) & 0xFFu), 0, nullptr);
+                        mbarWait(&sm.mbar[buf], (phaseBits >> buf) & 1u);
+                        phaseBits ^= 1u << buf;
+                        const int xf = mvx & 3, yf = mvy & 3, pitch = (int)((gm >> 4) & 3u) * 16;
+                        const uint8_t *G0 = sm.luma[buf] + (gm & 15u) + (yf ? 2 * pitch : 0) + (xf ? 2 : 0);
+                        const int lw = 31 - __clz(pw);
+#pragma unroll 1
+                        for (int q = lane; q < pw * ph; q += 32) {
+                            const int x = q & (pw - 1), y = q >> lw;
+                            sm.pred[(py + y) * 16 + px + x] = (uint8_t)lumaQpel(G0, pitch, x, y, xf, yf);
+                        }
+                        const int cw = pw >> 1, chh = ph >> 1, ncp = cw * chh, lcw = lw - 1;
+                        const int cxf = mvx & 7, cyf = mvy & 7, pitchC = (int)((gm >> 12) & 3u) * 16, cxo = (int)((gm >> 8) & 7u);
+#pragma unroll 1
+                        for (int q = lane; q < 2 * ncp; q += 32) {
+                            const int pl = q >= ncp, qq = q - pl * ncp;
+                            const int x = qq & (cw - 1), y = qq >> lcw;
+                            auto S = [&](int sx, int sy) -> int {
+                                const int col = cxo + sx;
+                                return sm.chroma[buf][sy * pitchC + (col >> 3) * 16 + pl * 8 + (col & 7)];
+                            };
+                            // (a sample that meets a zero weight may lie outside the box: it is read, not used)
+                            const int A = S(x, y), B = S(x + 1, y), Cc = S(x, y + 1), D = S(x + 1, y + 1);
+                            sm.pred[256 + pl * 64 + ((py >> 1) + y) * 8 + (px >> 1) + x] =
+                                (uint8_t)(((8 - cxf) * (8 - cyf) * A + cxf * (8 - cyf) * B + (8 - cxf) * cyf * Cc + cxf * cyf * D + 32) >> 6);
+                        }
+                        __syncwarp();
+                    }
+                    pv = *reinterpret_cast<const uint2 *>(sm.pred + r8 * 16 + c8);
+                    pc = *reinterpret_cast<const uint32_t *>(sm.pred + 256 + cp * 64 + cr * 8 + cc);
+                }
+                // (every path above ends with a warp barrier: both window buffers are free)
+                if (interMask) prepare(__ffs(interMask) - 1, buf ^ 1);
+            }
+            // add residual + clip + store (h264bsdWriteOutputBlocks, image.c:172-344)
+            if (mask) {
+                const uint4 ra = *reinterpret_cast<const uint4 *>(&sm.resY[r8][c8]), rb = *reinterpret_cast<const uint4 *>(&sm.resY[r8][c8 + 4]);
+                const uint4 rc = *reinterpret_cast<const uint4 *>(&sm.resC[cp][cr][cc]);
+                auto px = [](uint32_t w, int k) { return (int)((w >> (8 * k)) & 0xFF); };
+                pv = make_uint2(pack4sat(px(pv.x, 0) + (int)ra.x, px(pv.x, 1) + (int)ra.y, px(pv.x, 2) + (int)ra.z, px(pv.x, 3) + (int)ra.w),
+                                pack4sat(px(pv.y, 0) + (int)rb.x, px(pv.y, 1) + (int)rb.y, px(pv.y, 2) + (int)rb.z, px(pv.y, 3) + (int)rb.w));
+                pc = pack4sat(px(pc, 0) + (int)rc.x, px(pc, 1) + (int)rc.y, px(pc, 2) + (int)rc.z, px(pc, 3) + (int)rc.w);
+            }
+            *reinterpret_cast<uint2 *>(dstY) = pv;
+            *reinterpret_cast<uint32_t *>(dstC) = pc;
+            __syncwarp();
         }
-        // add residual + clip + store (h264bsdWriteOutputBlocks, image.c:172-344)
-        if (h.mask) {
-            int resY[8], resC[4];
-            laneResidual(sm.res, lane, resY, resC);
-            auto px = [](uint32_t w, int k) { return (int)((w >> (8 * k)) & 0xFF); };
-            pv = make_uint2(pack4sat(px(pv.x, 0) + resY[0], px(pv.x, 1) + resY[1], px(pv.x, 2) + resY[2], px(pv.x, 3) + resY[3]),
-                            pack4sat(px(pv.y, 0) + resY[4], px(pv.y, 1) + resY[5], px(pv.y, 2) + resY[6], px(pv.y, 3) + resY[7]));
-            pc = pack4sat(px(pc, 0) + resC[0], px(pc, 1) + resC[1], px(pc, 2) + resC[2], px(pc, 3) + resC[3]);
-        }
-        *reinterpret_cast<uint2 *>(dstY) = pv;
-        *reinterpret_cast<uint32_t *>(dstC) = pc;
-        __syncwarp();
+        chunk = __shfl_sync(0xffffffffu, nextChunk, 0);
     }
-    }  // virtual CTA loop
 }
 
 // =====================================================================================================
 // pass B: intra-predicted macroblocks.  They read the unfiltered current picture, so an intra macroblock
-// must come after its intra neighbours (the others were written by the copy pass and pass A).  CTAs take tickets; a
+// must come after its intra neighbours (the others were written by pass A).  CTAs take tickets; a
 // ticket is kReconWarps warp tasks; warp task w is chunk w / nStreams of stream w % nStreams of the stream's
 // wavefront-ordered list.  A warp works through its chunk in list order, so dependencies inside a chunk cost nothing,
 // the warps of a CTA belong to different streams (they never wait for each other), and a warp only ever waits for
@@ -662,14 +835,16 @@ __global__ void __launch_bounds__(kReconWarps * 32, 5) reconIntraKernel(const Re
     IntraWarpSmem &sm = smemAll[warp];
     uint32_t *doneS = p.done + (size_t)s * g.nMbs;
     uint8_t *cur = framePtr(p.pool, g, s * (uint32_t)g.numSlots + job.curSlot);
+    // this lane's spans inside a macroblock, as in pass A: 8 luma samples = bytes 8 lane.. of the 256, 4 chroma samples =
+    // bytes 4 lane.. of the 128
     const int r8 = lane >> 1, c8 = (lane & 1) * 8;
-    const int cp = lane >> 4, cr = (lane >> 1) & 7, cc = (lane & 1) * 4;
+    const int cr = lane >> 2, cp = (lane >> 1) & 1, cc = (lane & 1) * 4;
 
     // lane j < n fetches entry j's address and record head: one chain of dependent loads per chunk
     uint32_t mMb = 0, mMisc = 0;
     uint4 mHead = make_uint4(0, 0, 0, 0);
     if (lane < n) {
-        mMb = __ldg(job.order + (2u * job.nR + job.nC + job.nA) + e0 + lane);
+        mMb = __ldg(job.orderB + e0 + lane);
         const uint32_t *rw = reinterpret_cast<const uint32_t *>(job.recs + mMb);
         mHead = __ldg(reinterpret_cast<const uint4 *>(rw));
         mMisc = (__ldg(rw + 5) & 0xFF) | ((__ldg(rw + 7) & 0xFF) << 8);
@@ -688,8 +863,8 @@ __global__ void __launch_bounds__(kReconWarps * 32, 5) reconIntraKernel(const Re
         }
         const uint32_t misc = __shfl_sync(0xffffffffu, mMisc, i);   // intraChromaMode | waitMask << 8
         const int16_t *coef = job.coefs + (size_t)h.coefIndex * 16;
-        uint8_t *dstY = lumaAt(cur, g, mbx * 16 + c8, mby * 16 + r8);
-        uint8_t *dstC = chromaAt(cur, g, cp, mbx * 8 + cc, mby * 8 + cr);
+        uint8_t *dstY = mbLuma(cur, g, mbx, mby) + lane * 8;
+        uint8_t *dstC = mbChroma(cur, g, mbx, mby) + lane * 4;
         int resY[8], resC[4];
         if (h.mask) {
             mbResidual(h, coef, sm.res, lane, p.errors);

@@ -150,3 +150,30 @@ def legacy():
         nd += 1
     assert n >= 4 and nd >= 2, (n, nd)
     print(f"legacy ok: {n} valid and {nd} damaged streams")
+
+
+def sweep(first, count, limit=60):
+    """many synthetic streams through the host build of the engine, two instances, stage by stage against the oracle
+    (development aid: python -c 'import conftest, _hostemu_bodies as t; t.sweep(0, 100)' with B200_LIB set)"""
+    seeds = [int(s) for s in sorted(GOLD, key=lambda s: (len(s), s)) if not s.startswith("L") and small(GOLD[s], limit)][first:first + count]
+    pics = 0
+    for seed in seeds:
+        ps = ParsedStream(synth_h264.make_stream(seed))
+        assert ps.status == 0
+        orc = _oracle.OracleDecoder(ps)
+        b = Batch(2, ps.width_mbs, ps.height_mbs, ps.num_slots)
+        b.upload(0, ps)
+        b.replicate(0)
+        for k in range(ps.num_pics):
+            slot = ps.pics[k].curSlot
+            b.debug_stage(k, True, False)
+            orc.recon(k)
+            assert np.array_equal(b.read_frame(1, slot), orc.frame(slot)), f"seed {seed}: reconstruction of picture {k}"
+            b.debug_stage(k, False, True)
+            orc.deblock(k)
+            assert np.array_equal(b.read_frame(0, slot), orc.frame(slot)), f"seed {seed}: picture {k}"
+            pics += 1
+        assert b.idct_errors() == 0 and b.watchdog() == (0, 0), f"seed {seed}"
+        b.close(); orc.close(); ps.close()
+        print(f"seed {seed} ok", flush=True)
+    print(f"sweep ok: {len(seeds)} streams, {pics} pictures")

@@ -51,12 +51,11 @@ def prepare_engine_source():
             line = line[:m.start()] + f"EMU_LAUNCH({m.group(1)}, {cfg[0]}, {cfg[1]}, {m.group(3)});" + line[m.end():]
             n += 1
         lines.append(line)
-    assert n == src.count("<<<") and n >= 14, n
+    assert n == src.count("<<<") and n >= 12, n
     src = "\n".join(lines)
     assert src.count('#include "recon_kernel.cuh"') == 1
     src = src.replace('#include "recon_kernel.cuh"', '#include "recon_kernel_emu.cuh"')
-    src += ("\nnamespace b200 {\nalignas(128) uint8_t interSmemRaw[sizeof(InterWarpSmem) * kReconWarps];\n"
-            "alignas(128) uint8_t bulkSmemRaw[sizeof(BulkWarpSmem) * kBulkWarps];\n}\n")
+    src += "\nnamespace b200 {\nalignas(128) uint8_t interSmemRaw[sizeof(PassAWarpSmem) * kReconWarps];\n}\n"
     with open(os.path.join(BUILD, "engine_hostemu.cpp"), "w") as f:
         f.write(src)
 
