@@ -29,7 +29,7 @@ STREAM = os.path.join(ROOT, "tests", "golden", "test_1920x1080.h264")
 E2E_GROUP = 10  # pictures per streamed upload group in the end-to-end leg
 METRIC = "1080p macroblocks/s (H.264 Baseline macroblock reconstruction, bit-exact YUV)"
 UNIT = "MB/s"
-MB_REC_BYTES = 96   # + 2 bytes per macroblock in the per-picture order list: D = 98
+MB_REC_BYTES = 96   # D: work-list bytes per macroblock (intra macroblocks: + 2 in the order list)
 
 
 def shard_streams(total, world, rank):
@@ -100,6 +100,16 @@ class ClockSampler(threading.Thread):
                     reasons.add(n)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def kernel_source_sha16():
+    """identifies the build a profile belongs to: hash of the kernel sources"""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "h264bsd_b200", "csrc", "engine")
+    for n in sorted(os.listdir(d)):
+        if n.endswith((".cuh", ".cu", ".hpp")):
+            h.update(open(os.path.join(d, n), "rb").read())
+    return h.hexdigest()[:16]
 
 
 def measured_peak_gbs():
@@ -174,9 +184,10 @@ def run_reference_arm(args):
 
 
 def algorithmic_bytes(ps):
-    """per-picture algorithmic bytes of the fused reconstruct kernel and of the in-loop filter:
-    inter MB 768 + 32*nCoded + D, intra MB 384 + 32*nCoded + D (I_PCM: its 384 raw bytes are the 12 'coded' blocks),
-    D = 96-byte record; deblock 768 + D (it re-reads the record) per MB."""
+    """per-picture algorithmic bytes of pass A (the fused MC + dequant/IDCT + add + write kernel), of the intra pass and of the
+    in-loop filter: inter MB 768 + 32*nCoded + D, intra MB 384 + 32*nCoded + D (I_PCM: its 384 raw bytes are the
+    12 'coded' blocks), D = the 96-byte record; a zero-motion copy 768 + 64 (pass A reads the two 32-byte sectors of the record
+    that hold head, reference slots and first vector); deblock 768 + D per MB."""
     import numpy as np
     t = ps.ptr.contents
     area = np.ctypeslib.as_array(t.mbRecs, shape=(t.mbRecBytes,))
@@ -192,14 +203,13 @@ def algorithmic_bytes(ps):
     inter = types <= 5
     pass_a = inter | (types == 31)
     mv0 = recs[:, 32:36].copy().view("<i2")
-    copy = (types <= 1) & (masks == 0) & (((mv0[:, 0] | mv0[:, 1]) & 7) == 0)   # picture.cpp finalizeRecords: plainCopy
-    recon = np.where(inter, 768, 384) + 32 * pop + MB_REC_BYTES + 2   # + 2: the macroblock's entry in the order list
+    copy = (types <= 1) & (masks == 0) & ((mv0[:, 0] | mv0[:, 1]) == 0)   # passAKernel: isCopy
+    recon = np.where(inter, 768, 384) + 32 * pop + MB_REC_BYTES
     nmb = ps.mbs_per_pic
-    per_pic_recon_a = np.where(pass_a & ~copy, recon, 0).reshape(-1, nmb).sum(axis=1)
-    per_pic_recon_b = np.where(pass_a, 0, recon).reshape(-1, nmb).sum(axis=1)
-    per_pic_copy = np.where(copy, 768 + 8 + 2, 0).reshape(-1, nmb).sum(axis=1)   # the copy kernel reads 8 bytes of the record
+    per_pic_a = np.where(pass_a, np.where(copy, 768 + 64, recon), 0).reshape(-1, nmb).sum(axis=1)
+    per_pic_b = np.where(pass_a, 0, recon + 2).reshape(-1, nmb).sum(axis=1)   # + 2: the macroblock's entry in the order list
     per_pic_deblock = np.full(ps.num_pics, (768 + MB_REC_BYTES) * nmb, np.int64)
-    return per_pic_recon_a, per_pic_recon_b, per_pic_deblock, float(inter.mean()), float(pop.mean()), per_pic_copy, float(copy.mean())
+    return per_pic_a, per_pic_b, per_pic_deblock, float(inter.mean()), float(pop.mean()), float(copy.mean()), float((pass_a & ~copy).mean())
 
 
 def main():
@@ -239,7 +249,7 @@ def main():
     first, count = shard_streams(total_streams, world, rank)
     nmb = ps.mbs_per_pic
     mbs_per_step_rank = count * ps.num_pics * nmb
-    per_pic_recon_bytes, per_pic_intra_bytes, per_pic_deblock_bytes, inter_frac, coded_per_mb, per_pic_copy_bytes, copy_frac = algorithmic_bytes(ps)
+    per_pic_a_bytes, per_pic_intra_bytes, per_pic_deblock_bytes, inter_frac, coded_per_mb, copy_frac, other_frac = algorithmic_bytes(ps)
 
     b = Batch(count, ps.width_mbs, ps.height_mbs, ps.num_slots, device=local)
     b.upload(0, ps)
@@ -308,29 +318,23 @@ def main():
     peak, peak_src = measured_peak_gbs()
     gbs = lambda nbytes, msec: nbytes / max(1e-9, msec / 1000.0) / 1e9
     per_launch = lambda key: stage_ms[key] / max(1, stage_n[key])
-    recon_bytes_per_launch = float(per_pic_recon_bytes[per_pic_recon_bytes > 0].mean()) * count   # pass A launches only (P pictures)
-    copy_bytes_per_launch = float(per_pic_copy_bytes[per_pic_copy_bytes > 0].mean()) * count
-    recon_ms_per_launch, copy_ms_per_launch = per_launch("recon"), per_launch("recon_copy")
-    # pass A = the fused MC + dequant/IDCT + add + write path of SURVEY 8(d) for every inter / I_PCM macroblock of a picture;
-    # the engine dispatches it as two launches (plain copies, everything else)
-    pass_a_bytes, pass_a_ms = recon_bytes_per_launch + copy_bytes_per_launch, recon_ms_per_launch + copy_ms_per_launch
+    # pass A = the fused MC + dequant/IDCT + add + write path of SURVEY 8(d) for every inter / I_PCM macroblock of a picture: one
+    # launch of passAKernel per picture (an IDR picture's launch finds nothing to do: every macroblock is intra)
+    pass_a_bytes = float(per_pic_a_bytes.sum()) * count / max(1, ps.num_pics)
+    pass_a_ms = per_launch("recon")
     achieved = gbs(pass_a_bytes, pass_a_ms)
     # in-loop filter: pels (768 B) only of the macroblocks that have a non-zero boundary strength, record + strengths of all
     deb_bytes_per_launch = (768.0 * deblock_work_frac + MB_REC_BYTES + 17) * nmb * count
     deb_ms_per_launch = per_launch("deblock") + per_launch("strength")
     step_ms = max(1e-9, sum(stage_ms.values()))
-    roof = {"bound": "hbm", "kernel": "pass A = reconCopyKernel + reconInterKernel (fused MC + dequant/IDCT + add + write of every inter / I_PCM "
-                                      "macroblock; plain copies and the rest are two launches)", "achieved": achieved, "peak": peak,
+    roof = {"bound": "hbm", "kernel": "passAKernel (fused MC + dequant/IDCT + add + write of every inter / I_PCM macroblock, zero-motion copies "
+                                      "included; one launch per picture over all streams)", "achieved": achieved, "peak": peak,
             "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": pass_a_bytes, "ms_per_launch": pass_a_ms,
-            "share_of_step": (stage_ms["recon"] + stage_ms["recon_copy"]) / step_ms,
+            "share_of_step": stage_ms["recon"] / step_ms,
             "serialized_step_ms": ms_serial / args.steps,
-            "other_kernels": {"reconInterKernel": {"achieved_gbs": gbs(recon_bytes_per_launch, recon_ms_per_launch), "ms_per_launch": recon_ms_per_launch,
-                                                   "frac": gbs(recon_bytes_per_launch, recon_ms_per_launch) / peak, "share_of_step": stage_ms["recon"] / step_ms},
-                              "reconCopyKernel": {"achieved_gbs": gbs(copy_bytes_per_launch, copy_ms_per_launch), "ms_per_launch": copy_ms_per_launch,
-                                                  "frac": gbs(copy_bytes_per_launch, copy_ms_per_launch) / peak, "share_of_macroblocks": copy_frac,
-                                                  "share_of_step": stage_ms["recon_copy"] / step_ms},
-                              "strengthKernel + deblockKernel": {"achieved_gbs": gbs(deb_bytes_per_launch, deb_ms_per_launch), "ms_per_launch": deb_ms_per_launch,
+            "macroblock_mix": {"zero_motion_copies": copy_frac, "other_inter_and_pcm": other_frac, "intra": 1.0 - copy_frac - other_frac},
+            "other_kernels": {"strengthKernel + deblockKernel": {"achieved_gbs": gbs(deb_bytes_per_launch, deb_ms_per_launch), "ms_per_launch": deb_ms_per_launch,
                                                                  "frac": gbs(deb_bytes_per_launch, deb_ms_per_launch) / peak,
                                                                  "macroblocks_with_work": deblock_work_frac,
                                                                  "share_of_step": (stage_ms["deblock"] + stage_ms["strength"]) / step_ms},
@@ -341,13 +345,20 @@ def main():
     conv_reps = 3
     conv_ms = b.convert_bench_all(last_slot, 1, conv_reps) / conv_reps
     conv_bytes = count * (ps.width_mbs * 16) * (ps.height_mbs * 16) * 5.5
-    roof["other_kernels"]["convertKernel"] = {"achieved_gbs": gbs(conv_bytes, conv_ms), "ms_per_launch": conv_ms,
+    roof["other_kernels"]["convertFrameKernel"] = {"achieved_gbs": gbs(conv_bytes, conv_ms), "ms_per_launch": conv_ms,
                                              "frac": gbs(conv_bytes, conv_ms) / peak,
                                              "note": "BGRA of the last output frame of all streams in one launch; not part of the timed step"}
-    prof = os.path.join(ROOT, "profiles", "r01_recon_traffic.json")
+    # DRAM bytes of one passAKernel launch from the committed `ncu --set full` capture, scaled to this run's stream count; only
+    # a capture of THIS build counts (the file names the source hash of the kernels it was taken with)
+    prof = os.path.join(ROOT, "profiles", "r02_passA_traffic.json")
     if os.path.exists(prof):
         try:
-            roof["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+            pj = json.load(open(prof))
+            if pj.get("kernel_source_sha16") == kernel_source_sha16():
+                roof["traffic"] = pj["dram_bytes_per_launch_per_stream"] * count
+                roof["traffic_source"] = pj.get("source")
+            else:
+                roof["traffic_source"] = "no capture of this build (profiles/r02_passA_traffic.json is of another one)"
         except Exception:
             pass
 

@@ -3,7 +3,7 @@
 set -euo pipefail
 here="$(cd "$(dirname "$0")" && pwd)"
 src="$here/csrc"
-out="$here/libh264bsd_b200.so"
+out="${B200_OUT:-$here/libh264bsd_b200.so}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 "$NVCC" -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
   -Xcompiler -fPIC,-Wall,-Wno-unused-function -shared \

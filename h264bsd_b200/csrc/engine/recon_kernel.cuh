@@ -221,7 +221,7 @@ __device__ __forceinline__ uint2 avg8(uint2 a, uint2 b) { return make_uint2(__va
 // clause 8.4.2.2.1 for 8 horizontally adjacent samples: (x0, y) = position of the first sample inside the partition; the
 // same arithmetic as lumaQpel, 8 at a time, on packed bytes: the rounded averages (a + b + 1) >> 1 are per-byte averages of
 // clipped values
-__device__ __forceinline__ uint2 lumaQpel8(const uint8_t *G0, int pitch, int x0, int y, int xf, int yf) {
+__device__ __noinline__ uint2 lumaQpel8(const uint8_t *G0, int pitch, int x0, int y, int xf, int yf) {
     const uint8_t *at = G0 + y * pitch + x0;   // the lane's first integer sample
     if ((xf | yf) == 0) return lds8(at);       // h264bsdFillBlock copy (reconstruct.c:1852)
     const bool jfam = (xf == 2 || yf == 2) && xf != 0 && yf != 0;
@@ -276,7 +276,7 @@ __device__ __forceinline__ void chromaRow5(const uint8_t *pA, uint32_t sh, uint3
     hi = __funnelshift_r(w1, w2, s);
 }
 // four samples of plane cp: window columns cxo + lcx .. + 3, row lcy; the four weights times four pels are one dot product
-__device__ __forceinline__ uint32_t chromaPred4(const uint8_t *cbuf, int pitchC, int cxo, int cp, int lcx, int lcy, int cxf, int cyf) {
+__device__ __noinline__ uint32_t chromaPred4(const uint8_t *cbuf, int pitchC, int cxo, int cp, int lcx, int lcy, int cxf, int cyf) {
     const int col0 = cxo + lcx;
     const uint8_t *pA = cbuf + lcy * pitchC + (col0 >> 3) * 16 + cp * 8;
     const uint32_t sh = (uint32_t)col0 & 7u;
@@ -461,7 +461,7 @@ __device__ __forceinline__ void laneResidual(const int16_t (*res)[16], int lane,
 // h264bsdProcessBlock (transform.c:97-234) with the row transform inside a lane (lane r of a group owns row r of the block)
 // and the column transform across the group's four lanes by two shuffle exchanges; h264bsdProcessChromaDc (:359-401) by
 // lanes 16..23 first.  `cbuf` = the macroblock's levels in shared memory (b200_mb_rec layout: [chroma DC][coded blocks]).
-__device__ __forceinline__ void residualShfl(PassAWarpSmem &sm, const uint8_t *cbuf, uint32_t mask, int qpY, int qpC, int lane, uint32_t *errors) {
+__device__ __noinline__ void residualShfl(PassAWarpSmem &sm, const uint8_t *cbuf, uint32_t mask, int qpY, int qpC, int lane, uint32_t *errors) {
     {   // every block that is not visited below has a zero residual
         uint4 *z = reinterpret_cast<uint4 *>(&sm.resY[0][0]);   // resY and resC are contiguous: 96 x 16 bytes
         const uint4 zero = make_uint4(0, 0, 0, 0);
@@ -525,7 +525,35 @@ __device__ __forceinline__ void residualShfl(PassAWarpSmem &sm, const uint8_t *c
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(kReconWarps * 32, 3)
+// window of a partition at picture position (px, py), size w x h (wh = w | h << 8), vector (mvx, mvy): clamp the origin into
+// the bordered plane (a window wholly outside the picture on an axis equals the window at the clamped origin because the border
+// is a replication), pick the boxes, and have lane 0 issue the loads (+ the bulk copy of `extraBytes` of levels) on
+// mbarrier `buf`.  Returns xo | nx << 4 | cxo << 8 | nxC << 12.
+__device__ __noinline__ uint32_t issueWindowFn(PassAWarpSmem *sm, int buf, const PassAMaps *maps, int W, int H, int px, int py, int wh,
+                                               int mvx, int mvy, uint32_t refFrame, uint32_t extraBytes, const void *extraSrc, int lane) {
+    const int w = wh & 0xFF, h = wh >> 8;
+    const int xf = mvx & 3, yf = mvy & 3, nc = w + (xf ? 5 : 0), nr = h + (yf ? 5 : 0);
+    const int x0 = clip3(-kPadY, W + kPadY - nc, px + (mvx >> 2) - (xf ? 2 : 0)) + kPadY;
+    const int y0 = clip3(-kPadY, H + kPadY - nr, py + (mvy >> 2) - (yf ? 2 : 0)) + kPadY;
+    const int xo = x0 & 15, nx = (xo + nc + 15) >> 4;
+    const int cxf = mvx & 7, cyf = mvy & 7, ncC = (w >> 1) + (cxf ? 1 : 0), nrC = (h >> 1) + (cyf ? 1 : 0);
+    const int cx0 = clip3(-kPadC, W / 2 + kPadC - ncC, (px >> 1) + (mvx >> 3)) + kPadC;
+    const int cy0 = clip3(-kPadC, H / 2 + kPadC - nrC, (py >> 1) + (mvy >> 3)) + kPadC;
+    const int cxo = cx0 & 7, nxC = (cxo + ncC + 7) >> 3;
+    if (lane == 0) {
+        fenceProxyAsync();
+        mbarExpectTx(&sm->mbar[buf], (uint32_t)(16 * nx * (yf ? 21 : 16) + 16 * nxC * (cyf ? 9 : 8)) + extraBytes);
+        tmaLoad4d(sm->luma[buf], &maps->luma[nx - 1][yf ? 1 : 0], 0, x0 >> 4, y0, (int)refFrame, &sm->mbar[buf]);
+        tmaLoad4d(sm->chroma[buf], &maps->chroma[nxC - 1][cyf ? 1 : 0], 0, cx0 >> 3, cy0, (int)refFrame, &sm->mbar[buf]);
+        if (extraBytes) bulkLoad(sm->coef[buf], extraSrc, extraBytes, &sm->mbar[buf]);
+    }
+    return (uint32_t)xo | ((uint32_t)nx << 4) | ((uint32_t)cxo << 8) | ((uint32_t)nxC << 12);
+}
+
+#ifndef B200_PASSA_MINBLOCKS
+#define B200_PASSA_MINBLOCKS 2
+#endif
+__global__ void __launch_bounds__(kReconWarps * 32, B200_PASSA_MINBLOCKS)
 passAKernel(const ReconParams p, const __grid_constant__ PassAMaps maps) {
     extern __shared__ __align__(128) uint8_t interSmemRaw[];   // kReconWarps x PassAWarpSmem (more than the 48 KB static limit)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -579,85 +607,88 @@ passAKernel(const ReconParams p, const __grid_constant__ PassAMaps maps) {
         }
         const uint32_t copyMask = __ballot_sync(0xffffffffu, isCopy);
         uint32_t interMask = __ballot_sync(0xffffffffu, isInter);
-
-        // ---- what is staged for the macroblock whose turn comes next ------------------------------------------------
-        uint32_t nW0 = 0, nMask = 0, nW3 = 0, nRef = 0, nMv = 0, nGeom = 0;
-        int nL = 0;
-        bool nArmed = false;
-        // window of a partition at picture position (px, py), size w x h, vector (mvx, mvy): clamp the origin into the bordered
-        // plane (a window wholly outside the picture on an axis equals the window at the clamped origin because the border is a
-        // replication), pick the boxes, and have lane 0 issue the loads.  Returns xo | nx << 4 | cxo << 8 | nxC << 12.
-        auto issueWindow = [&](int buf, int px, int py, int w, int h, int mvx, int mvy, uint32_t refFrame, uint32_t extraBytes,
-                               const void *extraSrc) -> uint32_t {
-            const int xf = mvx & 3, yf = mvy & 3, nc = w + (xf ? 5 : 0), nr = h + (yf ? 5 : 0);
+        // Every lane works out where the windows of ITS macroblock lie (one partition: P_Skip / P_L0_16x16), all macroblocks of
+        // the chunk at once instead of one after the other when their turn comes: the origin clamped into the bordered plane (a
+        // window wholly outside the picture on an axis equals the window at the clamped origin because the border is a
+        // replication), the boxes, the bytes to expect.
+        //   gX = luma strip | chroma strip << 16     gY = luma row | chroma row << 16
+        //   gM = luma map (3 bits) | chroma map << 3 (2) | xo << 5 (4) | cxo << 9 (3) | mvx & 7 << 12 | mvy & 7 << 15 | window bytes << 18
+        uint32_t gX = 0, gY = 0, gM = 0;
+        if (isInter && (mW0 & 0xFFu) <= B200_MB_P_16x16) {
+            const int mvx = (int)(int16_t)(mMv & 0xFFFFu), mvy = (int)(int16_t)(mMv >> 16);
+            const int px = mbx * 16, py = (row0 + lane) * 16;
+            const int xf = mvx & 3, yf = mvy & 3, nc = 16 + (xf ? 5 : 0), nr = 16 + (yf ? 5 : 0);
             const int x0 = clip3(-kPadY, g.W + kPadY - nc, px + (mvx >> 2) - (xf ? 2 : 0)) + kPadY;
             const int y0 = clip3(-kPadY, g.H + kPadY - nr, py + (mvy >> 2) - (yf ? 2 : 0)) + kPadY;
             const int xo = x0 & 15, nx = (xo + nc + 15) >> 4;
-            const int cxf = mvx & 7, cyf = mvy & 7, ncC = (w >> 1) + (cxf ? 1 : 0), nrC = (h >> 1) + (cyf ? 1 : 0);
+            const int cxf = mvx & 7, cyf = mvy & 7, ncC = 8 + (cxf ? 1 : 0), nrC = 8 + (cyf ? 1 : 0);
             const int cx0 = clip3(-kPadC, g.W / 2 + kPadC - ncC, (px >> 1) + (mvx >> 3)) + kPadC;
             const int cy0 = clip3(-kPadC, g.H / 2 + kPadC - nrC, (py >> 1) + (mvy >> 3)) + kPadC;
             const int cxo = cx0 & 7, nxC = (cxo + ncC + 7) >> 3;
-            if (lane == 0) {
-                fenceProxyAsync();
-                mbarExpectTx(&sm.mbar[buf], (uint32_t)(16 * nx * (yf ? 21 : 16) + 16 * nxC * (cyf ? 9 : 8)) + extraBytes);
-                tmaLoad4d(sm.luma[buf], &maps.luma[nx - 1][yf ? 1 : 0], 0, x0 >> 4, y0, (int)refFrame, &sm.mbar[buf]);
-                tmaLoad4d(sm.chroma[buf], &maps.chroma[nxC - 1][cyf ? 1 : 0], 0, cx0 >> 3, cy0, (int)refFrame, &sm.mbar[buf]);
-                if (extraBytes) bulkLoad(sm.coef[buf], extraSrc, extraBytes, &sm.mbar[buf]);
-            }
-            return (uint32_t)xo | ((uint32_t)nx << 4) | ((uint32_t)cxo << 8) | ((uint32_t)nxC << 12);
+            const uint32_t bytes = (uint32_t)(16 * nx * (yf ? 21 : 16) + 16 * nxC * (cyf ? 9 : 8));
+            gX = (uint32_t)(x0 >> 4) | ((uint32_t)(cx0 >> 3) << 16);
+            gY = (uint32_t)y0 | ((uint32_t)cy0 << 16);
+            gM = (uint32_t)((nx - 1) * 2 + (yf ? 1 : 0)) | ((uint32_t)((nxC - 1) * 2 + (cyf ? 1 : 0)) << 3) | ((uint32_t)xo << 5) |
+                 ((uint32_t)cxo << 9) | ((uint32_t)cxf << 12) | ((uint32_t)cyf << 15) | (bytes << 18);
+        }
+
+        // ---- what is staged for the macroblock whose turn comes next ------------------------------------------------
+        uint32_t nW0 = 0, nMask = 0, nRef = 0, nGeom = 0;
+        int nL = 0;
+        bool nArmed = false;
+        auto issueWindow = [&](int buf, int px, int py, int w, int h, int mvx, int mvy, uint32_t refFrame, uint32_t extraBytes,
+                               const void *extraSrc) -> uint32_t {
+            return issueWindowFn(&sm, buf, &maps, g.W, g.H, px, py, w | (h << 8), mvx, mvy, refFrame, extraBytes, extraSrc, lane);
         };
         // stage macroblock l of the chunk into buffer `buf`: its levels always, its windows when it has one partition
         auto prepare = [&](int l, int buf) {
             nL = l;
             nW0 = __shfl_sync(0xffffffffu, mW0, l); nMask = __shfl_sync(0xffffffffu, mMask, l);
-            nW3 = __shfl_sync(0xffffffffu, mW3, l); nRef = __shfl_sync(0xffffffffu, mRef, l);
-            nMv = __shfl_sync(0xffffffffu, mMv, l);
+            nRef = __shfl_sync(0xffffffffu, mRef, l);
+            nGeom = __shfl_sync(0xffffffffu, gM, l);
             const uint32_t coefIndex = __shfl_sync(0xffffffffu, mCoef, l);
+            const uint32_t gx = __shfl_sync(0xffffffffu, gX, l), gy = __shfl_sync(0xffffffffu, gY, l);
             const uint32_t type = nW0 & 0xFFu;
             const uint32_t coefBytes = type == B200_MB_I_PCM ? 384u : 32u * (uint32_t)__popc(nMask & 0x3FFFFFFu);
-            const void *coefSrc = job.coefs + (size_t)coefIndex * 16;
-            nArmed = true;
-            if (type <= B200_MB_P_16x16) {
-                nGeom = issueWindow(buf, mbx * 16, (row0 + l) * 16, 16, 16, (int)(int16_t)(nMv & 0xFFFFu), (int)(int16_t)(nMv >> 16),
-                                    frameBase + (nRef & 0xFFu), coefBytes, coefSrc);
-            } else if (coefBytes) {
-                if (lane == 0) {
-                    fenceProxyAsync();
-                    mbarExpectTx(&sm.mbar[buf], coefBytes);
-                    bulkLoad(sm.coef[buf], coefSrc, coefBytes, &sm.mbar[buf]);
+            nArmed = type <= B200_MB_P_16x16 || coefBytes != 0;
+            if (lane == 0 && nArmed) {
+                fenceProxyAsync();
+                mbarExpectTx(&sm.mbar[buf], (nGeom >> 18) + coefBytes);
+                if (type <= B200_MB_P_16x16) {
+                    const int ref = (int)(frameBase + (nRef & 0xFFu));
+                    tmaLoad4d(sm.luma[buf], &maps.luma[0][0] + (nGeom & 7u), 0, (int)(gx & 0xFFFFu), (int)(gy & 0xFFFFu), ref, &sm.mbar[buf]);
+                    tmaLoad4d(sm.chroma[buf], &maps.chroma[0][0] + ((nGeom >> 3) & 3u), 0, (int)(gx >> 16), (int)(gy >> 16), ref, &sm.mbar[buf]);
                 }
-            } else {
-                nArmed = false;
+                if (coefBytes) bulkLoad(sm.coef[buf], job.coefs + (size_t)coefIndex * 16, coefBytes, &sm.mbar[buf]);
             }
         };
         if (interMask) prepare(__ffs(interMask) - 1, 0);
 
-        // ---- copies ---------------------------------------------------------------------------------------------------
+        // ---- copies: lanes 0..23 move the 16 luma + 8 chroma 16-byte units of a macroblock, four macroblocks in flight ----------
         if (copyMask) {
-            if (isCopy) sm.list[__popc(copyMask & ((1u << lane) - 1u))] = (uint8_t)lane;
-            __syncwarp();
-            const uint32_t units = 24u * (uint32_t)__popc(copyMask);   // 16 luma + 8 chroma 16-byte units per macroblock
             const long long stride = (long long)g.frameStride;
+            uint8_t *mine = lane < 16 ? lbase + lane * 16 : cbase + (lane - 16) * 16;   // this lane's unit of macroblock 0 of the chunk
+            const uint32_t step = lane < 16 ? 256u : 128u;
+            uint32_t cm = copyMask;
 #pragma unroll 1
-            for (uint32_t u0 = 0; u0 < units; u0 += 128u) {
+            while (cm) {
                 uint4 v[4];
                 uint8_t *dst[4];
                 bool ok[4];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    const uint32_t u = u0 + 32u * j + lane;
-                    ok[j] = u < units;
-                    const uint32_t q = ok[j] ? (u * 2731u) >> 16 : 0u, w = u - 24u * q;   // u / 24, u % 24 (u < 768)
-                    const uint32_t e = sm.list[q];
-                    const uint32_t slot = __shfl_sync(0xffffffffu, mRef, (int)e) & 0xFFu;
-                    dst[j] = w < 16u ? lbase + e * 256u + w * 16u : cbase + e * 128u + (w - 16u) * 16u;
-                    if (ok[j]) v[j] = __ldg(reinterpret_cast<const uint4 *>(dst[j] + ((long long)slot - (long long)job.curSlot) * stride));
+                    ok[j] = cm != 0;
+                    const int e = ok[j] ? __ffs(cm) - 1 : 0;
+                    cm &= cm - 1;
+                    const long long slot = (long long)(__shfl_sync(0xffffffffu, mRef, e) & 0xFFu);
+                    dst[j] = mine + (uint32_t)e * step;
+                    ok[j] = ok[j] && lane < 24;
+                    if (ok[j]) v[j] = __ldg(reinterpret_cast<const uint4 *>(dst[j] + (slot - (long long)job.curSlot) * stride));
                 }
 #pragma unroll
                 for (int j = 0; j < 4; j++)
                     if (ok[j]) *reinterpret_cast<uint4 *>(dst[j]) = v[j];
             }
-            __syncwarp();   // the list is used again by the residual
         }
 
         // ---- inter macroblocks, one after the other -------------------------------------------------------------------------
@@ -668,7 +699,7 @@ passAKernel(const ReconParams p, const __grid_constant__ PassAMaps maps) {
             const int buf = it & 1;
             it++;
             const int l = nL;
-            const uint32_t w0 = nW0, mask = nMask, w3 = nW3, refSlots = nRef, mvv = nMv, geom = nGeom;
+            const uint32_t w0 = nW0, mask = nMask, refSlots = nRef, geom = nGeom;
             const bool armed = nArmed;
             const uint32_t type = w0 & 0xFFu;
             const int qpY = (w0 >> 8) & 0xFF, qpC = (w0 >> 16) & 0xFF;
@@ -695,15 +726,14 @@ passAKernel(const ReconParams p, const __grid_constant__ PassAMaps maps) {
             uint32_t pc = 0;               // and 4 chroma prediction samples
             const int mby = row0 + l;
             if (single) {
-                const int mvx = (int)(int16_t)(mvv & 0xFFFFu), mvy = (int)(int16_t)(mvv >> 16);
-                const int xf = mvx & 3, yf = mvy & 3;
-                const int pitch = (int)((geom >> 4) & 3u) * 16, pitchC = (int)((geom >> 12) & 3u) * 16;
-                const uint8_t *G0 = sm.luma[buf] + (geom & 15u) + (yf ? 2 * pitch : 0) + (xf ? 2 : 0);
+                const int cxf = (int)((geom >> 12) & 7u), cyf = (int)((geom >> 15) & 7u), xf = cxf & 3, yf = cyf & 3;
+                const int pitch = (int)(((geom >> 1) & 3u) + 1u) * 16, pitchC = (int)(((geom >> 4) & 1u) + 1u) * 16;
+                const uint8_t *G0 = sm.luma[buf] + ((geom >> 5) & 15u) + (yf ? 2 * pitch : 0) + (xf ? 2 : 0);
                 pv = lumaQpel8(G0, pitch, c8, r8, xf, yf);
-                pc = chromaPred4(sm.chroma[buf], pitchC, (int)((geom >> 8) & 7u), cp, cc, cr, mvx & 7, mvy & 7);
+                pc = chromaPred4(sm.chroma[buf], pitchC, (int)((geom >> 9) & 7u), cp, cc, cr, cxf, cyf);
             } else {
                 const uint32_t *rw = reinterpret_cast<const uint32_t *>(rec0 + (size_t)l * g.widthMbs);
-                const uint32_t subTypes = type >= B200_MB_P_8x8 ? (w3 >> 24) & 0xFFu : 0u;
+                const uint32_t subTypes = type >= B200_MB_P_8x8 ? (__ldg(rw + 3) >> 24) & 0xFFu : 0u;
                 if (type <= B200_MB_P_8x16 || subTypes == 0) {
                     // Partitions that are at least 8 wide (16x8, 8x16, 8x8 sub-macroblocks): every lane's 8-sample luma span and
                     // 4-sample chroma span lie inside ONE partition, so the lane only has to pick that partition's window,

@@ -22,6 +22,7 @@
 #define __constant__
 #define __shared__ static
 #define __forceinline__ inline
+#define __noinline__
 #define __launch_bounds__(...)
 #define __align__(n) alignas(n)
 #define __grid_constant__
@@ -114,6 +115,7 @@ inline unsigned __ballot_sync(unsigned, int pred) {
     warp_emu::warpSync();
     return r;
 }
+inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
 inline void __syncwarp() { warp_emu::warpSync(); }
 inline void __syncthreads() { warp_emu::gBlockBarrier.wait((int)blockDim.x); }
 inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }

@@ -98,55 +98,6 @@ DAMAGED = json.load(open(os.path.join(_oracle.GOLDEN, "synth_damaged_md5.json"))
 
 
 @pytest.mark.parametrize("chunk", range(4))
-def test_legacy_api_matches_reference_golden(chunk):
-    """h264bsdInit/Decode/NextOutputPicture over the synthetic streams: output pictures, output order"""
-    for seed in SEEDS[chunk::4]:
-        g = GOLD[str(seed)]
-        frames = decode_stream(_stream(seed))
-        assert len(frames) == g["outputs"], f"seed {seed}"
-        h = hashlib.md5()
-        for f in frames:
-            h.update(np.ascontiguousarray(f).tobytes())
-        assert h.hexdigest() == g["post_md5"], f"seed {seed}: output pictures differ from the reference"
-
-
-def test_large_still_streams_match_oracle_and_golden():
-    """rows wider than a copy run, runs cut by slice / slice-group borders, several reference slots: four instances per stream"""
-    for key in LARGE:
-        g = GOLD[key]
-        data = synth_h264.make_stream(g["seed"], **g["knobs"])
-        if hashlib.md5(data).hexdigest() != g["stream_md5"]:
-            pytest.skip("generator drifted from tests/golden/synth_md5.json: re-run tests/make_synth_golden.py")
-        ps = ParsedStream(data)
-        orc = _oracle.OracleDecoder(ps)
-        b = Batch(4, ps.width_mbs, ps.height_mbs, ps.num_slots)
-        b.upload(0, ps)
-        b.replicate(0)
-        for k in range(ps.num_pics):
-            slot = ps.pics[k].curSlot
-            b.decode_picture(k)
-            orc.recon(k)
-            orc.deblock(k)
-            assert np.array_equal(b.read_frame(3, slot), orc.frame(slot)), f"{key}: picture {k}"
-            assert b.compare_streams([slot] * 4) == 0, f"{key}: instances differ at picture {k}"
-        assert b.idct_errors() == 0 and b.watchdog() == (0, 0), key
-        b.close()
-        orc.close()
-        ps.close()
-        frames = decode_stream(data)
-        h = hashlib.md5()
-        for f in frames:
-            h.update(np.ascontiguousarray(f).tobytes())
-        assert len(frames) == g["outputs"] and h.hexdigest() == g["post_md5"], f"{key}: legacy API output differs from the reference"
-
-
-DAMAGED = json.load(open(os.path.join(_oracle.GOLDEN, "synth_damaged_md5.json")))
-
-
-@pytest.mark.xfail(strict=False, reason="error-concealment path (concealKernel, concealed-copy records) was written after round 1's GPU "
-                                        "budget was spent: checked on the host by emulation (tests/test_cpu_kernel_emu.py), not yet run on "
-                                        "hardware -- the first run decides (DESIGN.md, known gaps)")
-@pytest.mark.parametrize("chunk", range(4))
 def test_damaged_streams_concealment_matches_oracle(chunk):
     """damaged streams in resilient mode: lost macroblocks copied from the reference picture or estimated from their
     neighbours (concealKernel), then filtered as intra / QP 40 -- every picture against the CPU oracle, the output against the
