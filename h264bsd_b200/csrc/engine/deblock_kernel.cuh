@@ -1,6 +1,6 @@
 // deblock_kernel.cuh -- in-loop deblocking filter (h264bsdFilterPicture, h264bsd_deblocking.c:575-640)
-// as a dependency-flag wavefront: half a warp per macroblock, tickets in x+2y order; a macroblock waits
-// for its left, top and top-right neighbours (exactly the macroblocks whose filtering the reference's
+// with the reference's raster order kept where it matters: half a warp walks a macroblock row left to right
+// and waits for the row above to be two macroblocks ahead (the macroblocks whose filtering the reference's
 // raster order puts before it and whose pels it reads or rewrites).
 //
 // Also here: replication of the picture border (what h264bsdFillBlock's coordinate clamp computes on
@@ -11,20 +11,17 @@
 namespace b200 {
 
 constexpr int kDeblockWarps = 8;
-constexpr int kFilterChunk = 8;  // stage 2: most consecutive tickets per warp (DeblockParams::filterChunk <= kFilterChunk)
 
 struct DeblockParams {
     uint8_t *pool;
     PoolGeom g;
     const StreamJob *jobs;
-    const uint16_t *order;
-    uint32_t *done;
+    uint32_t *done;            // nStreams * heightMbs row-progress words of stage 2: serial << 16 | macroblocks finished
     uint32_t *ticket;
     uint32_t serial;
-    uint32_t totalTickets;
+    uint32_t totalTickets;     // stage 2: heightMbs * ceil(nStreams / 2)
     uint32_t *bsWords;         // nStreams * nMbs * 4 words: packed boundary strengths (stage 1 -> stage 2)
     uint8_t *work;             // nStreams * nMbs: 1 = the macroblock has a non-zero boundary strength
-    uint32_t filterChunk;      // stage 2: tickets a warp takes at a time
     unsigned long long *workCount;   // running total of macroblocks with work (statistics for the roofline accounting)
 };
 
@@ -224,25 +221,21 @@ __global__ void __launch_bounds__(kDeblockWarps * 32) strengthKernel(const Deblo
 }
 
 // ---- stage 2: the filter proper, macroblocks with work only ---------------------------------------------------------
-// Tickets in wavefront order (x + 2y ascending, streams interleaved); a warp takes filterChunk consecutive tickets.  A
-// macroblock waits for its left, top and top-right neighbours -- the macroblocks whose filtering the reference's raster order
-// puts before it and whose pels it reads or rewrites -- but only for those that have work themselves (the others never touch
-// a pel).
+// The reference filters the macroblocks of a picture in raster order (deblocking.c:604-640); what that order means for the
+// pels is: a macroblock comes after its left neighbour, and after its upper and upper-right neighbours (it reads and rewrites
+// 3 pels beyond its left and upper edges, and the upper-right neighbour's left edge reaches the upper neighbour's columns
+// 13..15).  Here a HALF-WARP owns one macroblock row of one stream and walks it left to right -- the left neighbour is its own
+// previous step -- and rows publish their progress in a per-row counter: macroblock x of row y starts when row y - 1 has
+// finished x + 2 macroblocks.  Tickets are handed out row-major (row y of every stream before row y + 1 of any), so the row
+// above is normally finished long before: nobody spins.  The two halves of a warp take rows of two different streams.
 //
-// A HALF-WARP filters a macroblock, so a warp filters two macroblocks (of different streams) side by side: every instruction
-// of the edge loops serves 32 lines, none of them idle.  The macroblock and the 4 (2) pels of its left / upper neighbours are
-// staged in shared memory by vector loads (in the strip layout 20 contiguous luma rows, 2 x 10 chroma half-rows).  Lane i of
-// the half owns luma line i -- a row for the vertical edges, left to right, then a column for the horizontal edges, top to
-// bottom, which is the order of FilterLuma (deblocking.c:1569-1623) because edges of one direction only interact along a
-// line -- and afterwards chroma line i & 7 of plane i >> 3 (FilterChroma :1633-1745; chroma edges are luma edges 0 and 2).  A
-// step is skipped when neither macroblock has a strength for it.
+// The macroblock and the 4 (2) pels of its left / upper neighbours are staged in shared memory by vector loads (in the strip
+// layout 20 contiguous luma rows, 2 x 10 chroma half-rows).  Lane i of the half owns luma line i -- a row for the vertical
+// edges, left to right, then a column for the horizontal edges, top to bottom, which is the order of FilterLuma
+// (deblocking.c:1569-1623) because edges of one direction only interact along a line -- and afterwards chroma line i & 7 of
+// plane i >> 3 (FilterChroma :1633-1745; chroma edges are luma edges 0 and 2).  A step is skipped when neither macroblock has a
+// strength for it.
 __device__ __forceinline__ int bsNibble(uint32_t word, int idx) { return (int)((word >> (4 * idx)) & 15u); }
-
-struct FilterMeta {   // what lane j < filterChunk gathers for ticket j of the warp's chunk
-    uint32_t mb, s, w0, w3, qp, work;
-    uint4 bw;
-    unsigned long long frame;
-};
 
 __global__ void __launch_bounds__(kDeblockWarps * 32, 4) deblockKernel(const DeblockParams p) {
     __shared__ DeblockWarpSmem smemAll[kDeblockWarps][2];
@@ -260,179 +253,172 @@ __global__ void __launch_bounds__(kDeblockWarps * 32, 4) deblockKernel(const Deb
     // this lane's lines: luma row / column li; chroma plane cpl, row / column cl
     const int cpl = li >> 3, cl = li & 7;
     const int grpY = li >> 2, grpC = cl >> 1;   // which 4-line strength segment a line belongs to
+    const uint32_t pairs = ((uint32_t)g.nStreams + 1u) / 2u, serial16 = p.serial & 0xFFFFu;
+    const int W = g.widthMbs;
+    const size_t stripY = (size_t)g.rowsY * 16, stripC = (size_t)g.rowsC * 16;
     __syncthreads();   // the tables
     for (;;) {
-        // every warp takes its own tickets (no CTA barrier: a warp that waits for a neighbour does not hold up the others)
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(p.ticket, p.filterChunk);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= p.totalTickets) break;
-        // lane j < filterChunk walks the dependent loads of the warp's ticket j (order -> work flag -> record, strengths,
-        // neighbours), all tickets at once: one chain of memory latencies per chunk instead of one per macroblock
-        FilterMeta m;
-        m.mb = m.s = m.w0 = m.w3 = m.qp = m.work = 0;
-        m.bw = make_uint4(0, 0, 0, 0);
-        m.frame = 0;
-        if (lane < (int)p.filterChunk) {
-            const uint32_t t = base + lane;
-            if (t < p.totalTickets) {
-                const uint32_t k = t / (uint32_t)g.nStreams, s = t - k * (uint32_t)g.nStreams;
-                const uint32_t mb = p.order[k];
-                const size_t sIdx = (size_t)s * g.nMbs;
-                if (p.work[sIdx + mb]) {   // else nothing to filter: this macroblock touches no pel
-                    const int mby = mbRowOf(mb, g), mbx = (int)(mb - (uint32_t)mby * g.widthMbs);
-                    const StreamJob job = p.jobs[s];
-                    const uint32_t *cw = reinterpret_cast<const uint32_t *>(job.recs + mb);
-                    m.w0 = __ldg(cw); m.w3 = __ldg(cw + 3);
-                    m.bw = __ldg(reinterpret_cast<const uint4 *>(p.bsWords + (sIdx + mb) * 4));
-                    const int flags = m.w0 >> 24;
+        // every warp takes its own tickets (no CTA barrier): ticket = (row, pair of streams), row-major
+        uint32_t ticket = 0;
+        if (lane == 0) ticket = atomicAdd(p.ticket, 1u);
+        ticket = __shfl_sync(0xffffffffu, ticket, 0);
+        if (ticket >= p.totalTickets) break;
+        const int y = (int)(ticket / pairs);
+        const uint32_t s0 = 2u * (ticket - (uint32_t)y * pairs);
+        const bool live = s0 + half < (uint32_t)g.nStreams;     // (an odd stream count leaves the last half idle: it shadows half 0)
+        const uint32_t s = live ? s0 + half : s0;
+        const StreamJob job = p.jobs[s];
+        uint8_t *frame = p.pool + (unsigned long long)(s * (uint32_t)g.numSlots + job.curSlot) * g.frameStride;
+        const b200_mb_rec *recsRow = job.recs + (size_t)y * W;
+        const size_t rowIdx = (size_t)s * g.nMbs + (size_t)y * W;
+        uint32_t *rowMine = p.done + (size_t)s * g.heightMbs + y;
+        uint32_t seen = 0;    // macroblocks the row above is known to have finished
+#pragma unroll 1
+        for (int x0 = 0; x0 < W; x0 += 16) {
+            // lane i of the half gathers what macroblock x0 + i needs (work flag -> record, strengths, neighbours' qp): one chain
+            // of memory latencies per 16 macroblocks
+            uint32_t mW0 = 0, mW3 = 0, mQp = 0, mWork = 0;
+            uint4 mBw = make_uint4(0, 0, 0, 0);
+            {
+                const int x = x0 + li;
+                if (x < W && p.work[rowIdx + x]) {   // else nothing to filter: this macroblock touches no pel
+                    const uint32_t *cw = reinterpret_cast<const uint32_t *>(recsRow + x);
+                    mW0 = __ldg(cw); mW3 = __ldg(cw + 3);
+                    mBw = __ldg(reinterpret_cast<const uint4 *>(p.bsWords + (rowIdx + x) * 4));
+                    const int flags = mW0 >> 24;
                     // qp of the neighbours filtered against (never read otherwise: they may not exist)
-                    const uint32_t qp = (m.w0 >> 8) & 0xFF;
+                    const uint32_t qp = (mW0 >> 8) & 0xFF;
                     const uint32_t qpL = (flags & B200_MBF_FILTER_LEFT) ? (__ldg(cw - 24) >> 8) & 0xFF : qp;
-                    const uint32_t qpT = (flags & B200_MBF_FILTER_TOP) ? (__ldg(cw - 24 * g.widthMbs) >> 8) & 0xFF : qp;
-                    m.qp = qpL | (qpT << 8);
-                    // bits 1..3: wait for the left / top / top-right neighbour (it exists and has work)
-                    m.work = 1;
-                    if (mbx > 0 && p.work[sIdx + mb - 1]) m.work |= 2;
-                    if (mby > 0 && p.work[sIdx + mb - g.widthMbs]) m.work |= 4;
-                    if (mby > 0 && mbx < g.widthMbs - 1 && p.work[sIdx + mb - g.widthMbs + 1]) m.work |= 8;
-                    m.mb = mb; m.s = s;
-                    m.frame = (unsigned long long)(s * (uint32_t)g.numSlots + job.curSlot) * g.frameStride;
+                    const uint32_t qpT = (flags & B200_MBF_FILTER_TOP) ? (__ldg(cw - 24 * W) >> 8) & 0xFF : qp;
+                    mQp = qpL | (qpT << 8);
+                    mWork = 1;
                 }
             }
-        }
-        // the tickets with work, two at a time: half 0 takes the first, half 1 the second -- unless both belong to the same
-        // stream (fewer streams than tickets in a chunk): the second might depend on the first, it then waits for its own turn
-        uint32_t todo = __ballot_sync(0xffffffffu, m.work != 0);
+            uint32_t todo = (__ballot_sync(0xffffffffu, mWork != 0) >> (16 * half)) & 0xFFFFu;
 #pragma unroll 1
-        while (todo) {
-            const int ja = __ffs(todo) - 1;
-            todo &= todo - 1;
-            int jb = todo ? __ffs(todo) - 1 : -1;
-            if (jb >= 0 && __shfl_sync(0xffffffffu, m.s, jb) == __shfl_sync(0xffffffffu, m.s, ja)) jb = -1;
-            if (jb >= 0) todo &= todo - 1;
-            const int j = (half && jb >= 0) ? jb : ja;          // the ticket this half works on
-            const bool active = !half || jb >= 0;               // (without a second macroblock half 1 shadows half 0 and stores nothing)
-            const uint32_t workBits = __shfl_sync(0xffffffffu, m.work, j);
-            const uint32_t mb = __shfl_sync(0xffffffffu, m.mb, j), s = __shfl_sync(0xffffffffu, m.s, j);
-            const uint32_t w0 = __shfl_sync(0xffffffffu, m.w0, j), w3 = __shfl_sync(0xffffffffu, m.w3, j);
-            const uint32_t qpn = __shfl_sync(0xffffffffu, m.qp, j);
-            uint4 bw;
-            bw.x = __shfl_sync(0xffffffffu, m.bw.x, j); bw.y = __shfl_sync(0xffffffffu, m.bw.y, j);
-            bw.z = __shfl_sync(0xffffffffu, m.bw.z, j); bw.w = __shfl_sync(0xffffffffu, m.bw.w, j);
-            uint8_t *frame = p.pool + __shfl_sync(0xffffffffu, m.frame, j);
-            const size_t sIdx = (size_t)s * g.nMbs;
-            const int mby = mbRowOf(mb, g), mbx = (int)(mb - (uint32_t)mby * g.widthMbs);
-            uint32_t *doneS = p.done + sIdx;
-            const int qp = (w0 >> 8) & 0xFF, qpL = qpn & 0xFF, qpT = (qpn >> 8) & 0xFF;
-            if (active && li < 3 && ((workBits >> (li + 1)) & 1)) {
-                const int nmb = li == 0 ? (int)mb - 1 : li == 1 ? (int)mb - g.widthMbs : (int)mb - g.widthMbs + 1;
-                waitFlag(doneS + nmb, p.serial);
-            }
-            __syncwarp();
-            // stage 20 luma rows and 2 x 10 chroma rows (incl. 4 / 2 rows of the upper and 4 columns of the left neighbour): the
-            // 20 luma rows are 320 contiguous bytes of the macroblock's strip, the columns of the left neighbour the last 4 bytes
-            // of the same rows one strip earlier; a chroma row holds 8 Cb | 8 Cr
-            uint8_t *lum = mbLuma(frame, g, mbx, mby) - 4 * 16, *chr = mbChroma(frame, g, mbx, mby) - 2 * 16;
-            const size_t stripY = (size_t)g.rowsY * 16, stripC = (size_t)g.rowsC * 16;
-#pragma unroll
-            for (int rd = 0; rd < 2; rd++) {
-                const int r = li + 16 * rd;
-                if (r < 20) {
-                    const uint4 own = __ldcg(reinterpret_cast<const uint4 *>(lum + r * 16));
-                    const uint32_t lef = __ldcg(reinterpret_cast<const uint32_t *>(lum + r * 16 - stripY + 12));
-                    *reinterpret_cast<uint4 *>(&sm.y[r][16]) = own;
-                    *reinterpret_cast<uint32_t *>(&sm.y[r][12]) = lef;
-                    const int pl = r >= 10, cr = r - pl * 10;
-                    const uint2 cown = __ldcg(reinterpret_cast<const uint2 *>(chr + cr * 16 + pl * 8));
-                    const uint32_t clef = __ldcg(reinterpret_cast<const uint32_t *>(chr + cr * 16 + pl * 8 - stripC + 4));
-                    *reinterpret_cast<uint2 *>(&sm.c[pl][cr][8]) = cown;
-                    *reinterpret_cast<uint32_t *>(&sm.c[pl][cr][4]) = clef;
-                }
-            }
-            // thresholds: GetLumaEdgeThresholds :1390-1458, GetChromaEdgeThresholds :1469-1541
-            const int offA = (int)(int8_t)(w3 & 0xFF), offB = (int)(int8_t)((w3 >> 8) & 0xFF), cqo = (int)(int8_t)((w3 >> 16) & 0xFF);
-            __syncwarp();
-
-#pragma unroll 1
-            for (int pass = 0; pass < 2; pass++) {
-                // pass 0: luma lines (16 per macroblock), pass 1: chroma lines (2 planes x 8)
-                const bool chroma = pass != 0;
-                const int qs = chroma ? tb.qpc[clip3(0, 51, qp + cqo)] : qp;
-                const int qsL = chroma ? tb.qpc[clip3(0, 51, qpL + cqo)] : qpL;
-                const int qsT = chroma ? tb.qpc[clip3(0, 51, qpT + cqo)] : qpT;
-                const EdgeThr tIn = makeThr(tb, qs, offA, offB);
-                const EdgeThr tL = makeThr(tb, (qs + qsL + 1) >> 1, offA, offB), tT = makeThr(tb, (qs + qsT + 1) >> 1, offA, offB);
-                const int grp = chroma ? grpC : grpY;
-                uint8_t *rowp = chroma ? &sm.c[cpl][2 + cl][8] : &sm.y[4 + li][16];    // sample (0, line)
-                uint8_t *colp = chroma ? &sm.c[cpl][2][8 + cl] : &sm.y[4][16 + li];    // sample (line, 0)
-                const int pitch = chroma ? 16 : 32;
-                const int estep = chroma ? 2 : 4;                            // pels between edge e and e + 1 (luma numbering)
-                // vertical edges: segment (grp, e) is nibble (grp & 1) * 4 + e of word grp >> 1
-                const uint32_t vWord = (grp >> 1) ? bw.y : bw.x;
-                const uint32_t vAny = bw.x | bw.y;   // (per lane: the halves differ)
-#pragma unroll 1
-                for (int e = 0; e < 4; e += (chroma ? 2 : 1)) {
-                    // no strength on this edge in any row of either macroblock: skip (warp-uniform)
-                    if (!__any_sync(0xffffffffu, ((vAny >> (4 * e)) & 0x000F000Fu) != 0)) continue;
-                    const int bs = bsNibble(vWord, (grp & 1) * 4 + e);
-                    if (bs) {
-                        uint32_t *wp = reinterpret_cast<uint32_t *>(rowp + e * estep);
-                        const uint32_t P = wp[-1], Q = wp[0];
-                        EdgeLine v;
-                        v.p3 = P & 0xFF; v.p2 = (P >> 8) & 0xFF; v.p1 = (P >> 16) & 0xFF; v.p0 = P >> 24;
-                        v.q0 = Q & 0xFF; v.q1 = (Q >> 8) & 0xFF; v.q2 = (Q >> 16) & 0xFF; v.q3 = Q >> 24;
-                        const EdgeThr &th = e ? tIn : tL;
-                        if (filterLine(v, bs, th, tb.tc0[th.idxA][bs - 1], chroma)) {
-                            wp[-1] = (uint32_t)v.p3 | ((uint32_t)(v.p2 & 0xFF) << 8) | ((uint32_t)(v.p1 & 0xFF) << 16) | ((uint32_t)v.p0 << 24);
-                            wp[0] = (uint32_t)(v.q0 & 0xFF) | ((uint32_t)(v.q1 & 0xFF) << 8) | ((uint32_t)(v.q2 & 0xFF) << 16) | ((uint32_t)v.q3 << 24);
-                        }
-                    }
-                }
-                __syncwarp();
-                // horizontal edges: segment 16 + e * 4 + grp is nibble (e & 1) * 4 + grp of word 2 + (e >> 1)
-#pragma unroll 1
-                for (int e = 0; e < 4; e += (chroma ? 2 : 1)) {
-                    const uint32_t hWord = (e >> 1) ? bw.w : bw.z;
-                    if (!__any_sync(0xffffffffu, ((hWord >> ((e & 1) * 16)) & 0xFFFFu) != 0)) continue;   // no strength on this edge in any column
-                    const int bs = bsNibble(hWord, (e & 1) * 4 + grp);
-                    if (bs) {
-                        uint8_t *q = colp + e * estep * pitch;
-                        EdgeLine v;
-                        v.p0 = q[-pitch]; v.p1 = q[-2 * pitch]; v.q0 = q[0]; v.q1 = q[pitch];
-                        if (chroma) { v.p2 = v.p3 = v.q2 = v.q3 = 0; }   // outside the chroma tile for the top edge; never used
-                        else { v.p2 = q[-3 * pitch]; v.p3 = q[-4 * pitch]; v.q2 = q[2 * pitch]; v.q3 = q[3 * pitch]; }
-                        const EdgeLine o = v;
-                        const EdgeThr &th = e ? tIn : tT;
-                        if (filterLine(v, bs, th, tb.tc0[th.idxA][bs - 1], chroma)) {
-                            q[-pitch] = (uint8_t)v.p0; q[0] = (uint8_t)v.q0;
-                            if (v.p1 != o.p1) q[-2 * pitch] = (uint8_t)v.p1;
-                            if (v.q1 != o.q1) q[pitch] = (uint8_t)v.q1;
-                            if (v.p2 != o.p2) q[-3 * pitch] = (uint8_t)v.p2;
-                            if (v.q2 != o.q2) q[2 * pitch] = (uint8_t)v.q2;
-                        }
-                    }
-                }
-                __syncwarp();
-            }
-            // write back: own rows incl. the 4 columns of the left neighbour, and the 4 (2) rows of the upper neighbour
-            if (active) {
+            while (__any_sync(0xffffffffu, todo != 0)) {
+                const bool active = live && todo != 0;
+                const int i = todo ? __ffs(todo) - 1 : 0;
+                todo &= todo - 1;
+                const int src = half * 16 + i, x = x0 + i;
+                const uint32_t w0 = __shfl_sync(0xffffffffu, mW0, src), w3 = __shfl_sync(0xffffffffu, mW3, src);
+                const uint32_t qpn = __shfl_sync(0xffffffffu, mQp, src);
+                uint4 bw;
+                bw.x = __shfl_sync(0xffffffffu, mBw.x, src); bw.y = __shfl_sync(0xffffffffu, mBw.y, src);
+                bw.z = __shfl_sync(0xffffffffu, mBw.z, src); bw.w = __shfl_sync(0xffffffffu, mBw.w, src);
+                if (!active) bw = make_uint4(0, 0, 0, 0);
+                const int qp = (w0 >> 8) & 0xFF, qpL = qpn & 0xFF, qpT = (qpn >> 8) & 0xFF;
+                // the row above must have finished macroblocks x and x + 1
+                const uint32_t need = (active && y > 0) ? (uint32_t)min(x + 2, W) : 0u;
+                if (li == 0 && seen < need) seen = waitRow(rowMine - 1, serial16, need);
+                seen = __shfl_sync(0xffffffffu, seen, half * 16);
+                // stage 20 luma rows and 2 x 10 chroma rows (incl. 4 / 2 rows of the upper and 4 columns of the left neighbour): the
+                // 20 luma rows are 320 contiguous bytes of the macroblock's strip, the columns of the left neighbour the last 4 bytes
+                // of the same rows one strip earlier; a chroma row holds 8 Cb | 8 Cr
+                uint8_t *lum = mbLuma(frame, g, x, y) - 4 * 16, *chr = mbChroma(frame, g, x, y) - 2 * 16;
 #pragma unroll
                 for (int rd = 0; rd < 2; rd++) {
                     const int r = li + 16 * rd;
                     if (r < 20) {
-                        if (r >= 4 || mby > 0) *reinterpret_cast<uint4 *>(lum + r * 16) = *reinterpret_cast<const uint4 *>(&sm.y[r][16]);
-                        if (r >= 4 && mbx > 0) *reinterpret_cast<uint32_t *>(lum + r * 16 - stripY + 12) = *reinterpret_cast<const uint32_t *>(&sm.y[r][12]);
+                        const uint4 own = __ldcg(reinterpret_cast<const uint4 *>(lum + r * 16));
+                        const uint32_t lef = __ldcg(reinterpret_cast<const uint32_t *>(lum + r * 16 - stripY + 12));
+                        *reinterpret_cast<uint4 *>(&sm.y[r][16]) = own;
+                        *reinterpret_cast<uint32_t *>(&sm.y[r][12]) = lef;
                         const int pl = r >= 10, cr = r - pl * 10;
-                        if (cr >= 2 || mby > 0) *reinterpret_cast<uint2 *>(chr + cr * 16 + pl * 8) = *reinterpret_cast<const uint2 *>(&sm.c[pl][cr][8]);
-                        if (cr >= 2 && mbx > 0) *reinterpret_cast<uint32_t *>(chr + cr * 16 + pl * 8 - stripC + 4) = *reinterpret_cast<const uint32_t *>(&sm.c[pl][cr][4]);
+                        const uint2 cown = __ldcg(reinterpret_cast<const uint2 *>(chr + cr * 16 + pl * 8));
+                        const uint32_t clef = __ldcg(reinterpret_cast<const uint32_t *>(chr + cr * 16 + pl * 8 - stripC + 4));
+                        *reinterpret_cast<uint2 *>(&sm.c[pl][cr][8]) = cown;
+                        *reinterpret_cast<uint32_t *>(&sm.c[pl][cr][4]) = clef;
                     }
                 }
+                // thresholds: GetLumaEdgeThresholds :1390-1458, GetChromaEdgeThresholds :1469-1541
+                const int offA = (int)(int8_t)(w3 & 0xFF), offB = (int)(int8_t)((w3 >> 8) & 0xFF), cqo = (int)(int8_t)((w3 >> 16) & 0xFF);
+                __syncwarp();
+
+#pragma unroll 1
+                for (int pass = 0; pass < 2; pass++) {
+                    // pass 0: luma lines (16 per macroblock), pass 1: chroma lines (2 planes x 8)
+                    const bool chroma = pass != 0;
+                    const int qs = chroma ? tb.qpc[clip3(0, 51, qp + cqo)] : qp;
+                    const int qsL = chroma ? tb.qpc[clip3(0, 51, qpL + cqo)] : qpL;
+                    const int qsT = chroma ? tb.qpc[clip3(0, 51, qpT + cqo)] : qpT;
+                    const EdgeThr tIn = makeThr(tb, qs, offA, offB);
+                    const EdgeThr tL = makeThr(tb, (qs + qsL + 1) >> 1, offA, offB), tT = makeThr(tb, (qs + qsT + 1) >> 1, offA, offB);
+                    const int grp = chroma ? grpC : grpY;
+                    uint8_t *rowp = chroma ? &sm.c[cpl][2 + cl][8] : &sm.y[4 + li][16];    // sample (0, line)
+                    uint8_t *colp = chroma ? &sm.c[cpl][2][8 + cl] : &sm.y[4][16 + li];    // sample (line, 0)
+                    const int pitch = chroma ? 16 : 32;
+                    const int estep = chroma ? 2 : 4;                            // pels between edge e and e + 1 (luma numbering)
+                    // vertical edges: segment (grp, e) is nibble (grp & 1) * 4 + e of word grp >> 1
+                    const uint32_t vWord = (grp >> 1) ? bw.y : bw.x;
+                    const uint32_t vAny = bw.x | bw.y;   // (per lane: the halves differ)
+#pragma unroll 1
+                    for (int e = 0; e < 4; e += (chroma ? 2 : 1)) {
+                        // no strength on this edge in any row of either macroblock: skip (warp-uniform)
+                        if (!__any_sync(0xffffffffu, ((vAny >> (4 * e)) & 0x000F000Fu) != 0)) continue;
+                        const int bs = bsNibble(vWord, (grp & 1) * 4 + e);
+                        if (bs) {
+                            uint32_t *wp = reinterpret_cast<uint32_t *>(rowp + e * estep);
+                            const uint32_t P = wp[-1], Q = wp[0];
+                            EdgeLine v;
+                            v.p3 = P & 0xFF; v.p2 = (P >> 8) & 0xFF; v.p1 = (P >> 16) & 0xFF; v.p0 = P >> 24;
+                            v.q0 = Q & 0xFF; v.q1 = (Q >> 8) & 0xFF; v.q2 = (Q >> 16) & 0xFF; v.q3 = Q >> 24;
+                            const EdgeThr &th = e ? tIn : tL;
+                            if (filterLine(v, bs, th, tb.tc0[th.idxA][bs - 1], chroma)) {
+                                wp[-1] = (uint32_t)v.p3 | ((uint32_t)(v.p2 & 0xFF) << 8) | ((uint32_t)(v.p1 & 0xFF) << 16) | ((uint32_t)v.p0 << 24);
+                                wp[0] = (uint32_t)(v.q0 & 0xFF) | ((uint32_t)(v.q1 & 0xFF) << 8) | ((uint32_t)(v.q2 & 0xFF) << 16) | ((uint32_t)v.q3 << 24);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    // horizontal edges: segment 16 + e * 4 + grp is nibble (e & 1) * 4 + grp of word 2 + (e >> 1)
+#pragma unroll 1
+                    for (int e = 0; e < 4; e += (chroma ? 2 : 1)) {
+                        const uint32_t hWord = (e >> 1) ? bw.w : bw.z;
+                        if (!__any_sync(0xffffffffu, ((hWord >> ((e & 1) * 16)) & 0xFFFFu) != 0)) continue;   // no strength on this edge in any column
+                        const int bs = bsNibble(hWord, (e & 1) * 4 + grp);
+                        if (bs) {
+                            uint8_t *q = colp + e * estep * pitch;
+                            EdgeLine v;
+                            v.p0 = q[-pitch]; v.p1 = q[-2 * pitch]; v.q0 = q[0]; v.q1 = q[pitch];
+                            if (chroma) { v.p2 = v.p3 = v.q2 = v.q3 = 0; }   // outside the chroma tile for the top edge; never used
+                            else { v.p2 = q[-3 * pitch]; v.p3 = q[-4 * pitch]; v.q2 = q[2 * pitch]; v.q3 = q[3 * pitch]; }
+                            const EdgeLine o = v;
+                            const EdgeThr &th = e ? tIn : tT;
+                            if (filterLine(v, bs, th, tb.tc0[th.idxA][bs - 1], chroma)) {
+                                q[-pitch] = (uint8_t)v.p0; q[0] = (uint8_t)v.q0;
+                                if (v.p1 != o.p1) q[-2 * pitch] = (uint8_t)v.p1;
+                                if (v.q1 != o.q1) q[pitch] = (uint8_t)v.q1;
+                                if (v.p2 != o.p2) q[-3 * pitch] = (uint8_t)v.p2;
+                                if (v.q2 != o.q2) q[2 * pitch] = (uint8_t)v.q2;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+                // write back: own rows incl. the 4 columns of the left neighbour, and the 4 (2) rows of the upper neighbour
+                if (active) {
+#pragma unroll
+                    for (int rd = 0; rd < 2; rd++) {
+                        const int r = li + 16 * rd;
+                        if (r < 20) {
+                            if (r >= 4 || y > 0) *reinterpret_cast<uint4 *>(lum + r * 16) = *reinterpret_cast<const uint4 *>(&sm.y[r][16]);
+                            if (r >= 4 && x > 0) *reinterpret_cast<uint32_t *>(lum + r * 16 - stripY + 12) = *reinterpret_cast<const uint32_t *>(&sm.y[r][12]);
+                            const int pl = r >= 10, cr = r - pl * 10;
+                            if (cr >= 2 || y > 0) *reinterpret_cast<uint2 *>(chr + cr * 16 + pl * 8) = *reinterpret_cast<const uint2 *>(&sm.c[pl][cr][8]);
+                            if (cr >= 2 && x > 0) *reinterpret_cast<uint32_t *>(chr + cr * 16 + pl * 8 - stripC + 4) = *reinterpret_cast<const uint32_t *>(&sm.c[pl][cr][4]);
+                        }
+                    }
+                }
+                // publish the row's progress: everything before the half's next macroblock with work (or the end of this group)
+                // is finished.  The warp barrier orders every lane's stores before the release of lane 0 of each half, and a
+                // release at gpu scope is cumulative (the same pattern as a CTA semaphore: barrier, then st.release by one thread)
+                __syncwarp();
+                if (active && li == 0) stRelease(rowMine, (serial16 << 16) | (uint32_t)min(todo ? x0 + __ffs(todo) - 1 : x0 + 16, W));
             }
-            // publish: the warp barrier orders every lane's stores before the release of lane 0 of each half, and a release at
-            // gpu scope is cumulative (the same pattern as a CTA semaphore: barrier, then st.release by one thread)
+            // a group without work (or whose last macroblock had none) still moves the row on
             __syncwarp();
-            if (active && li == 0) stRelease(doneS + mb, p.serial);
+            if (live && li == 0) stRelease(rowMine, (serial16 << 16) | (uint32_t)min(x0 + 16, W));
         }
     }
 }

@@ -38,6 +38,23 @@ __device__ __forceinline__ void waitFlag(const uint32_t *p, uint32_t serial) {
     }
 }
 
+// progress of a macroblock row: serial << 16 | macroblocks finished
+__device__ __forceinline__ uint32_t waitRow(const uint32_t *p, uint32_t serial16, uint32_t need) {
+    unsigned ns = 20, spins = 0;
+    unsigned long long t0 = 0;
+    for (;;) {
+        const uint32_t v = ldAcquire(p);
+        if ((v >> 16) == serial16 && (v & 0xFFFFu) >= need) return v & 0xFFFFu;
+        __nanosleep(ns);
+        if (ns < 640) ns <<= 1;
+        if ((++spins & 1023u) == 0) {
+            const unsigned long long now = globalTimerNs();
+            if (!t0) t0 = now;
+            else if (now - t0 > kWatchdogNs) { atomicAdd(&gWatchdog[0], 1u); return need; }
+        }
+    }
+}
+
 // ---- TMA / mbarrier -------------------------------------------------------------------------------
 __device__ __forceinline__ void mbarWait(uint64_t *bar, uint32_t parity) {
     unsigned spins = 0;

@@ -157,11 +157,13 @@ bool Batch::create(int device, uint32_t nStreams, uint32_t widthMbs, uint32_t he
             for (int v = 0; v < 2; v++)
                 if (!encodeStripMap(enc, &m->chroma[nx - 1][v], pool_ + g.offC, g, g.rowsC, nFrames, nx, v ? 9 : 8)) return false;
     }
-    int occA = 1, occD = 0, occS = 0;
+    int occA = 1, occD = 0, occS = 0, occB = 0;
     CK(cudaFuncSetAttribute(passAKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(PassAWarpSmem) * kReconWarps)));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occA, passAKernel, kReconWarps * 32, sizeof(PassAWarpSmem) * kReconWarps));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occD, deblockKernel, kDeblockWarps * 32, 0));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, strengthKernel, kDeblockWarps * 32, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occB, reconIntraKernel, kReconWarps * 32, 0));
+    intraBlocks_ = std::max(1, occB) * numSms_;
     strengthBlocks_ = std::max(1, occS) * numSms_;
     passABlocks_ = std::max(1, occA) * numSms_;
     deblockBlocks_ = std::max(1, occD) * numSms_;
@@ -170,7 +172,6 @@ bool Batch::create(int device, uint32_t nStreams, uint32_t widthMbs, uint32_t he
     chunkRows_ = (heightMbs + chunksPerCol_ - 1) / chunksPerCol_;
     // tuning knobs (defaults are the measured best on the 512-stream 1080p batch)
     if (const char *e = std::getenv("B200_CHUNK_B")) chunkB_ = std::max(1, std::min((int)kChunkB, std::atoi(e)));
-    if (const char *e = std::getenv("B200_FILTER_CHUNK")) filterChunk_ = std::max(1, std::min((int)kFilterChunk, std::atoi(e)));
     tapes_.assign(nStreams, DevTape());
     CK(cudaStreamCreateWithFlags(&auxStream_, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&joinEv_, cudaEventDisableTiming));
@@ -366,7 +367,6 @@ bool Batch::kernelTimes(float ms[6], uint32_t *launchesPerStage) {
 }
 
 bool Batch::launchPicture(const StreamJob *dJobs, const StreamJob *dJobsFilter, uint32_t maxB, uint32_t maxE, bool recon, bool deblock) {
-    const uint32_t total = (uint32_t)g_.nStreams * (uint32_t)g_.nMbs;
     serial_++;
     auto mark = [&](int stageEnded) {
         if (!timing_) return;
@@ -390,11 +390,11 @@ bool Batch::launchPicture(const StreamJob *dJobs, const StreamJob *dJobsFilter, 
     }
     DeblockParams dp;
     if (deblock) {
-        dp.pool = pool_; dp.g = g_; dp.jobs = dJobsFilter; dp.order = dOrder_; dp.done = dDoneDeblock_;
-        dp.ticket = dCounters_ + 1; dp.serial = serial_; dp.totalTickets = total;
+        dp.pool = pool_; dp.g = g_; dp.jobs = dJobsFilter; dp.done = dDoneDeblock_;
+        dp.ticket = dCounters_ + 1; dp.serial = serial_;
+        dp.totalTickets = (uint32_t)g_.heightMbs * (((uint32_t)g_.nStreams + 1u) / 2u);
         dp.bsWords = dBsWords_; dp.work = dWork_;
         dp.workCount = reinterpret_cast<unsigned long long *>(dCounters_ + 4);
-        dp.filterChunk = (uint32_t)filterChunk_;
     }
     auto launchStrength = [&](cudaStream_t st) {
         const uint32_t chunks = ((uint32_t)g_.nMbs + kDeblockWarps * 32 - 1) / (kDeblockWarps * 32) * (uint32_t)g_.nStreams;
@@ -416,7 +416,8 @@ bool Batch::launchPicture(const StreamJob *dJobs, const StreamJob *dJobsFilter, 
             mark(0);
         }
         if (maxB) {
-            reconIntraKernel<<<(rp.chunksB * (uint32_t)g_.nStreams + kReconWarps - 1) / kReconWarps, kReconWarps * 32, 0, stream_>>>(rp);
+            const uint32_t ctasB = ((uint32_t)g_.heightMbs * (uint32_t)g_.nStreams + kReconWarps - 1) / kReconWarps;
+            reconIntraKernel<<<std::min<uint32_t>(ctasB, (uint32_t)intraBlocks_), kReconWarps * 32, 0, stream_>>>(rp);
             launches_++;
             mark(3);
         }
@@ -435,7 +436,7 @@ bool Batch::launchPicture(const StreamJob *dJobs, const StreamJob *dJobsFilter, 
             launchStrength(stream_);
             mark(4);
         }
-        const uint32_t ctas = (total + kDeblockWarps * filterChunk_ - 1) / (kDeblockWarps * filterChunk_);
+        const uint32_t ctas = (dp.totalTickets + kDeblockWarps - 1) / kDeblockWarps;
         deblockKernel<<<std::min<uint32_t>(ctas, (uint32_t)deblockBlocks_), kDeblockWarps * 32, 0, stream_>>>(dp);
         launches_++;
         mark(1);

@@ -89,12 +89,12 @@ private:
     uint8_t *dWork_ = nullptr;
     int strengthBlocks_ = 0;
     uint32_t serial_ = 0;
-    int passABlocks_ = 0, deblockBlocks_ = 0;
+    int passABlocks_ = 0, deblockBlocks_ = 0, intraBlocks_ = 0;
     uint32_t chunkRows_ = 32, chunksPerCol_ = 1;
     cudaEvent_t syncEv_ = nullptr, forkEv_ = nullptr, joinEv_ = nullptr;
     size_t jobsCap_ = 0;
     uint32_t *dConvertAll_ = nullptr;
-    int chunkB_ = 1, filterChunk_ = 8;   // list entries per intra warp task / tickets per filter warp step
+    int chunkB_ = 1;   // list entries per intra warp task
     cudaStream_t uploadStream_ = nullptr;
     std::deque<std::pair<uint32_t, cudaEvent_t>> fences_;   // (pictures below this index, upload-stream event)
     std::vector<cudaEvent_t> fenceFree_;

@@ -840,50 +840,64 @@ passAKernel(const ReconParams p, const __grid_constant__ PassAMaps maps) {
 
 // =====================================================================================================
 // pass B: intra-predicted macroblocks.  They read the unfiltered current picture, so an intra macroblock
-// must come after its intra neighbours (the others were written by pass A).  CTAs take tickets; a
-// ticket is kReconWarps warp tasks; warp task w is chunk w / nStreams of stream w % nStreams of the stream's
-// wavefront-ordered list.  A warp works through its chunk in list order, so dependencies inside a chunk cost nothing,
-// the warps of a CTA belong to different streams (they never wait for each other), and a warp only ever waits for
-// chunks whose CTA took an earlier ticket.
+// must come after its intra neighbours (the others were written by pass A).  A warp owns one macroblock row of one
+// stream: it reads the row's record heads 32 at a time, picks the intra-predicted ones and works through them left to right,
+// so the left neighbour is its own previous step; rows publish their progress in a per-row counter and a macroblock whose
+// upper neighbours are intra-predicted waits until the row above is past them.  Tickets are handed out row-major (row y of
+// every stream before row y + 1 of any), so the row above is normally through long before and a warp only ever waits for rows
+// with earlier tickets.
 // =====================================================================================================
 __global__ void __launch_bounds__(kReconWarps * 32, 5) reconIntraKernel(const ReconParams p) {
     __shared__ IntraWarpSmem smemAll[kReconWarps];
     __shared__ uint32_t sI4Table[9 * 16];
-    __shared__ uint32_t sTicket;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const PoolGeom &g = p.g;
-    if (threadIdx.x == 0) sTicket = atomicAdd(p.ticket, 1u);
     if (threadIdx.x < 9 * 16) sI4Table[threadIdx.x] = gIntra4x4Table[threadIdx.x];
     __syncthreads();
-    const uint32_t t = sTicket * kReconWarps + warp;
-    const uint32_t chunk = t / (uint32_t)g.nStreams, s = t - chunk * (uint32_t)g.nStreams;
-    if (chunk >= p.chunksB) return;
-    const StreamJob job = p.jobs[s];
-    const uint32_t e0 = chunk * p.chunkB;
-    if (e0 >= job.nB) return;
-    const int n = min(p.chunkB, job.nB - e0);
     IntraWarpSmem &sm = smemAll[warp];
-    uint32_t *doneS = p.done + (size_t)s * g.nMbs;
-    uint8_t *cur = framePtr(p.pool, g, s * (uint32_t)g.numSlots + job.curSlot);
+    const int W = g.widthMbs;
+    const uint32_t serial16 = p.serial & 0xFFFFu, totalRows = (uint32_t)g.heightMbs * (uint32_t)g.nStreams;
     // this lane's spans inside a macroblock, as in pass A: 8 luma samples = bytes 8 lane.. of the 256, 4 chroma samples =
     // bytes 4 lane.. of the 128
     const int r8 = lane >> 1, c8 = (lane & 1) * 8;
     const int cr = lane >> 2, cp = (lane >> 1) & 1, cc = (lane & 1) * 4;
-
-    // lane j < n fetches entry j's address and record head: one chain of dependent loads per chunk
-    uint32_t mMb = 0, mMisc = 0;
-    uint4 mHead = make_uint4(0, 0, 0, 0);
-    if (lane < n) {
-        mMb = __ldg(job.orderB + e0 + lane);
-        const uint32_t *rw = reinterpret_cast<const uint32_t *>(job.recs + mMb);
-        mHead = __ldg(reinterpret_cast<const uint4 *>(rw));
-        mMisc = (__ldg(rw + 5) & 0xFF) | ((__ldg(rw + 7) & 0xFF) << 8);
-    }
+    for (;;) {
+    uint32_t ticket = 0;
+    if (lane == 0) ticket = atomicAdd(p.ticket, 1u);
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    if (ticket >= totalRows) break;
+    const int mby = (int)(ticket / (uint32_t)g.nStreams);
+    const uint32_t s = ticket - (uint32_t)mby * (uint32_t)g.nStreams;
+    const StreamJob job = p.jobs[s];
+    if (!job.nB) continue;
+    uint32_t *rowMine = p.done + (size_t)s * g.heightMbs + mby;
+    uint8_t *cur = framePtr(p.pool, g, s * (uint32_t)g.numSlots + job.curSlot);
+    const b200_mb_rec *recsRow = job.recs + (size_t)mby * W;
+    uint32_t seen = 0;      // macroblocks of the row above known to be through
+    bool any = false;       // this row has had an intra-predicted macroblock (only such rows are ever waited for)
 #pragma unroll 1
-    for (int i = 0; i < n; i++) {
-        const uint32_t mb = __shfl_sync(0xffffffffu, mMb, i);
-        const int mby = (int)(mb / (uint32_t)g.widthMbs), mbx = (int)(mb - (uint32_t)mby * g.widthMbs);
-        const b200_mb_rec *rec = job.recs + mb;
+    for (int x0 = 0; x0 < W; x0 += 32) {
+    // lane i reads the head of record x0 + i: which macroblocks of this stretch are intra-predicted
+    uint32_t mMisc = 0;
+    uint4 mHead = make_uint4(0, 0, 0, 0);
+    bool isIntra = false;
+    if (x0 + lane < W) {
+        const uint32_t *rw = reinterpret_cast<const uint32_t *>(recsRow + x0 + lane);
+        mHead = __ldg(reinterpret_cast<const uint4 *>(rw));
+        const uint32_t type = mHead.x & 0xFFu;
+        // (a concealed macroblock carries Intra4x4 for the filter's sake; its pels come from pass A or concealKernel)
+        isIntra = type > B200_MB_P_8x8REF0 && type != B200_MB_I_PCM && !((mHead.x >> 24) & B200_MBF_CONCEALED);
+        if (isIntra) mMisc = (__ldg(rw + 5) & 0xFF) | ((__ldg(rw + 7) & 0xFF) << 8);
+    }
+    uint32_t todo = __ballot_sync(0xffffffffu, isIntra);
+    any = any || todo != 0;
+#pragma unroll 1
+    while (todo) {
+        const int i = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int mbx = x0 + i;
+        const uint32_t mb = (uint32_t)mby * (uint32_t)W + (uint32_t)mbx;
+        const b200_mb_rec *rec = recsRow + mbx;
         MbHead h;
         {
             const uint32_t hx = __shfl_sync(0xffffffffu, mHead.x, i);
@@ -908,18 +922,14 @@ __global__ void __launch_bounds__(kReconWarps * 32, 5) reconIntraKernel(const Re
         const int flags = h.flags;
         const bool avA = flags & B200_MBF_AVAIL_A, avB = flags & B200_MBF_AVAIL_B;
         const bool avC = flags & B200_MBF_AVAIL_C, avD = flags & B200_MBF_AVAIL_D;
-        // wait for the intra neighbours this macroblock reads (record byte 28: waitMask)
+        // wait for the intra neighbours this macroblock reads (record byte 28: waitMask).  The left one is this warp's own
+        // previous step; the row above has to be past the above-left (x), above (x + 1) or above-right (x + 2) macroblock
         const int waitMask = (misc >> 8) & 0xFF;
         {
-            // a neighbour that is an earlier entry of this warp's own chunk needs no flag: program order + the warp barrier
-            const int nmb = lane == 0 ? (int)mb - 1 : lane == 1 ? (int)mb - g.widthMbs : lane == 2 ? (int)mb - g.widthMbs + 1 : (int)mb - g.widthMbs - 1;
-            bool mine = false;
-#pragma unroll
-            for (int j = 0; j < kChunkB - 1; j++) {
-                const uint32_t mj = __shfl_sync(0xffffffffu, mMb, j);
-                mine |= j < i && (int)mj == nmb;
-            }
-            if (lane < 4 && ((waitMask >> lane) & 1) && !mine) waitFlag(doneS + nmb, p.serial);
+            const uint32_t need = (uint32_t)min(W, (waitMask & B200_MBF_AVAIL_C) ? mbx + 2 : (waitMask & B200_MBF_AVAIL_B) ? mbx + 1
+                                                   : (waitMask & B200_MBF_AVAIL_D) ? mbx : 0);
+            if (lane == 0 && seen < need) seen = waitRow(rowMine - 1, serial16, need);
+            seen = __shfl_sync(0xffffffffu, seen, 0);
         }
         __syncwarp();
         // neighbouring pels (h264bsdGetNeighbourPels :545-614), straight from L2
@@ -1055,10 +1065,14 @@ __global__ void __launch_bounds__(kReconWarps * 32, 5) reconIntraKernel(const Re
             for (int k = 0; k < 4; k++) oc |= (uint32_t)clip255(pv[k] + resC[k]) << (8 * k);
             *reinterpret_cast<uint32_t *>(dstC) = oc;
         }
-        // publish: the warp barrier orders every lane's stores before lane 0's release at gpu scope (cumulative; no extra fence)
+        // publish the row's progress -- everything before its next intra macroblock (or the end of this stretch) is through.  The
+        // warp barrier orders every lane's stores before lane 0's release at gpu scope (cumulative; no extra fence)
         __syncwarp();
-        if (lane == 0) stRelease(doneS + mb, p.serial);
+        if (lane == 0) stRelease(rowMine, (serial16 << 16) | (uint32_t)min(W, todo ? x0 + __ffs(todo) - 1 : x0 + 32));
     }
+    if (any && lane == 0 && x0 + 32 >= W) stRelease(rowMine, (serial16 << 16) | (uint32_t)W);   // (a row that ends without one)
+    }  // stretch of 32 macroblocks
+    }  // row tickets
 }
 
 }  // namespace b200
