@@ -56,7 +56,8 @@ BATCH_SYMBOLS = [
     "h264bsdB200BatchConvertFrame", "h264bsdB200BatchConvertBench", "h264bsdB200BatchConvertBenchAll", "h264bsdB200BatchCompareStreams",
     "h264bsdB200BatchDebugStage", "h264bsdB200BatchIdctErrors", "h264bsdB200BatchDeblockWorkMbs", "h264bsdB200BatchWatchdog", "h264bsdB200BatchReadPictureAll", "h264bsdB200HostAlloc", "h264bsdB200HostFree",
     "h264bsdB200PinTape", "h264bsdB200UnpinTape", "h264bsdB200BatchKernelTiming", "h264bsdB200BatchKernelTimes", "h264bsdB200BatchLaunches", "h264bsdB200BatchH2DBytes",
-    "h264bsdB200BatchD2HBytes",
+    "h264bsdB200BatchD2HBytes", "h264bsdB200ParseUploadPoolCreate", "h264bsdB200ParseUploadPoolDestroy", "h264bsdB200BatchParseUploadBegin",
+    "h264bsdB200BatchParseUploadWait", "h264bsdB200BatchReadPictureAllEx",
 ]
 
 _lib = None
@@ -134,5 +135,12 @@ def load():
     L.h264bsdB200BatchWatchdog.restype = u32; L.h264bsdB200BatchWatchdog.argtypes = [vp, C.c_int]
     for n in ("h264bsdB200BatchLaunches", "h264bsdB200BatchH2DBytes", "h264bsdB200BatchD2HBytes"):
         getattr(L, n).restype = C.c_uint64; getattr(L, n).argtypes = [vp]
+    L.h264bsdB200ParseUploadPoolCreate.restype = vp; L.h264bsdB200ParseUploadPoolCreate.argtypes = [u32]
+    L.h264bsdB200ParseUploadPoolDestroy.restype = None; L.h264bsdB200ParseUploadPoolDestroy.argtypes = [vp]
+    L.h264bsdB200BatchParseUploadBegin.restype = vp
+    L.h264bsdB200BatchParseUploadBegin.argtypes = [vp, vp, u32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), u32]
+    L.h264bsdB200BatchParseUploadWait.restype = C.c_int; L.h264bsdB200BatchParseUploadWait.argtypes = [vp]
+    L.h264bsdB200BatchReadPictureAllEx.restype = C.c_int
+    L.h264bsdB200BatchReadPictureAllEx.argtypes = [vp, u32, vp, C.c_size_t, u32, u32, u32, u32, C.c_int]
     _lib = L
     return L

@@ -140,6 +140,26 @@ class Batch:
     def upload_fence(self, through_pic):
         self._ck(self._L.h264bsdB200BatchUploadFence(self.h, through_pic), "upload_fence")
 
+    def parse_upload_begin(self, pool, bufs, flags=0):
+        """parse the bitstreams `bufs` (ctypes byte arrays, one per stream of this batch) on the pool's host threads and upload
+        each work-list as it is finished (h264bsdB200BatchParseUploadBegin); returns a token for parse_upload_wait"""
+        n = len(bufs)
+        ptrs = (C.c_void_p * n)(*[C.addressof(b) for b in bufs])
+        lens = (C.c_size_t * n)(*[len(b) for b in bufs])
+        job = self._L.h264bsdB200BatchParseUploadBegin(self.h, pool, n, ptrs, lens, flags)
+        if not job:
+            raise MemoryError("h264bsdB200BatchParseUploadBegin failed")
+        return (job, ptrs, lens, bufs)     # keeps the arrays alive
+
+    def parse_upload_wait(self, token):
+        bad = self._L.h264bsdB200BatchParseUploadWait(token[0])
+        if bad:
+            raise RuntimeError("parse + upload failed for %d streams" % bad)
+
+    def read_picture_all_ex(self, k, dst, stride, crop=(0, 0, 0, 0), nv12=False):
+        """picture k of every stream, cropped to crop = (x, y, w, h) (w == 0: coded size) and / or as NV12 -> dst + s * stride"""
+        self._ck(self._L.h264bsdB200BatchReadPictureAllEx(self.h, k, dst, stride, crop[0], crop[1], crop[2], crop[3], int(nv12)), "read_picture_all_ex")
+
     def replicate(self, src=0):
         self._ck(self._L.h264bsdB200BatchReplicateTape(self.h, src), "replicate")
 

@@ -9,7 +9,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <atomic>
 #include <new>
+#include <thread>
 #include <vector>
 #include <cuda_runtime.h>
 #include "h264bsd_decoder.h"
@@ -93,7 +96,12 @@ u32 h264bsdInit(storage_t *pStorage, u32 noOutputReordering) {
 u32 h264bsdDecode(storage_t *pStorage, u8 *byteStrm, u32 len, u32 picId, u32 *readBytes) {
     LegacyDecoder *d = self(pStorage);
     if (!d || !byteStrm || !readBytes) return H264BSD_ERROR;
-    u32 r = d->dec.decode(byteStrm, len, picId, readBytes);
+    u32 r;
+    try {
+        r = d->dec.decode(byteStrm, len, picId, readBytes);
+    } catch (const std::exception &) {     // an allocation that failed (or a size nothing could satisfy): no exception leaves the C-ABI
+        return H264BSD_MEMALLOC_ERROR;
+    }
     if (d->failed) return H264BSD_MEMALLOC_ERROR;
     return r;
 }
@@ -223,19 +231,26 @@ void h264bsdB200HostFree(void *p) { if (p) cudaFreeHost(p); }
 int h264bsdB200PinTape(b200_tape *t) {
     if (!t || deviceCount() <= 0) return -1;
     if (t->pinned == 1) return 0;
+    // the whole allocations, not just the bytes in use: a tape that is re-used for a longer stream stays page-locked as long as
+    // it fits (tape_builder.cpp unpins before an array has to move)
     int rc = 0;
-    if (t->mbRecBytes) rc |= cudaHostRegister(t->mbRecs, t->mbRecBytes, cudaHostRegisterPortable) != cudaSuccess;
-    if (t->coefBytes) rc |= cudaHostRegister(t->coefs, t->coefBytes, cudaHostRegisterPortable) != cudaSuccess;
-    rc |= cudaHostRegister(t->mbOrder, (size_t)t->numPics * t->widthMbs * t->heightMbs * 2, cudaHostRegisterPortable) != cudaSuccess;
-    if (rc) cudaGetLastError();
+    if (t->mbRecs && t->capRecs) rc |= cudaHostRegister(t->mbRecs, t->capRecs, cudaHostRegisterPortable) != cudaSuccess;
+    if (!rc && t->coefs && t->capCoefs) rc |= cudaHostRegister(t->coefs, t->capCoefs, cudaHostRegisterPortable) != cudaSuccess;
+    if (!rc && t->mbOrder && t->capOrder) rc |= cudaHostRegister(t->mbOrder, t->capOrder, cudaHostRegisterPortable) != cudaSuccess;
+    if (rc) {
+        cudaGetLastError();
+        cudaHostUnregister(t->mbRecs); cudaHostUnregister(t->coefs); cudaHostUnregister(t->mbOrder);   // whatever did register
+        cudaGetLastError();
+    }
     t->pinned = rc ? 0 : 1;
     return rc ? -1 : 0;
 }
 void h264bsdB200UnpinTape(b200_tape *t) {
     if (!t || t->pinned != 1) return;
-    cudaHostUnregister(t->mbRecs);
-    cudaHostUnregister(t->coefs);
-    cudaHostUnregister(t->mbOrder);
+    if (t->mbRecs && t->capRecs) cudaHostUnregister(t->mbRecs);
+    if (t->coefs && t->capCoefs) cudaHostUnregister(t->coefs);
+    if (t->mbOrder && t->capOrder) cudaHostUnregister(t->mbOrder);
+    cudaGetLastError();
     t->pinned = 0;
 }
 
@@ -251,6 +266,43 @@ b200_batch *h264bsdB200BatchCreate(int device, uint32_t nStreams, uint32_t width
 void h264bsdB200BatchDestroy(b200_batch *h) { delete reinterpret_cast<Batch *>(h); }
 
 #define B(h) reinterpret_cast<Batch *>(h)
+
+// ---- parse + upload in one go (the end-to-end path): every worker thread parses a stream into ITS re-used page-locked tape,
+// queues the work-list's upload on ITS copy stream, waits for the copy and takes the next stream.  The host holds `threads`
+// tapes instead of one per stream, nothing is issued from the caller's thread, and parsing overlaps the H2D copies.
+struct b200_pu_worker {
+    b200_tape *tape = nullptr;
+    cudaStream_t st = nullptr;
+};
+struct b200_pu_pool {             // lives as long as the process: a worker slot keeps its tape and stream across jobs
+    std::vector<b200_pu_worker> w;
+};
+struct b200_pu_job {
+    std::thread th;
+    int failed = 0;
+};
+static void puRun(Batch *b, b200_pu_pool *pool, uint32_t n, const uint8_t *const *streams, const size_t *lens, uint32_t flags, uint32_t threads, int *failedOut) {
+    std::atomic<uint32_t> next(0), failed(0);
+    auto work = [&](uint32_t slot) {
+        cudaSetDevice(b->device());
+        b200_pu_worker &w = pool->w[slot];
+        if (!w.st && cudaStreamCreateWithFlags(&w.st, cudaStreamNonBlocking) != cudaSuccess) { failed.fetch_add(n); return; }
+        for (;;) {
+            const uint32_t i = next.fetch_add(1);
+            if (i >= n) break;
+            w.tape = h264bsdB200ReparseStream(w.tape, streams[i], lens[i], flags);
+            if (!w.tape || w.tape->status != 0) { failed.fetch_add(1); continue; }
+            if (w.tape->pinned != 1) h264bsdB200PinTape(w.tape);     // first use, or an array had to grow
+            if (!b->uploadTapeOn(i, w.tape, w.st) || cudaStreamSynchronize(w.st) != cudaSuccess) failed.fetch_add(1);
+        }
+    };
+    std::vector<std::thread> pool_;
+    for (uint32_t t = 1; t < threads; t++) pool_.emplace_back(work, t);
+    work(0);
+    for (auto &t : pool_) t.join();
+    b->tapesChanged();
+    *failedOut = (int)failed.load();
+}
 int h264bsdB200BatchUploadTape(b200_batch *h, uint32_t stream, const b200_tape *tape) { return h && B(h)->uploadTape(stream, tape) ? 0 : -1; }
 int h264bsdB200BatchUploadTapeRange(b200_batch *h, uint32_t stream, const b200_tape *tape, uint32_t firstPic, uint32_t numPics) {
     return h && B(h)->uploadTapeRange(stream, tape, firstPic, numPics) ? 0 : -1;
@@ -285,6 +337,40 @@ uint64_t h264bsdB200BatchLaunches(b200_batch *h) { return h ? B(h)->launches() :
 uint64_t h264bsdB200BatchH2DBytes(b200_batch *h) { return h ? B(h)->h2dBytes() : 0; }
 uint64_t h264bsdB200BatchD2HBytes(b200_batch *h) { return h ? B(h)->d2hBytes() : 0; }
 uint32_t h264bsdB200BatchNumPics(b200_batch *h) { return h ? B(h)->numPics() : 0; }
+b200_pu_pool *h264bsdB200ParseUploadPoolCreate(uint32_t threads) {
+    b200_pu_pool *p = new (std::nothrow) b200_pu_pool();
+    if (p) p->w.resize(threads ? threads : 1);
+    return p;
+}
+void h264bsdB200ParseUploadPoolDestroy(b200_pu_pool *p) {
+    if (!p) return;
+    for (auto &w : p->w) {
+        if (w.tape) { h264bsdB200UnpinTape(w.tape); h264bsdB200FreeTape(w.tape); }
+        if (w.st) cudaStreamDestroy(w.st);
+    }
+    delete p;
+}
+b200_pu_job *h264bsdB200BatchParseUploadBegin(b200_batch *h, b200_pu_pool *pool, uint32_t n, const uint8_t *const *streams, const size_t *lens,
+                                              uint32_t flags) {
+    if (!h || !pool || !n || !streams || !lens || pool->w.empty()) return nullptr;
+    b200_pu_job *j = new (std::nothrow) b200_pu_job();
+    if (!j) return nullptr;
+    Batch *b = B(h);
+    const uint32_t threads = (uint32_t)std::min<size_t>(pool->w.size(), n);
+    j->th = std::thread([=]() { puRun(b, pool, n, streams, lens, flags, threads, &j->failed); });
+    return j;
+}
+int h264bsdB200BatchParseUploadWait(b200_pu_job *j) {
+    if (!j) return -1;
+    j->th.join();
+    const int f = j->failed;
+    delete j;
+    return f;
+}
+int h264bsdB200BatchReadPictureAllEx(b200_batch *h, uint32_t picIndex, uint8_t *dst, size_t strideBytes, uint32_t cropX, uint32_t cropY,
+                                     uint32_t cropW, uint32_t cropH, int nv12) {
+    return h && B(h)->readPictureAllEx(picIndex, dst, strideBytes, (int)cropX, (int)cropY, (int)cropW, (int)cropH, nv12) ? 0 : -1;
+}
 #undef B
 
 }  // extern "C"

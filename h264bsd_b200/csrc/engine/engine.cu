@@ -73,7 +73,20 @@ void Batch::destroy() {
     // every pointer, capacity, event and stream back to its default: a second create() on this object (a stream that activates
     // another sequence parameter set, api.cpp LegacyDecoder::configure) must not see anything of the first
     created_ = false;
-    *this = Batch();
+    resetState();
+}
+
+void Batch::resetState() {
+    created_ = false; device_ = 0; numSms_ = 0; stream_ = nullptr; evA_ = evB_ = nullptr; g_ = PoolGeom{}; pool_ = nullptr;
+    dOrder_ = nullptr; dDoneRecon_ = dDoneDeblock_ = dCounters_ = dSlots_ = dBsWords_ = nullptr; dWork_ = nullptr;
+    strengthBlocks_ = 0; serial_ = 0; passABlocks_ = deblockBlocks_ = intraBlocks_ = 0; chunkRows_ = 32; chunksPerCol_ = 1;
+    syncEv_ = forkEv_ = joinEv_ = nullptr; jobsCap_ = 0; dConvertAll_ = nullptr; chunkB_ = 1; uploadStream_ = nullptr;
+    fences_.clear(); fenceFree_.clear(); auxStream_ = nullptr; tapes_.clear(); dJobs_ = nullptr; jobsFilterAt_ = 0; numPics_ = 0;
+    jobsDirty_ = true; hStage_[0] = hStage_[1] = nullptr; dStage_[0] = dStage_[1] = nullptr; stageCap_[0] = stageCap_[1] = 0;
+    stageEv_[0] = stageEv_[1] = nullptr; stageIdx_ = 0; dConvert_ = nullptr; convertCap_ = 0; dFrameStage_ = nullptr; frameStageCap_ = 0;
+    launches_ = 0; d2hBytes_ = 0; h2dBytes_ = 0; timing_ = false; evPool_.clear(); evUsed_ = 0; evStage_.clear();
+    dPack_[0] = dPack_[1] = nullptr; packEv_[0] = packEv_[1] = nullptr; packedEv_[0] = packedEv_[1] = nullptr; copyStream_ = nullptr;
+    packUsed_[0] = packUsed_[1] = false; packIdx_ = 0; picMaxB_.clear(); picMaxE_.clear();
 }
 
 static bool encodeStripMap(EncodeTiledFn enc, CUtensorMap *m, uint8_t *base, const PoolGeom &g, int rows, unsigned long long nFrames, int nx, int nr) {
@@ -95,7 +108,8 @@ bool Batch::create(int device, uint32_t nStreams, uint32_t widthMbs, uint32_t he
     }
     if (device < 0 || device >= n || !nStreams || !widthMbs || !heightMbs || !numSlots || numSlots > 32) return false;
     // macroblock addresses are 16 bits on the device (order lists); checked before anything is allocated
-    if ((unsigned long long)widthMbs * heightMbs > 65535ull || widthMbs > 16383 || heightMbs > 16383) return false;
+    // (and pass A packs a window's row into 16 bits: rows incl. border < 65536)
+    if ((unsigned long long)widthMbs * heightMbs > 65535ull || widthMbs > 4000 || heightMbs > 4000) return false;
     if (created_) destroy();
     device_ = device;
     CK(cudaSetDevice(device));
@@ -181,6 +195,14 @@ bool Batch::create(int device, uint32_t nStreams, uint32_t widthMbs, uint32_t he
 }
 
 bool Batch::uploadTape(uint32_t stream, const b200_tape *t) {
+    if (!created_) return false;
+    CK(cudaSetDevice(device_));
+    if (!uploadTapeOn(stream, t, stream_)) return false;
+    jobsDirty_ = true;
+    return true;
+}
+
+bool Batch::uploadTapeOn(uint32_t stream, const b200_tape *t, cudaStream_t st) {
     if (!created_ || stream >= (uint32_t)g_.nStreams || !t) return false;
     if (t->widthMbs != (uint32_t)g_.widthMbs || t->heightMbs != (uint32_t)g_.heightMbs || t->numSlots > (uint32_t)g_.numSlots) return false;
     CK(cudaSetDevice(device_));
@@ -200,11 +222,10 @@ bool Batch::uploadTape(uint32_t stream, const b200_tape *t) {
         d.owned = true;
     }
     d.recBytes = t->mbRecBytes; d.coefBytes = t->coefBytes; d.orderBytes = orderBytes;
-    CK(cudaMemcpyAsync(d.recs, t->mbRecs, t->mbRecBytes, cudaMemcpyHostToDevice, stream_));
-    CK(cudaMemcpyAsync(d.coefs, t->coefs, t->coefBytes, cudaMemcpyHostToDevice, stream_));
-    CK(cudaMemcpyAsync(d.order, t->mbOrder, orderBytes, cudaMemcpyHostToDevice, stream_));
+    CK(cudaMemcpyAsync(d.recs, t->mbRecs, t->mbRecBytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d.coefs, t->coefs, t->coefBytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d.order, t->mbOrder, orderBytes, cudaMemcpyHostToDevice, st));
     d.pics.assign(t->pics, t->pics + t->numPics);
-    jobsDirty_ = true;
     h2dBytes_ += t->mbRecBytes + t->coefBytes + orderBytes;
     return true;
 }

@@ -1,6 +1,7 @@
 // engine.hpp -- host-visible interface of the B200 reconstruction engine (see engine.cu)
 #pragma once
 #include <cstdint>
+#include <atomic>
 #include <deque>
 #include <vector>
 #include <cuda.h>
@@ -24,6 +25,10 @@ public:
     void destroy();
 
     bool uploadTape(uint32_t stream, const b200_tape *t);
+    // the same on a caller-owned CUDA stream; safe to call from several host threads at once for DISTINCT streams (the caller
+    // waits for `st` before it re-uses the tape's memory, and calls tapesChanged() once when all uploads are queued)
+    bool uploadTapeOn(uint32_t stream, const b200_tape *t, cudaStream_t st);
+    void tapesChanged() { jobsDirty_ = true; }
     bool replicateTape(uint32_t srcStream);
     bool uploadTapeRange(uint32_t stream, const b200_tape *t, uint32_t firstPic, uint32_t numPics);
     bool uploadFence(uint32_t throughPic);
@@ -56,14 +61,14 @@ public:
     const PoolGeom &geom() const { return g_; }
     uint32_t numPics() const { return numPics_; }
     uint64_t launches() const { return launches_; }
-    uint64_t h2dBytes() const { return h2dBytes_; }
+    uint64_t h2dBytes() const { return h2dBytes_.load(); }
     uint64_t d2hBytes() const { return d2hBytes_; }
     size_t frameBytes() const { return (size_t)g_.nMbs * 384; }
     const std::vector<b200_pic_hdr> &pics(uint32_t stream) const { return tapes_[stream].pics; }
     int device() const { return device_; }
 
 private:
-    Batch &operator=(Batch &&) = default;   // destroy() only: back to the default state (nothing dangles after a re-create)
+    void resetState();   // destroy() only: every member back to its default (nothing dangles after a re-create)
     struct DevTape {
         uint8_t *recs = nullptr, *coefs = nullptr, *order = nullptr;
         size_t recBytes = 0, coefBytes = 0, orderBytes = 0, capRecs = 0, capCoefs = 0, capOrder = 0;
@@ -113,7 +118,8 @@ private:
     size_t convertCap_ = 0;
     uint8_t *dFrameStage_ = nullptr;    // one picture, planar: readFrame / writeFrame
     size_t frameStageCap_ = 0;
-    uint64_t launches_ = 0, h2dBytes_ = 0, d2hBytes_ = 0;
+    uint64_t launches_ = 0, d2hBytes_ = 0;
+    std::atomic<uint64_t> h2dBytes_{0};
     bool timing_ = false;
     std::vector<cudaEvent_t> evPool_;
     size_t evUsed_ = 0;

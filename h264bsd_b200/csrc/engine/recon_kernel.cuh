@@ -587,7 +587,7 @@ passAKernel(const ReconParams p, const __grid_constant__ PassAMaps maps) {
         uint8_t *lbase = mbLuma(cur, g, mbx, row0), *cbase = mbChroma(cur, g, mbx, row0);   // macroblock l of the chunk: + 256 l / + 128 l
 
         // lane l: head, reference slots, wait mask and first vector of record l
-        uint32_t mW0 = 0, mMask = 0, mCoef = 0, mW3 = 0, mRef = 0, mMv = 0;
+        uint32_t mW0 = 0, mMask = 0, mCoef = 0, mRef = 0, mMv = 0;
         bool isCopy = false, isInter = false;
         const b200_mb_rec *rec0 = job.recs + (size_t)row0 * g.widthMbs + mbx;   // record of macroblock l: + l * widthMbs
         if (lane < n) {
@@ -596,7 +596,7 @@ passAKernel(const ReconParams p, const __grid_constant__ PassAMaps maps) {
             mRef = __ldg(rw + 4);
             const uint32_t w7 = __ldg(rw + 7);
             mMv = __ldg(rw + 8);
-            mW0 = hw.x; mMask = hw.y; mCoef = hw.z; mW3 = hw.w;
+            mW0 = hw.x; mMask = hw.y; mCoef = hw.z;
             const uint32_t type = mW0 & 0xFFu;
             // a concealed macroblock carries the state the filter wants to see (Intra4x4); its pels are a copy of the reference
             // picture (no neighbours to wait for) or come from concealKernel (h264bsd_b200_tape.h)
@@ -896,7 +896,6 @@ __global__ void __launch_bounds__(kReconWarps * 32, 5) reconIntraKernel(const Re
         const int i = __ffs(todo) - 1;
         todo &= todo - 1;
         const int mbx = x0 + i;
-        const uint32_t mb = (uint32_t)mby * (uint32_t)W + (uint32_t)mbx;
         const b200_mb_rec *rec = recsRow + mbx;
         MbHead h;
         {

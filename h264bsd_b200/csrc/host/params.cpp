@@ -38,7 +38,7 @@ static uint32_t levelDpbSize(uint32_t picSizeInMbs, uint32_t levelIdc, bool &val
         if (l.level != levelIdc) continue;
         if (picSizeInMbs > l.maxFs) return 0;
         valid = true;
-        return std::min<uint32_t>(l.maxDpbBytes / (picSizeInMbs * 384), 16);
+        return std::min<uint32_t>(l.maxDpbBytes / (std::max<uint32_t>(picSizeInMbs, 1u) * 384u), 16);
     }
     return 0;
 }
@@ -158,6 +158,11 @@ bool parseSps(BitReader &br, Sps &sps) {
     sps.widthMbs = v + 1;
     if (!br.ue(v)) return false;
     sps.heightMbs = v + 1;
+    // the picture size comes from an untrusted stream: checked in 64 bits against what the engine can address (16-bit macroblock
+    // addresses, 16-bit row coordinates) before anything is sized by it.  Level 5.1 allows 36 864 macroblocks per frame; the
+    // reference fails later, in its allocation (MEMORY_ALLOCATION_ERROR, h264bsd_storage.c:347-378), here the parameter set is
+    // refused
+    if ((uint64_t)sps.widthMbs * (uint64_t)sps.heightMbs > 65535ull || sps.widthMbs > 4000u || sps.heightMbs > 4000u) return false;
     if (!br.get1(v)) return false;
     if (!v) return false;           // frame_mbs_only_flag must be 1
     if (!br.get1(v)) return false;  // direct_8x8_inference_flag

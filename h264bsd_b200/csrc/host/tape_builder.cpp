@@ -99,7 +99,16 @@ private:
 
 }  // namespace b200
 
+static b200_tape *reparseStream(b200_tape *t, const uint8_t *stream, size_t len, uint32_t noOutputReordering);
 extern "C" b200_tape *h264bsdB200ReparseStream(b200_tape *t, const uint8_t *stream, size_t len, uint32_t noOutputReordering) {
+    try {
+        return reparseStream(t, stream, len, noOutputReordering);
+    } catch (const std::exception &) {      // std::bad_alloc / length_error: no exception leaves the C-ABI
+        if (t) t->status = b200::MEMALLOC_ERROR;
+        return t;
+    }
+}
+static b200_tape *reparseStream(b200_tape *t, const uint8_t *stream, size_t len, uint32_t noOutputReordering) {
     using namespace b200;
     if (!t) {
         t = (b200_tape *)std::calloc(1, sizeof(b200_tape));
@@ -176,6 +185,7 @@ extern "C" b200_tape *h264bsdB200ParseStream(const uint8_t *stream, size_t len, 
 
 extern "C" void h264bsdB200FreeTape(b200_tape *t) {
     if (!t) return;
+    if (t->pinned == 1) h264bsdB200UnpinTape(t);     // never free page-locked memory while it is registered
     std::free(t->pics);
     std::free(t->mbRecs);
     std::free(t->coefs);

@@ -70,6 +70,20 @@ int h264bsdB200BatchUploadFence(b200_batch *batch, uint32_t throughPic);
 /* UploadTapeRange for streams 0..nStreams-1 (tapes[s] -> stream s) followed by UploadFence(firstPic + numPics) */
 int h264bsdB200BatchUploadTapesRange(b200_batch *batch, const b200_tape *const *tapes, uint32_t nStreams, uint32_t firstPic, uint32_t numPics);
 
+/* Parse + upload in one go (the end-to-end path): `threads` host threads (the pool's size) each parse a stream into their own
+ * re-used page-locked tape -- everything h264bsdDecode does up to the pixel path (h264bsd_decoder.c:152-515,
+ * h264bsd_slice_data.c:131-220 without the pels) -- and queue the work-list's upload as stream i of `batch` on their own copy
+ * stream, so that parsing, H2D copies and (on another batch) the GPU's work overlap and the host holds one tape per thread instead
+ * of one per stream.  Begin returns at once; Wait joins and returns the number of streams that failed.  The arrays passed to
+ * Begin must stay alive until Wait; `batch` must not be decoding meanwhile (alternate between two batches). */
+typedef struct b200_pu_pool b200_pu_pool;
+typedef struct b200_pu_job b200_pu_job;
+b200_pu_pool *h264bsdB200ParseUploadPoolCreate(uint32_t threads);
+void h264bsdB200ParseUploadPoolDestroy(b200_pu_pool *pool);
+b200_pu_job *h264bsdB200BatchParseUploadBegin(b200_batch *batch, b200_pu_pool *pool, uint32_t n, const uint8_t *const *streams,
+                                              const size_t *lens, uint32_t flags);
+int h264bsdB200BatchParseUploadWait(b200_pu_job *job);
+
 /* reconstruct + in-loop filter + border for picture `picIndex` of EVERY stream (asynchronous).
  * Replaces, per macroblock, h264bsdDecodeMacroblock's pixel half (macroblock_layer.c:965-1131) and,
  * per picture, h264bsdFilterPicture (deblocking.c:575-640). */
@@ -88,6 +102,12 @@ int h264bsdB200BatchReadFrame(b200_batch *batch, uint32_t stream, uint32_t slot,
 /* picture `picIndex` of EVERY stream -> dst + s * strideBytes, one packed transfer (asynchronous: call
  * h264bsdB200BatchSync before reading dst; dst should come from h264bsdB200HostAlloc) */
 int h264bsdB200BatchReadPictureAll(b200_batch *batch, uint32_t picIndex, uint8_t *dst, size_t strideBytes);
+/* the same for a cropping rectangle (h264bsdCroppingParams, decoder.c:887-921; cropW x cropH luma pels at (cropX, cropY), all
+ * even; cropW == 0: the coded size) and / or as NV12 (one interleaved chroma plane): cropping, pitch stripping and format
+ * conversion happen in the kernel that stages the pictures for the transfer; dst + s * strideBytes receives cropW * cropH * 3 / 2
+ * bytes per stream */
+int h264bsdB200BatchReadPictureAllEx(b200_batch *batch, uint32_t picIndex, uint8_t *dst, size_t strideBytes, uint32_t cropX,
+                                     uint32_t cropY, uint32_t cropW, uint32_t cropH, int nv12);
 int h264bsdB200BatchWriteFrame(b200_batch *batch, uint32_t stream, uint32_t slot, const uint8_t *src);
 /* h264bsdConvertTo{RGBA(0),BGRA(1),YCbCrA(2)} of a frame slot (decoder.c:1163-1370) into host memory */
 int h264bsdB200BatchConvertFrame(b200_batch *batch, uint32_t stream, uint32_t slot, int mode, uint32_t *dst);

@@ -29,8 +29,6 @@ def batched():
         assert hashlib.md5(data).hexdigest() == GOLD[str(seed)]["stream_md5"]
         ps = ParsedStream(data)
         assert ps.status == 0
-        os.environ["B200_COPY_BULK"] = "1" if i % 3 == 1 else "0"        # read by Batch::create
-        os.environ["B200_COPY_VARIANT"] = "2" if i % 3 == 2 else "0"
         orc = _oracle.OracleDecoder(ps)
         b = Batch(2, ps.width_mbs, ps.height_mbs, ps.num_slots)
         b.upload(0, ps)
@@ -177,3 +175,66 @@ def sweep(first, count, limit=60):
         b.close(); orc.close(); ps.close()
         print(f"seed {seed} ok", flush=True)
     print(f"sweep ok: {len(seeds)} streams, {pics} pictures")
+
+
+def replay(ps, n_streams, max_pics=None, stages=True):
+    """a tape through the host build of the engine next to the oracle, `n_streams` instances, every picture of every instance"""
+    orc = _oracle.OracleDecoder(ps)
+    b = Batch(n_streams, ps.width_mbs, ps.height_mbs, ps.num_slots)
+    b.upload(0, ps)
+    if n_streams > 1:
+        b.replicate(0)
+    n = ps.num_pics if max_pics is None else min(ps.num_pics, max_pics)
+    for k in range(n):
+        slot = ps.pics[k].curSlot
+        if stages:
+            b.debug_stage(k, True, False)
+            orc.recon(k)
+            for st in range(n_streams):
+                assert np.array_equal(b.read_frame(st, slot), orc.frame(slot)), f"reconstruction of picture {k}, instance {st}"
+            b.debug_stage(k, False, True)
+            orc.deblock(k)
+        else:
+            b.decode_picture(k)
+            orc.recon(k)
+            orc.deblock(k)
+        for st in range(n_streams):
+            assert np.array_equal(b.read_frame(st, slot), orc.frame(slot)), f"picture {k}, instance {st}"
+    assert b.idct_errors() == 0 and b.watchdog() == (0, 0)
+    b.close(); orc.close()
+    return n
+
+
+def kernels(kind):
+    """what the kernels see beyond the few streams of batched(): all macroblock types, several reference frames, vectors far outside
+    the picture (valid); concealment and concealed copies (damaged); long columns of copies in pictures taller than a pass-A chunk
+    and wider than a filter stretch (large); an encoder's pictures -- every interpolation position -- with three instances, an odd
+    count for the filter's half-warp pairs (reference)"""
+    pics = 0
+    if kind == "valid":
+        for seed in range(0, 26):
+            ps = ParsedStream(synth_h264.make_stream(seed))
+            if ps.status == 0 and ps.num_pics and ps.mbs_per_pic <= 40:
+                pics += replay(ps, 2, max_pics=6)
+            ps.close()
+        assert pics >= 40, pics
+    elif kind == "damaged":
+        for seed in range(0, 40):
+            ps = ParsedStream(synth_h264.make_damaged_stream(seed), resilient=True)
+            if ps.status == 0 and ps.num_pics and ps.mbs_per_pic <= 40:
+                pics += replay(ps, 2, max_pics=6, stages=False)
+            ps.close()
+        assert pics >= 40, pics
+    elif kind == "large":
+        for data, mp in ((synth_h264.make_stream(2, W=45, H=18, still=True, pictures=4), 3), (synth_h264.make_stream(21, W=64, H=4, still=True, pictures=5), 4),
+                         (synth_h264.make_stream(12, W=3, H=35, still=True, pictures=4), 4)):
+            ps = ParsedStream(data)
+            assert ps.status == 0
+            pics += replay(ps, 2, max_pics=mp, stages=False)
+            ps.close()
+        assert pics >= 10, pics
+    else:
+        ps = ParsedStream(_oracle.stream_bytes("test_640x360.h264"))
+        pics += replay(ps, 3, max_pics=5, stages=False)
+        ps.close()
+    print(f"kernels ok: {kind}, {pics} pictures")

@@ -3,8 +3,7 @@ sequence, staging, read-back) and the C-ABI in api.cpp -- built for the host: te
 whose device memory is host memory and whose kernel launches run the kernels' sources under tests/emu/warp_emu.hpp.  The library
 that comes out exports the product's C-ABI, so the Python bindings drive it like the real one (B200_LIB, in a process of its
 own) and the same checks as the GPU suite run against the CPU oracle and the reference's md5s -- on small synthetic streams, the
-emulation is slow.  What this covers that tests/test_cpu_kernel_emu.py does not: engine.cu itself (that test drives the kernels
-from a harness that mirrors Batch::launchPicture).  What it cannot show: anything about asynchrony (every call completes before
+emulation is slow.  What it cannot show: anything about asynchrony (every call completes before
 it returns) or the hardware.  The product never loads this library."""
 import os
 import re
@@ -38,7 +37,7 @@ def split_top(s):
 
 def prepare_engine_source():
     """engine.cu with every kernel<<<grid, block, smem, stream>>>(args); spelled EMU_LAUNCH(kernel, grid, block, args); and the
-    inter kernel's header taken from the copy tests/test_cpu_kernel_emu.py prepares (dynamic shared memory as a plain array)"""
+    reconstruction kernels' header with pass A's dynamic shared memory declared as a plain array"""
     src = open(os.path.join(CSRC, "engine", "engine.cu")).read()
     launch = re.compile(r"([A-Za-z_]\w*(?:<\d+>)?)<<<(.*?)>>>\((.*)\);")
     n = 0
@@ -97,3 +96,11 @@ def test_legacy_api_on_the_host_matches_reference_md5(hostemu_lib):
     streams -- redundant slices with filter-only records and damaged streams with concealment among them -- against the md5s of
     the reference decoder"""
     assert "legacy ok" in run_body(hostemu_lib, "legacy()")
+
+
+@pytest.mark.parametrize("kind", ["valid", "damaged", "large", "reference"])
+def test_kernels_on_the_host_match_oracle(hostemu_lib, kind):
+    """the shipped kernel sources under the warp emulation on wider ground: synthetic streams with every macroblock type (stage by
+    stage), damaged streams (concealment), still scenes larger than a pass-A chunk / a filter stretch, and the first pictures of
+    the reference's own test_640x360.h264 with three instances"""
+    assert "kernels ok" in run_body(hostemu_lib, f"kernels('{kind}')", timeout=1500)

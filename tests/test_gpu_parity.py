@@ -81,9 +81,10 @@ def test_legacy_api_getters_and_headers_ready():
 
 
 @pytest.mark.parametrize("name,pics", [("test_640x360.h264", list(range(0, 10)) + [39, 40, 41, 72]),
-                                       ("test_1920x1080.h264", [0, 1, 2, 40, 41])])
+                                       ("test_1920x1080.h264", list(range(0, 42)))])
 def test_stages_in_isolation_vs_oracle(parsed, name, pics):
-    """reconstruction and in-loop filter each checked alone: the GPU gets the oracle's frames as input state"""
+    """reconstruction and in-loop filter each checked alone: the GPU gets the oracle's frames as input state (1080p: every
+    picture of the first IDR period and the IDR picture that follows)"""
     ps = parsed(name)
     orc = _oracle.OracleDecoder(ps)
     b = Batch(1, ps.width_mbs, ps.height_mbs, ps.num_slots)
@@ -218,6 +219,130 @@ def test_streamed_upload_matches_golden(parsed):
         b.sync()
     assert b.idct_errors() == 0 and b.watchdog() == (0, 0)
     b.close()
+
+
+@pytest.mark.parametrize("name,n_streams", [("test_640x360.h264", 6), ("test_1920x1080.h264", 4)])
+def test_end_to_end_path_every_stream_every_picture(name, n_streams):
+    """the data path of the bench's end-to-end leg -- bitstream bytes parsed and uploaded by the host threads
+    (h264bsdB200BatchParseUploadBegin / Wait), decode_picture, read_picture_all into page-locked memory -- two passes over two
+    alternating batches: every picture of every stream against the reference's md5"""
+    L = _lib.load()
+    data = _oracle.stream_bytes(name)
+    g = GOLD[name]
+    bits = (C.c_uint8 * len(data)).from_buffer_copy(data)
+    ps = ParsedStream(data)
+    fb, npics = ps.frame_bytes, ps.num_pics
+    batches = [Batch(n_streams, ps.width_mbs, ps.height_mbs, ps.num_slots) for _ in range(2)]
+    pool = L.h264bsdB200ParseUploadPoolCreate(3)
+    host = L.h264bsdB200HostAlloc(fb * n_streams)
+    assert pool and host
+    view = np.ctypeslib.as_array(C.cast(host, C.POINTER(C.c_uint8)), shape=(fb * n_streams,))
+    tok = batches[0].parse_upload_begin(pool, [bits] * n_streams)
+    for i in range(3):
+        cur = batches[i & 1]
+        cur.parse_upload_wait(tok)
+        if i + 1 < 3:
+            tok = batches[(i + 1) & 1].parse_upload_begin(pool, [bits] * n_streams)   # overlaps this pass's GPU work
+        for k in range(npics):
+            cur.decode_picture(k)
+            cur.read_picture_all(k, host, fb)
+            cur.sync()
+            for s in range(n_streams):
+                assert md5(view[s * fb:(s + 1) * fb]) == g["post_frame_md5"][k], f"{name}: pass {i}, stream {s}, picture {k}"
+        assert cur.idct_errors() == 0 and cur.watchdog() == (0, 0)
+    L.h264bsdB200ParseUploadPoolDestroy(pool)
+    L.h264bsdB200HostFree(host)
+    for b in batches:
+        b.close()
+    ps.close()
+
+
+def test_64_stream_1080p_batch_every_picture(parsed):
+    """the throughput configuration in small: 64 instances of the 1080p stream, EVERY picture: stream 0 against the reference's
+    md5 and every other stream against stream 0 (device-side compare)"""
+    ps = parsed("test_1920x1080.h264")
+    g = GOLD["test_1920x1080.h264"]
+    n = 64
+    b = Batch(n, ps.width_mbs, ps.height_mbs, ps.num_slots)
+    b.upload(0, ps)
+    b.replicate(0)
+    for k in range(ps.num_pics):
+        b.decode_picture(k)
+        slot = ps.pics[k].curSlot
+        assert md5(b.read_frame(0, slot)) == g["post_frame_md5"][k], f"picture {k}"
+        assert b.compare_streams([slot] * n) == 0, f"picture {k}: the instances differ"
+    assert md5(b.read_frame(n - 1, ps.pics[-1].curSlot)) == g["post_frame_md5"][-1]
+    assert b.idct_errors() == 0 and b.watchdog() == (0, 0)
+    b.close()
+
+
+def test_cropped_and_nv12_output(parsed):
+    """the output kernel: picture k of every stream de-stripped, cropped to the display rectangle of
+    h264bsdCroppingParams and delivered as I420 or NV12 in one transfer -- against the coded-size picture cropped on the host"""
+    L = _lib.load()
+    name = "test_640x360.h264"
+    ps = parsed(name)
+    t = ps.ptr.contents
+    assert t.cropFlag and (t.cropWidth, t.cropHeight) == (640, 360)
+    W, H = ps.width_mbs * 16, ps.height_mbs * 16
+    n = 3
+    b = Batch(n, ps.width_mbs, ps.height_mbs, ps.num_slots)
+    b.upload(0, ps)
+    b.replicate(0)
+    for crop in ((t.cropLeft, t.cropTop, t.cropWidth, t.cropHeight), (16, 2, 600, 300), (34, 20, 90, 66)):
+        x0, y0, cw, ch = crop
+        ob = cw * ch * 3 // 2
+        host = L.h264bsdB200HostAlloc(ob * n)
+        view = np.ctypeslib.as_array(C.cast(host, C.POINTER(C.c_uint8)), shape=(ob * n,))
+        for k in range(3):
+            b.decode_picture(k) if crop[2] == t.cropWidth else None
+            full = b.read_frame(1, ps.pics[k].curSlot)
+            Y = full[:W * H].reshape(H, W)[y0:y0 + ch, x0:x0 + cw]
+            Cb = full[W * H:W * H * 5 // 4].reshape(H // 2, W // 2)[y0 // 2:(y0 + ch) // 2, x0 // 2:(x0 + cw) // 2]
+            Cr = full[W * H * 5 // 4:].reshape(H // 2, W // 2)[y0 // 2:(y0 + ch) // 2, x0 // 2:(x0 + cw) // 2]
+            for nv12 in (False, True):
+                view[:] = 0xEE
+                b.read_picture_all_ex(k, host, ob, crop, nv12)
+                b.sync()
+                chroma = np.stack([Cb, Cr], axis=2).reshape(-1) if nv12 else np.concatenate([Cb.reshape(-1), Cr.reshape(-1)])
+                want = np.concatenate([Y.reshape(-1), chroma])
+                for s in range(n):
+                    assert np.array_equal(view[s * ob:(s + 1) * ob], want), f"crop {crop}, nv12 {nv12}, picture {k}, stream {s}"
+        L.h264bsdB200HostFree(host)
+    b.close()
+
+
+def test_legacy_api_sequence_parameter_set_change():
+    """a stream that activates another sequence parameter set (another picture size) in the middle: h264bsdDecode re-creates
+    the engine on H264BSD_HDRS_RDY like the reference re-allocates (h264bsd_decoder.c:343-389, h264bsd_storage.c:297-420) --
+    same, smaller and larger size, the RGBA output path included"""
+    small = _oracle.stream_bytes("test_640x360.h264")
+    big = _oracle.stream_bytes("test_1920x1080.h264")[:330000]
+    for first, second in ((small, small), (small, big), (big, small)):
+        want = decode_stream(first) + decode_stream(second)
+        d = H264bsdDecoder()
+        got = []
+        for part in (first, second):
+            d.queueInput(part)
+            while d.inputBytesRemaining() > 0:
+                if d.decode() == PIC_RDY:
+                    while (f := d.nextOutputPicture()) is not None:
+                        got.append(f.copy())
+            d.flush()
+            while (f := d.nextOutputPicture()) is not None:
+                got.append(f.copy())
+        assert len(got) == len(want)
+        for k, (a, w) in enumerate(zip(got, want)):
+            assert a.shape == w.shape and np.array_equal(a, w), f"picture {k}"
+        # the converted output after the switch
+        d.queueInput(first)
+        while d.decode() != PIC_RDY:
+            pass
+        rgba = d.nextOutputPictureRGBA()
+        ref = decode_stream(first)[0]
+        Wd, Hd = d.outputPictureWidth(), d.outputPictureHeight()
+        assert np.array_equal(rgba, _oracle.oracle_convert(0, Wd, Hd, ref))
+        d.release()
 
 
 POSIX_B200 = os.path.join(_oracle.ROOT, "oracle", "_ref", "test_h264bsd_b200")
