@@ -425,30 +425,31 @@ def main():
             gpu_side(eb)
             eb.sync()
         barrier()
-        reps = max(3, min(args.steps, 6))
+        # The timed window is the pipeline in steady state: `reps` GPU passes (decode + D2H of every picture) and, overlapping
+        # them, the `reps` parse + upload passes that feed the following ones; the very first parse, which nothing can overlap,
+        # primes the pipeline before the clock starts (cold_start_value below includes it).
+        reps = max(3, min(args.steps, 8))
+        tc = time.time()
+        tok = batches[0].parse_upload_begin(pool, bufs)
+        batches[0].parse_upload_wait(tok)
         h2d0, d2h0 = sum(x.h2d_bytes() for x in batches), sum(x.d2h_bytes() for x in batches)
         t0 = time.time()
-        tok = batches[0].parse_upload_begin(pool, bufs)               # pass 0 is parsed inside the timed region too
-        t_first = None
         for i in range(reps):
-            cur = batches[i & 1]
-            tw = time.time()
-            cur.parse_upload_wait(tok)
+            cur, nxt = batches[i & 1], batches[(i + 1) & 1]
             ti = time.time()
-            if t_first is None:
-                t_first = ti
-            gpu_side(cur)
-            if i + 1 < reps:
-                tok = batches[(i + 1) & 1].parse_upload_begin(pool, bufs)
+            gpu_side(cur)                                             # pass i: GPU + D2H, asynchronous
+            tok = nxt.parse_upload_begin(pool, bufs)                  # pass i+1: parse + H2D on the host threads, overlapping it
             tg = time.time()
             cur.sync()
             te = time.time()
-            phase["parse_upload_wait"] += ti - tw
+            nxt.parse_upload_wait(tok)
+            tw = time.time()
             phase["issue"] += tg - ti
             phase["gpu_and_d2h_wait"] += te - tg
+            phase["parse_upload_wait"] += tw - te
         t1 = time.time()
         dt = (t1 - t0) / reps
-        dt_steady = (t1 - t_first) / reps      # without the first parse, which nothing overlaps
+        dt_cold = (t1 - tc) / reps             # the same passes with the priming parse counted in
         h2d = (sum(x.h2d_bytes() for x in batches) - h2d0) // reps
         d2h = (sum(x.d2h_bytes() for x in batches) - d2h0) // reps
         last = np.ctypeslib.as_array(C.cast(host_out[(ps.num_pics - 1) & 1], C.POINTER(C.c_uint8)), shape=(fb * ne,))
@@ -456,18 +457,19 @@ def main():
         ok2 = ok2 and all(x.watchdog() == (0, 0) and x.idct_errors() == 0 for x in batches)
         if dist is not None:
             import torch
-            tt = torch.tensor([dt, dt_steady], device="cuda", dtype=torch.float64)
+            tt = torch.tensor([dt, dt_cold], device="cuda", dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt, dt_steady = float(tt[0].item()), float(tt[1].item())
+            dt, dt_cold = float(tt[0].item()), float(tt[1].item())
         e2e = {"value": world * ne * ps.num_pics * nmb / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world,
                "d2h_bytes_per_step": int(d2h) * world, "streams_per_gpu": ne, "host_threads_per_gpu": threads, "host_cpus": cpu_note,
                "bit_exact": bool(ok2), "passes": reps, "seconds_per_pass": dt,
-               "steady_state_value": world * ne * ps.num_pics * nmb / dt_steady,
+               "cold_start_value": world * ne * ps.num_pics * nmb / dt_cold,
                "phase_seconds_per_pass": {k_: round(v_ / reps, 4) for k_, v_ in phase.items()},
                "note": "host bitstream bytes -> host I420 frames through the C-ABI: every host thread parses a stream into its page-locked tape and "
                        "uploads the work-list; the GPU replays a pass while the host parses the next one into a second batch; every output "
-                       "picture is de-stripped on the GPU and copied into page-locked host memory; all inside the timed region, the first "
-                       "(un-overlapped) parse included -- steady_state_value leaves that one out"}
+                       "picture is de-stripped on the GPU and copied into page-locked host memory.  The timed window holds `passes` parse + upload "
+                       "passes and `passes` GPU + D2H passes of the running pipeline; cold_start_value also counts the first parse, which "
+                       "nothing overlaps"}
         L.h264bsdB200ParseUploadPoolDestroy(pool)
         for hp in host_out:
             L.h264bsdB200HostFree(hp)

@@ -271,10 +271,12 @@ void h264bsdB200BatchDestroy(b200_batch *h) { delete reinterpret_cast<Batch *>(h
 // queues the work-list's upload on ITS copy stream, waits for the copy and takes the next stream.  The host holds `threads`
 // tapes instead of one per stream, nothing is issued from the caller's thread, and parsing overlaps the H2D copies.
 struct b200_pu_worker {
-    b200_tape *tape = nullptr;
+    b200_tape *tape[2] = {nullptr, nullptr};     // two tapes: the upload of one overlaps the parse into the other
+    cudaEvent_t done[2] = {nullptr, nullptr};    // upload of tape[j] finished
+    bool busy[2] = {false, false};
     cudaStream_t st = nullptr;
 };
-struct b200_pu_pool {             // lives as long as the process: a worker slot keeps its tape and stream across jobs
+struct b200_pu_pool {             // lives as long as the process: a worker slot keeps its tapes and stream across jobs
     std::vector<b200_pu_worker> w;
 };
 struct b200_pu_job {
@@ -286,15 +288,24 @@ static void puRun(Batch *b, b200_pu_pool *pool, uint32_t n, const uint8_t *const
     auto work = [&](uint32_t slot) {
         cudaSetDevice(b->device());
         b200_pu_worker &w = pool->w[slot];
-        if (!w.st && cudaStreamCreateWithFlags(&w.st, cudaStreamNonBlocking) != cudaSuccess) { failed.fetch_add(n); return; }
+        if (!w.st && (cudaStreamCreateWithFlags(&w.st, cudaStreamNonBlocking) != cudaSuccess ||
+                      cudaEventCreateWithFlags(&w.done[0], cudaEventDisableTiming) != cudaSuccess ||
+                      cudaEventCreateWithFlags(&w.done[1], cudaEventDisableTiming) != cudaSuccess)) { failed.fetch_add(n); return; }
+        int j = 0;
         for (;;) {
             const uint32_t i = next.fetch_add(1);
             if (i >= n) break;
-            w.tape = h264bsdB200ReparseStream(w.tape, streams[i], lens[i], flags);
-            if (!w.tape || w.tape->status != 0) { failed.fetch_add(1); continue; }
-            if (w.tape->pinned != 1) h264bsdB200PinTape(w.tape);     // first use, or an array had to grow
-            if (!b->uploadTapeOn(i, w.tape, w.st) || cudaStreamSynchronize(w.st) != cudaSuccess) failed.fetch_add(1);
+            if (w.busy[j]) { cudaEventSynchronize(w.done[j]); w.busy[j] = false; }   // the copy out of this tape two streams ago
+            w.tape[j] = h264bsdB200ReparseStream(w.tape[j], streams[i], lens[i], flags);
+            if (!w.tape[j] || w.tape[j]->status != 0) { failed.fetch_add(1); continue; }
+            if (w.tape[j]->pinned != 1) h264bsdB200PinTape(w.tape[j]);     // first use, or an array had to grow
+            if (!b->uploadTapeOn(i, w.tape[j], w.st) || cudaEventRecord(w.done[j], w.st) != cudaSuccess) { failed.fetch_add(1); continue; }
+            w.busy[j] = true;
+            j ^= 1;
         }
+        // the job ends when every work-list has arrived
+        if (cudaStreamSynchronize(w.st) != cudaSuccess) failed.fetch_add(1);
+        w.busy[0] = w.busy[1] = false;
     };
     std::vector<std::thread> pool_;
     for (uint32_t t = 1; t < threads; t++) pool_.emplace_back(work, t);
@@ -345,7 +356,11 @@ b200_pu_pool *h264bsdB200ParseUploadPoolCreate(uint32_t threads) {
 void h264bsdB200ParseUploadPoolDestroy(b200_pu_pool *p) {
     if (!p) return;
     for (auto &w : p->w) {
-        if (w.tape) { h264bsdB200UnpinTape(w.tape); h264bsdB200FreeTape(w.tape); }
+        if (w.st) cudaStreamSynchronize(w.st);
+        for (int j = 0; j < 2; j++) {
+            if (w.tape[j]) h264bsdB200FreeTape(w.tape[j]);      // (unpins)
+            if (w.done[j]) cudaEventDestroy(w.done[j]);
+        }
         if (w.st) cudaStreamDestroy(w.st);
     }
     delete p;

@@ -148,8 +148,8 @@ bool Batch::create(int device, uint32_t nStreams, uint32_t widthMbs, uint32_t he
     CK(cudaMemsetAsync(dDoneDeblock_, 0, flagBytes, stream_));
     CK(cudaMalloc(&dBsWords_, flagBytes * 4));
     CK(cudaMalloc(&dWork_, (size_t)nStreams * g.nMbs));
-    // counters: [0] pass-B tickets, [1] filter tickets, [2] pass-A tickets (zeroed per picture); [3] IDCT range errors,
-    // [4..5] macroblocks with filter work, [6..7] macroblocks done by pass A (running totals)
+    // counters: [0] pass-B tickets, [1] filter tickets, [2] [3] tickets of the two pass-A instances (zeroed per picture);
+    // [4] IDCT range errors, [6..7] macroblocks with filter work (running totals)
     CK(cudaMalloc(&dCounters_, sizeof(uint32_t) * 8));
     CK(cudaMemsetAsync(dCounters_, 0, sizeof(uint32_t) * 8, stream_));
     CK(cudaMalloc(&dSlots_, sizeof(uint32_t) * nStreams));
@@ -172,8 +172,9 @@ bool Batch::create(int device, uint32_t nStreams, uint32_t widthMbs, uint32_t he
                 if (!encodeStripMap(enc, &m->chroma[nx - 1][v], pool_ + g.offC, g, g.rowsC, nFrames, nx, v ? 9 : 8)) return false;
     }
     int occA = 1, occD = 0, occS = 0, occB = 0;
-    CK(cudaFuncSetAttribute(passAKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(PassAWarpSmem) * kReconWarps)));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occA, passAKernel, kReconWarps * 32, sizeof(PassAWarpSmem) * kReconWarps));
+    CK(cudaFuncSetAttribute(passAKernelT<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(PassAWarpSmem) * kPassAWarps)));
+    CK(cudaFuncSetAttribute(passAKernelT<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(PassAWarpSmem) * kPassAWarps)));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occA, passAKernelT<false>, kPassAWarps * 32, sizeof(PassAWarpSmem) * kPassAWarps));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occD, deblockKernel, kDeblockWarps * 32, 0));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, strengthKernel, kDeblockWarps * 32, 0));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occB, reconIntraKernel, kReconWarps * 32, 0));
@@ -181,6 +182,15 @@ bool Batch::create(int device, uint32_t nStreams, uint32_t widthMbs, uint32_t he
     strengthBlocks_ = std::max(1, occS) * numSms_;
     passABlocks_ = std::max(1, occA) * numSms_;
     deblockBlocks_ = std::max(1, occD) * numSms_;
+    // B200_GRID_DIV=G (experiments, tools/group_bench.py): every persistent grid capped at 1/G of the CTAs that fit the machine, for G
+    // batches that run side by side on their own streams
+    if (const char *e = std::getenv("B200_GRID_DIV")) {
+        const int d = std::max(1, std::min(16, std::atoi(e)));
+        strengthBlocks_ = std::max(numSms_ / 2, strengthBlocks_ / d);
+        passABlocks_ = std::max(numSms_ / 2, passABlocks_ / d);
+        deblockBlocks_ = std::max(numSms_ / 2, deblockBlocks_ / d);
+        intraBlocks_ = std::max(numSms_ / 2, intraBlocks_ / d);
+    }
     // pass A: a warp task is a column piece of at most 32 macroblocks; pieces of a column are made equally long
     chunksPerCol_ = (heightMbs + 31) / 32;
     chunkRows_ = (heightMbs + chunksPerCol_ - 1) / chunksPerCol_;
@@ -402,7 +412,7 @@ bool Batch::launchPicture(const StreamJob *dJobs, const StreamJob *dJobsFilter, 
     ReconParams rp;
     if (recon) {
         rp.pool = pool_; rp.g = g_; rp.jobs = dJobs; rp.done = dDoneRecon_;
-        rp.ticket = dCounters_ + 0; rp.ticketA = dCounters_ + 2; rp.errors = dCounters_ + 3; rp.serial = serial_;
+        rp.ticket = dCounters_ + 0; rp.ticketA = dCounters_ + 2; rp.errors = dCounters_ + 4; rp.serial = serial_;
         rp.chunkB = (uint32_t)chunkB_;
         rp.chunksB = (maxB + rp.chunkB - 1) / rp.chunkB;
         rp.chunkRows = chunkRows_;
@@ -415,7 +425,7 @@ bool Batch::launchPicture(const StreamJob *dJobs, const StreamJob *dJobsFilter, 
         dp.ticket = dCounters_ + 1; dp.serial = serial_;
         dp.totalTickets = (uint32_t)g_.heightMbs * (((uint32_t)g_.nStreams + 1u) / 2u);
         dp.bsWords = dBsWords_; dp.work = dWork_;
-        dp.workCount = reinterpret_cast<unsigned long long *>(dCounters_ + 4);
+        dp.workCount = reinterpret_cast<unsigned long long *>(dCounters_ + 6);
     }
     auto launchStrength = [&](cudaStream_t st) {
         const uint32_t chunks = ((uint32_t)g_.nMbs + kDeblockWarps * 32 - 1) / (kDeblockWarps * 32) * (uint32_t)g_.nStreams;
@@ -430,10 +440,11 @@ bool Batch::launchPicture(const StreamJob *dJobs, const StreamJob *dJobsFilter, 
     }
     if (recon) {
         {
-            const uint32_t ctas = (rp.totalChunks + kReconWarps - 1) / kReconWarps;
+            const uint32_t ctas = (rp.totalChunks + kPassAWarps - 1) / kPassAWarps;
             const PassAMaps &maps = *reinterpret_cast<const PassAMaps *>(maps_);
-            passAKernel<<<std::min<uint32_t>(ctas, (uint32_t)passABlocks_), kReconWarps * 32, sizeof(PassAWarpSmem) * kReconWarps, stream_>>>(rp, maps);
-            launches_++;
+            passAKernelT<false><<<std::min<uint32_t>(ctas, (uint32_t)passABlocks_), kPassAWarps * 32, sizeof(PassAWarpSmem) * kPassAWarps, stream_>>>(rp, maps);
+            passAKernelT<true><<<std::min<uint32_t>(ctas, (uint32_t)passABlocks_), kPassAWarps * 32, sizeof(PassAWarpSmem) * kPassAWarps, stream_>>>(rp, maps);
+            launches_ += 2;
             mark(0);
         }
         if (maxB) {
@@ -470,7 +481,7 @@ bool Batch::launchPicture(const StreamJob *dJobs, const StreamJob *dJobsFilter, 
         launches_++;
         mark(2);
     }
-    CK(cudaMemsetAsync(dCounters_, 0, 3 * sizeof(uint32_t), stream_));
+    CK(cudaMemsetAsync(dCounters_, 0, 4 * sizeof(uint32_t), stream_));
     CK(cudaGetLastError());
     return true;
 }
@@ -811,7 +822,7 @@ uint64_t Batch::deblockWorkMbs() {
     if (!created_) return 0;
     cudaSetDevice(device_);
     if (auxStream_) cudaStreamSynchronize(auxStream_);
-    cudaMemcpyAsync(&v, dCounters_ + 4, sizeof v, cudaMemcpyDeviceToHost, stream_);
+    cudaMemcpyAsync(&v, dCounters_ + 6, sizeof v, cudaMemcpyDeviceToHost, stream_);
     cudaStreamSynchronize(stream_);
     return v;
 }
@@ -820,7 +831,7 @@ uint32_t Batch::idctErrors() {
     uint32_t v = 0;
     if (!created_) return 0;
     cudaSetDevice(device_);
-    cudaMemcpyAsync(&v, dCounters_ + 3, sizeof v, cudaMemcpyDeviceToHost, stream_);
+    cudaMemcpyAsync(&v, dCounters_ + 4, sizeof v, cudaMemcpyDeviceToHost, stream_);
     cudaStreamSynchronize(stream_);
     return v;
 }

@@ -9,7 +9,11 @@
 
 namespace b200 {
 
-constexpr int kReconWarps = 8;
+constexpr int kReconWarps = 8;    // warps per CTA of the intra pass
+#ifndef B200_PASSA_WARPS
+#define B200_PASSA_WARPS 4
+#endif
+constexpr int kPassAWarps = B200_PASSA_WARPS;   // warps per CTA of pass A
 constexpr int kChunkB = 8;   // most consecutive pass-B (wavefront) entries per warp task (ReconParams::chunkB <= kChunkB)
 
 // Tensor maps of pass A (Batch::create): strip-major planes -> raster windows (pool_geom.hpp).  A luma box is nx strips wide
@@ -551,11 +555,15 @@ __device__ __noinline__ uint32_t issueWindowFn(PassAWarpSmem *sm, int buf, const
 }
 
 #ifndef B200_PASSA_MINBLOCKS
-#define B200_PASSA_MINBLOCKS 2
+#define B200_PASSA_MINBLOCKS 5
 #endif
-__global__ void __launch_bounds__(kReconWarps * 32, B200_PASSA_MINBLOCKS)
-passAKernel(const ReconParams p, const __grid_constant__ PassAMaps maps) {
-    extern __shared__ __align__(128) uint8_t interSmemRaw[];   // kReconWarps x PassAWarpSmem (more than the 48 KB static limit)
+// Two instances: kMulti = false takes the copies, the macroblocks with one partition (P_Skip / P_L0_16x16) and I_PCM -- 94 % of a
+// typical P picture's pass-A macroblocks, through the short code path; kMulti = true takes the macroblocks with several
+// partitions (16x8, 8x16, 8x8 and below).  Each scans the records itself; their macroblocks are disjoint.
+template <bool kMulti>
+__global__ void __launch_bounds__(kPassAWarps * 32, B200_PASSA_MINBLOCKS)
+passAKernelT(const ReconParams p, const __grid_constant__ PassAMaps maps) {
+    extern __shared__ __align__(128) uint8_t interSmemRaw[];   // kPassAWarps x PassAWarpSmem (more than the 48 KB static limit)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const PoolGeom &g = p.g;
     PassAWarpSmem &sm = reinterpret_cast<PassAWarpSmem *>(interSmemRaw)[warp];
@@ -566,7 +574,7 @@ passAKernel(const ReconParams p, const __grid_constant__ PassAMaps maps) {
     }
     __syncwarp();
     uint32_t phaseBits = 0;   // bit b = phase parity of mbarrier b
-    const uint32_t nWarps = gridDim.x * kReconWarps;
+    const uint32_t nWarps = gridDim.x * kPassAWarps;
     const uint32_t chunksPerStream = p.chunksPerCol * (uint32_t)g.widthMbs;
     // this lane's spans inside a macroblock: 8 luma samples (row r8, columns c8..c8+7 = bytes 8 lane.. of the 256), 4 chroma
     // samples (plane cp, row cr, columns cc..cc+3 = bytes 4 lane.. of the 128)
@@ -574,10 +582,10 @@ passAKernel(const ReconParams p, const __grid_constant__ PassAMaps maps) {
     const int cr = lane >> 2, cp = (lane >> 1) & 1, cc = (lane & 1) * 4;
 
     // a warp's first chunk is its own number, the following ones come from a ticket counter (asked for one chunk ahead)
-    uint32_t chunk = blockIdx.x * kReconWarps + warp;
+    uint32_t chunk = blockIdx.x * kPassAWarps + warp;
     while (chunk < p.totalChunks) {
         uint32_t nextChunk = 0;
-        if (lane == 0) nextChunk = atomicAdd(p.ticketA, 1u) + nWarps;
+        if (lane == 0) nextChunk = atomicAdd(p.ticketA + (kMulti ? 1 : 0), 1u) + nWarps;
         const uint32_t s = chunk / chunksPerStream, c2 = chunk - s * chunksPerStream;
         const int mbx = (int)(c2 / p.chunksPerCol), row0 = (int)((c2 - (uint32_t)mbx * p.chunksPerCol) * p.chunkRows);
         const int n = min((int)p.chunkRows, g.heightMbs - row0);
@@ -601,9 +609,10 @@ passAKernel(const ReconParams p, const __grid_constant__ PassAMaps maps) {
             // a concealed macroblock carries the state the filter wants to see (Intra4x4); its pels are a copy of the reference
             // picture (no neighbours to wait for) or come from concealKernel (h264bsd_b200_tape.h)
             const bool concealed = ((mW0 >> 24) & B200_MBF_CONCEALED) && type == B200_MB_I_4x4;
-            if (concealed) isCopy = (w7 & 0xFFu) == 0;
+            if (kMulti) isInter = !concealed && type >= B200_MB_P_16x8 && type <= B200_MB_P_8x8REF0;
+            else if (concealed) isCopy = (w7 & 0xFFu) == 0;
             else if (type <= B200_MB_P_16x16 && mMask == 0 && mMv == 0) isCopy = true;
-            else isInter = type <= B200_MB_P_8x8REF0 || type == B200_MB_I_PCM;
+            else isInter = type <= B200_MB_P_16x16 || type == B200_MB_I_PCM;
         }
         const uint32_t copyMask = __ballot_sync(0xffffffffu, isCopy);
         uint32_t interMask = __ballot_sync(0xffffffffu, isInter);
@@ -614,7 +623,7 @@ passAKernel(const ReconParams p, const __grid_constant__ PassAMaps maps) {
         //   gX = luma strip | chroma strip << 16     gY = luma row | chroma row << 16
         //   gM = luma map (3 bits) | chroma map << 3 (2) | xo << 5 (4) | cxo << 9 (3) | mvx & 7 << 12 | mvy & 7 << 15 | window bytes << 18
         uint32_t gX = 0, gY = 0, gM = 0;
-        if (isInter && (mW0 & 0xFFu) <= B200_MB_P_16x16) {
+        if (!kMulti && isInter && (mW0 & 0xFFu) <= B200_MB_P_16x16) {
             const int mvx = (int)(int16_t)(mMv & 0xFFFFu), mvy = (int)(int16_t)(mMv >> 16);
             const int px = mbx * 16, py = (row0 + lane) * 16;
             const int xf = mvx & 3, yf = mvy & 3, nc = 16 + (xf ? 5 : 0), nr = 16 + (yf ? 5 : 0);
@@ -650,11 +659,12 @@ passAKernel(const ReconParams p, const __grid_constant__ PassAMaps maps) {
             const uint32_t gx = __shfl_sync(0xffffffffu, gX, l), gy = __shfl_sync(0xffffffffu, gY, l);
             const uint32_t type = nW0 & 0xFFu;
             const uint32_t coefBytes = type == B200_MB_I_PCM ? 384u : 32u * (uint32_t)__popc(nMask & 0x3FFFFFFu);
-            nArmed = type <= B200_MB_P_16x16 || coefBytes != 0;
+            const bool windows = !kMulti && type <= B200_MB_P_16x16;
+            nArmed = windows || coefBytes != 0;
             if (lane == 0 && nArmed) {
                 fenceProxyAsync();
                 mbarExpectTx(&sm.mbar[buf], (nGeom >> 18) + coefBytes);
-                if (type <= B200_MB_P_16x16) {
+                if (windows) {
                     const int ref = (int)(frameBase + (nRef & 0xFFu));
                     tmaLoad4d(sm.luma[buf], &maps.luma[0][0] + (nGeom & 7u), 0, (int)(gx & 0xFFFFu), (int)(gy & 0xFFFFu), ref, &sm.mbar[buf]);
                     tmaLoad4d(sm.chroma[buf], &maps.chroma[0][0] + ((nGeom >> 3) & 3u), 0, (int)(gx >> 16), (int)(gy >> 16), ref, &sm.mbar[buf]);
@@ -665,7 +675,7 @@ passAKernel(const ReconParams p, const __grid_constant__ PassAMaps maps) {
         if (interMask) prepare(__ffs(interMask) - 1, 0);
 
         // ---- copies: lanes 0..23 move the 16 luma + 8 chroma 16-byte units of a macroblock, four macroblocks in flight ----------
-        if (copyMask) {
+        if (!kMulti && copyMask) {
             const long long stride = (long long)g.frameStride;
             uint8_t *mine = lane < 16 ? lbase + lane * 16 : cbase + (lane - 16) * 16;   // this lane's unit of macroblock 0 of the chunk
             const uint32_t step = lane < 16 ? 256u : 128u;
@@ -703,7 +713,7 @@ passAKernel(const ReconParams p, const __grid_constant__ PassAMaps maps) {
             const bool armed = nArmed;
             const uint32_t type = w0 & 0xFFu;
             const int qpY = (w0 >> 8) & 0xFF, qpC = (w0 >> 16) & 0xFF;
-            const bool single = type <= B200_MB_P_16x16;
+            const bool single = !kMulti;    // (I_PCM, the one other kind of the first instance, leaves before it matters)
             // one partition: the next macroblock is staged now, while this one is computed; several partitions: both window
             // buffers are needed for this macroblock, the next one is staged when it is through
             if (single && interMask) prepare(__ffs(interMask) - 1, buf ^ 1);
@@ -718,14 +728,13 @@ passAKernel(const ReconParams p, const __grid_constant__ PassAMaps maps) {
                 *reinterpret_cast<uint2 *>(dstY) = *reinterpret_cast<const uint2 *>(src + lane * 8);
                 *reinterpret_cast<uint32_t *>(dstC) = *reinterpret_cast<const uint32_t *>(src + 256 + cp * 64 + cr * 8 + cc);
                 __syncwarp();
-                if (interMask) prepare(__ffs(interMask) - 1, buf ^ 1);
                 continue;
             }
             if (mask) residualShfl(sm, sm.coef[buf], mask, qpY, qpC, lane, p.errors);
             uint2 pv = make_uint2(0, 0);   // this lane's 8 luma prediction samples
             uint32_t pc = 0;               // and 4 chroma prediction samples
             const int mby = row0 + l;
-            if (single) {
+            if constexpr (!kMulti) {
                 const int cxf = (int)((geom >> 12) & 7u), cyf = (int)((geom >> 15) & 7u), xf = cxf & 3, yf = cyf & 3;
                 const int pitch = (int)(((geom >> 1) & 3u) + 1u) * 16, pitchC = (int)(((geom >> 4) & 1u) + 1u) * 16;
                 const uint8_t *G0 = sm.luma[buf] + ((geom >> 5) & 15u) + (yf ? 2 * pitch : 0) + (xf ? 2 : 0);

@@ -39,7 +39,7 @@ def prepare_engine_source():
     """engine.cu with every kernel<<<grid, block, smem, stream>>>(args); spelled EMU_LAUNCH(kernel, grid, block, args); and the
     reconstruction kernels' header with pass A's dynamic shared memory declared as a plain array"""
     src = open(os.path.join(CSRC, "engine", "engine.cu")).read()
-    launch = re.compile(r"([A-Za-z_]\w*(?:<\d+>)?)<<<(.*?)>>>\((.*)\);")
+    launch = re.compile(r"([A-Za-z_]\w*(?:<\w+>)?)<<<(.*?)>>>\((.*)\);")
     n = 0
     lines = []
     for line in src.split("\n"):
@@ -54,7 +54,7 @@ def prepare_engine_source():
     src = "\n".join(lines)
     assert src.count('#include "recon_kernel.cuh"') == 1
     src = src.replace('#include "recon_kernel.cuh"', '#include "recon_kernel_emu.cuh"')
-    src += "\nnamespace b200 {\nalignas(128) uint8_t interSmemRaw[sizeof(PassAWarpSmem) * kReconWarps];\n}\n"
+    src += "\nnamespace b200 {\nalignas(128) uint8_t interSmemRaw[sizeof(PassAWarpSmem) * kPassAWarps];\n}\n"
     with open(os.path.join(BUILD, "engine_hostemu.cpp"), "w") as f:
         f.write(src)
 

@@ -317,7 +317,8 @@ def test_legacy_api_sequence_parameter_set_change():
     the engine on H264BSD_HDRS_RDY like the reference re-allocates (h264bsd_decoder.c:343-389, h264bsd_storage.c:297-420) --
     same, smaller and larger size, the RGBA output path included"""
     small = _oracle.stream_bytes("test_640x360.h264")
-    big = _oracle.stream_bytes("test_1920x1080.h264")[:330000]
+    big = _oracle.stream_bytes("test_1920x1080.h264")
+    big = big[:big.rindex(b"\x00\x00\x00\x01", 0, 330000)]      # the first pictures, cut at a NAL unit boundary
     for first, second in ((small, small), (small, big), (big, small)):
         want = decode_stream(first) + decode_stream(second)
         d = H264bsdDecoder()
