@@ -295,6 +295,23 @@ __global__ void __launch_bounds__(kDeblockWarps * 32, 4) deblockKernel(const Deb
                 }
             }
             uint32_t todo = (__ballot_sync(0xffffffffu, mWork != 0) >> (16 * half)) & 0xFFFFu;
+            // The macroblock's own 16 luma rows / 2 x 8 chroma rows (and the 4 columns of its left neighbour) do not depend on the
+            // row above: they are fetched one macroblock ahead, into registers, while the current one is filtered.  When the next
+            // macroblock with work is the right neighbour, its left columns are this macroblock's right columns: taken from the
+            // tile in shared memory once it is finished.
+            uint4 pfY = make_uint4(0, 0, 0, 0);     // lane li: luma row li
+            uint2 pfC = make_uint2(0, 0);           // lane li: chroma plane li >> 3, row li & 7
+            uint32_t pfYl = 0, pfCl = 0;            // the left neighbour's last 4 luma / chroma pels of those rows
+            auto fetchOwn = [&](int x, bool withLeft) {
+                const uint8_t *lum = mbLuma(frame, g, x, y) + li * 16, *chr = mbChroma(frame, g, x, y) + cl * 16 + cpl * 8;
+                pfY = __ldcg(reinterpret_cast<const uint4 *>(lum));
+                pfC = __ldcg(reinterpret_cast<const uint2 *>(chr));
+                if (withLeft) {
+                    pfYl = __ldcg(reinterpret_cast<const uint32_t *>(lum - stripY + 12));
+                    pfCl = __ldcg(reinterpret_cast<const uint32_t *>(chr - stripC + 4));
+                }
+            };
+            if (__any_sync(0xffffffffu, todo != 0)) fetchOwn(x0 + (todo ? __ffs(todo) - 1 : 0), true);
 #pragma unroll 1
             while (__any_sync(0xffffffffu, todo != 0)) {
                 const bool active = live && todo != 0;
@@ -308,50 +325,32 @@ __global__ void __launch_bounds__(kDeblockWarps * 32, 4) deblockKernel(const Deb
                 bw.z = __shfl_sync(0xffffffffu, mBw.z, src); bw.w = __shfl_sync(0xffffffffu, mBw.w, src);
                 if (!active) bw = make_uint4(0, 0, 0, 0);
                 const int qp = (w0 >> 8) & 0xFF, qpL = qpn & 0xFF, qpT = (qpn >> 8) & 0xFF;
-                // the row above must have finished macroblocks x and x + 1
-                const uint32_t need = (active && y > 0) ? (uint32_t)min(x + 2, W) : 0u;
-                if (li == 0 && seen < need) seen = waitRow(rowMine - 1, serial16, need);
-                seen = __shfl_sync(0xffffffffu, seen, half * 16);
-                // stage 20 luma rows and 2 x 10 chroma rows (incl. 4 / 2 rows of the upper and 4 columns of the left neighbour): the
-                // 20 luma rows are 320 contiguous bytes of the macroblock's strip, the columns of the left neighbour the last 4 bytes
-                // of the same rows one strip earlier; a chroma row holds 8 Cb | 8 Cr
-                uint8_t *lum = mbLuma(frame, g, x, y) - 4 * 16, *chr = mbChroma(frame, g, x, y) - 2 * 16;
-#pragma unroll
-                for (int rd = 0; rd < 2; rd++) {
-                    const int r = li + 16 * rd;
-                    if (r < 20) {
-                        const uint4 own = __ldcg(reinterpret_cast<const uint4 *>(lum + r * 16));
-                        const uint32_t lef = __ldcg(reinterpret_cast<const uint32_t *>(lum + r * 16 - stripY + 12));
-                        *reinterpret_cast<uint4 *>(&sm.y[r][16]) = own;
-                        *reinterpret_cast<uint32_t *>(&sm.y[r][12]) = lef;
-                        const int pl = r >= 10, cr = r - pl * 10;
-                        const uint2 cown = __ldcg(reinterpret_cast<const uint2 *>(chr + cr * 16 + pl * 8));
-                        const uint32_t clef = __ldcg(reinterpret_cast<const uint32_t *>(chr + cr * 16 + pl * 8 - stripC + 4));
-                        *reinterpret_cast<uint2 *>(&sm.c[pl][cr][8]) = cown;
-                        *reinterpret_cast<uint32_t *>(&sm.c[pl][cr][4]) = clef;
-                    }
-                }
+                // the tile: rows 0..15 from the registers filled one step ago ...
+                *reinterpret_cast<uint4 *>(&sm.y[4 + li][16]) = pfY;
+                *reinterpret_cast<uint32_t *>(&sm.y[4 + li][12]) = pfYl;
+                *reinterpret_cast<uint2 *>(&sm.c[cpl][2 + cl][8]) = pfC;
+                *reinterpret_cast<uint32_t *>(&sm.c[cpl][2 + cl][4]) = pfCl;
+                // ... and the next macroblock's on their way
+                const int iNext = todo ? __ffs(todo) - 1 : -1;
+                const bool nextAdjacent = iNext == i + 1;
+                if (__any_sync(0xffffffffu, iNext >= 0)) fetchOwn(x0 + (iNext >= 0 ? iNext : i), !nextAdjacent);
                 // thresholds: GetLumaEdgeThresholds :1390-1458, GetChromaEdgeThresholds :1469-1541
                 const int offA = (int)(int8_t)(w3 & 0xFF), offB = (int)(int8_t)((w3 >> 8) & 0xFF), cqo = (int)(int8_t)((w3 >> 16) & 0xFF);
+                const int qcs = tb.qpc[clip3(0, 51, qp + cqo)], qcsL = tb.qpc[clip3(0, 51, qpL + cqo)], qcsT = tb.qpc[clip3(0, 51, qpT + cqo)];
                 __syncwarp();
 
+                // ---- vertical edges, luma then chroma: own rows only, nothing of the row above ----------------------------------
+                // segment (grp, e) is nibble (grp & 1) * 4 + e of word grp >> 1
+                const uint32_t vAny = bw.x | bw.y;   // (per lane: the halves differ)
 #pragma unroll 1
                 for (int pass = 0; pass < 2; pass++) {
-                    // pass 0: luma lines (16 per macroblock), pass 1: chroma lines (2 planes x 8)
                     const bool chroma = pass != 0;
-                    const int qs = chroma ? tb.qpc[clip3(0, 51, qp + cqo)] : qp;
-                    const int qsL = chroma ? tb.qpc[clip3(0, 51, qpL + cqo)] : qpL;
-                    const int qsT = chroma ? tb.qpc[clip3(0, 51, qpT + cqo)] : qpT;
-                    const EdgeThr tIn = makeThr(tb, qs, offA, offB);
-                    const EdgeThr tL = makeThr(tb, (qs + qsL + 1) >> 1, offA, offB), tT = makeThr(tb, (qs + qsT + 1) >> 1, offA, offB);
+                    const int qs = chroma ? qcs : qp, qsL = chroma ? qcsL : qpL;
+                    const EdgeThr tIn = makeThr(tb, qs, offA, offB), tL = makeThr(tb, (qs + qsL + 1) >> 1, offA, offB);
                     const int grp = chroma ? grpC : grpY;
                     uint8_t *rowp = chroma ? &sm.c[cpl][2 + cl][8] : &sm.y[4 + li][16];    // sample (0, line)
-                    uint8_t *colp = chroma ? &sm.c[cpl][2][8 + cl] : &sm.y[4][16 + li];    // sample (line, 0)
-                    const int pitch = chroma ? 16 : 32;
                     const int estep = chroma ? 2 : 4;                            // pels between edge e and e + 1 (luma numbering)
-                    // vertical edges: segment (grp, e) is nibble (grp & 1) * 4 + e of word grp >> 1
                     const uint32_t vWord = (grp >> 1) ? bw.y : bw.x;
-                    const uint32_t vAny = bw.x | bw.y;   // (per lane: the halves differ)
 #pragma unroll 1
                     for (int e = 0; e < 4; e += (chroma ? 2 : 1)) {
                         // no strength on this edge in any row of either macroblock: skip (warp-uniform)
@@ -370,8 +369,33 @@ __global__ void __launch_bounds__(kDeblockWarps * 32, 4) deblockKernel(const Deb
                             }
                         }
                     }
-                    __syncwarp();
-                    // horizontal edges: segment 16 + e * 4 + grp is nibble (e & 1) * 4 + grp of word 2 + (e >> 1)
+                }
+                // ---- the row above: needed by the top edge only.  It must have finished macroblocks x and x + 1 ------------------
+                const bool topEdge = (bw.z & 0xFFFFu) != 0;      // a strength on the macroblock's top edge (segments 16..19)
+                const uint32_t need = (active && topEdge && y > 0) ? (uint32_t)min(x + 2, W) : 0u;
+                if (li == 0 && seen < need) seen = waitRow(rowMine - 1, serial16, need);
+                seen = __shfl_sync(0xffffffffu, seen, half * 16);
+                __syncwarp();     // (orders the other lanes' loads of the upper rows after lane 0's acquire)
+                uint8_t *lum = mbLuma(frame, g, x, y), *chr = mbChroma(frame, g, x, y);
+                if (topEdge) {
+                    // the upper neighbour's last 4 luma rows (lanes 0..3) and last 2 chroma rows of both planes (lanes 4..7)
+                    if (li < 4) *reinterpret_cast<uint4 *>(&sm.y[li][16]) = __ldcg(reinterpret_cast<const uint4 *>(lum - (4 - li) * 16));
+                    else if (li < 8) {
+                        const int pl = (li >> 1) & 1, r = li & 1;
+                        *reinterpret_cast<uint2 *>(&sm.c[pl][r][8]) = __ldcg(reinterpret_cast<const uint2 *>(chr - (2 - r) * 16 + pl * 8));
+                    }
+                }
+                __syncwarp();
+                // ---- horizontal edges, luma then chroma: segment 16 + e * 4 + grp is nibble (e & 1) * 4 + grp of word 2 + (e >> 1) ----
+#pragma unroll 1
+                for (int pass = 0; pass < 2; pass++) {
+                    const bool chroma = pass != 0;
+                    const int qs = chroma ? qcs : qp, qsT = chroma ? qcsT : qpT;
+                    const EdgeThr tIn = makeThr(tb, qs, offA, offB), tT = makeThr(tb, (qs + qsT + 1) >> 1, offA, offB);
+                    const int grp = chroma ? grpC : grpY;
+                    uint8_t *colp = chroma ? &sm.c[cpl][2][8 + cl] : &sm.y[4][16 + li];    // sample (line, 0)
+                    const int pitch = chroma ? 16 : 32;
+                    const int estep = chroma ? 2 : 4;
 #pragma unroll 1
                     for (int e = 0; e < 4; e += (chroma ? 2 : 1)) {
                         const uint32_t hWord = (e >> 1) ? bw.w : bw.z;
@@ -394,21 +418,30 @@ __global__ void __launch_bounds__(kDeblockWarps * 32, 4) deblockKernel(const Deb
                             }
                         }
                     }
-                    __syncwarp();
                 }
-                // write back: own rows incl. the 4 columns of the left neighbour, and the 4 (2) rows of the upper neighbour
+                __syncwarp();
+                // write back: own rows incl. the 4 columns of the left neighbour, and -- where the top edge was filtered -- the
+                // 4 (2) rows of the upper neighbour
                 if (active) {
-#pragma unroll
-                    for (int rd = 0; rd < 2; rd++) {
-                        const int r = li + 16 * rd;
-                        if (r < 20) {
-                            if (r >= 4 || y > 0) *reinterpret_cast<uint4 *>(lum + r * 16) = *reinterpret_cast<const uint4 *>(&sm.y[r][16]);
-                            if (r >= 4 && x > 0) *reinterpret_cast<uint32_t *>(lum + r * 16 - stripY + 12) = *reinterpret_cast<const uint32_t *>(&sm.y[r][12]);
-                            const int pl = r >= 10, cr = r - pl * 10;
-                            if (cr >= 2 || y > 0) *reinterpret_cast<uint2 *>(chr + cr * 16 + pl * 8) = *reinterpret_cast<const uint2 *>(&sm.c[pl][cr][8]);
-                            if (cr >= 2 && x > 0) *reinterpret_cast<uint32_t *>(chr + cr * 16 + pl * 8 - stripC + 4) = *reinterpret_cast<const uint32_t *>(&sm.c[pl][cr][4]);
+                    *reinterpret_cast<uint4 *>(lum + li * 16) = *reinterpret_cast<const uint4 *>(&sm.y[4 + li][16]);
+                    *reinterpret_cast<uint2 *>(chr + cl * 16 + cpl * 8) = *reinterpret_cast<const uint2 *>(&sm.c[cpl][2 + cl][8]);
+                    if (x > 0) {
+                        *reinterpret_cast<uint32_t *>(lum + li * 16 - stripY + 12) = *reinterpret_cast<const uint32_t *>(&sm.y[4 + li][12]);
+                        *reinterpret_cast<uint32_t *>(chr + cl * 16 + cpl * 8 - stripC + 4) = *reinterpret_cast<const uint32_t *>(&sm.c[cpl][2 + cl][4]);
+                    }
+                    if (topEdge) {
+                        if (li < 4) *reinterpret_cast<uint4 *>(lum - (4 - li) * 16) = *reinterpret_cast<const uint4 *>(&sm.y[li][16]);
+                        else if (li < 8) {
+                            const int pl = (li >> 1) & 1, r = li & 1;
+                            *reinterpret_cast<uint2 *>(chr - (2 - r) * 16 + pl * 8) = *reinterpret_cast<const uint2 *>(&sm.c[pl][r][8]);
                         }
                     }
+                }
+                // the right neighbour comes next: its left columns are this macroblock's columns 12..15 (7..4 of chroma) as they
+                // are now
+                if (nextAdjacent) {
+                    pfYl = *reinterpret_cast<const uint32_t *>(&sm.y[4 + li][28]);
+                    pfCl = *reinterpret_cast<const uint32_t *>(&sm.c[cpl][2 + cl][12]);
                 }
                 // publish the row's progress: everything before the half's next macroblock with work (or the end of this group)
                 // is finished.  The warp barrier orders every lane's stores before the release of lane 0 of each half, and a

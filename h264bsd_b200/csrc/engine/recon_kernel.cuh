@@ -160,14 +160,15 @@ __device__ __forceinline__ int lumaQpel(const uint8_t *G0, int pitch, int x, int
 }
 
 // 8 consecutive bytes from an arbitrarily aligned shared-memory address
+// (the low bits of a generic pointer into shared memory are those of the shared offset: no address-space conversion needed)
 __device__ __forceinline__ uint2 lds8(const uint8_t *p) {
-    const uint32_t a = smemAddr(p), sh = (a & 3u) * 8u;
+    const uint32_t a = (uint32_t)reinterpret_cast<uintptr_t>(p), sh = (a & 3u) * 8u;
     const uint32_t *w = reinterpret_cast<const uint32_t *>(p - (a & 3u));
     const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
     return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
 }
 __device__ __forceinline__ uint32_t lds4(const uint8_t *p) {
-    const uint32_t a = smemAddr(p), sh = (a & 3u) * 8u;
+    const uint32_t a = (uint32_t)reinterpret_cast<uintptr_t>(p), sh = (a & 3u) * 8u;
     const uint32_t *w = reinterpret_cast<const uint32_t *>(p - (a & 3u));
     return __funnelshift_r(w[0], w[1], sh);
 }
@@ -179,7 +180,7 @@ constexpr int kTapsHi = 0x000001FB;  // bytes (-5, 1, 0, 0)
 // horizontal 6-tap sums (+ acc0) for 8 outputs; rowp points at sample x0-2 of the row (13 samples are read).  The taps of
 // output k are bytes k..k+5 of the row: two dot products, over bytes k..k+3 and k+4..k+7 (the last two times zero)
 __device__ __forceinline__ void hrow8(const uint8_t *rowp, int *hs, int acc0) {
-    const uint32_t a = smemAddr(rowp), sh0 = (a & 3u) * 8u;
+    const uint32_t a = (uint32_t)reinterpret_cast<uintptr_t>(rowp), sh0 = (a & 3u) * 8u;
     const uint32_t *w = reinterpret_cast<const uint32_t *>(rowp - (a & 3u));
     const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
     // aligned view: byte k of the row = byte (k + (a&3)) of (w0,w1,w2,w3)
@@ -485,14 +486,19 @@ __device__ __noinline__ void residualShfl(PassAWarpSmem &sm, const uint8_t *cbuf
     const int r = lane & 3, g4 = lane >> 2;
     const uint32_t zz = r == 0 ? 0x6510u : r == 1 ? 0xC742u : r == 2 ? 0xDB83u : 0xFEA9u;   // zig-zag positions of raster row r
     const int orow = ((r & 1) << 1) | (r >> 1);   // the row this lane holds after the column transform
+    // this lane's two scale factors (columns 0, 2 / 1, 3 of its row), for a luma and for a chroma block
+    int sAY, sBY, sAC, sBC;
+    {
+        const int dY = qpY / 6, mY = qpY - 6 * dY, dC = qpC / 6, mC = qpC - 6 * dC;
+        sAY = levelScale(mY, r & 1) << dY; sBY = levelScale(mY, 1 + (r & 1)) << dY;
+        sAC = levelScale(mC, r & 1) << dC; sBC = levelScale(mC, 1 + (r & 1)) << dC;
+    }
 #pragma unroll 1
     for (int base = 0; base < nAct; base += 8) {
         const bool valid = base + g4 < nAct;
         const int b = valid ? sm.list[base + g4] : 0;
         const bool isCoded = valid && ((coded >> b) & 1u);
-        const int qp = b < 16 ? qpY : qpC;
-        const int qpDiv = qp / 6, qpMod = qp - 6 * qpDiv;
-        const int sA = levelScale(qpMod, r & 1) << qpDiv, sB = levelScale(qpMod, 1 + (r & 1)) << qpDiv;
+        const int sA = b < 16 ? sAY : sAC, sB = b < 16 ? sBY : sBC;
         int d0 = 0, d1 = 0, d2 = 0, d3 = 0;
         if (isCoded) {
             const int16_t *lev = reinterpret_cast<const int16_t *>(cbuf) + (nDc + __popc(coded & ((1u << b) - 1u))) * 16;
@@ -508,7 +514,7 @@ __device__ __noinline__ void residualShfl(PassAWarpSmem &sm, const uint8_t *cbuf
         // column transform: rows 0/2 and 1/3 meet first (f0 = E0 + E2 in lane 0, f1 = E0 - E2 in lane 2, f2 = (E1 >> 1) - E3 in
         // lane 1, f3 = E1 + (E3 >> 1) in lane 3), then 0/3 and 1/2 (rows 0 and 3 out of lanes 0 and 3, rows 1 and 2 out of lanes 2 and 1)
         int o[4];
-        bool bad = false;
+        uint32_t range = 0;
 #pragma unroll
         for (int c = 0; c < 4; c++) {
             const int pv = __shfl_xor_sync(0xffffffffu, e[c], 2);
@@ -516,10 +522,10 @@ __device__ __noinline__ void residualShfl(PassAWarpSmem &sm, const uint8_t *cbuf
             const int f = (r == 2 ? -h : h) + (r == 1 ? -pv : pv);
             const int q = __shfl_xor_sync(0xffffffffu, f, 3);
             o[c] = ((r & 1) ? q - f : f + q) >> 6;
-            bad |= (unsigned)(o[c] + 512) > 1023u;
+            range |= (uint32_t)(o[c] + 512);    // inside [-512, 511] exactly when no bit above the tenth is set
         }
         if (valid) {
-            if (bad) atomicAdd(errors, 1u);
+            if (range >> 10) atomicAdd(errors, 1u);
             int32_t *dst;
             if (b < 16) dst = &sm.resY[(((b >> 1) & 1) + ((b >> 3) & 1) * 2) * 4 + orow][((b & 1) + ((b >> 2) & 1) * 2) * 4];
             else dst = &sm.resC[(b - 16) >> 2][((b >> 1) & 1) * 4 + orow][(b & 1) * 4];
@@ -662,7 +668,9 @@ passAKernelT(const ReconParams p, const __grid_constant__ PassAMaps maps) {
             const bool windows = !kMulti && type <= B200_MB_P_16x16;
             nArmed = windows || coefBytes != 0;
             if (lane == 0 && nArmed) {
+#ifndef B200_NO_PREP_FENCE
                 fenceProxyAsync();
+#endif
                 mbarExpectTx(&sm.mbar[buf], (nGeom >> 18) + coefBytes);
                 if (windows) {
                     const int ref = (int)(frameBase + (nRef & 0xFFu));
@@ -676,7 +684,9 @@ passAKernelT(const ReconParams p, const __grid_constant__ PassAMaps maps) {
 
         // ---- copies: lanes 0..23 move the 16 luma + 8 chroma 16-byte units of a macroblock, four macroblocks in flight ----------
         if (!kMulti && copyMask) {
-            const long long stride = (long long)g.frameStride;
+            // lane l: where the reference frame of ITS macroblock lies relative to the current frame, in 256-byte units (a frame
+            // stride is a multiple of 256)
+            const int myDelta = ((int)(mRef & 0xFFu) - (int)job.curSlot) * (int)(g.frameStride >> 8);
             uint8_t *mine = lane < 16 ? lbase + lane * 16 : cbase + (lane - 16) * 16;   // this lane's unit of macroblock 0 of the chunk
             const uint32_t step = lane < 16 ? 256u : 128u;
             uint32_t cm = copyMask;
@@ -684,20 +694,17 @@ passAKernelT(const ReconParams p, const __grid_constant__ PassAMaps maps) {
             while (cm) {
                 uint4 v[4];
                 uint8_t *dst[4];
-                bool ok[4];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    ok[j] = cm != 0;
-                    const int e = ok[j] ? __ffs(cm) - 1 : 0;
+                    const int e = __ffs(cm) - 1;          // (-1 once the mask is empty: lanes >= 24 and those steps do nothing)
                     cm &= cm - 1;
-                    const long long slot = (long long)(__shfl_sync(0xffffffffu, mRef, e) & 0xFFu);
-                    dst[j] = mine + (uint32_t)e * step;
-                    ok[j] = ok[j] && lane < 24;
-                    if (ok[j]) v[j] = __ldg(reinterpret_cast<const uint4 *>(dst[j] + (slot - (long long)job.curSlot) * stride));
+                    const long long delta = (long long)__shfl_sync(0xffffffffu, myDelta, e & 31) * 256;
+                    dst[j] = (e >= 0 && lane < 24) ? mine + (uint32_t)e * step : nullptr;
+                    if (dst[j]) v[j] = __ldg(reinterpret_cast<const uint4 *>(dst[j] + delta));
                 }
 #pragma unroll
                 for (int j = 0; j < 4; j++)
-                    if (ok[j]) *reinterpret_cast<uint4 *>(dst[j]) = v[j];
+                    if (dst[j]) *reinterpret_cast<uint4 *>(dst[j]) = v[j];
             }
         }
 
