@@ -20,7 +20,7 @@ class PicHdr(C.Structure):
         ("picIndex", C.c_uint32), ("isIdr", C.c_uint32), ("isRef", C.c_uint32), ("numCoefBlocks", C.c_uint32),
         ("mbRecOffset", C.c_uint64), ("coefOffset", C.c_uint64), ("numErrMbs", C.c_uint32), ("numOut", C.c_uint32),
         ("outSlot", C.c_uint8 * 20), ("outPicIndex", C.c_uint32 * 20), ("picId", C.c_uint32), ("numPassA", C.c_uint32),
-        ("numPassB", C.c_uint32), ("numCopy", C.c_uint32), ("numRun", C.c_uint32), ("numRunMbs", C.c_uint32),
+        ("numPassB", C.c_uint32), ("numCopy", C.c_uint32), ("orderOffset", C.c_uint32), ("reserved7", C.c_uint32),
         ("numConceal", C.c_uint32), ("reserved5", C.c_uint32), ("filterRecOffset", C.c_uint64),
     ]
 
@@ -33,7 +33,7 @@ class Tape(C.Structure):
         ("mbRecBytes", C.c_uint64), ("coefBytes", C.c_uint64),
         ("pics", C.POINTER(PicHdr)), ("mbRecs", C.POINTER(C.c_uint8)), ("coefs", C.POINTER(C.c_uint8)),
         ("mbOrder", C.POINTER(C.c_uint16)),
-        ("numOutputs", C.c_uint32), ("reserved2", C.c_uint32), ("outputPicIndex", C.POINTER(C.c_uint32)),
+        ("numOutputs", C.c_uint32), ("numOrder", C.c_uint32), ("outputPicIndex", C.POINTER(C.c_uint32)),
         ("status", C.c_uint32), ("pinned", C.c_uint32),
         ("capRecs", C.c_uint64), ("capCoefs", C.c_uint64), ("capOrder", C.c_uint64), ("capPics", C.c_uint64),
         ("capOutputs", C.c_uint32), ("reserved4", C.c_uint32),

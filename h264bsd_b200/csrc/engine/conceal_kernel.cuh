@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(kConcealWarps * 32) concealKernel(const ReconP
     const StreamJob job = p.jobs[s];
     if (!job.nE) return;
     uint8_t *cur = framePtr(p.pool, g, s * (uint32_t)g.numSlots + job.curSlot);
-    const uint16_t *list = job.orderB + job.nB;
+    const uint16_t *list = job.orderE;
 #pragma unroll 1
     for (uint32_t e = 0; e < job.nE; e++) {
         const uint32_t mb = __ldg(list + e);

@@ -217,7 +217,7 @@ bool Batch::uploadTapeOn(uint32_t stream, const b200_tape *t, cudaStream_t st) {
     if (t->widthMbs != (uint32_t)g_.widthMbs || t->heightMbs != (uint32_t)g_.heightMbs || t->numSlots > (uint32_t)g_.numSlots) return false;
     CK(cudaSetDevice(device_));
     DevTape &d = tapes_[stream];
-    const size_t orderBytes = (size_t)t->numPics * g_.nMbs * sizeof(uint16_t);
+    const size_t orderBytes = (size_t)t->numOrder * sizeof(uint16_t);
     // re-use the device arrays of a previous upload when they are large enough (no cudaMalloc in steady state)
     if (!d.owned || d.capRecs < t->mbRecBytes || d.capCoefs < t->coefBytes || d.capOrder < orderBytes) {
         CK(cudaStreamSynchronize(stream_));
@@ -234,7 +234,7 @@ bool Batch::uploadTapeOn(uint32_t stream, const b200_tape *t, cudaStream_t st) {
     d.recBytes = t->mbRecBytes; d.coefBytes = t->coefBytes; d.orderBytes = orderBytes;
     CK(cudaMemcpyAsync(d.recs, t->mbRecs, t->mbRecBytes, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d.coefs, t->coefs, t->coefBytes, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(d.order, t->mbOrder, orderBytes, cudaMemcpyHostToDevice, st));
+    if (orderBytes) CK(cudaMemcpyAsync(d.order, t->mbOrder, orderBytes, cudaMemcpyHostToDevice, st));
     d.pics.assign(t->pics, t->pics + t->numPics);
     h2dBytes_ += t->mbRecBytes + t->coefBytes + orderBytes;
     return true;
@@ -250,7 +250,7 @@ bool Batch::uploadTapeRange(uint32_t stream, const b200_tape *t, uint32_t firstP
     CK(cudaSetDevice(device_));
     if (!uploadStream_) CK(cudaStreamCreateWithFlags(&uploadStream_, cudaStreamNonBlocking));
     DevTape &d = tapes_[stream];
-    const size_t orderBytes = (size_t)t->numPics * g_.nMbs * sizeof(uint16_t);
+    const size_t orderBytes = (size_t)t->numOrder * sizeof(uint16_t);
     if (firstPic == 0) {
         if (!d.owned || d.capRecs < t->mbRecBytes || d.capCoefs < t->coefBytes || d.capOrder < orderBytes) {
             CK(cudaStreamSynchronize(stream_));
@@ -274,10 +274,10 @@ bool Batch::uploadTapeRange(uint32_t stream, const b200_tape *t, uint32_t firstP
     const uint32_t last = firstPic + numPics;
     const uint64_t r0 = t->pics[firstPic].mbRecOffset, r1 = last < t->numPics ? t->pics[last].mbRecOffset : t->mbRecBytes;
     const uint64_t c0 = t->pics[firstPic].coefOffset, c1 = last < t->numPics ? t->pics[last].coefOffset : t->coefBytes;
-    const size_t o0 = (size_t)firstPic * g_.nMbs * sizeof(uint16_t), o1 = (size_t)last * g_.nMbs * sizeof(uint16_t);
+    const size_t o0 = (size_t)t->pics[firstPic].orderOffset * sizeof(uint16_t), o1 = (size_t)(last < t->numPics ? t->pics[last].orderOffset : t->numOrder) * sizeof(uint16_t);
     if (r1 > r0) CK(cudaMemcpyAsync(d.recs + r0, t->mbRecs + r0, r1 - r0, cudaMemcpyHostToDevice, uploadStream_));
     if (c1 > c0) CK(cudaMemcpyAsync(d.coefs + c0, t->coefs + c0, c1 - c0, cudaMemcpyHostToDevice, uploadStream_));
-    CK(cudaMemcpyAsync(d.order + o0, reinterpret_cast<const uint8_t *>(t->mbOrder) + o0, o1 - o0, cudaMemcpyHostToDevice, uploadStream_));
+    if (o1 > o0) CK(cudaMemcpyAsync(d.order + o0, reinterpret_cast<const uint8_t *>(t->mbOrder) + o0, o1 - o0, cudaMemcpyHostToDevice, uploadStream_));
     h2dBytes_ += (r1 - r0) + (c1 - c0) + (o1 - o0);
     return true;
 }
@@ -310,16 +310,12 @@ bool Batch::replicateTape(uint32_t src) {
         d.recBytes = s.recBytes; d.coefBytes = s.coefBytes; d.orderBytes = s.orderBytes;
         CK(cudaMemcpyAsync(d.recs, s.recs, s.recBytes, cudaMemcpyDeviceToDevice, stream_));
         CK(cudaMemcpyAsync(d.coefs, s.coefs, s.coefBytes, cudaMemcpyDeviceToDevice, stream_));
-        CK(cudaMemcpyAsync(d.order, s.order, s.orderBytes, cudaMemcpyDeviceToDevice, stream_));
+        if (s.orderBytes) CK(cudaMemcpyAsync(d.order, s.order, s.orderBytes, cudaMemcpyDeviceToDevice, stream_));
         d.pics = s.pics;
     }
     jobsDirty_ = true;
     return true;
 }
-
-// where the pass-B (intra) entries start inside a picture's processing-order list (b200_tape.mbOrder: runs, single copies and
-// the other pass-A macroblocks come first; pass A reads the records in raster order and does not use those sections)
-static inline uint32_t orderBOffset(const b200_pic_hdr &h) { return 2u * h.numRun + h.numPassA - h.numRunMbs; }
 
 bool Batch::buildJobs() {
     uint32_t np = 0xFFFFFFFFu;
@@ -338,7 +334,7 @@ bool Batch::buildJobs() {
             StreamJob &j = jobs[(size_t)k * g_.nStreams + s];
             j.recs = reinterpret_cast<const b200_mb_rec *>(t.recs + t.pics[k].mbRecOffset);
             j.coefs = reinterpret_cast<const int16_t *>(t.coefs + t.pics[k].coefOffset);
-            j.orderB = reinterpret_cast<const uint16_t *>(t.order) + (size_t)k * g_.nMbs + orderBOffset(t.pics[k]);
+            j.orderE = reinterpret_cast<const uint16_t *>(t.order) + t.pics[k].orderOffset;
             j.curSlot = (uint16_t)t.pics[k].curSlot;
             j.nB = (uint16_t)t.pics[k].numPassB;
             j.nE = (uint16_t)t.pics[k].numConceal;
@@ -550,9 +546,7 @@ bool Batch::submitHostPicture(uint32_t stream, const b200_pic_hdr &hdr, const b2
     CK(cudaSetDevice(device_));
     const size_t recBytes = (size_t)g_.nMbs * sizeof(b200_mb_rec);
     const size_t coefBytes = (size_t)hdr.numCoefBlocks * B200_COEF_BLOCK_BYTES;
-    // of the processing-order list only the intra and concealment sections are needed
-    const uint32_t ordOff = orderBOffset(hdr), ordN = hdr.numPassB + hdr.numConceal;
-    const size_t orderBytes = (size_t)ordN * sizeof(uint16_t);
+    const size_t orderBytes = (size_t)hdr.numConceal * sizeof(uint16_t);     // the concealment order
     const size_t need = recBytes + coefBytes + orderBytes + (filterRecs ? recBytes + 256 : 0) + 1024;
     const int b = stageIdx_ ^= 1;
     if (stageCap_[b] < need) {
@@ -575,7 +569,7 @@ bool Batch::submitHostPicture(uint32_t stream, const b200_pic_hdr &hdr, const b2
     const size_t recOff = 256, orderOff = (recOff + recBytes + 255) & ~(size_t)255, coefOff = (orderOff + orderBytes + 255) & ~(size_t)255;
     job.recs = reinterpret_cast<const b200_mb_rec *>(dStage_[b] + recOff);
     job.coefs = reinterpret_cast<const int16_t *>(dStage_[b] + coefOff);
-    job.orderB = reinterpret_cast<const uint16_t *>(dStage_[b] + orderOff);
+    job.orderE = reinterpret_cast<const uint16_t *>(dStage_[b] + orderOff);
     job.curSlot = (uint16_t)hdr.curSlot;
     job.nB = (uint16_t)hdr.numPassB;
     job.nE = (uint16_t)hdr.numConceal;
@@ -592,7 +586,7 @@ bool Batch::submitHostPicture(uint32_t stream, const b200_pic_hdr &hdr, const b2
     std::memcpy(h, &job, sizeof job);
     std::memcpy(h + 64, &jobF, sizeof jobF);
     std::memcpy(h + recOff, recs, recBytes);
-    if (orderBytes) std::memcpy(h + orderOff, order + ordOff, orderBytes);
+    if (orderBytes) std::memcpy(h + orderOff, order, orderBytes);
     if (coefBytes) std::memcpy(h + coefOff, coefs, coefBytes);
     CK(cudaMemcpyAsync(dStage_[b], h, end, cudaMemcpyHostToDevice, stream_));
     h2dBytes_ += end;

@@ -39,10 +39,9 @@ struct PoolGeom {
 struct StreamJob {
     const b200_mb_rec *recs;  // nMbs records of this picture, raster order
     const int16_t *coefs;     // this picture's coefficient pool
-    const uint16_t *orderB;   // nB intra-predicted macroblocks in wavefront order, then nE spatially concealed ones in
-                              // concealment order (the tail of b200_tape.mbOrder for this picture)
+    const uint16_t *orderE;   // the nE spatially concealed macroblocks in concealment order (b200_tape.mbOrder for this picture)
     uint16_t curSlot;
-    uint16_t nB;
+    uint16_t nB;              // intra-predicted macroblocks (0: the intra pass has nothing to do for this stream)
     uint16_t nE;
     uint16_t pad;
 };

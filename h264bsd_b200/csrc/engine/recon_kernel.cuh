@@ -668,9 +668,7 @@ passAKernelT(const ReconParams p, const __grid_constant__ PassAMaps maps) {
             const bool windows = !kMulti && type <= B200_MB_P_16x16;
             nArmed = windows || coefBytes != 0;
             if (lane == 0 && nArmed) {
-#ifndef B200_NO_PREP_FENCE
                 fenceProxyAsync();
-#endif
                 mbarExpectTx(&sm.mbar[buf], (nGeom >> 18) + coefBytes);
                 if (windows) {
                     const int ref = (int)(frameBase + (nRef & 0xFFu));

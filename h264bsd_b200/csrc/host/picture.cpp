@@ -70,7 +70,7 @@ void PictureState::resize(uint32_t w, uint32_t h) {
     coefs.clear();
     orderClass.assign(2 * (size_t)picSizeInMbs, 0);
     lateFixup_ = false;
-    numIntraPred_ = 0;
+    numIntraPred_ = numCopies_ = 0;
     sliceIdCounter = numDecodedMbs = lastMbAddr = 0;
 }
 
@@ -103,7 +103,7 @@ void PictureState::beginPicture() {
     coefs.clear();
     orderClass.resize(2 * (size_t)picSizeInMbs);
     lateFixup_ = false;
-    numIntraPred_ = 0;
+    numIntraPred_ = numCopies_ = 0;
     concealOrder.clear();
 }
 
@@ -608,14 +608,13 @@ bool PictureState::residualInRange(const MbSyntax &mb, bool i16, int qpY, int qp
     return true;
 }
 
-// Class of a macroblock for the processing order (0 other pass-A, 1 plain copy, 4 pass-B; zr = 1 + reference slot of a
-// zero-vector plain copy), its deblocking edge flags (GetMbFilteringFlags, deblocking.c:289-320) and, for an intra-predicted
+// Class of a macroblock (0 other pass-A, 1 zero-vector copy without residual, 4 pass-B: intra-predicted), its deblocking edge flags (GetMbFilteringFlags, deblocking.c:289-320) and, for an intra-predicted
 // macroblock, the neighbours it has to wait for inside the intra pass -- settled right after the record is written, while it
 // is in cache.  Everything it looks at is final at this point: a left / upper neighbour of the same slice has been decoded
 // before this macroblock (curNb_), one that is decoded later belongs to a later slice.  Pictures where that does not hold
 // (a macroblock decoded twice by redundant slices, corrupted slices, concealment) take the full pass of finalizeRecords.
 inline void PictureState::classify(uint32_t a, b200_mb_rec &r) {
-    uint8_t *cls = orderClass.data(), *zr = cls + picSizeInMbs;
+    uint8_t *cls = orderClass.data();
     const uint32_t idc = r.reserved0;
     uint8_t f = r.flags & (uint8_t)(B200_MBF_AVAIL_A | B200_MBF_AVAIL_B | B200_MBF_AVAIL_C | B200_MBF_AVAIL_D);
     if (idc != 1) {
@@ -623,7 +622,7 @@ inline void PictureState::classify(uint32_t a, b200_mb_rec &r) {
         if (curX_ && (idc != 2 || curNb_[0] >= 0)) f |= B200_MBF_FILTER_LEFT;
         if (a >= widthMbs && (idc != 2 || curNb_[1] >= 0)) f |= B200_MBF_FILTER_TOP;
     }
-    uint8_t c = 0, z = 0, w = 0;
+    uint8_t c = 0, w = 0;
     if (r.mbType > B200_MB_P_8x8REF0 && r.mbType != B200_MB_I_PCM) {
         c = 4;
         numIntraPred_++;
@@ -631,14 +630,13 @@ inline void PictureState::classify(uint32_t a, b200_mb_rec &r) {
         if ((f & B200_MBF_AVAIL_B) && cls[a - widthMbs] == 4) w |= B200_MBF_AVAIL_B;
         if ((f & B200_MBF_AVAIL_C) && cls[a - widthMbs + 1] == 4) w |= B200_MBF_AVAIL_C;
         if ((f & B200_MBF_AVAIL_D) && cls[a - widthMbs - 1] == 4) w |= B200_MBF_AVAIL_D;
-    } else if (r.mbType <= B200_MB_P_16x16 && r.codedMask == 0 && ((r.u.mv[0][0] | r.u.mv[0][1]) & 7) == 0) {
+    } else if (r.mbType <= B200_MB_P_16x16 && r.codedMask == 0 && (r.u.mv[0][0] | r.u.mv[0][1]) == 0) {
         c = 1;
-        if ((r.u.mv[0][0] | r.u.mv[0][1]) == 0) z = (uint8_t)(1 + r.refSlot[0]);
+        numCopies_++;
     }
     r.flags = f;
     r.waitMask = w;
     cls[a] = c;
-    zr[a] = z;
 }
 
 // the syntax-level half of h264bsdDecodeMacroblock (h264bsd_macroblock_layer.c:965-1131)
@@ -886,129 +884,75 @@ void PictureState::markSliceCorrupted(uint32_t firstMbInSlice, const Sps &sps) {
 
 void PictureState::finalizeRecords() {
     bindOutput();
-    // Class of every macroblock for the processing order -- 0 other pass-A, 1 plain copy (P_Skip / P_L0_16x16 without residual
-    // whose vector is integer for luma and chroma), 4 pass-B (intra-predicted), 5 spatially concealed; zr = 1 + reference slot
-    // of a zero-vector plain copy -- and its deblocking edge flags (GetMbFilteringFlags, deblocking.c:289-320).  The common
-    // picture had both settled per macroblock by classify().  A picture with macroblocks decoded twice, corrupted slices or
-    // concealment takes the pass over the records below instead (the slice ids are final only now).
+    // Which pass a macroblock belongs to -- 0 / 1 pass A (inter, I_PCM, concealed copy; 1 = a zero-vector copy without residual),
+    // 4 pass B (intra-predicted), 5 spatially concealed -- and its deblocking edge flags (GetMbFilteringFlags,
+    // deblocking.c:289-320) were settled per macroblock by classify().  A picture with macroblocks decoded twice, corrupted
+    // slices or concealment takes the pass over the records below instead (the slice ids are final only now).  The GPU reads the
+    // records in raster order and sorts the macroblocks itself: the only list left is the concealment order.
     std::vector<uint8_t> &cls = orderClass;
     cls.resize(2 * (size_t)picSizeInMbs);
-    uint8_t *zr = cls.data() + picSizeInMbs;
-    order.resize(picSizeInMbs);
-    uint32_t a = 0, nB = lateFixup_ ? 0 : numIntraPred_;
-    if (lateFixup_)
-    for (uint32_t y = 0; y < heightMbs; y++)
-        for (uint32_t x = 0; x < widthMbs; x++, a++) {
-            b200_mb_rec &r = recs[a];
-            const uint32_t idc = r.reserved0;
-            uint8_t f = r.flags & (uint8_t)(B200_MBF_AVAIL_A | B200_MBF_AVAIL_B | B200_MBF_AVAIL_C | B200_MBF_AVAIL_D | B200_MBF_CONCEALED);
-            if (idc != 1) {
-                f |= B200_MBF_FILTER_INNER;
-                if (x && (idc != 2 || aux[a - 1].sliceId == aux[a].sliceId)) f |= B200_MBF_FILTER_LEFT;
-                if (y && (idc != 2 || aux[a - widthMbs].sliceId == aux[a].sliceId)) f |= B200_MBF_FILTER_TOP;
-            }
-            r.flags = f;
-            r.sliceId = aux[a].sliceId;
-            if (st != recs) {
-                // a macroblock decoded again by a redundant slice: the filter sees the state of its LAST decode (st), with the
-                // edge flags that state asks for
-                b200_mb_rec &fr = st[a];
-                const uint32_t idcF = fr.reserved0;
-                uint8_t ff = fr.flags & (uint8_t)(B200_MBF_AVAIL_A | B200_MBF_AVAIL_B | B200_MBF_AVAIL_C | B200_MBF_AVAIL_D | B200_MBF_CONCEALED);
-                if (idcF != 1) {
-                    ff |= B200_MBF_FILTER_INNER;
-                    if (x && (idcF != 2 || aux[a - 1].sliceId == aux[a].sliceId)) ff |= B200_MBF_FILTER_LEFT;
-                    if (y && (idcF != 2 || aux[a - widthMbs].sliceId == aux[a].sliceId)) ff |= B200_MBF_FILTER_TOP;
+    uint32_t nB = numIntraPred_, nCopy = numCopies_;
+    if (lateFixup_) {
+        nB = nCopy = 0;
+        uint32_t a = 0;
+        for (uint32_t y = 0; y < heightMbs; y++)
+            for (uint32_t x = 0; x < widthMbs; x++, a++) {
+                b200_mb_rec &r = recs[a];
+                const uint32_t idc = r.reserved0;
+                uint8_t f = r.flags & (uint8_t)(B200_MBF_AVAIL_A | B200_MBF_AVAIL_B | B200_MBF_AVAIL_C | B200_MBF_AVAIL_D | B200_MBF_CONCEALED);
+                if (idc != 1) {
+                    f |= B200_MBF_FILTER_INNER;
+                    if (x && (idc != 2 || aux[a - 1].sliceId == aux[a].sliceId)) f |= B200_MBF_FILTER_LEFT;
+                    if (y && (idc != 2 || aux[a - widthMbs].sliceId == aux[a].sliceId)) f |= B200_MBF_FILTER_TOP;
                 }
-                fr.flags = ff;
-                fr.sliceId = aux[a].sliceId;
-            }
-            uint8_t c = 0, z = 0;
-            if ((f & B200_MBF_CONCEALED) && r.mbType == B200_MB_I_4x4) {
-                // concealed: a zero-vector copy of the reference picture, or (class 5) spatial -- listed in its own section
-                if (r.waitMask == 0) { c = 1; z = (uint8_t)(1 + r.refSlot[0]); }
-                else c = 5;
+                r.flags = f;
+                r.sliceId = aux[a].sliceId;
+                if (st != recs) {
+                    // a macroblock decoded again by a redundant slice: the filter sees the state of its LAST decode (st), with the
+                    // edge flags that state asks for
+                    b200_mb_rec &fr = st[a];
+                    const uint32_t idcF = fr.reserved0;
+                    uint8_t ff = fr.flags & (uint8_t)(B200_MBF_AVAIL_A | B200_MBF_AVAIL_B | B200_MBF_AVAIL_C | B200_MBF_AVAIL_D | B200_MBF_CONCEALED);
+                    if (idcF != 1) {
+                        ff |= B200_MBF_FILTER_INNER;
+                        if (x && (idcF != 2 || aux[a - 1].sliceId == aux[a].sliceId)) ff |= B200_MBF_FILTER_LEFT;
+                        if (y && (idcF != 2 || aux[a - widthMbs].sliceId == aux[a].sliceId)) ff |= B200_MBF_FILTER_TOP;
+                    }
+                    fr.flags = ff;
+                    fr.sliceId = aux[a].sliceId;
+                }
+                uint8_t c = 0;
+                if ((f & B200_MBF_CONCEALED) && r.mbType == B200_MB_I_4x4) {
+                    // concealed: a zero-vector copy of the reference picture (pass A), or (class 5) spatial: concealKernel
+                    c = r.waitMask == 0 ? 1 : 5;
+                    nCopy += c == 1;
+                    cls[a] = c;
+                    continue;
+                }
+                r.waitMask = 0;
+                if (r.mbType > B200_MB_P_8x8REF0 && r.mbType != B200_MB_I_PCM) { c = 4; nB++; }
+                else if (r.mbType <= B200_MB_P_16x16 && r.codedMask == 0 && (r.u.mv[0][0] | r.u.mv[0][1]) == 0) { c = 1; nCopy++; }
                 cls[a] = c;
-                zr[a] = z;
-                continue;
             }
-            r.waitMask = 0;
-            if (r.mbType > B200_MB_P_8x8REF0 && r.mbType != B200_MB_I_PCM) { c = 4; nB++; }
-            else if (r.mbType <= B200_MB_P_16x16 && r.codedMask == 0 && ((r.u.mv[0][0] | r.u.mv[0][1]) & 7) == 0) {
-                c = 1;
-                if ((r.u.mv[0][0] | r.u.mv[0][1]) == 0) z = (uint8_t)(1 + r.refSlot[0]);
-            }
-            cls[a] = c;
-            zr[a] = z;
-        }
-    // horizontal runs of zero-vector copies from one reference slot (2..32 macroblocks) become one list entry pair: the
-    // copy kernel moves them as whole row segments; class 2 = first of a run, 3 = rest of a run
-    uint32_t n = 0;
-    numRunMbs = 0;
-    for (uint32_t row = 0; row < heightMbs; row++) {
-        const uint8_t *z = zr + (size_t)row * widthMbs;
-        uint8_t *c = cls.data() + (size_t)row * widthMbs;
-        uint32_t x = 0;
-        while (x < widthMbs) {
-            if (!z[x]) { x++; continue; }
-            uint32_t len = 1;
-            while (x + len < widthMbs && len < 32 && z[x + len] == z[x]) len++;
-            if (len >= 2) {
-                c[x] = 2;
-                for (uint32_t i = 1; i < len; i++) c[x + i] = 3;
-                order[n++] = (uint16_t)(row * widthMbs + x);
-                order[n++] = (uint16_t)len;
-                numRunMbs += len;
-            }
-            x += len;
-        }
-    }
-    numRun = n / 2;
-    // one pass sorts the rest into its three sections: single copies go straight into the list, the other pass-A macroblocks
-    // and the intra-predicted ones (with their wavefront key x + 2y) are parked and appended behind
-    std::vector<uint32_t> &park = orderKeys;       // [0, nMbs): other pass-A addresses; [nMbs, 2 nMbs): intra address | key << 16
-    park.resize(2 * (size_t)picSizeInMbs);
-    uint32_t *others = park.data(), *intra = park.data() + picSizeInMbs;
-    uint32_t nOthers = 0, nIntra = 0;
-    a = 0;
-    for (uint32_t y = 0; y < heightMbs; y++)
-        for (uint32_t x = 0; x < widthMbs; x++, a++) {
-            const uint8_t c = cls[a];
-            if (c == 1) order[n++] = (uint16_t)a;
-            else if (c == 0) others[nOthers++] = a;
-            else if (c == 4) intra[nIntra++] = a | ((x + 2 * y) << 16);
-        }
-    numCopy = n - 2 * numRun;
-    for (uint32_t i = 0; i < nOthers; i++) order[n++] = (uint16_t)others[i];
-    const uint32_t listB = n;   // where the pass-B entries start in the list
-    nB = nIntra;
-    numPassB = nB;
-    numPassA = picSizeInMbs - nB - (lateFixup_ ? (uint32_t)concealOrder.size() : 0);
-    if (numPassB) {
-        // bucket by wavefront key (stable in address order inside a key)
-        const uint32_t nKeys = widthMbs + 2 * heightMbs;
-        std::vector<uint32_t> &keys = orderKeyCount;
-        keys.assign(nKeys + 1, 0);
-        for (uint32_t i = 0; i < nIntra; i++) keys[(intra[i] >> 16) + 1]++;
-        for (uint32_t k = 0; k < nKeys; k++) keys[k + 1] += keys[k];
-        for (uint32_t i = 0; i < nIntra; i++) {
-            const uint32_t a2 = intra[i] & 0xFFFFu;
-            order[listB + keys[intra[i] >> 16]++] = (uint16_t)a2;
-            if (!lateFixup_) continue;
-            // the neighbours an intra macroblock has to wait for inside the intra pass: the available ones that are
-            // intra-predicted themselves
-            b200_mb_rec &r = recs[a2];
+        // the neighbours an intra macroblock has to wait for inside the intra pass: the available ones that are intra-predicted
+        // themselves
+        for (a = 0; a < picSizeInMbs; a++) {
+            if (cls[a] != 4) continue;
+            b200_mb_rec &r = recs[a];
             uint8_t w = 0;
-            if ((r.flags & B200_MBF_AVAIL_A) && cls[a2 - 1] == 4) w |= B200_MBF_AVAIL_A;
-            if ((r.flags & B200_MBF_AVAIL_B) && cls[a2 - widthMbs] == 4) w |= B200_MBF_AVAIL_B;
-            if ((r.flags & B200_MBF_AVAIL_C) && cls[a2 - widthMbs + 1] == 4) w |= B200_MBF_AVAIL_C;
-            if ((r.flags & B200_MBF_AVAIL_D) && cls[a2 - widthMbs - 1] == 4) w |= B200_MBF_AVAIL_D;
+            if ((r.flags & B200_MBF_AVAIL_A) && cls[a - 1] == 4) w |= B200_MBF_AVAIL_A;
+            if ((r.flags & B200_MBF_AVAIL_B) && cls[a - widthMbs] == 4) w |= B200_MBF_AVAIL_B;
+            if ((r.flags & B200_MBF_AVAIL_C) && cls[a - widthMbs + 1] == 4) w |= B200_MBF_AVAIL_C;
+            if ((r.flags & B200_MBF_AVAIL_D) && cls[a - widthMbs - 1] == 4) w |= B200_MBF_AVAIL_D;
             r.waitMask = w;
         }
     }
+    numPassB = nB;
+    numCopy = nCopy;
     // spatially concealed macroblocks, in concealment order
     numConceal = lateFixup_ ? (uint32_t)concealOrder.size() : 0;
-    for (uint32_t i = 0; i < numConceal; i++) order[listB + numPassB + i] = concealOrder[i];
+    numPassA = picSizeInMbs - nB - numConceal;
+    order.assign(concealOrder.begin(), concealOrder.begin() + numConceal);
 }
 
 // h264bsdConceal (h264bsd_conceal.c:124-262): records for the macroblocks of the picture that never arrived (or belonged to a

@@ -69,11 +69,10 @@ public:
         int16_t *p_ = nullptr;
         size_t n_ = 0, cap_ = 0;
     } coefs;
-    std::vector<uint16_t> order;    // processing order of the picture being built (see b200_tape.mbOrder)
-    uint32_t numPassA = 0, numPassB = 0, numCopy = 0, numRun = 0, numRunMbs = 0, numConceal = 0;
+    std::vector<uint16_t> order;    // concealment order of the picture being built (see b200_tape.mbOrder)
+    uint32_t numPassA = 0, numPassB = 0, numCopy = 0, numConceal = 0;
     std::vector<uint16_t> concealOrder;   // spatially concealed macroblocks of the picture being built, concealment order
     std::vector<uint8_t> orderClass;   // scratch of finalizeRecords
-    std::vector<uint32_t> orderKeys, orderKeyCount;
     std::vector<uint32_t> sliceGroupMap;
     uint32_t sliceIdCounter = 0, numDecodedMbs = 0, lastMbAddr = 0;
 
@@ -112,6 +111,7 @@ private:
     uint32_t curX_ = 0;                 // its column
     bool lateFixup_ = false;            // this picture needs the full pass of finalizeRecords (see classify)
     uint32_t numIntraPred_ = 0;         // intra-predicted macroblocks classified so far
+    uint32_t numCopies_ = 0;            // zero-vector copies without residual classified so far
     int failedMb_ = -1;                 // macroblock whose derivation failed after it was counted as decoded (decodeSlice)
     uint8_t failedPrevDecoded_ = 0;     // ... and its decode count before that
 

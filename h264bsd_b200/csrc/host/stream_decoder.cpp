@@ -234,8 +234,7 @@ void StreamDecoder::finishPicture() {
     hdr.numPassA = pic_.numPassA;
     hdr.numPassB = pic_.numPassB;
     hdr.numCopy = pic_.numCopy;
-    hdr.numRun = pic_.numRun;
-    hdr.numRunMbs = pic_.numRunMbs;
+    hdr.orderOffset = hdr.reserved7 = 0;     // (the tape builder places the list)
     hdr.numConceal = pic_.numConceal;
 
     int32_t poc = decodePicOrderCnt(poc_, *activeSps_, sliceHeader_, prevNal_);

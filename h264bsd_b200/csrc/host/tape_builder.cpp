@@ -56,25 +56,27 @@ public:
     }
     bool submitPicture(const b200_pic_hdr &hdr, const b200_mb_rec *r, const int16_t *c, const uint16_t *o, const b200_mb_rec *filterRecs) override {
         const size_t nMbs = (size_t)hdr.widthMbs * hdr.heightMbs;
-        const size_t nrec = nMbs * sizeof(b200_mb_rec), ncoef = (size_t)hdr.numCoefBlocks * B200_COEF_BLOCK_BYTES, nord = nMbs * 2;
-        uint64_t orderBytes = (uint64_t)t_->numPics * nMbs * 2;
+        const size_t nrec = nMbs * sizeof(b200_mb_rec), ncoef = (size_t)hdr.numCoefBlocks * B200_COEF_BLOCK_BYTES, nord = (size_t)hdr.numConceal * 2;
+        uint64_t orderBytes = (uint64_t)t_->numOrder * 2;
         uint64_t picBytes = (uint64_t)t_->numPics * sizeof(b200_pic_hdr);
         const bool inPlace = t_->mbRecs && reinterpret_cast<const uint8_t *>(r) == t_->mbRecs + t_->mbRecBytes;
-        if (t_->pinned == 1 && ((!inPlace && t_->mbRecBytes + nrec > t_->capRecs) || t_->coefBytes + ncoef > t_->capCoefs || orderBytes + nord > t_->capOrder)) {
+        if (t_->pinned == 1 && ((!inPlace && t_->mbRecBytes + nrec > t_->capRecs) || t_->coefBytes + ncoef > t_->capCoefs || orderBytes + nord + 2 > t_->capOrder)) {
             h264bsdB200UnpinTape(t_);   // never realloc a page-locked block
             repin = true;
         }
         if ((!inPlace && !ensure(t_->mbRecs, t_->capRecs, t_->mbRecBytes + nrec)) || !ensure(t_->coefs, t_->capCoefs, t_->coefBytes + ncoef) ||
-            !ensure(t_->mbOrder, t_->capOrder, orderBytes + nord) || !ensure(t_->pics, t_->capPics, picBytes + sizeof(b200_pic_hdr))) {
+            !ensure(t_->mbOrder, t_->capOrder, orderBytes + nord + 2) || !ensure(t_->pics, t_->capPics, picBytes + sizeof(b200_pic_hdr))) {
             ok = false;
             return false;
         }
         b200_pic_hdr h = hdr;
         h.mbRecOffset = t_->mbRecBytes;
         h.coefOffset = t_->coefBytes;
+        h.orderOffset = t_->numOrder;
         if (!inPlace) std::memcpy(t_->mbRecs + t_->mbRecBytes, r, nrec);
         std::memcpy(t_->coefs + t_->coefBytes, c, ncoef);
-        std::memcpy((uint8_t *)t_->mbOrder + orderBytes, o, nord);
+        if (nord) std::memcpy((uint8_t *)t_->mbOrder + orderBytes, o, nord);
+        t_->numOrder += hdr.numConceal;
         t_->mbRecBytes += nrec;
         if (filterRecs) {
             // the records the in-loop filter reads instead (rare: redundant slices decoded macroblocks a second time): right
@@ -119,7 +121,7 @@ static b200_tape *reparseStream(b200_tape *t, const uint8_t *stream, size_t len,
     t->cropFlag = t->cropLeft = t->cropWidth = t->cropTop = t->cropHeight = 0;
     t->videoRange = 0; t->matrixCoefficients = 2;
     t->mbRecBytes = t->coefBytes = 0;
-    t->numOutputs = 0; t->status = 0;
+    t->numOutputs = 0; t->status = 0; t->numOrder = 0;
     const uint64_t cap0[3] = {t->capRecs, t->capCoefs, t->capOrder};
 
     // bit 0 of the flags: no output reordering (h264bsdInit); bit 1: carry on after H264BSD_ERROR the way a player does (the

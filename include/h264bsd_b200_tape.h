@@ -5,7 +5,7 @@
  * Where the reference hands one parsed macroblock at a time straight to its pixel code
  * (h264bsd_slice_data.c:185 -> h264bsdDecodeMacroblock, h264bsd_macroblock_layer.c:965) and
  * one finished picture to the in-loop filter (h264bsd_decoder.c:475 -> h264bsdFilterPicture),
- * this engine RECORDS, per picture, one fixed-size record per macroblock plus a pool of
+ * this engine RECORDS, per picture, one fixed-size record per macroblock (raster order) plus a pool of
  * packed int16 coefficient blocks, and the GPU REPLAYS whole pictures (of many streams).
  *
  * Everything syntax-level is finished on the host before a record is written: QP update
@@ -56,11 +56,11 @@ enum {
  * slices) the host writes their records the way h264bsdConceal leaves the reference's state: mbType = B200_MB_I_4x4,
  * qpY = 40, filter offsets and chromaQpIndexOffset 0, filtering enabled (ConcealMb :296-306) -- that is what the in-loop
  * filter sees.  How the pels are made:
- *   copy     (P slice and a reference picture exists, :320-341): waitMask == 0, refSlot[] = that picture, u = 0; the record is
- *            listed with the plain copies (zero vector), so reconstruction moves the co-located macroblock;
+ *   copy     (P slice and a reference picture exists, :320-341): waitMask == 0, refSlot[] = that picture, u = 0: pass A moves
+ *            the co-located macroblock like any zero-vector copy;
  *   spatial  (otherwise, :346-600): waitMask = B200_CN_* bits of the neighbouring macroblocks whose edge pels enter the
  *            estimate (decoded or concealed earlier), coefIndex = position in the concealment order; the record is listed in
- *            the fifth section of the processing order, in that order (every entry may read what the previous ones wrote).
+ *            b200_tape.mbOrder, in that order (every entry may read what the previous ones wrote).
  * A picture of which nothing arrived is copied from the reference / set to 128 with the filter off (:172-201): ordinary
  * P_Skip / I_PCM records with disable_deblocking_filter_idc = 1.
  */
@@ -77,8 +77,7 @@ enum {
 #define B200_COEF_BLOCK_BYTES 32 /* 16 x int16, zig-zag order exactly as parsed */
 
 /*
- * One macroblock.  96 bytes (three 32-byte sectors), plus 2 bytes in the per-picture order list: D = 98 bytes
- * of work-list per macroblock enter the roofline accounting.
+ * One macroblock.  96 bytes (three 32-byte sectors): D = 96 bytes of work-list per macroblock enter the roofline accounting.
  *
  * coefficient pool layout for this MB, starting at 32-byte block index `coefIndex`
  * (relative to the picture's pool):
@@ -137,12 +136,11 @@ typedef struct b200_pic_hdr {
     uint32_t picId;        /* application picId (h264bsdDecode argument) */
     uint32_t numPassA;     /* macroblocks reconstructed without looking at the current picture: inter + I_PCM (+ concealed copies) */
     uint32_t numPassB;     /* intra-predicted macroblocks (read unfiltered neighbours of the current picture) */
-    uint32_t numCopy;      /* plain copies listed one by one: one 16x16 partition, no residual, motion vector a multiple of
-                              8 quarter-pels in both components (integer for luma AND chroma) */
-    uint32_t numRun;       /* horizontal runs of 2..32 plain copies with a zero vector and the same reference slot: two list
-                              entries (address of the first macroblock, length) per run */
-    uint32_t numRunMbs;    /* macroblocks covered by the runs */
-    uint32_t numConceal;   /* spatially concealed macroblocks: fifth section of the order list, concealment order */
+    uint32_t numCopy;      /* of numPassA: one 16x16 partition, no residual, zero vector (and concealed copies) -- a plain copy of the
+                              co-located macroblock of the reference frame (statistic; the GPU finds them itself) */
+    uint32_t orderOffset;  /* where this picture's concealment order starts inside the tape's mbOrder (entries) */
+    uint32_t reserved7;
+    uint32_t numConceal;   /* spatially concealed macroblocks: the picture's entries in mbOrder, concealment order */
     uint32_t reserved5;
     uint64_t filterRecOffset; /* 0: the in-loop filter reads the records at mbRecOffset.  Else byte offset of a second record
                               array for the filter alone: a picture in which redundant slices decoded macroblocks a second
@@ -168,15 +166,15 @@ typedef struct b200_tape {
     b200_pic_hdr *pics;  /* numPics */
     uint8_t *mbRecs;     /* mbRecBytes */
     uint8_t *coefs;      /* coefBytes  */
-    /* processing order, widthMbs*heightMbs uint16 macroblock addresses per picture (picture p at p*nMbs):
-     * numRun zero-motion runs (two entries each: first address, length), numCopy single plain copies, the other
-     * numPassA - numRunMbs - numCopy inter / I_PCM macroblocks (all three in raster order), then numPassB entries in
-     * wavefront order (x + 2y ascending), so that every macroblock an intra MB depends on precedes it, then numConceal
-     * spatially concealed macroblocks in concealment order.  The list of a picture never has more than
-     * widthMbs*heightMbs entries. */
+    /* concealment order: the numConceal spatially concealed macroblocks of a picture (addresses) at pics[p].orderOffset, numOrder
+     * entries in all; every entry may read
+     * what the previous ones wrote.  Everything else the GPU sorts itself from the records, which lie in raster order: pass A takes
+     * the inter / I_PCM / concealed-copy macroblocks in the order they lie in memory, pass B and the in-loop filter walk macroblock
+     * rows (round 1 shipped four more sections here: zero-motion runs, single copies, other pass-A macroblocks, intra macroblocks in
+     * wavefront order). */
     uint16_t *mbOrder;
     uint32_t numOutputs;        /* pictures in output order, incl. those drained by the final flush */
-    uint32_t reserved2;
+    uint32_t numOrder;          /* entries in mbOrder */
     uint32_t *outputPicIndex;   /* numOutputs decode-order indices */
     uint32_t status;            /* 0 ok, else the H264BSD_* code the parse stopped on, or B200_TAPE_SIZE_CHANGE */
     uint32_t pinned;            /* 0 pageable, 1 arrays page-locked (h264bsdB200PinTape), 2 page-lock stale after growth */

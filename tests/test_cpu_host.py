@@ -293,51 +293,34 @@ def test_reparse_many_matches_single_parse():
 
 
 @pytest.mark.parametrize("name", ["test_640x360.h264", "test_1920x1080.h264"])
-def test_processing_order_lists(name):
-    """the per-picture list: runs (address, length) | single plain copies | other pass-A macroblocks | pass-B macroblocks in
-    wavefront order -- every macroblock exactly once, every section what its name says (picture.cpp finalizeRecords)"""
+def test_picture_headers_count_the_passes(name):
+    """the records lie in raster order and the GPU sorts them itself (pass A: inter / I_PCM, pass B: intra-predicted); the
+    picture header's counts say what it will find, and an intra macroblock only waits for neighbours that are intra-predicted
+    themselves"""
     ps = ParsedStream(_oracle.stream_bytes(name))
     t = ps.ptr.contents
     nmb = ps.width_mbs * ps.height_mbs
     W = ps.width_mbs
     recs = np.ctypeslib.as_array(C.cast(t.mbRecs, C.POINTER(C.c_uint8)), shape=(ps.num_pics * nmb, 96))
-    order = np.ctypeslib.as_array(t.mbOrder, shape=(ps.num_pics * nmb,))
+    assert t.numOrder == 0 and all(h.numConceal == 0 for h in ps.pics), "nothing is concealed in a valid stream"
     for k, h in enumerate(ps.pics):
         r = recs[k * nmb:(k + 1) * nmb]
-        o = order[k * nmb:(k + 1) * nmb].astype(np.int64)
         types = r[:, 0]
         mask = np.ascontiguousarray(r[:, 4:8]).view("<u4")[:, 0]
         mv0 = np.ascontiguousarray(r[:, 32:36]).view("<i2")
-        ref0 = r[:, 16]
         intra = (types > 5) & (types != 31)
-        plain = (types <= 1) & (mask == 0) & (((mv0[:, 0] | mv0[:, 1]) & 7) == 0)
-        seen = np.zeros(nmb, np.int32)
-        pos = 0
-        run_mbs = 0
-        for _ in range(h.numRun):
-            a, ln = int(o[pos]), int(o[pos + 1]); pos += 2
-            assert 2 <= ln <= 32 and a // W == (a + ln - 1) // W, "a run stays inside one macroblock row"
-            sl = slice(a, a + ln)
-            assert plain[sl].all() and (mv0[sl] == 0).all() and (ref0[sl] == ref0[a]).all()
-            seen[sl] += 1
-            run_mbs += ln
-        assert run_mbs == h.numRunMbs
-        singles = o[pos:pos + h.numCopy]; pos += h.numCopy
-        assert plain[singles].all()
-        seen[singles] += 1
-        n_other = h.numPassA - h.numRunMbs - h.numCopy
-        others = o[pos:pos + n_other]; pos += n_other
-        assert (~intra[others]).all() and (np.diff(others) > 0).all()
-        seen[others] += 1
-        wave = o[pos:pos + h.numPassB]; pos += h.numPassB
-        assert intra[wave].all()
-        key = wave % W + 2 * (wave // W)
-        assert (np.diff(key) >= 0).all(), "pass B is in wavefront order"
-        seen[wave] += 1
-        assert (seen == 1).all() and pos <= nmb and h.numPassA + h.numPassB == nmb
-        # an intra macroblock only waits for neighbours that are intra-predicted themselves
+        copy = (types <= 1) & (mask == 0) & (mv0[:, 0] == 0) & (mv0[:, 1] == 0)
+        assert h.numPassB == int(intra.sum()) and h.numPassA == nmb - h.numPassB and h.numCopy == int(copy.sum())
         wm = r[:, 28]
         assert (wm[~intra] == 0).all()
+        g = intra.reshape(-1, W)
+        left = np.pad(g, ((0, 0), (1, 0)))[:, :-1]
+        up = np.pad(g, ((1, 0), (0, 0)))[:-1]
+        upright = np.pad(g, ((1, 0), (0, 1)))[:-1, 1:]
+        upleft = np.pad(g, ((1, 0), (1, 0)))[:-1, :-1]
+        flags = r[:, 3].reshape(-1, W)
+        want = ((flags & 1) * left) | (((flags >> 1) & 1) * up << 1) | (((flags >> 2) & 1) * upright << 2) | (((flags >> 3) & 1) * upleft << 3)
+        assert (wm.reshape(-1, W)[g] == want[g]).all()
     ps.close()
 
 
@@ -365,7 +348,7 @@ def test_tape_reuse_across_different_streams():
         t = ps.ptr.contents
         return (ps.status, ps.num_pics, ps.width_mbs, ps.height_mbs, ps.num_slots, tuple(ps.outputs),
                 hashlib.md5(C.string_at(t.mbRecs, t.mbRecBytes)).hexdigest(), hashlib.md5(C.string_at(t.coefs, t.coefBytes)).hexdigest(),
-                hashlib.md5(C.string_at(t.mbOrder, ps.num_pics * ps.mbs_per_pic * 2)).hexdigest())
+                hashlib.md5(C.string_at(t.mbOrder, t.numOrder * 2)).hexdigest() if t.numOrder else None)
 
     reused = ParsedStream(synth_h264.make_stream(0))
     for seed in range(1, 60):
