@@ -109,7 +109,7 @@ class ClockSampler(threading.Thread):
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu")
         while not self.stop_flag.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
@@ -131,6 +131,11 @@ class ClockSampler(threading.Thread):
                     reasons.add(n)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+    def gpu_busy(self):
+        """mean of nvidia-smi's utilization.gpu over the samples (percent of time a kernel was running)"""
+        u = [float(s[7]) for s in self.samples if len(s) > 7 and s[7].replace(".", "").isdigit()]
+        return sum(u) / len(u) if u else None
 
 
 def kernel_source_sha16():
@@ -432,6 +437,8 @@ def main():
         tc = time.time()
         tok = batches[0].parse_upload_begin(pool, bufs)
         batches[0].parse_upload_wait(tok)
+        busy = ClockSampler(local)
+        busy.start()
         h2d0, d2h0 = sum(x.h2d_bytes() for x in batches), sum(x.d2h_bytes() for x in batches)
         t0 = time.time()
         for i in range(reps):
@@ -448,6 +455,7 @@ def main():
             phase["gpu_and_d2h_wait"] += te - tg
             phase["parse_upload_wait"] += tw - te
         t1 = time.time()
+        busy.stop_flag.set()
         dt = (t1 - t0) / reps
         dt_cold = (t1 - tc) / reps             # the same passes with the priming parse counted in
         h2d = (sum(x.h2d_bytes() for x in batches) - h2d0) // reps
@@ -463,7 +471,7 @@ def main():
         e2e = {"value": world * ne * ps.num_pics * nmb / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world,
                "d2h_bytes_per_step": int(d2h) * world, "streams_per_gpu": ne, "host_threads_per_gpu": threads, "host_cpus": cpu_note,
                "bit_exact": bool(ok2), "passes": reps, "seconds_per_pass": dt,
-               "cold_start_value": world * ne * ps.num_pics * nmb / dt_cold,
+               "cold_start_value": world * ne * ps.num_pics * nmb / dt_cold, "gpu_busy_pct": busy.gpu_busy(),
                "phase_seconds_per_pass": {k_: round(v_ / reps, 4) for k_, v_ in phase.items()},
                "note": "host bitstream bytes -> host I420 frames through the C-ABI: every host thread parses a stream into its page-locked tape and "
                        "uploads the work-list; the GPU replays a pass while the host parses the next one into a second batch; every output "

@@ -63,6 +63,8 @@ struct LegacyDecoder : public PictureSink {
     bool submitPicture(const b200_pic_hdr &hdr, const b200_mb_rec *recs, const int16_t *coefs, const uint16_t *order,
                        const b200_mb_rec *filterRecs) override {
         if (!batch.submitHostPicture(0, hdr, recs, coefs, order, filterRecs)) { failed = true; return false; }
+        // the picture's way to the host starts now, behind its kernels; h264bsdNextOutputPicture only waits for it
+        if (hdr.curSlot < hostFrames.size() && !batch.mirrorFrameAsync(hdr.curSlot, hostFrames[hdr.curSlot])) { failed = true; return false; }
         return true;
     }
 };
@@ -123,7 +125,7 @@ u8 *h264bsdNextOutputPicture(storage_t *pStorage, u32 *picId, u32 *isIdrPic, u32
     if (isIdrPic) *isIdrPic = o->isIdr;
     if (numErrMbs) *numErrMbs = o->numErrMbs;
     if ((size_t)o->slot >= d->hostFrames.size()) return nullptr;
-    if (!d->batch.readFrame(0, (uint32_t)o->slot, d->hostFrames[o->slot])) return nullptr;
+    if (!d->batch.waitMirror((uint32_t)o->slot)) return nullptr;
     return d->hostFrames[o->slot];
 }
 

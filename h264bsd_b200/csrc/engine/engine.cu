@@ -58,7 +58,8 @@ void Batch::destroy() {
         if (t.owned) { cudaFree(t.recs); cudaFree(t.coefs); cudaFree(t.order); }
     }
     cudaFree(dBsWords_); cudaFree(dWork_); cudaFree(dPack_[0]); cudaFree(dPack_[1]);
-    cudaFree(dConvertAll_); cudaFree(dFrameStage_);
+    cudaFree(dConvertAll_); cudaFree(dFrameStage_); cudaFree(dMirror_);
+    for (cudaEvent_t e : mirrorEv_) if (e) cudaEventDestroy(e);
     cudaFree(pool_); cudaFree(dOrder_); cudaFree(dDoneRecon_); cudaFree(dDoneDeblock_); cudaFree(dCounters_);
     cudaFree(dJobs_); cudaFree(dStage_[0]); cudaFree(dStage_[1]); cudaFree(dConvert_); cudaFree(dSlots_);
     if (hStage_[0]) cudaFreeHost(hStage_[0]);
@@ -84,6 +85,7 @@ void Batch::resetState() {
     fences_.clear(); fenceFree_.clear(); auxStream_ = nullptr; tapes_.clear(); dJobs_ = nullptr; jobsFilterAt_ = 0; numPics_ = 0;
     jobsDirty_ = true; hStage_[0] = hStage_[1] = nullptr; dStage_[0] = dStage_[1] = nullptr; stageCap_[0] = stageCap_[1] = 0;
     stageEv_[0] = stageEv_[1] = nullptr; stageIdx_ = 0; dConvert_ = nullptr; convertCap_ = 0; dFrameStage_ = nullptr; frameStageCap_ = 0;
+    dMirror_ = nullptr; mirrorEv_.clear(); mirrorBusy_.clear();
     launches_ = 0; d2hBytes_ = 0; h2dBytes_ = 0; timing_ = false; evPool_.clear(); evUsed_ = 0; evStage_.clear();
     dPack_[0] = dPack_[1] = nullptr; packEv_[0] = packEv_[1] = nullptr; packedEv_[0] = packedEv_[1] = nullptr; copyStream_ = nullptr;
     packUsed_[0] = packUsed_[1] = false; packIdx_ = 0; picMaxB_.clear(); picMaxE_.clear();
@@ -627,6 +629,38 @@ bool Batch::readFrame(uint32_t stream, uint32_t slot, uint8_t *dst) {
     CK(cudaMemcpyAsync(dst, dFrameStage_, fb, cudaMemcpyDeviceToHost, stream_));
     CK(cudaStreamSynchronize(stream_));
     d2hBytes_ += fb;
+    return true;
+}
+
+bool Batch::mirrorFrameAsync(uint32_t slot, uint8_t *dst) {
+    if (!created_ || g_.nStreams != 1 || slot >= (uint32_t)g_.numSlots || !dst) return false;
+    CK(cudaSetDevice(device_));
+    const size_t fb = frameBytes();
+    if (!dMirror_) {
+        CK(cudaMalloc(&dMirror_, fb * g_.numSlots));
+        mirrorEv_.assign(g_.numSlots, nullptr);
+        mirrorBusy_.assign(g_.numSlots, 0);
+        for (auto &e : mirrorEv_) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        if (!copyStream_) CK(cudaStreamCreateWithFlags(&copyStream_, cudaStreamNonBlocking));
+        if (!packedEv_[0]) CK(cudaEventCreateWithFlags(&packedEv_[0], cudaEventDisableTiming));
+    }
+    // (the slot's previous copy has been waited for by the caller or is overwritten in stream order: the staging is per slot and
+    // a slot is decoded into again only after its picture has left the DPB)
+    if (mirrorBusy_[slot]) CK(cudaStreamWaitEvent(stream_, mirrorEv_[slot], 0));
+    launchPack(stream_, nullptr, slot, 0, 1, dMirror_ + fb * slot, fb, 0, 0, g_.W, g_.H, 0);
+    CK(cudaEventRecord(packedEv_[0], stream_));
+    CK(cudaStreamWaitEvent(copyStream_, packedEv_[0], 0));
+    CK(cudaMemcpyAsync(dst, dMirror_ + fb * slot, fb, cudaMemcpyDeviceToHost, copyStream_));   // next to the following picture's kernels
+    CK(cudaEventRecord(mirrorEv_[slot], copyStream_));
+    mirrorBusy_[slot] = 1;
+    d2hBytes_ += fb;
+    return true;
+}
+
+bool Batch::waitMirror(uint32_t slot) {
+    if (!created_ || slot >= mirrorEv_.size() || !mirrorBusy_[slot]) return false;
+    CK(cudaSetDevice(device_));
+    CK(cudaEventSynchronize(mirrorEv_[slot]));
     return true;
 }
 

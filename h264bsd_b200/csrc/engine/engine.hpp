@@ -44,6 +44,10 @@ public:
     bool submitHostPicture(uint32_t stream, const b200_pic_hdr &hdr, const b200_mb_rec *recs, const int16_t *coefs, const uint16_t *order,
                            const b200_mb_rec *filterRecs = nullptr);
     bool readFrame(uint32_t stream, uint32_t slot, uint8_t *dst);
+    // one-stream batches (the legacy API): start the de-stripped copy of frame `slot` into page-locked `dst` behind the work queued
+    // so far and return at once; waitMirror(slot) blocks until that copy has landed
+    bool mirrorFrameAsync(uint32_t slot, uint8_t *dst);
+    bool waitMirror(uint32_t slot);
     // picture k's frame of EVERY stream -> dst + s * strideBytes (asynchronous; dst should be pinned; sync() to wait)
     bool readPictureAll(uint32_t k, uint8_t *dst, size_t strideBytes);
     bool writeFrame(uint32_t stream, uint32_t slot, const uint8_t *src);
@@ -117,6 +121,9 @@ private:
     uint32_t *dConvert_ = nullptr;
     size_t convertCap_ = 0;
     uint8_t *dFrameStage_ = nullptr;    // one picture, planar: readFrame / writeFrame
+    uint8_t *dMirror_ = nullptr;        // numSlots pictures, planar: mirrorFrameAsync
+    std::vector<cudaEvent_t> mirrorEv_; // per slot: its copy to the host has landed
+    std::vector<char> mirrorBusy_;
     size_t frameStageCap_ = 0;
     uint64_t launches_ = 0, d2hBytes_ = 0;
     std::atomic<uint64_t> h2dBytes_{0};
