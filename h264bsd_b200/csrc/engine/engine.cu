@@ -86,7 +86,7 @@ void Batch::resetState() {
     jobsDirty_ = true; hStage_[0] = hStage_[1] = nullptr; dStage_[0] = dStage_[1] = nullptr; stageCap_[0] = stageCap_[1] = 0;
     stageEv_[0] = stageEv_[1] = nullptr; stageIdx_ = 0; dConvert_ = nullptr; convertCap_ = 0; dFrameStage_ = nullptr; frameStageCap_ = 0;
     dMirror_ = nullptr; mirrorEv_.clear(); mirrorBusy_.clear();
-    launches_ = 0; d2hBytes_ = 0; h2dBytes_ = 0; timing_ = false; evPool_.clear(); evUsed_ = 0; evStage_.clear();
+    launches_ = 0; d2hBytes_ = 0; h2dBytes_ = 0; timing_ = false; evPool_.clear(); evUsed_ = 0; evStage_.clear(); picMaxA_.clear();
     dPack_[0] = dPack_[1] = nullptr; packEv_[0] = packEv_[1] = nullptr; packedEv_[0] = packedEv_[1] = nullptr; copyStream_ = nullptr;
     packUsed_[0] = packUsed_[1] = false; packIdx_ = 0; picMaxB_.clear(); picMaxE_.clear();
 }
@@ -328,6 +328,7 @@ bool Batch::buildJobs() {
     numPics_ = np;
     picMaxB_.assign(np, 0);
     picMaxE_.assign(np, 0);
+    picMaxA_.assign(np, 0);
     jobsFilterAt_ = (size_t)np * g_.nStreams;
     std::vector<StreamJob> jobs(2 * jobsFilterAt_);
     for (uint32_t k = 0; k < np; k++)
@@ -343,6 +344,7 @@ bool Batch::buildJobs() {
             j.pad = 0;
             picMaxE_[k] = std::max<uint32_t>(picMaxE_[k], j.nE);
             picMaxB_[k] = std::max<uint32_t>(picMaxB_[k], j.nB);
+            picMaxA_[k] = std::max<uint32_t>(picMaxA_[k], t.pics[k].numPassA);
             // what the filter kernels get: the same job, with the picture's filter records where it has any
             StreamJob &jf = jobs[jobsFilterAt_ + (size_t)k * g_.nStreams + s];
             jf = j;
@@ -395,7 +397,7 @@ bool Batch::kernelTimes(float ms[6], uint32_t *launchesPerStage) {
     return true;
 }
 
-bool Batch::launchPicture(const StreamJob *dJobs, const StreamJob *dJobsFilter, uint32_t maxB, uint32_t maxE, bool recon, bool deblock) {
+bool Batch::launchPicture(const StreamJob *dJobs, const StreamJob *dJobsFilter, uint32_t maxA, uint32_t maxB, uint32_t maxE, bool recon, bool deblock) {
     serial_++;
     auto mark = [&](int stageEnded) {
         if (!timing_) return;
@@ -437,7 +439,7 @@ bool Batch::launchPicture(const StreamJob *dJobs, const StreamJob *dJobsFilter, 
         CK(cudaEventRecord(joinEv_, auxStream_));
     }
     if (recon) {
-        {
+        if (maxA) {     // (an IDR picture has nothing for pass A)
             const uint32_t ctas = (rp.totalChunks + kPassAWarps - 1) / kPassAWarps;
             const PassAMaps &maps = *reinterpret_cast<const PassAMaps *>(maps_);
             passAKernelT<false><<<std::min<uint32_t>(ctas, (uint32_t)passABlocks_), kPassAWarps * 32, sizeof(PassAWarpSmem) * kPassAWarps, stream_>>>(rp, maps);
@@ -497,7 +499,7 @@ bool Batch::decodePicture(uint32_t k) {
         fences_.pop_front();
         if (covers) break;
     }
-    return launchPicture(dJobs_ + (size_t)k * g_.nStreams, dJobs_ + jobsFilterAt_ + (size_t)k * g_.nStreams, picMaxB_[k], picMaxE_[k], true, true);
+    return launchPicture(dJobs_ + (size_t)k * g_.nStreams, dJobs_ + jobsFilterAt_ + (size_t)k * g_.nStreams, picMaxA_[k], picMaxB_[k], picMaxE_[k], true, true);
 }
 
 bool Batch::debugStage(uint32_t k, bool recon, bool deblock) {
@@ -505,7 +507,7 @@ bool Batch::debugStage(uint32_t k, bool recon, bool deblock) {
     CK(cudaSetDevice(device_));
     if (jobsDirty_ && !buildJobs()) return false;
     if (k >= numPics_) return false;
-    return launchPicture(dJobs_ + (size_t)k * g_.nStreams, dJobs_ + jobsFilterAt_ + (size_t)k * g_.nStreams, picMaxB_[k], picMaxE_[k], recon, deblock);
+    return launchPicture(dJobs_ + (size_t)k * g_.nStreams, dJobs_ + jobsFilterAt_ + (size_t)k * g_.nStreams, picMaxA_[k], picMaxB_[k], picMaxE_[k], recon, deblock);
 }
 
 bool Batch::run(uint32_t first, uint32_t count) {
@@ -592,7 +594,7 @@ bool Batch::submitHostPicture(uint32_t stream, const b200_pic_hdr &hdr, const b2
     if (coefBytes) std::memcpy(h + coefOff, coefs, coefBytes);
     CK(cudaMemcpyAsync(dStage_[b], h, end, cudaMemcpyHostToDevice, stream_));
     h2dBytes_ += end;
-    if (!launchPicture(reinterpret_cast<const StreamJob *>(dStage_[b]), reinterpret_cast<const StreamJob *>(dStage_[b] + 64), hdr.numPassB, hdr.numConceal, true, true)) return false;
+    if (!launchPicture(reinterpret_cast<const StreamJob *>(dStage_[b]), reinterpret_cast<const StreamJob *>(dStage_[b] + 64), hdr.numPassA, hdr.numPassB, hdr.numConceal, true, true)) return false;
     CK(cudaEventRecord(stageEv_[b], stream_));
     return true;
 }

@@ -80,11 +80,11 @@ private:
         std::vector<b200_pic_hdr> pics;
     };
     bool buildJobs();
-    bool launchPicture(const StreamJob *dJobs, const StreamJob *dJobsFilter, uint32_t maxB, uint32_t maxE, bool recon, bool deblock);
+    bool launchPicture(const StreamJob *dJobs, const StreamJob *dJobsFilter, uint32_t maxA, uint32_t maxB, uint32_t maxE, bool recon, bool deblock);
     bool ensureFrameStage(size_t bytes);
     void launchPack(cudaStream_t st, const StreamJob *jobs, uint32_t slot, uint32_t firstStream, uint32_t nStreams, uint8_t *out, size_t outStride,
                     int cropX, int cropY, int cropW, int cropH, int nv12);
-    std::vector<uint32_t> picMaxB_, picMaxE_;
+    std::vector<uint32_t> picMaxA_, picMaxB_, picMaxE_;
 
     bool created_ = false;
     int device_ = 0, numSms_ = 0;

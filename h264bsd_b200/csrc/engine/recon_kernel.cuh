@@ -875,15 +875,17 @@ __global__ void __launch_bounds__(kReconWarps * 32, 5) reconIntraKernel(const Re
     // bytes 4 lane.. of the 128
     const int r8 = lane >> 1, c8 = (lane & 1) * 8;
     const int cr = lane >> 2, cp = (lane >> 1) & 1, cc = (lane & 1) * 4;
+    // tickets in order, taken when a warp is ready for the row (a ticket taken ahead of time would let later rows start -- and
+    // spin -- before this one; measured)
     for (;;) {
-    uint32_t ticket = 0;
-    if (lane == 0) ticket = atomicAdd(p.ticket, 1u);
-    ticket = __shfl_sync(0xffffffffu, ticket, 0);
-    if (ticket >= totalRows) break;
-    const int mby = (int)(ticket / (uint32_t)g.nStreams);
-    const uint32_t s = ticket - (uint32_t)mby * (uint32_t)g.nStreams;
+    uint32_t thisTicket = 0;
+    if (lane == 0) thisTicket = atomicAdd(p.ticket, 1u);
+    thisTicket = __shfl_sync(0xffffffffu, thisTicket, 0);
+    if (thisTicket >= totalRows) break;
+    const int mby = (int)(thisTicket / (uint32_t)g.nStreams);
+    const uint32_t s = thisTicket - (uint32_t)mby * (uint32_t)g.nStreams;
     const StreamJob job = p.jobs[s];
-    if (!job.nB) continue;
+    if (job.nB) {
     uint32_t *rowMine = p.done + (size_t)s * g.heightMbs + mby;
     uint8_t *cur = framePtr(p.pool, g, s * (uint32_t)g.numSlots + job.curSlot);
     const b200_mb_rec *recsRow = job.recs + (size_t)mby * W;
@@ -1085,6 +1087,7 @@ __global__ void __launch_bounds__(kReconWarps * 32, 5) reconIntraKernel(const Re
     }
     if (any && lane == 0 && x0 + 32 >= W) stRelease(rowMine, (serial16 << 16) | (uint32_t)W);   // (a row that ends without one)
     }  // stretch of 32 macroblocks
+    }  // a stream with intra-predicted macroblocks in this picture
     }  // row tickets
 }
 
