@@ -60,7 +60,7 @@ void Batch::destroy() {
     cudaFree(dBsWords_); cudaFree(dWork_); cudaFree(dPack_[0]); cudaFree(dPack_[1]);
     cudaFree(dConvertAll_); cudaFree(dFrameStage_); cudaFree(dMirror_);
     for (cudaEvent_t e : mirrorEv_) if (e) cudaEventDestroy(e);
-    cudaFree(pool_); cudaFree(dOrder_); cudaFree(dDoneRecon_); cudaFree(dDoneDeblock_); cudaFree(dCounters_);
+    cudaFree(pool_); cudaFree(dDoneRecon_); cudaFree(dDoneDeblock_); cudaFree(dCounters_);
     cudaFree(dJobs_); cudaFree(dStage_[0]); cudaFree(dStage_[1]); cudaFree(dConvert_); cudaFree(dSlots_);
     if (hStage_[0]) cudaFreeHost(hStage_[0]);
     if (hStage_[1]) cudaFreeHost(hStage_[1]);
@@ -79,9 +79,9 @@ void Batch::destroy() {
 
 void Batch::resetState() {
     created_ = false; device_ = 0; numSms_ = 0; stream_ = nullptr; evA_ = evB_ = nullptr; g_ = PoolGeom{}; pool_ = nullptr;
-    dOrder_ = nullptr; dDoneRecon_ = dDoneDeblock_ = dCounters_ = dSlots_ = dBsWords_ = nullptr; dWork_ = nullptr;
+    dDoneRecon_ = dDoneDeblock_ = dCounters_ = dSlots_ = dBsWords_ = nullptr; dWork_ = nullptr;
     strengthBlocks_ = 0; serial_ = 0; passABlocks_ = deblockBlocks_ = intraBlocks_ = 0; chunkRows_ = 32; chunksPerCol_ = 1;
-    syncEv_ = forkEv_ = joinEv_ = nullptr; jobsCap_ = 0; dConvertAll_ = nullptr; chunkB_ = 1; uploadStream_ = nullptr;
+    syncEv_ = forkEv_ = joinEv_ = nullptr; jobsCap_ = 0; dConvertAll_ = nullptr; uploadStream_ = nullptr;
     fences_.clear(); fenceFree_.clear(); auxStream_ = nullptr; tapes_.clear(); dJobs_ = nullptr; jobsFilterAt_ = 0; numPics_ = 0;
     jobsDirty_ = true; hStage_[0] = hStage_[1] = nullptr; dStage_[0] = dStage_[1] = nullptr; stageCap_[0] = stageCap_[1] = 0;
     stageEv_[0] = stageEv_[1] = nullptr; stageIdx_ = 0; dConvert_ = nullptr; convertCap_ = 0; dFrameStage_ = nullptr; frameStageCap_ = 0;
@@ -133,22 +133,13 @@ bool Batch::create(int device, uint32_t nStreams, uint32_t widthMbs, uint32_t he
     CK(cudaMalloc(&pool_, nFrames * g.frameStride));
     CK(cudaMemsetAsync(pool_, 128, nFrames * g.frameStride, stream_));
 
-    // wavefront order: x + 2y ascending (every dependency of a macroblock has a smaller key)
-    std::vector<uint16_t> order(g.nMbs);
-    {
-        std::vector<std::pair<uint32_t, uint32_t>> keyed(g.nMbs);
-        for (int mb = 0; mb < g.nMbs; mb++) keyed[mb] = {(uint32_t)(mb % g.widthMbs + 2 * (mb / g.widthMbs)), (uint32_t)mb};
-        std::sort(keyed.begin(), keyed.end());
-        for (int i = 0; i < g.nMbs; i++) order[i] = (uint16_t)keyed[i].second;
-    }
-    CK(cudaMalloc(&dOrder_, sizeof(uint16_t) * g.nMbs));
-    CK(cudaMemcpyAsync(dOrder_, order.data(), sizeof(uint16_t) * g.nMbs, cudaMemcpyHostToDevice, stream_));
-    const size_t flagBytes = sizeof(uint32_t) * (size_t)nStreams * g.nMbs;
-    CK(cudaMalloc(&dDoneRecon_, flagBytes));
-    CK(cudaMalloc(&dDoneDeblock_, flagBytes));
-    CK(cudaMemsetAsync(dDoneRecon_, 0, flagBytes, stream_));
-    CK(cudaMemsetAsync(dDoneDeblock_, 0, flagBytes, stream_));
-    CK(cudaMalloc(&dBsWords_, flagBytes * 4));
+    // row-progress words of the intra pass and of the filter (serial << 16 | macroblocks finished), boundary strengths
+    const size_t rowBytes = sizeof(uint32_t) * (size_t)nStreams * g.heightMbs;
+    CK(cudaMalloc(&dDoneRecon_, rowBytes));
+    CK(cudaMalloc(&dDoneDeblock_, rowBytes));
+    CK(cudaMemsetAsync(dDoneRecon_, 0, rowBytes, stream_));
+    CK(cudaMemsetAsync(dDoneDeblock_, 0, rowBytes, stream_));
+    CK(cudaMalloc(&dBsWords_, sizeof(uint32_t) * 4 * (size_t)nStreams * g.nMbs));
     CK(cudaMalloc(&dWork_, (size_t)nStreams * g.nMbs));
     // counters: [0] pass-B tickets, [1] filter tickets, [2] [3] tickets of the two pass-A instances (zeroed per picture);
     // [4] IDCT range errors, [6..7] macroblocks with filter work (running totals)
@@ -196,8 +187,6 @@ bool Batch::create(int device, uint32_t nStreams, uint32_t widthMbs, uint32_t he
     // pass A: a warp task is a column piece of at most 32 macroblocks; pieces of a column are made equally long
     chunksPerCol_ = (heightMbs + 31) / 32;
     chunkRows_ = (heightMbs + chunksPerCol_ - 1) / chunksPerCol_;
-    // tuning knobs (defaults are the measured best on the 512-stream 1080p batch)
-    if (const char *e = std::getenv("B200_CHUNK_B")) chunkB_ = std::max(1, std::min((int)kChunkB, std::atoi(e)));
     tapes_.assign(nStreams, DevTape());
     CK(cudaStreamCreateWithFlags(&auxStream_, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&joinEv_, cudaEventDisableTiming));
@@ -413,8 +402,6 @@ bool Batch::launchPicture(const StreamJob *dJobs, const StreamJob *dJobsFilter, 
     if (recon) {
         rp.pool = pool_; rp.g = g_; rp.jobs = dJobs; rp.done = dDoneRecon_;
         rp.ticket = dCounters_ + 0; rp.ticketA = dCounters_ + 2; rp.errors = dCounters_ + 4; rp.serial = serial_;
-        rp.chunkB = (uint32_t)chunkB_;
-        rp.chunksB = (maxB + rp.chunkB - 1) / rp.chunkB;
         rp.chunkRows = chunkRows_;
         rp.chunksPerCol = chunksPerCol_;
         rp.totalChunks = chunksPerCol_ * (uint32_t)g_.widthMbs * (uint32_t)g_.nStreams;

@@ -93,7 +93,6 @@ private:
     PoolGeom g_{};
     uint8_t *pool_ = nullptr;
     CUtensorMap maps_[10];             // PassAMaps (recon_kernel.cuh): luma [nx 1..3][16 / 21 rows], chroma [nx 1..2][8 / 9 rows]
-    uint16_t *dOrder_ = nullptr;
     uint32_t *dDoneRecon_ = nullptr, *dDoneDeblock_ = nullptr, *dCounters_ = nullptr, *dSlots_ = nullptr, *dBsWords_ = nullptr;
     uint8_t *dWork_ = nullptr;
     int strengthBlocks_ = 0;
@@ -103,7 +102,6 @@ private:
     cudaEvent_t syncEv_ = nullptr, forkEv_ = nullptr, joinEv_ = nullptr;
     size_t jobsCap_ = 0;
     uint32_t *dConvertAll_ = nullptr;
-    int chunkB_ = 1;   // list entries per intra warp task
     cudaStream_t uploadStream_ = nullptr;
     std::deque<std::pair<uint32_t, cudaEvent_t>> fences_;   // (pictures below this index, upload-stream event)
     std::vector<cudaEvent_t> fenceFree_;

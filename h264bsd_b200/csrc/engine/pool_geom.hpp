@@ -51,13 +51,11 @@ struct ReconParams {
     uint8_t *pool;
     PoolGeom g;
     const StreamJob *jobs;     // nStreams
-    uint32_t *done;            // nStreams * nMbs completion flags (pass B only)
+    uint32_t *done;            // nStreams * heightMbs row-progress words of pass B: serial << 16 | macroblocks finished
     uint32_t *ticket;          // CTA ticket counter of pass B (zeroed before launch)
     uint32_t *ticketA;         // chunk ticket counter of pass A (zeroed before launch)
     uint32_t *errors;          // [0] IDCT range errors (h264bsd_transform.c:183-188)
     uint32_t serial;           // value that marks "done in this launch"
-    uint32_t chunksB;          // pass B: warp tasks (chunkB entries) per stream
-    uint32_t chunkB;           // pass B: list entries per warp task
     uint32_t chunkRows;        // pass A: macroblocks of one column per warp task (<= 32)
     uint32_t chunksPerCol;     // pass A: ceil(heightMbs / chunkRows)
     uint32_t totalChunks;      // pass A: chunksPerCol * widthMbs * nStreams

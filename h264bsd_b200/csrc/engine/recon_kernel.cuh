@@ -14,7 +14,6 @@ constexpr int kReconWarps = 8;    // warps per CTA of the intra pass
 #define B200_PASSA_WARPS 4
 #endif
 constexpr int kPassAWarps = B200_PASSA_WARPS;   // warps per CTA of pass A
-constexpr int kChunkB = 8;   // most consecutive pass-B (wavefront) entries per warp task (ReconParams::chunkB <= kChunkB)
 
 // Tensor maps of pass A (Batch::create): strip-major planes -> raster windows (pool_geom.hpp).  A luma box is nx strips wide
 // (16 nx pels) and 16 rows (integer vertical vector) or 21 rows (16 + 5 for the six-tap filter) high; a chroma box nx strips

@@ -13,4 +13,9 @@ slot = ps.pics[3].curSlot
 b.convert_bench_all(slot, 1, 2)
 ms = b.convert_bench_all(slot, 1, 5) / 5
 nbytes = n * ps.width_mbs * 16 * ps.height_mbs * 16 * 5.5
+from h264bsd_b200 import _lib
+L = _lib.load()
+fb = ps.frame_bytes
+host = L.h264bsdB200HostAlloc(fb * n)
+b.read_picture_all(3, host, fb); b.sync()          # packKernel: strip layout -> planar I420 of every stream, then one D2H
 print(json.dumps({"streams": n, "ms_per_launch": ms, "GB_per_s": nbytes / (ms / 1e3) / 1e9}))
