@@ -357,7 +357,8 @@ def main():
     # pass A = the fused MC + dequant/IDCT + add + write path of SURVEY 8(d) for every inter / I_PCM macroblock of a picture: one
     # launch of passAKernel per picture (an IDR picture's launch finds nothing to do: every macroblock is intra)
     pass_a_bytes = float(per_pic_a_bytes.sum()) * count / max(1, ps.num_pics)
-    pass_a_ms = per_launch("recon")
+    # (the engine dispatches it as two instances -- one partition / several partitions -- timed one after the other)
+    pass_a_ms = per_launch("recon") + per_launch("recon_multi")
     achieved = gbs(pass_a_bytes, pass_a_ms)
     # in-loop filter: pels (768 B) only of the macroblocks that have a non-zero boundary strength, record + strengths of all
     deb_bytes_per_launch = (768.0 * deblock_work_frac + MB_REC_BYTES + 17) * nmb * count
@@ -367,7 +368,8 @@ def main():
                                       "included; one launch per picture over all streams)", "achieved": achieved, "peak": peak,
             "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": pass_a_bytes, "ms_per_launch": pass_a_ms,
-            "share_of_step": stage_ms["recon"] / step_ms,
+            "share_of_step": (stage_ms["recon"] + stage_ms["recon_multi"]) / step_ms,
+            "ms_per_launch_instances": {"one_partition_and_copies": per_launch("recon"), "several_partitions": per_launch("recon_multi")},
             "serialized_step_ms": ms_serial / args.steps,
             "macroblock_mix": {"zero_motion_copies": copy_frac, "other_inter_and_pcm": other_frac, "intra": 1.0 - copy_frac - other_frac},
             "other_kernels": {"strengthKernel + deblockKernel": {"achieved_gbs": gbs(deb_bytes_per_launch, deb_ms_per_launch), "ms_per_launch": deb_ms_per_launch,

@@ -229,7 +229,7 @@ class Batch:
         ms = (C.c_float * 6)()
         n = (C.c_uint32 * 6)()
         self._ck(self._L.h264bsdB200BatchKernelTimes(self.h, ms, n), 'kernel_times')
-        keys = ('recon', 'deblock', 'border', 'recon_intra', 'strength', 'unused')
+        keys = ('recon', 'deblock', 'border', 'recon_intra', 'strength', 'recon_multi')
         return ({k: ms[i] for i, k in enumerate(keys)}, {k: n[i] for i, k in enumerate(keys)})
 
     def deblock_work_mbs(self):

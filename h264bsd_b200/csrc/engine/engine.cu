@@ -184,8 +184,9 @@ bool Batch::create(int device, uint32_t nStreams, uint32_t widthMbs, uint32_t he
         deblockBlocks_ = std::max(numSms_ / 2, deblockBlocks_ / d);
         intraBlocks_ = std::max(numSms_ / 2, intraBlocks_ / d);
     }
-    // pass A: a warp task is a column piece of at most 32 macroblocks; pieces of a column are made equally long
-    chunksPerCol_ = (heightMbs + 31) / 32;
+    // pass A: a warp task is a column piece of at most kStageMbs macroblocks (what a warp's copy staging buffer holds); pieces of a
+    // column are made equally long
+    chunksPerCol_ = (heightMbs + kStageMbs - 1) / kStageMbs;
     chunkRows_ = (heightMbs + chunksPerCol_ - 1) / chunksPerCol_;
     tapes_.assign(nStreams, DevTape());
     CK(cudaStreamCreateWithFlags(&auxStream_, cudaStreamNonBlocking));
@@ -430,9 +431,10 @@ bool Batch::launchPicture(const StreamJob *dJobs, const StreamJob *dJobsFilter, 
             const uint32_t ctas = (rp.totalChunks + kPassAWarps - 1) / kPassAWarps;
             const PassAMaps &maps = *reinterpret_cast<const PassAMaps *>(maps_);
             passAKernelT<false><<<std::min<uint32_t>(ctas, (uint32_t)passABlocks_), kPassAWarps * 32, sizeof(PassAWarpSmem) * kPassAWarps, stream_>>>(rp, maps);
+            mark(0);
             passAKernelT<true><<<std::min<uint32_t>(ctas, (uint32_t)passABlocks_), kPassAWarps * 32, sizeof(PassAWarpSmem) * kPassAWarps, stream_>>>(rp, maps);
             launches_ += 2;
-            mark(0);
+            mark(5);
         }
         if (maxB) {
             const uint32_t ctasB = ((uint32_t)g_.heightMbs * (uint32_t)g_.nStreams + kReconWarps - 1) / kReconWarps;

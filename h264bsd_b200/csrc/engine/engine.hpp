@@ -56,7 +56,7 @@ public:
     int compareStreams(const uint32_t *slots);
     // per-stage device time (CUDA events on the engine's stream around every launch)
     void kernelTiming(bool enable);
-    bool kernelTimes(float ms[6], uint32_t *launchesPerStage);  // recon pass A, deblock filter, border, recon pass B, boundary strengths, (unused)
+    bool kernelTimes(float ms[6], uint32_t *launchesPerStage);  // recon pass A (first instance), deblock filter, border, recon pass B, boundary strengths, pass A (second instance: several partitions)
     // picture k's frame of every stream, cropped / as NV12 (see packKernel); cropW == 0: the coded size
     bool readPictureAllEx(uint32_t k, uint8_t *dst, size_t strideBytes, int cropX, int cropY, int cropW, int cropH, int nv12);
     uint32_t idctErrors();

@@ -26,20 +26,25 @@ struct PassAMaps {
 constexpr int kLumaBufBytes = 1024;     // >= 48 x 21
 constexpr int kChromaBufBytes = 384;    // >= 32 x 9
 constexpr int kCoefBufBytes = 896;      // >= 26 blocks of 32 bytes (I_PCM: 12)
+constexpr int kStageMbs = 15;           // macroblocks of a chunk at most (Batch::create): what the copy staging buffer holds
 
 struct __align__(128) PassAWarpSmem {
     uint8_t luma[2][kLumaBufBytes];       // reference windows: the macroblock being computed / the next one (TMA, mbarrier double buffer)
     uint8_t chroma[2][kChromaBufBytes];
     uint8_t coef[2][kCoefBufBytes];       // the macroblock's levels (cp.async.bulk, same mbarrier)
-    int32_t resY[16][16];                 // residual of the macroblock being computed, raster
-    int32_t resC[2][8][8];
+    int16_t resY[16][16];                 // residual of the macroblock being computed, raster
+    int16_t resC[2][8][8];
     uint64_t mbar[2];
-    uint8_t list[32];                     // compaction scratch: lanes of the chunk's copies / the macroblock's active 4x4 blocks
+    uint64_t mbarCopy;                    // the chunk's copies have arrived in `stage`
+    uint8_t list[32];                     // compaction scratch: the macroblock's active 4x4 blocks
     int32_t dcC[8];                       // chroma DC values of the macroblock being computed
-    uint8_t pred[384];                    // sub-macroblocks with 8x4 / 4x8 / 4x4 partitions only
-    uint8_t pad[48];
+    uint8_t pad[40];
+    // first instance: the chunk's zero-motion copies on their way from the reference frame to the current one (bulk copies
+    // global -> shared -> global: luma of macroblock l at 256 l, chroma at 256 kStageMbs + 128 l).  Second instance (it has no
+    // copies): prediction of sub-macroblocks with 8x4 / 4x8 / 4x4 partitions in the first 384 bytes.
+    uint8_t stage[kStageMbs * 384];
 };
-static_assert(sizeof(PassAWarpSmem) % 128 == 0, "per-warp shared memory keeps the TMA destinations 128-byte aligned");
+static_assert(sizeof(PassAWarpSmem) % 128 == 0 && offsetof(PassAWarpSmem, stage) % 128 == 0, "per-warp shared memory keeps the TMA destinations 128-byte aligned");
 
 struct __align__(16) IntraWarpSmem {
     int16_t res[24][16];
@@ -467,9 +472,10 @@ __device__ __forceinline__ void laneResidual(const int16_t (*res)[16], int lane,
 // lanes 16..23 first.  `cbuf` = the macroblock's levels in shared memory (b200_mb_rec layout: [chroma DC][coded blocks]).
 __device__ __noinline__ void residualShfl(PassAWarpSmem &sm, const uint8_t *cbuf, uint32_t mask, int qpY, int qpC, int lane, uint32_t *errors) {
     {   // every block that is not visited below has a zero residual
-        uint4 *z = reinterpret_cast<uint4 *>(&sm.resY[0][0]);   // resY and resC are contiguous: 96 x 16 bytes
+        uint4 *z = reinterpret_cast<uint4 *>(&sm.resY[0][0]);   // resY and resC are contiguous: 48 x 16 bytes
         const uint4 zero = make_uint4(0, 0, 0, 0);
-        z[lane] = zero; z[lane + 32] = zero; z[lane + 64] = zero;
+        z[lane] = zero;
+        if (lane < 16) z[lane + 32] = zero;
     }
     int dc = 0;
     if ((mask & B200_CM_CHROMA_DC) && lane >= 16 && lane < 24) {
@@ -525,22 +531,24 @@ __device__ __noinline__ void residualShfl(PassAWarpSmem &sm, const uint8_t *cbuf
         }
         if (valid) {
             if (range >> 10) atomicAdd(errors, 1u);
-            int32_t *dst;
+            int16_t *dst;
             if (b < 16) dst = &sm.resY[(((b >> 1) & 1) + ((b >> 3) & 1) * 2) * 4 + orow][((b & 1) + ((b >> 2) & 1) * 2) * 4];
             else dst = &sm.resC[(b - 16) >> 2][((b >> 1) & 1) * 4 + orow][(b & 1) * 4];
-            *reinterpret_cast<uint4 *>(dst) = make_uint4((uint32_t)o[0], (uint32_t)o[1], (uint32_t)o[2], (uint32_t)o[3]);
+            *reinterpret_cast<uint2 *>(dst) = make_uint2(((uint32_t)o[0] & 0xFFFFu) | ((uint32_t)o[1] << 16), ((uint32_t)o[2] & 0xFFFFu) | ((uint32_t)o[3] << 16));
         }
     }
     __syncwarp();
 }
 
-// window of a partition at picture position (px, py), size w x h (wh = w | h << 8), vector (mvx, mvy): clamp the origin into
-// the bordered plane (a window wholly outside the picture on an axis equals the window at the clamped origin because the border
-// is a replication), pick the boxes, and have lane 0 issue the loads (+ the bulk copy of `extraBytes` of levels) on
-// mbarrier `buf`.  Returns xo | nx << 4 | cxo << 8 | nxC << 12.
-__device__ __noinline__ uint32_t issueWindowFn(PassAWarpSmem *sm, int buf, const PassAMaps *maps, int W, int H, int px, int py, int wh,
-                                               int mvx, int mvy, uint32_t refFrame, uint32_t extraBytes, const void *extraSrc, int lane) {
-    const int w = wh & 0xFF, h = wh >> 8;
+// window of a partition at picture position (px, py), size w x h, vector (mvx, mvy): clamp the origin into the bordered plane (a
+// window wholly outside the picture on an axis equals the window at the clamped origin because the border is a replication,
+// SURVEY 7.2) and pick the boxes.  geom = xo | nx << 4 | cxo << 8 | nxC << 12.
+struct WindowGeom {
+    int strip, row, map;       // luma box: first strip, first row, tensor map (nx - 1) * 2 + (21 rows ? 1 : 0)
+    int stripC, rowC, mapC;    // chroma box
+    uint32_t bytes, geom;
+};
+__device__ __forceinline__ WindowGeom windowGeom(int W, int H, int px, int py, int w, int h, int mvx, int mvy) {
     const int xf = mvx & 3, yf = mvy & 3, nc = w + (xf ? 5 : 0), nr = h + (yf ? 5 : 0);
     const int x0 = clip3(-kPadY, W + kPadY - nc, px + (mvx >> 2) - (xf ? 2 : 0)) + kPadY;
     const int y0 = clip3(-kPadY, H + kPadY - nr, py + (mvy >> 2) - (yf ? 2 : 0)) + kPadY;
@@ -549,14 +557,24 @@ __device__ __noinline__ uint32_t issueWindowFn(PassAWarpSmem *sm, int buf, const
     const int cx0 = clip3(-kPadC, W / 2 + kPadC - ncC, (px >> 1) + (mvx >> 3)) + kPadC;
     const int cy0 = clip3(-kPadC, H / 2 + kPadC - nrC, (py >> 1) + (mvy >> 3)) + kPadC;
     const int cxo = cx0 & 7, nxC = (cxo + ncC + 7) >> 3;
+    WindowGeom r;
+    r.strip = x0 >> 4; r.row = y0; r.map = (nx - 1) * 2 + (yf ? 1 : 0);
+    r.stripC = cx0 >> 3; r.rowC = cy0; r.mapC = (nxC - 1) * 2 + (cyf ? 1 : 0);
+    r.bytes = (uint32_t)(16 * nx * (yf ? 21 : 16) + 16 * nxC * (cyf ? 9 : 8));
+    r.geom = (uint32_t)xo | ((uint32_t)nx << 4) | ((uint32_t)cxo << 8) | ((uint32_t)nxC << 12);
+    return r;
+}
+// one window into (dstL, dstC), completion on `bar`, issued by lane 0 (sub-macroblock partitions below 8x8 only)
+__device__ __noinline__ uint32_t issueWindowFn(uint8_t *dstL, uint8_t *dstC, uint64_t *bar, const PassAMaps *maps, int W, int H, int px, int py,
+                                               int wh, int mvx, int mvy, uint32_t refFrame, int lane) {
+    const WindowGeom wg = windowGeom(W, H, px, py, wh & 0xFF, wh >> 8, mvx, mvy);
     if (lane == 0) {
         fenceProxyAsync();
-        mbarExpectTx(&sm->mbar[buf], (uint32_t)(16 * nx * (yf ? 21 : 16) + 16 * nxC * (cyf ? 9 : 8)) + extraBytes);
-        tmaLoad4d(sm->luma[buf], &maps->luma[nx - 1][yf ? 1 : 0], 0, x0 >> 4, y0, (int)refFrame, &sm->mbar[buf]);
-        tmaLoad4d(sm->chroma[buf], &maps->chroma[nxC - 1][cyf ? 1 : 0], 0, cx0 >> 3, cy0, (int)refFrame, &sm->mbar[buf]);
-        if (extraBytes) bulkLoad(sm->coef[buf], extraSrc, extraBytes, &sm->mbar[buf]);
+        mbarExpectTx(bar, wg.bytes);
+        tmaLoad4d(dstL, &maps->luma[0][0] + wg.map, 0, wg.strip, wg.row, (int)refFrame, bar);
+        tmaLoad4d(dstC, &maps->chroma[0][0] + wg.mapC, 0, wg.stripC, wg.rowC, (int)refFrame, bar);
     }
-    return (uint32_t)xo | ((uint32_t)nx << 4) | ((uint32_t)cxo << 8) | ((uint32_t)nxC << 12);
+    return wg.geom;
 }
 
 #ifndef B200_PASSA_MINBLOCKS
@@ -575,10 +593,11 @@ passAKernelT(const ReconParams p, const __grid_constant__ PassAMaps maps) {
     if (lane == 0) {
         mbarInit(&sm.mbar[0], 1);
         mbarInit(&sm.mbar[1], 1);
+        mbarInit(&sm.mbarCopy, 1);
         fenceMbarInit();
     }
     __syncwarp();
-    uint32_t phaseBits = 0;   // bit b = phase parity of mbarrier b
+    uint32_t phaseBits = 0;   // bit b = phase parity of mbarrier b, bit 2 = of the copy barrier
     const uint32_t nWarps = gridDim.x * kPassAWarps;
     const uint32_t chunksPerStream = p.chunksPerCol * (uint32_t)g.widthMbs;
     // this lane's spans inside a macroblock: 8 luma samples (row r8, columns c8..c8+7 = bytes 8 lane.. of the 256), 4 chroma
@@ -586,30 +605,49 @@ passAKernelT(const ReconParams p, const __grid_constant__ PassAMaps maps) {
     const int r8 = lane >> 1, c8 = (lane & 1) * 8;
     const int cr = lane >> 2, cp = (lane >> 1) & 1, cc = (lane & 1) * 4;
 
-    // a warp's first chunk is its own number, the following ones come from a ticket counter (asked for one chunk ahead)
+    // Lane l fetches the words of record l of a chunk one chunk ahead: while a chunk is worked on, the records of the warp's next
+    // one are on their way (ticket -> job -> records is a chain of three dependent memory round trips otherwise).  First
+    // instance: head, reference slots, word 7 (concealment), first vector; second: head, reference slots, the first vector of
+    // each 8x8 quadrant
+    uint32_t fPos = 0, fS = 0, fW0 = 0, fMask = 0, fCoef = 0, fW3 = 0, fRef = 0, fW7 = 0, fMv = 0, fMv1 = 0, fMv2 = 0, fMv3 = 0;
+    auto fetch = [&](uint32_t c) {
+        if (c >= p.totalChunks) return;
+        const uint32_t s = c / chunksPerStream, c2 = c - s * chunksPerStream;
+        const uint32_t mbx = c2 / p.chunksPerCol, row0 = (c2 - mbx * p.chunksPerCol) * p.chunkRows;
+        fS = s;
+        fPos = mbx | (row0 << 16);
+        if ((int)(row0 + (uint32_t)lane) < g.heightMbs && (uint32_t)lane < p.chunkRows) {
+            const uint32_t *rw = reinterpret_cast<const uint32_t *>(p.jobs[s].recs + (size_t)(row0 + (uint32_t)lane) * g.widthMbs + mbx);
+            const uint4 hw = __ldg(reinterpret_cast<const uint4 *>(rw));
+            fRef = __ldg(rw + 4);
+            fMv = __ldg(rw + 8);
+            if (kMulti) { fMv1 = __ldg(rw + 12); fMv2 = __ldg(rw + 16); fMv3 = __ldg(rw + 20); }
+            else fW7 = __ldg(rw + 7);
+            fW0 = hw.x; fMask = hw.y; fCoef = hw.z; fW3 = hw.w;
+        }
+    };
+
+    // a warp's first chunk is its own number, the following ones come from a ticket counter (asked for two chunks ahead)
     uint32_t chunk = blockIdx.x * kPassAWarps + warp;
+    fetch(chunk);
+    uint32_t nextChunk = 0;
+    if (lane == 0) nextChunk = atomicAdd(p.ticketA + (kMulti ? 1 : 0), 1u) + nWarps;
+    nextChunk = __shfl_sync(0xffffffffu, nextChunk, 0);
     while (chunk < p.totalChunks) {
-        uint32_t nextChunk = 0;
-        if (lane == 0) nextChunk = atomicAdd(p.ticketA + (kMulti ? 1 : 0), 1u) + nWarps;
-        const uint32_t s = chunk / chunksPerStream, c2 = chunk - s * chunksPerStream;
-        const int mbx = (int)(c2 / p.chunksPerCol), row0 = (int)((c2 - (uint32_t)mbx * p.chunksPerCol) * p.chunkRows);
+        uint32_t ticket2 = 0;
+        if (lane == 0) ticket2 = atomicAdd(p.ticketA + (kMulti ? 1 : 0), 1u) + nWarps;
+        const uint32_t s = fS;
+        const int mbx = (int)(fPos & 0xFFFFu), row0 = (int)(fPos >> 16);
         const int n = min((int)p.chunkRows, g.heightMbs - row0);
+        const uint32_t mW0 = fW0, mMask = fMask, mCoef = fCoef, mW3 = fW3, mRef = fRef, mMv = fMv, w7 = fW7, mMv1 = fMv1, mMv2 = fMv2, mMv3 = fMv3;
+        fetch(nextChunk);
         const StreamJob job = p.jobs[s];
         const uint32_t frameBase = s * (uint32_t)g.numSlots;
         uint8_t *cur = framePtr(p.pool, g, frameBase + job.curSlot);
         uint8_t *lbase = mbLuma(cur, g, mbx, row0), *cbase = mbChroma(cur, g, mbx, row0);   // macroblock l of the chunk: + 256 l / + 128 l
 
-        // lane l: head, reference slots, wait mask and first vector of record l
-        uint32_t mW0 = 0, mMask = 0, mCoef = 0, mRef = 0, mMv = 0;
         bool isCopy = false, isInter = false;
-        const b200_mb_rec *rec0 = job.recs + (size_t)row0 * g.widthMbs + mbx;   // record of macroblock l: + l * widthMbs
         if (lane < n) {
-            const uint32_t *rw = reinterpret_cast<const uint32_t *>(rec0 + (size_t)lane * g.widthMbs);
-            const uint4 hw = __ldg(reinterpret_cast<const uint4 *>(rw));
-            mRef = __ldg(rw + 4);
-            const uint32_t w7 = __ldg(rw + 7);
-            mMv = __ldg(rw + 8);
-            mW0 = hw.x; mMask = hw.y; mCoef = hw.z;
             const uint32_t type = mW0 & 0xFFu;
             // a concealed macroblock carries the state the filter wants to see (Intra4x4); its pels are a copy of the reference
             // picture (no neighbours to wait for) or come from concealKernel (h264bsd_b200_tape.h)
@@ -619,175 +657,250 @@ passAKernelT(const ReconParams p, const __grid_constant__ PassAMaps maps) {
             else if (type <= B200_MB_P_16x16 && mMask == 0 && mMv == 0) isCopy = true;
             else isInter = type <= B200_MB_P_16x16 || type == B200_MB_I_PCM;
         }
-        const uint32_t copyMask = __ballot_sync(0xffffffffu, isCopy);
+        const uint32_t copyMask = kMulti ? 0u : __ballot_sync(0xffffffffu, isCopy);
         uint32_t interMask = __ballot_sync(0xffffffffu, isInter);
-        // Every lane works out where the windows of ITS macroblock lie (one partition: P_Skip / P_L0_16x16), all macroblocks of
-        // the chunk at once instead of one after the other when their turn comes: the origin clamped into the bordered plane (a
-        // window wholly outside the picture on an axis equals the window at the clamped origin because the border is a
-        // replication), the boxes, the bytes to expect.
-        //   gX = luma strip | chroma strip << 16     gY = luma row | chroma row << 16
-        //   gM = luma map (3 bits) | chroma map << 3 (2) | xo << 5 (4) | cxo << 9 (3) | mvx & 7 << 12 | mvy & 7 << 15 | window bytes << 18
-        uint32_t gX = 0, gY = 0, gM = 0;
-        if (!kMulti && isInter && (mW0 & 0xFFu) <= B200_MB_P_16x16) {
-            const int mvx = (int)(int16_t)(mMv & 0xFFFFu), mvy = (int)(int16_t)(mMv >> 16);
-            const int px = mbx * 16, py = (row0 + lane) * 16;
-            const int xf = mvx & 3, yf = mvy & 3, nc = 16 + (xf ? 5 : 0), nr = 16 + (yf ? 5 : 0);
-            const int x0 = clip3(-kPadY, g.W + kPadY - nc, px + (mvx >> 2) - (xf ? 2 : 0)) + kPadY;
-            const int y0 = clip3(-kPadY, g.H + kPadY - nr, py + (mvy >> 2) - (yf ? 2 : 0)) + kPadY;
-            const int xo = x0 & 15, nx = (xo + nc + 15) >> 4;
-            const int cxf = mvx & 7, cyf = mvy & 7, ncC = 8 + (cxf ? 1 : 0), nrC = 8 + (cyf ? 1 : 0);
-            const int cx0 = clip3(-kPadC, g.W / 2 + kPadC - ncC, (px >> 1) + (mvx >> 3)) + kPadC;
-            const int cy0 = clip3(-kPadC, g.H / 2 + kPadC - nrC, (py >> 1) + (mvy >> 3)) + kPadC;
-            const int cxo = cx0 & 7, nxC = (cxo + ncC + 7) >> 3;
-            const uint32_t bytes = (uint32_t)(16 * nx * (yf ? 21 : 16) + 16 * nxC * (cyf ? 9 : 8));
-            gX = (uint32_t)(x0 >> 4) | ((uint32_t)(cx0 >> 3) << 16);
-            gY = (uint32_t)y0 | ((uint32_t)cy0 << 16);
-            gM = (uint32_t)((nx - 1) * 2 + (yf ? 1 : 0)) | ((uint32_t)((nxC - 1) * 2 + (cyf ? 1 : 0)) << 3) | ((uint32_t)xo << 5) |
-                 ((uint32_t)cxo << 9) | ((uint32_t)cxf << 12) | ((uint32_t)cyf << 15) | (bytes << 18);
-        }
 
-        // ---- what is staged for the macroblock whose turn comes next ------------------------------------------------
-        uint32_t nW0 = 0, nMask = 0, nRef = 0, nGeom = 0;
-        int nL = 0;
-        bool nArmed = false;
-        auto issueWindow = [&](int buf, int px, int py, int w, int h, int mvx, int mvy, uint32_t refFrame, uint32_t extraBytes,
-                               const void *extraSrc) -> uint32_t {
-            return issueWindowFn(&sm, buf, &maps, g.W, g.H, px, py, w | (h << 8), mvx, mvy, refFrame, extraBytes, extraSrc, lane);
-        };
-        // stage macroblock l of the chunk into buffer `buf`: its levels always, its windows when it has one partition
-        auto prepare = [&](int l, int buf) {
-            nL = l;
-            nW0 = __shfl_sync(0xffffffffu, mW0, l); nMask = __shfl_sync(0xffffffffu, mMask, l);
-            nRef = __shfl_sync(0xffffffffu, mRef, l);
-            nGeom = __shfl_sync(0xffffffffu, gM, l);
-            const uint32_t coefIndex = __shfl_sync(0xffffffffu, mCoef, l);
-            const uint32_t gx = __shfl_sync(0xffffffffu, gX, l), gy = __shfl_sync(0xffffffffu, gY, l);
-            const uint32_t type = nW0 & 0xFFu;
-            const uint32_t coefBytes = type == B200_MB_I_PCM ? 384u : 32u * (uint32_t)__popc(nMask & 0x3FFFFFFu);
-            const bool windows = !kMulti && type <= B200_MB_P_16x16;
-            nArmed = windows || coefBytes != 0;
-            if (lane == 0 && nArmed) {
-                fenceProxyAsync();
-                mbarExpectTx(&sm.mbar[buf], (nGeom >> 18) + coefBytes);
-                if (windows) {
-                    const int ref = (int)(frameBase + (nRef & 0xFFu));
-                    tmaLoad4d(sm.luma[buf], &maps.luma[0][0] + (nGeom & 7u), 0, (int)(gx & 0xFFFFu), (int)(gy & 0xFFFFu), ref, &sm.mbar[buf]);
-                    tmaLoad4d(sm.chroma[buf], &maps.chroma[0][0] + ((nGeom >> 3) & 3u), 0, (int)(gx >> 16), (int)(gy >> 16), ref, &sm.mbar[buf]);
-                }
-                if (coefBytes) bulkLoad(sm.coef[buf], job.coefs + (size_t)coefIndex * 16, coefBytes, &sm.mbar[buf]);
+        // add residual + clip + store of macroblock l of the chunk (h264bsdWriteOutputBlocks, image.c:172-344): a pel leaves its
+        // word and meets its residual in one dot product
+        auto finish = [&](int l, uint32_t mask, uint2 pv, uint32_t pc) {
+            if (mask) {
+                const uint4 ra = *reinterpret_cast<const uint4 *>(&sm.resY[r8][c8]);
+                const uint2 rc = *reinterpret_cast<const uint2 *>(&sm.resC[cp][cr][cc]);
+                auto lo = [](uint32_t w) { return (int)(int16_t)(w & 0xFFFFu); };
+                auto hi = [](uint32_t w) { return (int)w >> 16; };
+                pv = make_uint2(pack4sat(dp4aUS(pv.x, 0x00000001, lo(ra.x)), dp4aUS(pv.x, 0x00000100, hi(ra.x)),
+                                         dp4aUS(pv.x, 0x00010000, lo(ra.y)), dp4aUS(pv.x, 0x01000000, hi(ra.y))),
+                                pack4sat(dp4aUS(pv.y, 0x00000001, lo(ra.z)), dp4aUS(pv.y, 0x00000100, hi(ra.z)),
+                                         dp4aUS(pv.y, 0x00010000, lo(ra.w)), dp4aUS(pv.y, 0x01000000, hi(ra.w))));
+                pc = pack4sat(dp4aUS(pc, 0x00000001, lo(rc.x)), dp4aUS(pc, 0x00000100, hi(rc.x)),
+                              dp4aUS(pc, 0x00010000, lo(rc.y)), dp4aUS(pc, 0x01000000, hi(rc.y)));
             }
+            *reinterpret_cast<uint2 *>(lbase + l * 256 + lane * 8) = pv;
+            *reinterpret_cast<uint32_t *>(cbase + l * 128 + lane * 4) = pc;
         };
-        if (interMask) prepare(__ffs(interMask) - 1, 0);
 
-        // ---- copies: lanes 0..23 move the 16 luma + 8 chroma 16-byte units of a macroblock, four macroblocks in flight ----------
-        if (!kMulti && copyMask) {
-            // lane l: where the reference frame of ITS macroblock lies relative to the current frame, in 256-byte units (a frame
-            // stride is a multiple of 256)
-            const int myDelta = ((int)(mRef & 0xFFu) - (int)job.curSlot) * (int)(g.frameStride >> 8);
-            uint8_t *mine = lane < 16 ? lbase + lane * 16 : cbase + (lane - 16) * 16;   // this lane's unit of macroblock 0 of the chunk
-            const uint32_t step = lane < 16 ? 256u : 128u;
-            uint32_t cm = copyMask;
-#pragma unroll 1
-            while (cm) {
-                uint4 v[4];
-                uint8_t *dst[4];
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const int e = __ffs(cm) - 1;          // (-1 once the mask is empty: lanes >= 24 and those steps do nothing)
-                    cm &= cm - 1;
-                    const long long delta = (long long)__shfl_sync(0xffffffffu, myDelta, e & 31) * 256;
-                    dst[j] = (e >= 0 && lane < 24) ? mine + (uint32_t)e * step : nullptr;
-                    if (dst[j]) v[j] = __ldg(reinterpret_cast<const uint4 *>(dst[j] + delta));
+        if constexpr (!kMulti) {
+            // ---- copies: every run of vertically adjacent copies with the same reference frame is 256 n contiguous bytes of
+            // luma and 128 n of chroma in the strip layout.  The lane of a run's first macroblock sends them through the staging
+            // buffer with bulk copies -- no registers, no issue slots, and the inter macroblocks below are computed while they fly
+            int runLen = 0;
+            bulkWaitRead<0>();   // the staging buffer is free again once this lane's stores of the previous chunk have read it ...
+            __syncwarp();        // ... and every other lane's
+            if (copyMask) {
+                // where the reference frame of this lane's macroblock lies relative to the current frame, in 256-byte units (a
+                // frame stride is a multiple of 256)
+                const int myDelta = ((int)(mRef & 0xFFu) - (int)job.curSlot) * (int)(g.frameStride >> 8);
+                const int prevDelta = __shfl_up_sync(0xffffffffu, myDelta, 1);
+                const bool cont = isCopy && lane > 0 && ((copyMask >> (lane - 1)) & 1u) && prevDelta == myDelta;
+                const uint32_t contMask = __ballot_sync(0xffffffffu, cont);
+                if (isCopy && !cont) runLen = __ffs(~((contMask >> lane) >> 1));   // 1 + the continuations that follow
+                if (lane == 0) mbarExpectTx(&sm.mbarCopy, 384u * (uint32_t)__popc(copyMask));
+                __syncwarp();
+                if (runLen) {
+                    const long long delta = (long long)myDelta * 256;
+                    bulkLoad(sm.stage + lane * 256, lbase + lane * 256 + delta, 256u * (uint32_t)runLen, &sm.mbarCopy);
+                    bulkLoad(sm.stage + kStageMbs * 256 + lane * 128, cbase + lane * 128 + delta, 128u * (uint32_t)runLen, &sm.mbarCopy);
                 }
-#pragma unroll
-                for (int j = 0; j < 4; j++)
-                    if (dst[j]) *reinterpret_cast<uint4 *>(dst[j]) = v[j];
             }
-        }
 
-        // ---- inter macroblocks, one after the other -------------------------------------------------------------------------
-        int it = 0;
+            // Every lane works out where the windows of ITS macroblock lie (one partition: P_Skip / P_L0_16x16), all macroblocks
+            // of the chunk at once instead of one after the other when their turn comes.
+            //   gX = luma strip | chroma strip << 16     gY = luma row | chroma row << 16
+            //   gM = luma map (3 bits) | chroma map << 3 (2) | xo << 5 (4) | cxo << 9 (3) | mvx & 7 << 12 | mvy & 7 << 15 | window bytes << 18
+            uint32_t gX = 0, gY = 0, gM = 0;
+            if (isInter && (mW0 & 0xFFu) <= B200_MB_P_16x16) {
+                const int mvx = (int)(int16_t)(mMv & 0xFFFFu), mvy = (int)(int16_t)(mMv >> 16);
+                const WindowGeom wg = windowGeom(g.W, g.H, mbx * 16, (row0 + lane) * 16, 16, 16, mvx, mvy);
+                gX = (uint32_t)wg.strip | ((uint32_t)wg.stripC << 16);
+                gY = (uint32_t)wg.row | ((uint32_t)wg.rowC << 16);
+                gM = (uint32_t)wg.map | ((uint32_t)wg.mapC << 3) | ((wg.geom & 15u) << 5) | (((wg.geom >> 8) & 7u) << 9) |
+                     ((uint32_t)(mvx & 7) << 12) | ((uint32_t)(mvy & 7) << 15) | (wg.bytes << 18);
+            }
+
+            // ---- what is staged for the macroblock whose turn comes next ------------------------------------------------
+            uint32_t nW0 = 0, nMask = 0, nGeom = 0;
+            int nL = 0;
+            // stage macroblock l of the chunk into buffer `buf`: its levels and its windows.  The lane that holds the record
+            // issues the loads; the others learn what they need to compute with
+            auto prepare = [&](int l, int buf) {
+                nL = l;
+                nW0 = __shfl_sync(0xffffffffu, mW0, l); nMask = __shfl_sync(0xffffffffu, mMask, l);
+                nGeom = __shfl_sync(0xffffffffu, gM, l);
+                if (lane == l) {
+                    const uint32_t type = mW0 & 0xFFu;
+                    const uint32_t coefBytes = type == B200_MB_I_PCM ? 384u : 32u * (uint32_t)__popc(mMask & 0x3FFFFFFu);
+                    fenceProxyAsync();
+                    mbarExpectTx(&sm.mbar[buf], (gM >> 18) + coefBytes);
+                    if (type != B200_MB_I_PCM) {
+                        const int ref = (int)(frameBase + (mRef & 0xFFu));
+                        tmaLoad4d(sm.luma[buf], &maps.luma[0][0] + (gM & 7u), 0, (int)(gX & 0xFFFFu), (int)(gY & 0xFFFFu), ref, &sm.mbar[buf]);
+                        tmaLoad4d(sm.chroma[buf], &maps.chroma[0][0] + ((gM >> 3) & 3u), 0, (int)(gX >> 16), (int)(gY >> 16), ref, &sm.mbar[buf]);
+                    }
+                    if (coefBytes) bulkLoad(sm.coef[buf], job.coefs + (size_t)mCoef * 16, coefBytes, &sm.mbar[buf]);
+                }
+            };
+            if (interMask) prepare(__ffs(interMask) - 1, 0);
+
+            // ---- inter macroblocks, one after the other: the next one is staged while this one is computed ----------------------
+            int it = 0;
 #pragma unroll 1
-        while (interMask) {
-            interMask &= interMask - 1;
-            const int buf = it & 1;
-            it++;
-            const int l = nL;
-            const uint32_t w0 = nW0, mask = nMask, refSlots = nRef, geom = nGeom;
-            const bool armed = nArmed;
-            const uint32_t type = w0 & 0xFFu;
-            const int qpY = (w0 >> 8) & 0xFF, qpC = (w0 >> 16) & 0xFF;
-            const bool single = !kMulti;    // (I_PCM, the one other kind of the first instance, leaves before it matters)
-            // one partition: the next macroblock is staged now, while this one is computed; several partitions: both window
-            // buffers are needed for this macroblock, the next one is staged when it is through
-            if (single && interMask) prepare(__ffs(interMask) - 1, buf ^ 1);
-            if (armed) {
+            while (interMask) {
+                interMask &= interMask - 1;
+                const int buf = it & 1;
+                it++;
+                const int l = nL;
+                const uint32_t w0 = nW0, mask = nMask, geom = nGeom;
+                const uint32_t type = w0 & 0xFFu;
+                if (interMask) prepare(__ffs(interMask) - 1, buf ^ 1);
                 mbarWait(&sm.mbar[buf], (phaseBits >> buf) & 1u);
                 phaseBits ^= 1u << buf;
-            }
-            uint8_t *dstY = lbase + l * 256 + lane * 8, *dstC = cbase + l * 128 + lane * 4;
-            if (type == B200_MB_I_PCM) {
-                // h264bsdWriteMacroblock (image.c:81-144): 384 raw bytes, 256 Y then 64 Cb then 64 Cr
-                const uint8_t *src = sm.coef[buf];
-                *reinterpret_cast<uint2 *>(dstY) = *reinterpret_cast<const uint2 *>(src + lane * 8);
-                *reinterpret_cast<uint32_t *>(dstC) = *reinterpret_cast<const uint32_t *>(src + 256 + cp * 64 + cr * 8 + cc);
-                __syncwarp();
-                continue;
-            }
-            if (mask) residualShfl(sm, sm.coef[buf], mask, qpY, qpC, lane, p.errors);
-            uint2 pv = make_uint2(0, 0);   // this lane's 8 luma prediction samples
-            uint32_t pc = 0;               // and 4 chroma prediction samples
-            const int mby = row0 + l;
-            if constexpr (!kMulti) {
+                if (type == B200_MB_I_PCM) {
+                    // h264bsdWriteMacroblock (image.c:81-144): 384 raw bytes, 256 Y then 64 Cb then 64 Cr
+                    const uint8_t *src = sm.coef[buf];
+                    *reinterpret_cast<uint2 *>(lbase + l * 256 + lane * 8) = *reinterpret_cast<const uint2 *>(src + lane * 8);
+                    *reinterpret_cast<uint32_t *>(cbase + l * 128 + lane * 4) = *reinterpret_cast<const uint32_t *>(src + 256 + cp * 64 + cr * 8 + cc);
+                    __syncwarp();
+                    continue;
+                }
+                if (mask) residualShfl(sm, sm.coef[buf], mask, (w0 >> 8) & 0xFF, (w0 >> 16) & 0xFF, lane, p.errors);
                 const int cxf = (int)((geom >> 12) & 7u), cyf = (int)((geom >> 15) & 7u), xf = cxf & 3, yf = cyf & 3;
                 const int pitch = (int)(((geom >> 1) & 3u) + 1u) * 16, pitchC = (int)(((geom >> 4) & 1u) + 1u) * 16;
                 const uint8_t *G0 = sm.luma[buf] + ((geom >> 5) & 15u) + (yf ? 2 * pitch : 0) + (xf ? 2 : 0);
-                pv = lumaQpel8(G0, pitch, c8, r8, xf, yf);
-                pc = chromaPred4(sm.chroma[buf], pitchC, (int)((geom >> 9) & 7u), cp, cc, cr, cxf, cyf);
-            } else {
-                const uint32_t *rw = reinterpret_cast<const uint32_t *>(rec0 + (size_t)l * g.widthMbs);
-                const uint32_t subTypes = type >= B200_MB_P_8x8 ? (__ldg(rw + 3) >> 24) & 0xFFu : 0u;
-                if (type <= B200_MB_P_8x16 || subTypes == 0) {
-                    // Partitions that are at least 8 wide (16x8, 8x16, 8x8 sub-macroblocks): every lane's 8-sample luma span and
-                    // 4-sample chroma span lie inside ONE partition, so the lane only has to pick that partition's window,
-                    // vector and origin.  Two partitions are staged at a time (inter_prediction.c:361-482).
-                    const int rounds = type >= B200_MB_P_8x8 ? 2 : 1;
+                const uint2 pv = lumaQpel8(G0, pitch, c8, r8, xf, yf);
+                const uint32_t pc = chromaPred4(sm.chroma[buf], pitchC, (int)((geom >> 9) & 7u), cp, cc, cr, cxf, cyf);
+                finish(l, mask, pv, pc);
+                __syncwarp();
+            }
+
+            // ---- the copies have arrived: on to the current frame --------------------------------------------------------------
+            if (copyMask) {
+                mbarWait(&sm.mbarCopy, (phaseBits >> 2) & 1u);
+                phaseBits ^= 4u;
+                if (runLen) {
+                    bulkStore(lbase + lane * 256, sm.stage + lane * 256, 256u * (uint32_t)runLen);
+                    bulkStore(cbase + lane * 128, sm.stage + kStageMbs * 256 + lane * 128, 128u * (uint32_t)runLen);
+                    bulkCommit();
+                }
+            }
+        } else {
+            // ---- macroblocks with several partitions (inter_prediction.c:361-482), as a pipeline of ROUNDS: a round is two
+            // partitions that are at least 8 wide -- the two of a 16x8 / 8x16 macroblock, the upper or the lower two 8x8
+            // sub-macroblocks -- so that every lane's 8-sample luma span and 4-sample chroma span lie inside ONE of them and the
+            // lane only has to pick that partition's window, vector and origin.  The four windows of a round land in one of two
+            // buffer pairs (the second one lives in `stage`: this instance has no copies) on the pair's mbarrier, together with
+            // the macroblock's levels in its first round; the round after is staged before this one is waited for.
+            // A sub-macroblock with 8x4 / 4x8 / 4x4 partitions makes its macroblock one round without windows: its partitions
+            // are fetched one by one when its turn has come.
+            uint8_t *pred = sm.stage;
+            auto winL = [&](int pair, int w) -> uint8_t * { return pair ? sm.stage + 384 + w * kLumaBufBytes : sm.luma[w]; };
+            auto winC = [&](int pair, int w) -> uint8_t * { return pair ? sm.stage + 384 + 2 * kLumaBufBytes + w * kChromaBufBytes : sm.chroma[w]; };
+            // the staged round: macroblock, round, what every lane needs to compute it
+            int sL = 0, sRd = 0, sLast = 0;
+            uint32_t sW0 = 0, sMask = 0, sGeom = 0, sMvA = 0, sMvB = 0, sSub = 0;
+            bool sArmed = false;
+            int nl = interMask ? __ffs(interMask) - 1 : 0, nrd = 0;   // the round to stage next
+            bool more = interMask != 0, have = false;
+            int seq = 0, mbSeq = 0;
+            uint2 pv = make_uint2(0, 0);   // this lane's 8 luma prediction samples
+            uint32_t pc = 0;               // and 4 chroma prediction samples
 #pragma unroll 1
-                    for (int rd = 0; rd < rounds; rd++) {
-                        int blkA, blkB, pxB, pyA, pyB, pw, ph;
-                        if (type == B200_MB_P_16x8) { blkA = 0; blkB = 8; pxB = 0; pyA = 0; pyB = 8; pw = 16; ph = 8; }
-                        else if (type == B200_MB_P_8x16) { blkA = 0; blkB = 4; pxB = 8; pyA = 0; pyB = 0; pw = 8; ph = 16; }
-                        else { blkA = 8 * rd; blkB = 8 * rd + 4; pxB = 8; pyA = pyB = 8 * rd; pw = 8; ph = 8; }
-                        const uint32_t mvA = __ldg(rw + 8 + blkA), mvB = __ldg(rw + 8 + blkB);
-                        const int ax = (int)(int16_t)(mvA & 0xFFFFu), ay = (int)(int16_t)(mvA >> 16);
-                        const int bx = (int)(int16_t)(mvB & 0xFFFFu), by = (int)(int16_t)(mvB >> 16);
-                        const uint32_t geomA = issueWindow(buf, mbx * 16, mby * 16 + pyA, pw, ph, ax, ay,
-                                                           frameBase + ((refSlots >> (8 * (blkA >> 2))) & 0xFFu), 0, nullptr);
-                        const uint32_t geomB = issueWindow(buf ^ 1, mbx * 16 + pxB, mby * 16 + pyB, pw, ph, bx, by,
-                                                           frameBase + ((refSlots >> (8 * (blkB >> 2))) & 0xFFu), 0, nullptr);
-                        const bool inBL = type == B200_MB_P_16x8 ? r8 >= 8 : c8 == 8;
-                        const bool inBC = type == B200_MB_P_16x8 ? cr >= 4 : cc == 4;
-                        const bool actL = type < B200_MB_P_8x8 || (r8 >> 3) == rd, actC = type < B200_MB_P_8x8 || (cr >> 2) == rd;
-                        mbarWait(&sm.mbar[buf], (phaseBits >> buf) & 1u);
-                        mbarWait(&sm.mbar[buf ^ 1], (phaseBits >> (buf ^ 1)) & 1u);
-                        phaseBits ^= 3u;
-                        if (actL) {
-                            const uint32_t gm = inBL ? geomB : geomA;
-                            const int mvx = inBL ? bx : ax, mvy = inBL ? by : ay, xf = mvx & 3, yf = mvy & 3;
-                            const int pitch = (int)((gm >> 4) & 3u) * 16;
-                            const uint8_t *G0 = sm.luma[inBL ? buf ^ 1 : buf] + (gm & 15u) + (yf ? 2 * pitch : 0) + (xf ? 2 : 0);
-                            pv = lumaQpel8(G0, pitch, c8 - (inBL ? pxB : 0), r8 - (inBL ? pyB : pyA), xf, yf);
+            while (more || have) {
+                // the round staged in the previous turn is this turn's
+                const bool valid = have;
+                const int l = sL, rd = sRd, last = sLast, pair = (seq + 1) & 1, coefBuf = (mbSeq + 1) & 1;
+                const uint32_t w0 = sW0, mask = sMask, geomAB = sGeom, mvA = sMvA, mvB = sMvB, subTypes = sSub;
+                const bool armed = sArmed;
+                have = more;
+                if (more) {
+                    const int sp = seq & 1;
+                    seq++;
+                    sL = nl; sRd = nrd;
+                    sW0 = __shfl_sync(0xffffffffu, mW0, nl); sMask = __shfl_sync(0xffffffffu, mMask, nl);
+                    const uint32_t refs = __shfl_sync(0xffffffffu, mRef, nl), coefIndex = __shfl_sync(0xffffffffu, mCoef, nl);
+                    const uint32_t type = sW0 & 0xFFu;
+                    sSub = type >= B200_MB_P_8x8 ? __shfl_sync(0xffffffffu, mW3, nl) >> 24 : 0u;
+                    uint32_t coefBytes = 0;
+                    if (nrd == 0) { coefBytes = 32u * (uint32_t)__popc(sMask & 0x3FFFFFFu); mbSeq++; }
+                    const int cb = (mbSeq + 1) & 1;   // the macroblock's level buffer
+                    const int mby = row0 + nl;
+                    if (sSub == 0) {
+                        int qA, qB, pxB, pyA, pyB, pw, ph;
+                        if (type == B200_MB_P_16x8) { qA = 0; qB = 2; pxB = 0; pyA = 0; pyB = 8; pw = 16; ph = 8; }
+                        else if (type == B200_MB_P_8x16) { qA = 0; qB = 1; pxB = 8; pyA = 0; pyB = 0; pw = 8; ph = 16; }
+                        else { qA = 2 * nrd; qB = 2 * nrd + 1; pxB = 8; pyA = pyB = 8 * nrd; pw = 8; ph = 8; }
+                        sMvA = __shfl_sync(0xffffffffu, qA ? mMv2 : mMv, nl);
+                        sMvB = __shfl_sync(0xffffffffu, qB == 1 ? mMv1 : qB == 2 ? mMv2 : mMv3, nl);
+                        const WindowGeom wa = windowGeom(g.W, g.H, mbx * 16, mby * 16 + pyA, pw, ph, (int)(int16_t)(sMvA & 0xFFFFu), (int)(int16_t)(sMvA >> 16));
+                        const WindowGeom wb = windowGeom(g.W, g.H, mbx * 16 + pxB, mby * 16 + pyB, pw, ph, (int)(int16_t)(sMvB & 0xFFFFu), (int)(int16_t)(sMvB >> 16));
+                        sGeom = wa.geom | (wb.geom << 16);
+                        sArmed = true;
+                        sLast = type < B200_MB_P_8x8 || nrd == 1;
+                        if (lane == 0) {
+                            const int refA = (int)(frameBase + ((refs >> (8 * qA)) & 0xFFu)), refB = (int)(frameBase + ((refs >> (8 * qB)) & 0xFFu));
+                            fenceProxyAsync();
+                            mbarExpectTx(&sm.mbar[sp], wa.bytes + wb.bytes + coefBytes);
+                            tmaLoad4d(winL(sp, 0), &maps.luma[0][0] + wa.map, 0, wa.strip, wa.row, refA, &sm.mbar[sp]);
+                            tmaLoad4d(winC(sp, 0), &maps.chroma[0][0] + wa.mapC, 0, wa.stripC, wa.rowC, refA, &sm.mbar[sp]);
+                            tmaLoad4d(winL(sp, 1), &maps.luma[0][0] + wb.map, 0, wb.strip, wb.row, refB, &sm.mbar[sp]);
+                            tmaLoad4d(winC(sp, 1), &maps.chroma[0][0] + wb.mapC, 0, wb.stripC, wb.rowC, refB, &sm.mbar[sp]);
+                            if (coefBytes) bulkLoad(sm.coef[cb], job.coefs + (size_t)coefIndex * 16, coefBytes, &sm.mbar[sp]);
                         }
-                        if (actC) {
-                            const uint32_t gm = inBC ? geomB : geomA;
-                            const int mvx = inBC ? bx : ax, mvy = inBC ? by : ay;
-                            pc = chromaPred4(sm.chroma[inBC ? buf ^ 1 : buf], (int)((gm >> 12) & 3u) * 16, (int)((gm >> 8) & 7u), cp,
-                                             cc - (inBC ? (pxB >> 1) : 0), cr - ((inBC ? pyB : pyA) >> 1), mvx & 7, mvy & 7);
+                    } else {
+                        sGeom = refs;       // (the partitions' windows are fetched when the macroblock's turn has come)
+                        sArmed = coefBytes != 0;
+                        sLast = 1;
+                        if (lane == 0 && coefBytes) {
+                            fenceProxyAsync();
+                            mbarExpectTx(&sm.mbar[sp], coefBytes);
+                            bulkLoad(sm.coef[cb], job.coefs + (size_t)coefIndex * 16, coefBytes, &sm.mbar[sp]);
                         }
-                        __syncwarp();   // the windows are overwritten by the next round's (or the next macroblock's) loads
+                    }
+                    // the round after the one just staged
+                    if (!sLast) nrd = 1;
+                    else {
+                        interMask &= interMask - 1;
+                        more = interMask != 0;
+                        nl = more ? __ffs(interMask) - 1 : 0;
+                        nrd = 0;
+                    }
+                }
+                if (!valid) continue;
+                if (armed) {
+                    mbarWait(&sm.mbar[pair], (phaseBits >> pair) & 1u);
+                    phaseBits ^= 1u << pair;
+                }
+                const uint32_t type = w0 & 0xFFu;
+                const int mby = row0 + l;
+                if (rd == 0) {
+                    pv = make_uint2(0, 0);
+                    pc = 0;
+                    if (mask) residualShfl(sm, sm.coef[coefBuf], mask, (w0 >> 8) & 0xFF, (w0 >> 16) & 0xFF, lane, p.errors);
+                }
+                if (subTypes == 0) {
+                    int pxB, pyA, pyB;
+                    if (type == B200_MB_P_16x8) { pxB = 0; pyA = 0; pyB = 8; }
+                    else if (type == B200_MB_P_8x16) { pxB = 8; pyA = 0; pyB = 0; }
+                    else { pxB = 8; pyA = pyB = 8 * rd; }
+                    const bool inBL = type == B200_MB_P_16x8 ? r8 >= 8 : c8 == 8;
+                    const bool inBC = type == B200_MB_P_16x8 ? cr >= 4 : cc == 4;
+                    const bool actL = type < B200_MB_P_8x8 || (r8 >> 3) == rd, actC = type < B200_MB_P_8x8 || (cr >> 2) == rd;
+                    if (actL) {
+                        const uint32_t gm = inBL ? geomAB >> 16 : geomAB & 0xFFFFu, mv = inBL ? mvB : mvA;
+                        const int xf = (int)(mv & 3u), yf = (int)((mv >> 16) & 3u);
+                        const int pitch = (int)((gm >> 4) & 3u) * 16;
+                        const uint8_t *G0 = winL(pair, inBL ? 1 : 0) + (gm & 15u) + (yf ? 2 * pitch : 0) + (xf ? 2 : 0);
+                        pv = lumaQpel8(G0, pitch, c8 - (inBL ? pxB : 0), r8 - (inBL ? pyB : pyA), xf, yf);
+                    }
+                    if (actC) {
+                        const uint32_t gm = inBC ? geomAB >> 16 : geomAB & 0xFFFFu, mv = inBC ? mvB : mvA;
+                        pc = chromaPred4(winC(pair, inBC ? 1 : 0), (int)((gm >> 12) & 3u) * 16, (int)((gm >> 8) & 7u), cp,
+                                         cc - (inBC ? (pxB >> 1) : 0), cr - ((inBC ? pyB : pyA) >> 1), (int)(mv & 7u), (int)((mv >> 16) & 7u));
                     }
                 } else {
                     // sub-macroblocks with 8x4 / 4x8 / 4x4 partitions: one window per partition, sample by sample
+                    const uint32_t *rw = reinterpret_cast<const uint32_t *>(job.recs + (size_t)mby * g.widthMbs + mbx);
+                    const uint32_t refSlots = geomAB;
+                    uint8_t *wl = winL(pair, 0), *wc = winC(pair, 0);
 #pragma unroll 1
                     for (int pi = 0; pi < 16; pi++) {
                         int pw, ph;
@@ -799,17 +912,17 @@ passAKernelT(const ReconParams p, const __grid_constant__ PassAMaps maps) {
                         const int px = cBlkX[pi] * 4, py = cBlkY[pi] * 4;
                         const uint32_t mvw = __ldg(rw + 8 + pi);
                         const int mvx = (int)(int16_t)(mvw & 0xFFFFu), mvy = (int)(int16_t)(mvw >> 16);
-                        const uint32_t gm = issueWindow(buf, mbx * 16 + px, mby * 16 + py, pw, ph, mvx, mvy,
-                                                        frameBase + ((refSlots >> (8 * (pi >> 2))) & 0xFFu), 0, nullptr);
-                        mbarWait(&sm.mbar[buf], (phaseBits >> buf) & 1u);
-                        phaseBits ^= 1u << buf;
+                        const uint32_t gm = issueWindowFn(wl, wc, &sm.mbar[pair], &maps, g.W, g.H, mbx * 16 + px, mby * 16 + py, pw | (ph << 8), mvx, mvy,
+                                                          frameBase + ((refSlots >> (8 * (pi >> 2))) & 0xFFu), lane);
+                        mbarWait(&sm.mbar[pair], (phaseBits >> pair) & 1u);
+                        phaseBits ^= 1u << pair;
                         const int xf = mvx & 3, yf = mvy & 3, pitch = (int)((gm >> 4) & 3u) * 16;
-                        const uint8_t *G0 = sm.luma[buf] + (gm & 15u) + (yf ? 2 * pitch : 0) + (xf ? 2 : 0);
+                        const uint8_t *G0 = wl + (gm & 15u) + (yf ? 2 * pitch : 0) + (xf ? 2 : 0);
                         const int lw = 31 - __clz(pw);
 #pragma unroll 1
                         for (int q = lane; q < pw * ph; q += 32) {
                             const int x = q & (pw - 1), y = q >> lw;
-                            sm.pred[(py + y) * 16 + px + x] = (uint8_t)lumaQpel(G0, pitch, x, y, xf, yf);
+                            pred[(py + y) * 16 + px + x] = (uint8_t)lumaQpel(G0, pitch, x, y, xf, yf);
                         }
                         const int cw = pw >> 1, chh = ph >> 1, ncp = cw * chh, lcw = lw - 1;
                         const int cxf = mvx & 7, cyf = mvy & 7, pitchC = (int)((gm >> 12) & 3u) * 16, cxo = (int)((gm >> 8) & 7u);
@@ -819,36 +932,26 @@ passAKernelT(const ReconParams p, const __grid_constant__ PassAMaps maps) {
                             const int x = qq & (cw - 1), y = qq >> lcw;
                             auto S = [&](int sx, int sy) -> int {
                                 const int col = cxo + sx;
-                                return sm.chroma[buf][sy * pitchC + (col >> 3) * 16 + pl * 8 + (col & 7)];
+                                return wc[sy * pitchC + (col >> 3) * 16 + pl * 8 + (col & 7)];
                             };
                             // (a sample that meets a zero weight may lie outside the box: it is read, not used)
                             const int A = S(x, y), B = S(x + 1, y), Cc = S(x, y + 1), D = S(x + 1, y + 1);
-                            sm.pred[256 + pl * 64 + ((py >> 1) + y) * 8 + (px >> 1) + x] =
+                            pred[256 + pl * 64 + ((py >> 1) + y) * 8 + (px >> 1) + x] =
                                 (uint8_t)(((8 - cxf) * (8 - cyf) * A + cxf * (8 - cyf) * B + (8 - cxf) * cyf * Cc + cxf * cyf * D + 32) >> 6);
                         }
                         __syncwarp();
                     }
-                    pv = *reinterpret_cast<const uint2 *>(sm.pred + r8 * 16 + c8);
-                    pc = *reinterpret_cast<const uint32_t *>(sm.pred + 256 + cp * 64 + cr * 8 + cc);
+                    pv = *reinterpret_cast<const uint2 *>(pred + r8 * 16 + c8);
+                    pc = *reinterpret_cast<const uint32_t *>(pred + 256 + cp * 64 + cr * 8 + cc);
                 }
-                // (every path above ends with a warp barrier: both window buffers are free)
-                if (interMask) prepare(__ffs(interMask) - 1, buf ^ 1);
+                if (last) finish(l, mask, pv, pc);
+                __syncwarp();   // the pair's windows (and the residual) are free for the loads of the turn after next
             }
-            // add residual + clip + store (h264bsdWriteOutputBlocks, image.c:172-344)
-            if (mask) {
-                const uint4 ra = *reinterpret_cast<const uint4 *>(&sm.resY[r8][c8]), rb = *reinterpret_cast<const uint4 *>(&sm.resY[r8][c8 + 4]);
-                const uint4 rc = *reinterpret_cast<const uint4 *>(&sm.resC[cp][cr][cc]);
-                auto px = [](uint32_t w, int k) { return (int)((w >> (8 * k)) & 0xFF); };
-                pv = make_uint2(pack4sat(px(pv.x, 0) + (int)ra.x, px(pv.x, 1) + (int)ra.y, px(pv.x, 2) + (int)ra.z, px(pv.x, 3) + (int)ra.w),
-                                pack4sat(px(pv.y, 0) + (int)rb.x, px(pv.y, 1) + (int)rb.y, px(pv.y, 2) + (int)rb.z, px(pv.y, 3) + (int)rb.w));
-                pc = pack4sat(px(pc, 0) + (int)rc.x, px(pc, 1) + (int)rc.y, px(pc, 2) + (int)rc.z, px(pc, 3) + (int)rc.w);
-            }
-            *reinterpret_cast<uint2 *>(dstY) = pv;
-            *reinterpret_cast<uint32_t *>(dstC) = pc;
-            __syncwarp();
         }
-        chunk = __shfl_sync(0xffffffffu, nextChunk, 0);
+        chunk = nextChunk;
+        nextChunk = __shfl_sync(0xffffffffu, ticket2, 0);
     }
+    if (!kMulti) bulkWaitAll();   // this lane's last stores still read shared memory
 }
 
 // =====================================================================================================
@@ -862,10 +965,40 @@ passAKernelT(const ReconParams p, const __grid_constant__ PassAMaps maps) {
 // =====================================================================================================
 __global__ void __launch_bounds__(kReconWarps * 32, 5) reconIntraKernel(const ReconParams p) {
     __shared__ IntraWarpSmem smemAll[kReconWarps];
-    __shared__ uint32_t sI4Table[9 * 16];
+    // Intra4x4 tables, made once per CTA.  sI4Off[c][mode * 16 + sample]: gIntra4x4Table with the edge indices turned into byte
+    // offsets from the block's corner sample in the tile (left column (4 - i) * 24, corner 0, above row 1..8); c = 0 is for
+    // blocks whose above-right block is not available: above-row samples 4..7 fall back to sample 3 (intra_prediction.c:762-767).
+    // sI4Step[half][step]: the block a half-warp predicts in that step of the ten-step schedule, 31 = none, as
+    //   block | x4 << 5 | y4 << 7 | aboveRight << 9   (aboveRight: 0 no, 1 yes, 2 = the macroblock's B, 3 = its C neighbour)
+    __shared__ uint32_t sI4Off[2][9 * 16];
+    __shared__ uint32_t sI4Step[2][10];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const PoolGeom &g = p.g;
-    if (threadIdx.x < 9 * 16) sI4Table[threadIdx.x] = gIntra4x4Table[threadIdx.x];
+    for (int i = threadIdx.x; i < 2 * 9 * 16; i += blockDim.x) {
+        const int c = i / (9 * 16);
+        const uint32_t d = gIntra4x4Table[i - c * 9 * 16];
+        uint32_t o = d & 0xFF000000u;
+        for (int k = 0; k < 3; k++) {
+            const int e = (d >> (8 * k)) & 0xFF;
+            int off;
+            if (e <= 3) off = (4 - e) * 24;
+            else { off = e - 4; if (off > 4 && !c) off = 4; }
+            o |= (uint32_t)off << (8 * k);
+        }
+        sI4Off[c][i - c * 9 * 16] = o;
+    }
+    if (threadIdx.x < 20) {
+        const int hf = threadIdx.x / 10, st = threadIdx.x - hf * 10;
+        const int b = hf ? cI4StepB[st] : cI4StepA[st];
+        uint32_t v = 31;
+        if (b >= 0) {
+            const int bx = cBlkX[b], by = cBlkY[b];
+            // above-right block: the neighbouring macroblock's, or decoded earlier inside this one (intra_prediction.c:730-767)
+            const int ar = by == 0 ? (bx == 3 ? 3 : 2) : bx == 3 ? 0 : (cRasterToBlk[(by - 1) * 4 + bx + 1] < b ? 1 : 0);
+            v = (uint32_t)b | ((uint32_t)bx << 5) | ((uint32_t)by << 7) | ((uint32_t)ar << 9);
+        }
+        sI4Step[hf][st] = v;
+    }
     __syncthreads();
     IntraWarpSmem &sm = smemAll[warp];
     const int W = g.widthMbs;
@@ -939,6 +1072,9 @@ __global__ void __launch_bounds__(kReconWarps * 32, 5) reconIntraKernel(const Re
         // wait for the intra neighbours this macroblock reads (record byte 28: waitMask).  The left one is this warp's own
         // previous step; the row above has to be past the above-left (x), above (x + 1) or above-right (x + 2) macroblock
         const int waitMask = (misc >> 8) & 0xFF;
+        // Intra4x4: prediction modes of the sixteen blocks (record words 8..11), on their way while the row above is waited for
+        uint32_t modeWord = 0;
+        if (lane < 4 && h.mbType == B200_MB_I_4x4) modeWord = __ldg(reinterpret_cast<const uint32_t *>(rec) + 8 + lane);
         {
             const uint32_t need = (uint32_t)min(W, (waitMask & B200_MBF_AVAIL_C) ? mbx + 2 : (waitMask & B200_MBF_AVAIL_B) ? mbx + 1
                                                    : (waitMask & B200_MBF_AVAIL_D) ? mbx : 0);
@@ -947,6 +1083,7 @@ __global__ void __launch_bounds__(kReconWarps * 32, 5) reconIntraKernel(const Re
         }
         __syncwarp();
         // neighbouring pels (h264bsdGetNeighbourPels :545-614), straight from L2
+        if (lane < 4) reinterpret_cast<uint32_t *>(sm.stage)[lane] = modeWord;
         if (lane < 21) {
             const bool ok = lane == 0 ? avD : lane <= 16 ? avB : avC;
             sm.itY[0][lane] = ok ? __ldcg(lumaAt(cur, g, mbx * 16 - 1 + lane, mby * 16 - 1)) : 128;
@@ -964,43 +1101,34 @@ __global__ void __launch_bounds__(kReconWarps * 32, 5) reconIntraKernel(const Re
         __syncwarp();
 
         if (h.mbType == B200_MB_I_4x4) {
-            // h264bsdIntra4x4Prediction (:701-833): half-warp = block, lane = sample; edge samples straight from the tile
-            const uint32_t *modew = reinterpret_cast<const uint32_t *>(rec) + 8;
-            const int x = lane & 3, y = (lane >> 2) & 3;
+            // h264bsdIntra4x4Prediction (:701-833): half-warp = block, lane = sample; edge samples straight from the tile.  The
+            // sixteen prediction modes (record words 8..11) were fetched with the neighbouring pels and lie in sm.stage
+            const int smp = lane & 15, myOff = (1 + (smp >> 2)) * 24 + 1 + (smp & 3);   // this lane's sample from the block's corner
 #pragma unroll 1
             for (int st = 0; st < 10; st++) {
-                const int b = lane < 16 ? cI4StepA[st] : cI4StepB[st];
-                if (b >= 0) {
-                    const int bx = cBlkX[b], by = cBlkY[b];
-                    const int mode = (__ldg(modew + (b >> 2)) >> (8 * (b & 3))) & 0xFF;
-                    const bool bA = bx ? true : avA, bB = by ? true : avB;
-                    bool bC;   // above-right block available: decoded earlier (or the neighbouring macroblock's)
-                    if (by == 0) bC = (bx == 3) ? avC : avB;
-                    else if (bx == 3) bC = false;
-                    else bC = cRasterToBlk[(by - 1) * 4 + bx + 1] < b;
-                    const uint8_t *corner = &sm.itY[by * 4][bx * 4];   // E[4]; above row to its right, left column below it
-                    auto E = [&](int i) -> int {
-                        if (i <= 3) return corner[(4 - i) * 24];
-                        int k = i - 4;                         // 0 = corner, 1..8 = above row
-                        if (k > 4 && !bC) k = 4;
-                        return corner[k];
-                    };
+                const uint32_t si = sI4Step[lane >> 4][st];
+                const int b = si & 31;
+                if (b != 31) {
+                    const int bx = (si >> 5) & 3, by = (si >> 7) & 3, ar = (si >> 9) & 3;
+                    const int mode = sm.stage[b];
+                    uint8_t *corner = &sm.itY[by * 4][bx * 4];   // corner sample; above row to its right, left column below it
                     int v;
                     if (mode == 2) {
+                        const bool bA = bx ? true : avA, bB = by ? true : avB;
                         const int sa = corner[1] + corner[2] + corner[3] + corner[4];
                         const int sl = corner[24] + corner[48] + corner[72] + corner[96];
                         v = (bA && bB) ? (sa + sl + 4) >> 3 : bA ? (sl + 2) >> 2 : bB ? (sa + 2) >> 2 : 128;
                     } else {
-                        const uint32_t d = sI4Table[mode * 16 + y * 4 + x];
-                        const int kind = d >> 24, e0 = E(d & 0xFF);
-                        if (kind == 0) v = e0;
-                        else if (kind == 1) v = (e0 + E((d >> 8) & 0xFF) + 1) >> 1;
-                        else v = (e0 + 2 * E((d >> 8) & 0xFF) + E((d >> 16) & 0xFF) + 2) >> 2;
+                        const bool bC = ar == 1 || (ar == 2 && avB) || (ar == 3 && avC);
+                        const uint32_t d = sI4Off[bC ? 1 : 0][mode * 16 + smp];
+                        const int e0 = corner[d & 0xFF], e1 = corner[(d >> 8) & 0xFF], e2 = corner[(d >> 16) & 0xFF];
+                        const uint32_t kind = d >> 24;
+                        v = kind == 0 ? e0 : kind == 1 ? (e0 + e1 + 1) >> 1 : (e0 + 2 * e1 + e2 + 2) >> 2;
                     }
-                    if (h.mask) v = clip255(v + sm.res[b][y * 4 + x]);
+                    if (h.mask) v = clip255(v + sm.res[b][smp]);
                     // the sample lies inside the block, every edge sample outside it, and the two blocks of a step do not
                     // touch each other's edges: no barrier between the reads above and this write
-                    sm.itY[by * 4 + 1 + y][bx * 4 + 1 + x] = (uint8_t)v;
+                    corner[myOff] = (uint8_t)v;
                 }
                 __syncwarp();
             }
