@@ -83,6 +83,12 @@ __device__ __forceinline__ int dp4aUS(uint32_t pels, int taps, int acc) {
     asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(pels), "r"(taps), "r"(acc));
     return d;
 }
+// two-way dot product of signed 16-bit halves with signed bytes: acc + lo16(a) * byte0(b) + hi16(a) * byte1(b)
+__device__ __forceinline__ int dp2aLoSS(uint32_t a, int b, int acc) {
+    int d;
+    asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(acc));
+    return d;
+}
 // four ints saturated to bytes, p0 in the low byte: two cvt.pack (I2IP) instead of four clamps, shifts and ors
 __device__ __forceinline__ uint32_t pack4sat(int p0, int p1, int p2, int p3) {
     uint32_t hi, r;

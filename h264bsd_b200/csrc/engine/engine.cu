@@ -60,7 +60,7 @@ void Batch::destroy() {
     cudaFree(dBsWords_); cudaFree(dWork_); cudaFree(dPack_[0]); cudaFree(dPack_[1]);
     cudaFree(dConvertAll_); cudaFree(dFrameStage_); cudaFree(dMirror_);
     for (cudaEvent_t e : mirrorEv_) if (e) cudaEventDestroy(e);
-    cudaFree(pool_); cudaFree(dDoneRecon_); cudaFree(dDoneDeblock_); cudaFree(dCounters_);
+    cudaFree(pool_); cudaFree(dDoneRecon_); cudaFree(dDoneDeblock_); cudaFree(dCounters_); cudaFree(dMultiList_);
     cudaFree(dJobs_); cudaFree(dStage_[0]); cudaFree(dStage_[1]); cudaFree(dConvert_); cudaFree(dSlots_);
     if (hStage_[0]) cudaFreeHost(hStage_[0]);
     if (hStage_[1]) cudaFreeHost(hStage_[1]);
@@ -79,7 +79,7 @@ void Batch::destroy() {
 
 void Batch::resetState() {
     created_ = false; device_ = 0; numSms_ = 0; stream_ = nullptr; evA_ = evB_ = nullptr; g_ = PoolGeom{}; pool_ = nullptr;
-    dDoneRecon_ = dDoneDeblock_ = dCounters_ = dSlots_ = dBsWords_ = nullptr; dWork_ = nullptr;
+    dDoneRecon_ = dDoneDeblock_ = dCounters_ = dSlots_ = dBsWords_ = dMultiList_ = nullptr; dWork_ = nullptr;
     strengthBlocks_ = 0; serial_ = 0; passABlocks_ = deblockBlocks_ = intraBlocks_ = 0; chunkRows_ = 32; chunksPerCol_ = 1;
     syncEv_ = forkEv_ = joinEv_ = nullptr; jobsCap_ = 0; dConvertAll_ = nullptr; uploadStream_ = nullptr;
     fences_.clear(); fenceFree_.clear(); auxStream_ = nullptr; tapes_.clear(); dJobs_ = nullptr; jobsFilterAt_ = 0; numPics_ = 0;
@@ -141,10 +141,13 @@ bool Batch::create(int device, uint32_t nStreams, uint32_t widthMbs, uint32_t he
     CK(cudaMemsetAsync(dDoneDeblock_, 0, rowBytes, stream_));
     CK(cudaMalloc(&dBsWords_, sizeof(uint32_t) * 4 * (size_t)nStreams * g.nMbs));
     CK(cudaMalloc(&dWork_, (size_t)nStreams * g.nMbs));
-    // counters: [0] pass-B tickets, [1] filter tickets, [2] [3] tickets of the two pass-A instances (zeroed per picture);
-    // [4] IDCT range errors, [6..7] macroblocks with filter work (running totals)
-    CK(cudaMalloc(&dCounters_, sizeof(uint32_t) * 8));
-    CK(cudaMemsetAsync(dCounters_, 0, sizeof(uint32_t) * 8, stream_));
+    // counters: [0] pass-B tickets, [1] filter tickets, [2] [3] tickets of the two pass-A instances, [4] entries in the list of
+    // macroblocks with several partitions (zeroed per picture); [8] IDCT range errors, [10..11] macroblocks with filter work
+    // (running totals)
+    CK(cudaMalloc(&dCounters_, sizeof(uint32_t) * 16));
+    CK(cudaMemsetAsync(dCounters_, 0, sizeof(uint32_t) * 16, stream_));
+    if ((unsigned long long)nStreams * g.nMbs > 0xFFFFFFF0ull) return false;   // (list entries are stream * nMbs + address)
+    CK(cudaMalloc(&dMultiList_, sizeof(uint32_t) * (size_t)nStreams * g.nMbs));
     CK(cudaMalloc(&dSlots_, sizeof(uint32_t) * nStreams));
     serial_ = 0;
 
@@ -165,9 +168,9 @@ bool Batch::create(int device, uint32_t nStreams, uint32_t widthMbs, uint32_t he
                 if (!encodeStripMap(enc, &m->chroma[nx - 1][v], pool_ + g.offC, g, g.rowsC, nFrames, nx, v ? 9 : 8)) return false;
     }
     int occA = 1, occD = 0, occS = 0, occB = 0;
-    CK(cudaFuncSetAttribute(passAKernelT<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(PassAWarpSmem) * kPassAWarps)));
-    CK(cudaFuncSetAttribute(passAKernelT<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(PassAWarpSmem) * kPassAWarps)));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occA, passAKernelT<false>, kPassAWarps * 32, sizeof(PassAWarpSmem) * kPassAWarps));
+    CK(cudaFuncSetAttribute(passAKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(PassAWarpSmem) * kPassAWarps)));
+    CK(cudaFuncSetAttribute(passAMultiKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(PassAWarpSmem) * kPassAWarps)));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occA, passAKernel, kPassAWarps * 32, sizeof(PassAWarpSmem) * kPassAWarps));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occD, deblockKernel, kDeblockWarps * 32, 0));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, strengthKernel, kDeblockWarps * 32, 0));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occB, reconIntraKernel, kReconWarps * 32, 0));
@@ -402,7 +405,8 @@ bool Batch::launchPicture(const StreamJob *dJobs, const StreamJob *dJobsFilter, 
     ReconParams rp;
     if (recon) {
         rp.pool = pool_; rp.g = g_; rp.jobs = dJobs; rp.done = dDoneRecon_;
-        rp.ticket = dCounters_ + 0; rp.ticketA = dCounters_ + 2; rp.errors = dCounters_ + 4; rp.serial = serial_;
+        rp.ticket = dCounters_ + 0; rp.ticketA = dCounters_ + 2; rp.errors = dCounters_ + 8; rp.serial = serial_;
+        rp.multiCount = dCounters_ + 4; rp.multiList = dMultiList_;
         rp.chunkRows = chunkRows_;
         rp.chunksPerCol = chunksPerCol_;
         rp.totalChunks = chunksPerCol_ * (uint32_t)g_.widthMbs * (uint32_t)g_.nStreams;
@@ -413,7 +417,7 @@ bool Batch::launchPicture(const StreamJob *dJobs, const StreamJob *dJobsFilter, 
         dp.ticket = dCounters_ + 1; dp.serial = serial_;
         dp.totalTickets = (uint32_t)g_.heightMbs * (((uint32_t)g_.nStreams + 1u) / 2u);
         dp.bsWords = dBsWords_; dp.work = dWork_;
-        dp.workCount = reinterpret_cast<unsigned long long *>(dCounters_ + 6);
+        dp.workCount = reinterpret_cast<unsigned long long *>(dCounters_ + 10);
     }
     auto launchStrength = [&](cudaStream_t st) {
         const uint32_t chunks = ((uint32_t)g_.nMbs + kDeblockWarps * 32 - 1) / (kDeblockWarps * 32) * (uint32_t)g_.nStreams;
@@ -430,9 +434,9 @@ bool Batch::launchPicture(const StreamJob *dJobs, const StreamJob *dJobsFilter, 
         if (maxA) {     // (an IDR picture has nothing for pass A)
             const uint32_t ctas = (rp.totalChunks + kPassAWarps - 1) / kPassAWarps;
             const PassAMaps &maps = *reinterpret_cast<const PassAMaps *>(maps_);
-            passAKernelT<false><<<std::min<uint32_t>(ctas, (uint32_t)passABlocks_), kPassAWarps * 32, sizeof(PassAWarpSmem) * kPassAWarps, stream_>>>(rp, maps);
+            passAKernel<<<std::min<uint32_t>(ctas, (uint32_t)passABlocks_), kPassAWarps * 32, sizeof(PassAWarpSmem) * kPassAWarps, stream_>>>(rp, maps);
             mark(0);
-            passAKernelT<true><<<std::min<uint32_t>(ctas, (uint32_t)passABlocks_), kPassAWarps * 32, sizeof(PassAWarpSmem) * kPassAWarps, stream_>>>(rp, maps);
+            passAMultiKernel<<<std::min<uint32_t>(ctas, (uint32_t)passABlocks_), kPassAWarps * 32, sizeof(PassAWarpSmem) * kPassAWarps, stream_>>>(rp, maps);
             launches_ += 2;
             mark(5);
         }
@@ -470,7 +474,7 @@ bool Batch::launchPicture(const StreamJob *dJobs, const StreamJob *dJobsFilter, 
         launches_++;
         mark(2);
     }
-    CK(cudaMemsetAsync(dCounters_, 0, 4 * sizeof(uint32_t), stream_));
+    CK(cudaMemsetAsync(dCounters_, 0, 5 * sizeof(uint32_t), stream_));
     CK(cudaGetLastError());
     return true;
 }
@@ -841,7 +845,7 @@ uint64_t Batch::deblockWorkMbs() {
     if (!created_) return 0;
     cudaSetDevice(device_);
     if (auxStream_) cudaStreamSynchronize(auxStream_);
-    cudaMemcpyAsync(&v, dCounters_ + 6, sizeof v, cudaMemcpyDeviceToHost, stream_);
+    cudaMemcpyAsync(&v, dCounters_ + 10, sizeof v, cudaMemcpyDeviceToHost, stream_);
     cudaStreamSynchronize(stream_);
     return v;
 }
@@ -850,7 +854,7 @@ uint32_t Batch::idctErrors() {
     uint32_t v = 0;
     if (!created_) return 0;
     cudaSetDevice(device_);
-    cudaMemcpyAsync(&v, dCounters_ + 4, sizeof v, cudaMemcpyDeviceToHost, stream_);
+    cudaMemcpyAsync(&v, dCounters_ + 8, sizeof v, cudaMemcpyDeviceToHost, stream_);
     cudaStreamSynchronize(stream_);
     return v;
 }

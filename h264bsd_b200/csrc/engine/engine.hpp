@@ -93,7 +93,7 @@ private:
     PoolGeom g_{};
     uint8_t *pool_ = nullptr;
     CUtensorMap maps_[10];             // PassAMaps (recon_kernel.cuh): luma [nx 1..3][16 / 21 rows], chroma [nx 1..2][8 / 9 rows]
-    uint32_t *dDoneRecon_ = nullptr, *dDoneDeblock_ = nullptr, *dCounters_ = nullptr, *dSlots_ = nullptr, *dBsWords_ = nullptr;
+    uint32_t *dDoneRecon_ = nullptr, *dDoneDeblock_ = nullptr, *dCounters_ = nullptr, *dSlots_ = nullptr, *dBsWords_ = nullptr, *dMultiList_ = nullptr;
     uint8_t *dWork_ = nullptr;
     int strengthBlocks_ = 0;
     uint32_t serial_ = 0;

@@ -540,6 +540,52 @@ __device__ __noinline__ void residualShfl(PassAWarpSmem &sm, const uint8_t *cbuf
     __syncwarp();
 }
 
+// The centre positions (xf and yf both fractional, one of them a half: clause 8.4.2.2.1 "j" and its quarter-sample neighbours)
+// of a 16x16 partition, all lanes together: the 21 x 16 horizontal six-tap sums are computed ONCE (42 row halves over 32 lanes)
+// and shared through shared memory -- `scratch` = the residual arrays, not yet in use when the prediction is made -- instead of
+// six row halves per lane; the vertical six-tap sum over them is three two-way dot products per sample (dp2a over int16 pairs).
+// G0 = integer sample (0, 0) of the partition in the window.  Ends with all reads of `scratch` done by this lane only: the
+// caller puts a warp barrier before the residual overwrites it.
+__device__ __noinline__ uint2 lumaCentre8(int16_t *scratch, const uint8_t *G0, int pitch, int lane, int xf, int yf) {
+    int16_t (*H)[16] = reinterpret_cast<int16_t (*)[16]>(scratch);   // H[r] = sums of picture row r - 2; 21 rows, 672 bytes
+    const int r8 = lane >> 1, c8 = (lane & 1) * 8;
+#pragma unroll 1
+    for (int task = lane; task < 42; task += 32) {
+        const int hr = task >> 1, hc = (task & 1) * 8;
+        int hs[8];
+        hrow8(G0 + (hr - 2) * pitch + hc - 2, hs, 0);
+        *reinterpret_cast<uint4 *>(&H[hr][hc]) =
+            make_uint4(((uint32_t)hs[0] & 0xFFFFu) | ((uint32_t)hs[1] << 16), ((uint32_t)hs[2] & 0xFFFFu) | ((uint32_t)hs[3] << 16),
+                       ((uint32_t)hs[4] & 0xFFFFu) | ((uint32_t)hs[5] << 16), ((uint32_t)hs[6] & 0xFFFFu) | ((uint32_t)hs[7] << 16));
+    }
+    __syncwarp();
+    uint4 R[6];
+#pragma unroll
+    for (int t = 0; t < 6; t++) R[t] = *reinterpret_cast<const uint4 *>(&H[r8 + t][c8]);
+    int acc[8];
+    auto col2 = [&](uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4, uint32_t a5, int &lo, int &hi) {
+        // rows t, t + 1 of a column side by side: taps (1, -5), (20, 20), (-5, 1)
+        lo = dp2aLoSS(__byte_perm(a4, a5, 0x5410), 0x01FB, dp2aLoSS(__byte_perm(a2, a3, 0x5410), 0x1414, dp2aLoSS(__byte_perm(a0, a1, 0x5410), 0xFB01, 512)));
+        hi = dp2aLoSS(__byte_perm(a4, a5, 0x7632), 0x01FB, dp2aLoSS(__byte_perm(a2, a3, 0x7632), 0x1414, dp2aLoSS(__byte_perm(a0, a1, 0x7632), 0xFB01, 512)));
+    };
+    col2(R[0].x, R[1].x, R[2].x, R[3].x, R[4].x, R[5].x, acc[0], acc[1]);
+    col2(R[0].y, R[1].y, R[2].y, R[3].y, R[4].y, R[5].y, acc[2], acc[3]);
+    col2(R[0].z, R[1].z, R[2].z, R[3].z, R[4].z, R[5].z, acc[4], acc[5]);
+    col2(R[0].w, R[1].w, R[2].w, R[3].w, R[4].w, R[5].w, acc[6], acc[7]);
+    const uint2 j = pack8shift(acc, 10);
+    if (xf == 2 && yf == 2) return j;
+    if (xf == 2) {
+        const uint4 B = yf == 3 ? R[3] : R[2];   // the horizontal half-sample row next to j
+        int bs[8];
+        bs[0] = (int)(int16_t)(B.x & 0xFFFFu) + 16; bs[1] = ((int)B.x >> 16) + 16; bs[2] = (int)(int16_t)(B.y & 0xFFFFu) + 16; bs[3] = ((int)B.y >> 16) + 16;
+        bs[4] = (int)(int16_t)(B.z & 0xFFFFu) + 16; bs[5] = ((int)B.z >> 16) + 16; bs[6] = (int)(int16_t)(B.w & 0xFFFFu) + 16; bs[7] = ((int)B.w >> 16) + 16;
+        return avg8(j, pack8shift(bs, 5));
+    }
+    int hv[8];
+    vcol8(G0 + (r8 - 2) * pitch + c8 + (xf == 3 ? 1 : 0), pitch, hv, 16);
+    return avg8(j, pack8shift(hv, 5));
+}
+
 // window of a partition at picture position (px, py), size w x h, vector (mvx, mvy): clamp the origin into the bordered plane (a
 // window wholly outside the picture on an axis equals the window at the clamped origin because the border is a replication,
 // SURVEY 7.2) and pick the boxes.  geom = xo | nx << 4 | cxo << 8 | nxC << 12.
@@ -580,12 +626,46 @@ __device__ __noinline__ uint32_t issueWindowFn(uint8_t *dstL, uint8_t *dstC, uin
 #ifndef B200_PASSA_MINBLOCKS
 #define B200_PASSA_MINBLOCKS 5
 #endif
-// Two instances: kMulti = false takes the copies, the macroblocks with one partition (P_Skip / P_L0_16x16) and I_PCM -- 94 % of a
-// typical P picture's pass-A macroblocks, through the short code path; kMulti = true takes the macroblocks with several
-// partitions (16x8, 8x16, 8x8 and below).  Each scans the records itself; their macroblocks are disjoint.
-template <bool kMulti>
+
+// add residual + clip + store of a macroblock (h264bsdWriteOutputBlocks, image.c:172-344): lane = 8 luma samples (bytes 8 lane..
+// of the macroblock's 256) + 4 chroma samples (bytes 4 lane.. of its 128); a pel leaves its word and meets its residual in one
+// dot product
+__device__ __forceinline__ void addResidualStore(const PassAWarpSmem &sm, uint32_t mask, uint2 pv, uint32_t pc, uint8_t *mbY, uint8_t *mbC, int lane) {
+    if (mask) {
+        const uint4 ra = reinterpret_cast<const uint4 *>(&sm.resY[0][0])[lane];
+        const uint2 rc = *reinterpret_cast<const uint2 *>(&sm.resC[(lane >> 1) & 1][lane >> 2][(lane & 1) * 4]);
+        auto lo = [](uint32_t w) { return (int)(int16_t)(w & 0xFFFFu); };
+        auto hi = [](uint32_t w) { return (int)w >> 16; };
+        pv = make_uint2(pack4sat(dp4aUS(pv.x, 0x00000001, lo(ra.x)), dp4aUS(pv.x, 0x00000100, hi(ra.x)),
+                                 dp4aUS(pv.x, 0x00010000, lo(ra.y)), dp4aUS(pv.x, 0x01000000, hi(ra.y))),
+                        pack4sat(dp4aUS(pv.y, 0x00000001, lo(ra.z)), dp4aUS(pv.y, 0x00000100, hi(ra.z)),
+                                 dp4aUS(pv.y, 0x00010000, lo(ra.w)), dp4aUS(pv.y, 0x01000000, hi(ra.w))));
+        pc = pack4sat(dp4aUS(pc, 0x00000001, lo(rc.x)), dp4aUS(pc, 0x00000100, hi(rc.x)),
+                      dp4aUS(pc, 0x00010000, lo(rc.y)), dp4aUS(pc, 0x01000000, hi(rc.y)));
+    }
+    *reinterpret_cast<uint2 *>(mbY + lane * 8) = pv;
+    *reinterpret_cast<uint32_t *>(mbC + lane * 4) = pc;
+}
+
+// wait for bulk copies that take microseconds: back off instead of spinning in the issue slots the other warps compute with
+__device__ __forceinline__ void mbarWaitSleeping(uint64_t *bar, uint32_t parity) {
+    unsigned spins = 0;
+    unsigned long long t0 = 0;
+    while (!mbarTryWait(bar, parity)) {
+        __nanosleep(160);
+        if ((++spins & 255u) == 0) {
+            const unsigned long long now = globalTimerNs();
+            if (!t0) t0 = now;
+            else if (now - t0 > kWatchdogNs) { atomicAdd(&gWatchdog[1], 1u); break; }
+        }
+    }
+}
+
+// First instance: the copies, the macroblocks with one partition (P_Skip / P_L0_16x16) and I_PCM -- 94 % of a typical P picture's
+// pass-A macroblocks, through the short code path.  The macroblocks with several partitions (16x8, 8x16, 8x8 and below) are put
+// on a list (stream * nMbs + macroblock address, any order) for the second instance, passAMultiKernel.
 __global__ void __launch_bounds__(kPassAWarps * 32, B200_PASSA_MINBLOCKS)
-passAKernelT(const ReconParams p, const __grid_constant__ PassAMaps maps) {
+passAKernel(const ReconParams p, const __grid_constant__ PassAMaps maps) {
     extern __shared__ __align__(128) uint8_t interSmemRaw[];   // kPassAWarps x PassAWarpSmem (more than the 48 KB static limit)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const PoolGeom &g = p.g;
@@ -605,11 +685,10 @@ passAKernelT(const ReconParams p, const __grid_constant__ PassAMaps maps) {
     const int r8 = lane >> 1, c8 = (lane & 1) * 8;
     const int cr = lane >> 2, cp = (lane >> 1) & 1, cc = (lane & 1) * 4;
 
-    // Lane l fetches the words of record l of a chunk one chunk ahead: while a chunk is worked on, the records of the warp's next
-    // one are on their way (ticket -> job -> records is a chain of three dependent memory round trips otherwise).  First
-    // instance: head, reference slots, word 7 (concealment), first vector; second: head, reference slots, the first vector of
-    // each 8x8 quadrant
-    uint32_t fPos = 0, fS = 0, fW0 = 0, fMask = 0, fCoef = 0, fW3 = 0, fRef = 0, fW7 = 0, fMv = 0, fMv1 = 0, fMv2 = 0, fMv3 = 0;
+    // Lane l fetches the words of record l of a chunk -- head, reference slots, word 7 (concealment), first vector -- one chunk
+    // ahead: while a chunk is worked on, the records of the warp's next one are on their way (ticket -> job -> records is a
+    // chain of three dependent memory round trips otherwise)
+    uint32_t fPos = 0, fS = 0, fW0 = 0, fMask = 0, fCoef = 0, fRef = 0, fW7 = 0, fMv = 0;
     auto fetch = [&](uint32_t c) {
         if (c >= p.totalChunks) return;
         const uint32_t s = c / chunksPerStream, c2 = c - s * chunksPerStream;
@@ -620,10 +699,9 @@ passAKernelT(const ReconParams p, const __grid_constant__ PassAMaps maps) {
             const uint32_t *rw = reinterpret_cast<const uint32_t *>(p.jobs[s].recs + (size_t)(row0 + (uint32_t)lane) * g.widthMbs + mbx);
             const uint4 hw = __ldg(reinterpret_cast<const uint4 *>(rw));
             fRef = __ldg(rw + 4);
+            fW7 = __ldg(rw + 7);
             fMv = __ldg(rw + 8);
-            if (kMulti) { fMv1 = __ldg(rw + 12); fMv2 = __ldg(rw + 16); fMv3 = __ldg(rw + 20); }
-            else fW7 = __ldg(rw + 7);
-            fW0 = hw.x; fMask = hw.y; fCoef = hw.z; fW3 = hw.w;
+            fW0 = hw.x; fMask = hw.y; fCoef = hw.z;
         }
     };
 
@@ -631,327 +709,384 @@ passAKernelT(const ReconParams p, const __grid_constant__ PassAMaps maps) {
     uint32_t chunk = blockIdx.x * kPassAWarps + warp;
     fetch(chunk);
     uint32_t nextChunk = 0;
-    if (lane == 0) nextChunk = atomicAdd(p.ticketA + (kMulti ? 1 : 0), 1u) + nWarps;
+    if (lane == 0) nextChunk = atomicAdd(p.ticketA, 1u) + nWarps;
     nextChunk = __shfl_sync(0xffffffffu, nextChunk, 0);
     while (chunk < p.totalChunks) {
         uint32_t ticket2 = 0;
-        if (lane == 0) ticket2 = atomicAdd(p.ticketA + (kMulti ? 1 : 0), 1u) + nWarps;
+        if (lane == 0) ticket2 = atomicAdd(p.ticketA, 1u) + nWarps;
         const uint32_t s = fS;
         const int mbx = (int)(fPos & 0xFFFFu), row0 = (int)(fPos >> 16);
         const int n = min((int)p.chunkRows, g.heightMbs - row0);
-        const uint32_t mW0 = fW0, mMask = fMask, mCoef = fCoef, mW3 = fW3, mRef = fRef, mMv = fMv, w7 = fW7, mMv1 = fMv1, mMv2 = fMv2, mMv3 = fMv3;
+        const uint32_t mW0 = fW0, mMask = fMask, mCoef = fCoef, mRef = fRef, mMv = fMv, w7 = fW7;
         fetch(nextChunk);
         const StreamJob job = p.jobs[s];
         const uint32_t frameBase = s * (uint32_t)g.numSlots;
         uint8_t *cur = framePtr(p.pool, g, frameBase + job.curSlot);
         uint8_t *lbase = mbLuma(cur, g, mbx, row0), *cbase = mbChroma(cur, g, mbx, row0);   // macroblock l of the chunk: + 256 l / + 128 l
 
-        bool isCopy = false, isInter = false;
+        bool isCopy = false, isInter = false, isMulti = false;
         if (lane < n) {
             const uint32_t type = mW0 & 0xFFu;
             // a concealed macroblock carries the state the filter wants to see (Intra4x4); its pels are a copy of the reference
             // picture (no neighbours to wait for) or come from concealKernel (h264bsd_b200_tape.h)
             const bool concealed = ((mW0 >> 24) & B200_MBF_CONCEALED) && type == B200_MB_I_4x4;
-            if (kMulti) isInter = !concealed && type >= B200_MB_P_16x8 && type <= B200_MB_P_8x8REF0;
-            else if (concealed) isCopy = (w7 & 0xFFu) == 0;
+            if (concealed) isCopy = (w7 & 0xFFu) == 0;
             else if (type <= B200_MB_P_16x16 && mMask == 0 && mMv == 0) isCopy = true;
-            else isInter = type <= B200_MB_P_16x16 || type == B200_MB_I_PCM;
+            else if (type <= B200_MB_P_16x16 || type == B200_MB_I_PCM) isInter = true;
+            else isMulti = type <= B200_MB_P_8x8REF0;
         }
-        const uint32_t copyMask = kMulti ? 0u : __ballot_sync(0xffffffffu, isCopy);
+        const uint32_t copyMask = __ballot_sync(0xffffffffu, isCopy);
         uint32_t interMask = __ballot_sync(0xffffffffu, isInter);
+        const uint32_t multiMask = __ballot_sync(0xffffffffu, isMulti);
+        if (multiMask) {
+            uint32_t at = 0;
+            if (lane == 0) at = atomicAdd(p.multiCount, (uint32_t)__popc(multiMask));
+            at = __shfl_sync(0xffffffffu, at, 0);
+            if (isMulti) p.multiList[at + (uint32_t)__popc(multiMask & ((1u << lane) - 1u))] = s * (uint32_t)g.nMbs + (uint32_t)((row0 + lane) * g.widthMbs + mbx);
+        }
 
-        // add residual + clip + store of macroblock l of the chunk (h264bsdWriteOutputBlocks, image.c:172-344): a pel leaves its
-        // word and meets its residual in one dot product
-        auto finish = [&](int l, uint32_t mask, uint2 pv, uint32_t pc) {
-            if (mask) {
-                const uint4 ra = *reinterpret_cast<const uint4 *>(&sm.resY[r8][c8]);
-                const uint2 rc = *reinterpret_cast<const uint2 *>(&sm.resC[cp][cr][cc]);
-                auto lo = [](uint32_t w) { return (int)(int16_t)(w & 0xFFFFu); };
-                auto hi = [](uint32_t w) { return (int)w >> 16; };
-                pv = make_uint2(pack4sat(dp4aUS(pv.x, 0x00000001, lo(ra.x)), dp4aUS(pv.x, 0x00000100, hi(ra.x)),
-                                         dp4aUS(pv.x, 0x00010000, lo(ra.y)), dp4aUS(pv.x, 0x01000000, hi(ra.y))),
-                                pack4sat(dp4aUS(pv.y, 0x00000001, lo(ra.z)), dp4aUS(pv.y, 0x00000100, hi(ra.z)),
-                                         dp4aUS(pv.y, 0x00010000, lo(ra.w)), dp4aUS(pv.y, 0x01000000, hi(ra.w))));
-                pc = pack4sat(dp4aUS(pc, 0x00000001, lo(rc.x)), dp4aUS(pc, 0x00000100, hi(rc.x)),
-                              dp4aUS(pc, 0x00010000, lo(rc.y)), dp4aUS(pc, 0x01000000, hi(rc.y)));
+        // ---- copies: every run of vertically adjacent copies with the same reference frame is 256 n contiguous bytes of luma and
+        // 128 n of chroma in the strip layout.  The lane of a run's first macroblock sends them through the staging buffer with
+        // bulk copies -- no registers, no issue slots, and the inter macroblocks below are computed while they fly
+        int runLen = 0;
+        bulkWaitRead<0>();   // the staging buffer is free again once this lane's stores of the previous chunk have read it ...
+        __syncwarp();        // ... and every other lane's
+        if (copyMask) {
+            // where the reference frame of this lane's macroblock lies relative to the current frame, in 256-byte units (a frame
+            // stride is a multiple of 256)
+            const int myDelta = ((int)(mRef & 0xFFu) - (int)job.curSlot) * (int)(g.frameStride >> 8);
+            const int prevDelta = __shfl_up_sync(0xffffffffu, myDelta, 1);
+            const bool cont = isCopy && lane > 0 && ((copyMask >> (lane - 1)) & 1u) && prevDelta == myDelta;
+            const uint32_t contMask = __ballot_sync(0xffffffffu, cont);
+            if (isCopy && !cont) runLen = __ffs(~((contMask >> lane) >> 1));   // 1 + the continuations that follow
+            if (lane == 0) mbarExpectTx(&sm.mbarCopy, 384u * (uint32_t)__popc(copyMask));
+            __syncwarp();
+            if (runLen) {
+                const long long delta = (long long)myDelta * 256;
+                bulkLoad(sm.stage + lane * 256, lbase + lane * 256 + delta, 256u * (uint32_t)runLen, &sm.mbarCopy);
+                bulkLoad(sm.stage + kStageMbs * 256 + lane * 128, cbase + lane * 128 + delta, 128u * (uint32_t)runLen, &sm.mbarCopy);
             }
-            *reinterpret_cast<uint2 *>(lbase + l * 256 + lane * 8) = pv;
-            *reinterpret_cast<uint32_t *>(cbase + l * 128 + lane * 4) = pc;
+        }
+
+        // Every lane works out where the windows of ITS macroblock lie, all macroblocks of the chunk at once instead of one after
+        // the other when their turn comes.
+        //   gX = luma strip | chroma strip << 16     gY = luma row | chroma row << 16
+        //   gM = luma map (3 bits) | chroma map << 3 (2) | xo << 5 (4) | cxo << 9 (3) | mvx & 7 << 12 | mvy & 7 << 15 | window bytes << 18
+        uint32_t gX = 0, gY = 0, gM = 0;
+        if (isInter && (mW0 & 0xFFu) <= B200_MB_P_16x16) {
+            const int mvx = (int)(int16_t)(mMv & 0xFFFFu), mvy = (int)(int16_t)(mMv >> 16);
+            const WindowGeom wg = windowGeom(g.W, g.H, mbx * 16, (row0 + lane) * 16, 16, 16, mvx, mvy);
+            gX = (uint32_t)wg.strip | ((uint32_t)wg.stripC << 16);
+            gY = (uint32_t)wg.row | ((uint32_t)wg.rowC << 16);
+            gM = (uint32_t)wg.map | ((uint32_t)wg.mapC << 3) | ((wg.geom & 15u) << 5) | (((wg.geom >> 8) & 7u) << 9) |
+                 ((uint32_t)(mvx & 7) << 12) | ((uint32_t)(mvy & 7) << 15) | (wg.bytes << 18);
+        }
+
+        // ---- what is staged for the macroblock whose turn comes next ----------------------------------------------------
+        uint32_t nW0 = 0, nMask = 0, nGeom = 0;
+        int nL = 0;
+        // stage macroblock l of the chunk into buffer `buf`: its levels and its windows.  The lane that holds the record issues
+        // the loads; the others learn what they need to compute with
+        auto prepare = [&](int l, int buf) {
+            nL = l;
+            nW0 = __shfl_sync(0xffffffffu, mW0, l); nMask = __shfl_sync(0xffffffffu, mMask, l);
+            nGeom = __shfl_sync(0xffffffffu, gM, l);
+            if (lane == l) {
+                const uint32_t type = mW0 & 0xFFu;
+                const uint32_t coefBytes = type == B200_MB_I_PCM ? 384u : 32u * (uint32_t)__popc(mMask & 0x3FFFFFFu);
+                fenceProxyAsync();
+                mbarExpectTx(&sm.mbar[buf], (gM >> 18) + coefBytes);
+                if (type != B200_MB_I_PCM) {
+                    const int ref = (int)(frameBase + (mRef & 0xFFu));
+                    tmaLoad4d(sm.luma[buf], &maps.luma[0][0] + (gM & 7u), 0, (int)(gX & 0xFFFFu), (int)(gY & 0xFFFFu), ref, &sm.mbar[buf]);
+                    tmaLoad4d(sm.chroma[buf], &maps.chroma[0][0] + ((gM >> 3) & 3u), 0, (int)(gX >> 16), (int)(gY >> 16), ref, &sm.mbar[buf]);
+                }
+                if (coefBytes) bulkLoad(sm.coef[buf], job.coefs + (size_t)mCoef * 16, coefBytes, &sm.mbar[buf]);
+            }
         };
+        if (interMask) prepare(__ffs(interMask) - 1, 0);
 
-        if constexpr (!kMulti) {
-            // ---- copies: every run of vertically adjacent copies with the same reference frame is 256 n contiguous bytes of
-            // luma and 128 n of chroma in the strip layout.  The lane of a run's first macroblock sends them through the staging
-            // buffer with bulk copies -- no registers, no issue slots, and the inter macroblocks below are computed while they fly
-            int runLen = 0;
-            bulkWaitRead<0>();   // the staging buffer is free again once this lane's stores of the previous chunk have read it ...
-            __syncwarp();        // ... and every other lane's
-            if (copyMask) {
-                // where the reference frame of this lane's macroblock lies relative to the current frame, in 256-byte units (a
-                // frame stride is a multiple of 256)
-                const int myDelta = ((int)(mRef & 0xFFu) - (int)job.curSlot) * (int)(g.frameStride >> 8);
-                const int prevDelta = __shfl_up_sync(0xffffffffu, myDelta, 1);
-                const bool cont = isCopy && lane > 0 && ((copyMask >> (lane - 1)) & 1u) && prevDelta == myDelta;
-                const uint32_t contMask = __ballot_sync(0xffffffffu, cont);
-                if (isCopy && !cont) runLen = __ffs(~((contMask >> lane) >> 1));   // 1 + the continuations that follow
-                if (lane == 0) mbarExpectTx(&sm.mbarCopy, 384u * (uint32_t)__popc(copyMask));
+        // ---- inter macroblocks, one after the other: the next one is staged while this one is computed --------------------------
+        int it = 0;
+#pragma unroll 1
+        while (interMask) {
+            interMask &= interMask - 1;
+            const int buf = it & 1;
+            it++;
+            const int l = nL;
+            const uint32_t w0 = nW0, mask = nMask, geom = nGeom;
+            const uint32_t type = w0 & 0xFFu;
+            if (interMask) prepare(__ffs(interMask) - 1, buf ^ 1);
+            mbarWait(&sm.mbar[buf], (phaseBits >> buf) & 1u);
+            phaseBits ^= 1u << buf;
+            if (type == B200_MB_I_PCM) {
+                // h264bsdWriteMacroblock (image.c:81-144): 384 raw bytes, 256 Y then 64 Cb then 64 Cr
+                const uint8_t *src = sm.coef[buf];
+                *reinterpret_cast<uint2 *>(lbase + l * 256 + lane * 8) = *reinterpret_cast<const uint2 *>(src + lane * 8);
+                *reinterpret_cast<uint32_t *>(cbase + l * 128 + lane * 4) = *reinterpret_cast<const uint32_t *>(src + 256 + cp * 64 + cr * 8 + cc);
                 __syncwarp();
-                if (runLen) {
-                    const long long delta = (long long)myDelta * 256;
-                    bulkLoad(sm.stage + lane * 256, lbase + lane * 256 + delta, 256u * (uint32_t)runLen, &sm.mbarCopy);
-                    bulkLoad(sm.stage + kStageMbs * 256 + lane * 128, cbase + lane * 128 + delta, 128u * (uint32_t)runLen, &sm.mbarCopy);
-                }
+                continue;
             }
-
-            // Every lane works out where the windows of ITS macroblock lie (one partition: P_Skip / P_L0_16x16), all macroblocks
-            // of the chunk at once instead of one after the other when their turn comes.
-            //   gX = luma strip | chroma strip << 16     gY = luma row | chroma row << 16
-            //   gM = luma map (3 bits) | chroma map << 3 (2) | xo << 5 (4) | cxo << 9 (3) | mvx & 7 << 12 | mvy & 7 << 15 | window bytes << 18
-            uint32_t gX = 0, gY = 0, gM = 0;
-            if (isInter && (mW0 & 0xFFu) <= B200_MB_P_16x16) {
-                const int mvx = (int)(int16_t)(mMv & 0xFFFFu), mvy = (int)(int16_t)(mMv >> 16);
-                const WindowGeom wg = windowGeom(g.W, g.H, mbx * 16, (row0 + lane) * 16, 16, 16, mvx, mvy);
-                gX = (uint32_t)wg.strip | ((uint32_t)wg.stripC << 16);
-                gY = (uint32_t)wg.row | ((uint32_t)wg.rowC << 16);
-                gM = (uint32_t)wg.map | ((uint32_t)wg.mapC << 3) | ((wg.geom & 15u) << 5) | (((wg.geom >> 8) & 7u) << 9) |
-                     ((uint32_t)(mvx & 7) << 12) | ((uint32_t)(mvy & 7) << 15) | (wg.bytes << 18);
-            }
-
-            // ---- what is staged for the macroblock whose turn comes next ------------------------------------------------
-            uint32_t nW0 = 0, nMask = 0, nGeom = 0;
-            int nL = 0;
-            // stage macroblock l of the chunk into buffer `buf`: its levels and its windows.  The lane that holds the record
-            // issues the loads; the others learn what they need to compute with
-            auto prepare = [&](int l, int buf) {
-                nL = l;
-                nW0 = __shfl_sync(0xffffffffu, mW0, l); nMask = __shfl_sync(0xffffffffu, mMask, l);
-                nGeom = __shfl_sync(0xffffffffu, gM, l);
-                if (lane == l) {
-                    const uint32_t type = mW0 & 0xFFu;
-                    const uint32_t coefBytes = type == B200_MB_I_PCM ? 384u : 32u * (uint32_t)__popc(mMask & 0x3FFFFFFu);
-                    fenceProxyAsync();
-                    mbarExpectTx(&sm.mbar[buf], (gM >> 18) + coefBytes);
-                    if (type != B200_MB_I_PCM) {
-                        const int ref = (int)(frameBase + (mRef & 0xFFu));
-                        tmaLoad4d(sm.luma[buf], &maps.luma[0][0] + (gM & 7u), 0, (int)(gX & 0xFFFFu), (int)(gY & 0xFFFFu), ref, &sm.mbar[buf]);
-                        tmaLoad4d(sm.chroma[buf], &maps.chroma[0][0] + ((gM >> 3) & 3u), 0, (int)(gX >> 16), (int)(gY >> 16), ref, &sm.mbar[buf]);
-                    }
-                    if (coefBytes) bulkLoad(sm.coef[buf], job.coefs + (size_t)mCoef * 16, coefBytes, &sm.mbar[buf]);
-                }
-            };
-            if (interMask) prepare(__ffs(interMask) - 1, 0);
-
-            // ---- inter macroblocks, one after the other: the next one is staged while this one is computed ----------------------
-            int it = 0;
-#pragma unroll 1
-            while (interMask) {
-                interMask &= interMask - 1;
-                const int buf = it & 1;
-                it++;
-                const int l = nL;
-                const uint32_t w0 = nW0, mask = nMask, geom = nGeom;
-                const uint32_t type = w0 & 0xFFu;
-                if (interMask) prepare(__ffs(interMask) - 1, buf ^ 1);
-                mbarWait(&sm.mbar[buf], (phaseBits >> buf) & 1u);
-                phaseBits ^= 1u << buf;
-                if (type == B200_MB_I_PCM) {
-                    // h264bsdWriteMacroblock (image.c:81-144): 384 raw bytes, 256 Y then 64 Cb then 64 Cr
-                    const uint8_t *src = sm.coef[buf];
-                    *reinterpret_cast<uint2 *>(lbase + l * 256 + lane * 8) = *reinterpret_cast<const uint2 *>(src + lane * 8);
-                    *reinterpret_cast<uint32_t *>(cbase + l * 128 + lane * 4) = *reinterpret_cast<const uint32_t *>(src + 256 + cp * 64 + cr * 8 + cc);
-                    __syncwarp();
-                    continue;
-                }
-                if (mask) residualShfl(sm, sm.coef[buf], mask, (w0 >> 8) & 0xFF, (w0 >> 16) & 0xFF, lane, p.errors);
-                const int cxf = (int)((geom >> 12) & 7u), cyf = (int)((geom >> 15) & 7u), xf = cxf & 3, yf = cyf & 3;
-                const int pitch = (int)(((geom >> 1) & 3u) + 1u) * 16, pitchC = (int)(((geom >> 4) & 1u) + 1u) * 16;
-                const uint8_t *G0 = sm.luma[buf] + ((geom >> 5) & 15u) + (yf ? 2 * pitch : 0) + (xf ? 2 : 0);
-                const uint2 pv = lumaQpel8(G0, pitch, c8, r8, xf, yf);
-                const uint32_t pc = chromaPred4(sm.chroma[buf], pitchC, (int)((geom >> 9) & 7u), cp, cc, cr, cxf, cyf);
-                finish(l, mask, pv, pc);
+            // prediction first: the centre positions borrow the residual arrays
+            const int cxf = (int)((geom >> 12) & 7u), cyf = (int)((geom >> 15) & 7u), xf = cxf & 3, yf = cyf & 3;
+            const int pitch = (int)(((geom >> 1) & 3u) + 1u) * 16, pitchC = (int)(((geom >> 4) & 1u) + 1u) * 16;
+            const uint8_t *G0 = sm.luma[buf] + ((geom >> 5) & 15u) + (yf ? 2 * pitch : 0) + (xf ? 2 : 0);
+            const bool centre = (xf == 2 || yf == 2) && xf != 0 && yf != 0;
+            const uint2 pv = centre ? lumaCentre8(&sm.resY[0][0], G0, pitch, lane, xf, yf) : lumaQpel8(G0, pitch, c8, r8, xf, yf);
+            const uint32_t pc = chromaPred4(sm.chroma[buf], pitchC, (int)((geom >> 9) & 7u), cp, cc, cr, cxf, cyf);
+            if (mask) {
                 __syncwarp();
+                residualShfl(sm, sm.coef[buf], mask, (w0 >> 8) & 0xFF, (w0 >> 16) & 0xFF, lane, p.errors);
             }
+            addResidualStore(sm, mask, pv, pc, lbase + l * 256, cbase + l * 128, lane);
+            __syncwarp();
+        }
 
-            // ---- the copies have arrived: on to the current frame --------------------------------------------------------------
-            if (copyMask) {
-                mbarWait(&sm.mbarCopy, (phaseBits >> 2) & 1u);
-                phaseBits ^= 4u;
-                if (runLen) {
-                    bulkStore(lbase + lane * 256, sm.stage + lane * 256, 256u * (uint32_t)runLen);
-                    bulkStore(cbase + lane * 128, sm.stage + kStageMbs * 256 + lane * 128, 128u * (uint32_t)runLen);
-                    bulkCommit();
-                }
-            }
-        } else {
-            // ---- macroblocks with several partitions (inter_prediction.c:361-482), as a pipeline of ROUNDS: a round is two
-            // partitions that are at least 8 wide -- the two of a 16x8 / 8x16 macroblock, the upper or the lower two 8x8
-            // sub-macroblocks -- so that every lane's 8-sample luma span and 4-sample chroma span lie inside ONE of them and the
-            // lane only has to pick that partition's window, vector and origin.  The four windows of a round land in one of two
-            // buffer pairs (the second one lives in `stage`: this instance has no copies) on the pair's mbarrier, together with
-            // the macroblock's levels in its first round; the round after is staged before this one is waited for.
-            // A sub-macroblock with 8x4 / 4x8 / 4x4 partitions makes its macroblock one round without windows: its partitions
-            // are fetched one by one when its turn has come.
-            uint8_t *pred = sm.stage;
-            auto winL = [&](int pair, int w) -> uint8_t * { return pair ? sm.stage + 384 + w * kLumaBufBytes : sm.luma[w]; };
-            auto winC = [&](int pair, int w) -> uint8_t * { return pair ? sm.stage + 384 + 2 * kLumaBufBytes + w * kChromaBufBytes : sm.chroma[w]; };
-            // the staged round: macroblock, round, what every lane needs to compute it
-            int sL = 0, sRd = 0, sLast = 0;
-            uint32_t sW0 = 0, sMask = 0, sGeom = 0, sMvA = 0, sMvB = 0, sSub = 0;
-            bool sArmed = false;
-            int nl = interMask ? __ffs(interMask) - 1 : 0, nrd = 0;   // the round to stage next
-            bool more = interMask != 0, have = false;
-            int seq = 0, mbSeq = 0;
-            uint2 pv = make_uint2(0, 0);   // this lane's 8 luma prediction samples
-            uint32_t pc = 0;               // and 4 chroma prediction samples
-#pragma unroll 1
-            while (more || have) {
-                // the round staged in the previous turn is this turn's
-                const bool valid = have;
-                const int l = sL, rd = sRd, last = sLast, pair = (seq + 1) & 1, coefBuf = (mbSeq + 1) & 1;
-                const uint32_t w0 = sW0, mask = sMask, geomAB = sGeom, mvA = sMvA, mvB = sMvB, subTypes = sSub;
-                const bool armed = sArmed;
-                have = more;
-                if (more) {
-                    const int sp = seq & 1;
-                    seq++;
-                    sL = nl; sRd = nrd;
-                    sW0 = __shfl_sync(0xffffffffu, mW0, nl); sMask = __shfl_sync(0xffffffffu, mMask, nl);
-                    const uint32_t refs = __shfl_sync(0xffffffffu, mRef, nl), coefIndex = __shfl_sync(0xffffffffu, mCoef, nl);
-                    const uint32_t type = sW0 & 0xFFu;
-                    sSub = type >= B200_MB_P_8x8 ? __shfl_sync(0xffffffffu, mW3, nl) >> 24 : 0u;
-                    uint32_t coefBytes = 0;
-                    if (nrd == 0) { coefBytes = 32u * (uint32_t)__popc(sMask & 0x3FFFFFFu); mbSeq++; }
-                    const int cb = (mbSeq + 1) & 1;   // the macroblock's level buffer
-                    const int mby = row0 + nl;
-                    if (sSub == 0) {
-                        int qA, qB, pxB, pyA, pyB, pw, ph;
-                        if (type == B200_MB_P_16x8) { qA = 0; qB = 2; pxB = 0; pyA = 0; pyB = 8; pw = 16; ph = 8; }
-                        else if (type == B200_MB_P_8x16) { qA = 0; qB = 1; pxB = 8; pyA = 0; pyB = 0; pw = 8; ph = 16; }
-                        else { qA = 2 * nrd; qB = 2 * nrd + 1; pxB = 8; pyA = pyB = 8 * nrd; pw = 8; ph = 8; }
-                        sMvA = __shfl_sync(0xffffffffu, qA ? mMv2 : mMv, nl);
-                        sMvB = __shfl_sync(0xffffffffu, qB == 1 ? mMv1 : qB == 2 ? mMv2 : mMv3, nl);
-                        const WindowGeom wa = windowGeom(g.W, g.H, mbx * 16, mby * 16 + pyA, pw, ph, (int)(int16_t)(sMvA & 0xFFFFu), (int)(int16_t)(sMvA >> 16));
-                        const WindowGeom wb = windowGeom(g.W, g.H, mbx * 16 + pxB, mby * 16 + pyB, pw, ph, (int)(int16_t)(sMvB & 0xFFFFu), (int)(int16_t)(sMvB >> 16));
-                        sGeom = wa.geom | (wb.geom << 16);
-                        sArmed = true;
-                        sLast = type < B200_MB_P_8x8 || nrd == 1;
-                        if (lane == 0) {
-                            const int refA = (int)(frameBase + ((refs >> (8 * qA)) & 0xFFu)), refB = (int)(frameBase + ((refs >> (8 * qB)) & 0xFFu));
-                            fenceProxyAsync();
-                            mbarExpectTx(&sm.mbar[sp], wa.bytes + wb.bytes + coefBytes);
-                            tmaLoad4d(winL(sp, 0), &maps.luma[0][0] + wa.map, 0, wa.strip, wa.row, refA, &sm.mbar[sp]);
-                            tmaLoad4d(winC(sp, 0), &maps.chroma[0][0] + wa.mapC, 0, wa.stripC, wa.rowC, refA, &sm.mbar[sp]);
-                            tmaLoad4d(winL(sp, 1), &maps.luma[0][0] + wb.map, 0, wb.strip, wb.row, refB, &sm.mbar[sp]);
-                            tmaLoad4d(winC(sp, 1), &maps.chroma[0][0] + wb.mapC, 0, wb.stripC, wb.rowC, refB, &sm.mbar[sp]);
-                            if (coefBytes) bulkLoad(sm.coef[cb], job.coefs + (size_t)coefIndex * 16, coefBytes, &sm.mbar[sp]);
-                        }
-                    } else {
-                        sGeom = refs;       // (the partitions' windows are fetched when the macroblock's turn has come)
-                        sArmed = coefBytes != 0;
-                        sLast = 1;
-                        if (lane == 0 && coefBytes) {
-                            fenceProxyAsync();
-                            mbarExpectTx(&sm.mbar[sp], coefBytes);
-                            bulkLoad(sm.coef[cb], job.coefs + (size_t)coefIndex * 16, coefBytes, &sm.mbar[sp]);
-                        }
-                    }
-                    // the round after the one just staged
-                    if (!sLast) nrd = 1;
-                    else {
-                        interMask &= interMask - 1;
-                        more = interMask != 0;
-                        nl = more ? __ffs(interMask) - 1 : 0;
-                        nrd = 0;
-                    }
-                }
-                if (!valid) continue;
-                if (armed) {
-                    mbarWait(&sm.mbar[pair], (phaseBits >> pair) & 1u);
-                    phaseBits ^= 1u << pair;
-                }
-                const uint32_t type = w0 & 0xFFu;
-                const int mby = row0 + l;
-                if (rd == 0) {
-                    pv = make_uint2(0, 0);
-                    pc = 0;
-                    if (mask) residualShfl(sm, sm.coef[coefBuf], mask, (w0 >> 8) & 0xFF, (w0 >> 16) & 0xFF, lane, p.errors);
-                }
-                if (subTypes == 0) {
-                    int pxB, pyA, pyB;
-                    if (type == B200_MB_P_16x8) { pxB = 0; pyA = 0; pyB = 8; }
-                    else if (type == B200_MB_P_8x16) { pxB = 8; pyA = 0; pyB = 0; }
-                    else { pxB = 8; pyA = pyB = 8 * rd; }
-                    const bool inBL = type == B200_MB_P_16x8 ? r8 >= 8 : c8 == 8;
-                    const bool inBC = type == B200_MB_P_16x8 ? cr >= 4 : cc == 4;
-                    const bool actL = type < B200_MB_P_8x8 || (r8 >> 3) == rd, actC = type < B200_MB_P_8x8 || (cr >> 2) == rd;
-                    if (actL) {
-                        const uint32_t gm = inBL ? geomAB >> 16 : geomAB & 0xFFFFu, mv = inBL ? mvB : mvA;
-                        const int xf = (int)(mv & 3u), yf = (int)((mv >> 16) & 3u);
-                        const int pitch = (int)((gm >> 4) & 3u) * 16;
-                        const uint8_t *G0 = winL(pair, inBL ? 1 : 0) + (gm & 15u) + (yf ? 2 * pitch : 0) + (xf ? 2 : 0);
-                        pv = lumaQpel8(G0, pitch, c8 - (inBL ? pxB : 0), r8 - (inBL ? pyB : pyA), xf, yf);
-                    }
-                    if (actC) {
-                        const uint32_t gm = inBC ? geomAB >> 16 : geomAB & 0xFFFFu, mv = inBC ? mvB : mvA;
-                        pc = chromaPred4(winC(pair, inBC ? 1 : 0), (int)((gm >> 12) & 3u) * 16, (int)((gm >> 8) & 7u), cp,
-                                         cc - (inBC ? (pxB >> 1) : 0), cr - ((inBC ? pyB : pyA) >> 1), (int)(mv & 7u), (int)((mv >> 16) & 7u));
-                    }
-                } else {
-                    // sub-macroblocks with 8x4 / 4x8 / 4x4 partitions: one window per partition, sample by sample
-                    const uint32_t *rw = reinterpret_cast<const uint32_t *>(job.recs + (size_t)mby * g.widthMbs + mbx);
-                    const uint32_t refSlots = geomAB;
-                    uint8_t *wl = winL(pair, 0), *wc = winC(pair, 0);
-#pragma unroll 1
-                    for (int pi = 0; pi < 16; pi++) {
-                        int pw, ph;
-                        const int sub = (subTypes >> (2 * (pi >> 2))) & 3, j = pi & 3;
-                        if (sub == 0) { if (j) continue; pw = 8; ph = 8; }
-                        else if (sub == 1) { if (j & 1) continue; pw = 8; ph = 4; }
-                        else if (sub == 2) { if (j & 2) continue; pw = 4; ph = 8; }
-                        else { pw = 4; ph = 4; }
-                        const int px = cBlkX[pi] * 4, py = cBlkY[pi] * 4;
-                        const uint32_t mvw = __ldg(rw + 8 + pi);
-                        const int mvx = (int)(int16_t)(mvw & 0xFFFFu), mvy = (int)(int16_t)(mvw >> 16);
-                        const uint32_t gm = issueWindowFn(wl, wc, &sm.mbar[pair], &maps, g.W, g.H, mbx * 16 + px, mby * 16 + py, pw | (ph << 8), mvx, mvy,
-                                                          frameBase + ((refSlots >> (8 * (pi >> 2))) & 0xFFu), lane);
-                        mbarWait(&sm.mbar[pair], (phaseBits >> pair) & 1u);
-                        phaseBits ^= 1u << pair;
-                        const int xf = mvx & 3, yf = mvy & 3, pitch = (int)((gm >> 4) & 3u) * 16;
-                        const uint8_t *G0 = wl + (gm & 15u) + (yf ? 2 * pitch : 0) + (xf ? 2 : 0);
-                        const int lw = 31 - __clz(pw);
-#pragma unroll 1
-                        for (int q = lane; q < pw * ph; q += 32) {
-                            const int x = q & (pw - 1), y = q >> lw;
-                            pred[(py + y) * 16 + px + x] = (uint8_t)lumaQpel(G0, pitch, x, y, xf, yf);
-                        }
-                        const int cw = pw >> 1, chh = ph >> 1, ncp = cw * chh, lcw = lw - 1;
-                        const int cxf = mvx & 7, cyf = mvy & 7, pitchC = (int)((gm >> 12) & 3u) * 16, cxo = (int)((gm >> 8) & 7u);
-#pragma unroll 1
-                        for (int q = lane; q < 2 * ncp; q += 32) {
-                            const int pl = q >= ncp, qq = q - pl * ncp;
-                            const int x = qq & (cw - 1), y = qq >> lcw;
-                            auto S = [&](int sx, int sy) -> int {
-                                const int col = cxo + sx;
-                                return wc[sy * pitchC + (col >> 3) * 16 + pl * 8 + (col & 7)];
-                            };
-                            // (a sample that meets a zero weight may lie outside the box: it is read, not used)
-                            const int A = S(x, y), B = S(x + 1, y), Cc = S(x, y + 1), D = S(x + 1, y + 1);
-                            pred[256 + pl * 64 + ((py >> 1) + y) * 8 + (px >> 1) + x] =
-                                (uint8_t)(((8 - cxf) * (8 - cyf) * A + cxf * (8 - cyf) * B + (8 - cxf) * cyf * Cc + cxf * cyf * D + 32) >> 6);
-                        }
-                        __syncwarp();
-                    }
-                    pv = *reinterpret_cast<const uint2 *>(pred + r8 * 16 + c8);
-                    pc = *reinterpret_cast<const uint32_t *>(pred + 256 + cp * 64 + cr * 8 + cc);
-                }
-                if (last) finish(l, mask, pv, pc);
-                __syncwarp();   // the pair's windows (and the residual) are free for the loads of the turn after next
+        // ---- the copies have arrived: on to the current frame ------------------------------------------------------------------
+        if (copyMask) {
+            mbarWaitSleeping(&sm.mbarCopy, (phaseBits >> 2) & 1u);
+            phaseBits ^= 4u;
+            if (runLen) {
+                bulkStore(lbase + lane * 256, sm.stage + lane * 256, 256u * (uint32_t)runLen);
+                bulkStore(cbase + lane * 128, sm.stage + kStageMbs * 256 + lane * 128, 128u * (uint32_t)runLen);
+                bulkCommit();
             }
         }
         chunk = nextChunk;
         nextChunk = __shfl_sync(0xffffffffu, ticket2, 0);
     }
-    if (!kMulti) bulkWaitAll();   // this lane's last stores still read shared memory
+    bulkWaitAll();   // this lane's last stores still read shared memory
+}
+
+// Second instance: the macroblocks with several partitions (inter_prediction.c:361-482), from the list the first instance made.
+// A warp takes eight list entries at a time (lane e < 8 fetches entry e's record, one batch ahead) and works through them as a
+// pipeline of ROUNDS: a round is two partitions that are at least 8 wide -- the two of a 16x8 / 8x16 macroblock, the upper or the
+// lower two 8x8 sub-macroblocks -- so that every lane's 8-sample luma span and 4-sample chroma span lie inside ONE of them and
+// the lane only has to pick that partition's window, vector and origin.  The four windows of a round land in one of two buffer
+// pairs (the second one lives in `stage`: this instance has no copies) on the pair's mbarrier, together with the macroblock's
+// levels in its first round; the round after is staged before this one is waited for.  A sub-macroblock with 8x4 / 4x8 / 4x4
+// partitions makes its macroblock one round without windows: its partitions are fetched one by one when its turn has come.
+constexpr int kMultiBatch = 8;
+__global__ void __launch_bounds__(kPassAWarps * 32, B200_PASSA_MINBLOCKS)
+passAMultiKernel(const ReconParams p, const __grid_constant__ PassAMaps maps) {
+    extern __shared__ __align__(128) uint8_t interSmemRaw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const PoolGeom &g = p.g;
+    PassAWarpSmem &sm = reinterpret_cast<PassAWarpSmem *>(interSmemRaw)[warp];
+    if (lane == 0) {
+        mbarInit(&sm.mbar[0], 1);
+        mbarInit(&sm.mbar[1], 1);
+        fenceMbarInit();
+    }
+    __syncwarp();
+    uint32_t phaseBits = 0;
+    const uint32_t nWarps = gridDim.x * kPassAWarps;
+    const uint32_t count = __ldcg(p.multiCount), nBatches = (count + kMultiBatch - 1) / kMultiBatch;
+    const int r8 = lane >> 1, c8 = (lane & 1) * 8;
+    const int cr = lane >> 2, cp = (lane >> 1) & 1, cc = (lane & 1) * 4;
+    uint8_t *pred = sm.stage;
+    auto winL = [&](int pair, int w) -> uint8_t * { return pair ? sm.stage + 384 + w * kLumaBufBytes : sm.luma[w]; };
+    auto winC = [&](int pair, int w) -> uint8_t * { return pair ? sm.stage + 384 + 2 * kLumaBufBytes + w * kChromaBufBytes : sm.chroma[w]; };
+
+    // lane e < 8: entry e of a batch -- where the macroblock lies, its record's head, reference slots, first vector of each quadrant
+    uint32_t fEntry = 0xFFFFFFFFu, fW0 = 0, fMask = 0, fCoef = 0, fW3 = 0, fRef = 0, fMv = 0, fMv1 = 0, fMv2 = 0, fMv3 = 0;
+    auto fetch = [&](uint32_t b) {
+        fEntry = 0xFFFFFFFFu;
+        const uint32_t e = b * kMultiBatch + (uint32_t)lane;
+        if (b >= nBatches || lane >= kMultiBatch || e >= count) return;
+        fEntry = __ldcg(p.multiList + e);
+        const uint32_t s = fEntry / (uint32_t)g.nMbs, mb = fEntry - s * (uint32_t)g.nMbs;
+        const uint32_t *rw = reinterpret_cast<const uint32_t *>(p.jobs[s].recs + mb);
+        const uint4 hw = __ldg(reinterpret_cast<const uint4 *>(rw));
+        fRef = __ldg(rw + 4);
+        fMv = __ldg(rw + 8); fMv1 = __ldg(rw + 12); fMv2 = __ldg(rw + 16); fMv3 = __ldg(rw + 20);
+        fW0 = hw.x; fMask = hw.y; fCoef = hw.z; fW3 = hw.w;
+    };
+    uint32_t batch = blockIdx.x * kPassAWarps + warp;
+    fetch(batch);
+    uint32_t nextBatch = 0;
+    if (lane == 0) nextBatch = atomicAdd(p.ticketA + 1, 1u) + nWarps;
+    nextBatch = __shfl_sync(0xffffffffu, nextBatch, 0);
+    while (batch < nBatches) {
+        uint32_t ticket2 = 0;
+        if (lane == 0) ticket2 = atomicAdd(p.ticketA + 1, 1u) + nWarps;
+        const uint32_t mEntry = fEntry, mW0 = fW0, mMask = fMask, mCoef = fCoef, mW3 = fW3, mRef = fRef, mMv = fMv, mMv1 = fMv1, mMv2 = fMv2, mMv3 = fMv3;
+        fetch(nextBatch);
+        // this lane's macroblock: stream, position, frames, levels
+        uint32_t mPos = 0, mCurFrame = 0, mFrameBase = 0;
+        const int16_t *mCoefs = nullptr;
+        const b200_mb_rec *mRec = nullptr;
+        if (mEntry != 0xFFFFFFFFu) {
+            const uint32_t s = mEntry / (uint32_t)g.nMbs, mb = mEntry - s * (uint32_t)g.nMbs;
+            const StreamJob job = p.jobs[s];
+            const int mby = mbRowOf(mb, g), mbx = (int)mb - mby * g.widthMbs;
+            mPos = (uint32_t)mbx | ((uint32_t)mby << 16);
+            mFrameBase = s * (uint32_t)g.numSlots;
+            mCurFrame = mFrameBase + job.curSlot;
+            mCoefs = job.coefs;
+            mRec = job.recs + mb;
+        }
+        uint32_t todo = __ballot_sync(0xffffffffu, mEntry != 0xFFFFFFFFu);
+
+        // the staged round: macroblock, round, what every lane needs to compute it
+        int sL = 0, sRd = 0, sLast = 0;
+        uint32_t sW0 = 0, sMask = 0, sGeom = 0, sMvA = 0, sMvB = 0, sSub = 0, sPos = 0, sFrame = 0;
+        bool sArmed = false;
+        int nl = todo ? __ffs(todo) - 1 : 0, nrd = 0;   // the round to stage next
+        bool more = todo != 0, have = false;
+        int seq = 0, mbSeq = 0;
+        uint2 pv = make_uint2(0, 0);   // this lane's 8 luma prediction samples
+        uint32_t pc = 0;               // and 4 chroma prediction samples
+#pragma unroll 1
+        while (more || have) {
+            // the round staged in the previous turn is this turn's
+            const bool valid = have;
+            const int l = sL, rd = sRd, last = sLast, pair = (seq + 1) & 1, coefBuf = (mbSeq + 1) & 1;
+            const uint32_t w0 = sW0, mask = sMask, geomAB = sGeom, mvA = sMvA, mvB = sMvB, subTypes = sSub, pos = sPos, curFrame = sFrame;
+            const bool armed = sArmed;
+            have = more;
+            if (more) {
+                const int sp = seq & 1;
+                seq++;
+                sL = nl; sRd = nrd;
+                sW0 = __shfl_sync(0xffffffffu, mW0, nl); sMask = __shfl_sync(0xffffffffu, mMask, nl);
+                sPos = __shfl_sync(0xffffffffu, mPos, nl); sFrame = __shfl_sync(0xffffffffu, mCurFrame, nl);
+                const uint32_t type = sW0 & 0xFFu;
+                sSub = type >= B200_MB_P_8x8 ? __shfl_sync(0xffffffffu, mW3, nl) >> 24 : 0u;
+                uint32_t coefBytes = 0;
+                if (nrd == 0) { coefBytes = 32u * (uint32_t)__popc(sMask & 0x3FFFFFFu); mbSeq++; }
+                const int cb = (mbSeq + 1) & 1;   // the macroblock's level buffer
+                const int mbx = (int)(sPos & 0xFFFFu), mby = (int)(sPos >> 16);
+                if (sSub == 0) {
+                    int qA, qB, pxB, pyA, pyB, pw, ph;
+                    if (type == B200_MB_P_16x8) { qA = 0; qB = 2; pxB = 0; pyA = 0; pyB = 8; pw = 16; ph = 8; }
+                    else if (type == B200_MB_P_8x16) { qA = 0; qB = 1; pxB = 8; pyA = 0; pyB = 0; pw = 8; ph = 16; }
+                    else { qA = 2 * nrd; qB = 2 * nrd + 1; pxB = 8; pyA = pyB = 8 * nrd; pw = 8; ph = 8; }
+                    sMvA = __shfl_sync(0xffffffffu, qA ? mMv2 : mMv, nl);
+                    sMvB = __shfl_sync(0xffffffffu, qB == 1 ? mMv1 : qB == 2 ? mMv2 : mMv3, nl);
+                    const WindowGeom wa = windowGeom(g.W, g.H, mbx * 16, mby * 16 + pyA, pw, ph, (int)(int16_t)(sMvA & 0xFFFFu), (int)(int16_t)(sMvA >> 16));
+                    const WindowGeom wb = windowGeom(g.W, g.H, mbx * 16 + pxB, mby * 16 + pyB, pw, ph, (int)(int16_t)(sMvB & 0xFFFFu), (int)(int16_t)(sMvB >> 16));
+                    sGeom = wa.geom | (wb.geom << 16);
+                    sArmed = true;
+                    sLast = type < B200_MB_P_8x8 || nrd == 1;
+                    if (lane == nl) {
+                        const int refA = (int)(mFrameBase + ((mRef >> (8 * qA)) & 0xFFu)), refB = (int)(mFrameBase + ((mRef >> (8 * qB)) & 0xFFu));
+                        fenceProxyAsync();
+                        mbarExpectTx(&sm.mbar[sp], wa.bytes + wb.bytes + coefBytes);
+                        tmaLoad4d(winL(sp, 0), &maps.luma[0][0] + wa.map, 0, wa.strip, wa.row, refA, &sm.mbar[sp]);
+                        tmaLoad4d(winC(sp, 0), &maps.chroma[0][0] + wa.mapC, 0, wa.stripC, wa.rowC, refA, &sm.mbar[sp]);
+                        tmaLoad4d(winL(sp, 1), &maps.luma[0][0] + wb.map, 0, wb.strip, wb.row, refB, &sm.mbar[sp]);
+                        tmaLoad4d(winC(sp, 1), &maps.chroma[0][0] + wb.mapC, 0, wb.stripC, wb.rowC, refB, &sm.mbar[sp]);
+                        if (coefBytes) bulkLoad(sm.coef[cb], mCoefs + (size_t)mCoef * 16, coefBytes, &sm.mbar[sp]);
+                    }
+                } else {
+                    sArmed = coefBytes != 0;   // (the partitions' windows are fetched when the macroblock's turn has come)
+                    sLast = 1;
+                    if (lane == nl && coefBytes) {
+                        fenceProxyAsync();
+                        mbarExpectTx(&sm.mbar[sp], coefBytes);
+                        bulkLoad(sm.coef[cb], mCoefs + (size_t)mCoef * 16, coefBytes, &sm.mbar[sp]);
+                    }
+                }
+                // the round after the one just staged
+                if (!sLast) nrd = 1;
+                else {
+                    todo &= todo - 1;
+                    more = todo != 0;
+                    nl = more ? __ffs(todo) - 1 : 0;
+                    nrd = 0;
+                }
+            }
+            if (!valid) continue;
+            if (armed) {
+                mbarWait(&sm.mbar[pair], (phaseBits >> pair) & 1u);
+                phaseBits ^= 1u << pair;
+            }
+            const uint32_t type = w0 & 0xFFu;
+            const int mbx = (int)(pos & 0xFFFFu), mby = (int)(pos >> 16);
+            if (rd == 0) {
+                pv = make_uint2(0, 0);
+                pc = 0;
+                if (mask) residualShfl(sm, sm.coef[coefBuf], mask, (w0 >> 8) & 0xFF, (w0 >> 16) & 0xFF, lane, p.errors);
+            }
+            if (subTypes == 0) {
+                int pxB, pyA, pyB;
+                if (type == B200_MB_P_16x8) { pxB = 0; pyA = 0; pyB = 8; }
+                else if (type == B200_MB_P_8x16) { pxB = 8; pyA = 0; pyB = 0; }
+                else { pxB = 8; pyA = pyB = 8 * rd; }
+                const bool inBL = type == B200_MB_P_16x8 ? r8 >= 8 : c8 == 8;
+                const bool inBC = type == B200_MB_P_16x8 ? cr >= 4 : cc == 4;
+                const bool actL = type < B200_MB_P_8x8 || (r8 >> 3) == rd, actC = type < B200_MB_P_8x8 || (cr >> 2) == rd;
+                if (actL) {
+                    const uint32_t gm = inBL ? geomAB >> 16 : geomAB & 0xFFFFu, mv = inBL ? mvB : mvA;
+                    const int xf = (int)(mv & 3u), yf = (int)((mv >> 16) & 3u);
+                    const int pitch = (int)((gm >> 4) & 3u) * 16;
+                    const uint8_t *G0 = winL(pair, inBL ? 1 : 0) + (gm & 15u) + (yf ? 2 * pitch : 0) + (xf ? 2 : 0);
+                    pv = lumaQpel8(G0, pitch, c8 - (inBL ? pxB : 0), r8 - (inBL ? pyB : pyA), xf, yf);
+                }
+                if (actC) {
+                    const uint32_t gm = inBC ? geomAB >> 16 : geomAB & 0xFFFFu, mv = inBC ? mvB : mvA;
+                    pc = chromaPred4(winC(pair, inBC ? 1 : 0), (int)((gm >> 12) & 3u) * 16, (int)((gm >> 8) & 7u), cp,
+                                     cc - (inBC ? (pxB >> 1) : 0), cr - ((inBC ? pyB : pyA) >> 1), (int)(mv & 7u), (int)((mv >> 16) & 7u));
+                }
+            } else {
+                // sub-macroblocks with 8x4 / 4x8 / 4x4 partitions: one window per partition, sample by sample
+                const unsigned long long recBits = __shfl_sync(0xffffffffu, (unsigned long long)reinterpret_cast<uintptr_t>(mRec), l);
+                const uint32_t *rw = reinterpret_cast<const uint32_t *>((uintptr_t)recBits);
+                const uint32_t refSlots = __shfl_sync(0xffffffffu, mRef, l), frameBase = __shfl_sync(0xffffffffu, mFrameBase, l);
+                uint8_t *wl = winL(pair, 0), *wc = winC(pair, 0);
+#pragma unroll 1
+                for (int pi = 0; pi < 16; pi++) {
+                    int pw, ph;
+                    const int sub = (subTypes >> (2 * (pi >> 2))) & 3, j = pi & 3;
+                    if (sub == 0) { if (j) continue; pw = 8; ph = 8; }
+                    else if (sub == 1) { if (j & 1) continue; pw = 8; ph = 4; }
+                    else if (sub == 2) { if (j & 2) continue; pw = 4; ph = 8; }
+                    else { pw = 4; ph = 4; }
+                    const int px = cBlkX[pi] * 4, py = cBlkY[pi] * 4;
+                    const uint32_t mvw = __ldg(rw + 8 + pi);
+                    const int mvx = (int)(int16_t)(mvw & 0xFFFFu), mvy = (int)(int16_t)(mvw >> 16);
+                    const uint32_t gm = issueWindowFn(wl, wc, &sm.mbar[pair], &maps, g.W, g.H, mbx * 16 + px, mby * 16 + py, pw | (ph << 8), mvx, mvy,
+                                                      frameBase + ((refSlots >> (8 * (pi >> 2))) & 0xFFu), lane);
+                    mbarWait(&sm.mbar[pair], (phaseBits >> pair) & 1u);
+                    phaseBits ^= 1u << pair;
+                    const int xf = mvx & 3, yf = mvy & 3, pitch = (int)((gm >> 4) & 3u) * 16;
+                    const uint8_t *G0 = wl + (gm & 15u) + (yf ? 2 * pitch : 0) + (xf ? 2 : 0);
+                    const int lw = 31 - __clz(pw);
+#pragma unroll 1
+                    for (int q = lane; q < pw * ph; q += 32) {
+                        const int x = q & (pw - 1), y = q >> lw;
+                        pred[(py + y) * 16 + px + x] = (uint8_t)lumaQpel(G0, pitch, x, y, xf, yf);
+                    }
+                    const int cw = pw >> 1, chh = ph >> 1, ncp = cw * chh, lcw = lw - 1;
+                    const int cxf = mvx & 7, cyf = mvy & 7, pitchC = (int)((gm >> 12) & 3u) * 16, cxo = (int)((gm >> 8) & 7u);
+#pragma unroll 1
+                    for (int q = lane; q < 2 * ncp; q += 32) {
+                        const int pl = q >= ncp, qq = q - pl * ncp;
+                        const int x = qq & (cw - 1), y = qq >> lcw;
+                        auto S = [&](int sx, int sy) -> int {
+                            const int col = cxo + sx;
+                            return wc[sy * pitchC + (col >> 3) * 16 + pl * 8 + (col & 7)];
+                        };
+                        // (a sample that meets a zero weight may lie outside the box: it is read, not used)
+                        const int A = S(x, y), B = S(x + 1, y), Cc = S(x, y + 1), D = S(x + 1, y + 1);
+                        pred[256 + pl * 64 + ((py >> 1) + y) * 8 + (px >> 1) + x] =
+                            (uint8_t)(((8 - cxf) * (8 - cyf) * A + cxf * (8 - cyf) * B + (8 - cxf) * cyf * Cc + cxf * cyf * D + 32) >> 6);
+                    }
+                    __syncwarp();
+                }
+                pv = *reinterpret_cast<const uint2 *>(pred + r8 * 16 + c8);
+                pc = *reinterpret_cast<const uint32_t *>(pred + 256 + cp * 64 + cr * 8 + cc);
+            }
+            if (last) {
+                uint8_t *frame = framePtr(p.pool, g, curFrame);
+                addResidualStore(sm, mask, pv, pc, mbLuma(frame, g, mbx, mby), mbChroma(frame, g, mbx, mby), lane);
+            }
+            __syncwarp();   // the pair's windows (and the residual) are free for the loads of the turn after next
+        }
+        batch = nextBatch;
+        nextBatch = __shfl_sync(0xffffffffu, ticket2, 0);
+    }
 }
 
 // =====================================================================================================

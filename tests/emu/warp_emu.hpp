@@ -240,6 +240,10 @@ inline int dp4aUS(uint32_t pels, int taps, int acc) {
     for (int i = 0; i < 4; i++) acc += (int)((pels >> (8 * i)) & 0xFF) * (int)(int8_t)(((uint32_t)taps >> (8 * i)) & 0xFF);
     return acc;
 }
+// dp2a.lo.s32.s32: acc + lo16(a) x byte0(b) + hi16(a) x byte1(b), all signed
+inline int dp2aLoSS(uint32_t a, int b, int acc) {
+    return acc + (int)(int16_t)(a & 0xFFFFu) * (int)(int8_t)((uint32_t)b & 0xFF) + (int)(int16_t)(a >> 16) * (int)(int8_t)(((uint32_t)b >> 8) & 0xFF);
+}
 // cvt.pack.sat.u8.s32 twice: four ints saturated to bytes, p0 in the low byte
 inline uint32_t pack4sat(int p0, int p1, int p2, int p3) {
     auto sat = [](int v) { return (uint32_t)(v < 0 ? 0 : v > 255 ? 255 : v); };

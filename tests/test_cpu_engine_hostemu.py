@@ -64,7 +64,7 @@ def hostemu_lib():
     os.makedirs(BUILD, exist_ok=True)
     rk = open(os.path.join(CSRC, "engine", "recon_kernel.cuh")).read()
     line = "extern __shared__ __align__(128) uint8_t interSmemRaw[];"
-    assert rk.count(line) == 1
+    assert rk.count(line) == 2   # (the two pass-A kernels)
     with open(os.path.join(BUILD, "recon_kernel_emu.cuh"), "w") as f:
         f.write(rk.replace(line, "extern uint8_t interSmemRaw[];"))
     prepare_engine_source()
