@@ -770,38 +770,44 @@ passAKernel(const ReconParams p, const __grid_constant__ PassAMaps maps) {
 
         // Every lane works out where the windows of ITS macroblock lie, all macroblocks of the chunk at once instead of one after
         // the other when their turn comes.
-        //   gX = luma strip | chroma strip << 16     gY = luma row | chroma row << 16
-        //   gM = luma map (3 bits) | chroma map << 3 (2) | xo << 5 (4) | cxo << 9 (3) | mvx & 7 << 12 | mvy & 7 << 15 | window bytes << 18
-        uint32_t gX = 0, gY = 0, gM = 0;
+        //   gX = luma strip | chroma strip << 16     gY = luma row | chroma row << 16     gM = luma map | chroma map << 3 | window bytes << 8
+        // for the loads, and for the lanes that compute
+        //   gC = offset of integer sample (0, 0) in the luma window (7 bits) | luma pitch / 16 << 7 | chroma pitch / 16 << 9 |
+        //        first chroma column << 11 | mvx & 7 << 14 | mvy & 7 << 17
+        uint32_t gX = 0, gY = 0, gM = 0, gC = 0;
         if (isInter && (mW0 & 0xFFu) <= B200_MB_P_16x16) {
             const int mvx = (int)(int16_t)(mMv & 0xFFFFu), mvy = (int)(int16_t)(mMv >> 16);
             const WindowGeom wg = windowGeom(g.W, g.H, mbx * 16, (row0 + lane) * 16, 16, 16, mvx, mvy);
             gX = (uint32_t)wg.strip | ((uint32_t)wg.stripC << 16);
             gY = (uint32_t)wg.row | ((uint32_t)wg.rowC << 16);
-            gM = (uint32_t)wg.map | ((uint32_t)wg.mapC << 3) | ((wg.geom & 15u) << 5) | (((wg.geom >> 8) & 7u) << 9) |
-                 ((uint32_t)(mvx & 7) << 12) | ((uint32_t)(mvy & 7) << 15) | (wg.bytes << 18);
+            gM = (uint32_t)wg.map | ((uint32_t)wg.mapC << 3) | (wg.bytes << 8);
+            const uint32_t nx = (wg.geom >> 4) & 3u, nxC = (wg.geom >> 12) & 3u;
+            gC = ((wg.geom & 15u) + ((mvy & 3) ? 32u * nx : 0u) + ((mvx & 3) ? 2u : 0u)) | (nx << 7) | (nxC << 9) | (((wg.geom >> 8) & 7u) << 11) |
+                 ((uint32_t)(mvx & 7) << 14) | ((uint32_t)(mvy & 7) << 17);
         }
 
         // ---- what is staged for the macroblock whose turn comes next ----------------------------------------------------
         uint32_t nW0 = 0, nMask = 0, nGeom = 0;
         int nL = 0;
-        // stage macroblock l of the chunk into buffer `buf`: its levels and its windows.  The lane that holds the record issues
-        // the loads; the others learn what they need to compute with
+        // stage macroblock l of the chunk into buffer `buf`: its levels and its windows.  Everything the loads need is handed to
+        // lane 0, which issues them from uniform registers (issued by the record's own lane, a lane the compiler cannot name,
+        // every load becomes a loop that looks for the lane)
         auto prepare = [&](int l, int buf) {
             nL = l;
             nW0 = __shfl_sync(0xffffffffu, mW0, l); nMask = __shfl_sync(0xffffffffu, mMask, l);
-            nGeom = __shfl_sync(0xffffffffu, gM, l);
-            if (lane == l) {
-                const uint32_t type = mW0 & 0xFFu;
-                const uint32_t coefBytes = type == B200_MB_I_PCM ? 384u : 32u * (uint32_t)__popc(mMask & 0x3FFFFFFu);
-                fenceProxyAsync();
-                mbarExpectTx(&sm.mbar[buf], (gM >> 18) + coefBytes);
+            nGeom = __shfl_sync(0xffffffffu, gC, l);
+            const uint32_t gx = __shfl_sync(0xffffffffu, gX, l), gy = __shfl_sync(0xffffffffu, gY, l), gm = __shfl_sync(0xffffffffu, gM, l);
+            const uint32_t coefIndex = __shfl_sync(0xffffffffu, mCoef, l), ref = __shfl_sync(0xffffffffu, mRef, l);
+            if (lane == 0) {
+                const uint32_t type = nW0 & 0xFFu;
+                const uint32_t coefBytes = type == B200_MB_I_PCM ? 384u : 32u * (uint32_t)__popc(nMask & 0x3FFFFFFu);
+                mbarExpectTx(&sm.mbar[buf], (gm >> 8) + coefBytes);
                 if (type != B200_MB_I_PCM) {
-                    const int ref = (int)(frameBase + (mRef & 0xFFu));
-                    tmaLoad4d(sm.luma[buf], &maps.luma[0][0] + (gM & 7u), 0, (int)(gX & 0xFFFFu), (int)(gY & 0xFFFFu), ref, &sm.mbar[buf]);
-                    tmaLoad4d(sm.chroma[buf], &maps.chroma[0][0] + ((gM >> 3) & 3u), 0, (int)(gX >> 16), (int)(gY >> 16), ref, &sm.mbar[buf]);
+                    const int refFrame = (int)(frameBase + (ref & 0xFFu));
+                    tmaLoad4d(sm.luma[buf], &maps.luma[0][0] + (gm & 7u), 0, (int)(gx & 0xFFFFu), (int)(gy & 0xFFFFu), refFrame, &sm.mbar[buf]);
+                    tmaLoad4d(sm.chroma[buf], &maps.chroma[0][0] + ((gm >> 3) & 3u), 0, (int)(gx >> 16), (int)(gy >> 16), refFrame, &sm.mbar[buf]);
                 }
-                if (coefBytes) bulkLoad(sm.coef[buf], job.coefs + (size_t)mCoef * 16, coefBytes, &sm.mbar[buf]);
+                if (coefBytes) bulkLoad(sm.coef[buf], job.coefs + (size_t)coefIndex * 16, coefBytes, &sm.mbar[buf]);
             }
         };
         if (interMask) prepare(__ffs(interMask) - 1, 0);
@@ -828,12 +834,12 @@ passAKernel(const ReconParams p, const __grid_constant__ PassAMaps maps) {
                 continue;
             }
             // prediction first: the centre positions borrow the residual arrays
-            const int cxf = (int)((geom >> 12) & 7u), cyf = (int)((geom >> 15) & 7u), xf = cxf & 3, yf = cyf & 3;
-            const int pitch = (int)(((geom >> 1) & 3u) + 1u) * 16, pitchC = (int)(((geom >> 4) & 1u) + 1u) * 16;
-            const uint8_t *G0 = sm.luma[buf] + ((geom >> 5) & 15u) + (yf ? 2 * pitch : 0) + (xf ? 2 : 0);
+            const int cxf = (int)((geom >> 14) & 7u), cyf = (int)((geom >> 17) & 7u), xf = cxf & 3, yf = cyf & 3;
+            const int pitch = (int)((geom >> 3) & 0x30u), pitchC = (int)((geom >> 5) & 0x30u);
+            const uint8_t *G0 = sm.luma[buf] + (geom & 127u);
             const bool centre = (xf == 2 || yf == 2) && xf != 0 && yf != 0;
             const uint2 pv = centre ? lumaCentre8(&sm.resY[0][0], G0, pitch, lane, xf, yf) : lumaQpel8(G0, pitch, c8, r8, xf, yf);
-            const uint32_t pc = chromaPred4(sm.chroma[buf], pitchC, (int)((geom >> 9) & 7u), cp, cc, cr, cxf, cyf);
+            const uint32_t pc = chromaPred4(sm.chroma[buf], pitchC, (int)((geom >> 11) & 7u), cp, cc, cr, cxf, cyf);
             if (mask) {
                 __syncwarp();
                 residualShfl(sm, sm.coef[buf], mask, (w0 >> 8) & 0xFF, (w0 >> 16) & 0xFF, lane, p.errors);
@@ -862,11 +868,23 @@ passAKernel(const ReconParams p, const __grid_constant__ PassAMaps maps) {
 // A warp takes eight list entries at a time (lane e < 8 fetches entry e's record, one batch ahead) and works through them as a
 // pipeline of ROUNDS: a round is two partitions that are at least 8 wide -- the two of a 16x8 / 8x16 macroblock, the upper or the
 // lower two 8x8 sub-macroblocks -- so that every lane's 8-sample luma span and 4-sample chroma span lie inside ONE of them and
-// the lane only has to pick that partition's window, vector and origin.  The four windows of a round land in one of two buffer
-// pairs (the second one lives in `stage`: this instance has no copies) on the pair's mbarrier, together with the macroblock's
-// levels in its first round; the round after is staged before this one is waited for.  A sub-macroblock with 8x4 / 4x8 / 4x4
-// partitions makes its macroblock one round without windows: its partitions are fetched one by one when its turn has come.
+// the lane only has to pick that partition's window, vector and origin.  The lanes that hold the records work out, all at once,
+// what every round of the batch needs -- where its windows lie, what to expect, what to compute with -- and leave it in a box in
+// shared memory; after that a round costs the warp a few broadcast loads, and lane 0 issues its loads from uniform registers.
+// The four windows of a round land in one of two buffer pairs (the second one lives in `stage`: this instance has no copies) on
+// the pair's mbarrier, together with the macroblock's levels in its first round; the round after is staged before this one is
+// waited for.  A sub-macroblock with 8x4 / 4x8 / 4x4 partitions makes its macroblock one round without windows: its partitions
+// are fetched one by one when its turn has come.
 constexpr int kMultiBatch = 8;
+struct __align__(16) RoundBox {
+    uint32_t gxA, gyA, gxB, gyB;            // luma strip | chroma strip << 16, luma row | chroma row << 16 of the two windows
+    uint32_t maps, refA, refB, bytes;       // luma map A | chroma map A << 4 | luma B << 8 | chroma B << 12; reference frames; bytes to expect
+    uint32_t coefLo, coefHi, coefBytes, flags;   // the macroblock's levels (first round); flags: round | last << 1 | small partitions << 2 | level buffer << 3
+    uint32_t geomAB, fracs, w0, mask;       // WindowGeom.geom of A | B << 16; mvA.x & 7 | mvA.y & 7 << 3 | mvB.x & 7 << 6 | mvB.y & 7 << 9; record head
+    uint32_t pos, curFrame, recLo, recHi;   // mbx | mby << 16; frame to write; the record (small partitions read their vectors there)
+};
+static_assert(sizeof(RoundBox) == 80 && 384 + 2 * kLumaBufBytes + 2 * kChromaBufBytes + 2 * kMultiBatch * sizeof(RoundBox) <= sizeof(PassAWarpSmem::stage),
+              "the second window pair, the prediction of small partitions and the round boxes share `stage`");
 __global__ void __launch_bounds__(kPassAWarps * 32, B200_PASSA_MINBLOCKS)
 passAMultiKernel(const ReconParams p, const __grid_constant__ PassAMaps maps) {
     extern __shared__ __align__(128) uint8_t interSmemRaw[];
@@ -885,6 +903,7 @@ passAMultiKernel(const ReconParams p, const __grid_constant__ PassAMaps maps) {
     const int r8 = lane >> 1, c8 = (lane & 1) * 8;
     const int cr = lane >> 2, cp = (lane >> 1) & 1, cc = (lane & 1) * 4;
     uint8_t *pred = sm.stage;
+    RoundBox *boxes = reinterpret_cast<RoundBox *>(sm.stage + 384 + 2 * kLumaBufBytes + 2 * kChromaBufBytes);
     auto winL = [&](int pair, int w) -> uint8_t * { return pair ? sm.stage + 384 + w * kLumaBufBytes : sm.luma[w]; };
     auto winC = [&](int pair, int w) -> uint8_t * { return pair ? sm.stage + 384 + 2 * kLumaBufBytes + w * kChromaBufBytes : sm.chroma[w]; };
 
@@ -910,106 +929,100 @@ passAMultiKernel(const ReconParams p, const __grid_constant__ PassAMaps maps) {
     while (batch < nBatches) {
         uint32_t ticket2 = 0;
         if (lane == 0) ticket2 = atomicAdd(p.ticketA + 1, 1u) + nWarps;
-        const uint32_t mEntry = fEntry, mW0 = fW0, mMask = fMask, mCoef = fCoef, mW3 = fW3, mRef = fRef, mMv = fMv, mMv1 = fMv1, mMv2 = fMv2, mMv3 = fMv3;
+        const uint32_t mEntry = fEntry, mW0 = fW0, mMask = fMask, mCoef = fCoef, mW3 = fW3, mRef = fRef;
+        const uint32_t mMv = fMv, mMv1 = fMv1, mMv2 = fMv2, mMv3 = fMv3;
         fetch(nextBatch);
-        // this lane's macroblock: stream, position, frames, levels
-        uint32_t mPos = 0, mCurFrame = 0, mFrameBase = 0;
-        const int16_t *mCoefs = nullptr;
-        const b200_mb_rec *mRec = nullptr;
-        if (mEntry != 0xFFFFFFFFu) {
+
+        // ---- the lanes that hold a record fill the boxes of its rounds --------------------------------------------------------
+        const bool mine = mEntry != 0xFFFFFFFFu;
+        const uint32_t type = mW0 & 0xFFu, subTypes = type >= B200_MB_P_8x8 ? mW3 >> 24 : 0u;
+        const bool small = mine && subTypes != 0, two = mine && type >= B200_MB_P_8x8 && subTypes == 0;
+        const uint32_t mineMask = __ballot_sync(0xffffffffu, mine), twoMask = __ballot_sync(0xffffffffu, two);
+        const uint32_t below = (1u << lane) - 1u;
+        const int nRounds = __popc(mineMask) + __popc(twoMask);
+        if (mine) {
+            const int seq = __popc(mineMask & below), firstRound = seq + __popc(twoMask & below);
             const uint32_t s = mEntry / (uint32_t)g.nMbs, mb = mEntry - s * (uint32_t)g.nMbs;
             const StreamJob job = p.jobs[s];
             const int mby = mbRowOf(mb, g), mbx = (int)mb - mby * g.widthMbs;
-            mPos = (uint32_t)mbx | ((uint32_t)mby << 16);
-            mFrameBase = s * (uint32_t)g.numSlots;
-            mCurFrame = mFrameBase + job.curSlot;
-            mCoefs = job.coefs;
-            mRec = job.recs + mb;
-        }
-        uint32_t todo = __ballot_sync(0xffffffffu, mEntry != 0xFFFFFFFFu);
-
-        // the staged round: macroblock, round, what every lane needs to compute it
-        int sL = 0, sRd = 0, sLast = 0;
-        uint32_t sW0 = 0, sMask = 0, sGeom = 0, sMvA = 0, sMvB = 0, sSub = 0, sPos = 0, sFrame = 0;
-        bool sArmed = false;
-        int nl = todo ? __ffs(todo) - 1 : 0, nrd = 0;   // the round to stage next
-        bool more = todo != 0, have = false;
-        int seq = 0, mbSeq = 0;
-        uint2 pv = make_uint2(0, 0);   // this lane's 8 luma prediction samples
-        uint32_t pc = 0;               // and 4 chroma prediction samples
+            const uint32_t frameBase = s * (uint32_t)g.numSlots;
+            const int16_t *coefSrc = job.coefs + (size_t)mCoef * 16;
+            const uint32_t coefBytes = 32u * (uint32_t)__popc(mMask & 0x3FFFFFFu);
+            const unsigned long long recBits = (unsigned long long)reinterpret_cast<uintptr_t>(job.recs + mb);
 #pragma unroll 1
-        while (more || have) {
-            // the round staged in the previous turn is this turn's
-            const bool valid = have;
-            const int l = sL, rd = sRd, last = sLast, pair = (seq + 1) & 1, coefBuf = (mbSeq + 1) & 1;
-            const uint32_t w0 = sW0, mask = sMask, geomAB = sGeom, mvA = sMvA, mvB = sMvB, subTypes = sSub, pos = sPos, curFrame = sFrame;
-            const bool armed = sArmed;
-            have = more;
-            if (more) {
-                const int sp = seq & 1;
-                seq++;
-                sL = nl; sRd = nrd;
-                sW0 = __shfl_sync(0xffffffffu, mW0, nl); sMask = __shfl_sync(0xffffffffu, mMask, nl);
-                sPos = __shfl_sync(0xffffffffu, mPos, nl); sFrame = __shfl_sync(0xffffffffu, mCurFrame, nl);
-                const uint32_t type = sW0 & 0xFFu;
-                sSub = type >= B200_MB_P_8x8 ? __shfl_sync(0xffffffffu, mW3, nl) >> 24 : 0u;
-                uint32_t coefBytes = 0;
-                if (nrd == 0) { coefBytes = 32u * (uint32_t)__popc(sMask & 0x3FFFFFFu); mbSeq++; }
-                const int cb = (mbSeq + 1) & 1;   // the macroblock's level buffer
-                const int mbx = (int)(sPos & 0xFFFFu), mby = (int)(sPos >> 16);
-                if (sSub == 0) {
+            for (int rd = 0; rd < (two ? 2 : 1); rd++) {
+                RoundBox bx;
+                bx.coefLo = (uint32_t)reinterpret_cast<uintptr_t>(coefSrc); bx.coefHi = (uint32_t)((unsigned long long)reinterpret_cast<uintptr_t>(coefSrc) >> 32);
+                bx.coefBytes = rd == 0 ? coefBytes : 0u;
+                bx.flags = (uint32_t)rd | ((!two || rd == 1) ? 2u : 0u) | (small ? 4u : 0u) | ((uint32_t)(seq & 1) << 3);
+                bx.w0 = mW0; bx.mask = mMask;
+                bx.pos = (uint32_t)mbx | ((uint32_t)mby << 16); bx.curFrame = frameBase + job.curSlot;
+                bx.recLo = (uint32_t)recBits; bx.recHi = (uint32_t)(recBits >> 32);
+                if (!small) {
                     int qA, qB, pxB, pyA, pyB, pw, ph;
                     if (type == B200_MB_P_16x8) { qA = 0; qB = 2; pxB = 0; pyA = 0; pyB = 8; pw = 16; ph = 8; }
                     else if (type == B200_MB_P_8x16) { qA = 0; qB = 1; pxB = 8; pyA = 0; pyB = 0; pw = 8; ph = 16; }
-                    else { qA = 2 * nrd; qB = 2 * nrd + 1; pxB = 8; pyA = pyB = 8 * nrd; pw = 8; ph = 8; }
-                    sMvA = __shfl_sync(0xffffffffu, qA ? mMv2 : mMv, nl);
-                    sMvB = __shfl_sync(0xffffffffu, qB == 1 ? mMv1 : qB == 2 ? mMv2 : mMv3, nl);
-                    const WindowGeom wa = windowGeom(g.W, g.H, mbx * 16, mby * 16 + pyA, pw, ph, (int)(int16_t)(sMvA & 0xFFFFu), (int)(int16_t)(sMvA >> 16));
-                    const WindowGeom wb = windowGeom(g.W, g.H, mbx * 16 + pxB, mby * 16 + pyB, pw, ph, (int)(int16_t)(sMvB & 0xFFFFu), (int)(int16_t)(sMvB >> 16));
-                    sGeom = wa.geom | (wb.geom << 16);
-                    sArmed = true;
-                    sLast = type < B200_MB_P_8x8 || nrd == 1;
-                    if (lane == nl) {
-                        const int refA = (int)(mFrameBase + ((mRef >> (8 * qA)) & 0xFFu)), refB = (int)(mFrameBase + ((mRef >> (8 * qB)) & 0xFFu));
-                        fenceProxyAsync();
-                        mbarExpectTx(&sm.mbar[sp], wa.bytes + wb.bytes + coefBytes);
-                        tmaLoad4d(winL(sp, 0), &maps.luma[0][0] + wa.map, 0, wa.strip, wa.row, refA, &sm.mbar[sp]);
-                        tmaLoad4d(winC(sp, 0), &maps.chroma[0][0] + wa.mapC, 0, wa.stripC, wa.rowC, refA, &sm.mbar[sp]);
-                        tmaLoad4d(winL(sp, 1), &maps.luma[0][0] + wb.map, 0, wb.strip, wb.row, refB, &sm.mbar[sp]);
-                        tmaLoad4d(winC(sp, 1), &maps.chroma[0][0] + wb.mapC, 0, wb.stripC, wb.rowC, refB, &sm.mbar[sp]);
-                        if (coefBytes) bulkLoad(sm.coef[cb], mCoefs + (size_t)mCoef * 16, coefBytes, &sm.mbar[sp]);
-                    }
+                    else { qA = 2 * rd; qB = 2 * rd + 1; pxB = 8; pyA = pyB = 8 * rd; pw = 8; ph = 8; }
+                    const uint32_t mvA = qA ? mMv2 : mMv, mvB = qB == 1 ? mMv1 : qB == 2 ? mMv2 : mMv3;
+                    const WindowGeom wa = windowGeom(g.W, g.H, mbx * 16, mby * 16 + pyA, pw, ph, (int)(int16_t)(mvA & 0xFFFFu), (int)(int16_t)(mvA >> 16));
+                    const WindowGeom wb = windowGeom(g.W, g.H, mbx * 16 + pxB, mby * 16 + pyB, pw, ph, (int)(int16_t)(mvB & 0xFFFFu), (int)(int16_t)(mvB >> 16));
+                    bx.gxA = (uint32_t)wa.strip | ((uint32_t)wa.stripC << 16); bx.gyA = (uint32_t)wa.row | ((uint32_t)wa.rowC << 16);
+                    bx.gxB = (uint32_t)wb.strip | ((uint32_t)wb.stripC << 16); bx.gyB = (uint32_t)wb.row | ((uint32_t)wb.rowC << 16);
+                    bx.maps = (uint32_t)wa.map | ((uint32_t)wa.mapC << 4) | ((uint32_t)wb.map << 8) | ((uint32_t)wb.mapC << 12);
+                    bx.refA = frameBase + ((mRef >> (8 * qA)) & 0xFFu); bx.refB = frameBase + ((mRef >> (8 * qB)) & 0xFFu);
+                    bx.bytes = wa.bytes + wb.bytes + bx.coefBytes;
+                    bx.geomAB = wa.geom | (wb.geom << 16);
+                    bx.fracs = (mvA & 7u) | (((mvA >> 16) & 7u) << 3) | ((mvB & 7u) << 6) | (((mvB >> 16) & 7u) << 9);
                 } else {
-                    sArmed = coefBytes != 0;   // (the partitions' windows are fetched when the macroblock's turn has come)
-                    sLast = 1;
-                    if (lane == nl && coefBytes) {
-                        fenceProxyAsync();
-                        mbarExpectTx(&sm.mbar[sp], coefBytes);
-                        bulkLoad(sm.coef[cb], mCoefs + (size_t)mCoef * 16, coefBytes, &sm.mbar[sp]);
-                    }
+                    bx.gxA = bx.gyA = bx.gxB = bx.gyB = bx.maps = 0;
+                    bx.refA = mRef; bx.refB = frameBase;   // (the partitions' reference slots and the stream's first frame)
+                    bx.bytes = bx.coefBytes;
+                    bx.geomAB = 0; bx.fracs = subTypes;
                 }
-                // the round after the one just staged
-                if (!sLast) nrd = 1;
-                else {
-                    todo &= todo - 1;
-                    more = todo != 0;
-                    nl = more ? __ffs(todo) - 1 : 0;
-                    nrd = 0;
-                }
+                boxes[firstRound + rd] = bx;
             }
-            if (!valid) continue;
-            if (armed) {
+        }
+        __syncwarp();
+
+        // ---- the rounds: stage the next one, compute this one -----------------------------------------------------------------
+        auto stageRound = [&](int r) {
+            const uint4 q0 = reinterpret_cast<const uint4 *>(&boxes[r])[0], q1 = reinterpret_cast<const uint4 *>(&boxes[r])[1];
+            const uint4 q2 = reinterpret_cast<const uint4 *>(&boxes[r])[2];
+            if (lane == 0 && q1.w) {
+                const int sp = r & 1;
+                uint64_t *bar = &sm.mbar[sp];
+                mbarExpectTx(bar, q1.w);
+                if (!(q2.w & 4u)) {
+                    tmaLoad4d(winL(sp, 0), &maps.luma[0][0] + (q1.x & 15u), 0, (int)(q0.x & 0xFFFFu), (int)(q0.y & 0xFFFFu), (int)q1.y, bar);
+                    tmaLoad4d(winC(sp, 0), &maps.chroma[0][0] + ((q1.x >> 4) & 15u), 0, (int)(q0.x >> 16), (int)(q0.y >> 16), (int)q1.y, bar);
+                    tmaLoad4d(winL(sp, 1), &maps.luma[0][0] + ((q1.x >> 8) & 15u), 0, (int)(q0.z & 0xFFFFu), (int)(q0.w & 0xFFFFu), (int)q1.z, bar);
+                    tmaLoad4d(winC(sp, 1), &maps.chroma[0][0] + ((q1.x >> 12) & 15u), 0, (int)(q0.z >> 16), (int)(q0.w >> 16), (int)q1.z, bar);
+                }
+                if (q2.z) bulkLoad(sm.coef[(q2.w >> 3) & 1u], reinterpret_cast<const void *>((uintptr_t)(((unsigned long long)q2.y << 32) | q2.x)), q2.z, bar);
+            }
+        };
+        if (nRounds) stageRound(0);
+        uint2 pv = make_uint2(0, 0);   // this lane's 8 luma prediction samples
+        uint32_t pc = 0;               // and 4 chroma prediction samples
+#pragma unroll 1
+        for (int r = 0; r < nRounds; r++) {
+            if (r + 1 < nRounds) stageRound(r + 1);
+            const uint4 q2 = reinterpret_cast<const uint4 *>(&boxes[r])[2], q3 = reinterpret_cast<const uint4 *>(&boxes[r])[3];
+            const uint4 q4 = reinterpret_cast<const uint4 *>(&boxes[r])[4];
+            const int pair = r & 1, rd = (int)(q2.w & 1u);
+            const uint32_t w0 = q3.z, mask = q3.w, geomAB = q3.x, fracs = q3.y;
+            const uint32_t type = w0 & 0xFFu;
+            const int mbx = (int)(q4.x & 0xFFFFu), mby = (int)(q4.x >> 16);
+            if (reinterpret_cast<const uint4 *>(&boxes[r])[1].w) {   // (armed: something was asked for)
                 mbarWait(&sm.mbar[pair], (phaseBits >> pair) & 1u);
                 phaseBits ^= 1u << pair;
             }
-            const uint32_t type = w0 & 0xFFu;
-            const int mbx = (int)(pos & 0xFFFFu), mby = (int)(pos >> 16);
             if (rd == 0) {
                 pv = make_uint2(0, 0);
                 pc = 0;
-                if (mask) residualShfl(sm, sm.coef[coefBuf], mask, (w0 >> 8) & 0xFF, (w0 >> 16) & 0xFF, lane, p.errors);
+                if (mask) residualShfl(sm, sm.coef[(q2.w >> 3) & 1u], mask, (w0 >> 8) & 0xFF, (w0 >> 16) & 0xFF, lane, p.errors);
             }
-            if (subTypes == 0) {
+            if (!(q2.w & 4u)) {
                 int pxB, pyA, pyB;
                 if (type == B200_MB_P_16x8) { pxB = 0; pyA = 0; pyB = 8; }
                 else if (type == B200_MB_P_8x16) { pxB = 8; pyA = 0; pyB = 0; }
@@ -1018,22 +1031,22 @@ passAMultiKernel(const ReconParams p, const __grid_constant__ PassAMaps maps) {
                 const bool inBC = type == B200_MB_P_16x8 ? cr >= 4 : cc == 4;
                 const bool actL = type < B200_MB_P_8x8 || (r8 >> 3) == rd, actC = type < B200_MB_P_8x8 || (cr >> 2) == rd;
                 if (actL) {
-                    const uint32_t gm = inBL ? geomAB >> 16 : geomAB & 0xFFFFu, mv = inBL ? mvB : mvA;
-                    const int xf = (int)(mv & 3u), yf = (int)((mv >> 16) & 3u);
+                    const uint32_t gm = inBL ? geomAB >> 16 : geomAB & 0xFFFFu, fr = inBL ? fracs >> 6 : fracs;
+                    const int xf = (int)(fr & 3u), yf = (int)((fr >> 3) & 3u);
                     const int pitch = (int)((gm >> 4) & 3u) * 16;
                     const uint8_t *G0 = winL(pair, inBL ? 1 : 0) + (gm & 15u) + (yf ? 2 * pitch : 0) + (xf ? 2 : 0);
                     pv = lumaQpel8(G0, pitch, c8 - (inBL ? pxB : 0), r8 - (inBL ? pyB : pyA), xf, yf);
                 }
                 if (actC) {
-                    const uint32_t gm = inBC ? geomAB >> 16 : geomAB & 0xFFFFu, mv = inBC ? mvB : mvA;
+                    const uint32_t gm = inBC ? geomAB >> 16 : geomAB & 0xFFFFu, fr = inBC ? fracs >> 6 : fracs;
                     pc = chromaPred4(winC(pair, inBC ? 1 : 0), (int)((gm >> 12) & 3u) * 16, (int)((gm >> 8) & 7u), cp,
-                                     cc - (inBC ? (pxB >> 1) : 0), cr - ((inBC ? pyB : pyA) >> 1), (int)(mv & 7u), (int)((mv >> 16) & 7u));
+                                     cc - (inBC ? (pxB >> 1) : 0), cr - ((inBC ? pyB : pyA) >> 1), (int)(fr & 7u), (int)((fr >> 3) & 7u));
                 }
             } else {
                 // sub-macroblocks with 8x4 / 4x8 / 4x4 partitions: one window per partition, sample by sample
-                const unsigned long long recBits = __shfl_sync(0xffffffffu, (unsigned long long)reinterpret_cast<uintptr_t>(mRec), l);
-                const uint32_t *rw = reinterpret_cast<const uint32_t *>((uintptr_t)recBits);
-                const uint32_t refSlots = __shfl_sync(0xffffffffu, mRef, l), frameBase = __shfl_sync(0xffffffffu, mFrameBase, l);
+                const uint32_t *rw = reinterpret_cast<const uint32_t *>((uintptr_t)(((unsigned long long)q4.w << 32) | q4.z));
+                const uint4 q1 = reinterpret_cast<const uint4 *>(&boxes[r])[1];
+                const uint32_t refSlots = q1.y, frameBase = q1.z, subTypes = fracs;
                 uint8_t *wl = winL(pair, 0), *wc = winC(pair, 0);
 #pragma unroll 1
                 for (int pi = 0; pi < 16; pi++) {
@@ -1078,8 +1091,8 @@ passAMultiKernel(const ReconParams p, const __grid_constant__ PassAMaps maps) {
                 pv = *reinterpret_cast<const uint2 *>(pred + r8 * 16 + c8);
                 pc = *reinterpret_cast<const uint32_t *>(pred + 256 + cp * 64 + cr * 8 + cc);
             }
-            if (last) {
-                uint8_t *frame = framePtr(p.pool, g, curFrame);
+            if (q2.w & 2u) {
+                uint8_t *frame = framePtr(p.pool, g, q4.y);
                 addResidualStore(sm, mask, pv, pc, mbLuma(frame, g, mbx, mby), mbChroma(frame, g, mbx, mby), lane);
             }
             __syncwarp();   // the pair's windows (and the residual) are free for the loads of the turn after next
