@@ -477,18 +477,15 @@ __device__ __noinline__ void residualShfl(PassAWarpSmem &sm, const uint8_t *cbuf
         z[lane] = zero;
         if (lane < 16) z[lane + 32] = zero;
     }
-    int dc = 0;
-    if ((mask & B200_CM_CHROMA_DC) && lane >= 16 && lane < 24) {
-        const int k = lane - 16;
-        dc = chromaDcPick(reinterpret_cast<const int16_t *>(cbuf) + (k >> 2) * 4, qpC, k & 3);
-    }
-    if (lane >= 16 && lane < 24) sm.dcC[lane - 16] = dc;
-    const uint32_t coded = mask & 0xFFFFFFu;
-    const uint32_t act = coded | (__ballot_sync(0xffffffffu, dc != 0) & 0xFF0000u);
-    if ((act >> lane) & 1u) sm.list[__popc(act & ((1u << lane) - 1u))] = (uint8_t)lane;
-    __syncwarp();
-    const int nAct = __popc(act), nDc = (int)((mask >> 25) & 1u);
     const int r = lane & 3, g4 = lane >> 2;
+    // chroma DC: group g4 works on chroma block 16 + g4 in the third round and needs DC value g4 of the 2 x (2x2) transforms
+    // (macroblock_layer.c:1371-1374); every lane of the group computes it
+    int dcMine = 0;
+    if (mask & B200_CM_CHROMA_DC) dcMine = chromaDcPick(reinterpret_cast<const int16_t *>(cbuf) + (g4 >> 2) * 4, qpC, g4 & 3);
+    const uint32_t coded = mask & 0xFFFFFFu;
+    // rounds with something to do: coded blocks, and for the chroma round a DC block (its values reach blocks without levels)
+    const uint32_t active = coded | ((mask & B200_CM_CHROMA_DC) ? 0xFF0000u : 0u);
+    const int nDc = (int)((mask >> 25) & 1u);
     const uint32_t zz = r == 0 ? 0x6510u : r == 1 ? 0xC742u : r == 2 ? 0xDB83u : 0xFEA9u;   // zig-zag positions of raster row r
     const int orow = ((r & 1) << 1) | (r >> 1);   // the row this lane holds after the column transform
     // this lane's two scale factors (columns 0, 2 / 1, 3 of its row), for a luma and for a chroma block
@@ -498,19 +495,21 @@ __device__ __noinline__ void residualShfl(PassAWarpSmem &sm, const uint8_t *cbuf
         sAY = levelScale(mY, r & 1) << dY; sBY = levelScale(mY, 1 + (r & 1)) << dY;
         sAC = levelScale(mC, r & 1) << dC; sBC = levelScale(mC, 1 + (r & 1)) << dC;
     }
+    // three rounds of eight blocks: luma 0..7, luma 8..15, chroma 16..23; group g4 takes block 8 round + g4; a round without an
+    // active block is skipped
 #pragma unroll 1
-    for (int base = 0; base < nAct; base += 8) {
-        const bool valid = base + g4 < nAct;
-        const int b = valid ? sm.list[base + g4] : 0;
-        const bool isCoded = valid && ((coded >> b) & 1u);
-        const int sA = b < 16 ? sAY : sAC, sB = b < 16 ? sBY : sBC;
+    for (int round = 0; round < 3; round++) {
+        if (!((active >> (8 * round)) & 0xFFu)) continue;
+        const int b = 8 * round + g4;
+        const bool isCoded = (coded >> b) & 1u, valid = isCoded || (round == 2 && dcMine != 0);
+        const int sA = round < 2 ? sAY : sAC, sB = round < 2 ? sBY : sBC;
         int d0 = 0, d1 = 0, d2 = 0, d3 = 0;
         if (isCoded) {
             const int16_t *lev = reinterpret_cast<const int16_t *>(cbuf) + (nDc + __popc(coded & ((1u << b) - 1u))) * 16;
             d0 = lev[zz & 15u] * sA; d1 = lev[(zz >> 4) & 15u] * sB; d2 = lev[(zz >> 8) & 15u] * sA; d3 = lev[zz >> 12] * sB;
         }
         if (r == 0) {
-            if (b >= 16) d0 = sm.dcC[b - 16];   // chroma: the DC comes from the 2x2 transform (macroblock_layer.c:1371-1374)
+            if (round == 2) d0 = dcMine;        // chroma: the DC comes from the 2x2 transform
             d0 += 32;                           // the DC term reaches all sixteen outputs with weight 1: rounding for the final >> 6
         }
         // row transform
