@@ -169,7 +169,7 @@ bool Batch::create(int device, uint32_t nStreams, uint32_t widthMbs, uint32_t he
     }
     int occA = 1, occD = 0, occS = 0, occB = 0;
     CK(cudaFuncSetAttribute(passAKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(PassAWarpSmem) * kPassAWarps)));
-    CK(cudaFuncSetAttribute(passAMultiKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(PassAWarpSmem) * kPassAWarps)));
+    CK(cudaFuncSetAttribute(passAMultiKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(MultiWarpSmem) * kPassAWarps)));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occA, passAKernel, kPassAWarps * 32, sizeof(PassAWarpSmem) * kPassAWarps));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occD, deblockKernel, kDeblockWarps * 32, 0));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, strengthKernel, kDeblockWarps * 32, 0));
@@ -436,7 +436,7 @@ bool Batch::launchPicture(const StreamJob *dJobs, const StreamJob *dJobsFilter, 
             const PassAMaps &maps = *reinterpret_cast<const PassAMaps *>(maps_);
             passAKernel<<<std::min<uint32_t>(ctas, (uint32_t)passABlocks_), kPassAWarps * 32, sizeof(PassAWarpSmem) * kPassAWarps, stream_>>>(rp, maps);
             mark(0);
-            passAMultiKernel<<<std::min<uint32_t>(ctas, (uint32_t)passABlocks_), kPassAWarps * 32, sizeof(PassAWarpSmem) * kPassAWarps, stream_>>>(rp, maps);
+            passAMultiKernel<<<std::min<uint32_t>(ctas, (uint32_t)passABlocks_), kPassAWarps * 32, sizeof(MultiWarpSmem) * kPassAWarps, stream_>>>(rp, maps);
             launches_ += 2;
             mark(5);
         }

@@ -26,9 +26,12 @@ struct PassAMaps {
 constexpr int kLumaBufBytes = 1024;     // >= 48 x 21
 constexpr int kChromaBufBytes = 384;    // >= 32 x 9
 constexpr int kCoefBufBytes = 896;      // >= 26 blocks of 32 bytes (I_PCM: 12)
-constexpr int kStageMbs = 15;           // macroblocks of a chunk at most (Batch::create): what the copy staging buffer holds
+#ifndef B200_STAGE_MBS
+#define B200_STAGE_MBS 14
+#endif
+constexpr int kStageMbs = B200_STAGE_MBS;   // macroblocks of a chunk at most (Batch::create): what the copy staging buffer holds
 
-struct __align__(128) PassAWarpSmem {
+struct __align__(128) PassAWarpBase {
     uint8_t luma[2][kLumaBufBytes];       // reference windows: the macroblock being computed / the next one (TMA, mbarrier double buffer)
     uint8_t chroma[2][kChromaBufBytes];
     uint8_t coef[2][kCoefBufBytes];       // the macroblock's levels (cp.async.bulk, same mbarrier)
@@ -36,15 +39,20 @@ struct __align__(128) PassAWarpSmem {
     int16_t resC[2][8][8];
     uint64_t mbar[2];
     uint64_t mbarCopy;                    // the chunk's copies have arrived in `stage`
-    uint8_t list[32];                     // compaction scratch: the macroblock's active 4x4 blocks
-    int32_t dcC[8];                       // chroma DC values of the macroblock being computed
-    uint8_t pad[40];
-    // first instance: the chunk's zero-motion copies on their way from the reference frame to the current one (bulk copies
-    // global -> shared -> global: luma of macroblock l at 256 l, chroma at 256 kStageMbs + 128 l).  Second instance (it has no
-    // copies): prediction of sub-macroblocks with 8x4 / 4x8 / 4x4 partitions in the first 384 bytes.
-    uint8_t stage[kStageMbs * 384];
+    uint8_t pad[104];
 };
-static_assert(sizeof(PassAWarpSmem) % 128 == 0 && offsetof(PassAWarpSmem, stage) % 128 == 0, "per-warp shared memory keeps the TMA destinations 128-byte aligned");
+// first instance: the chunk's zero-motion copies on their way from the reference frame to the current one (bulk copies global ->
+// shared -> global: luma of macroblock l at 256 l, chroma at 256 kStageMbs + 128 l)
+struct __align__(128) PassAWarpSmem : PassAWarpBase {
+    uint8_t stage[(kStageMbs * 384 + 127) / 128 * 128];
+};
+// second instance (it has no copies): prediction of sub-macroblocks with 8x4 / 4x8 / 4x4 partitions in the first 384 bytes, then a
+// second pair of window buffers, then the round boxes
+struct __align__(128) MultiWarpSmem : PassAWarpBase {
+    uint8_t stage[4480];
+};
+static_assert(sizeof(PassAWarpBase) % 128 == 0 && sizeof(PassAWarpSmem) % 128 == 0 && sizeof(MultiWarpSmem) % 128 == 0,
+              "per-warp shared memory keeps the TMA destinations 128-byte aligned");
 
 struct __align__(16) IntraWarpSmem {
     int16_t res[24][16];
@@ -57,6 +65,8 @@ struct __align__(16) IntraWarpSmem {
 // h264bsd_transform.c:58-59; class 0 = both coordinates even, 2 = both odd, 1 = mixed
 __device__ __constant__ uint8_t cLevelScale[6][4] = {{10, 13, 16, 0}, {11, 14, 18, 0}, {13, 16, 20, 0}, {14, 18, 23, 0}, {16, 20, 25, 0}, {18, 23, 29, 0}};
 __device__ __forceinline__ int levelScale(int qpMod, int cls) { return cLevelScale[qpMod][cls]; }
+// the same times 2^(qp / 6), by qp (transform.c:122-127): what a level is multiplied with
+__device__ __constant__ uint16_t cScaleQp[52][4] = {{10, 13, 16, 0}, {11, 14, 18, 0}, {13, 16, 20, 0}, {14, 18, 23, 0}, {16, 20, 25, 0}, {18, 23, 29, 0}, {20, 26, 32, 0}, {22, 28, 36, 0}, {26, 32, 40, 0}, {28, 36, 46, 0}, {32, 40, 50, 0}, {36, 46, 58, 0}, {40, 52, 64, 0}, {44, 56, 72, 0}, {52, 64, 80, 0}, {56, 72, 92, 0}, {64, 80, 100, 0}, {72, 92, 116, 0}, {80, 104, 128, 0}, {88, 112, 144, 0}, {104, 128, 160, 0}, {112, 144, 184, 0}, {128, 160, 200, 0}, {144, 184, 232, 0}, {160, 208, 256, 0}, {176, 224, 288, 0}, {208, 256, 320, 0}, {224, 288, 368, 0}, {256, 320, 400, 0}, {288, 368, 464, 0}, {320, 416, 512, 0}, {352, 448, 576, 0}, {416, 512, 640, 0}, {448, 576, 736, 0}, {512, 640, 800, 0}, {576, 736, 928, 0}, {640, 832, 1024, 0}, {704, 896, 1152, 0}, {832, 1024, 1280, 0}, {896, 1152, 1472, 0}, {1024, 1280, 1600, 0}, {1152, 1472, 1856, 0}, {1280, 1664, 2048, 0}, {1408, 1792, 2304, 0}, {1664, 2048, 2560, 0}, {1792, 2304, 2944, 0}, {2048, 2560, 3200, 0}, {2304, 2944, 3712, 0}, {2560, 3328, 4096, 0}, {2816, 3584, 4608, 0}, {3328, 4096, 5120, 0}, {3584, 4608, 5888, 0}};
 
 // h264bsdProcessBlock (transform.c:97-234): lev in zig-zag order -> out[16] raster residual
 __device__ __forceinline__ bool idctBlock(const int16_t *lev, int qp, bool dcPreset, int dcValue, int *out) {
@@ -470,7 +480,7 @@ __device__ __forceinline__ void laneResidual(const int16_t (*res)[16], int lane,
 // h264bsdProcessBlock (transform.c:97-234) with the row transform inside a lane (lane r of a group owns row r of the block)
 // and the column transform across the group's four lanes by two shuffle exchanges; h264bsdProcessChromaDc (:359-401) by
 // lanes 16..23 first.  `cbuf` = the macroblock's levels in shared memory (b200_mb_rec layout: [chroma DC][coded blocks]).
-__device__ __noinline__ void residualShfl(PassAWarpSmem &sm, const uint8_t *cbuf, uint32_t mask, int qpY, int qpC, int lane, uint32_t *errors) {
+__device__ __noinline__ void residualShfl(PassAWarpBase &sm, const uint8_t *cbuf, uint32_t mask, int qpY, int qpC, int lane, uint32_t *errors) {
     {   // every block that is not visited below has a zero residual
         uint4 *z = reinterpret_cast<uint4 *>(&sm.resY[0][0]);   // resY and resC are contiguous: 48 x 16 bytes
         const uint4 zero = make_uint4(0, 0, 0, 0);
@@ -489,12 +499,7 @@ __device__ __noinline__ void residualShfl(PassAWarpSmem &sm, const uint8_t *cbuf
     const uint32_t zz = r == 0 ? 0x6510u : r == 1 ? 0xC742u : r == 2 ? 0xDB83u : 0xFEA9u;   // zig-zag positions of raster row r
     const int orow = ((r & 1) << 1) | (r >> 1);   // the row this lane holds after the column transform
     // this lane's two scale factors (columns 0, 2 / 1, 3 of its row), for a luma and for a chroma block
-    int sAY, sBY, sAC, sBC;
-    {
-        const int dY = qpY / 6, mY = qpY - 6 * dY, dC = qpC / 6, mC = qpC - 6 * dC;
-        sAY = levelScale(mY, r & 1) << dY; sBY = levelScale(mY, 1 + (r & 1)) << dY;
-        sAC = levelScale(mC, r & 1) << dC; sBC = levelScale(mC, 1 + (r & 1)) << dC;
-    }
+    const int sAY = cScaleQp[qpY][r & 1], sBY = cScaleQp[qpY][1 + (r & 1)], sAC = cScaleQp[qpC][r & 1], sBC = cScaleQp[qpC][1 + (r & 1)];
     // three rounds of eight blocks: luma 0..7, luma 8..15, chroma 16..23; group g4 takes block 8 round + g4; a round without an
     // active block is skipped
 #pragma unroll 1
@@ -629,7 +634,7 @@ __device__ __noinline__ uint32_t issueWindowFn(uint8_t *dstL, uint8_t *dstC, uin
 // add residual + clip + store of a macroblock (h264bsdWriteOutputBlocks, image.c:172-344): lane = 8 luma samples (bytes 8 lane..
 // of the macroblock's 256) + 4 chroma samples (bytes 4 lane.. of its 128); a pel leaves its word and meets its residual in one
 // dot product
-__device__ __forceinline__ void addResidualStore(const PassAWarpSmem &sm, uint32_t mask, uint2 pv, uint32_t pc, uint8_t *mbY, uint8_t *mbC, int lane) {
+__device__ __forceinline__ void addResidualStore(const PassAWarpBase &sm, uint32_t mask, uint2 pv, uint32_t pc, uint8_t *mbY, uint8_t *mbC, int lane) {
     if (mask) {
         const uint4 ra = reinterpret_cast<const uint4 *>(&sm.resY[0][0])[lane];
         const uint2 rc = *reinterpret_cast<const uint2 *>(&sm.resC[(lane >> 1) & 1][lane >> 2][(lane & 1) * 4]);
@@ -882,14 +887,14 @@ struct __align__(16) RoundBox {
     uint32_t geomAB, fracs, w0, mask;       // WindowGeom.geom of A | B << 16; mvA.x & 7 | mvA.y & 7 << 3 | mvB.x & 7 << 6 | mvB.y & 7 << 9; record head
     uint32_t pos, curFrame, recLo, recHi;   // mbx | mby << 16; frame to write; the record (small partitions read their vectors there)
 };
-static_assert(sizeof(RoundBox) == 80 && 384 + 2 * kLumaBufBytes + 2 * kChromaBufBytes + 2 * kMultiBatch * sizeof(RoundBox) <= sizeof(PassAWarpSmem::stage),
+static_assert(sizeof(RoundBox) == 80 && 384 + 2 * kLumaBufBytes + 2 * kChromaBufBytes + 2 * kMultiBatch * sizeof(RoundBox) <= sizeof(MultiWarpSmem::stage),
               "the second window pair, the prediction of small partitions and the round boxes share `stage`");
-__global__ void __launch_bounds__(kPassAWarps * 32, B200_PASSA_MINBLOCKS)
+__global__ void __launch_bounds__(kPassAWarps * 32, 5)
 passAMultiKernel(const ReconParams p, const __grid_constant__ PassAMaps maps) {
     extern __shared__ __align__(128) uint8_t interSmemRaw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const PoolGeom &g = p.g;
-    PassAWarpSmem &sm = reinterpret_cast<PassAWarpSmem *>(interSmemRaw)[warp];
+    MultiWarpSmem &sm = reinterpret_cast<MultiWarpSmem *>(interSmemRaw)[warp];
     if (lane == 0) {
         mbarInit(&sm.mbar[0], 1);
         mbarInit(&sm.mbar[1], 1);

@@ -54,7 +54,7 @@ def prepare_engine_source():
     src = "\n".join(lines)
     assert src.count('#include "recon_kernel.cuh"') == 1
     src = src.replace('#include "recon_kernel.cuh"', '#include "recon_kernel_emu.cuh"')
-    src += "\nnamespace b200 {\nalignas(128) uint8_t interSmemRaw[sizeof(PassAWarpSmem) * kPassAWarps];\n}\n"
+    src += "\nnamespace b200 {\nalignas(128) uint8_t interSmemRaw[(sizeof(PassAWarpSmem) > sizeof(MultiWarpSmem) ? sizeof(PassAWarpSmem) : sizeof(MultiWarpSmem)) * kPassAWarps];\n}\n"
     with open(os.path.join(BUILD, "engine_hostemu.cpp"), "w") as f:
         f.write(src)
 
