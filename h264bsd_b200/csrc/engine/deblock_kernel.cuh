@@ -235,9 +235,12 @@ __global__ void __launch_bounds__(kDeblockWarps * 32) strengthKernel(const Deblo
 // (deblocking.c:1569-1623) because edges of one direction only interact along a line -- and afterwards chroma line i & 7 of
 // plane i >> 3 (FilterChroma :1633-1745; chroma edges are luma edges 0 and 2).  A step is skipped when neither macroblock has a
 // strength for it.
+#ifndef B200_DEBLOCK_MINBLOCKS
+#define B200_DEBLOCK_MINBLOCKS 3
+#endif
 __device__ __forceinline__ int bsNibble(uint32_t word, int idx) { return (int)((word >> (4 * idx)) & 15u); }
 
-__global__ void __launch_bounds__(kDeblockWarps * 32, 4) deblockKernel(const DeblockParams p) {
+__global__ void __launch_bounds__(kDeblockWarps * 32, B200_DEBLOCK_MINBLOCKS) deblockKernel(const DeblockParams p) {
     __shared__ DeblockWarpSmem smemAll[kDeblockWarps][2];
     __shared__ DeblockTables tb;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

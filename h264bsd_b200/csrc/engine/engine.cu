@@ -178,15 +178,6 @@ bool Batch::create(int device, uint32_t nStreams, uint32_t widthMbs, uint32_t he
     strengthBlocks_ = std::max(1, occS) * numSms_;
     passABlocks_ = std::max(1, occA) * numSms_;
     deblockBlocks_ = std::max(1, occD) * numSms_;
-    // B200_GRID_DIV=G (experiments, tools/group_bench.py): every persistent grid capped at 1/G of the CTAs that fit the machine, for G
-    // batches that run side by side on their own streams
-    if (const char *e = std::getenv("B200_GRID_DIV")) {
-        const int d = std::max(1, std::min(16, std::atoi(e)));
-        strengthBlocks_ = std::max(numSms_ / 2, strengthBlocks_ / d);
-        passABlocks_ = std::max(numSms_ / 2, passABlocks_ / d);
-        deblockBlocks_ = std::max(numSms_ / 2, deblockBlocks_ / d);
-        intraBlocks_ = std::max(numSms_ / 2, intraBlocks_ / d);
-    }
     // pass A: a warp task is a column piece of at most kStageMbs macroblocks (what a warp's copy staging buffer holds); pieces of a
     // column are made equally long
     chunksPerCol_ = (heightMbs + kStageMbs - 1) / kStageMbs;

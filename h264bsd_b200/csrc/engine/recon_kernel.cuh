@@ -10,6 +10,9 @@
 namespace b200 {
 
 constexpr int kReconWarps = 8;    // warps per CTA of the intra pass
+#ifndef B200_INTRA_MINBLOCKS
+#define B200_INTRA_MINBLOCKS 5
+#endif
 #ifndef B200_PASSA_WARPS
 #define B200_PASSA_WARPS 4
 #endif
@@ -1115,7 +1118,7 @@ passAMultiKernel(const ReconParams p, const __grid_constant__ PassAMaps maps) {
 // every stream before row y + 1 of any), so the row above is normally through long before and a warp only ever waits for rows
 // with earlier tickets.
 // =====================================================================================================
-__global__ void __launch_bounds__(kReconWarps * 32, 5) reconIntraKernel(const ReconParams p) {
+__global__ void __launch_bounds__(kReconWarps * 32, B200_INTRA_MINBLOCKS) reconIntraKernel(const ReconParams p) {
     __shared__ IntraWarpSmem smemAll[kReconWarps];
     // Intra4x4 tables, made once per CTA.  sI4Off[c][mode * 16 + sample]: gIntra4x4Table with the edge indices turned into byte
     // offsets from the block's corner sample in the tile (left column (4 - i) * 24, corner 0, above row 1..8); c = 0 is for
