@@ -162,7 +162,7 @@ __device__ __forceinline__ bool strengthGeneral(const DeblockParams &p, const Po
     return any && e == 0 && write;
 }
 
-__global__ void __launch_bounds__(kDeblockWarps * 32) strengthKernel(const DeblockParams p) {
+__global__ void __launch_bounds__(kDeblockWarps * 32, 1) strengthKernel(const DeblockParams p) {
     __shared__ unsigned sWork;
     if (threadIdx.x == 0) sWork = 0;
     __syncthreads();

@@ -146,7 +146,7 @@ bool Batch::create(int device, uint32_t nStreams, uint32_t widthMbs, uint32_t he
     // (running totals)
     CK(cudaMalloc(&dCounters_, sizeof(uint32_t) * 16));
     CK(cudaMemsetAsync(dCounters_, 0, sizeof(uint32_t) * 16, stream_));
-    if ((unsigned long long)nStreams * g.nMbs > 0xFFFFFFF0ull) return false;   // (list entries are stream * nMbs + address)
+    if (nStreams > 65535u) return false;   // (list entries are stream << 16 | address)
     CK(cudaMalloc(&dMultiList_, sizeof(uint32_t) * (size_t)nStreams * g.nMbs));
     CK(cudaMalloc(&dSlots_, sizeof(uint32_t) * nStreams));
     serial_ = 0;

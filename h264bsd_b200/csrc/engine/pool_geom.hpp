@@ -55,7 +55,7 @@ struct ReconParams {
     uint32_t *ticket;          // CTA ticket counter of pass B (zeroed before launch)
     uint32_t *ticketA;         // ticket counters of the two pass-A instances (zeroed before launch)
     uint32_t *multiCount;      // pass A: entries in multiList (zeroed before launch)
-    uint32_t *multiList;       // pass A: the picture's macroblocks with several partitions, stream * nMbs + address (nStreams * nMbs entries)
+    uint32_t *multiList;       // pass A: the picture's macroblocks with several partitions, stream << 16 | address (nStreams * nMbs entries)
     uint32_t *errors;          // [0] IDCT range errors (h264bsd_transform.c:183-188)
     uint32_t serial;           // value that marks "done in this launch"
     uint32_t chunkRows;        // pass A: macroblocks of one column per warp task (<= 32)

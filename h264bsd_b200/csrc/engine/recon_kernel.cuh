@@ -670,7 +670,7 @@ __device__ __forceinline__ void mbarWaitSleeping(uint64_t *bar, uint32_t parity)
 
 // First instance: the copies, the macroblocks with one partition (P_Skip / P_L0_16x16) and I_PCM -- 94 % of a typical P picture's
 // pass-A macroblocks, through the short code path.  The macroblocks with several partitions (16x8, 8x16, 8x8 and below) are put
-// on a list (stream * nMbs + macroblock address, any order) for the second instance, passAMultiKernel.
+// on a list (stream << 16 | macroblock address, any order) for the second instance, passAMultiKernel.
 __global__ void __launch_bounds__(kPassAWarps * 32, B200_PASSA_MINBLOCKS)
 passAKernel(const ReconParams p, const __grid_constant__ PassAMaps maps) {
     extern __shared__ __align__(128) uint8_t interSmemRaw[];   // kPassAWarps x PassAWarpSmem (more than the 48 KB static limit)
@@ -749,7 +749,7 @@ passAKernel(const ReconParams p, const __grid_constant__ PassAMaps maps) {
             uint32_t at = 0;
             if (lane == 0) at = atomicAdd(p.multiCount, (uint32_t)__popc(multiMask));
             at = __shfl_sync(0xffffffffu, at, 0);
-            if (isMulti) p.multiList[at + (uint32_t)__popc(multiMask & ((1u << lane) - 1u))] = s * (uint32_t)g.nMbs + (uint32_t)((row0 + lane) * g.widthMbs + mbx);
+            if (isMulti) p.multiList[at + (uint32_t)__popc(multiMask & ((1u << lane) - 1u))] = (s << 16) | (uint32_t)((row0 + lane) * g.widthMbs + mbx);
         }
 
         // ---- copies: every run of vertically adjacent copies with the same reference frame is 256 n contiguous bytes of luma and
@@ -888,7 +888,8 @@ struct __align__(16) RoundBox {
     uint32_t maps, refA, refB, bytes;       // luma map A | chroma map A << 4 | luma B << 8 | chroma B << 12; reference frames; bytes to expect
     uint32_t coefLo, coefHi, coefBytes, flags;   // the macroblock's levels (first round); flags: round | last << 1 | small partitions << 2 | level buffer << 3
     uint32_t geomAB, fracs, w0, mask;       // WindowGeom.geom of A | B << 16; mvA.x & 7 | mvA.y & 7 << 3 | mvB.x & 7 << 6 | mvB.y & 7 << 9; record head
-    uint32_t pos, curFrame, recLo, recHi;   // mbx | mby << 16; frame to write; the record (small partitions read their vectors there)
+    uint32_t pos, dstLo, dstHi, dstC;       // mbx | mby << 16; the macroblock's luma in the current frame, its chroma relative to that
+                                            // (small partitions: gxA, gyA = the record, where they read their vectors)
 };
 static_assert(sizeof(RoundBox) == 80 && 384 + 2 * kLumaBufBytes + 2 * kChromaBufBytes + 2 * kMultiBatch * sizeof(RoundBox) <= sizeof(MultiWarpSmem::stage),
               "the second window pair, the prediction of small partitions and the round boxes share `stage`");
@@ -921,7 +922,7 @@ passAMultiKernel(const ReconParams p, const __grid_constant__ PassAMaps maps) {
         const uint32_t e = b * kMultiBatch + (uint32_t)lane;
         if (b >= nBatches || lane >= kMultiBatch || e >= count) return;
         fEntry = __ldcg(p.multiList + e);
-        const uint32_t s = fEntry / (uint32_t)g.nMbs, mb = fEntry - s * (uint32_t)g.nMbs;
+        const uint32_t s = fEntry >> 16, mb = fEntry & 0xFFFFu;
         const uint32_t *rw = reinterpret_cast<const uint32_t *>(p.jobs[s].recs + mb);
         const uint4 hw = __ldg(reinterpret_cast<const uint4 *>(rw));
         fRef = __ldg(rw + 4);
@@ -949,7 +950,7 @@ passAMultiKernel(const ReconParams p, const __grid_constant__ PassAMaps maps) {
         const int nRounds = __popc(mineMask) + __popc(twoMask);
         if (mine) {
             const int seq = __popc(mineMask & below), firstRound = seq + __popc(twoMask & below);
-            const uint32_t s = mEntry / (uint32_t)g.nMbs, mb = mEntry - s * (uint32_t)g.nMbs;
+            const uint32_t s = mEntry >> 16, mb = mEntry & 0xFFFFu;
             const StreamJob job = p.jobs[s];
             const int mby = mbRowOf(mb, g), mbx = (int)mb - mby * g.widthMbs;
             const uint32_t frameBase = s * (uint32_t)g.numSlots;
@@ -963,8 +964,13 @@ passAMultiKernel(const ReconParams p, const __grid_constant__ PassAMaps maps) {
                 bx.coefBytes = rd == 0 ? coefBytes : 0u;
                 bx.flags = (uint32_t)rd | ((!two || rd == 1) ? 2u : 0u) | (small ? 4u : 0u) | ((uint32_t)(seq & 1) << 3);
                 bx.w0 = mW0; bx.mask = mMask;
-                bx.pos = (uint32_t)mbx | ((uint32_t)mby << 16); bx.curFrame = frameBase + job.curSlot;
-                bx.recLo = (uint32_t)recBits; bx.recHi = (uint32_t)(recBits >> 32);
+                bx.pos = (uint32_t)mbx | ((uint32_t)mby << 16);
+                {
+                    uint8_t *frame = framePtr(p.pool, g, frameBase + job.curSlot);
+                    uint8_t *dy = mbLuma(frame, g, mbx, mby);
+                    bx.dstLo = (uint32_t)reinterpret_cast<uintptr_t>(dy); bx.dstHi = (uint32_t)((unsigned long long)reinterpret_cast<uintptr_t>(dy) >> 32);
+                    bx.dstC = (uint32_t)(mbChroma(frame, g, mbx, mby) - dy);
+                }
                 if (!small) {
                     int qA, qB, pxB, pyA, pyB, pw, ph;
                     if (type == B200_MB_P_16x8) { qA = 0; qB = 2; pxB = 0; pyA = 0; pyB = 8; pw = 16; ph = 8; }
@@ -981,7 +987,7 @@ passAMultiKernel(const ReconParams p, const __grid_constant__ PassAMaps maps) {
                     bx.geomAB = wa.geom | (wb.geom << 16);
                     bx.fracs = (mvA & 7u) | (((mvA >> 16) & 7u) << 3) | ((mvB & 7u) << 6) | (((mvB >> 16) & 7u) << 9);
                 } else {
-                    bx.gxA = bx.gyA = bx.gxB = bx.gyB = bx.maps = 0;
+                    bx.gxA = (uint32_t)recBits; bx.gyA = (uint32_t)(recBits >> 32); bx.gxB = bx.gyB = bx.maps = 0;
                     bx.refA = mRef; bx.refB = frameBase;   // (the partitions' reference slots and the stream's first frame)
                     bx.bytes = bx.coefBytes;
                     bx.geomAB = 0; bx.fracs = subTypes;
@@ -1051,7 +1057,8 @@ passAMultiKernel(const ReconParams p, const __grid_constant__ PassAMaps maps) {
                 }
             } else {
                 // sub-macroblocks with 8x4 / 4x8 / 4x4 partitions: one window per partition, sample by sample
-                const uint32_t *rw = reinterpret_cast<const uint32_t *>((uintptr_t)(((unsigned long long)q4.w << 32) | q4.z));
+                const uint4 q0 = reinterpret_cast<const uint4 *>(&boxes[r])[0];
+                const uint32_t *rw = reinterpret_cast<const uint32_t *>((uintptr_t)(((unsigned long long)q0.y << 32) | q0.x));
                 const uint4 q1 = reinterpret_cast<const uint4 *>(&boxes[r])[1];
                 const uint32_t refSlots = q1.y, frameBase = q1.z, subTypes = fracs;
                 uint8_t *wl = winL(pair, 0), *wc = winC(pair, 0);
@@ -1099,8 +1106,8 @@ passAMultiKernel(const ReconParams p, const __grid_constant__ PassAMaps maps) {
                 pc = *reinterpret_cast<const uint32_t *>(pred + 256 + cp * 64 + cr * 8 + cc);
             }
             if (q2.w & 2u) {
-                uint8_t *frame = framePtr(p.pool, g, q4.y);
-                addResidualStore(sm, mask, pv, pc, mbLuma(frame, g, mbx, mby), mbChroma(frame, g, mbx, mby), lane);
+                uint8_t *dy = reinterpret_cast<uint8_t *>((uintptr_t)(((unsigned long long)q4.z << 32) | q4.y));
+                addResidualStore(sm, mask, pv, pc, dy, dy + q4.w, lane);
             }
             __syncwarp();   // the pair's windows (and the residual) are free for the loads of the turn after next
         }
