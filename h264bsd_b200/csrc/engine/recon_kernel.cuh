@@ -757,6 +757,7 @@ passAKernel(const ReconParams p, const __grid_constant__ PassAMaps maps) {
         // bulk copies -- no registers, no issue slots, and the inter macroblocks below are computed while they fly
         int runLen = 0;
         bulkWaitRead<0>();   // the staging buffer is free again once this lane's stores of the previous chunk have read it ...
+        fenceProxyAsync();   // (... and what the previous chunk's computed macroblocks kept in their idle slots is out of the way)
         __syncwarp();        // ... and every other lane's
         if (copyMask) {
             // where the reference frame of this lane's macroblock lies relative to the current frame, in 256-byte units (a frame
@@ -793,28 +794,36 @@ passAKernel(const ReconParams p, const __grid_constant__ PassAMaps maps) {
                  ((uint32_t)(mvx & 7) << 14) | ((uint32_t)(mvy & 7) << 17);
         }
 
+        // A macroblock that is computed leaves what its turn will need in ITS staging slot (copies never touch it): the lanes
+        // that compute fetch it with one broadcast load, lane 0 a second one with what the loads need
+        if (isInter) {
+            uint4 *box = reinterpret_cast<uint4 *>(sm.stage + lane * 256);
+            box[0] = make_uint4(mW0, mMask, gC, 0u);
+            box[1] = make_uint4(gX, gY, gM | ((mRef & 0xFFu) << 24), mCoef);
+        }
+        __syncwarp();
+
         // ---- what is staged for the macroblock whose turn comes next ----------------------------------------------------
         uint32_t nW0 = 0, nMask = 0, nGeom = 0;
         int nL = 0;
-        // stage macroblock l of the chunk into buffer `buf`: its levels and its windows.  Everything the loads need is handed to
-        // lane 0, which issues them from uniform registers (issued by the record's own lane, a lane the compiler cannot name,
-        // every load becomes a loop that looks for the lane)
+        // stage macroblock l of the chunk into buffer `buf`: its levels and its windows, issued by lane 0 from uniform registers
+        // (issued by the record's own lane, a lane the compiler cannot name, every load becomes a loop that looks for the lane)
         auto prepare = [&](int l, int buf) {
             nL = l;
-            nW0 = __shfl_sync(0xffffffffu, mW0, l); nMask = __shfl_sync(0xffffffffu, mMask, l);
-            nGeom = __shfl_sync(0xffffffffu, gC, l);
-            const uint32_t gx = __shfl_sync(0xffffffffu, gX, l), gy = __shfl_sync(0xffffffffu, gY, l), gm = __shfl_sync(0xffffffffu, gM, l);
-            const uint32_t coefIndex = __shfl_sync(0xffffffffu, mCoef, l), ref = __shfl_sync(0xffffffffu, mRef, l);
+            const uint4 *box = reinterpret_cast<const uint4 *>(sm.stage + l * 256);
+            const uint4 a = box[0];
+            nW0 = a.x; nMask = a.y; nGeom = a.z;
             if (lane == 0) {
+                const uint4 q = box[1];
                 const uint32_t type = nW0 & 0xFFu;
                 const uint32_t coefBytes = type == B200_MB_I_PCM ? 384u : 32u * (uint32_t)__popc(nMask & 0x3FFFFFFu);
-                mbarExpectTx(&sm.mbar[buf], (gm >> 8) + coefBytes);
+                mbarExpectTx(&sm.mbar[buf], ((q.z >> 8) & 0xFFFFu) + coefBytes);
                 if (type != B200_MB_I_PCM) {
-                    const int refFrame = (int)(frameBase + (ref & 0xFFu));
-                    tmaLoad4d(sm.luma[buf], &maps.luma[0][0] + (gm & 7u), 0, (int)(gx & 0xFFFFu), (int)(gy & 0xFFFFu), refFrame, &sm.mbar[buf]);
-                    tmaLoad4d(sm.chroma[buf], &maps.chroma[0][0] + ((gm >> 3) & 3u), 0, (int)(gx >> 16), (int)(gy >> 16), refFrame, &sm.mbar[buf]);
+                    const int refFrame = (int)(frameBase + (q.z >> 24));
+                    tmaLoad4d(sm.luma[buf], &maps.luma[0][0] + (q.z & 7u), 0, (int)(q.x & 0xFFFFu), (int)(q.y & 0xFFFFu), refFrame, &sm.mbar[buf]);
+                    tmaLoad4d(sm.chroma[buf], &maps.chroma[0][0] + ((q.z >> 3) & 3u), 0, (int)(q.x >> 16), (int)(q.y >> 16), refFrame, &sm.mbar[buf]);
                 }
-                if (coefBytes) bulkLoad(sm.coef[buf], job.coefs + (size_t)coefIndex * 16, coefBytes, &sm.mbar[buf]);
+                if (coefBytes) bulkLoad(sm.coef[buf], job.coefs + (size_t)q.w * 16, coefBytes, &sm.mbar[buf]);
             }
         };
         if (interMask) prepare(__ffs(interMask) - 1, 0);
