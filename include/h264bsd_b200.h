@@ -122,8 +122,9 @@ int h264bsdB200BatchDebugStage(b200_batch *batch, uint32_t picIndex, int recon, 
 uint32_t h264bsdB200BatchIdctErrors(b200_batch *batch);
 /* macroblocks that had at least one non-zero boundary strength (the ones the in-loop filter touches) since creation */
 uint64_t h264bsdB200BatchDeblockWorkMbs(b200_batch *batch);
-/* per-stage device time: CUDA events around every launch on the engine's stream.  ms6/launches6 = {reconstruct pass A
- * (inter), in-loop filter, border, reconstruct pass B (intra), boundary strengths, copy pass}; reading resets the accumulators */
+/* per-stage device time: CUDA events around every launch on the engine's stream.  ms6/launches6 = {reconstruct pass A, first
+ * instance (copies, one partition, I_PCM), in-loop filter, border, reconstruct pass B (intra), boundary strengths, pass A second
+ * instance (several partitions)}; reading resets the accumulators */
 void h264bsdB200BatchKernelTiming(b200_batch *batch, int enable);
 int h264bsdB200BatchKernelTimes(b200_batch *batch, float *ms6, uint32_t *launches6);
 /* waits inside the kernels that gave up (0: macroblock-flag waits, 1: TMA waits); non-zero = engine bug */
